@@ -1,0 +1,360 @@
+"""beluga_b200 -- B200-native backend for the MCL particle-filter update of Ekumen-OS/beluga.
+
+The product is `libbeluga_b200.so` (hand-written sm_100a CUDA kernels behind the C ABI of
+`include/beluga_b200.h`) plus the header-only C++ adaptors in `include/beluga_b200/` that give it
+beluga's MotionModel / SensorModel / Amcl shapes.  This package is the thin Python view of the same
+C ABI used by the tests and by bench.py; names follow the reference:
+
+    reference (C++)                                         here
+    ------------------------------------------------------  --------------------------------------
+    beluga::Amcl<...> (algorithm/amcl_core.hpp:81)          Amcl
+    Amcl::initialize(pose, covariance)  (:145)              Amcl.initialize(mean_xytheta, cov)
+    Amcl::update(control, measurement)  (:165)              Amcl.update(control_pose, points)
+    Amcl::update_map(map)               (:150)              Amcl.update_map(...)
+    Amcl::particles()                   (:128)              Amcl.particles()
+    DifferentialDriveModelParam                             DifferentialDriveModelParam
+    LikelihoodFieldModelParam / BeamModelParam              LikelihoodFieldModelParam / BeamModelParam
+    AmclParams                                              AmclParams
+
+No computation happens in Python and there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi
+from ._capi import (RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC, SENSOR_BEAM, SENSOR_LIKELIHOOD_FIELD,
+                    SENSOR_LIKELIHOOD_FIELD_PROB)
+
+__all__ = [
+    "Amcl", "AmclParams", "BeamModelParam", "DifferentialDriveModelParam", "Filter", "LikelihoodFieldModelParam",
+    "OccupancyGrid", "BelugaB200Error", "device_count", "se2",
+    "RESAMPLE_MULTINOMIAL", "RESAMPLE_SYSTEMATIC", "SENSOR_BEAM", "SENSOR_LIKELIHOOD_FIELD", "SENSOR_LIKELIHOOD_FIELD_PROB",
+]
+
+
+class BelugaB200Error(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"[bb200 status {status}] {message}")
+        self.status = status
+
+
+def device_count() -> int:
+    return _capi.load().bb200_device_count()
+
+
+def se2(x: float, y: float, theta: float) -> np.ndarray:
+    """Sophus::SE2d{theta, (x, y)} in data() order (cos, sin, x, y), normalised through hypot."""
+    c, s = np.cos(theta), np.sin(theta)
+    n = np.hypot(c, s)
+    return np.array([c / n, s / n, x, y], dtype=np.float64)
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+@dataclass
+class DifferentialDriveModelParam:
+    """beluga::DifferentialDriveModelParam (motion/differential_drive_model.hpp:40-68)."""
+    rotation_noise_from_rotation: float = 0.0
+    rotation_noise_from_translation: float = 0.0
+    translation_noise_from_translation: float = 0.0
+    translation_noise_from_rotation: float = 0.0
+    distance_threshold: float = 0.01
+
+    def c(self) -> _capi.DiffDriveParam:
+        return _capi.DiffDriveParam(self.rotation_noise_from_rotation, self.rotation_noise_from_translation,
+                                    self.translation_noise_from_translation, self.translation_noise_from_rotation,
+                                    self.distance_threshold)
+
+
+@dataclass
+class LikelihoodFieldModelParam:
+    """beluga::LikelihoodFieldModelParam (sensor/likelihood_field_model_base.hpp:42-64)."""
+    max_obstacle_distance: float = 100.0
+    max_laser_distance: float = 2.0
+    z_hit: float = 0.5
+    z_random: float = 0.5
+    sigma_hit: float = 0.2
+    model_unknown_space: bool = False
+    only_obstacle_boundaries: bool = False
+
+    def c(self) -> _capi.LikelihoodFieldParam:
+        return _capi.LikelihoodFieldParam(self.max_obstacle_distance, self.max_laser_distance, self.z_hit, self.z_random,
+                                          self.sigma_hit, int(self.model_unknown_space), int(self.only_obstacle_boundaries))
+
+
+@dataclass
+class BeamModelParam:
+    """beluga::BeamModelParam (sensor/beam_model.hpp:43-58)."""
+    z_hit: float = 0.5
+    z_short: float = 0.5
+    z_max: float = 0.05
+    z_rand: float = 0.05
+    sigma_hit: float = 0.2
+    lambda_short: float = 0.1
+    beam_max_range: float = 60.0
+
+    def c(self) -> _capi.BeamParam:
+        return _capi.BeamParam(self.z_hit, self.z_short, self.z_max, self.z_rand, self.sigma_hit, self.lambda_short, self.beam_max_range)
+
+
+@dataclass
+class AmclParams:
+    """beluga::AmclParams (algorithm/amcl_core.hpp:34-55) + spatial hash resolutions + backend knobs."""
+    update_min_d: float = 0.25
+    update_min_a: float = 0.2
+    resample_interval: int = 1
+    selective_resampling: bool = False
+    min_particles: int = 500
+    max_particles: int = 2000
+    alpha_slow: float = 0.001
+    alpha_fast: float = 0.1
+    kld_epsilon: float = 0.05
+    kld_z: float = 3.0
+    spatial_resolution: tuple = (0.5, 0.5, float(np.deg2rad(10.0)))  # beluga_ros/amcl.hpp:91-97
+    resample_scheme: int = RESAMPLE_MULTINOMIAL
+    seed: int = 0
+    device: int = 0
+    record_ancestors: bool = False
+
+    def c(self) -> _capi.AmclParam:
+        return _capi.AmclParam(self.update_min_d, self.update_min_a, self.resample_interval, int(self.selective_resampling),
+                               self.min_particles, self.max_particles, self.alpha_slow, self.alpha_fast, self.kld_epsilon,
+                               self.kld_z, (C.c_double * 3)(*self.spatial_resolution), self.resample_scheme, self.seed,
+                               self.device, int(self.record_ancestors))
+
+
+@dataclass
+class OccupancyGrid:
+    """Occupancy grid with ROS trinary values: int8 [height, width], 0 free / 100 occupied / -1 unknown."""
+    cells: np.ndarray
+    resolution: float = 1.0
+    origin: np.ndarray = field(default_factory=lambda: np.array([1.0, 0.0, 0.0, 0.0]))
+
+    def __post_init__(self):
+        c = np.asarray(self.cells)
+        if c.dtype == np.bool_:
+            c = np.where(c, 100, 0)
+        self.cells = np.ascontiguousarray(c, dtype=np.int8)
+        self.origin = _f64(self.origin)
+
+    def c(self) -> _capi.OccupancyGrid:
+        return _capi.OccupancyGrid(self.cells.ctypes.data_as(C.POINTER(C.c_int8)), self.cells.shape[1], self.cells.shape[0],
+                                   float(self.resolution), (C.c_double * 4)(*self.origin))
+
+
+class Filter:
+    """bb200_filter: the device-resident particle set and the per-step kernels."""
+
+    def __init__(self, capacity: int | None = None, seed: int = 0, device: int = 0, first_index: int = 0, global_count: int = 0,
+                 record_ancestors: bool = False, _handle=None, _owner=None):
+        self._lib = _capi.load()
+        self._owner = _owner
+        if _handle is not None:
+            self._h = C.c_void_p(_handle)
+            return
+        cfg = _capi.FilterConfig(device, capacity, seed, first_index, global_count, int(record_ancestors))
+        h = C.c_void_p()
+        st = self._lib.bb200_filter_create(C.byref(cfg), C.byref(h))
+        if st != _capi.OK:
+            raise BelugaB200Error(st, self._lib.bb200_create_error().decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and self._owner is None:
+            self._lib.bb200_filter_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, st: int):
+        if st != _capi.OK:
+            raise BelugaB200Error(st, self._lib.bb200_last_error(self._h).decode())
+
+    # maps
+    def set_likelihood_field_map(self, params: LikelihoodFieldModelParam, grid: OccupancyGrid, prob: bool = False):
+        p, g = params.c(), grid.c()
+        self._grid_shape = grid.cells.shape
+        self._check(self._lib.bb200_filter_set_likelihood_field_map(self._h, C.byref(p), C.byref(g), int(prob)))
+
+    def set_beam_map(self, params: BeamModelParam, grid: OccupancyGrid):
+        p, g = params.c(), grid.c()
+        self._grid_shape = grid.cells.shape
+        self._check(self._lib.bb200_filter_set_beam_map(self._h, C.byref(p), C.byref(g)))
+
+    def likelihood_field(self) -> np.ndarray:
+        out = np.zeros(self._grid_shape, dtype=np.float32)
+        self._check(self._lib.bb200_filter_get_likelihood_field(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), out.size))
+        return out
+
+    # particles
+    def set_particles(self, states, weights=None):
+        st = _f64(states).reshape(-1, 4)
+        w = None if weights is None else _f64(weights)
+        self._check(self._lib.bb200_filter_set_particles(self._h, _dptr(st), None if w is None else _dptr(w), len(st)))
+
+    def size(self) -> int:
+        n = C.c_uint64()
+        self._check(self._lib.bb200_filter_size(self._h, C.byref(n)))
+        return n.value
+
+    def particles(self):
+        n = self.size()
+        st, w = np.zeros((n, 4)), np.zeros(n)
+        self._check(self._lib.bb200_filter_get_particles(self._h, _dptr(st), _dptr(w), n))
+        return st, w
+
+    def initialize_normal(self, mean_xytheta, cov, n: int):
+        self._check(self._lib.bb200_filter_initialize_normal(self._h, _dptr(_f64(mean_xytheta)), _dptr(_f64(cov).reshape(9)), n))
+
+    # per-step operations
+    @staticmethod
+    def _sampling(s) -> _capi.DiffDriveSampling:
+        return s if isinstance(s, _capi.DiffDriveSampling) else _capi.DiffDriveSampling(*[float(v) for v in s])
+
+    def propagate(self, sampling, step: int):
+        s = self._sampling(sampling)
+        self._check(self._lib.bb200_filter_propagate(self._h, C.byref(s), step))
+
+    def reweight(self, points):
+        pts = _f64(points).reshape(-1, 2)
+        self._check(self._lib.bb200_filter_reweight(self._h, _dptr(pts), len(pts)))
+
+    def propagate_reweight(self, sampling, step: int, points):
+        s = self._sampling(sampling)
+        pts = _f64(points).reshape(-1, 2)
+        self._check(self._lib.bb200_filter_propagate_reweight(self._h, C.byref(s), step, _dptr(pts), len(pts)))
+
+    def max_weight(self) -> float:
+        v = C.c_double()
+        self._check(self._lib.bb200_filter_max_weight(self._h, C.byref(v)))
+        return v.value
+
+    def build_cdf(self, global_wmax: float = -1.0):
+        total, ex = C.c_uint64(), C.c_int()
+        self._check(self._lib.bb200_filter_build_cdf(self._h, global_wmax, C.byref(total), C.byref(ex)))
+        return total.value, ex.value
+
+    def normalize_by(self, global_total: int) -> float:
+        sq = C.c_double()
+        self._check(self._lib.bb200_filter_normalize_by(self._h, global_total, C.byref(sq)))
+        return sq.value
+
+    def normalize(self):
+        f, sq = C.c_double(), C.c_double()
+        self._check(self._lib.bb200_filter_normalize(self._h, C.byref(f), C.byref(sq)))
+        return f.value, sq.value
+
+    def resample(self, scheme: int, step: int, max_particles: int, min_particles: int | None = None, kld_epsilon: float = 0.05,
+                 kld_z: float = 3.0, spatial_resolution=(0.5, 0.5, float(np.deg2rad(10.0))), random_state_probability: float = 0.0) -> int:
+        o = _capi.ResampleOpts(scheme, step, max_particles if min_particles is None else min_particles, max_particles, kld_epsilon,
+                               kld_z, (C.c_double * 3)(*spatial_resolution), random_state_probability)
+        n = C.c_uint64()
+        self._check(self._lib.bb200_filter_resample(self._h, C.byref(o), C.byref(n)))
+        return n.value
+
+    def ancestors(self) -> np.ndarray:
+        out = np.zeros(self.size(), dtype=np.int64)
+        self._check(self._lib.bb200_filter_ancestors(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), len(out)))
+        return out
+
+    def cdf(self) -> np.ndarray:
+        out = np.zeros(self.size(), dtype=np.uint64)
+        self._check(self._lib.bb200_filter_cdf(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), len(out)))
+        return out
+
+    def estimate(self):
+        e = _capi.Estimate()
+        self._check(self._lib.bb200_filter_estimate(self._h, C.byref(e)))
+        return np.array(e.mean), np.array(e.cov).reshape(3, 3)
+
+    def moments(self, pivot=(0.0, 0.0)) -> np.ndarray:
+        out = np.zeros(9)
+        self._check(self._lib.bb200_filter_moments(self._h, _dptr(_f64(pivot)), _dptr(out)))
+        return out
+
+    def set_timing(self, enabled: bool):
+        self._check(self._lib.bb200_filter_set_timing(self._h, int(enabled)))
+
+    def last_timings(self) -> list[tuple[str, float]]:
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        n = self._lib.bb200_filter_last_timings(self._h, names, ms, 32)
+        return [(names[i].decode(), ms[i]) for i in range(min(n, 32))]
+
+    def launch_count(self) -> int:
+        return self._lib.bb200_filter_launch_count(self._h)
+
+    def synchronize(self):
+        self._check(self._lib.bb200_filter_synchronize(self._h))
+
+    def device_pointer(self, which: int):
+        p, b = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.bb200_filter_device_pointer(self._h, which, C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+
+class Amcl:
+    """bb200_amcl: beluga::Amcl (algorithm/amcl_core.hpp:81-233) with the particle set on the GPU."""
+
+    def __init__(self, motion: DifferentialDriveModelParam, params: AmclParams):
+        self._lib = _capi.load()
+        p, m = params.c(), motion.c()
+        h = C.c_void_p()
+        st = self._lib.bb200_amcl_create(C.byref(p), C.byref(m), C.byref(h))
+        if st != _capi.OK:
+            raise BelugaB200Error(st, self._lib.bb200_create_error().decode())
+        self._h = h
+        self.params = params
+        self.filter = Filter(_handle=self._lib.bb200_amcl_filter(self._h), _owner=self)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.filter._h = None
+            self._lib.bb200_amcl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, st: int):
+        if st != _capi.OK:
+            raise BelugaB200Error(st, self._lib.bb200_amcl_last_error(self._h).decode())
+
+    def update_map(self, sensor: int, params, grid: OccupancyGrid):
+        """Amcl::update_map (amcl_core.hpp:150) / sensor model construction."""
+        if sensor == SENSOR_BEAM:
+            self.filter.set_beam_map(params, grid)
+        else:
+            self.filter.set_likelihood_field_map(params, grid, prob=(sensor == SENSOR_LIKELIHOOD_FIELD_PROB))
+
+    def initialize(self, mean_xytheta, cov):
+        self._check(self._lib.bb200_amcl_initialize(self._h, _dptr(_f64(mean_xytheta)), _dptr(_f64(cov).reshape(9))))
+
+    def initialize_states(self, states, weights=None):
+        st = _f64(states).reshape(-1, 4)
+        w = None if weights is None else _f64(weights)
+        self._check(self._lib.bb200_amcl_initialize_states(self._h, _dptr(st), None if w is None else _dptr(w), len(st)))
+
+    def force_update(self):
+        self._lib.bb200_amcl_force_update(self._h)
+
+    def particles(self):
+        return self.filter.particles()
+
+    def update(self, control_pose, points) -> _capi.UpdateResult:
+        """Amcl::update: returns the result block; `.updated == 0` is the reference's std::nullopt."""
+        pts = _f64(points).reshape(-1, 2)
+        res = _capi.UpdateResult()
+        self._check(self._lib.bb200_amcl_update(self._h, _dptr(_f64(control_pose)), _dptr(pts), len(pts), C.byref(res)))
+        return res

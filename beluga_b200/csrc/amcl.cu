@@ -1,0 +1,164 @@
+#include "amcl.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+namespace bb200 {
+
+namespace {
+
+/// rotation_variance -- differential_drive_model.hpp:167-173: backward and forward motion are
+/// treated symmetrically.
+double rotation_variance(const Rot2& rotation) {
+  static const Rot2 kFlip = rot_exp(3.14159265358979323846);
+  const Rot2 flipped = rot_mul(rotation, kFlip);
+  const double delta = std::min(std::fabs(rot_log(rotation)), std::fabs(rot_log(flipped)));
+  return delta * delta;
+}
+
+double exponential_filter(double& output, double alpha, double input) {  // exponential_filter.hpp:41-44
+  output += (output == 0.) ? input : alpha * (input - output);
+  return output;
+}
+
+}  // namespace
+
+bb200_diff_drive_sampling diff_drive_sampling(const bb200_diff_drive_param& p, const Pose2& pose, const Pose2& prev) {
+  const double tx = pose.x - prev.x, ty = pose.y - prev.y;
+  const double distance = std::sqrt(tx * tx + ty * ty);
+  const double distance_variance = distance * distance;
+  const Rot2 previous_orientation{prev.c, prev.s};
+  const Rot2 current_orientation{pose.c, pose.s};
+  const Rot2 heading_rotation = rot_exp(std::atan2(ty, tx));
+  const Rot2 first_rotation = distance > p.distance_threshold ? rot_mul(heading_rotation, rot_inverse(previous_orientation)) : Rot2{1.0, 0.0};
+  const Rot2 second_rotation = rot_mul(rot_mul(current_orientation, rot_inverse(previous_orientation)), rot_inverse(first_rotation));
+  const double v1 = rotation_variance(first_rotation), v2 = rotation_variance(second_rotation);
+  bb200_diff_drive_sampling s;
+  s.rot1_mean = rot_log(first_rotation);
+  s.rot1_std = std::sqrt(p.rotation_noise_from_rotation * v1 + p.rotation_noise_from_translation * distance_variance);
+  s.trans_mean = distance;
+  s.trans_std = std::sqrt(p.translation_noise_from_translation * distance_variance + p.translation_noise_from_rotation * (v1 + v2));
+  s.rot2_mean = rot_log(second_rotation);
+  s.rot2_std = std::sqrt(p.rotation_noise_from_rotation * v2 + p.rotation_noise_from_translation * distance_variance);
+  return s;
+}
+
+Amcl::Amcl(const bb200_amcl_param& p, const bb200_diff_drive_param& motion) : params_(p), motion_(motion) {
+  bb200_filter_config c{};
+  c.device = p.device;
+  c.capacity = p.max_particles;
+  c.seed = p.seed;
+  c.first_index = 0;
+  c.global_count = p.max_particles;
+  c.record_ancestors = p.record_ancestors;
+  filter_ = std::make_unique<Filter>(c);
+  if (params_.resample_interval == 0) params_.resample_interval = 1;
+}
+
+int Amcl::initialize(const double mean[3], const double cov[9]) {
+  error_.clear();
+  const int st = filter_->initialize_normal(mean, cov, params_.max_particles);
+  if (st == BB200_OK) force_update_ = true;  // amcl_core.hpp:136
+  return st;
+}
+
+int Amcl::initialize_states(const double* states, const double* weights, uint64_t n) {
+  error_.clear();
+  const int st = filter_->set_particles(states, weights, n);
+  if (st == BB200_OK) force_update_ = true;
+  return st;
+}
+
+int Amcl::update(const double control[4], const double* points_xy, uint64_t n_points, bb200_update_result* out) {
+  error_.clear();
+  *out = bb200_update_result{};
+  const Pose2 pose{control[0], control[1], control[2], control[3]};
+  const uint64_t n = filter_->size();
+  if (n == 0) return BB200_OK;  // amcl_core.hpp:166-168 -> std::nullopt
+
+  // update_policy_(control_action) -- on_motion vs the last ACCEPTED pose (on_motion.hpp:121-133)
+  bool moved;
+  if (!latest_pose_) {
+    latest_pose_ = pose;
+    moved = true;
+  } else {
+    const Pose2 delta = pose_mul(pose_inverse(*latest_pose_), pose);
+    moved = std::sqrt(delta.x * delta.x + delta.y * delta.y) > params_.update_min_d ||
+            std::fabs(rot_log(Rot2{delta.c, delta.s})) > params_.update_min_a;
+    if (moved) latest_pose_ = pose;
+  }
+  if (!moved && !force_update_) return BB200_OK;
+
+  // control_action_window_ << control (circular_array.hpp:473-480); reads clamp to size-1 (:353-361)
+  window_[1] = window_[0];
+  window_[0] = pose;
+  window_size_ = std::min(window_size_ + 1, 2);
+  const Pose2& previous = window_[std::min(1, window_size_ - 1)];
+  const bb200_diff_drive_sampling sampling = diff_drive_sampling(motion_, window_[0], previous);
+  ++step_;
+
+  // random_probability_estimator_(particles_) (thrun_recovery_probability_estimator.hpp:69-89) on the
+  // normalised weights, whose total is 1 by construction: average = 1 / N.
+  const double average_weight = 1.0 / static_cast<double>(n);
+  const double fast_average = exponential_filter(fast_output_, params_.alpha_fast, average_weight);
+  const double slow_average = exponential_filter(slow_output_, params_.alpha_slow, average_weight);
+  double random_state_probability = 0.0;
+  if (!(std::fabs(slow_average) < std::numeric_limits<double>::epsilon())) {
+    random_state_probability = std::clamp(1.0 - fast_average / slow_average, 0.0, 1.0);
+  }
+  out->random_state_probability = random_state_probability;
+
+  // resample_policy_: every_n (every_n.hpp:47-50) [&& on_effective_size_drop]
+  every_n_current_ = (every_n_current_ + 1) % params_.resample_interval;
+  bool do_resample = every_n_current_ == 0;
+
+  bb200_resample_opts o{};
+  o.scheme = params_.resample_scheme;
+  o.step = step_;
+  o.min_particles = params_.min_particles;
+  o.max_particles = params_.max_particles;
+  o.kld_epsilon = params_.kld_epsilon;
+  o.kld_z = params_.kld_z;
+  for (int k = 0; k < 3; ++k) o.spatial_resolution[k] = params_.spatial_resolution[k];
+  o.random_state_probability = random_state_probability;
+
+  int st;
+  const bool kld_active = params_.min_particles < params_.max_particles;
+  if (do_resample && !params_.selective_resampling && !kld_active) {
+    // The whole step in one stream-ordered sequence with a single host synchronisation.
+    if (random_state_probability > 0.0) fast_output_ = slow_output_ = 0.0;  // amcl_core.hpp:184-186
+    uint64_t new_size = 0;
+    st = filter_->step_resample(sampling, step_, points_xy, n_points, o, &out->estimate, &out->weight_sum, &new_size);
+    if (st != BB200_OK) return st;
+    out->resampled = 1;
+    out->n_particles = new_size;
+  } else {
+    st = filter_->propagate_reweight(&sampling, step_, points_xy, n_points);
+    if (st != BB200_OK) return st;
+    double factor = 0.0, sum_sq = 0.0;
+    st = filter_->normalize(&factor, &sum_sq);
+    if (st != BB200_OK) return st;
+    out->weight_sum = factor;
+    if (do_resample && params_.selective_resampling) {
+      // on_effective_size_drop (on_effective_size_drop.hpp:45-49): ESS = 1 / sum w~^2 < N / 2
+      const double ess = sum_sq > 0.0 ? 1.0 / sum_sq : 0.0;
+      do_resample = ess < static_cast<double>(n) * 0.5;
+    }
+    if (do_resample) {
+      if (random_state_probability > 0.0) fast_output_ = slow_output_ = 0.0;
+      uint64_t new_size = 0;
+      st = filter_->resample(o, &new_size);
+      if (st != BB200_OK) return st;
+      out->resampled = 1;
+    }
+    st = filter_->estimate(&out->estimate);
+    if (st != BB200_OK) return st;
+    out->n_particles = filter_->size();
+  }
+  force_update_ = false;
+  out->updated = 1;
+  return BB200_OK;
+}
+
+}  // namespace bb200

@@ -1,0 +1,51 @@
+// Host control flow of beluga::Amcl (reference: algorithm/amcl_core.hpp:81-233) over the device
+// filter: update / resample policies, rolling control window, recovery-probability estimator.
+// Only scalars live here; particles never leave the GPU.
+#pragma once
+
+#include <memory>
+#include <optional>
+#include <string>
+
+#include "filter.hpp"
+
+namespace bb200 {
+
+/// DifferentialDriveModel::sampling_fn_2d host part -- motion/differential_drive_model.hpp:129-154.
+bb200_diff_drive_sampling diff_drive_sampling(const bb200_diff_drive_param& p, const Pose2& pose, const Pose2& previous_pose);
+
+class Amcl {
+ public:
+  Amcl(const bb200_amcl_param& p, const bb200_diff_drive_param& motion);
+
+  Filter& filter() { return *filter_; }
+  bool ok() const { return filter_ && filter_->ok(); }
+  int create_status() const { return filter_ ? filter_->create_status() : BB200_ERR_CUDA; }
+  const char* last_error() const { return error_.empty() ? filter_->last_error() : error_.c_str(); }
+
+  int initialize(const double mean[3], const double cov[9]);
+  int initialize_states(const double* states, const double* weights, uint64_t n);
+  void force_update() { force_update_ = true; }
+  int update(const double control[4], const double* points_xy, uint64_t n_points, bb200_update_result* out);
+
+ private:
+  bb200_amcl_param params_;
+  bb200_diff_drive_param motion_;
+  std::unique_ptr<Filter> filter_;
+  std::string error_;
+
+  // policies/on_motion.hpp:121-133
+  std::optional<Pose2> latest_pose_;
+  // policies/every_n.hpp:47-50
+  uint64_t every_n_current_{0};
+  // algorithm/thrun_recovery_probability_estimator.hpp:40-94 + exponential_filter.hpp:35-44
+  double slow_output_{0.0}, fast_output_{0.0};
+  // containers/circular_array.hpp:461-480 RollingWindow<SE2d, 2>
+  Pose2 window_[2]{{1, 0, 0, 0}, {1, 0, 0, 0}};
+  int window_size_{0};
+
+  bool force_update_{true};
+  uint32_t step_{0};
+};
+
+}  // namespace bb200

@@ -1,0 +1,230 @@
+// extern "C" surface of libbeluga_b200.so (declared in include/beluga_b200.h).
+#include <new>
+#include <string>
+
+#include "../../include/beluga_b200.h"
+#include "amcl.hpp"
+#include "filter.hpp"
+
+using bb200::Amcl;
+using bb200::Filter;
+
+struct bb200_filter {
+  Filter impl;
+  explicit bb200_filter(const bb200_filter_config& c) : impl(c) {}
+};
+
+struct bb200_amcl {
+  Amcl impl;
+  bb200_filter* filter_view;  // non-owning alias handed out by bb200_amcl_filter
+  bb200_amcl(const bb200_amcl_param& p, const bb200_diff_drive_param& m) : impl(p, m), filter_view(nullptr) {}
+};
+
+namespace {
+thread_local std::string g_create_error;
+
+// bb200_filter is layout-compatible with its only member, so the Amcl-owned Filter can be viewed
+// through the same handle type without a second allocation.
+static_assert(sizeof(bb200_filter) == sizeof(Filter), "bb200_filter must wrap Filter exactly");
+}  // namespace
+
+extern "C" {
+
+int bb200_abi_version(void) { return BB200_ABI_VERSION; }
+
+int bb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* bb200_create_error(void) { return g_create_error.c_str(); }
+
+int bb200_filter_create(const bb200_filter_config* config, bb200_filter** out) {
+  if (config == nullptr || out == nullptr) {
+    g_create_error = "null argument";
+    return BB200_ERR_INVALID_ARGUMENT;
+  }
+  *out = nullptr;
+  bb200_filter* f = new (std::nothrow) bb200_filter(*config);
+  if (f == nullptr) {
+    g_create_error = "out of host memory";
+    return BB200_ERR_CUDA;
+  }
+  if (!f->impl.ok()) {
+    g_create_error = f->impl.last_error();
+    const int st = f->impl.create_status();
+    delete f;
+    return st;
+  }
+  *out = f;
+  return BB200_OK;
+}
+
+void bb200_filter_destroy(bb200_filter* f) { delete f; }
+const char* bb200_last_error(const bb200_filter* f) { return f != nullptr ? f->impl.last_error() : "null filter"; }
+
+#define BB_REQUIRE(cond)                              \
+  do {                                                \
+    if (!(cond)) return BB200_ERR_INVALID_ARGUMENT;   \
+  } while (0)
+
+int bb200_filter_set_likelihood_field_map(bb200_filter* f, const bb200_likelihood_field_param* p, const bb200_occupancy_grid* grid, int prob) {
+  BB_REQUIRE(f && p && grid);
+  return f->impl.set_likelihood_field_map(*p, *grid, prob != 0);
+}
+int bb200_filter_set_beam_map(bb200_filter* f, const bb200_beam_param* p, const bb200_occupancy_grid* grid) {
+  BB_REQUIRE(f && p && grid);
+  return f->impl.set_beam_map(*p, *grid);
+}
+int bb200_filter_get_likelihood_field(const bb200_filter* f, float* out, uint64_t capacity) {
+  BB_REQUIRE(f && out);
+  return f->impl.get_likelihood_field(out, capacity);
+}
+int bb200_filter_set_particles(bb200_filter* f, const double* states, const double* weights, uint64_t n) {
+  BB_REQUIRE(f);
+  return f->impl.set_particles(states, weights, n);
+}
+int bb200_filter_size(const bb200_filter* f, uint64_t* n) {
+  BB_REQUIRE(f && n);
+  *n = f->impl.size();
+  return BB200_OK;
+}
+int bb200_filter_get_particles(bb200_filter* f, double* states, double* weights, uint64_t capacity) {
+  BB_REQUIRE(f);
+  return f->impl.get_particles(states, weights, capacity);
+}
+int bb200_filter_initialize_normal(bb200_filter* f, const double mean_xytheta[3], const double cov[9], uint64_t n) {
+  BB_REQUIRE(f && mean_xytheta && cov);
+  return f->impl.initialize_normal(mean_xytheta, cov, n);
+}
+int bb200_filter_propagate(bb200_filter* f, const bb200_diff_drive_sampling* s, uint32_t step) {
+  BB_REQUIRE(f && s);
+  return f->impl.propagate_reweight(s, step, nullptr, 0);
+}
+int bb200_filter_reweight(bb200_filter* f, const double* points_xy, uint64_t n_points) {
+  BB_REQUIRE(f && (points_xy || n_points == 0));
+  static const double kNoPoints[2] = {0.0, 0.0};
+  return f->impl.propagate_reweight(nullptr, 0, points_xy != nullptr ? points_xy : kNoPoints, n_points);
+}
+int bb200_filter_propagate_reweight(bb200_filter* f, const bb200_diff_drive_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points) {
+  BB_REQUIRE(f && s && (points_xy || n_points == 0));
+  static const double kNoPoints[2] = {0.0, 0.0};
+  return f->impl.propagate_reweight(s, step, points_xy != nullptr ? points_xy : kNoPoints, n_points);
+}
+int bb200_filter_max_weight(bb200_filter* f, double* wmax) {
+  BB_REQUIRE(f && wmax);
+  return f->impl.max_weight(wmax);
+}
+int bb200_filter_build_cdf(bb200_filter* f, double global_wmax, uint64_t* local_total, int* exponent) {
+  BB_REQUIRE(f);
+  return f->impl.build_cdf(global_wmax, local_total, exponent);
+}
+int bb200_filter_normalize_by(bb200_filter* f, uint64_t global_total, double* local_sum_sq) {
+  BB_REQUIRE(f);
+  return f->impl.normalize_by(global_total, local_sum_sq);
+}
+int bb200_filter_normalize(bb200_filter* f, double* factor, double* sum_sq) {
+  BB_REQUIRE(f);
+  return f->impl.normalize(factor, sum_sq);
+}
+int bb200_filter_resample(bb200_filter* f, const bb200_resample_opts* o, uint64_t* new_size) {
+  BB_REQUIRE(f && o);
+  return f->impl.resample(*o, new_size);
+}
+int bb200_filter_ancestors(bb200_filter* f, int64_t* out, uint64_t capacity) {
+  BB_REQUIRE(f && out);
+  return f->impl.ancestors(out, capacity);
+}
+int bb200_filter_cdf(bb200_filter* f, uint64_t* out, uint64_t capacity) {
+  BB_REQUIRE(f && out);
+  return f->impl.cdf(out, capacity);
+}
+int bb200_filter_estimate(bb200_filter* f, bb200_estimate* out) {
+  BB_REQUIRE(f && out);
+  return f->impl.estimate(out);
+}
+int bb200_filter_moments(bb200_filter* f, const double pivot_xy[2], double out[9]) {
+  BB_REQUIRE(f && pivot_xy && out);
+  return f->impl.moments(pivot_xy, out);
+}
+int bb200_filter_set_timing(bb200_filter* f, int enabled) {
+  BB_REQUIRE(f);
+  f->impl.set_timing(enabled != 0);
+  return BB200_OK;
+}
+int bb200_filter_last_timings(const bb200_filter* f, const char** names, float* ms, int capacity) {
+  if (f == nullptr) return 0;
+  return f->impl.last_timings(names, ms, capacity);
+}
+uint64_t bb200_filter_launch_count(const bb200_filter* f) { return f != nullptr ? f->impl.launch_count() : 0; }
+int bb200_filter_synchronize(bb200_filter* f) {
+  BB_REQUIRE(f);
+  return f->impl.synchronize();
+}
+int bb200_filter_device_pointer(bb200_filter* f, int which, void** ptr, uint64_t* bytes) {
+  BB_REQUIRE(f && ptr && bytes);
+  return f->impl.device_pointer(which, ptr, bytes);
+}
+
+// ---- amcl ---------------------------------------------------------------------------------------
+
+int bb200_amcl_create(const bb200_amcl_param* p, const bb200_diff_drive_param* motion, bb200_amcl** out) {
+  if (p == nullptr || motion == nullptr || out == nullptr) {
+    g_create_error = "null argument";
+    return BB200_ERR_INVALID_ARGUMENT;
+  }
+  *out = nullptr;
+  if (p->max_particles == 0 || p->min_particles > p->max_particles) {
+    g_create_error = "need 0 < min_particles <= max_particles";
+    return BB200_ERR_INVALID_ARGUMENT;
+  }
+  if (!(p->alpha_slow >= 0.0) || !(p->alpha_slow <= p->alpha_fast)) {  // thrun_recovery_probability_estimator.hpp:49-50
+    g_create_error = "need 0 <= alpha_slow <= alpha_fast";
+    return BB200_ERR_INVALID_ARGUMENT;
+  }
+  bb200_amcl* a = new (std::nothrow) bb200_amcl(*p, *motion);
+  if (a == nullptr) {
+    g_create_error = "out of host memory";
+    return BB200_ERR_CUDA;
+  }
+  if (!a->impl.ok()) {
+    g_create_error = a->impl.last_error();
+    const int st = a->impl.create_status();
+    delete a;
+    return st;
+  }
+  a->filter_view = reinterpret_cast<bb200_filter*>(&a->impl.filter());
+  *out = a;
+  return BB200_OK;
+}
+void bb200_amcl_destroy(bb200_amcl* a) { delete a; }
+const char* bb200_amcl_last_error(const bb200_amcl* a) { return a != nullptr ? a->impl.last_error() : "null amcl"; }
+bb200_filter* bb200_amcl_filter(bb200_amcl* a) { return a != nullptr ? a->filter_view : nullptr; }
+int bb200_amcl_initialize(bb200_amcl* a, const double mean_xytheta[3], const double cov[9]) {
+  BB_REQUIRE(a && mean_xytheta && cov);
+  return a->impl.initialize(mean_xytheta, cov);
+}
+int bb200_amcl_initialize_states(bb200_amcl* a, const double* states, const double* weights, uint64_t n) {
+  BB_REQUIRE(a);
+  return a->impl.initialize_states(states, weights, n);
+}
+void bb200_amcl_force_update(bb200_amcl* a) {
+  if (a != nullptr) a->impl.force_update();
+}
+int bb200_amcl_update(bb200_amcl* a, const double control_pose[4], const double* points_xy, uint64_t n_points, bb200_update_result* out) {
+  BB_REQUIRE(a && control_pose && out && (points_xy || n_points == 0));
+  static const double kNoPoints[2] = {0.0, 0.0};
+  return a->impl.update(control_pose, points_xy != nullptr ? points_xy : kNoPoints, n_points, out);
+}
+int bb200_diff_drive_sampling_from_control(const bb200_diff_drive_param* p, const double pose[4], const double previous_pose[4], bb200_diff_drive_sampling* out) {
+  BB_REQUIRE(p && pose && previous_pose && out);
+  *out = bb200::diff_drive_sampling(*p, bb200::Pose2{pose[0], pose[1], pose[2], pose[3]},
+                                    bb200::Pose2{previous_pose[0], previous_pose[1], previous_pose[2], previous_pose[3]});
+  return BB200_OK;
+}
+
+}  // extern "C"

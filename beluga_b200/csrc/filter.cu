@@ -1,0 +1,684 @@
+#include "filter.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "map_host.hpp"
+
+namespace bb200 {
+
+namespace {
+
+template <class T>
+cudaError_t dev_alloc(T** p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
+}
+
+Pose2 pose_from_array(const double* d) { return Pose2{d[0], d[1], d[2], d[3]}; }
+
+}  // namespace
+
+bool normal_transform(const double cov[9], double transform[9], std::string* error) {
+  // isApprox(transpose) of Eigen: ||C - C^T||_F^2 <= 1e-24 * ||C||_F^2
+  double diff2 = 0.0, norm2 = 0.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const double d = cov[3 * i + j] - cov[3 * j + i];
+      diff2 += d * d;
+      norm2 += cov[3 * i + j] * cov[3 * i + j];
+    }
+  if (!(diff2 <= 1e-24 * norm2)) {
+    if (error) *error = "Invalid covariance matrix, it is not symmetric.";
+    return false;
+  }
+  // Cyclic Jacobi on the symmetric 3x3; eigenvalues ascending like SelfAdjointEigenSolver.
+  double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) a[i][j] = cov[3 * i + j];
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    if (a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2] == 0.0) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (a[p][q] == 0.0) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {
+          const double akp = a[k][p], akq = a[k][q];
+          a[k][p] = c * akp - s * akq;
+          a[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double apk = a[p][k], aqk = a[q][k];
+          a[p][k] = c * apk - s * aqk;
+          a[q][k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = v[k][p], vkq = v[k][q];
+          v[k][p] = c * vkp - s * vkq;
+          v[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int order[3] = {0, 1, 2};
+  std::sort(order, order + 3, [&](int i, int j) { return a[i][i] < a[j][j]; });
+  for (int j = 0; j < 3; ++j) {
+    const double lambda = a[order[j]][order[j]];
+    if (lambda < 0.0) {
+      if (error) *error = "Invalid covariance matrix, it has negative eigenvalues.";
+      return false;
+    }
+    for (int i = 0; i < 3; ++i) transform[3 * i + j] = v[i][order[j]] * std::sqrt(lambda);
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+
+Filter::Filter(const bb200_filter_config& config) : config_(config) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    create_status_ = fail(BB200_ERR_NO_DEVICE, "no CUDA device available (this backend has no CPU fallback)");
+    return;
+  }
+  if (config.device < 0 || config.device >= count) {
+    create_status_ = fail(BB200_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    return;
+  }
+  if (config.capacity == 0) {
+    create_status_ = fail(BB200_ERR_INVALID_ARGUMENT, "capacity must be positive");
+    return;
+  }
+  if (config_.global_count == 0) config_.global_count = config_.capacity;
+  capacity_ = config.capacity;
+#define BB_TRY(expr)                                \
+  do {                                              \
+    const int st = check((expr), #expr);            \
+    if (st != BB200_OK) {                           \
+      create_status_ = st;                          \
+      return;                                       \
+    }                                               \
+  } while (0)
+  BB_TRY(cudaSetDevice(config.device));
+  BB_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  BB_TRY(dev_alloc(&states_[0], capacity_));
+  BB_TRY(dev_alloc(&states_[1], capacity_));
+  BB_TRY(dev_alloc(&weights_, capacity_));
+  BB_TRY(dev_alloc(&cdf_, capacity_));
+  if (config.record_ancestors) BB_TRY(dev_alloc(&ancestors_, capacity_));
+  BB_TRY(dev_alloc(&scalars_, 1));
+  BB_TRY(cudaMallocHost(reinterpret_cast<void**>(&scalars_host_), sizeof(Scalars)));
+  tile_capacity_ = scan_tile_count(capacity_) + 1;
+  BB_TRY(dev_alloc(&tile_state_, tile_capacity_));
+  partials_rows_ = std::max(std::max(resample_block_count(capacity_), moments_block_count(capacity_)), 148u * 8u);
+  BB_TRY(dev_alloc(&partials_, static_cast<size_t>(partials_rows_) * kMomentCount));
+  BB_TRY(dev_alloc(&results_, 16));
+  BB_TRY(cudaMallocHost(reinterpret_cast<void**>(&results_host_), 16 * sizeof(double)));
+  BB_TRY(cudaMemsetAsync(scalars_, 0, sizeof(Scalars), stream_));
+  BB_TRY(cudaStreamSynchronize(stream_));
+#undef BB_TRY
+  created_ = true;
+}
+
+Filter::~Filter() {
+  if (stream_ != nullptr) cudaStreamSynchronize(stream_);
+  for (auto& e : event_pool_) cudaEventDestroy(e);
+  cudaFree(states_[0]);
+  cudaFree(states_[1]);
+  cudaFree(weights_);
+  cudaFree(cdf_);
+  cudaFree(ancestors_);
+  cudaFree(hashes_);
+  cudaFree(scalars_);
+  cudaFreeHost(scalars_host_);
+  cudaFree(tile_state_);
+  cudaFree(partials_);
+  cudaFree(results_);
+  cudaFreeHost(results_host_);
+  cudaFree(kld_keys_);
+  cudaFree(kld_vals_);
+  cudaFree(kld_flags_);
+  cudaFree(kld_scan_);
+  cudaFree(points_);
+  cudaFreeHost(points_host_);
+  cudaFree(table_);
+  cudaFree(occupancy_);
+  cudaFree(free_cells_);
+  if (stream_ != nullptr) cudaStreamDestroy(stream_);
+}
+
+int Filter::fail(int status, const std::string& message) {
+  error_ = message;
+  return status;
+}
+
+int Filter::check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return BB200_OK;
+  return fail(BB200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define BB_CHECK(expr)                          \
+  do {                                          \
+    const int st_ = check((expr), #expr);       \
+    if (st_ != BB200_OK) return st_;            \
+  } while (0)
+#define BB_LAUNCHED(name)                                   \
+  do {                                                      \
+    ++launches_;                                            \
+    const int st_ = check(cudaGetLastError(), name);        \
+    if (st_ != BB200_OK) return st_;                        \
+  } while (0)
+
+void Filter::mark(const char* name) {
+  if (!timing_) return;
+  if (events_used_ == event_pool_.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    event_pool_.push_back(e);
+  }
+  cudaEvent_t e = event_pool_[events_used_++];
+  cudaEventRecord(e, stream_);
+  marks_.push_back(Mark{name, e});
+}
+
+void Filter::finish_marks() {
+  if (!timing_ || marks_.empty()) {
+    marks_.clear();
+    events_used_ = 0;
+    return;
+  }
+  mark("end");
+  cudaEventSynchronize(marks_.back().event);
+  timings_.clear();
+  for (size_t i = 0; i + 1 < marks_.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, marks_[i].event, marks_[i + 1].event);
+    timings_.emplace_back(marks_[i].name, ms);
+  }
+  marks_.clear();
+  events_used_ = 0;
+}
+
+int Filter::last_timings(const char** names, float* ms, int capacity) const {
+  const int n = std::min<int>(capacity, static_cast<int>(timings_.size()));
+  for (int i = 0; i < n; ++i) {
+    names[i] = timings_[i].first;
+    ms[i] = timings_[i].second;
+  }
+  return static_cast<int>(timings_.size());
+}
+
+int Filter::synchronize() {
+  BB_CHECK(cudaSetDevice(config_.device));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  return BB200_OK;
+}
+
+int Filter::device_pointer(int which, void** ptr, uint64_t* bytes) {
+  switch (which) {
+    case 0: *ptr = states_[cur_]; *bytes = capacity_ * sizeof(Pose2); return BB200_OK;
+    case 1: *ptr = weights_; *bytes = capacity_ * sizeof(double); return BB200_OK;
+    case 2: *ptr = cdf_; *bytes = capacity_ * sizeof(unsigned long long); return BB200_OK;
+    case 3: *ptr = states_[cur_ ^ 1]; *bytes = capacity_ * sizeof(Pose2); return BB200_OK;
+    default: return fail(BB200_ERR_INVALID_ARGUMENT, "unknown device pointer id");
+  }
+}
+
+// ---- maps -----------------------------------------------------------------------------------------
+
+int Filter::set_likelihood_field_map(const bb200_likelihood_field_param& p, const bb200_occupancy_grid& g, bool prob) {
+  if (g.cells == nullptr || g.width <= 0 || g.height <= 0 || !(g.resolution > 0.0)) return fail(BB200_ERR_INVALID_ARGUMENT, "invalid occupancy grid");
+  if (!(p.sigma_hit > 0.0) || !(p.max_laser_distance > 0.0)) return fail(BB200_ERR_INVALID_ARGUMENT, "invalid likelihood field parameters");
+  BB_CHECK(cudaSetDevice(config_.device));
+  field_host_ = make_likelihood_field(p, g);
+  const size_t count = field_host_.size();
+  // Per-cell f(pz) in double: pz^3 (likelihood_field_model.hpp:84-89) or log pz (prob model :84-86).
+  std::vector<double> table(count);
+  auto f = [prob](float pzf) {
+    const double pz = static_cast<double>(pzf);
+    return prob ? std::log(pz) : pz * pz * pz;
+  };
+  for (size_t i = 0; i < count; ++i) table[i] = f(field_host_[i]);
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  cudaFree(table_);
+  table_ = nullptr;
+  BB_CHECK(dev_alloc(&table_, count));
+  BB_CHECK(cudaMemcpyAsync(table_, table.data(), count * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+
+  field_.table = table_;
+  field_.width = g.width;
+  field_.height = g.height;
+  field_.inv_resolution = 1. / g.resolution;
+  field_.unknown_value = f(static_cast<float>(1. / p.max_laser_distance));
+  field_.init = prob ? 0.0 : 1.0;
+  field_.exp_epilogue = prob ? 1 : 0;
+  field_.world_to_field = pose_inverse(pose_from_array(g.origin));
+  sensor_ = prob ? BB200_SENSOR_LIKELIHOOD_FIELD_PROB : BB200_SENSOR_LIKELIHOOD_FIELD;
+
+  // Free cells for the recovery random-state generator.
+  const std::vector<uint32_t> free = make_free_cells(g);
+  cudaFree(free_cells_);
+  free_cells_ = nullptr;
+  n_free_ = free.size();
+  BB_CHECK(dev_alloc(&free_cells_, free.size()));
+  if (!free.empty()) BB_CHECK(cudaMemcpy(free_cells_, free.data(), free.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  grid_width_ = g.width;
+  grid_resolution_ = g.resolution;
+  grid_origin_ = pose_from_array(g.origin);
+  return BB200_OK;
+}
+
+int Filter::set_beam_map(const bb200_beam_param& p, const bb200_occupancy_grid& g) {
+  if (g.cells == nullptr || g.width <= 0 || g.height <= 0 || !(g.resolution > 0.0)) return fail(BB200_ERR_INVALID_ARGUMENT, "invalid occupancy grid");
+  BB_CHECK(cudaSetDevice(config_.device));
+  const size_t count = static_cast<size_t>(g.width) * static_cast<size_t>(g.height);
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  cudaFree(occupancy_);
+  occupancy_ = nullptr;
+  BB_CHECK(dev_alloc(&occupancy_, count));
+  BB_CHECK(cudaMemcpy(occupancy_, g.cells, count, cudaMemcpyHostToDevice));
+  occupancy_view_.cells = occupancy_;
+  occupancy_view_.width = g.width;
+  occupancy_view_.height = g.height;
+  occupancy_view_.resolution = g.resolution;
+  occupancy_view_.inv_resolution = 1. / g.resolution;
+  occupancy_view_.world_to_grid = pose_inverse(pose_from_array(g.origin));
+  beam_ = BeamParams{p.z_hit, p.z_short, p.z_max, p.z_rand, p.sigma_hit, p.lambda_short, p.beam_max_range};
+  sensor_ = BB200_SENSOR_BEAM;
+  field_host_.clear();
+
+  const std::vector<uint32_t> free = make_free_cells(g);
+  cudaFree(free_cells_);
+  free_cells_ = nullptr;
+  n_free_ = free.size();
+  BB_CHECK(dev_alloc(&free_cells_, free.size()));
+  if (!free.empty()) BB_CHECK(cudaMemcpy(free_cells_, free.data(), free.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  grid_width_ = g.width;
+  grid_resolution_ = g.resolution;
+  grid_origin_ = pose_from_array(g.origin);
+  return BB200_OK;
+}
+
+int Filter::get_likelihood_field(float* out, uint64_t capacity) const {
+  if (field_host_.empty()) return BB200_ERR_STATE;
+  if (capacity < field_host_.size()) return BB200_ERR_CAPACITY;
+  std::memcpy(out, field_host_.data(), field_host_.size() * sizeof(float));
+  return BB200_OK;
+}
+
+// ---- particle access ---------------------------------------------------------------------------------
+
+int Filter::set_particles(const double* states, const double* weights, uint64_t n) {
+  if (n > capacity_) return fail(BB200_ERR_CAPACITY, "more particles than the filter capacity");
+  if (n > 0 && states == nullptr) return fail(BB200_ERR_INVALID_ARGUMENT, "states is null");
+  BB_CHECK(cudaSetDevice(config_.device));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  if (n > 0) {
+    BB_CHECK(cudaMemcpy(states_[cur_], states, n * sizeof(Pose2), cudaMemcpyHostToDevice));
+    if (weights != nullptr) {
+      BB_CHECK(cudaMemcpy(weights_, weights, n * sizeof(double), cudaMemcpyHostToDevice));
+    } else {
+      const std::vector<double> ones(n, 1.0);
+      BB_CHECK(cudaMemcpy(weights_, ones.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    }
+  }
+  n_ = n;
+  cdf_valid_ = false;
+  return BB200_OK;
+}
+
+int Filter::get_particles(double* states, double* weights, uint64_t capacity) {
+  BB_CHECK(cudaSetDevice(config_.device));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  const uint64_t n = std::min(capacity, n_);
+  if (states != nullptr && n > 0) BB_CHECK(cudaMemcpy(states, states_[cur_], n * sizeof(Pose2), cudaMemcpyDeviceToHost));
+  if (weights != nullptr && n > 0) BB_CHECK(cudaMemcpy(weights, weights_, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return BB200_OK;
+}
+
+int Filter::initialize_normal(const double mean[3], const double cov[9], uint64_t n) {
+  if (n > capacity_) return fail(BB200_ERR_CAPACITY, "more particles than the filter capacity");
+  double transform[9];
+  std::string message;
+  if (!normal_transform(cov, transform, &message)) return fail(BB200_ERR_INVALID_ARGUMENT, message);
+  BB_CHECK(cudaSetDevice(config_.device));
+  launch_initialize_normal(states_[cur_], weights_, n, mean, transform, config_.seed, config_.first_index, stream_);
+  BB_LAUNCHED("initialize_normal");
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  n_ = n;
+  cdf_valid_ = false;
+  pivot_[0] = mean[0];
+  pivot_[1] = mean[1];
+  return BB200_OK;
+}
+
+// ---- per-step operations -----------------------------------------------------------------------------
+
+int Filter::upload_points(const double* points_xy, uint64_t n_points) {
+  if (n_points > points_capacity_) {
+    cudaFree(points_);
+    cudaFreeHost(points_host_);
+    points_ = nullptr;
+    points_host_ = nullptr;
+    points_capacity_ = 0;
+    const uint64_t cap = std::max<uint64_t>(n_points, 2048);
+    BB_CHECK(dev_alloc(&points_, 2 * cap));
+    BB_CHECK(cudaMallocHost(reinterpret_cast<void**>(&points_host_), 2 * cap * sizeof(double)));
+    points_capacity_ = cap;
+  }
+  double radius = 0.0;
+  for (uint64_t i = 0; i < n_points; ++i) {
+    const double r = std::fabs(points_xy[2 * i]) + std::fabs(points_xy[2 * i + 1]);
+    radius = (r > radius || std::isnan(r)) ? r : radius;  // NaN sticks -> general lookup path
+  }
+  points_radius_ = radius;
+  if (n_points > 0) {
+    // The previous step's copy must have left the staging buffer before it is overwritten.
+    std::memcpy(points_host_, points_xy, 2 * n_points * sizeof(double));
+    BB_CHECK(cudaMemcpyAsync(points_, points_host_, 2 * n_points * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  }
+  return BB200_OK;
+}
+
+int Filter::propagate_reweight(const bb200_diff_drive_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  const bool do_reweight = points_xy != nullptr;
+  if (do_reweight && sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set");
+  if (do_reweight && n_points > 0xffffffffull) return fail(BB200_ERR_INVALID_ARGUMENT, "too many points");
+  BB_CHECK(cudaSetDevice(config_.device));
+  BB_CHECK(cudaStreamSynchronize(stream_));  // staging buffer reuse + keeps the fine-grained API simple
+  if (do_reweight) {
+    const int st = upload_points(points_xy, n_points);
+    if (st != BB200_OK) return st;
+  }
+  DiffDriveSampling s{};
+  if (sampling != nullptr) s = DiffDriveSampling{sampling->rot1_mean, sampling->rot1_std, sampling->trans_mean, sampling->trans_std, sampling->rot2_mean, sampling->rot2_std};
+  mark("begin_step");
+  launch_begin_step(scalars_, stream_);
+  BB_LAUNCHED("begin_step");
+  if (do_reweight && sensor_ == BB200_SENSOR_BEAM) {
+    mark("propagate_reweight_beam");
+    launch_propagate_reweight_beam(states_[cur_], weights_, n_, sampling != nullptr, s, config_.seed, step, config_.first_index, occupancy_view_,
+                                   beam_, points_, static_cast<uint32_t>(n_points), scalars_, stream_);
+    BB_LAUNCHED("propagate_reweight_beam");
+  } else {
+    mark("propagate_reweight_lfm");
+    launch_propagate_reweight_lfm(states_[cur_], weights_, n_, sampling != nullptr, s, config_.seed, step, config_.first_index, do_reweight,
+                                  field_, points_, static_cast<uint32_t>(n_points), points_radius_, scalars_, stream_);
+    BB_LAUNCHED("propagate_reweight_lfm");
+  }
+  cdf_valid_ = false;
+  finish_marks();
+  return BB200_OK;
+}
+
+int Filter::max_weight(double* wmax) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  BB_CHECK(cudaSetDevice(config_.device));
+  launch_begin_step(scalars_, stream_);
+  BB_LAUNCHED("begin_step");
+  launch_max_weight(weights_, n_, scalars_, stream_);
+  BB_LAUNCHED("max_weight");
+  BB_CHECK(cudaMemcpyAsync(scalars_host_, scalars_, sizeof(Scalars), cudaMemcpyDeviceToHost, stream_));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  double v;
+  std::memcpy(&v, &scalars_host_->wmax_bits, sizeof(double));
+  *wmax = v;
+  return BB200_OK;
+}
+
+int Filter::build_cdf(double global_wmax, uint64_t* local_total, int* exponent) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  BB_CHECK(cudaSetDevice(config_.device));
+  if (global_wmax < 0.0) {
+    launch_begin_step(scalars_, stream_);
+    BB_LAUNCHED("begin_step");
+    launch_max_weight(weights_, n_, scalars_, stream_);
+    BB_LAUNCHED("max_weight");
+  }
+  mark("prepare_cdf");
+  launch_prepare_cdf(scalars_, global_wmax, config_.global_count, tile_state_, scan_tile_count(n_), stream_);
+  BB_LAUNCHED("prepare_cdf");
+  mark("quantize_scan");
+  launch_quantize_scan(weights_, n_, cdf_, scalars_, tile_state_, stream_);
+  BB_LAUNCHED("quantize_scan");
+  BB_CHECK(cudaMemcpyAsync(scalars_host_, scalars_, sizeof(Scalars), cudaMemcpyDeviceToHost, stream_));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  finish_marks();
+  cdf_valid_ = true;
+  if (local_total != nullptr) *local_total = scalars_host_->total;
+  if (exponent != nullptr) *exponent = scalars_host_->exponent;
+  if (scalars_host_->valid == 0) return fail(BB200_ERR_STATE, "no positive finite weight (uniform CDF substituted)");
+  return BB200_OK;
+}
+
+int Filter::normalize_by(uint64_t global_total, double* local_sum_sq) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  if (!cdf_valid_) return fail(BB200_ERR_STATE, "build_cdf must run before normalize_by");
+  BB_CHECK(cudaSetDevice(config_.device));
+  uint32_t rows = 0;
+  mark("normalize");
+  launch_normalize(weights_, n_, scalars_, global_total, partials_, &rows, stream_);
+  BB_LAUNCHED("normalize");
+  launch_reduce_partials(partials_, rows, 1, results_, stream_);
+  BB_LAUNCHED("reduce_partials");
+  BB_CHECK(cudaMemcpyAsync(results_host_, results_, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  finish_marks();
+  if (local_sum_sq != nullptr) *local_sum_sq = results_host_[0];
+  return BB200_OK;
+}
+
+int Filter::normalize(double* factor, double* sum_sq) {
+  uint64_t total = 0;
+  int exponent = 0;
+  const int st = build_cdf(-1.0, &total, &exponent);
+  if (st != BB200_OK) return st;
+  if (factor != nullptr) *factor = std::ldexp(static_cast<double>(total), -exponent);
+  return normalize_by(total, sum_sq);
+}
+
+int Filter::ensure_cdf_ready() {
+  if (cdf_valid_) return BB200_OK;
+  return build_cdf(-1.0, nullptr, nullptr);
+}
+
+void Filter::estimate_from_moments(const double m[kMomentCount], bb200_estimate* out) const {
+  // estimation.hpp:436-475 from raw moments about the pivot: normalised weights w/S,
+  // mean of (cos, sin, x, y); cov = (E[d d^T] - E[d] E[d]^T) / (1 - sum (w/S)^2).
+  const double sum = m[0];
+  const double mc = m[2] / sum, ms = m[3] / sum, mdx = m[4] / sum, mdy = m[5] / sum;
+  const double correction = 1.0 - m[1] / (sum * sum);
+  for (double& c : out->cov) c = 0.0;
+  out->cov[0] = (m[6] / sum - mdx * mdx) / correction;
+  out->cov[1] = (m[7] / sum - mdx * mdy) / correction;
+  out->cov[3] = out->cov[1];
+  out->cov[4] = (m[8] / sum - mdy * mdy) / correction;
+  out->mean[2] = pivot_[0] + mdx;
+  out->mean[3] = pivot_[1] + mdy;
+  const double norm = std::sqrt(mc * mc + ms * ms);
+  if (norm < std::numeric_limits<double>::epsilon()) {
+    out->cov[8] = std::numeric_limits<double>::infinity();
+    out->mean[0] = 1.0;
+    out->mean[1] = 0.0;
+  } else {
+    out->cov[8] = -2.0 * std::log(norm);
+    const double len = std::hypot(mc, ms);
+    out->mean[0] = mc / len;
+    out->mean[1] = ms / len;
+  }
+}
+
+int Filter::moments(const double pivot[2], double out[9]) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  BB_CHECK(cudaSetDevice(config_.device));
+  mark("moments");
+  launch_moments(states_[cur_], weights_, n_, pivot[0], pivot[1], partials_, stream_);
+  BB_LAUNCHED("moments");
+  launch_reduce_partials(partials_, moments_block_count(n_), kMomentCount, results_, stream_);
+  BB_LAUNCHED("reduce_partials");
+  BB_CHECK(cudaMemcpyAsync(results_host_, results_, kMomentCount * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  finish_marks();
+  std::memcpy(out, results_host_, kMomentCount * sizeof(double));
+  return BB200_OK;
+}
+
+int Filter::estimate(bb200_estimate* out) {
+  double m[kMomentCount];
+  const int st = moments(pivot_, m);
+  if (st != BB200_OK) return st;
+  estimate_from_moments(m, out);
+  pivot_[0] = out->mean[2];
+  pivot_[1] = out->mean[3];
+  return BB200_OK;
+}
+
+int Filter::resample(const bb200_resample_opts& o, uint64_t* new_size) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  if (o.max_particles == 0 || o.max_particles > capacity_) return fail(BB200_ERR_CAPACITY, "max_particles exceeds the filter capacity");
+  if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
+  if (o.min_particles < o.max_particles) return fail(BB200_ERR_STATE, "KLD-adaptive resampling is not enabled in this build");
+  int st = ensure_cdf_ready();
+  if (st != BB200_OK && !cdf_valid_) return st;
+  BB_CHECK(cudaSetDevice(config_.device));
+
+  ResampleArgs a{};
+  a.states_in = states_[cur_];
+  a.cdf = cdf_;
+  a.n_in = n_;
+  a.states_out = states_[cur_ ^ 1];
+  a.weights_out = weights_;
+  a.ancestors = ancestors_;
+  a.hashes = nullptr;
+  a.slot_first = config_.first_index;
+  a.slot_count = o.max_particles;
+  a.total_slots = o.max_particles;
+  a.scheme = o.scheme;
+  a.seed = config_.seed;
+  a.step = o.step;
+  a.random_state_probability = o.random_state_probability;
+  a.free_cells = free_cells_;
+  a.n_free = n_free_;
+  a.grid_width = grid_width_;
+  a.grid_resolution = grid_resolution_;
+  a.grid_origin = grid_origin_;
+  for (int k = 0; k < 3; ++k) a.hash_resolution[k] = o.spatial_resolution[k];
+  a.pivot_x = pivot_[0];
+  a.pivot_y = pivot_[1];
+  mark("resample");
+  launch_resample(a, scalars_, partials_, stream_);
+  BB_LAUNCHED("resample");
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  finish_marks();
+  cur_ ^= 1;
+  n_ = o.max_particles;
+  ancestors_n_ = n_;
+  cdf_valid_ = false;
+  if (new_size != nullptr) *new_size = n_;
+  return BB200_OK;
+}
+
+int Filter::step_resample(const bb200_diff_drive_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points,
+                          const bb200_resample_opts& o, bb200_estimate* est, double* weight_sum, uint64_t* new_size) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  if (sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set");
+  if (o.max_particles == 0 || o.max_particles > capacity_) return fail(BB200_ERR_CAPACITY, "max_particles exceeds the filter capacity");
+  if (o.min_particles < o.max_particles) return fail(BB200_ERR_STATE, "KLD-adaptive resampling is not enabled in this build");
+  if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
+  BB_CHECK(cudaSetDevice(config_.device));
+  int st = upload_points(points_xy, n_points);
+  if (st != BB200_OK) return st;
+  const DiffDriveSampling s{sampling.rot1_mean, sampling.rot1_std, sampling.trans_mean, sampling.trans_std, sampling.rot2_mean, sampling.rot2_std};
+
+  mark("begin_step");
+  launch_begin_step(scalars_, stream_);
+  BB_LAUNCHED("begin_step");
+  if (sensor_ == BB200_SENSOR_BEAM) {
+    mark("propagate_reweight_beam");
+    launch_propagate_reweight_beam(states_[cur_], weights_, n_, true, s, config_.seed, step, config_.first_index, occupancy_view_, beam_, points_,
+                                   static_cast<uint32_t>(n_points), scalars_, stream_);
+    BB_LAUNCHED("propagate_reweight_beam");
+  } else {
+    mark("propagate_reweight_lfm");
+    launch_propagate_reweight_lfm(states_[cur_], weights_, n_, true, s, config_.seed, step, config_.first_index, true, field_, points_,
+                                  static_cast<uint32_t>(n_points), points_radius_, scalars_, stream_);
+    BB_LAUNCHED("propagate_reweight_lfm");
+  }
+  mark("prepare_cdf");
+  launch_prepare_cdf(scalars_, -1.0, config_.global_count, tile_state_, scan_tile_count(n_), stream_);
+  BB_LAUNCHED("prepare_cdf");
+  mark("quantize_scan");
+  launch_quantize_scan(weights_, n_, cdf_, scalars_, tile_state_, stream_);
+  BB_LAUNCHED("quantize_scan");
+
+  ResampleArgs a{};
+  a.states_in = states_[cur_];
+  a.cdf = cdf_;
+  a.n_in = n_;
+  a.states_out = states_[cur_ ^ 1];
+  a.weights_out = weights_;
+  a.ancestors = ancestors_;
+  a.hashes = nullptr;
+  a.slot_first = config_.first_index;
+  a.slot_count = o.max_particles;
+  a.total_slots = o.max_particles;
+  a.scheme = o.scheme;
+  a.seed = config_.seed;
+  a.step = o.step;
+  a.random_state_probability = o.random_state_probability;
+  a.free_cells = free_cells_;
+  a.n_free = n_free_;
+  a.grid_width = grid_width_;
+  a.grid_resolution = grid_resolution_;
+  a.grid_origin = grid_origin_;
+  for (int k = 0; k < 3; ++k) a.hash_resolution[k] = o.spatial_resolution[k];
+  a.pivot_x = pivot_[0];
+  a.pivot_y = pivot_[1];
+  mark("resample");
+  launch_resample(a, scalars_, partials_, stream_);
+  BB_LAUNCHED("resample");
+  mark("reduce_partials");
+  launch_reduce_partials(partials_, resample_block_count(a.slot_count), kMomentCount, results_, stream_);
+  BB_LAUNCHED("reduce_partials");
+  BB_CHECK(cudaMemcpyAsync(results_host_, results_, kMomentCount * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  BB_CHECK(cudaMemcpyAsync(scalars_host_, scalars_, sizeof(Scalars), cudaMemcpyDeviceToHost, stream_));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  finish_marks();
+
+  cur_ ^= 1;
+  n_ = o.max_particles;
+  ancestors_n_ = n_;
+  cdf_valid_ = false;
+  if (new_size != nullptr) *new_size = n_;
+  if (weight_sum != nullptr) *weight_sum = std::ldexp(static_cast<double>(scalars_host_->total), -scalars_host_->exponent);
+  if (est != nullptr) {
+    estimate_from_moments(results_host_, est);
+    pivot_[0] = est->mean[2];
+    pivot_[1] = est->mean[3];
+  }
+  return BB200_OK;
+}
+
+int Filter::ancestors(int64_t* out, uint64_t capacity) {
+  if (ancestors_ == nullptr) return fail(BB200_ERR_STATE, "filter was created without record_ancestors");
+  BB_CHECK(cudaSetDevice(config_.device));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  const uint64_t n = std::min(capacity, ancestors_n_);
+  if (n > 0) BB_CHECK(cudaMemcpy(out, ancestors_, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  return BB200_OK;
+}
+
+int Filter::cdf(uint64_t* out, uint64_t capacity) {
+  if (!cdf_valid_) return fail(BB200_ERR_STATE, "no CDF has been built for the current weights");
+  BB_CHECK(cudaSetDevice(config_.device));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  const uint64_t n = std::min(capacity, n_);
+  if (n > 0) BB_CHECK(cudaMemcpy(out, cdf_, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return BB200_OK;
+}
+
+}  // namespace bb200

@@ -1,0 +1,145 @@
+// Device-resident particle set of the B200 MCL backend: buffers, map uploads and the per-step
+// kernel sequence behind the C ABI of include/beluga_b200.h.  Host-side counterpart of
+// beluga::TupleVector<std::tuple<SE2d, Weight>> (reference: containers/tuple_vector.hpp:50-223)
+// plus the actions/views that iterate it (propagate, reweight, normalize, sample, assign).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/beluga_b200.h"
+#include "kernels.cuh"
+
+namespace bb200 {
+
+class Filter {
+ public:
+  explicit Filter(const bb200_filter_config& config);
+  ~Filter();
+  Filter(const Filter&) = delete;
+  Filter& operator=(const Filter&) = delete;
+
+  // Every method returns a bb200_status and records the message for last_error().
+  int set_likelihood_field_map(const bb200_likelihood_field_param& p, const bb200_occupancy_grid& grid, bool prob);
+  int set_beam_map(const bb200_beam_param& p, const bb200_occupancy_grid& grid);
+  int get_likelihood_field(float* out, uint64_t capacity) const;
+
+  int set_particles(const double* states, const double* weights, uint64_t n);
+  int get_particles(double* states, double* weights, uint64_t capacity);
+  int initialize_normal(const double mean[3], const double cov[9], uint64_t n);
+  uint64_t size() const { return n_; }
+
+  int propagate_reweight(const bb200_diff_drive_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points);
+  int max_weight(double* wmax);
+  int build_cdf(double global_wmax, uint64_t* local_total, int* exponent);
+  int normalize_by(uint64_t global_total, double* local_sum_sq);
+  int normalize(double* factor, double* sum_sq);
+  int resample(const bb200_resample_opts& o, uint64_t* new_size);
+  int ancestors(int64_t* out, uint64_t capacity);
+  int cdf(uint64_t* out, uint64_t capacity);
+  int estimate(bb200_estimate* out);
+  int moments(const double pivot[2], double out[9]);
+
+  /// Fused single-GPU step: propagate | reweight | normalize | resample | estimate with one
+  /// host synchronisation at the end (the composition Amcl::update performs every step).
+  int step_resample(const bb200_diff_drive_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points,
+                    const bb200_resample_opts& o, bb200_estimate* est, double* weight_sum, uint64_t* new_size);
+
+  int synchronize();
+  int device_pointer(int which, void** ptr, uint64_t* bytes);
+
+  void set_timing(bool on) { timing_ = on; }
+  int last_timings(const char** names, float* ms, int capacity) const;
+  uint64_t launch_count() const { return launches_; }
+  const char* last_error() const { return error_.c_str(); }
+  bool ok() const { return created_; }
+  int create_status() const { return create_status_; }
+
+ private:
+  int fail(int status, const std::string& message);
+  int check(cudaError_t e, const char* what);
+  int upload_points(const double* points_xy, uint64_t n_points);
+  int ensure_cdf_ready();
+  void estimate_from_moments(const double m[kMomentCount], bb200_estimate* out) const;
+  void mark(const char* name);  // timing: record an event before the next kernel
+  void finish_marks();
+  bool use_device() const;
+
+  bb200_filter_config config_{};
+  bool created_{false};
+  int create_status_{BB200_OK};
+  std::string error_;
+  cudaStream_t stream_{nullptr};
+
+  // particle set (ping-pong states for the resample gather)
+  uint64_t capacity_{0}, n_{0};
+  Pose2* states_[2]{nullptr, nullptr};
+  int cur_{0};
+  double* weights_{nullptr};
+  unsigned long long* cdf_{nullptr};
+  long long* ancestors_{nullptr};
+  uint64_t ancestors_n_{0};
+  unsigned long long* hashes_{nullptr};
+  bool cdf_valid_{false};
+  bool weights_uniform_{false};
+
+  // scratch
+  Scalars* scalars_{nullptr};
+  Scalars* scalars_host_{nullptr};  // pinned
+  unsigned long long* tile_state_{nullptr};
+  uint32_t tile_capacity_{0};
+  double* partials_{nullptr};
+  uint32_t partials_rows_{0};
+  double* results_{nullptr};       // device: kMomentCount + extras
+  double* results_host_{nullptr};  // pinned
+
+  // KLD scratch
+  unsigned long long* kld_keys_{nullptr};
+  unsigned int* kld_vals_{nullptr};
+  uint64_t kld_table_size_{0};
+  unsigned int* kld_flags_{nullptr};
+  unsigned long long* kld_scan_{nullptr};
+
+  // measurement
+  double* points_{nullptr};
+  double* points_host_{nullptr};  // pinned staging
+  uint64_t points_capacity_{0};
+  double points_radius_{0.0};
+
+  // maps
+  int sensor_{-1};
+  std::vector<float> field_host_;
+  double* table_{nullptr};
+  FieldView field_{};
+  int8_t* occupancy_{nullptr};
+  OccupancyView occupancy_view_{};
+  BeamParams beam_{};
+  uint32_t* free_cells_{nullptr};
+  uint64_t n_free_{0};
+  int grid_width_{0};
+  double grid_resolution_{1.0};
+  Pose2 grid_origin_{1.0, 0.0, 0.0, 0.0};
+
+  double pivot_[2]{0.0, 0.0};
+
+  // timing
+  bool timing_{false};
+  struct Mark {
+    const char* name;
+    cudaEvent_t event;
+  };
+  std::vector<Mark> marks_;
+  std::vector<cudaEvent_t> event_pool_;
+  size_t events_used_{0};
+  std::vector<std::pair<const char*, float>> timings_;
+  uint64_t launches_{0};
+};
+
+/// Symmetric 3x3 covariance -> V * sqrt(Lambda) (multivariate_normal_distribution.hpp:109-126).
+/// Returns false with a message for non-symmetric / negative-eigenvalue input.
+bool normal_transform(const double cov[9], double transform[9], std::string* error);
+
+}  // namespace bb200

@@ -1,0 +1,768 @@
+// Hand-written sm_100a kernels of the MCL particle-filter update.
+//
+// One filter step on the device (fixed particle count, resample every step):
+//
+//   begin_step            zero the per-filter scalars
+//   propagate_reweight    a2 + a6 + a3 + a5 of SURVEY.md section 8(a): Philox normals, SE2 compose,
+//                         B likelihood-field lookups per particle, w *= L, block max of w
+//   prepare_cdf           exponent of the fixed-point grid from the largest weight
+//   quantize_scan         q = floor(w * 2^e), single-pass decoupled look-back inclusive scan (u64)
+//   resample              a10 + a11 + a13: one thread per output slot; counter draw, CDF search,
+//                         32-byte state gather, w = 1, per-block raw moments for a14
+//   reduce_partials       fixed-order sum of the per-block moments
+//
+// All floating-point arithmetic that decides a likelihood-field cell or a weight follows the
+// reference's operation order without FMA contraction (the file is compiled with -fmad=false).
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cfloat>
+
+namespace bb200 {
+
+namespace {
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// ---- fixed-order block reductions --------------------------------------------------------------
+
+template <int kThreads>
+__device__ __forceinline__ double block_sum(double v, double* scratch /* kThreads/32 doubles */) {
+#pragma unroll
+  for (int off = kWarp / 2; off > 0; off >>= 1) v = v + __shfl_down_sync(0xffffffffu, v, off);
+  const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  __syncthreads();  // scratch may still be read by a previous call
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double total = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < kThreads / kWarp; ++w) total = total + scratch[w];
+  }
+  return total;  // valid in thread 0
+}
+
+template <int kThreads>
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* scratch) {
+#pragma unroll
+  for (int off = kWarp / 2; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_down_sync(0xffffffffu, v, off);
+    v = o > v ? o : v;
+  }
+  const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  unsigned long long m = 0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < kThreads / kWarp; ++w) m = scratch[w] > m ? scratch[w] : m;
+  }
+  return m;
+}
+
+/// Positive finite weights order like their bit patterns; anything else counts as 0.
+__device__ __forceinline__ unsigned long long weight_order_bits(double w) {
+  return (w > 0.0 && w <= DBL_MAX) ? static_cast<unsigned long long>(__double_as_longlong(w)) : 0ull;
+}
+
+// ---- TMA 1-D bulk copy of the scan points into shared memory ------------------------------------
+
+__device__ __forceinline__ void mbarrier_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarrier_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbarrier_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+               "l"(src_global), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbarrier_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "BB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra BB_DONE;\n"
+      "bra BB_WAIT;\n"
+      "BB_DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---- begin_step ----------------------------------------------------------------------------------
+
+__global__ void begin_step_kernel(Scalars* s) {
+  s->wmax_bits = 0;
+  s->tile_ticket = 0;
+  s->total = 0;
+  s->exponent = 0;
+  s->valid = 0;
+  s->kld_cutoff = ~0ull;
+}
+
+// ---- initialize_normal (a16) ---------------------------------------------------------------------
+// MultivariateNormalDistribution<SE2d>: (x, y, theta) = mean + T * delta, SE2(exp(theta), (x, y))
+// (random/multivariate_normal_distribution.hpp:96-103, multivariate_distribution_traits.hpp:110-112).
+
+struct NormalInit {
+  double mean[3];
+  double t[9];
+};
+
+__global__ void __launch_bounds__(256) initialize_normal_kernel(Pose2* states, double* weights, uint64_t n, NormalInit p, uint64_t seed,
+                                                                uint64_t first_index) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double d0, d1, d2, unused;
+  box_muller(counter_draw(seed, first_index + i, 0, kStreamInit0), d0, d1);
+  box_muller(counter_draw(seed, first_index + i, 0, kStreamInit1), d2, unused);
+  double v[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) v[r] = p.mean[r] + (p.t[3 * r + 0] * d0 + p.t[3 * r + 1] * d1 + p.t[3 * r + 2] * d2);
+  const Rot2 r = rot_exp(v[2]);
+  states[i] = Pose2{r.c, r.s, v[0], v[1]};
+  weights[i] = 1.0;
+}
+
+// ---- propagate | reweight (likelihood field) ---------------------------------------------------
+
+constexpr int kPrThreads = 512;        // 2 CTAs per SM at <= 64 registers
+constexpr uint32_t kChunkBeams = 2048; // beams staged per shared-memory chunk (32 KB), multiple of 4
+
+__device__ __forceinline__ Pose2 load_pose(const Pose2* p) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+  return Pose2{a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ void store_pose(Pose2* p, const Pose2& v) {
+  *reinterpret_cast<double2*>(p) = make_double2(v.c, v.s);
+  *(reinterpret_cast<double2*>(p) + 1) = make_double2(v.x, v.y);
+}
+
+__device__ __forceinline__ Pose2 propagate_one(const Pose2& st, const DiffDriveSampling& p, uint64_t seed, uint64_t index, uint32_t step) {
+  double z0, z1, z2, unused;
+  box_muller(counter_draw(seed, index, step, kStreamMotion0), z0, z1);
+  box_muller(counter_draw(seed, index, step, kStreamMotion1), z2, unused);
+  // std::normal_distribution: ret * stddev + mean (libstdc++ bits/random.tcc:1843)
+  const double rot1 = z0 * p.rot1_std + p.rot1_mean;
+  const double trans = z1 * p.trans_std + p.trans_mean;
+  const double rot2 = z2 * p.rot2_std + p.rot2_mean;
+  return diff_drive_apply(st, rot1, trans, rot2);
+}
+
+/// floor(g) as int32 for |g| < 2^31 through one round-down add: g + 1.5*2^52 has ulp 1, so the low
+/// mantissa word of the sum is floor(g) in two's complement.
+__device__ __forceinline__ int floor_to_int_fast(double g) { return __double2loint(__dadd_rd(g, 6755399441055744.0)); }
+
+template <bool kFast>
+__device__ __forceinline__ double field_lookup(const FieldView& f, double px, double py, double c, double s, double tx, double ty) {
+  // likelihood_field_model.hpp:82-83 -- two products, one difference/sum, one offset; each rounded.
+  const double x = (px * c - py * s) + tx;
+  const double y = (px * s + py * c) + ty;
+  // regular_grid.hpp:75-78 -- floor(p * inv_resolution) cast to int.
+  const double gx = x * f.inv_resolution;
+  const double gy = y * f.inv_resolution;
+  int xi, yi;
+  if (kFast) {
+    xi = floor_to_int_fast(gx);
+    yi = floor_to_int_fast(gy);
+  } else {
+    // General path: saturating conversion; non-finite coordinates fall outside the grid.
+    const double fx = floor(gx), fy = floor(gy);
+    xi = (fx >= 0.0 && fx < 2147483647.0) ? static_cast<int>(fx) : -1;
+    yi = (fy >= 0.0 && fy < 2147483647.0) ? static_cast<int>(fy) : -1;
+  }
+  // dense_grid.hpp:92-96 contains(); linear_grid.hpp:73-75 index_at().
+  const bool inside = static_cast<unsigned>(xi) < static_cast<unsigned>(f.width) && static_cast<unsigned>(yi) < static_cast<unsigned>(f.height);
+  double v = f.unknown_value;
+  if (inside) v = __ldg(f.table + (static_cast<size_t>(yi) * static_cast<size_t>(f.width) + static_cast<size_t>(xi)));
+  return v;
+}
+
+template <bool kFast>
+__device__ __forceinline__ double accumulate_chunk(const FieldView& f, const double2* pts, uint32_t count, double acc, double c, double s,
+                                                   double tx, double ty) {
+  // libstdc++ std::transform_reduce (numeric:439-462): groups of four, init += ((f0+f1)+(f2+f3)).
+  uint32_t b = 0;
+#pragma unroll 2
+  for (; b + 4 <= count; b += 4) {
+    const double2 p0 = pts[b], p1 = pts[b + 1], p2 = pts[b + 2], p3 = pts[b + 3];
+    const double f0 = field_lookup<kFast>(f, p0.x, p0.y, c, s, tx, ty);
+    const double f1 = field_lookup<kFast>(f, p1.x, p1.y, c, s, tx, ty);
+    const double f2 = field_lookup<kFast>(f, p2.x, p2.y, c, s, tx, ty);
+    const double f3 = field_lookup<kFast>(f, p3.x, p3.y, c, s, tx, ty);
+    acc = acc + ((f0 + f1) + (f2 + f3));
+  }
+  for (; b < count; ++b) acc = acc + field_lookup<kFast>(f, pts[b].x, pts[b].y, c, s, tx, ty);
+  return acc;
+}
+
+__global__ void __launch_bounds__(kPrThreads, 2)
+    propagate_reweight_lfm_kernel(Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, int do_propagate,
+                                  DiffDriveSampling sampling, uint64_t seed, uint32_t step, uint64_t first_index, int do_reweight,
+                                  FieldView field, const double2* __restrict__ points, uint32_t n_points, double points_radius,
+                                  Scalars* __restrict__ scalars) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* s_pts = reinterpret_cast<double2*>(smem_raw);
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ unsigned long long s_red[kPrThreads / kWarp];
+
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kPrThreads + threadIdx.x;
+  const bool active = i < n;
+
+  if (do_reweight && threadIdx.x == 0) {
+    mbarrier_init(&s_bar, 1);
+    mbarrier_init_fence();
+  }
+
+  Pose2 st{1.0, 0.0, 0.0, 0.0};
+  double w = 0.0;
+  if (active) {
+    st = load_pose(states + i);
+    w = weights[i];
+    if (do_propagate) {
+      st = propagate_one(st, sampling, seed, first_index + i, step);
+      store_pose(states + i, st);
+    }
+  }
+
+  if (do_reweight) {
+    // transform = world_to_likelihood_field * state (likelihood_field_model.hpp:70-74)
+    const Pose2 t = pose_mul(field.world_to_field, st);
+    // Fast floor is exact while every |coordinate * inv_resolution| stays below 2^30.
+    const double reach = (points_radius + fmax(fabs(t.x), fabs(t.y))) * field.inv_resolution;
+    const bool fast = reach < 1073741824.0;  // false for NaN
+    double acc = field.init;
+    uint32_t phase = 0;
+    __syncthreads();  // barrier initialised
+    for (uint32_t base = 0; base < n_points; base += kChunkBeams) {
+      const uint32_t count = min(kChunkBeams, n_points - base);
+      if (threadIdx.x == 0) {
+        const uint32_t bytes = count * static_cast<uint32_t>(sizeof(double2));
+        mbarrier_expect_tx(&s_bar, bytes);
+        bulk_copy_g2s(s_pts, points + base, bytes, &s_bar);
+      }
+      mbarrier_wait(&s_bar, phase);
+      phase ^= 1u;
+      if (active) {
+        acc = fast ? accumulate_chunk<true>(field, s_pts, count, acc, t.c, t.s, t.x, t.y)
+                   : accumulate_chunk<false>(field, s_pts, count, acc, t.c, t.s, t.x, t.y);
+      }
+      __syncthreads();  // everyone is done with s_pts before the next chunk overwrites it
+    }
+    if (active) {
+      const double likelihood = field.exp_epilogue ? exp(acc) : acc;
+      w = w * likelihood;  // actions/reweight.hpp:54-60
+      weights[i] = w;
+    }
+  }
+
+  const unsigned long long m = block_max_u64<kPrThreads>(active ? weight_order_bits(w) : 0ull, s_red);
+  if (threadIdx.x == 0 && m != 0) atomicMax(&scalars->wmax_bits, m);
+}
+
+
+// ---- propagate | reweight (beam model) -----------------------------------------------------------
+// BeamSensorModel (sensor/beam_model.hpp:104-150): one thread per particle, beams in the inner
+// loop, so the lanes of a warp (neighbouring particles, same beam) walk rays of similar length.
+// Ray casting is Ray2d::cast (algorithm/raycasting.hpp:79-107) over the standard Bresenham2i
+// iterator (algorithm/raycasting/bresenham.hpp:84-160) on the int8 occupancy grid.
+
+struct BeamRay {
+  double far_x, far_y;  // bearing.unit_complex() * max_range  (raycasting.hpp:83)
+  double z;             // measured range (beam_model.hpp:116)
+};
+
+__device__ __forceinline__ int cell_near(double p, double inv_resolution) { return static_cast<int>(floor(p * inv_resolution)); }
+
+/// Distance in metres from the source cell centroid to the first non-free cell, or -1 on a miss.
+__device__ __forceinline__ double cast_ray(const OccupancyView& g, int sx, int sy, int fx, int fy, double max_range) {
+  int xspan = fx - sx, xstep = 1;
+  if (xspan < 0) {
+    xspan = -xspan;
+    xstep = -1;
+  }
+  int yspan = fy - sy, ystep = 1;
+  if (yspan < 0) {
+    yspan = -yspan;
+    ystep = -1;
+  }
+  int x = sx, y = sy;
+  bool reversed = false;
+  if (xspan < yspan) {  // iterate along the longer axis (bresenham.hpp:99-105)
+    int t = x; x = y; y = t;
+    t = xspan; xspan = yspan; yspan = t;
+    t = xstep; xstep = ystep; ystep = t;
+    reversed = true;
+  }
+  const int dxspan = 2 * xspan, dyspan = 2 * yspan;
+  int error = xspan;
+  for (int step = 0; step <= xspan; ++step) {
+    const int cx = reversed ? y : x, cy = reversed ? x : y;
+    if (!(static_cast<unsigned>(cx) < static_cast<unsigned>(g.width) && static_cast<unsigned>(cy) < static_cast<unsigned>(g.height)))
+      return -1.0;  // take_while(cell_is_valid), raycasting.hpp:86-87
+    if (__ldg(g.cells + (static_cast<size_t>(cy) * static_cast<size_t>(g.width) + static_cast<size_t>(cx))) != 0) {  // !free_at
+      const double dxm = (static_cast<double>(cx) + 0.5) * g.resolution - (static_cast<double>(sx) + 0.5) * g.resolution;
+      const double dym = (static_cast<double>(cy) + 0.5) * g.resolution - (static_cast<double>(sy) + 0.5) * g.resolution;
+      return fmin(sqrt(dxm * dxm + dym * dym), max_range);
+    }
+    x += xstep;
+    error += dyspan;
+    if (error > dxspan) {
+      y += ystep;
+      error -= dxspan;
+    }
+  }
+  return -1.0;
+}
+
+__device__ __forceinline__ double beam_pz3(const BeamParams& p, double z, double z_mean, double n) {
+  const double sqrt2 = sqrt(2.);
+  const double eta_hit = 2. / (erf((p.beam_max_range - z_mean) / (sqrt2 * p.sigma_hit)) - erf(-z_mean / (sqrt2 * p.sigma_hit)));
+  const double d = (z - z_mean) / p.sigma_hit;
+  double pz = p.z_hit * eta_hit * n * exp(-(d * d) / 2.);
+  if (z < z_mean) {
+    const double eta_short = 1. / (1. - exp(-p.lambda_short * z_mean));
+    pz += p.z_short * p.lambda_short * eta_short * exp(-p.lambda_short * z);
+  }
+  if (z < p.beam_max_range) {
+    pz += p.z_rand / p.beam_max_range;
+  } else {
+    pz += p.z_max;
+  }
+  return pz * pz * pz;
+}
+
+constexpr int kBeamThreads = 256;
+constexpr uint32_t kBeamChunk = 1024;  // rays staged per shared-memory chunk (24 KB), multiple of 4
+
+__global__ void __launch_bounds__(kBeamThreads)
+    propagate_reweight_beam_kernel(Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, int do_propagate,
+                                   DiffDriveSampling sampling, uint64_t seed, uint32_t step, uint64_t first_index, OccupancyView grid,
+                                   BeamParams params, const double2* __restrict__ points, uint32_t n_points, Scalars* __restrict__ scalars) {
+  __shared__ BeamRay s_rays[kBeamChunk];
+  __shared__ unsigned long long s_red[kBeamThreads / kWarp];
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kBeamThreads + threadIdx.x;
+  const bool active = i < n;
+
+  Pose2 st{1.0, 0.0, 0.0, 0.0};
+  double w = 0.0;
+  if (active) {
+    st = load_pose(states + i);
+    w = weights[i];
+    if (do_propagate) {
+      st = propagate_one(st, sampling, seed, first_index + i, step);
+      store_pose(states + i, st);
+    }
+  }
+  // Ray2d: source pose in the grid frame and its cell (raycasting.hpp:67-70).
+  const Pose2 src = pose_mul(grid.world_to_grid, st);
+  const int sx = cell_near(src.x, grid.inv_resolution), sy = cell_near(src.y, grid.inv_resolution);
+  const double n_norm = 1. / (sqrt(2. * 3.14159265358979323846) * params.sigma_hit);  // beam_model.hpp:107
+
+  auto one_beam = [&](const BeamRay& ray) {
+    // far end = r1 * t2 + t1 (raycasting.hpp:81-85)
+    const double ex = (src.c * ray.far_x - src.s * ray.far_y) + src.x;
+    const double ey = (src.s * ray.far_x + src.c * ray.far_y) + src.y;
+    const int fx = cell_near(ex, grid.inv_resolution), fy = cell_near(ey, grid.inv_resolution);
+    const double hit = cast_ray(grid, sx, sy, fx, fy, params.beam_max_range);
+    const double z_mean = hit >= 0.0 ? hit : params.beam_max_range;  // value_or(beam_max_range)
+    return beam_pz3(params, ray.z, z_mean, n_norm);
+  };
+
+  double acc = 0.0;
+  for (uint32_t base = 0; base < n_points; base += kBeamChunk) {
+    const uint32_t count = min(kBeamChunk, n_points - base);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < count; b += kBeamThreads) {
+      const double2 p = points[base + b];
+      const double z = sqrt(p.x * p.x + p.y * p.y);                      // beam_model.hpp:116
+      const double bx = p.x / z, by = p.y / z;                            // :120-123
+      s_rays[b] = BeamRay{bx * params.beam_max_range, by * params.beam_max_range, z};
+    }
+    __syncthreads();
+    if (active) {
+      uint32_t b = 0;
+      for (; b + 4 <= count; b += 4) {  // transform_reduce grouping (numeric:439-462)
+        const double f0 = one_beam(s_rays[b]), f1 = one_beam(s_rays[b + 1]), f2 = one_beam(s_rays[b + 2]), f3 = one_beam(s_rays[b + 3]);
+        acc = acc + ((f0 + f1) + (f2 + f3));
+      }
+      for (; b < count; ++b) acc = acc + one_beam(s_rays[b]);
+    }
+  }
+  if (active) {
+    w = w * acc;
+    weights[i] = w;
+  }
+  const unsigned long long m = block_max_u64<kBeamThreads>(active ? weight_order_bits(w) : 0ull, s_red);
+  if (threadIdx.x == 0 && m != 0) atomicMax(&scalars->wmax_bits, m);
+}
+
+__global__ void __launch_bounds__(512) max_weight_kernel(const double* __restrict__ weights, uint64_t n, Scalars* scalars) {
+  __shared__ unsigned long long s_red[512 / kWarp];
+  unsigned long long m = 0;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * 512 + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * 512) {
+    const unsigned long long b = weight_order_bits(weights[i]);
+    m = b > m ? b : m;
+  }
+  m = block_max_u64<512>(m, s_red);
+  if (threadIdx.x == 0 && m != 0) atomicMax(&scalars->wmax_bits, m);
+}
+
+// ---- fixed-point CDF ------------------------------------------------------------------------------
+// q_i = floor(w_i * 2^e) with e chosen so that the largest weight lands in [2^(P-1), 2^P),
+// P = min(52, 62 - ceil(log2(N_global))): the total stays below 2^62 and integer addition is
+// associative, so the CDF is identical for any scan order, tile size or number of ranks.
+
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 4;
+constexpr uint32_t kScanTile = kScanThreads * kScanItems;
+// tile_state word: [63:62] flag (0 empty, 1 aggregate, 2 inclusive prefix), [61:0] value
+constexpr unsigned long long kFlagAggregate = 1ull << 62, kFlagPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1;
+
+__global__ void prepare_cdf_kernel(Scalars* s, double host_wmax, int ceil_log2_count, unsigned long long* tile_state, uint32_t n_tiles) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) tile_state[t] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double wmax = host_wmax >= 0.0 ? host_wmax : __longlong_as_double(static_cast<long long>(s->wmax_bits));
+    int ex = 0;
+    const bool ok = wmax > 0.0 && wmax <= DBL_MAX;
+    if (ok) (void)frexp(wmax, &ex);
+    const int p = min(52, 62 - ceil_log2_count);
+    s->exponent = p - ex;
+    s->valid = ok ? 1 : 0;
+    s->tile_ticket = 0;
+    s->total = 0;
+  }
+}
+
+__device__ __forceinline__ unsigned long long quantize(double w, int exponent) {
+  const double scaled = scalbn(w, exponent);
+  return scaled > 0.0 ? __double2ull_rd(scaled) : 0ull;  // zero / negative / NaN weights are never selected
+}
+
+/// Inclusive scan of per-thread totals across the block (warp shuffles + one smem hop).
+__device__ __forceinline__ unsigned long long block_inclusive_scan_u64(unsigned long long v, unsigned long long* warp_sums,
+                                                                        unsigned long long& block_total) {
+  const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
+#pragma unroll
+  for (int off = 1; off < kWarp; off <<= 1) {
+    const unsigned long long o = __shfl_up_sync(0xffffffffu, v, off);
+    if (lane >= off) v += o;
+  }
+  if (lane == kWarp - 1) warp_sums[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long ws = lane < kScanThreads / kWarp ? warp_sums[lane] : 0ull;
+#pragma unroll
+    for (int off = 1; off < kWarp; off <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, ws, off);
+      if (lane >= off) ws += o;
+    }
+    if (lane < kScanThreads / kWarp) warp_sums[lane] = ws;
+  }
+  __syncthreads();
+  block_total = warp_sums[kScanThreads / kWarp - 1];
+  return v + (warp > 0 ? warp_sums[warp - 1] : 0ull);
+}
+
+/// Decoupled look-back: returns the exclusive prefix of this tile and publishes its inclusive one.
+__device__ __forceinline__ unsigned long long lookback_exclusive_prefix(unsigned long long* tile_state, uint32_t tile,
+                                                                         unsigned long long tile_total, unsigned long long* s_prefix) {
+  if (threadIdx.x == 0) {
+    unsigned long long exclusive = 0;
+    if (tile == 0) {
+      atomicExch(&tile_state[0], kFlagPrefix | tile_total);
+    } else {
+      atomicExch(&tile_state[tile], kFlagAggregate | tile_total);
+      int32_t look = static_cast<int32_t>(tile) - 1;
+      while (true) {
+        unsigned long long word;
+        do {
+          word = *reinterpret_cast<volatile unsigned long long*>(&tile_state[look]);
+        } while ((word >> 62) == 0);
+        exclusive += word & kValueMask;
+        if ((word >> 62) == 2) break;
+        --look;
+      }
+      atomicExch(&tile_state[tile], kFlagPrefix | (exclusive + tile_total));
+    }
+    *s_prefix = exclusive;
+  }
+  __syncthreads();
+  return *s_prefix;
+}
+
+__global__ void __launch_bounds__(kScanThreads) quantize_scan_kernel(const double* __restrict__ weights, uint64_t n,
+                                                                     unsigned long long* __restrict__ cdf, Scalars* scalars,
+                                                                     unsigned long long* tile_state) {
+  __shared__ unsigned long long s_warp[kScanThreads / kWarp];
+  __shared__ unsigned long long s_prefix;
+  __shared__ uint32_t s_tile;
+  if (threadIdx.x == 0) s_tile = static_cast<uint32_t>(atomicAdd(&scalars->tile_ticket, 1ull));
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int exponent = scalars->exponent;
+  const bool valid = scalars->valid != 0;
+
+  const uint64_t base = static_cast<uint64_t>(tile) * kScanTile + static_cast<uint64_t>(threadIdx.x) * kScanItems;
+  unsigned long long q[kScanItems];
+  unsigned long long local = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint64_t idx = base + k;
+    // Degenerate weight set (no positive finite weight): fall back to a uniform CDF.
+    q[k] = idx < n ? (valid ? quantize(weights[idx], exponent) : (1ull << 20)) : 0ull;
+    local += q[k];
+  }
+  unsigned long long tile_total;
+  const unsigned long long inclusive = block_inclusive_scan_u64(local, s_warp, tile_total);
+  const unsigned long long prefix = lookback_exclusive_prefix(tile_state, tile, tile_total, &s_prefix);
+  unsigned long long running = prefix + inclusive - local;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint64_t idx = base + k;
+    running += q[k];
+    if (idx < n) cdf[idx] = running;
+  }
+  if (base <= n - 1 && n - 1 < base + kScanItems) scalars->total = prefix + inclusive;  // thread holding the last element
+}
+
+// ---- normalize -------------------------------------------------------------------------------------
+
+constexpr int kStreamThreads = 256;
+
+__global__ void __launch_bounds__(kStreamThreads) normalize_kernel(double* __restrict__ weights, uint64_t n, const Scalars* scalars,
+                                                                   unsigned long long global_total, double* __restrict__ partials) {
+  __shared__ double s_red[kStreamThreads / kWarp];
+  // S = T * 2^-e: the normalisation factor derived from the exact integer total.
+  const unsigned long long t = global_total != 0 ? global_total : scalars->total;  // 0: single GPU, total is on the device
+  const double factor = scalbn(static_cast<double>(t), -scalars->exponent);
+  const bool valid = scalars->valid != 0 && factor > 0.0;
+  double sq = 0.0;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kStreamThreads + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * kStreamThreads) {
+    double w = weights[i];
+    if (valid) {
+      w = w / factor;  // actions/normalize.hpp:82
+      weights[i] = w;
+    }
+    sq = sq + w * w;
+  }
+  const double total = block_sum<kStreamThreads>(sq, s_red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
+// ---- resample -------------------------------------------------------------------------------------
+
+constexpr int kRsThreads = 256;
+
+/// Smallest i in [0, n) with cdf[i] > t.
+__device__ __forceinline__ uint64_t cdf_upper_bound(const unsigned long long* __restrict__ cdf, uint64_t n, unsigned long long t) {
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint64_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(cdf + mid) > t) {
+      hi = mid;
+    } else {
+      lo = mid + 1;
+    }
+  }
+  return lo < n ? lo : n - 1;  // unreachable clamp (t < total by construction)
+}
+
+__device__ __forceinline__ void accumulate_moments(double* m, const Pose2& st, double w, double px, double py) {
+  const double dx = st.x - px, dy = st.y - py;
+  m[0] += w;
+  m[1] += w * w;
+  m[2] += w * st.c;
+  m[3] += w * st.s;
+  m[4] += w * dx;
+  m[5] += w * dy;
+  m[6] += w * dx * dx;
+  m[7] += w * dx * dy;
+  m[8] += w * dy * dy;
+}
+
+template <int kThreads>
+__device__ __forceinline__ void store_block_moments(double* m, double* scratch, double* __restrict__ partials_row) {
+#pragma unroll
+  for (int k = 0; k < kMomentCount; ++k) {
+    const double total = block_sum<kThreads>(m[k], scratch);
+    if (threadIdx.x == 0) partials_row[k] = total;
+  }
+}
+
+__global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, const Scalars* __restrict__ scalars, double* __restrict__ moment_partials) {
+  __shared__ double s_red[kRsThreads / kWarp];
+  const unsigned long long total = scalars->total;
+  unsigned long long stride = 0, offset = 0;
+  if (a.scheme == 1) {
+    // Systematic comb: stride = T / M, offset uniform in [0, stride).
+    stride = total / a.total_slots;
+    offset = mulhi64(counter_draw(a.seed, 0, a.step, kStreamSystematic).a, stride);
+  }
+  double m[kMomentCount];
+#pragma unroll
+  for (int k = 0; k < kMomentCount; ++k) m[k] = 0.0;
+
+  for (uint64_t local = static_cast<uint64_t>(blockIdx.x) * kRsThreads + threadIdx.x; local < a.slot_count;
+       local += static_cast<uint64_t>(gridDim.x) * kRsThreads) {
+    const uint64_t j = a.slot_first + local;
+    Pose2 st;
+    long long ancestor = -1;
+    bool inject = false;
+    Draw d{0, 0};
+    if (a.random_state_probability > 0.0 || a.scheme == 0) d = counter_draw(a.seed, j, a.step, kStreamResample);
+    if (a.random_state_probability > 0.0) inject = uniform01(d.a) < a.random_state_probability;  // random_intersperse.hpp:93-100
+    if (inject) {
+      // MultivariateUniformDistribution<SE2d, OccupancyGrid> (multivariate_uniform_distribution.hpp:143-160)
+      const Draw r = counter_draw(a.seed, j, a.step, kStreamRandomState);
+      const uint32_t cell = a.free_cells[mulhi64(r.a, a.n_free)];
+      const double pi = 3.14159265358979323846;
+      const double yaw = uniform01(r.b) * (pi - (-pi)) + (-pi);
+      const double lx = (static_cast<double>(static_cast<int>(cell % static_cast<uint32_t>(a.grid_width))) + 0.5) * a.grid_resolution;
+      const double ly = (static_cast<double>(static_cast<int>(cell / static_cast<uint32_t>(a.grid_width))) + 0.5) * a.grid_resolution;
+      const Rot2 rot = rot_exp(yaw);
+      st = Pose2{rot.c, rot.s, (a.grid_origin.c * lx - a.grid_origin.s * ly) + a.grid_origin.x,
+                 (a.grid_origin.s * lx + a.grid_origin.c * ly) + a.grid_origin.y};
+    } else {
+      const unsigned long long t = a.scheme == 1 ? offset + j * stride : mulhi64(d.b, total);
+      const uint64_t idx = cdf_upper_bound(a.cdf, a.n_in, t);
+      ancestor = static_cast<long long>(idx);
+      st = load_pose(a.states_in + idx);
+    }
+    store_pose(a.states_out + local, st);
+    a.weights_out[local] = 1.0;  // make_from_state (particle_traits.hpp:105)
+    if (a.ancestors != nullptr) a.ancestors[local] = ancestor;
+    if (a.hashes != nullptr) a.hashes[local] = spatial_hash(st, a.hash_resolution[0], a.hash_resolution[1], a.hash_resolution[2]);
+    accumulate_moments(m, st, 1.0, a.pivot_x, a.pivot_y);
+  }
+  store_block_moments<kRsThreads>(m, s_red, moment_partials + static_cast<size_t>(blockIdx.x) * kMomentCount);
+}
+
+// ---- moments / reductions -------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kStreamThreads) moments_kernel(const Pose2* __restrict__ states, const double* __restrict__ weights, uint64_t n,
+                                                                 double px, double py, double* __restrict__ moment_partials) {
+  __shared__ double s_red[kStreamThreads / kWarp];
+  double m[kMomentCount];
+#pragma unroll
+  for (int k = 0; k < kMomentCount; ++k) m[k] = 0.0;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kStreamThreads + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * kStreamThreads) {
+    accumulate_moments(m, load_pose(states + i), weights[i], px, py);
+  }
+  store_block_moments<kStreamThreads>(m, s_red, moment_partials + static_cast<size_t>(blockIdx.x) * kMomentCount);
+}
+
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, uint32_t n_partials, int width, double* __restrict__ out) {
+  __shared__ double s_red[256 / kWarp];
+  for (int k = 0; k < width; ++k) {
+    double v = 0.0;
+    for (uint32_t r = threadIdx.x; r < n_partials; r += 256) v = v + partials[static_cast<size_t>(r) * width + k];
+    const double total = block_sum<256>(v, s_red);
+    if (threadIdx.x == 0) out[k] = total;
+  }
+}
+
+int ceil_log2_u64(uint64_t n) {
+  int b = 0;
+  while ((uint64_t{1} << b) < n) ++b;
+  return b;
+}
+
+constexpr uint32_t kStreamMaxBlocks = 148 * 8;
+
+}  // namespace
+
+// ---- launchers -------------------------------------------------------------------------------------
+
+void launch_begin_step(Scalars* scalars, cudaStream_t stream) { begin_step_kernel<<<1, 1, 0, stream>>>(scalars); }
+
+void launch_initialize_normal(Pose2* states, double* weights, uint64_t n, const double mean[3], const double transform[9], uint64_t seed,
+                              uint64_t first_index, cudaStream_t stream) {
+  if (n == 0) return;
+  NormalInit p;
+  for (int i = 0; i < 3; ++i) p.mean[i] = mean[i];
+  for (int i = 0; i < 9; ++i) p.t[i] = transform[i];
+  initialize_normal_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(states, weights, n, p, seed, first_index);
+}
+
+void launch_propagate_reweight_lfm(Pose2* states, double* weights, uint64_t n, bool do_propagate, const DiffDriveSampling& sampling,
+                                   uint64_t seed, uint32_t step, uint64_t first_index, bool do_reweight, const FieldView& field,
+                                   const double* points_xy_device, uint32_t n_points, double points_radius, Scalars* scalars,
+                                   cudaStream_t stream) {
+  if (n == 0) return;
+  const unsigned blocks = static_cast<unsigned>((n + kPrThreads - 1) / kPrThreads);
+  const size_t smem = do_reweight ? static_cast<size_t>(n_points < kChunkBeams ? n_points : kChunkBeams) * sizeof(double2) : 0;
+  propagate_reweight_lfm_kernel<<<blocks, kPrThreads, smem, stream>>>(states, weights, n, do_propagate ? 1 : 0, sampling, seed, step,
+                                                                      first_index, do_reweight ? 1 : 0, field,
+                                                                      reinterpret_cast<const double2*>(points_xy_device), n_points,
+                                                                      points_radius, scalars);
+}
+
+void launch_propagate_reweight_beam(Pose2* states, double* weights, uint64_t n, bool do_propagate, const DiffDriveSampling& sampling,
+                                    uint64_t seed, uint32_t step, uint64_t first_index, const OccupancyView& grid,
+                                    const BeamParams& params, const double* points_xy_device, uint32_t n_points, Scalars* scalars,
+                                    cudaStream_t stream) {
+  if (n == 0) return;
+  const unsigned blocks = static_cast<unsigned>((n + kBeamThreads - 1) / kBeamThreads);
+  propagate_reweight_beam_kernel<<<blocks, kBeamThreads, 0, stream>>>(states, weights, n, do_propagate ? 1 : 0, sampling, seed, step,
+                                                                      first_index, grid, params,
+                                                                      reinterpret_cast<const double2*>(points_xy_device), n_points, scalars);
+}
+
+void launch_max_weight(const double* weights, uint64_t n, Scalars* scalars, cudaStream_t stream) {
+  if (n == 0) return;
+  const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((n + 511) / 512, kStreamMaxBlocks));
+  max_weight_kernel<<<blocks, 512, 0, stream>>>(weights, n, scalars);
+}
+
+uint32_t scan_tile_count(uint64_t n) { return static_cast<uint32_t>((n + kScanTile - 1) / kScanTile); }
+
+void launch_prepare_cdf(Scalars* scalars, double host_wmax, uint64_t global_count, unsigned long long* tile_state, uint32_t n_tiles,
+                        cudaStream_t stream) {
+  const unsigned blocks = std::max(1u, std::min((n_tiles + 255u) / 256u, 64u));
+  prepare_cdf_kernel<<<blocks, 256, 0, stream>>>(scalars, host_wmax, ceil_log2_u64(global_count), tile_state, n_tiles);
+}
+
+void launch_quantize_scan(const double* weights, uint64_t n, unsigned long long* cdf, Scalars* scalars, unsigned long long* tile_state,
+                          cudaStream_t stream) {
+  if (n == 0) return;
+  quantize_scan_kernel<<<scan_tile_count(n), kScanThreads, 0, stream>>>(weights, n, cdf, scalars, tile_state);
+}
+
+void launch_normalize(double* weights, uint64_t n, const Scalars* scalars, unsigned long long global_total, double* partials,
+                      uint32_t* n_partials, cudaStream_t stream) {
+  const unsigned blocks = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>((n + kStreamThreads - 1) / kStreamThreads, kStreamMaxBlocks)));
+  *n_partials = blocks;
+  normalize_kernel<<<blocks, kStreamThreads, 0, stream>>>(weights, n, scalars, global_total, partials);
+}
+
+uint32_t resample_block_count(uint64_t slots) {
+  return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>((slots + kRsThreads - 1) / kRsThreads, 148 * 16)));
+}
+
+void launch_resample(const ResampleArgs& args, const Scalars* scalars, double* moment_partials, cudaStream_t stream) {
+  resample_kernel<<<resample_block_count(args.slot_count), kRsThreads, 0, stream>>>(args, scalars, moment_partials);
+}
+
+uint32_t moments_block_count(uint64_t n) {
+  return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>((n + kStreamThreads - 1) / kStreamThreads, kStreamMaxBlocks)));
+}
+
+void launch_moments(const Pose2* states, const double* weights, uint64_t n, double pivot_x, double pivot_y, double* moment_partials,
+                    cudaStream_t stream) {
+  moments_kernel<<<moments_block_count(n), kStreamThreads, 0, stream>>>(states, weights, n, pivot_x, pivot_y, moment_partials);
+}
+
+void launch_reduce_partials(const double* partials, uint32_t n_partials, int width, double* out, cudaStream_t stream) {
+  reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, n_partials, width, out);
+}
+
+}  // namespace bb200

@@ -1,0 +1,132 @@
+// Kernel launch interface of the B200 MCL backend (see kernels.cu for the kernels themselves).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "se2_math.cuh"
+
+namespace bb200 {
+
+/// Device view of the likelihood-field lookup table (LFM / LFM-prob).
+struct FieldView {
+  const double* table;  // f(pz) per cell, row-major (f = pz^3 or log pz)
+  int width, height;
+  double inv_resolution;  // 1. / resolution  (regular_grid.hpp:76)
+  double unknown_value;   // f(float(1/max_laser_distance)) for out-of-grid end points
+  double init;            // transform_reduce init: 1.0 (LFM) or 0.0 (prob)
+  int exp_epilogue;       // prob model: weight = exp(sum)
+  Pose2 world_to_field;   // grid.origin().inverse()
+};
+
+/// Device view of the occupancy grid (beam model).
+struct OccupancyView {
+  const int8_t* cells;
+  int width, height;
+  double resolution, inv_resolution;
+  Pose2 world_to_grid;  // grid.origin().inverse()
+};
+
+struct BeamParams {
+  double z_hit, z_short, z_max, z_rand, sigma_hit, lambda_short, beam_max_range;
+};
+
+struct DiffDriveSampling {
+  double rot1_mean, rot1_std, trans_mean, trans_std, rot2_mean, rot2_std;
+};
+
+/// Per-filter device scalars (one cache line; zeroed by launch_begin_step).
+struct Scalars {
+  unsigned long long wmax_bits;   // bit pattern of the largest weight (positive doubles order like integers)
+  unsigned long long tile_ticket; // decoupled look-back: next tile id
+  unsigned long long total;       // fixed-point total of the local CDF
+  int exponent;                   // q = floor(w * 2^exponent)
+  int valid;                      // 0 when no positive finite weight exists
+  unsigned long long kld_cutoff;  // first slot (1-based count) at which the KLD condition fails
+  unsigned long long pad[3];
+};
+
+constexpr int kMomentCount = 9;  // sum w, sum w^2, sum w c, sum w s, sum w dx, sum w dy, sum w dx^2, sum w dx dy, sum w dy^2
+
+// ---- launchers (all asynchronous on `stream`) ---------------------------------------------------
+
+void launch_begin_step(Scalars* scalars, cudaStream_t stream);
+
+void launch_initialize_normal(Pose2* states, double* weights, uint64_t n, const double mean[3], const double transform[9],
+                              uint64_t seed, uint64_t first_index, cudaStream_t stream);
+
+/// propagate (optional) | reweight with the likelihood-field table (optional) | block max of weights.
+void launch_propagate_reweight_lfm(Pose2* states, double* weights, uint64_t n, bool do_propagate, const DiffDriveSampling& sampling,
+                                   uint64_t seed, uint32_t step, uint64_t first_index, bool do_reweight, const FieldView& field,
+                                   const double* points_xy_device, uint32_t n_points, double points_radius, Scalars* scalars,
+                                   cudaStream_t stream);
+
+/// propagate (optional) | reweight with the beam model (Bresenham ray casting) | block max.
+void launch_propagate_reweight_beam(Pose2* states, double* weights, uint64_t n, bool do_propagate, const DiffDriveSampling& sampling,
+                                    uint64_t seed, uint32_t step, uint64_t first_index, const OccupancyView& grid,
+                                    const BeamParams& params, const double* points_xy_device, uint32_t n_points, Scalars* scalars,
+                                    cudaStream_t stream);
+
+/// Largest weight only (when propagate/reweight ran separately or particles were set by hand).
+void launch_max_weight(const double* weights, uint64_t n, Scalars* scalars, cudaStream_t stream);
+
+/// Sets scalars->exponent from wmax (device value when host_wmax < 0) and resets the scan state.
+void launch_prepare_cdf(Scalars* scalars, double host_wmax, uint64_t global_count, unsigned long long* tile_state, uint32_t n_tiles,
+                        cudaStream_t stream);
+uint32_t scan_tile_count(uint64_t n);
+/// Fixed-point quantisation + single-pass inclusive scan (decoupled look-back).
+void launch_quantize_scan(const double* weights, uint64_t n, unsigned long long* cdf, Scalars* scalars, unsigned long long* tile_state,
+                          cudaStream_t stream);
+
+/// w /= S (S = global_total * 2^-exponent) and per-block partial sums of (w/S)^2.
+void launch_normalize(double* weights, uint64_t n, const Scalars* scalars, unsigned long long global_total, double* partials,
+                      uint32_t* n_partials, cudaStream_t stream);
+
+struct ResampleArgs {
+  const Pose2* states_in;
+  const unsigned long long* cdf;
+  uint64_t n_in;
+  Pose2* states_out;
+  double* weights_out;
+  long long* ancestors;  // nullable
+  unsigned long long* hashes;  // nullable (KLD)
+  uint64_t slot_first;    // global index of local output slot 0
+  uint64_t slot_count;    // local output slots
+  uint64_t total_slots;   // M: the comb of systematic resampling spans all global slots
+  int scheme;
+  uint64_t seed;
+  uint32_t step;
+  double random_state_probability;
+  const uint32_t* free_cells;
+  uint64_t n_free;
+  int grid_width;
+  double grid_resolution;
+  Pose2 grid_origin;
+  double hash_resolution[3];
+  double pivot_x, pivot_y;
+};
+uint32_t resample_block_count(uint64_t slots);
+/// sample | random_intersperse | (hash) | assign, plus per-block raw moments of the new set.
+void launch_resample(const ResampleArgs& args, const Scalars* scalars, double* moment_partials, cudaStream_t stream);
+
+/// Per-block raw weighted moments of (states, weights).
+uint32_t moments_block_count(uint64_t n);
+void launch_moments(const Pose2* states, const double* weights, uint64_t n, double pivot_x, double pivot_y, double* moment_partials,
+                    cudaStream_t stream);
+/// Sums `n_partials` rows of kMomentCount doubles in a fixed order into out[kMomentCount].
+void launch_reduce_partials(const double* partials, uint32_t n_partials, int width, double* out, cudaStream_t stream);
+
+/// KLD: first-occurrence flags through a device hash set, prefix count, first failing slot.
+struct KldArgs {
+  const unsigned long long* hashes;
+  uint64_t n;            // slots examined
+  uint64_t count_offset; // slots accepted before this chunk
+  uint64_t min_particles;
+  double epsilon, z;
+};
+void launch_kld_cutoff(const KldArgs& args, unsigned long long* table_keys, unsigned int* table_vals, uint64_t table_size,
+                       unsigned int* first_flags, unsigned long long* flag_scan, Scalars* scalars, unsigned long long* tile_state,
+                       cudaStream_t stream);
+
+}  // namespace bb200

@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- MCL filter-steps/s on the BASELINE.json configuration.
+
+    python bench.py --gpus N --steps K --warmup W            # this backend (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on the host cores
+
+A "step" is one beluga::Amcl::update (amcl_core.hpp:165-201) on one scan of the synthetic
+trajectory: diff-drive propagate -> likelihood-field reweight -> normalize -> systematic resample
+-> estimate.  Workload (BASELINE.json configs[1]): 1M particles x 1080 beams, 2000x2000 grid.
+
+Reported (one JSON line on stdout, rank 0):
+  value      steps/s from the device time of the step's kernels (CUDA events on the launching
+             stream; scan points already in HBM when the first event is recorded)
+  e2e        steps/s through the C-ABI call bb200_amcl_update with HOST buffers: per step the scan
+             (H2D from pinned staging) goes in and the pose estimate comes back, host clock around it
+  roofline   the dominant kernel (propagate_reweight_lfm) against the measured HBM copy peak
+  cpu_baseline  the CPU oracle (a port of the reference pipeline; the reference itself needs
+             Eigen/Sophus/range-v3, absent here) on the host cores, bounded sample, same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MCL filter-steps/sec at 1M particles x 1080 beams (likelihood field, 2000x2000 grid, systematic resample)"
+UNIT = "steps/s"
+MOTION = (0.1, 0.05, 0.1, 0.05)  # likelihood_params.yaml:6-12
+LFM = dict(max_obstacle_distance=2.0, max_laser_distance=100.0, z_hit=0.5, z_random=0.5, sigma_hit=0.2)  # :55-65
+PATH_STEPS = 100
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU (weak scaling)")
+    ap.add_argument("--beams", type=int, default=1080)
+    ap.add_argument("--grid", type=int, default=2000)
+    ap.add_argument("--cpu-sample", type=int, default=50_000, help="particles in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_workload(args):
+    from beluga_b200 import synthetic
+
+    return synthetic.make_scenario(grid_size=args.grid, n_beams=args.beams, steps=PATH_STEPS)
+
+
+def workload_name(args, n_total):
+    return f"{n_total} particles x {args.beams}-beam LikelihoodFieldModel, {args.grid}x{args.grid} grid @0.05 m, diff-drive + systematic resample"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.device)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=5)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_steps_per_s(args, scenario, n_full, sample_particles, steps=3):
+    """The reference algorithm (oracle port, counter-RNG mode, propagate/reweight/normalize threaded
+    like std::execution::par) on a bounded sample; linear extrapolation to the full particle count."""
+    from oracle import pyoracle as orc
+
+    threads = os.cpu_count() or 1
+    n = min(sample_particles, n_full)
+    o = orc.Amcl(orc.AmclParam(min_particles=n, max_particles=n, scheme=orc.SYSTEMATIC, seed=1, rng_mode=1, threads=threads),
+                 orc.MotionParam(*MOTION))
+    o.set_map(orc.LFM, orc.LfmParam(**LFM), orc.Grid(scenario.cells, scenario.resolution))
+    o.initialize_normal(scenario.initial_mean, scenario.initial_cov)
+    o.update(orc.se2(*scenario.poses[0]), scenario.scans[0])  # warm-up
+    t0 = time.perf_counter()
+    for k in range(1, steps + 1):
+        o.update(orc.se2(*scenario.poses[k]), scenario.scans[k])
+    dt = (time.perf_counter() - t0) / steps
+    full_step_s = dt * (n_full / n)
+    return {
+        "value": 1.0 / full_step_s, "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": f"{steps} steps of {n} particles x {args.beams} beams on the same map/scans, {dt * 1e3:.1f} ms/step, scaled x{n_full / n:.0f} to {n_full} particles",
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scenario = make_workload(args)
+    n_total = args.particles * args.gpus
+    base = cpu_reference_steps_per_s(args, scenario, n_total, args.cpu_sample, steps=max(1, min(args.steps, 5)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, n_total), "particles_per_gpu": args.particles, "parallelism": f"cpu-omp{base['cores']}"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args):
+    import torch
+
+    import beluga_b200 as bb
+    from beluga_b200 import build as bb_build
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        bb_build.build()
+    if world > 1:
+        dist.barrier()
+    if bb.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device (the backend has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+
+    scenario = make_workload(args)
+    n = args.particles
+    n_total = n * world
+    # Independent shards: rank r owns global particles [r*n, (r+1)*n) of one filter (weak scaling).
+    params = bb.AmclParams(min_particles=n, max_particles=n, resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=1, device=local_rank)
+    amcl = bb.Amcl(bb.DifferentialDriveModelParam(*MOTION), params)
+    amcl.update_map(bb.SENSOR_LIKELIHOOD_FIELD, bb.LikelihoodFieldModelParam(**LFM), bb.OccupancyGrid(scenario.cells, scenario.resolution))
+    amcl.initialize(scenario.initial_mean, scenario.initial_cov)
+    amcl.filter.set_timing(True)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > L2 (126 MB)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    poses = [bb.se2(*scenario.poses[k % PATH_STEPS]) for k in range(args.warmup + args.steps + 1)]
+    scans = [np.ascontiguousarray(scenario.scans[k % PATH_STEPS]) for k in range(args.warmup + args.steps + 1)]
+    for k in range(args.warmup):
+        r = amcl.update(poses[k], scans[k])
+        assert r.updated == 1
+
+    launches0 = amcl.filter.launch_count()
+    device_ms, wall_ms, kernel_ms = [], [], {}
+    sync_all()
+    with ClockSampler(local_rank) as clocks:
+        for k in range(args.warmup, args.warmup + args.steps):
+            flush.zero_()  # evict L2 between timed steps
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = amcl.update(poses[k], scans[k])  # synchronous: the estimate is read back inside
+            wall_ms.append((time.perf_counter() - t0) * 1e3)
+            assert r.updated == 1 and r.resampled == 1
+            step_kernels = amcl.filter.last_timings()
+            device_ms.append(sum(ms for _, ms in step_kernels))
+            for name, ms in step_kernels:
+                kernel_ms.setdefault(name, []).append(ms)
+        sync_all()
+    launches = amcl.filter.launch_count() - launches0
+
+    dev_total = torch.tensor([sum(device_ms), sum(wall_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dev_total, op=dist.ReduceOp.MAX)  # max over ranks
+    dev_total_ms, wall_total_ms = dev_total.tolist()
+
+    if rank == 0:
+        est = r.estimate
+        err = float(np.hypot(est.mean[2] - scenario.poses[(args.warmup + args.steps - 1) % PATH_STEPS][0],
+                             est.mean[3] - scenario.poses[(args.warmup + args.steps - 1) % PATH_STEPS][1]))
+        value = args.steps / (dev_total_ms * 1e-3)
+        e2e = args.steps / (wall_total_ms * 1e-3)
+        peak, peak_src = measured_peak_gbs()
+        k1 = float(np.mean(kernel_ms["propagate_reweight_lfm"]))
+        g = args.grid * args.grid
+        k1_bytes = n * (80 + 4 * args.beams) + 4 * g  # 80 B state+weight r/w, 4 B per beam lookup, field once
+        step_bytes = n * (216 + 4 * args.beams) + 4 * g
+        achieved = k1_bytes / (k1 * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args, n_total), "particles_per_gpu": n, "parallelism": f"shard{world}",
+                       "l2": "256 MiB device write between timed steps (flushes the 126 MB L2)", "timing": "CUDA events on the filter stream, per step, max over ranks",
+                       "final_position_error_m": err},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(scans[0].nbytes + 32), "d2h_bytes_per_step": int(9 * 8 + 128),
+                    "ms_per_step": wall_total_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "propagate_reweight_lfm_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
+                         "kernel_ms": k1, "kernel_share_of_step": k1 / (dev_total_ms / args.steps),
+                         "step_achieved_gbs": step_bytes / (dev_total_ms / args.steps * 1e-3) / 1e9},
+            "kernels_ms": {name: float(np.mean(v)) for name, v in kernel_ms.items()},
+            "clocks": clocks.summary(),
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_steps_per_s(args, scenario, n_total, args.cpu_sample)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,271 @@
+/*
+ * beluga_b200 -- C ABI of the B200-native MCL particle-filter update.
+ *
+ * This is the drop-in boundary for ONE path of Ekumen-OS/beluga: the per-step
+ * particle-filter update `beluga::Amcl::update`
+ * (beluga/include/beluga/algorithm/amcl_core.hpp:165-201) and the models, actions, views and
+ * reductions it composes.  The reference is a header-only C++17 template library without any
+ * FFI; the C++ adaptors in include/beluga_b200/ give these entry points the reference's own
+ * MotionModel / SensorModel / Amcl shapes.  Each entry point cites the
+ * reference interface it replaces (paths relative to /root/reference/beluga/include/beluga).
+ *
+ * Conventions
+ *   - Poses are `double[4]` in Sophus::SE2d::data() order {cos, sin, x, y}
+ *     (what estimation.hpp:448-452 relies on); particle states are arrays of such quadruples.
+ *   - Every function returns BB200_OK (0) or a negative bb200_status; bb200_last_error() gives
+ *     the message of the last failure on that context.  Nothing throws across this boundary.
+ *   - All pointers are HOST pointers unless the name says `_device`.  A context owns its
+ *     device buffers and one CUDA stream; calls on one context must come from one thread at a
+ *     time (same contract as the reference: no internal locking, amcl_node.cpp:581-603).
+ *   - There is NO CPU fallback: creating a context without a usable CUDA device fails.
+ */
+#ifndef BELUGA_B200_H_
+#define BELUGA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB200_ABI_VERSION 1
+
+typedef enum bb200_status {
+  BB200_OK = 0,
+  BB200_ERR_INVALID_ARGUMENT = -1,
+  BB200_ERR_CUDA = -2,
+  BB200_ERR_NO_DEVICE = -3,
+  BB200_ERR_STATE = -4, /* call sequence error: no map, no particles, ... */
+  BB200_ERR_CAPACITY = -5
+} bb200_status;
+
+typedef struct bb200_filter bb200_filter; /* device-resident particle set + kernels        */
+typedef struct bb200_amcl bb200_amcl;     /* beluga::Amcl control flow on top of a filter   */
+
+/* ---------------------------------------------------------------------------------------------
+ * Parameter blocks (plain doubles/ints; same members and defaults as the reference structs)
+ * ------------------------------------------------------------------------------------------- */
+
+/* beluga::DifferentialDriveModelParam -- motion/differential_drive_model.hpp:40-68 */
+typedef struct bb200_diff_drive_param {
+  double rotation_noise_from_rotation;       /* alpha1 */
+  double rotation_noise_from_translation;    /* alpha2 */
+  double translation_noise_from_translation; /* alpha3 */
+  double translation_noise_from_rotation;    /* alpha4 */
+  double distance_threshold;                 /* default 0.01 */
+} bb200_diff_drive_param;
+
+/* The three std::normal_distribution parameter sets that sampling_fn_2d derives from a control
+ * action -- motion/differential_drive_model.hpp:141-154. */
+typedef struct bb200_diff_drive_sampling {
+  double rot1_mean, rot1_std;
+  double trans_mean, trans_std;
+  double rot2_mean, rot2_std;
+} bb200_diff_drive_sampling;
+
+/* beluga::LikelihoodFieldModelBaseParam -- sensor/likelihood_field_model_base.hpp:42-64 */
+typedef struct bb200_likelihood_field_param {
+  double max_obstacle_distance; /* default 100.0 */
+  double max_laser_distance;    /* default 2.0 */
+  double z_hit;                 /* default 0.5 */
+  double z_random;              /* default 0.5 */
+  double sigma_hit;             /* default 0.2 */
+  int model_unknown_space;      /* default 0 */
+  int only_obstacle_boundaries; /* default 0 */
+} bb200_likelihood_field_param;
+
+/* beluga::BeamModelParam -- sensor/beam_model.hpp:43-58 */
+typedef struct bb200_beam_param {
+  double z_hit, z_short, z_max, z_rand, sigma_hit, lambda_short, beam_max_range;
+} bb200_beam_param;
+
+/* Occupancy grid view -- the OccupancyGrid2 named requirement (sensor/data/occupancy_grid.hpp)
+ * with the ROS trinary value traits (beluga_ros/include/beluga_ros/occupancy_grid.hpp:48-64):
+ * 0 free, 100 occupied, -1 unknown; row-major, index = yi*width + xi (linear_grid.hpp:73-75). */
+typedef struct bb200_occupancy_grid {
+  const int8_t* cells;
+  int32_t width, height;
+  double resolution;
+  double origin[4]; /* grid.origin() as {cos, sin, x, y} */
+} bb200_occupancy_grid;
+
+typedef enum bb200_sensor_model {
+  BB200_SENSOR_LIKELIHOOD_FIELD = 0,      /* sensor/likelihood_field_model.hpp:69-90: 1 + sum pz^3 */
+  BB200_SENSOR_LIKELIHOOD_FIELD_PROB = 1, /* sensor/likelihood_field_prob_model.hpp:69-90: exp(sum log pz) */
+  BB200_SENSOR_BEAM = 2                   /* sensor/beam_model.hpp:104-150 */
+} bb200_sensor_model;
+
+typedef enum bb200_resample_scheme {
+  BB200_RESAMPLE_MULTINOMIAL = 0, /* views/sample.hpp:128-135 in counter-RNG form */
+  BB200_RESAMPLE_SYSTEMATIC = 1   /* not in the reference; low-variance comb over the same CDF */
+} bb200_resample_scheme;
+
+/* Pose estimate -- std::pair<Sophus::SE2d, Sophus::Matrix3d> of algorithm/estimation.hpp:436-475 */
+typedef struct bb200_estimate {
+  double mean[4]; /* {cos, sin, x, y}, rotation renormalised */
+  double cov[9];  /* row-major 3x3 over (x, y, theta) */
+} bb200_estimate;
+
+/* ---------------------------------------------------------------------------------------------
+ * Library
+ * ------------------------------------------------------------------------------------------- */
+
+int bb200_abi_version(void);
+/* Number of CUDA devices visible; 0 when there is none (then every create call fails). */
+int bb200_device_count(void);
+/* Message of the last failure of a create call on this thread. */
+const char* bb200_create_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * bb200_filter -- the particle set on the device and the per-step kernels.
+ * Replaces beluga::TupleVector<std::tuple<SE2d, Weight>> (containers/tuple_vector.hpp:50-223)
+ * plus the range adaptors that iterate it.
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct bb200_filter_config {
+  int device;             /* CUDA device ordinal */
+  uint64_t capacity;      /* maximum number of LOCAL particles (max_particles, or the shard size) */
+  uint64_t seed;          /* counter-RNG key (Philox4x32-10) */
+  /* Sharding (single GPU: rank 0 of 1).  Global particle index = first_index + local index. */
+  uint64_t first_index;   /* global index of local particle 0 */
+  uint64_t global_count;  /* total particles over all ranks (0: same as local) */
+  int record_ancestors;   /* keep the resample indices for bb200_filter_ancestors (parity hook) */
+} bb200_filter_config;
+
+int bb200_filter_create(const bb200_filter_config* config, bb200_filter** out);
+void bb200_filter_destroy(bb200_filter* f);
+const char* bb200_last_error(const bb200_filter* f);
+
+/* Sensor models.  LikelihoodFieldModel{params, grid} (likelihood_field_model.hpp:58-59): builds
+ * the likelihood field on the host exactly as make_likelihood_field
+ * (likelihood_field_model_base.hpp:130-185, distance_map.hpp:55-98) and uploads it.
+ * `prob` selects LikelihoodFieldProbModel.  Also the target of update_map() (:113-116). */
+int bb200_filter_set_likelihood_field_map(bb200_filter* f, const bb200_likelihood_field_param* p, const bb200_occupancy_grid* grid, int prob);
+/* BeamSensorModel{params, grid} (beam_model.hpp:96) / update_map (:156). */
+int bb200_filter_set_beam_map(bb200_filter* f, const bb200_beam_param* p, const bb200_occupancy_grid* grid);
+/* likelihood_field() accessor (likelihood_field_model_base.hpp:102): width*height floats. */
+int bb200_filter_get_likelihood_field(const bb200_filter* f, float* out, uint64_t capacity);
+
+/* Particle set access.  weights == NULL means 1.0 (make_from_state, particle_traits.hpp:105). */
+int bb200_filter_set_particles(bb200_filter* f, const double* states, const double* weights, uint64_t n);
+int bb200_filter_size(const bb200_filter* f, uint64_t* n);
+/* particles() (amcl_core.hpp:128): copies min(n, capacity) particles out; either may be NULL. */
+int bb200_filter_get_particles(bb200_filter* f, double* states, double* weights, uint64_t capacity);
+/* Amcl::initialize(pose, covariance) (amcl_core.hpp:145-147) with
+ * MultivariateNormalDistribution<SE2d> (random/multivariate_normal_distribution.hpp:96-126):
+ * n particles ~ N(mean {x, y, theta}, cov 3x3), weights 1. */
+int bb200_filter_initialize_normal(bb200_filter* f, const double mean_xytheta[3], const double cov[9], uint64_t n);
+
+/* actions::propagate(model(control)) (actions/propagate.hpp:57-79) for DifferentialDriveModel:
+ * per particle 3 normals (counter RNG keyed by seed / global index / step) and the SE2 compose of
+ * differential_drive_model.hpp:156-163. */
+int bb200_filter_propagate(bb200_filter* f, const bb200_diff_drive_sampling* s, uint32_t step);
+/* actions::reweight(sensor_model(points)) (actions/reweight.hpp:54-60): w *= L(state). */
+int bb200_filter_reweight(bb200_filter* f, const double* points_xy, uint64_t n_points);
+/* Fused propagate | reweight (one pass over the particle set). */
+int bb200_filter_propagate_reweight(bb200_filter* f, const bb200_diff_drive_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points);
+
+/* Weight statistics of the local shard after reweight: the largest weight and, once an exponent
+ * is fixed, the fixed-point total.  Single GPU: bb200_filter_normalize does all of it. */
+int bb200_filter_max_weight(bb200_filter* f, double* wmax);
+/* Fixes the quantisation exponent from the GLOBAL largest weight (all ranks pass the same value),
+ * builds the local inclusive fixed-point CDF and returns the local total. */
+int bb200_filter_build_cdf(bb200_filter* f, double global_wmax, uint64_t* local_total, int* exponent);
+/* actions::normalize (actions/normalize.hpp:54-85): w /= S with S = global_total * 2^-exponent.
+ * Also returns sum((w/S)^2) over the local shard (effective_sample_size.hpp:46-59). */
+int bb200_filter_normalize_by(bb200_filter* f, uint64_t global_total, double* local_sum_sq);
+/* Single-GPU convenience: max -> cdf -> normalize.  Returns the factor S and sum of squares. */
+int bb200_filter_normalize(bb200_filter* f, double* factor, double* sum_sq);
+
+/* views::sample | random_intersperse | take_while_kld | actions::assign
+ * (views/sample.hpp:128-153, views/random_intersperse.hpp:93-100, views/take_while_kld.hpp:72-137,
+ *  actions/assign.hpp:56-63) in counter-RNG form. */
+typedef struct bb200_resample_opts {
+  int scheme;                       /* bb200_resample_scheme */
+  uint32_t step;
+  uint64_t min_particles;           /* KLD lower bound (== max_particles disables KLD) */
+  uint64_t max_particles;           /* number of output slots */
+  double kld_epsilon, kld_z;
+  double spatial_resolution[3];     /* spatial_hash<SE2d>{x, y, theta} (spatial_hash.hpp:160-197) */
+  double random_state_probability;  /* recovery injection probability */
+} bb200_resample_opts;
+int bb200_filter_resample(bb200_filter* f, const bb200_resample_opts* o, uint64_t* new_size);
+/* Ancestor index of every particle produced by the last resample (-1: injected random state). */
+int bb200_filter_ancestors(bb200_filter* f, int64_t* out, uint64_t capacity);
+/* The local fixed-point CDF built by the last build_cdf / normalize (parity hook). */
+int bb200_filter_cdf(bb200_filter* f, uint64_t* out, uint64_t capacity);
+
+/* beluga::estimate(states, weights) (algorithm/estimation.hpp:436-475). */
+int bb200_filter_estimate(bb200_filter* f, bb200_estimate* out);
+/* Raw weighted moments of the local shard for a multi-rank estimate:
+ * {sum w, sum w^2, sum w*cos, sum w*sin, sum w*dx, sum w*dy, sum w*dx^2, sum w*dx*dy, sum w*dy^2}
+ * with (dx, dy) = (x, y) - pivot. */
+int bb200_filter_moments(bb200_filter* f, const double pivot_xy[2], double out[9]);
+
+/* Device-side timing of the kernels launched by the last call on this filter (milliseconds,
+ * CUDA events on the filter's stream); names[i] are static strings.  Returns the count. */
+int bb200_filter_set_timing(bb200_filter* f, int enabled);
+int bb200_filter_last_timings(const bb200_filter* f, const char** names, float* ms, int capacity);
+/* Total number of kernel launches issued by this filter since creation. */
+uint64_t bb200_filter_launch_count(const bb200_filter* f);
+/* Block until everything enqueued on the filter's stream has finished. */
+int bb200_filter_synchronize(bb200_filter* f);
+/* Raw device pointers (for torch.distributed / peer access plumbing): which = 0 states (double4),
+ * 1 weights (double), 2 cdf (uint64), 3 staging states buffer (double4). */
+int bb200_filter_device_pointer(bb200_filter* f, int which, void** ptr, uint64_t* bytes);
+
+/* ---------------------------------------------------------------------------------------------
+ * bb200_amcl -- beluga::Amcl (algorithm/amcl_core.hpp:81-233) on top of a filter: update /
+ * resample policies, rolling control window, recovery estimator, estimate.
+ * ------------------------------------------------------------------------------------------- */
+
+/* beluga::AmclParams (amcl_core.hpp:34-55) + spatial hasher resolutions + backend knobs. */
+typedef struct bb200_amcl_param {
+  double update_min_d;         /* 0.25 */
+  double update_min_a;         /* 0.2 */
+  uint64_t resample_interval;  /* 1 */
+  int selective_resampling;    /* 0 */
+  uint64_t min_particles;      /* 500 */
+  uint64_t max_particles;      /* 2000 */
+  double alpha_slow;           /* 0.001 */
+  double alpha_fast;           /* 0.1 */
+  double kld_epsilon;          /* 0.05 */
+  double kld_z;                /* 3.0 */
+  double spatial_resolution[3];/* spatial_hash<SE2d>: x, y, theta */
+  int resample_scheme;         /* bb200_resample_scheme */
+  uint64_t seed;
+  int device;
+  int record_ancestors;
+} bb200_amcl_param;
+
+typedef struct bb200_update_result {
+  int updated;                 /* 0: std::nullopt (no motion / no particles) */
+  int resampled;
+  uint64_t n_particles;
+  bb200_estimate estimate;
+  double random_state_probability;
+  double weight_sum;           /* normalisation factor S of this step */
+} bb200_update_result;
+
+int bb200_amcl_create(const bb200_amcl_param* p, const bb200_diff_drive_param* motion, bb200_amcl** out);
+void bb200_amcl_destroy(bb200_amcl* a);
+const char* bb200_amcl_last_error(const bb200_amcl* a);
+/* The filter owned by the driver (for set_*_map, get_particles, timings ...). */
+bb200_filter* bb200_amcl_filter(bb200_amcl* a);
+/* Amcl::initialize(pose, covariance) -- amcl_core.hpp:145-147 (max_particles samples). */
+int bb200_amcl_initialize(bb200_amcl* a, const double mean_xytheta[3], const double cov[9]);
+/* Amcl::initialize from explicit states (tests / custom distributions, amcl_core.hpp:131-137). */
+int bb200_amcl_initialize_states(bb200_amcl* a, const double* states, const double* weights, uint64_t n);
+/* Amcl::force_update -- amcl_core.hpp:204 */
+void bb200_amcl_force_update(bb200_amcl* a);
+/* Amcl::update(control_action, measurement) -- amcl_core.hpp:165-201.  `points_xy` is the
+ * measurement_type std::vector<std::pair<double,double>> flattened (x0, y0, x1, y1, ...). */
+int bb200_amcl_update(bb200_amcl* a, const double control_pose[4], const double* points_xy, uint64_t n_points, bb200_update_result* out);
+/* DifferentialDriveModel::operator()(control) host part -- differential_drive_model.hpp:129-154. */
+int bb200_diff_drive_sampling_from_control(const bb200_diff_drive_param* p, const double pose[4], const double previous_pose[4], bb200_diff_drive_sampling* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BELUGA_B200_H_ */

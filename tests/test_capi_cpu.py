@@ -1,0 +1,78 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/beluga_b200.h declares, refuses to run without a GPU, and its host-only logic matches the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from beluga_b200 import build as bb_build
+    from beluga_b200 import _capi
+
+    bb_build.build()
+    return _capi.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "beluga_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    from beluga_b200 import _capi
+
+    out = subprocess.run(["nm", "-D", "--defined-only", _capi.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (bb200_[a-z0-9_]+)", out))
+    declared = declared_symbols()
+    assert len(declared) >= 35
+    missing = [s for s in declared if s not in exported]
+    assert not missing, f"declared in include/beluga_b200.h but not exported: {missing}"
+    assert set(_capi.SIGNATURES) == set(declared), "ctypes table and header disagree"
+    assert lib.bb200_abi_version() == 1
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the product must fail loudly, never compute on the host."""
+    import beluga_b200 as bb
+
+    if bb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(bb.BelugaB200Error) as e:
+        bb.Filter(capacity=16)
+    assert e.value.status == -3  # BB200_ERR_NO_DEVICE
+    with pytest.raises(bb.BelugaB200Error):
+        bb.Amcl(bb.DifferentialDriveModelParam(), bb.AmclParams())
+
+
+def test_invalid_arguments_do_not_crash(lib):
+    assert lib.bb200_filter_create(None, None) == -1
+    assert lib.bb200_filter_size(None, None) == -1
+    assert lib.bb200_last_error(None) == b"null filter"
+
+
+@pytest.mark.parametrize(
+    "pose,prev",
+    [((1.0, 0.0, 0.0), (0.0, 0.0, 0.0)), ((0.0, 1.0, np.pi / 2), (0.0, 0.0, 0.0)), ((1.0, 2.0, -np.pi / 2), (0.0, 0.0, 0.0)),
+     ((0.003, 0.002, 0.4), (0.0, 0.0, 0.1)), ((-1.0, -1.0, 0.0), (0.0, 0.0, 0.0)), ((5.3, -2.1, 2.9), (5.0, -2.0, -3.0))],
+)
+def test_diff_drive_sampling_matches_oracle(lib, orc, pose, prev):
+    """Host part of DifferentialDriveModel::operator() (differential_drive_model.hpp:129-154)."""
+    from beluga_b200 import _capi
+
+    alphas = (0.1, 0.05, 0.1, 0.05)
+    p = _capi.DiffDriveParam(*alphas, 0.01)
+    a, b = orc.se2(*pose), orc.se2(*prev)
+    out = _capi.DiffDriveSampling()
+    assert lib.bb200_diff_drive_sampling_from_control(C.byref(p), a.ctypes.data_as(C.POINTER(C.c_double)),
+                                                      b.ctypes.data_as(C.POINTER(C.c_double)), C.byref(out)) == 0
+    got = np.array([out.rot1_mean, out.rot1_std, out.trans_mean, out.trans_std, out.rot2_mean, out.rot2_std])
+    exp = orc.diff_drive_sampling(orc.MotionParam(*alphas), a, b)
+    assert np.array_equal(got, exp)  # same libm, same operation order: bit-identical
