@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -92,6 +93,7 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
     return;
   }
   if (config_.global_count == 0) config_.global_count = config_.capacity;
+  if (const char* v = std::getenv("BB200_SCHEDULE")) schedule_enabled_ = std::atoi(v) != 0;  // development knob: 0 disables the pose-sorted schedule
   capacity_ = config.capacity;
 #define BB_TRY(expr)                                \
   do {                                              \
@@ -116,6 +118,11 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   BB_TRY(dev_alloc(&partials_, static_cast<size_t>(partials_rows_) * kMomentCount));
   BB_TRY(dev_alloc(&results_, 16));
   BB_TRY(cudaMallocHost(reinterpret_cast<void**>(&results_host_), 16 * sizeof(double)));
+  BB_TRY(dev_alloc(&sched_, 1));
+  BB_TRY(dev_alloc(&bins_, capacity_));
+  BB_TRY(dev_alloc(&perm_, capacity_));
+  BB_TRY(dev_alloc(&counters_, schedule_max_bins()));
+  BB_TRY(dev_alloc(&sched_tiles_, schedule_tile_count()));
   BB_TRY(cudaMemsetAsync(scalars_, 0, sizeof(Scalars), stream_));
   BB_TRY(cudaStreamSynchronize(stream_));
 #undef BB_TRY
@@ -132,6 +139,11 @@ Filter::~Filter() {
   cudaFree(ancestors_);
   cudaFree(hashes_);
   cudaFree(scalars_);
+  cudaFree(sched_);
+  cudaFree(bins_);
+  cudaFree(perm_);
+  cudaFree(counters_);
+  cudaFree(sched_tiles_);
   cudaFreeHost(scalars_host_);
   cudaFree(tile_state_);
   cudaFree(partials_);
@@ -144,6 +156,7 @@ Filter::~Filter() {
   cudaFree(points_);
   cudaFreeHost(points_host_);
   cudaFree(table_);
+  cudaFree(tiled_);
   cudaFree(occupancy_);
   cudaFree(free_cells_);
   if (stream_ != nullptr) cudaStreamDestroy(stream_);
@@ -164,12 +177,13 @@ int Filter::check(cudaError_t e, const char* what) {
     const int st_ = check((expr), #expr);       \
     if (st_ != BB200_OK) return st_;            \
   } while (0)
-#define BB_LAUNCHED(name)                                   \
+#define BB_LAUNCHED_N(name, count)                          \
   do {                                                      \
-    ++launches_;                                            \
+    launches_ += (count);                                   \
     const int st_ = check(cudaGetLastError(), name);        \
     if (st_ != BB200_OK) return st_;                        \
   } while (0)
+#define BB_LAUNCHED(name) BB_LAUNCHED_N(name, 1)
 
 void Filter::mark(const char* name) {
   if (!timing_) return;
@@ -247,6 +261,19 @@ int Filter::set_likelihood_field_map(const bb200_likelihood_field_param& p, cons
   BB_CHECK(dev_alloc(&table_, count));
   BB_CHECK(cudaMemcpyAsync(table_, table.data(), count * sizeof(double), cudaMemcpyHostToDevice, stream_));
   BB_CHECK(cudaStreamSynchronize(stream_));
+  // Tiled copy (4x4-cell tiles, Z-order inside) for the beam-parallel lookup kernel.
+  const int tiles_x = (g.width + 3) / 4, tiles_y = (g.height + 3) / 4;
+  const double unknown = f(static_cast<float>(1. / p.max_laser_distance));
+  std::vector<double> tiled(static_cast<size_t>(tiles_x) * tiles_y * 16, unknown);
+  for (int yi = 0; yi < g.height; ++yi)
+    for (int xi = 0; xi < g.width; ++xi) tiled[tiled_index(xi, yi, tiles_x)] = table[static_cast<size_t>(yi) * g.width + xi];
+  cudaFree(tiled_);
+  tiled_ = nullptr;
+  BB_CHECK(dev_alloc(&tiled_, tiled.size()));
+  BB_CHECK(cudaMemcpyAsync(tiled_, tiled.data(), tiled.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  field_.tiled = tiled_;
+  field_.tiles_x = tiles_x;
 
   field_.table = table_;
   field_.width = g.width;
@@ -369,16 +396,48 @@ int Filter::upload_points(const double* points_xy, uint64_t n_points) {
     BB_CHECK(cudaMallocHost(reinterpret_cast<void**>(&points_host_), 2 * cap * sizeof(double)));
     points_capacity_ = cap;
   }
-  double radius = 0.0;
+  double radius = 0.0, range_sum = 0.0;
   for (uint64_t i = 0; i < n_points; ++i) {
     const double r = std::fabs(points_xy[2 * i]) + std::fabs(points_xy[2 * i + 1]);
     radius = (r > radius || std::isnan(r)) ? r : radius;  // NaN sticks -> general lookup path
+    const double e = std::hypot(points_xy[2 * i], points_xy[2 * i + 1]);
+    if (std::isfinite(e)) range_sum += e;
   }
   points_radius_ = radius;
+  points_mean_range_ = n_points > 0 ? range_sum / static_cast<double>(n_points) : 1.0;  // lever arm of the heading in the schedule
   if (n_points > 0) {
     // The previous step's copy must have left the staging buffer before it is overwritten.
     std::memcpy(points_host_, points_xy, 2 * n_points * sizeof(double));
     BB_CHECK(cudaMemcpyAsync(points_, points_host_, 2 * n_points * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  }
+  return BB200_OK;
+}
+
+int Filter::enqueue_propagate_reweight(const DiffDriveSampling* sampling, uint32_t step, bool do_reweight, uint64_t n_points) {
+  const bool scheduled = do_reweight && schedule_enabled_ && n_ >= kScheduleMinParticles;
+  if (sampling != nullptr || scheduled) {
+    mark("propagate");
+    launch_propagate(states_[cur_], n_, sampling != nullptr, sampling != nullptr ? *sampling : DiffDriveSampling{}, config_.seed, step,
+                     config_.first_index, scheduled ? sched_ : nullptr, stream_);
+    BB_LAUNCHED_N("propagate", scheduled ? 2 : 1);
+  }
+  const uint32_t* perm = nullptr;
+  if (scheduled) {
+    mark("schedule");
+    launch_build_schedule(states_[cur_], n_, sched_, bins_, counters_, perm_, sched_tiles_, points_mean_range_, 0.5 * grid_resolution_, stream_);
+    BB_LAUNCHED_N("schedule", 4);
+    perm = perm_;
+  }
+  if (do_reweight) {
+    if (sensor_ == BB200_SENSOR_BEAM) {
+      mark("reweight_beam");
+      launch_reweight_beam(states_[cur_], weights_, n_, perm, occupancy_view_, beam_, points_, static_cast<uint32_t>(n_points), scalars_, stream_);
+      BB_LAUNCHED("reweight_beam");
+    } else {
+      mark("reweight_lfm");
+      launch_reweight_lfm(states_[cur_], weights_, n_, perm, field_, points_, static_cast<uint32_t>(n_points), points_radius_, scalars_, stream_);
+      BB_LAUNCHED("reweight_lfm");
+    }
   }
   return BB200_OK;
 }
@@ -399,17 +458,8 @@ int Filter::propagate_reweight(const bb200_diff_drive_sampling* sampling, uint32
   mark("begin_step");
   launch_begin_step(scalars_, stream_);
   BB_LAUNCHED("begin_step");
-  if (do_reweight && sensor_ == BB200_SENSOR_BEAM) {
-    mark("propagate_reweight_beam");
-    launch_propagate_reweight_beam(states_[cur_], weights_, n_, sampling != nullptr, s, config_.seed, step, config_.first_index, occupancy_view_,
-                                   beam_, points_, static_cast<uint32_t>(n_points), scalars_, stream_);
-    BB_LAUNCHED("propagate_reweight_beam");
-  } else {
-    mark("propagate_reweight_lfm");
-    launch_propagate_reweight_lfm(states_[cur_], weights_, n_, sampling != nullptr, s, config_.seed, step, config_.first_index, do_reweight,
-                                  field_, points_, static_cast<uint32_t>(n_points), points_radius_, scalars_, stream_);
-    BB_LAUNCHED("propagate_reweight_lfm");
-  }
+  const int st = enqueue_propagate_reweight(sampling != nullptr ? &s : nullptr, step, do_reweight, n_points);
+  if (st != BB200_OK) return st;
   cdf_valid_ = false;
   finish_marks();
   return BB200_OK;
@@ -597,17 +647,8 @@ int Filter::step_resample(const bb200_diff_drive_sampling& sampling, uint32_t st
   mark("begin_step");
   launch_begin_step(scalars_, stream_);
   BB_LAUNCHED("begin_step");
-  if (sensor_ == BB200_SENSOR_BEAM) {
-    mark("propagate_reweight_beam");
-    launch_propagate_reweight_beam(states_[cur_], weights_, n_, true, s, config_.seed, step, config_.first_index, occupancy_view_, beam_, points_,
-                                   static_cast<uint32_t>(n_points), scalars_, stream_);
-    BB_LAUNCHED("propagate_reweight_beam");
-  } else {
-    mark("propagate_reweight_lfm");
-    launch_propagate_reweight_lfm(states_[cur_], weights_, n_, true, s, config_.seed, step, config_.first_index, true, field_, points_,
-                                  static_cast<uint32_t>(n_points), points_radius_, scalars_, stream_);
-    BB_LAUNCHED("propagate_reweight_lfm");
-  }
+  st = enqueue_propagate_reweight(&s, step, true, n_points);
+  if (st != BB200_OK) return st;
   mark("prepare_cdf");
   launch_prepare_cdf(scalars_, -1.0, config_.global_count, tile_state_, scan_tile_count(n_), stream_);
   BB_LAUNCHED("prepare_cdf");

@@ -62,6 +62,7 @@ class Filter {
   int fail(int status, const std::string& message);
   int check(cudaError_t e, const char* what);
   int upload_points(const double* points_xy, uint64_t n_points);
+  int enqueue_propagate_reweight(const DiffDriveSampling* sampling, uint32_t step, bool do_reweight, uint64_t n_points);
   int ensure_cdf_ready();
   void estimate_from_moments(const double m[kMomentCount], bb200_estimate* out) const;
   void mark(const char* name);  // timing: record an event before the next kernel
@@ -108,11 +109,22 @@ class Filter {
   double* points_host_{nullptr};  // pinned staging
   uint64_t points_capacity_{0};
   double points_radius_{0.0};
+  double points_mean_range_{1.0};
+
+  // execution schedule (pose-sorted processing order of the reweight kernels)
+  static constexpr uint64_t kScheduleMinParticles = 32768;
+  bool schedule_enabled_{true};
+  Schedule* sched_{nullptr};
+  uint32_t* bins_{nullptr};
+  uint32_t* perm_{nullptr};
+  uint32_t* counters_{nullptr};
+  unsigned long long* sched_tiles_{nullptr};
 
   // maps
   int sensor_{-1};
   std::vector<float> field_host_;
   double* table_{nullptr};
+  double* tiled_{nullptr};
   FieldView field_{};
   int8_t* occupancy_{nullptr};
   OccupancyView occupancy_view_{};

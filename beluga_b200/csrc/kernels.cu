@@ -3,8 +3,10 @@
 // One filter step on the device (fixed particle count, resample every step):
 //
 //   begin_step            zero the per-filter scalars
-//   propagate_reweight    a2 + a6 + a3 + a5 of SURVEY.md section 8(a): Philox normals, SE2 compose,
-//                         B likelihood-field lookups per particle, w *= L, block max of w
+//   propagate             a2 + a6 of SURVEY.md section 8(a): Philox normals, SE2 compose; cloud moments
+//   schedule_*            counting sort of the particles over pose bins (execution order only)
+//   reweight_lfm / _beam  a3 / a4 + a5: B likelihood-field lookups (or ray casts) per particle in
+//                         schedule order, w *= L written to the particle's own slot, block max of w
 //   prepare_cdf           exponent of the fixed-point grid from the largest weight
 //   quantize_scan         q = floor(w * 2^e), single-pass decoupled look-back inclusive scan (u64)
 //   resample              a10 + a11 + a13: one thread per output slot; counter draw, CDF search,
@@ -131,10 +133,12 @@ __global__ void __launch_bounds__(256) initialize_normal_kernel(Pose2* states, d
   weights[i] = 1.0;
 }
 
-// ---- propagate | reweight (likelihood field) ---------------------------------------------------
+// ---- propagate (a2 + a6) --------------------------------------------------------------------------
+// One thread per particle, original order.  Also accumulates the first and second moments of the
+// propagated cloud (block reduction + double atomics); they only feed the execution schedule below,
+// never a result, so their summation order does not matter.
 
-constexpr int kPrThreads = 512;        // 2 CTAs per SM at <= 64 registers
-constexpr uint32_t kChunkBeams = 2048; // beams staged per shared-memory chunk (32 KB), multiple of 4
+constexpr int kPrThreads = 256;
 
 __device__ __forceinline__ Pose2 load_pose(const Pose2* p) {
   const double2 a = *reinterpret_cast<const double2*>(p);
@@ -156,6 +160,107 @@ __device__ __forceinline__ Pose2 propagate_one(const Pose2& st, const DiffDriveS
   const double rot2 = z2 * p.rot2_std + p.rot2_mean;
   return diff_drive_apply(st, rot1, trans, rot2);
 }
+
+__global__ void __launch_bounds__(kPrThreads) propagate_kernel(Pose2* __restrict__ states, uint64_t n, int do_propagate, DiffDriveSampling sampling,
+                                                               uint64_t seed, uint32_t step, uint64_t first_index, Schedule* __restrict__ sched) {
+  __shared__ double s_red[kPrThreads / kWarp];
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kPrThreads + threadIdx.x;
+  double m[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (i < n) {
+    Pose2 st = load_pose(states + i);
+    if (do_propagate) {
+      st = propagate_one(st, sampling, seed, first_index + i, step);
+      store_pose(states + i, st);
+    }
+    m[0] = st.c, m[1] = st.s, m[2] = st.x, m[3] = st.y, m[4] = st.x * st.x, m[5] = st.y * st.y;
+  }
+  if (sched != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double total = block_sum<kPrThreads>(m[k], s_red);
+      if (threadIdx.x == 0) atomicAdd(&sched->sums[k], total);
+    }
+  }
+}
+
+// ---- execution schedule ---------------------------------------------------------------------------
+// The likelihood-field lookup of beam k lands, for two particles, in nearby cells only if their poses
+// are close (x, y, and theta scaled by the beam range).  The posterior is wide, so in index order the
+// 32 lanes of a warp gather from ~31 distinct 32-byte sectors and the kernel is bound by L2 sector
+// bandwidth (profiles/r01_lfm_v1_*).  The reweight kernels therefore walk the particles in the order
+// of a counting sort over a 3-D grid of pose bins.  This only permutes WHICH THREAD handles a
+// particle: weights are written back to the particle's own slot, so every result is independent of it.
+
+constexpr uint32_t kMaxBins = 1u << 20;
+
+__global__ void schedule_reset_kernel(Schedule* sched) {
+  for (int k = 0; k < 6; ++k) sched->sums[k] = 0.0;
+  sched->tile_ticket = 0;
+}
+
+__global__ void schedule_params_kernel(Schedule* sched, uint64_t n, double mean_range, double min_bin) {
+  const double inv_n = 1.0 / static_cast<double>(n);
+  const double cbar = sched->sums[0] * inv_n, sbar = sched->sums[1] * inv_n;
+  const double mx = sched->sums[2] * inv_n, my = sched->sums[3] * inv_n;
+  const double vx = fmax(sched->sums[4] * inv_n - mx * mx, 0.0), vy = fmax(sched->sums[5] * inv_n - my * my, 0.0);
+  const double r = hypot(cbar, sbar);
+  const double pi = 3.14159265358979323846;
+  double c0 = 1.0, s0 = 0.0, sigma_theta = pi;
+  if (r > 1e-9) {
+    c0 = cbar / r;
+    s0 = sbar / r;
+    sigma_theta = r < 1.0 ? sqrt(-2.0 * log(r)) : 0.0;
+  }
+  const double half_theta = fmin(pi, fmax(3.0 * sigma_theta, 1e-4));
+  const double half_x = fmax(3.0 * sqrt(vx), min_bin), half_y = fmax(3.0 * sqrt(vy), min_bin);
+  // Bins of equal physical edge q in (range * theta, x, y), about 16 particles per bin.
+  const double ext_t = 2.0 * half_theta * fmax(mean_range, 1.0), ext_x = 2.0 * half_x, ext_y = 2.0 * half_y;
+  double q = cbrt(ext_t * ext_x * ext_y / fmax(static_cast<double>(n) / 16.0, 1.0));
+  q = fmax(q, min_bin);
+  uint32_t nt, nx, ny;
+  for (;;) {
+    nt = static_cast<uint32_t>(fmin(fmax(ceil(ext_t / q), 1.0), 65536.0));
+    nx = static_cast<uint32_t>(fmin(fmax(ceil(ext_x / q), 1.0), 65536.0));
+    ny = static_cast<uint32_t>(fmin(fmax(ceil(ext_y / q), 1.0), 65536.0));
+    if (static_cast<uint64_t>(nt) * nx * ny <= kMaxBins) break;
+    q = q * 1.3;
+  }
+  sched->c0 = c0, sched->s0 = s0;
+  sched->x0 = mx - half_x, sched->y0 = my - half_y, sched->half_theta = half_theta;
+  sched->scale_t = static_cast<double>(nt) / (2.0 * half_theta);
+  sched->scale_x = static_cast<double>(nx) / ext_x;
+  sched->scale_y = static_cast<double>(ny) / ext_y;
+  sched->nt = nt, sched->nx = nx, sched->ny = ny;
+}
+
+__device__ __forceinline__ uint32_t schedule_bin(const Schedule& g, const Pose2& st) {
+  const double dtheta = atan2(st.s * g.c0 - st.c * g.s0, st.c * g.c0 + st.s * g.s0);
+  const int bt = min(max(static_cast<int>((dtheta + g.half_theta) * g.scale_t), 0), static_cast<int>(g.nt) - 1);
+  const int bx = min(max(static_cast<int>((st.x - g.x0) * g.scale_x), 0), static_cast<int>(g.nx) - 1);
+  const int by = min(max(static_cast<int>((st.y - g.y0) * g.scale_y), 0), static_cast<int>(g.ny) - 1);
+  return (static_cast<uint32_t>(bt) * g.ny + static_cast<uint32_t>(by)) * g.nx + static_cast<uint32_t>(bx);
+}
+
+__global__ void __launch_bounds__(256) schedule_histogram_kernel(const Pose2* __restrict__ states, uint64_t n, const Schedule* __restrict__ sched,
+                                                                 uint32_t* __restrict__ bins, uint32_t* __restrict__ counters) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t b = schedule_bin(*sched, load_pose(states + i));
+  bins[i] = b;
+  atomicAdd(counters + b, 1u);
+}
+
+__global__ void __launch_bounds__(256) schedule_scatter_kernel(const uint32_t* __restrict__ bins, uint64_t n, uint32_t* __restrict__ offsets,
+                                                               uint32_t* __restrict__ perm) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  perm[atomicAdd(offsets + bins[i], 1u)] = static_cast<uint32_t>(i);
+}
+
+// ---- reweight (likelihood field; a3 + a5) --------------------------------------------------------
+
+constexpr int kRwThreads = 512;        // 2 CTAs per SM at <= 64 registers
+constexpr uint32_t kChunkBeams = 2048; // beams staged per shared-memory chunk (32 KB), multiple of 4
 
 /// floor(g) as int32 for |g| < 2^31 through one round-down add: g + 1.5*2^52 has ulp 1, so the low
 /// mantissa word of the sum is floor(g) in two's complement.
@@ -179,10 +284,10 @@ __device__ __forceinline__ double field_lookup(const FieldView& f, double px, do
     xi = (fx >= 0.0 && fx < 2147483647.0) ? static_cast<int>(fx) : -1;
     yi = (fy >= 0.0 && fy < 2147483647.0) ? static_cast<int>(fy) : -1;
   }
-  // dense_grid.hpp:92-96 contains(); linear_grid.hpp:73-75 index_at().
+  // dense_grid.hpp:92-96 contains(); the table is stored in 4x4 tiles (kernels.cuh tiled_index()).
   const bool inside = static_cast<unsigned>(xi) < static_cast<unsigned>(f.width) && static_cast<unsigned>(yi) < static_cast<unsigned>(f.height);
   double v = f.unknown_value;
-  if (inside) v = __ldg(f.table + (static_cast<size_t>(yi) * static_cast<size_t>(f.width) + static_cast<size_t>(xi)));
+  if (inside) v = __ldg(f.tiled + tiled_index(xi, yi, f.tiles_x));
   return v;
 }
 
@@ -204,72 +309,63 @@ __device__ __forceinline__ double accumulate_chunk(const FieldView& f, const dou
   return acc;
 }
 
-__global__ void __launch_bounds__(kPrThreads, 2)
-    propagate_reweight_lfm_kernel(Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, int do_propagate,
-                                  DiffDriveSampling sampling, uint64_t seed, uint32_t step, uint64_t first_index, int do_reweight,
-                                  FieldView field, const double2* __restrict__ points, uint32_t n_points, double points_radius,
-                                  Scalars* __restrict__ scalars) {
+__global__ void __launch_bounds__(kRwThreads, 2)
+    reweight_lfm_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
+                        FieldView field, const double2* __restrict__ points, uint32_t n_points, double points_radius,
+                        Scalars* __restrict__ scalars) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* s_pts = reinterpret_cast<double2*>(smem_raw);
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ unsigned long long s_red[kPrThreads / kWarp];
+  __shared__ unsigned long long s_red[kRwThreads / kWarp];
 
-  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kPrThreads + threadIdx.x;
-  const bool active = i < n;
+  const uint64_t slot = static_cast<uint64_t>(blockIdx.x) * kRwThreads + threadIdx.x;
+  const bool active = slot < n;
+  const uint64_t i = active ? (perm != nullptr ? perm[slot] : slot) : 0;
 
-  if (do_reweight && threadIdx.x == 0) {
+  if (threadIdx.x == 0) {
     mbarrier_init(&s_bar, 1);
     mbarrier_init_fence();
   }
-
   Pose2 st{1.0, 0.0, 0.0, 0.0};
   double w = 0.0;
   if (active) {
     st = load_pose(states + i);
     w = weights[i];
-    if (do_propagate) {
-      st = propagate_one(st, sampling, seed, first_index + i, step);
-      store_pose(states + i, st);
-    }
   }
-
-  if (do_reweight) {
-    // transform = world_to_likelihood_field * state (likelihood_field_model.hpp:70-74)
-    const Pose2 t = pose_mul(field.world_to_field, st);
-    // Fast floor is exact while every |coordinate * inv_resolution| stays below 2^30.
-    const double reach = (points_radius + fmax(fabs(t.x), fabs(t.y))) * field.inv_resolution;
-    const bool fast = reach < 1073741824.0;  // false for NaN
-    double acc = field.init;
-    uint32_t phase = 0;
-    __syncthreads();  // barrier initialised
-    for (uint32_t base = 0; base < n_points; base += kChunkBeams) {
-      const uint32_t count = min(kChunkBeams, n_points - base);
-      if (threadIdx.x == 0) {
-        const uint32_t bytes = count * static_cast<uint32_t>(sizeof(double2));
-        mbarrier_expect_tx(&s_bar, bytes);
-        bulk_copy_g2s(s_pts, points + base, bytes, &s_bar);
-      }
-      mbarrier_wait(&s_bar, phase);
-      phase ^= 1u;
-      if (active) {
-        acc = fast ? accumulate_chunk<true>(field, s_pts, count, acc, t.c, t.s, t.x, t.y)
-                   : accumulate_chunk<false>(field, s_pts, count, acc, t.c, t.s, t.x, t.y);
-      }
-      __syncthreads();  // everyone is done with s_pts before the next chunk overwrites it
+  // transform = world_to_likelihood_field * state (likelihood_field_model.hpp:70-74)
+  const Pose2 t = pose_mul(field.world_to_field, st);
+  // Fast floor is exact while every |coordinate * inv_resolution| stays below 2^30.
+  const double reach = (points_radius + fmax(fabs(t.x), fabs(t.y))) * field.inv_resolution;
+  const bool fast = reach < 1073741824.0;  // false for NaN
+  double acc = field.init;
+  uint32_t phase = 0;
+  __syncthreads();  // barrier initialised
+  for (uint32_t base = 0; base < n_points; base += kChunkBeams) {
+    const uint32_t count = min(kChunkBeams, n_points - base);
+    if (threadIdx.x == 0) {
+      // TMA bulk copy of the scan points into shared memory (UBLKCP), completion on the mbarrier.
+      const uint32_t bytes = count * static_cast<uint32_t>(sizeof(double2));
+      mbarrier_expect_tx(&s_bar, bytes);
+      bulk_copy_g2s(s_pts, points + base, bytes, &s_bar);
     }
+    mbarrier_wait(&s_bar, phase);
+    phase ^= 1u;
     if (active) {
-      const double likelihood = field.exp_epilogue ? exp(acc) : acc;
-      w = w * likelihood;  // actions/reweight.hpp:54-60
-      weights[i] = w;
+      acc = fast ? accumulate_chunk<true>(field, s_pts, count, acc, t.c, t.s, t.x, t.y)
+                 : accumulate_chunk<false>(field, s_pts, count, acc, t.c, t.s, t.x, t.y);
     }
+    __syncthreads();  // everyone is done with s_pts before the next chunk overwrites it
   }
-
-  const unsigned long long m = block_max_u64<kPrThreads>(active ? weight_order_bits(w) : 0ull, s_red);
+  if (active) {
+    const double likelihood = field.exp_epilogue ? exp(acc) : acc;
+    w = w * likelihood;  // actions/reweight.hpp:54-60
+    weights[i] = w;
+  }
+  const unsigned long long m = block_max_u64<kRwThreads>(active ? weight_order_bits(w) : 0ull, s_red);
   if (threadIdx.x == 0 && m != 0) atomicMax(&scalars->wmax_bits, m);
 }
 
-
-// ---- propagate | reweight (beam model) -----------------------------------------------------------
+// ---- reweight (beam model; a4 + a5) -----------------------------------------------------------
 // BeamSensorModel (sensor/beam_model.hpp:104-150): one thread per particle, beams in the inner
 // loop, so the lanes of a warp (neighbouring particles, same beam) walk rays of similar length.
 // Ray casting is Ray2d::cast (algorithm/raycasting.hpp:79-107) over the standard Bresenham2i
@@ -344,23 +440,20 @@ constexpr int kBeamThreads = 256;
 constexpr uint32_t kBeamChunk = 1024;  // rays staged per shared-memory chunk (24 KB), multiple of 4
 
 __global__ void __launch_bounds__(kBeamThreads)
-    propagate_reweight_beam_kernel(Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, int do_propagate,
-                                   DiffDriveSampling sampling, uint64_t seed, uint32_t step, uint64_t first_index, OccupancyView grid,
-                                   BeamParams params, const double2* __restrict__ points, uint32_t n_points, Scalars* __restrict__ scalars) {
+    reweight_beam_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
+                         OccupancyView grid, BeamParams params, const double2* __restrict__ points, uint32_t n_points,
+                         Scalars* __restrict__ scalars) {
   __shared__ BeamRay s_rays[kBeamChunk];
   __shared__ unsigned long long s_red[kBeamThreads / kWarp];
-  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kBeamThreads + threadIdx.x;
-  const bool active = i < n;
+  const uint64_t slot = static_cast<uint64_t>(blockIdx.x) * kBeamThreads + threadIdx.x;
+  const bool active = slot < n;
+  const uint64_t i = active ? (perm != nullptr ? perm[slot] : slot) : 0;
 
   Pose2 st{1.0, 0.0, 0.0, 0.0};
   double w = 0.0;
   if (active) {
     st = load_pose(states + i);
     w = weights[i];
-    if (do_propagate) {
-      st = propagate_one(st, sampling, seed, first_index + i, step);
-      store_pose(states + i, st);
-    }
   }
   // Ray2d: source pose in the grid frame and its cell (raycasting.hpp:67-70).
   const Pose2 src = pose_mul(grid.world_to_grid, st);
@@ -534,6 +627,34 @@ __global__ void __launch_bounds__(kScanThreads) quantize_scan_kernel(const doubl
   if (base <= n - 1 && n - 1 < base + kScanItems) scalars->total = prefix + inclusive;  // thread holding the last element
 }
 
+/// Exclusive prefix sum of the bin counters (same decoupled look-back machinery, u32 payload).
+__global__ void __launch_bounds__(kScanThreads) scan_counters_kernel(uint32_t* __restrict__ counters, uint32_t n, Schedule* sched,
+                                                                     unsigned long long* tile_state) {
+  __shared__ unsigned long long s_warp[kScanThreads / kWarp];
+  __shared__ unsigned long long s_prefix;
+  __shared__ uint32_t s_tile;
+  if (threadIdx.x == 0) s_tile = static_cast<uint32_t>(atomicAdd(&sched->tile_ticket, 1ull));
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
+  unsigned long long q[kScanItems];
+  unsigned long long local = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    q[k] = base + k < n ? counters[base + k] : 0u;
+    local += q[k];
+  }
+  unsigned long long tile_total;
+  const unsigned long long inclusive = block_inclusive_scan_u64(local, s_warp, tile_total);
+  const unsigned long long prefix = lookback_exclusive_prefix(tile_state, tile, tile_total, &s_prefix);
+  unsigned long long running = prefix + inclusive - local;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) counters[base + k] = static_cast<uint32_t>(running);
+    running += q[k];
+  }
+}
+
 // ---- normalize -------------------------------------------------------------------------------------
 
 constexpr int kStreamThreads = 256;
@@ -693,28 +814,44 @@ void launch_initialize_normal(Pose2* states, double* weights, uint64_t n, const 
   initialize_normal_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(states, weights, n, p, seed, first_index);
 }
 
-void launch_propagate_reweight_lfm(Pose2* states, double* weights, uint64_t n, bool do_propagate, const DiffDriveSampling& sampling,
-                                   uint64_t seed, uint32_t step, uint64_t first_index, bool do_reweight, const FieldView& field,
-                                   const double* points_xy_device, uint32_t n_points, double points_radius, Scalars* scalars,
-                                   cudaStream_t stream) {
+void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const DiffDriveSampling& sampling, uint64_t seed, uint32_t step,
+                      uint64_t first_index, Schedule* sched, cudaStream_t stream) {
   if (n == 0) return;
-  const unsigned blocks = static_cast<unsigned>((n + kPrThreads - 1) / kPrThreads);
-  const size_t smem = do_reweight ? static_cast<size_t>(n_points < kChunkBeams ? n_points : kChunkBeams) * sizeof(double2) : 0;
-  propagate_reweight_lfm_kernel<<<blocks, kPrThreads, smem, stream>>>(states, weights, n, do_propagate ? 1 : 0, sampling, seed, step,
-                                                                      first_index, do_reweight ? 1 : 0, field,
-                                                                      reinterpret_cast<const double2*>(points_xy_device), n_points,
-                                                                      points_radius, scalars);
+  if (sched != nullptr) schedule_reset_kernel<<<1, 1, 0, stream>>>(sched);
+  propagate_kernel<<<static_cast<unsigned>((n + kPrThreads - 1) / kPrThreads), kPrThreads, 0, stream>>>(states, n, do_propagate ? 1 : 0, sampling,
+                                                                                                      seed, step, first_index, sched);
 }
 
-void launch_propagate_reweight_beam(Pose2* states, double* weights, uint64_t n, bool do_propagate, const DiffDriveSampling& sampling,
-                                    uint64_t seed, uint32_t step, uint64_t first_index, const OccupancyView& grid,
-                                    const BeamParams& params, const double* points_xy_device, uint32_t n_points, Scalars* scalars,
-                                    cudaStream_t stream) {
+uint32_t schedule_max_bins() { return kMaxBins; }
+uint32_t schedule_tile_count() { return (kMaxBins + kScanTile - 1) / kScanTile; }
+
+void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uint32_t* bins, uint32_t* counters, uint32_t* perm,
+                           unsigned long long* tile_state, double mean_range, double min_bin, cudaStream_t stream) {
+  if (n == 0) return;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  cudaMemsetAsync(counters, 0, kMaxBins * sizeof(uint32_t), stream);
+  cudaMemsetAsync(tile_state, 0, schedule_tile_count() * sizeof(unsigned long long), stream);
+  schedule_params_kernel<<<1, 1, 0, stream>>>(sched, n, mean_range, min_bin);
+  schedule_histogram_kernel<<<blocks, 256, 0, stream>>>(states, n, sched, bins, counters);
+  scan_counters_kernel<<<schedule_tile_count(), kScanThreads, 0, stream>>>(counters, kMaxBins, sched, tile_state);
+  schedule_scatter_kernel<<<blocks, 256, 0, stream>>>(bins, n, counters, perm);
+}
+
+void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const FieldView& field,
+                         const double* points_xy_device, uint32_t n_points, double points_radius, Scalars* scalars, cudaStream_t stream) {
+  if (n == 0) return;
+  const unsigned blocks = static_cast<unsigned>((n + kRwThreads - 1) / kRwThreads);
+  const size_t smem = static_cast<size_t>(n_points < kChunkBeams ? n_points : kChunkBeams) * sizeof(double2);
+  reweight_lfm_kernel<<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, reinterpret_cast<const double2*>(points_xy_device),
+                                                            n_points, points_radius, scalars);
+}
+
+void launch_reweight_beam(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const OccupancyView& grid,
+                          const BeamParams& params, const double* points_xy_device, uint32_t n_points, Scalars* scalars, cudaStream_t stream) {
   if (n == 0) return;
   const unsigned blocks = static_cast<unsigned>((n + kBeamThreads - 1) / kBeamThreads);
-  propagate_reweight_beam_kernel<<<blocks, kBeamThreads, 0, stream>>>(states, weights, n, do_propagate ? 1 : 0, sampling, seed, step,
-                                                                      first_index, grid, params,
-                                                                      reinterpret_cast<const double2*>(points_xy_device), n_points, scalars);
+  reweight_beam_kernel<<<blocks, kBeamThreads, 0, stream>>>(states, weights, n, perm, grid, params,
+                                                            reinterpret_cast<const double2*>(points_xy_device), n_points, scalars);
 }
 
 void launch_max_weight(const double* weights, uint64_t n, Scalars* scalars, cudaStream_t stream) {

@@ -12,6 +12,10 @@ namespace bb200 {
 /// Device view of the likelihood-field lookup table (LFM / LFM-prob).
 struct FieldView {
   const double* table;  // f(pz) per cell, row-major (f = pz^3 or log pz)
+  // Same values in 4x4-cell tiles (one 128-byte line per tile, Z-order inside: each 32-byte sector
+  // is a 2x2 block), padded to whole tiles with unknown_value.  Index: see tiled_index().
+  const double* tiled;
+  int tiles_x;
   int width, height;
   double inv_resolution;  // 1. / resolution  (regular_grid.hpp:76)
   double unknown_value;   // f(float(1/max_laser_distance)) for out-of-grid end points
@@ -56,17 +60,38 @@ void launch_begin_step(Scalars* scalars, cudaStream_t stream);
 void launch_initialize_normal(Pose2* states, double* weights, uint64_t n, const double mean[3], const double transform[9],
                               uint64_t seed, uint64_t first_index, cudaStream_t stream);
 
-/// propagate (optional) | reweight with the likelihood-field table (optional) | block max of weights.
-void launch_propagate_reweight_lfm(Pose2* states, double* weights, uint64_t n, bool do_propagate, const DiffDriveSampling& sampling,
-                                   uint64_t seed, uint32_t step, uint64_t first_index, bool do_reweight, const FieldView& field,
-                                   const double* points_xy_device, uint32_t n_points, double points_radius, Scalars* scalars,
-                                   cudaStream_t stream);
+/// Offset of cell (xi, yi) in the tiled table.
+BB_HD size_t tiled_index(int xi, int yi, int tiles_x) {
+  const unsigned x = static_cast<unsigned>(xi), y = static_cast<unsigned>(yi);
+  const size_t tile = static_cast<size_t>(y >> 2) * static_cast<size_t>(tiles_x) + (x >> 2);
+  const unsigned inner = ((y & 2u) << 2) | ((x & 2u) << 1) | ((y & 1u) << 1) | (x & 1u);
+  return tile * 16 + inner;
+}
 
-/// propagate (optional) | reweight with the beam model (Bresenham ray casting) | block max.
-void launch_propagate_reweight_beam(Pose2* states, double* weights, uint64_t n, bool do_propagate, const DiffDriveSampling& sampling,
-                                    uint64_t seed, uint32_t step, uint64_t first_index, const OccupancyView& grid,
-                                    const BeamParams& params, const double* points_xy_device, uint32_t n_points, Scalars* scalars,
-                                    cudaStream_t stream);
+/// Execution schedule state (device): cloud moments and the pose-bin grid derived from them.
+struct Schedule {
+  double sums[6];  // sum cos, sin, x, y, x^2, y^2 of the propagated cloud
+  unsigned long long tile_ticket;
+  double c0, s0;            // mean heading (unit complex)
+  double x0, y0, half_theta;
+  double scale_t, scale_x, scale_y;
+  uint32_t nt, nx, ny;
+};
+
+/// propagate (or only accumulate the cloud moments when do_propagate is false).  sched may be null.
+void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const DiffDriveSampling& sampling, uint64_t seed, uint32_t step,
+                      uint64_t first_index, Schedule* sched, cudaStream_t stream);
+uint32_t schedule_max_bins();
+uint32_t schedule_tile_count();
+/// Counting sort of the particle indices over pose bins -> perm (needs launch_propagate's moments).
+void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uint32_t* bins, uint32_t* counters, uint32_t* perm,
+                           unsigned long long* tile_state, double mean_range, double min_bin, cudaStream_t stream);
+/// reweight with the likelihood-field table in schedule order (perm may be null) | block max.
+void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const FieldView& field,
+                         const double* points_xy_device, uint32_t n_points, double points_radius, Scalars* scalars, cudaStream_t stream);
+/// reweight with the beam model (Bresenham ray casting) in schedule order | block max.
+void launch_reweight_beam(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const OccupancyView& grid,
+                          const BeamParams& params, const double* points_xy_device, uint32_t n_points, Scalars* scalars, cudaStream_t stream);
 
 /// Largest weight only (when propagate/reweight ran separately or particles were set by hand).
 void launch_max_weight(const double* weights, uint64_t n, Scalars* scalars, cudaStream_t stream);

@@ -13,7 +13,7 @@ Reported (one JSON line on stdout, rank 0):
              stream; scan points already in HBM when the first event is recorded)
   e2e        steps/s through the C-ABI call bb200_amcl_update with HOST buffers: per step the scan
              (H2D from pinned staging) goes in and the pose estimate comes back, host clock around it
-  roofline   the dominant kernel (propagate_reweight_lfm) against the measured HBM copy peak
+  roofline   the dominant kernel (reweight_lfm) against the measured HBM copy peak
   cpu_baseline  the CPU oracle (a port of the reference pipeline; the reference itself needs
              Eigen/Sophus/range-v3, absent here) on the host cores, bounded sample, same workload
 """
@@ -236,9 +236,11 @@ def run_native(args):
         value = args.steps / (dev_total_ms * 1e-3)
         e2e = args.steps / (wall_total_ms * 1e-3)
         peak, peak_src = measured_peak_gbs()
-        k1 = float(np.mean(kernel_ms["propagate_reweight_lfm"]))
+        k1 = float(np.mean(kernel_ms["reweight_lfm"]))
         g = args.grid * args.grid
-        k1_bytes = n * (80 + 4 * args.beams) + 4 * g  # 80 B state+weight r/w, 4 B per beam lookup, field once
+        # SURVEY 8(d) per-unit figures for the reweight launch: 32 B state read + 8 B weight read + 8 B weight write
+        # per particle, one 4-byte field value per beam lookup, the field once.
+        k1_bytes = n * (48 + 4 * args.beams) + 4 * g
         step_bytes = n * (216 + 4 * args.beams) + 4 * g
         achieved = k1_bytes / (k1 * 1e-3) / 1e9
         line = {
@@ -251,7 +253,7 @@ def run_native(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(scans[0].nbytes + 32), "d2h_bytes_per_step": int(9 * 8 + 128),
                     "ms_per_step": wall_total_ms / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "propagate_reweight_lfm_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "reweight_lfm_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
                          "kernel_ms": k1, "kernel_share_of_step": k1 / (dev_total_ms / args.steps),
                          "step_achieved_gbs": step_bytes / (dev_total_ms / args.steps * 1e-3) / 1e9},
