@@ -94,6 +94,7 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   }
   if (config_.global_count == 0) config_.global_count = config_.capacity;
   if (const char* v = std::getenv("BB200_SCHEDULE")) schedule_enabled_ = std::atoi(v) != 0;  // development knob: 0 disables the pose-sorted schedule
+  if (const char* v = std::getenv("BB200_TILED")) tiled_layout_ = std::atoi(v) != 0;         // development knob: table layout
   capacity_ = config.capacity;
 #define BB_TRY(expr)                                \
   do {                                              \
@@ -249,22 +250,25 @@ int Filter::set_likelihood_field_map(const bb200_likelihood_field_param& p, cons
   field_host_ = make_likelihood_field(p, g);
   const size_t count = field_host_.size();
   // Per-cell f(pz) in double: pz^3 (likelihood_field_model.hpp:84-89) or log pz (prob model :84-86).
-  std::vector<double> table(count);
+  if (count + 64 >= (1ull << 32)) return fail(BB200_ERR_CAPACITY, "map too large for 32-bit cell indices");
+  std::vector<double> table(count + 1);
   auto f = [prob](float pzf) {
     const double pz = static_cast<double>(pzf);
     return prob ? std::log(pz) : pz * pz * pz;
   };
   for (size_t i = 0; i < count; ++i) table[i] = f(field_host_[i]);
+  table[count] = f(static_cast<float>(1. / p.max_laser_distance));  // spare cell for out-of-grid end points
   BB_CHECK(cudaStreamSynchronize(stream_));
   cudaFree(table_);
   table_ = nullptr;
-  BB_CHECK(dev_alloc(&table_, count));
-  BB_CHECK(cudaMemcpyAsync(table_, table.data(), count * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  BB_CHECK(dev_alloc(&table_, count + 1));
+  BB_CHECK(cudaMemcpyAsync(table_, table.data(), (count + 1) * sizeof(double), cudaMemcpyHostToDevice, stream_));
   BB_CHECK(cudaStreamSynchronize(stream_));
   // Tiled copy (4x4-cell tiles, Z-order inside) for the beam-parallel lookup kernel.
   const int tiles_x = (g.width + 3) / 4, tiles_y = (g.height + 3) / 4;
   const double unknown = f(static_cast<float>(1. / p.max_laser_distance));
-  std::vector<double> tiled(static_cast<size_t>(tiles_x) * tiles_y * 16, unknown);
+  if (static_cast<size_t>(tiles_x) * tiles_y * 16 + 64 >= (1ull << 32)) return fail(BB200_ERR_CAPACITY, "map too large for 32-bit cell indices");
+  std::vector<double> tiled(static_cast<size_t>(tiles_x) * tiles_y * 16 + 1, unknown);
   for (int yi = 0; yi < g.height; ++yi)
     for (int xi = 0; xi < g.width; ++xi) tiled[tiled_index(xi, yi, tiles_x)] = table[static_cast<size_t>(yi) * g.width + xi];
   cudaFree(tiled_);
@@ -274,6 +278,8 @@ int Filter::set_likelihood_field_map(const bb200_likelihood_field_param& p, cons
   BB_CHECK(cudaStreamSynchronize(stream_));
   field_.tiled = tiled_;
   field_.tiles_x = tiles_x;
+  field_.use_tiled = tiled_layout_ ? 1 : 0;
+  field_.spare_index = static_cast<uint32_t>(tiled_layout_ ? tiled.size() - 1 : count);
 
   field_.table = table_;
   field_.width = g.width;

@@ -114,6 +114,7 @@ class Filter {
   // execution schedule (pose-sorted processing order of the reweight kernels)
   static constexpr uint64_t kScheduleMinParticles = 32768;
   bool schedule_enabled_{true};
+  bool tiled_layout_{true};
   Schedule* sched_{nullptr};
   uint32_t* bins_{nullptr};
   uint32_t* perm_{nullptr};

@@ -266,7 +266,7 @@ constexpr uint32_t kChunkBeams = 2048; // beams staged per shared-memory chunk (
 /// mantissa word of the sum is floor(g) in two's complement.
 __device__ __forceinline__ int floor_to_int_fast(double g) { return __double2loint(__dadd_rd(g, 6755399441055744.0)); }
 
-template <bool kFast>
+template <bool kFast, bool kTiled>
 __device__ __forceinline__ double field_lookup(const FieldView& f, double px, double py, double c, double s, double tx, double ty) {
   // likelihood_field_model.hpp:82-83 -- two products, one difference/sum, one offset; each rounded.
   const double x = (px * c - py * s) + tx;
@@ -284,14 +284,21 @@ __device__ __forceinline__ double field_lookup(const FieldView& f, double px, do
     xi = (fx >= 0.0 && fx < 2147483647.0) ? static_cast<int>(fx) : -1;
     yi = (fy >= 0.0 && fy < 2147483647.0) ? static_cast<int>(fy) : -1;
   }
-  // dense_grid.hpp:92-96 contains(); the table is stored in 4x4 tiles (kernels.cuh tiled_index()).
+  // dense_grid.hpp:92-96 contains().  Out-of-grid end points read the spare cell that holds
+  // f(unknown_space_occupancy_prob), so the load is unconditional (no divergent branch).
   const bool inside = static_cast<unsigned>(xi) < static_cast<unsigned>(f.width) && static_cast<unsigned>(yi) < static_cast<unsigned>(f.height);
-  double v = f.unknown_value;
-  if (inside) v = __ldg(f.tiled + tiled_index(xi, yi, f.tiles_x));
-  return v;
+  uint32_t idx;
+  if (kTiled) {
+    const uint32_t ux = static_cast<uint32_t>(xi), uy = static_cast<uint32_t>(yi);
+    idx = (((uy >> 2) * static_cast<uint32_t>(f.tiles_x) + (ux >> 2)) << 4) | ((uy & 3u) << 2) | (ux & 3u);
+  } else {
+    idx = static_cast<uint32_t>(yi) * static_cast<uint32_t>(f.width) + static_cast<uint32_t>(xi);  // linear_grid.hpp:73-75
+  }
+  idx = inside ? idx : f.spare_index;
+  return __ldg((kTiled ? f.tiled : f.table) + idx);
 }
 
-template <bool kFast>
+template <bool kFast, bool kTiled>
 __device__ __forceinline__ double accumulate_chunk(const FieldView& f, const double2* pts, uint32_t count, double acc, double c, double s,
                                                    double tx, double ty) {
   // libstdc++ std::transform_reduce (numeric:439-462): groups of four, init += ((f0+f1)+(f2+f3)).
@@ -299,16 +306,17 @@ __device__ __forceinline__ double accumulate_chunk(const FieldView& f, const dou
 #pragma unroll 2
   for (; b + 4 <= count; b += 4) {
     const double2 p0 = pts[b], p1 = pts[b + 1], p2 = pts[b + 2], p3 = pts[b + 3];
-    const double f0 = field_lookup<kFast>(f, p0.x, p0.y, c, s, tx, ty);
-    const double f1 = field_lookup<kFast>(f, p1.x, p1.y, c, s, tx, ty);
-    const double f2 = field_lookup<kFast>(f, p2.x, p2.y, c, s, tx, ty);
-    const double f3 = field_lookup<kFast>(f, p3.x, p3.y, c, s, tx, ty);
+    const double f0 = field_lookup<kFast, kTiled>(f, p0.x, p0.y, c, s, tx, ty);
+    const double f1 = field_lookup<kFast, kTiled>(f, p1.x, p1.y, c, s, tx, ty);
+    const double f2 = field_lookup<kFast, kTiled>(f, p2.x, p2.y, c, s, tx, ty);
+    const double f3 = field_lookup<kFast, kTiled>(f, p3.x, p3.y, c, s, tx, ty);
     acc = acc + ((f0 + f1) + (f2 + f3));
   }
-  for (; b < count; ++b) acc = acc + field_lookup<kFast>(f, pts[b].x, pts[b].y, c, s, tx, ty);
+  for (; b < count; ++b) acc = acc + field_lookup<kFast, kTiled>(f, pts[b].x, pts[b].y, c, s, tx, ty);
   return acc;
 }
 
+template <bool kTiled>
 __global__ void __launch_bounds__(kRwThreads, 2)
     reweight_lfm_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
                         FieldView field, const double2* __restrict__ points, uint32_t n_points, double points_radius,
@@ -351,8 +359,8 @@ __global__ void __launch_bounds__(kRwThreads, 2)
     mbarrier_wait(&s_bar, phase);
     phase ^= 1u;
     if (active) {
-      acc = fast ? accumulate_chunk<true>(field, s_pts, count, acc, t.c, t.s, t.x, t.y)
-                 : accumulate_chunk<false>(field, s_pts, count, acc, t.c, t.s, t.x, t.y);
+      acc = fast ? accumulate_chunk<true, kTiled>(field, s_pts, count, acc, t.c, t.s, t.x, t.y)
+                 : accumulate_chunk<false, kTiled>(field, s_pts, count, acc, t.c, t.s, t.x, t.y);
     }
     __syncthreads();  // everyone is done with s_pts before the next chunk overwrites it
   }
@@ -842,8 +850,13 @@ void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const
   if (n == 0) return;
   const unsigned blocks = static_cast<unsigned>((n + kRwThreads - 1) / kRwThreads);
   const size_t smem = static_cast<size_t>(n_points < kChunkBeams ? n_points : kChunkBeams) * sizeof(double2);
-  reweight_lfm_kernel<<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, reinterpret_cast<const double2*>(points_xy_device),
-                                                            n_points, points_radius, scalars);
+  if (field.use_tiled) {
+    reweight_lfm_kernel<true><<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, reinterpret_cast<const double2*>(points_xy_device),
+                                                                    n_points, points_radius, scalars);
+  } else {
+    reweight_lfm_kernel<false><<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, reinterpret_cast<const double2*>(points_xy_device),
+                                                                     n_points, points_radius, scalars);
+  }
 }
 
 void launch_reweight_beam(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const OccupancyView& grid,

@@ -11,11 +11,15 @@ namespace bb200 {
 
 /// Device view of the likelihood-field lookup table (LFM / LFM-prob).
 struct FieldView {
-  const double* table;  // f(pz) per cell, row-major (f = pz^3 or log pz)
-  // Same values in 4x4-cell tiles (one 128-byte line per tile, Z-order inside: each 32-byte sector
-  // is a 2x2 block), padded to whole tiles with unknown_value.  Index: see tiled_index().
+  // f(pz) per cell (f = pz^3 or log pz), row-major, followed by one spare cell holding
+  // unknown_value (index width*height) that out-of-grid end points read.
+  const double* table;
+  // The same values in 4x4-cell tiles (one 128-byte line per tile, row-major inside), padded to whole
+  // tiles with unknown_value, plus the spare cell at tiles_x*tiles_y*16.  Index: tiled_index().
   const double* tiled;
   int tiles_x;
+  int use_tiled;          // which of the two layouts the kernel gathers from
+  uint32_t spare_index;   // index of the spare cell in the selected layout
   int width, height;
   double inv_resolution;  // 1. / resolution  (regular_grid.hpp:76)
   double unknown_value;   // f(float(1/max_laser_distance)) for out-of-grid end points
@@ -64,8 +68,7 @@ void launch_initialize_normal(Pose2* states, double* weights, uint64_t n, const 
 BB_HD size_t tiled_index(int xi, int yi, int tiles_x) {
   const unsigned x = static_cast<unsigned>(xi), y = static_cast<unsigned>(yi);
   const size_t tile = static_cast<size_t>(y >> 2) * static_cast<size_t>(tiles_x) + (x >> 2);
-  const unsigned inner = ((y & 2u) << 2) | ((x & 2u) << 1) | ((y & 1u) << 1) | (x & 1u);
-  return tile * 16 + inner;
+  return tile * 16 + (((y & 3u) << 2) | (x & 3u));
 }
 
 /// Execution schedule state (device): cloud moments and the pose-bin grid derived from them.
