@@ -24,6 +24,10 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall",
     "-ccbin", "/usr/bin/g++",
 ]
+# Development knobs of the reweight kernel (defaults in csrc/kernels.cu).
+for _knob in ("BB200_RW_THREADS", "BB200_RW_UNROLL", "BB200_RW_BLOCKS"):
+    if os.environ.get(_knob):
+        NVCC_FLAGS.append(f"-D{_knob}=" + os.environ[_knob])
 
 
 def nvcc() -> str:

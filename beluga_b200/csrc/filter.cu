@@ -95,6 +95,7 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   if (config_.global_count == 0) config_.global_count = config_.capacity;
   if (const char* v = std::getenv("BB200_SCHEDULE")) schedule_enabled_ = std::atoi(v) != 0;  // development knob: 0 disables the pose-sorted schedule
   if (const char* v = std::getenv("BB200_TILED")) tiled_layout_ = std::atoi(v) != 0;         // development knob: table layout
+  if (const char* v = std::getenv("BB200_PER_BIN")) schedule_per_bin_ = std::atof(v);        // development knob: particles per pose bin
   capacity_ = config.capacity;
 #define BB_TRY(expr)                                \
   do {                                              \
@@ -204,7 +205,7 @@ void Filter::finish_marks() {
     events_used_ = 0;
     return;
   }
-  mark("end");
+  if (std::string(marks_.back().name) != "end") mark("end");
   cudaEventSynchronize(marks_.back().event);
   timings_.clear();
   for (size_t i = 0; i + 1 < marks_.size(); ++i) {
@@ -430,7 +431,7 @@ int Filter::enqueue_propagate_reweight(const DiffDriveSampling* sampling, uint32
   const uint32_t* perm = nullptr;
   if (scheduled) {
     mark("schedule");
-    launch_build_schedule(states_[cur_], n_, sched_, bins_, counters_, perm_, sched_tiles_, points_mean_range_, 0.5 * grid_resolution_, stream_);
+    launch_build_schedule(states_[cur_], n_, sched_, bins_, counters_, perm_, sched_tiles_, points_mean_range_, 0.5 * grid_resolution_, schedule_per_bin_, stream_);
     BB_LAUNCHED_N("schedule", 4);
     perm = perm_;
   }
@@ -691,8 +692,10 @@ int Filter::step_resample(const bb200_diff_drive_sampling& sampling, uint32_t st
   mark("reduce_partials");
   launch_reduce_partials(partials_, resample_block_count(a.slot_count), kMomentCount, results_, stream_);
   BB_LAUNCHED("reduce_partials");
+  mark("readback");
   BB_CHECK(cudaMemcpyAsync(results_host_, results_, kMomentCount * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   BB_CHECK(cudaMemcpyAsync(scalars_host_, scalars_, sizeof(Scalars), cudaMemcpyDeviceToHost, stream_));
+  mark("end");
   BB_CHECK(cudaStreamSynchronize(stream_));
   finish_marks();
 

@@ -115,6 +115,7 @@ class Filter {
   static constexpr uint64_t kScheduleMinParticles = 32768;
   bool schedule_enabled_{true};
   bool tiled_layout_{true};
+  double schedule_per_bin_{16.0};
   Schedule* sched_{nullptr};
   uint32_t* bins_{nullptr};
   uint32_t* perm_{nullptr};

@@ -17,6 +17,17 @@
 // reference's operation order without FMA contraction (the file is compiled with -fmad=false).
 #include "kernels.cuh"
 
+// Tuning knobs of the reweight kernel (overridable with -D from beluga_b200/build.py).
+#ifndef BB200_RW_THREADS
+#define BB200_RW_THREADS 256
+#endif
+#ifndef BB200_RW_UNROLL
+#define BB200_RW_UNROLL 2
+#endif
+#ifndef BB200_RW_BLOCKS
+#define BB200_RW_BLOCKS (1024 / BB200_RW_THREADS)
+#endif
+
 #include <algorithm>
 #include <cfloat>
 
@@ -198,7 +209,7 @@ __global__ void schedule_reset_kernel(Schedule* sched) {
   sched->tile_ticket = 0;
 }
 
-__global__ void schedule_params_kernel(Schedule* sched, uint64_t n, double mean_range, double min_bin) {
+__global__ void schedule_params_kernel(Schedule* sched, uint64_t n, double mean_range, double min_bin, double per_bin) {
   const double inv_n = 1.0 / static_cast<double>(n);
   const double cbar = sched->sums[0] * inv_n, sbar = sched->sums[1] * inv_n;
   const double mx = sched->sums[2] * inv_n, my = sched->sums[3] * inv_n;
@@ -213,9 +224,9 @@ __global__ void schedule_params_kernel(Schedule* sched, uint64_t n, double mean_
   }
   const double half_theta = fmin(pi, fmax(3.0 * sigma_theta, 1e-4));
   const double half_x = fmax(3.0 * sqrt(vx), min_bin), half_y = fmax(3.0 * sqrt(vy), min_bin);
-  // Bins of equal physical edge q in (range * theta, x, y), about 16 particles per bin.
+  // Bins of equal physical edge q in (range * theta, x, y), about `per_bin` particles per bin.
   const double ext_t = 2.0 * half_theta * fmax(mean_range, 1.0), ext_x = 2.0 * half_x, ext_y = 2.0 * half_y;
-  double q = cbrt(ext_t * ext_x * ext_y / fmax(static_cast<double>(n) / 16.0, 1.0));
+  double q = cbrt(ext_t * ext_x * ext_y / fmax(static_cast<double>(n) / per_bin, 1.0));
   q = fmax(q, min_bin);
   uint32_t nt, nx, ny;
   for (;;) {
@@ -259,7 +270,9 @@ __global__ void __launch_bounds__(256) schedule_scatter_kernel(const uint32_t* _
 
 // ---- reweight (likelihood field; a3 + a5) --------------------------------------------------------
 
-constexpr int kRwThreads = 512;        // 2 CTAs per SM at <= 64 registers
+constexpr int kRwThreads = BB200_RW_THREADS;  // x kRwBlocksPerSm CTAs per SM
+constexpr int kRwBlocksPerSm = BB200_RW_BLOCKS;
+constexpr int kRwUnroll = BB200_RW_UNROLL;  // groups of four beams in flight per thread
 constexpr uint32_t kChunkBeams = 2048; // beams staged per shared-memory chunk (32 KB), multiple of 4
 
 /// floor(g) as int32 for |g| < 2^31 through one round-down add: g + 1.5*2^52 has ulp 1, so the low
@@ -303,7 +316,7 @@ __device__ __forceinline__ double accumulate_chunk(const FieldView& f, const dou
                                                    double tx, double ty) {
   // libstdc++ std::transform_reduce (numeric:439-462): groups of four, init += ((f0+f1)+(f2+f3)).
   uint32_t b = 0;
-#pragma unroll 2
+#pragma unroll kRwUnroll
   for (; b + 4 <= count; b += 4) {
     const double2 p0 = pts[b], p1 = pts[b + 1], p2 = pts[b + 2], p3 = pts[b + 3];
     const double f0 = field_lookup<kFast, kTiled>(f, p0.x, p0.y, c, s, tx, ty);
@@ -316,21 +329,44 @@ __device__ __forceinline__ double accumulate_chunk(const FieldView& f, const dou
   return acc;
 }
 
+/// Block-wide max of the weight bit patterns without a closing barrier: every warp folds its max
+/// into a shared word and the last warp to arrive publishes the block's value.  Warps that finish
+/// their beams early retire instead of idling at a __syncthreads.
+__device__ __forceinline__ void publish_weight_max(unsigned long long bits, unsigned long long* s_max, unsigned int* s_arrived,
+                                                   unsigned int n_warps, Scalars* scalars) {
+#pragma unroll
+  for (int off = kWarp / 2; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_down_sync(0xffffffffu, bits, off);
+    bits = o > bits ? o : bits;
+  }
+  if (threadIdx.x % kWarp == 0) {
+    atomicMax(s_max, bits);
+    __threadfence_block();
+    if (atomicAdd(s_arrived, 1u) + 1u == n_warps) {
+      const unsigned long long m = atomicMax(s_max, 0ull);  // read the final value
+      if (m != 0) atomicMax(&scalars->wmax_bits, m);
+    }
+  }
+}
+
 template <bool kTiled>
-__global__ void __launch_bounds__(kRwThreads, 2)
+__global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     reweight_lfm_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
                         FieldView field, const double2* __restrict__ points, uint32_t n_points, double points_radius,
                         Scalars* __restrict__ scalars) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* s_pts = reinterpret_cast<double2*>(smem_raw);
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ unsigned long long s_red[kRwThreads / kWarp];
+  __shared__ unsigned long long s_max;
+  __shared__ unsigned int s_arrived;
 
   const uint64_t slot = static_cast<uint64_t>(blockIdx.x) * kRwThreads + threadIdx.x;
   const bool active = slot < n;
   const uint64_t i = active ? (perm != nullptr ? perm[slot] : slot) : 0;
 
   if (threadIdx.x == 0) {
+    s_max = 0ull;
+    s_arrived = 0u;
     mbarrier_init(&s_bar, 1);
     mbarrier_init_fence();
   }
@@ -347,7 +383,7 @@ __global__ void __launch_bounds__(kRwThreads, 2)
   const bool fast = reach < 1073741824.0;  // false for NaN
   double acc = field.init;
   uint32_t phase = 0;
-  __syncthreads();  // barrier initialised
+  __syncthreads();  // barrier and s_max initialised
   for (uint32_t base = 0; base < n_points; base += kChunkBeams) {
     const uint32_t count = min(kChunkBeams, n_points - base);
     if (threadIdx.x == 0) {
@@ -362,15 +398,14 @@ __global__ void __launch_bounds__(kRwThreads, 2)
       acc = fast ? accumulate_chunk<true, kTiled>(field, s_pts, count, acc, t.c, t.s, t.x, t.y)
                  : accumulate_chunk<false, kTiled>(field, s_pts, count, acc, t.c, t.s, t.x, t.y);
     }
-    __syncthreads();  // everyone is done with s_pts before the next chunk overwrites it
+    if (base + kChunkBeams < n_points) __syncthreads();  // s_pts is about to be overwritten by the next chunk
   }
   if (active) {
     const double likelihood = field.exp_epilogue ? exp(acc) : acc;
     w = w * likelihood;  // actions/reweight.hpp:54-60
     weights[i] = w;
   }
-  const unsigned long long m = block_max_u64<kRwThreads>(active ? weight_order_bits(w) : 0ull, s_red);
-  if (threadIdx.x == 0 && m != 0) atomicMax(&scalars->wmax_bits, m);
+  publish_weight_max(active ? weight_order_bits(w) : 0ull, &s_max, &s_arrived, kRwThreads / kWarp, scalars);
 }
 
 // ---- reweight (beam model; a4 + a5) -----------------------------------------------------------
@@ -790,13 +825,13 @@ __global__ void __launch_bounds__(kStreamThreads) moments_kernel(const Pose2* __
 }
 
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, uint32_t n_partials, int width, double* __restrict__ out) {
+  // One block per column; fixed summation order (thread-strided, then the block tree).
   __shared__ double s_red[256 / kWarp];
-  for (int k = 0; k < width; ++k) {
-    double v = 0.0;
-    for (uint32_t r = threadIdx.x; r < n_partials; r += 256) v = v + partials[static_cast<size_t>(r) * width + k];
-    const double total = block_sum<256>(v, s_red);
-    if (threadIdx.x == 0) out[k] = total;
-  }
+  const int k = blockIdx.x;
+  double v = 0.0;
+  for (uint32_t r = threadIdx.x; r < n_partials; r += 256) v = v + partials[static_cast<size_t>(r) * width + k];
+  const double total = block_sum<256>(v, s_red);
+  if (threadIdx.x == 0) out[k] = total;
 }
 
 int ceil_log2_u64(uint64_t n) {
@@ -834,12 +869,12 @@ uint32_t schedule_max_bins() { return kMaxBins; }
 uint32_t schedule_tile_count() { return (kMaxBins + kScanTile - 1) / kScanTile; }
 
 void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uint32_t* bins, uint32_t* counters, uint32_t* perm,
-                           unsigned long long* tile_state, double mean_range, double min_bin, cudaStream_t stream) {
+                           unsigned long long* tile_state, double mean_range, double min_bin, double per_bin, cudaStream_t stream) {
   if (n == 0) return;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   cudaMemsetAsync(counters, 0, kMaxBins * sizeof(uint32_t), stream);
   cudaMemsetAsync(tile_state, 0, schedule_tile_count() * sizeof(unsigned long long), stream);
-  schedule_params_kernel<<<1, 1, 0, stream>>>(sched, n, mean_range, min_bin);
+  schedule_params_kernel<<<1, 1, 0, stream>>>(sched, n, mean_range, min_bin, per_bin);
   schedule_histogram_kernel<<<blocks, 256, 0, stream>>>(states, n, sched, bins, counters);
   scan_counters_kernel<<<schedule_tile_count(), kScanThreads, 0, stream>>>(counters, kMaxBins, sched, tile_state);
   schedule_scatter_kernel<<<blocks, 256, 0, stream>>>(bins, n, counters, perm);
@@ -912,7 +947,7 @@ void launch_moments(const Pose2* states, const double* weights, uint64_t n, doub
 }
 
 void launch_reduce_partials(const double* partials, uint32_t n_partials, int width, double* out, cudaStream_t stream) {
-  reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, n_partials, width, out);
+  reduce_partials_kernel<<<width, 256, 0, stream>>>(partials, n_partials, width, out);
 }
 
 }  // namespace bb200

@@ -88,7 +88,7 @@ uint32_t schedule_max_bins();
 uint32_t schedule_tile_count();
 /// Counting sort of the particle indices over pose bins -> perm (needs launch_propagate's moments).
 void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uint32_t* bins, uint32_t* counters, uint32_t* perm,
-                           unsigned long long* tile_state, double mean_range, double min_bin, cudaStream_t stream);
+                           unsigned long long* tile_state, double mean_range, double min_bin, double per_bin, cudaStream_t stream);
 /// reweight with the likelihood-field table in schedule order (perm may be null) | block max.
 void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const FieldView& field,
                          const double* points_xy_device, uint32_t n_points, double points_radius, Scalars* scalars, cudaStream_t stream);

@@ -148,6 +148,22 @@ def test_reweight_far_away_particles(bb, orc, scene):
     assert np.array_equal(got, exp)
 
 
+def test_reweight_cell_boundaries(bb, orc, scene):
+    """End points exactly on (and one ulp either side of) cell boundaries: the guarded FMA evaluation
+    must hand these to the exact operation sequence and land in the reference's cell."""
+    res = scene.resolution
+    rng = np.random.default_rng(17)
+    k = rng.integers(5, 150, (400, 2)).astype(np.float64)
+    states = np.array([orc.se2(a * res, b * res, 0.0) for a, b in k])
+    states = np.concatenate([states, np.array([orc.se2(a * res, b * res, np.pi / 2) for a, b in k[:200]])])
+    m = rng.integers(-40, 40, (96, 2)).astype(np.float64) * res
+    pts = np.concatenate([m, np.nextafter(m, np.inf), np.nextafter(m, -np.inf)])
+    params = dict(max_obstacle_distance=2.0, max_laser_distance=100.0, z_hit=0.5, z_random=0.5, sigma_hit=0.2)
+    got = gpu_weights(bb, 0, bb.LikelihoodFieldModelParam(**params), scene.cells, res, orc.IDENTITY, pts, states)
+    exp = orc.sensor_weights(0, orc.LfmParam(**params), orc.Grid(scene.cells, res), pts, states)
+    assert np.array_equal(got, exp)
+
+
 def test_reweight_beam_matches_oracle(bb, orc, scene):
     rng = np.random.default_rng(5)
     extent = scene.cells.shape[0] * scene.resolution

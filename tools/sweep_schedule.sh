@@ -1,9 +1,10 @@
 #!/bin/bash
-# Development A/B of the dev knobs (results must be identical; only time differs).
+# Development A/B: unroll / occupancy of the reweight kernel (rebuilds the library on the box each time).
 mkdir -p gpurun_out
-for cfg in "BB200_TILED=0" "BB200_TILED=1" "BB200_TILED=0 BB200_SCHEDULE=0"; do
+for cfg in "BB200_RW_UNROLL=1 BB200_RW_BLOCKS=4" "BB200_RW_UNROLL=2 BB200_RW_BLOCKS=4" "BB200_RW_UNROLL=4 BB200_RW_BLOCKS=4" "BB200_RW_UNROLL=1 BB200_RW_BLOCKS=5" "BB200_RW_UNROLL=2 BB200_RW_BLOCKS=3" "BB200_RW_UNROLL=4 BB200_RW_BLOCKS=2" "BB200_RW_UNROLL=1 BB200_RW_BLOCKS=6"; do
   echo "=== $cfg"
-  env $cfg timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+  env $cfg python -m beluga_b200.build --force -v 2>&1 | grep -A2 "reweight_lfm_kernelILb1" | grep -E "Used|spill" | tr '\n' ' '; echo
+  timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'frac', round(d['roofline']['frac'],3), {k: round(v,4) for k,v in d['kernels_ms'].items()}, 'err', round(d['config']['final_position_error_m'],6))"
+d=json.loads(sys.stdin.read()); print('value', round(d['value'],1), 'rw_ms', round(d['kernels_ms']['reweight_lfm'],4), 'err', round(d['config']['final_position_error_m'],6))"
 done
