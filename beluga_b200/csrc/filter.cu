@@ -594,25 +594,17 @@ int Filter::estimate(bb200_estimate* out) {
   return BB200_OK;
 }
 
-int Filter::resample(const bb200_resample_opts& o, uint64_t* new_size) {
-  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
-  if (o.max_particles == 0 || o.max_particles > capacity_) return fail(BB200_ERR_CAPACITY, "max_particles exceeds the filter capacity");
-  if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
-  if (o.min_particles < o.max_particles) return fail(BB200_ERR_STATE, "KLD-adaptive resampling is not enabled in this build");
-  int st = ensure_cdf_ready();
-  if (st != BB200_OK && !cdf_valid_) return st;
-  BB_CHECK(cudaSetDevice(config_.device));
-
+ResampleArgs Filter::make_resample_args(const bb200_resample_opts& o, uint64_t slot_begin, uint64_t slot_end, bool with_hashes) const {
   ResampleArgs a{};
   a.states_in = states_[cur_];
   a.cdf = cdf_;
   a.n_in = n_;
-  a.states_out = states_[cur_ ^ 1];
-  a.weights_out = weights_;
-  a.ancestors = ancestors_;
-  a.hashes = nullptr;
-  a.slot_first = config_.first_index;
-  a.slot_count = o.max_particles;
+  a.states_out = states_[cur_ ^ 1] + slot_begin;
+  a.weights_out = weights_ + slot_begin;
+  a.ancestors = ancestors_ != nullptr ? ancestors_ + slot_begin : nullptr;
+  a.hashes = with_hashes ? hashes_ + slot_begin : nullptr;
+  a.slot_first = config_.first_index + slot_begin;
+  a.slot_count = slot_end - slot_begin;
   a.total_slots = o.max_particles;
   a.scheme = o.scheme;
   a.seed = config_.seed;
@@ -626,16 +618,71 @@ int Filter::resample(const bb200_resample_opts& o, uint64_t* new_size) {
   for (int k = 0; k < 3; ++k) a.hash_resolution[k] = o.spatial_resolution[k];
   a.pivot_x = pivot_[0];
   a.pivot_y = pivot_[1];
-  mark("resample");
-  launch_resample(a, scalars_, partials_, stream_);
-  BB_LAUNCHED("resample");
-  BB_CHECK(cudaStreamSynchronize(stream_));
+  return a;
+}
+
+int Filter::resample(const bb200_resample_opts& o, uint64_t* new_size) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  if (o.max_particles == 0 || o.max_particles > capacity_) return fail(BB200_ERR_CAPACITY, "max_particles exceeds the filter capacity");
+  if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
+  int st = ensure_cdf_ready();
+  if (st != BB200_OK && !cdf_valid_) return st;
+  BB_CHECK(cudaSetDevice(config_.device));
+  // The weight array is reused for the output (all ones); the CDF already holds what sampling needs.
+  uint64_t m = o.max_particles;
+  if (o.min_particles >= o.max_particles) {
+    // take_while_kld never stops before max when min == max (take_while_kld.hpp:86-87,136).
+    mark("resample");
+    launch_resample(make_resample_args(o, 0, o.max_particles, false), scalars_, partials_, stream_);
+    BB_LAUNCHED("resample");
+    BB_CHECK(cudaStreamSynchronize(stream_));
+  } else {
+    st = resample_kld(o, &m);
+    if (st != BB200_OK) return st;
+  }
   finish_marks();
   cur_ ^= 1;
-  n_ = o.max_particles;
+  n_ = m;
   ancestors_n_ = n_;
   cdf_valid_ = false;
   if (new_size != nullptr) *new_size = n_;
+  return BB200_OK;
+}
+
+int Filter::resample_kld(const bb200_resample_opts& o, uint64_t* accepted) {
+  if (config_.global_count != capacity_ || config_.first_index != 0) return fail(BB200_ERR_STATE, "KLD-adaptive resampling runs on a single shard");
+  if (hashes_ == nullptr) {
+    BB_CHECK(dev_alloc(&hashes_, capacity_));
+    BB_CHECK(dev_alloc(&kld_flags_, capacity_));
+    BB_CHECK(dev_alloc(&kld_scan_, capacity_));
+    kld_table_size_ = 2;
+    while (kld_table_size_ < 2 * capacity_) kld_table_size_ <<= 1;
+    BB_CHECK(dev_alloc(&kld_keys_, kld_table_size_));
+    BB_CHECK(dev_alloc(&kld_vals_, kld_table_size_));
+  }
+  mark("kld");
+  launch_kld_clear(kld_keys_, kld_vals_, kld_table_size_, stream_);
+  const uint64_t max = o.max_particles;
+  uint64_t begin = 0, k_before = 0;
+  uint64_t end = std::min<uint64_t>(max, std::max<uint64_t>(2 * o.min_particles, 65536));
+  *accepted = max;
+  while (begin < max) {
+    launch_resample(make_resample_args(o, begin, end, true), scalars_, partials_, stream_);
+    BB_LAUNCHED("resample");
+    KldArgs k{hashes_ + begin, end - begin, begin, k_before, o.min_particles, o.kld_epsilon, o.kld_z};
+    launch_kld_chunk(k, kld_keys_, kld_vals_, kld_table_size_, kld_flags_, kld_scan_, scalars_, tile_state_, stream_);
+    BB_LAUNCHED_N("kld", 5);
+    BB_CHECK(cudaMemcpyAsync(scalars_host_, scalars_, sizeof(Scalars), cudaMemcpyDeviceToHost, stream_));
+    BB_CHECK(cudaStreamSynchronize(stream_));
+    if (scalars_host_->kld_cutoff != ~0ull) {
+      // take_while drops the first element whose condition fails (take_while_kld.hpp:134-136).
+      *accepted = std::min<uint64_t>(scalars_host_->kld_cutoff - 1, max);
+      break;
+    }
+    k_before += scalars_host_->pad[1];
+    begin = end;
+    end = std::min<uint64_t>(max, end * 2);
+  }
   return BB200_OK;
 }
 
@@ -644,7 +691,7 @@ int Filter::step_resample(const bb200_diff_drive_sampling& sampling, uint32_t st
   if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
   if (sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set");
   if (o.max_particles == 0 || o.max_particles > capacity_) return fail(BB200_ERR_CAPACITY, "max_particles exceeds the filter capacity");
-  if (o.min_particles < o.max_particles) return fail(BB200_ERR_STATE, "KLD-adaptive resampling is not enabled in this build");
+  if (o.min_particles < o.max_particles) return fail(BB200_ERR_STATE, "the fused step does not run KLD; use resample()");
   if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
   BB_CHECK(cudaSetDevice(config_.device));
   int st = upload_points(points_xy, n_points);
@@ -663,29 +710,7 @@ int Filter::step_resample(const bb200_diff_drive_sampling& sampling, uint32_t st
   launch_quantize_scan(weights_, n_, cdf_, scalars_, tile_state_, stream_);
   BB_LAUNCHED("quantize_scan");
 
-  ResampleArgs a{};
-  a.states_in = states_[cur_];
-  a.cdf = cdf_;
-  a.n_in = n_;
-  a.states_out = states_[cur_ ^ 1];
-  a.weights_out = weights_;
-  a.ancestors = ancestors_;
-  a.hashes = nullptr;
-  a.slot_first = config_.first_index;
-  a.slot_count = o.max_particles;
-  a.total_slots = o.max_particles;
-  a.scheme = o.scheme;
-  a.seed = config_.seed;
-  a.step = o.step;
-  a.random_state_probability = o.random_state_probability;
-  a.free_cells = free_cells_;
-  a.n_free = n_free_;
-  a.grid_width = grid_width_;
-  a.grid_resolution = grid_resolution_;
-  a.grid_origin = grid_origin_;
-  for (int k = 0; k < 3; ++k) a.hash_resolution[k] = o.spatial_resolution[k];
-  a.pivot_x = pivot_[0];
-  a.pivot_y = pivot_[1];
+  const ResampleArgs a = make_resample_args(o, 0, o.max_particles, false);
   mark("resample");
   launch_resample(a, scalars_, partials_, stream_);
   BB_LAUNCHED("resample");

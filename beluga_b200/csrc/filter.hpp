@@ -64,6 +64,8 @@ class Filter {
   int upload_points(const double* points_xy, uint64_t n_points);
   int enqueue_propagate_reweight(const DiffDriveSampling* sampling, uint32_t step, bool do_reweight, uint64_t n_points);
   int ensure_cdf_ready();
+  int resample_kld(const bb200_resample_opts& o, uint64_t* accepted);
+  ResampleArgs make_resample_args(const bb200_resample_opts& o, uint64_t slot_begin, uint64_t slot_end, bool with_hashes) const;
   void estimate_from_moments(const double m[kMomentCount], bb200_estimate* out) const;
   void mark(const char* name);  // timing: record an event before the next kernel
   void finish_marks();
@@ -101,8 +103,8 @@ class Filter {
   unsigned long long* kld_keys_{nullptr};
   unsigned int* kld_vals_{nullptr};
   uint64_t kld_table_size_{0};
-  unsigned int* kld_flags_{nullptr};
-  unsigned long long* kld_scan_{nullptr};
+  uint32_t* kld_flags_{nullptr};
+  uint32_t* kld_scan_{nullptr};
 
   // measurement
   double* points_{nullptr};

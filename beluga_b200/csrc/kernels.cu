@@ -25,7 +25,7 @@
 #define BB200_RW_UNROLL 2
 #endif
 #ifndef BB200_RW_BLOCKS
-#define BB200_RW_BLOCKS (1024 / BB200_RW_THREADS)
+#define BB200_RW_BLOCKS 3
 #endif
 
 #include <algorithm>
@@ -670,13 +670,14 @@ __global__ void __launch_bounds__(kScanThreads) quantize_scan_kernel(const doubl
   if (base <= n - 1 && n - 1 < base + kScanItems) scalars->total = prefix + inclusive;  // thread holding the last element
 }
 
-/// Exclusive prefix sum of the bin counters (same decoupled look-back machinery, u32 payload).
-__global__ void __launch_bounds__(kScanThreads) scan_counters_kernel(uint32_t* __restrict__ counters, uint32_t n, Schedule* sched,
-                                                                     unsigned long long* tile_state) {
+/// Exclusive prefix sum of u32 values (bin counters, KLD first-occurrence flags) with the same
+/// decoupled look-back machinery; `in` and `out` may alias.
+__global__ void __launch_bounds__(kScanThreads) scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, unsigned long long* ticket,
+                                                                unsigned long long* tile_state, unsigned long long* total_out) {
   __shared__ unsigned long long s_warp[kScanThreads / kWarp];
   __shared__ unsigned long long s_prefix;
   __shared__ uint32_t s_tile;
-  if (threadIdx.x == 0) s_tile = static_cast<uint32_t>(atomicAdd(&sched->tile_ticket, 1ull));
+  if (threadIdx.x == 0) s_tile = static_cast<uint32_t>(atomicAdd(ticket, 1ull));
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
@@ -684,7 +685,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_counters_kernel(uint32_t* _
   unsigned long long local = 0;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    q[k] = base + k < n ? counters[base + k] : 0u;
+    q[k] = base + k < n ? in[base + k] : 0u;
     local += q[k];
   }
   unsigned long long tile_total;
@@ -693,9 +694,80 @@ __global__ void __launch_bounds__(kScanThreads) scan_counters_kernel(uint32_t* _
   unsigned long long running = prefix + inclusive - local;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    if (base + k < n) counters[base + k] = static_cast<uint32_t>(running);
+    if (base + k < n) out[base + k] = static_cast<uint32_t>(running);
     running += q[k];
   }
+  if (total_out != nullptr && base <= n - 1 && n - 1 < base + kScanItems) *total_out = prefix + inclusive;
+}
+
+// ---- KLD-adaptive sample size (a12) -----------------------------------------------------------------
+// views::take_while_kld (views/take_while_kld.hpp:72-137) keeps drawing while
+//   count <= min  ||  count <= target(k),   k = number of distinct spatial-hash buckets so far,
+// a sequential early exit over an unordered_set.  Here candidate slots are generated in chunks;
+// a device hash set keeps, per bucket, the SMALLEST slot index that produced it, so "slot j is the
+// first occurrence of its bucket" is an order-independent fact; a prefix sum of those flags gives
+// k after every slot and the first failing count is a min-reduction.
+
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+__device__ __forceinline__ uint64_t kld_probe_start(unsigned long long key, uint64_t mask) {
+  unsigned long long h = key * 0x9E3779B97F4A7C15ull;
+  return (h ^ (h >> 29)) & mask;
+}
+
+__global__ void __launch_bounds__(256) kld_insert_kernel(const unsigned long long* __restrict__ hashes, uint64_t n, uint64_t slot_base,
+                                                         unsigned long long* keys, unsigned int* vals, uint64_t mask) {
+  const uint64_t j = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (j >= n) return;
+  unsigned long long key = hashes[j];
+  if (key == kEmptyKey) key = kEmptyKey - 1;  // the sentinel itself cannot be stored (2^-64 event)
+  uint64_t pos = kld_probe_start(key, mask);
+  for (;;) {
+    const unsigned long long prev = atomicCAS(keys + pos, kEmptyKey, key);
+    if (prev == kEmptyKey || prev == key) {
+      atomicMin(vals + pos, static_cast<unsigned int>(slot_base + j));
+      return;
+    }
+    pos = (pos + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(256) kld_flag_kernel(const unsigned long long* __restrict__ hashes, uint64_t n, uint64_t slot_base,
+                                                       const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ vals,
+                                                       uint64_t mask, uint32_t* __restrict__ flags) {
+  const uint64_t j = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (j >= n) return;
+  unsigned long long key = hashes[j];
+  if (key == kEmptyKey) key = kEmptyKey - 1;
+  uint64_t pos = kld_probe_start(key, mask);
+  while (keys[pos] != key) pos = (pos + 1) & mask;
+  flags[j] = vals[pos] == static_cast<unsigned int>(slot_base + j) ? 1u : 0u;
+}
+
+/// kld_condition target size (views/take_while_kld.hpp:73-80), same operation order as the reference.
+__device__ __forceinline__ bool kld_count_allowed(unsigned long long count, unsigned long long k, unsigned long long min_count, double two_epsilon, double z) {
+  if (count <= min_count || k <= 2ull) return true;
+  const double common = 2. / static_cast<double>(9 * (k - 1));
+  const double base = 1. - common + sqrt(common) * z;
+  const double result = (static_cast<double>(k - 1) / two_epsilon) * base * base * base;
+  const double target = ceil(result);
+  return target >= 18446744073709551615.0 || count <= static_cast<unsigned long long>(target);
+}
+
+__global__ void __launch_bounds__(256) kld_check_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ exclusive, uint64_t n,
+                                                        uint64_t slot_base, unsigned long long k_before, unsigned long long min_count,
+                                                        double two_epsilon, double z, Scalars* scalars) {
+  const uint64_t j = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (j >= n) return;
+  const unsigned long long count = slot_base + j + 1;
+  const unsigned long long k = k_before + exclusive[j] + flags[j];
+  if (!kld_count_allowed(count, k, min_count, two_epsilon, z)) atomicMin(&scalars->kld_cutoff, count);
+}
+
+__global__ void kld_reset_kernel(Scalars* scalars) {
+  scalars->kld_cutoff = ~0ull;
+  scalars->pad[0] = 0;  // tile ticket of the flag scan
+  scalars->pad[1] = 0;  // distinct buckets in the chunk
 }
 
 // ---- normalize -------------------------------------------------------------------------------------
@@ -876,7 +948,7 @@ void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uin
   cudaMemsetAsync(tile_state, 0, schedule_tile_count() * sizeof(unsigned long long), stream);
   schedule_params_kernel<<<1, 1, 0, stream>>>(sched, n, mean_range, min_bin, per_bin);
   schedule_histogram_kernel<<<blocks, 256, 0, stream>>>(states, n, sched, bins, counters);
-  scan_counters_kernel<<<schedule_tile_count(), kScanThreads, 0, stream>>>(counters, kMaxBins, sched, tile_state);
+  scan_u32_kernel<<<schedule_tile_count(), kScanThreads, 0, stream>>>(counters, counters, kMaxBins, &sched->tile_ticket, tile_state, nullptr);
   schedule_scatter_kernel<<<blocks, 256, 0, stream>>>(bins, n, counters, perm);
 }
 
@@ -927,6 +999,24 @@ void launch_normalize(double* weights, uint64_t n, const Scalars* scalars, unsig
   const unsigned blocks = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>((n + kStreamThreads - 1) / kStreamThreads, kStreamMaxBlocks)));
   *n_partials = blocks;
   normalize_kernel<<<blocks, kStreamThreads, 0, stream>>>(weights, n, scalars, global_total, partials);
+}
+
+void launch_kld_clear(unsigned long long* keys, unsigned int* vals, uint64_t table_size, cudaStream_t stream) {
+  cudaMemsetAsync(keys, 0xFF, table_size * sizeof(unsigned long long), stream);
+  cudaMemsetAsync(vals, 0xFF, table_size * sizeof(unsigned int), stream);
+}
+
+void launch_kld_chunk(const KldArgs& a, unsigned long long* keys, unsigned int* vals, uint64_t table_size, uint32_t* flags, uint32_t* exclusive,
+                      Scalars* scalars, unsigned long long* tile_state, cudaStream_t stream) {
+  if (a.n == 0) return;
+  const unsigned blocks = static_cast<unsigned>((a.n + 255) / 256);
+  const uint32_t tiles = static_cast<uint32_t>((a.n + kScanTile - 1) / kScanTile);
+  kld_reset_kernel<<<1, 1, 0, stream>>>(scalars);
+  cudaMemsetAsync(tile_state, 0, static_cast<size_t>(tiles) * sizeof(unsigned long long), stream);
+  kld_insert_kernel<<<blocks, 256, 0, stream>>>(a.hashes, a.n, a.slot_base, keys, vals, table_size - 1);
+  kld_flag_kernel<<<blocks, 256, 0, stream>>>(a.hashes, a.n, a.slot_base, keys, vals, table_size - 1, flags);
+  scan_u32_kernel<<<tiles, kScanThreads, 0, stream>>>(flags, exclusive, static_cast<uint32_t>(a.n), &scalars->pad[0], tile_state, &scalars->pad[1]);
+  kld_check_kernel<<<blocks, 256, 0, stream>>>(flags, exclusive, a.n, a.slot_base, a.k_before, a.min_particles, 2 * a.epsilon, a.z, scalars);
 }
 
 uint32_t resample_block_count(uint64_t slots) {

@@ -145,16 +145,20 @@ void launch_moments(const Pose2* states, const double* weights, uint64_t n, doub
 /// Sums `n_partials` rows of kMomentCount doubles in a fixed order into out[kMomentCount].
 void launch_reduce_partials(const double* partials, uint32_t n_partials, int width, double* out, cudaStream_t stream);
 
-/// KLD: first-occurrence flags through a device hash set, prefix count, first failing slot.
+/// KLD (views/take_while_kld.hpp:72-137) over one chunk of candidate slots [slot_base, slot_base + n):
+/// device hash set of buckets -> first-occurrence flags -> prefix count -> first failing count in
+/// scalars->kld_cutoff (1-based; ~0 when every count in the chunk passes); scalars->pad[1] receives
+/// the number of new buckets of the chunk.
 struct KldArgs {
-  const unsigned long long* hashes;
-  uint64_t n;            // slots examined
-  uint64_t count_offset; // slots accepted before this chunk
+  const unsigned long long* hashes;  // spatial hash of each candidate of the chunk
+  uint64_t n;
+  uint64_t slot_base;     // slots accepted before this chunk
+  uint64_t k_before;      // distinct buckets before this chunk
   uint64_t min_particles;
   double epsilon, z;
 };
-void launch_kld_cutoff(const KldArgs& args, unsigned long long* table_keys, unsigned int* table_vals, uint64_t table_size,
-                       unsigned int* first_flags, unsigned long long* flag_scan, Scalars* scalars, unsigned long long* tile_state,
-                       cudaStream_t stream);
+void launch_kld_clear(unsigned long long* keys, unsigned int* vals, uint64_t table_size, cudaStream_t stream);
+void launch_kld_chunk(const KldArgs& args, unsigned long long* keys, unsigned int* vals, uint64_t table_size, uint32_t* flags,
+                      uint32_t* exclusive, Scalars* scalars, unsigned long long* tile_state, cudaStream_t stream);
 
 }  // namespace bb200

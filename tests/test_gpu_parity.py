@@ -277,6 +277,58 @@ def test_estimate_known_answers(bb, orc):
     assert math.isinf(cov[2, 2]) and np.allclose(mean, orc.se2(0.0, 0.0, 0.0), atol=1e-3)
 
 
+# ---- KLD-adaptive sample size (views/test_take_while_kld.cpp) ------------------------------------------
+def kld_count_on_gpu(bb, orc, buckets, min_particles, max_particles, epsilon, z):
+    """Runs take_while_kld on the GPU over a prescribed bucket sequence: particle j sits in bucket
+    buckets[j]; equal weights + the systematic comb make output slot j a copy of particle j."""
+    buckets = np.asarray(buckets)
+    n = len(buckets)
+    assert n == max_particles
+    states = np.tile(orc.IDENTITY, (n, 1))
+    states[:, 2] = buckets * 10.0 + 0.5  # 10 m apart: distinct x buckets of a 1 m spatial hash
+    f = bb.Filter(capacity=n, seed=9, record_ancestors=True)
+    f.set_particles(states)
+    m = f.resample(bb.RESAMPLE_SYSTEMATIC, step=1, max_particles=max_particles, min_particles=min_particles, kld_epsilon=epsilon, kld_z=z,
+                   spatial_resolution=(1.0, 1.0, 1.0))
+    assert np.array_equal(f.ancestors(), np.arange(m))
+    hashes = [orc.spatial_hash(s, 1.0, 1.0, 1.0) for s in states[:: max(1, n // 64)]]  # sanity: buckets really differ
+    assert len(set(hashes)) == len(set(buckets[:: max(1, n // 64)].tolist()))
+    return m
+
+
+@pytest.mark.parametrize(
+    "z,clusters,expected",
+    [(1.28155156327703, 3, 228), (1.28155156327703, 4, 311), (1.28155156327703, 5, 388), (1.28155156327703, 6, 461),
+     (1.28155156327703, 7, 531), (1.28155156327703, 100, 5871), (2.32634787735669, 3, 462), (2.32634787735669, 4, 569),
+     (2.32634787735669, 5, 666), (2.32634787735669, 6, 756), (2.32634787735669, 7, 843), (2.32634787735669, 100, 6733)],
+)
+def test_kld_known_answers(bb, orc, z, clusters, expected):
+    """KldConditionWithParam.Limit (views/test_take_while_kld.cpp:119-148): exact counts."""
+    n = 8192
+    buckets = np.minimum(np.arange(1, n + 1), clusters)
+    assert kld_count_on_gpu(bb, orc, buckets, 0, n, 0.01, z) == expected
+
+
+def test_kld_take_limits(bb, orc):
+    """TakeMaximum / TakeLimit / TakeMinimum (views/test_take_while_kld.cpp:159-188)."""
+    assert kld_count_on_gpu(bb, orc, np.ones(1200, dtype=int), 200, 1200, 0.05, 3.0) == 1200
+    seq = np.tile([1, 3, 2, 3], 300)
+    assert kld_count_on_gpu(bb, orc, seq, 0, 1200, 0.05, 3.0) == 135
+    assert kld_count_on_gpu(bb, orc, seq, 200, 1200, 0.05, 3.0) == 200
+
+
+def test_kld_multi_chunk(bb, orc):
+    """A cutoff beyond the first chunk of candidates (chunks double from 65536 slots)."""
+    n = 300_000
+    rng = np.random.default_rng(2)
+    buckets = rng.integers(0, 15000, n)  # ~15000 buckets: target(k) ~ 10 k = 150k > first chunk
+    got = kld_count_on_gpu(bb, orc, buckets, 1000, n, 0.05, 3.0)
+    states_x = buckets * 10.0 + 0.5
+    hashes = [orc.spatial_hash(np.array([1.0, 0.0, x, 0.0]), 1.0, 1.0, 1.0) for x in states_x]
+    assert got == orc.kld_take_count(hashes, 1000, n, 0.05, 3.0)
+    assert got > 65536
+
+
 # ---- whole-filter parity along a seeded trajectory ------------------------------------------------------
 def run_trajectory(bb, orc, scene, sensor, scheme, n, steps, selective=False, interval=1, beam_stride=1):
     motion = dict(alpha1=0.1, alpha2=0.05, alpha3=0.1, alpha4=0.05)
@@ -333,6 +385,32 @@ def test_trajectory_selective_resampling(bb, orc, scene):
 def test_trajectory_beam(bb, orc, scene):
     # erf/exp differ by ulps between CUDA and glibc, so a handful of CDF boundary flips are tolerated
     assert run_trajectory(bb, orc, scene, bb.SENSOR_BEAM, 1, n=2_000, steps=6, beam_stride=6) <= 5
+
+
+def test_trajectory_kld_adaptive(bb, orc, scene):
+    """min_particles < max_particles: the particle count follows take_while_kld step by step."""
+    motion = dict(alpha1=0.1, alpha2=0.05, alpha3=0.1, alpha4=0.05)
+    lfm = dict(max_obstacle_distance=2.0, max_laser_distance=100.0, z_hit=0.5, z_random=0.5, sigma_hit=0.2)
+    ap = dict(min_particles=500, max_particles=40_000, kld_epsilon=0.05, kld_z=3.0, seed=5)
+    res = (0.5, 0.5, float(np.deg2rad(10.0)))  # beluga_ros defaults (amcl.hpp:91-97)
+    g = bb.Amcl(bb.DifferentialDriveModelParam(0.1, 0.05, 0.1, 0.05), bb.AmclParams(resample_scheme=1, record_ancestors=True, spatial_resolution=res, **ap))
+    o = orc.Amcl(orc.AmclParam(rng_mode=1, scheme=1, spatial_resolution_x=res[0], spatial_resolution_y=res[1], spatial_resolution_theta=res[2], **ap),
+                 orc.MotionParam(**motion))
+    g.update_map(0, bb.LikelihoodFieldModelParam(**lfm), bb.OccupancyGrid(scene.cells, scene.resolution))
+    o.set_map(0, orc.LfmParam(**lfm), orc.Grid(scene.cells, scene.resolution))
+    g.initialize(scene.initial_mean, scene.initial_cov)
+    o.initialize_normal(scene.initial_mean, scene.initial_cov)
+    sizes = []
+    for k in range(8):
+        pose = orc.se2(*scene.poses[k])
+        rg, ro = g.update(pose, scene.scans[k]), o.update(pose, scene.scans[k])
+        assert rg.n_particles == ro.n_particles
+        assert rg.random_state_probability == ro.random_state_probability  # Thrun estimator reacts to the size change
+        a_g, a_o = g.filter.ancestors(), o.last_indices()
+        assert np.array_equal(a_g, a_o)
+        assert np.abs(np.array(rg.estimate.mean) - np.array(ro.mean)).max() < 1e-9
+        sizes.append(rg.n_particles)
+    assert min(sizes) < 40_000 and len(set(sizes)) > 1  # the count really adapts
 
 
 def test_update_policy_and_force_update(bb, orc, scene):
