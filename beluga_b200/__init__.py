@@ -53,6 +53,25 @@ def se2(x: float, y: float, theta: float) -> np.ndarray:
     return np.array([c / n, s / n, x, y], dtype=np.float64)
 
 
+def systematic_comb(seed: int, step: int, global_total: int, total_slots: int):
+    """(stride, offset) of the systematic resampling comb over a fixed-point CDF with the given total."""
+    stride, offset = C.c_uint64(), C.c_uint64()
+    st = _capi.load().bb200_systematic_comb(seed, step, global_total, total_slots, C.byref(stride), C.byref(offset))
+    if st != _capi.OK:
+        raise BelugaB200Error(st, "bb200_systematic_comb")
+    return stride.value, offset.value
+
+
+def estimate_from_moments(moments, pivot):
+    """beluga::estimate (algorithm/estimation.hpp:436-475) from globally summed raw moments."""
+    e = _capi.Estimate()
+    m, p = _f64(moments), _f64(pivot)
+    st = _capi.load().bb200_estimate_from_moments(m.ctypes.data_as(C.POINTER(C.c_double)), p.ctypes.data_as(C.POINTER(C.c_double)), C.byref(e))
+    if st != _capi.OK:
+        raise BelugaB200Error(st, "bb200_estimate_from_moments")
+    return np.array(e.mean), np.array(e.cov).reshape(3, 3)
+
+
 def _dptr(a: np.ndarray):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
@@ -125,12 +144,14 @@ class AmclParams:
     seed: int = 0
     device: int = 0
     record_ancestors: bool = False
+    shard_first_index: int = 0  # sharded filters: global index of this rank's first particle
+    shard_capacity: int = 0     # ... and its particle count (0: single GPU); max_particles is then the global count
 
     def c(self) -> _capi.AmclParam:
         return _capi.AmclParam(self.update_min_d, self.update_min_a, self.resample_interval, int(self.selective_resampling),
                                self.min_particles, self.max_particles, self.alpha_slow, self.alpha_fast, self.kld_epsilon,
                                self.kld_z, (C.c_double * 3)(*self.spatial_resolution), self.resample_scheme, self.seed,
-                               self.device, int(self.record_ancestors))
+                               self.device, int(self.record_ancestors), self.shard_first_index, self.shard_capacity)
 
 
 @dataclass
@@ -263,6 +284,12 @@ class Filter:
         self._check(self._lib.bb200_filter_resample(self._h, C.byref(o), C.byref(n)))
         return n.value
 
+    def resample_range(self, opts: _capi.ResampleOpts, global_total: int, cdf_offset: int, slot_begin: int, slot_end: int):
+        self._check(self._lib.bb200_filter_resample_range(self._h, C.byref(opts), global_total, cdf_offset, slot_begin, slot_end))
+
+    def adopt(self, n: int, from_staging: bool = False):
+        self._check(self._lib.bb200_filter_adopt(self._h, n, int(from_staging)))
+
     def ancestors(self) -> np.ndarray:
         out = np.zeros(self.size(), dtype=np.int64)
         self._check(self._lib.bb200_filter_ancestors(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), len(out)))
@@ -286,11 +313,15 @@ class Filter:
     def set_timing(self, enabled: bool):
         self._check(self._lib.bb200_filter_set_timing(self._h, int(enabled)))
 
+    def clear_timings(self):
+        self._check(self._lib.bb200_filter_clear_timings(self._h))
+
     def last_timings(self) -> list[tuple[str, float]]:
-        names = (C.c_char_p * 32)()
-        ms = (C.c_float * 32)()
-        n = self._lib.bb200_filter_last_timings(self._h, names, ms, 32)
-        return [(names[i].decode(), ms[i]) for i in range(min(n, 32))]
+        """(kernel, ms) pairs recorded since clear_timings()."""
+        names = (C.c_char_p * 128)()
+        ms = (C.c_float * 128)()
+        n = self._lib.bb200_filter_last_timings(self._h, names, ms, 128)
+        return [(names[i].decode(), ms[i]) for i in range(min(n, 128))]
 
     def launch_count(self) -> int:
         return self._lib.bb200_filter_launch_count(self._h)
@@ -351,6 +382,15 @@ class Amcl:
 
     def particles(self):
         return self.filter.particles()
+
+    def plan_update(self, control_pose) -> _capi.StepPlan:
+        """Host half of Amcl::update (policies, control window, recovery estimator)."""
+        plan = _capi.StepPlan()
+        self._check(self._lib.bb200_amcl_plan_update(self._h, _dptr(_f64(control_pose)), C.byref(plan)))
+        return plan
+
+    def commit_update(self, resampled: bool, random_state_probability: float):
+        self._lib.bb200_amcl_commit_update(self._h, int(resampled), random_state_probability)
 
     def update(self, control_pose, points) -> _capi.UpdateResult:
         """Amcl::update: returns the result block; `.updated == 0` is the reference's std::nullopt."""

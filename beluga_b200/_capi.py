@@ -63,7 +63,12 @@ class AmclParam(C.Structure):
                 ("selective_resampling", C.c_int), ("min_particles", C.c_uint64), ("max_particles", C.c_uint64),
                 ("alpha_slow", C.c_double), ("alpha_fast", C.c_double), ("kld_epsilon", C.c_double), ("kld_z", C.c_double),
                 ("spatial_resolution", C.c_double * 3), ("resample_scheme", C.c_int), ("seed", C.c_uint64), ("device", C.c_int),
-                ("record_ancestors", C.c_int)]
+                ("record_ancestors", C.c_int), ("shard_first_index", C.c_uint64), ("shard_capacity", C.c_uint64)]
+
+
+class StepPlan(C.Structure):
+    _fields_ = [("update", C.c_int), ("resample", C.c_int), ("needs_ess", C.c_int), ("step", C.c_uint32),
+                ("random_state_probability", C.c_double), ("sampling", DiffDriveSampling), ("opts", ResampleOpts)]
 
 
 class UpdateResult(C.Structure):
@@ -98,11 +103,16 @@ SIGNATURES = {
     "bb200_filter_normalize_by": (C.c_int, [_vp, C.c_uint64, _dbl]),
     "bb200_filter_normalize": (C.c_int, [_vp, _dbl, _dbl]),
     "bb200_filter_resample": (C.c_int, [_vp, _P(ResampleOpts), _P(C.c_uint64)]),
+    "bb200_filter_resample_range": (C.c_int, [_vp, _P(ResampleOpts), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "bb200_filter_adopt": (C.c_int, [_vp, C.c_uint64, C.c_int]),
+    "bb200_systematic_comb": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _P(C.c_uint64), _P(C.c_uint64)]),
+    "bb200_estimate_from_moments": (C.c_int, [_dbl, _dbl, _P(Estimate)]),
     "bb200_filter_ancestors": (C.c_int, [_vp, _P(C.c_int64), C.c_uint64]),
     "bb200_filter_cdf": (C.c_int, [_vp, _P(C.c_uint64), C.c_uint64]),
     "bb200_filter_estimate": (C.c_int, [_vp, _P(Estimate)]),
     "bb200_filter_moments": (C.c_int, [_vp, _dbl, _dbl]),
     "bb200_filter_set_timing": (C.c_int, [_vp, C.c_int]),
+    "bb200_filter_clear_timings": (C.c_int, [_vp]),
     "bb200_filter_last_timings": (C.c_int, [_vp, _P(C.c_char_p), _P(C.c_float), C.c_int]),
     "bb200_filter_launch_count": (C.c_uint64, [_vp]),
     "bb200_filter_synchronize": (C.c_int, [_vp]),
@@ -115,6 +125,8 @@ SIGNATURES = {
     "bb200_amcl_initialize_states": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64]),
     "bb200_amcl_force_update": (None, [_vp]),
     "bb200_amcl_update": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64, _P(UpdateResult)]),
+    "bb200_amcl_plan_update": (C.c_int, [_vp, _dbl, _P(StepPlan)]),
+    "bb200_amcl_commit_update": (None, [_vp, C.c_int, C.c_double]),
     "bb200_diff_drive_sampling_from_control": (C.c_int, [_P(DiffDriveParam), _dbl, _dbl, _P(DiffDriveSampling)]),
 }
 

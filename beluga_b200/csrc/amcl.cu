@@ -47,9 +47,9 @@ bb200_diff_drive_sampling diff_drive_sampling(const bb200_diff_drive_param& p, c
 Amcl::Amcl(const bb200_amcl_param& p, const bb200_diff_drive_param& motion) : params_(p), motion_(motion) {
   bb200_filter_config c{};
   c.device = p.device;
-  c.capacity = p.max_particles;
+  c.capacity = p.shard_capacity != 0 ? p.shard_capacity : p.max_particles;
   c.seed = p.seed;
-  c.first_index = 0;
+  c.first_index = p.shard_first_index;
   c.global_count = p.max_particles;
   c.record_ancestors = p.record_ancestors;
   filter_ = std::make_unique<Filter>(c);
@@ -58,23 +58,30 @@ Amcl::Amcl(const bb200_amcl_param& p, const bb200_diff_drive_param& motion) : pa
 
 int Amcl::initialize(const double mean[3], const double cov[9]) {
   error_.clear();
-  const int st = filter_->initialize_normal(mean, cov, params_.max_particles);
-  if (st == BB200_OK) force_update_ = true;  // amcl_core.hpp:136
+  const int st = filter_->initialize_normal(mean, cov, sharded() ? params_.shard_capacity : params_.max_particles);
+  if (st == BB200_OK) {
+    force_update_ = true;  // amcl_core.hpp:136
+    initialized_ = true;
+  }
   return st;
 }
 
 int Amcl::initialize_states(const double* states, const double* weights, uint64_t n) {
   error_.clear();
   const int st = filter_->set_particles(states, weights, n);
-  if (st == BB200_OK) force_update_ = true;
+  if (st == BB200_OK) {
+    force_update_ = true;
+    initialized_ = n > 0;
+  }
   return st;
 }
 
-int Amcl::update(const double control[4], const double* points_xy, uint64_t n_points, bb200_update_result* out) {
+int Amcl::plan_update(const double control[4], bb200_step_plan* plan) {
   error_.clear();
-  *out = bb200_update_result{};
+  *plan = bb200_step_plan{};
   const Pose2 pose{control[0], control[1], control[2], control[3]};
-  const uint64_t n = filter_->size();
+  // Sharded filters gate on the GLOBAL particle count, which never drops to zero once initialised.
+  const uint64_t n = sharded() ? params_.max_particles * (initialized_ ? 1u : 0u) : filter_->size();
   if (n == 0) return BB200_OK;  // amcl_core.hpp:166-168 -> std::nullopt
 
   // update_policy_(control_action) -- on_motion vs the last ACCEPTED pose (on_motion.hpp:121-133)
@@ -95,8 +102,8 @@ int Amcl::update(const double control[4], const double* points_xy, uint64_t n_po
   window_[0] = pose;
   window_size_ = std::min(window_size_ + 1, 2);
   const Pose2& previous = window_[std::min(1, window_size_ - 1)];
-  const bb200_diff_drive_sampling sampling = diff_drive_sampling(motion_, window_[0], previous);
-  ++step_;
+  plan->sampling = diff_drive_sampling(motion_, window_[0], previous);
+  plan->step = ++step_;
 
   // random_probability_estimator_(particles_) (thrun_recovery_probability_estimator.hpp:69-89) on the
   // normalised weights, whose total is 1 by construction: average = 1 / N.
@@ -107,13 +114,15 @@ int Amcl::update(const double control[4], const double* points_xy, uint64_t n_po
   if (!(std::fabs(slow_average) < std::numeric_limits<double>::epsilon())) {
     random_state_probability = std::clamp(1.0 - fast_average / slow_average, 0.0, 1.0);
   }
-  out->random_state_probability = random_state_probability;
+  plan->random_state_probability = random_state_probability;
 
-  // resample_policy_: every_n (every_n.hpp:47-50) [&& on_effective_size_drop]
+  // resample_policy_: every_n (every_n.hpp:47-50); on_effective_size_drop is applied by the caller
+  // once the effective sample size is known (commit_resample_decision).
   every_n_current_ = (every_n_current_ + 1) % params_.resample_interval;
-  bool do_resample = every_n_current_ == 0;
+  plan->resample = every_n_current_ == 0 ? 1 : 0;
+  plan->needs_ess = (plan->resample && params_.selective_resampling) ? 1 : 0;
 
-  bb200_resample_opts o{};
+  bb200_resample_opts& o = plan->opts;
   o.scheme = params_.resample_scheme;
   o.step = step_;
   o.min_particles = params_.min_particles;
@@ -122,33 +131,46 @@ int Amcl::update(const double control[4], const double* points_xy, uint64_t n_po
   o.kld_z = params_.kld_z;
   for (int k = 0; k < 3; ++k) o.spatial_resolution[k] = params_.spatial_resolution[k];
   o.random_state_probability = random_state_probability;
+  plan->update = 1;
+  return BB200_OK;
+}
 
-  int st;
+void Amcl::commit_update(int resampled, double random_state_probability) {
+  if (resampled && random_state_probability > 0.0) fast_output_ = slow_output_ = 0.0;  // amcl_core.hpp:184-186
+  force_update_ = false;
+}
+
+int Amcl::update(const double control[4], const double* points_xy, uint64_t n_points, bb200_update_result* out) {
+  *out = bb200_update_result{};
+  bb200_step_plan plan;
+  int st = plan_update(control, &plan);
+  if (st != BB200_OK || !plan.update) return st;
+  out->random_state_probability = plan.random_state_probability;
+  const uint64_t n = filter_->size();
+  bool do_resample = plan.resample != 0;
   const bool kld_active = params_.min_particles < params_.max_particles;
-  if (do_resample && !params_.selective_resampling && !kld_active) {
+  if (do_resample && !plan.needs_ess && !kld_active) {
     // The whole step in one stream-ordered sequence with a single host synchronisation.
-    if (random_state_probability > 0.0) fast_output_ = slow_output_ = 0.0;  // amcl_core.hpp:184-186
     uint64_t new_size = 0;
-    st = filter_->step_resample(sampling, step_, points_xy, n_points, o, &out->estimate, &out->weight_sum, &new_size);
+    st = filter_->step_resample(plan.sampling, plan.step, points_xy, n_points, plan.opts, &out->estimate, &out->weight_sum, &new_size);
     if (st != BB200_OK) return st;
     out->resampled = 1;
     out->n_particles = new_size;
   } else {
-    st = filter_->propagate_reweight(&sampling, step_, points_xy, n_points);
+    st = filter_->propagate_reweight(&plan.sampling, plan.step, points_xy, n_points);
     if (st != BB200_OK) return st;
     double factor = 0.0, sum_sq = 0.0;
     st = filter_->normalize(&factor, &sum_sq);
     if (st != BB200_OK) return st;
     out->weight_sum = factor;
-    if (do_resample && params_.selective_resampling) {
+    if (plan.needs_ess) {
       // on_effective_size_drop (on_effective_size_drop.hpp:45-49): ESS = 1 / sum w~^2 < N / 2
       const double ess = sum_sq > 0.0 ? 1.0 / sum_sq : 0.0;
       do_resample = ess < static_cast<double>(n) * 0.5;
     }
     if (do_resample) {
-      if (random_state_probability > 0.0) fast_output_ = slow_output_ = 0.0;
       uint64_t new_size = 0;
-      st = filter_->resample(o, &new_size);
+      st = filter_->resample(plan.opts, &new_size);
       if (st != BB200_OK) return st;
       out->resampled = 1;
     }
@@ -156,7 +178,7 @@ int Amcl::update(const double control[4], const double* points_xy, uint64_t n_po
     if (st != BB200_OK) return st;
     out->n_particles = filter_->size();
   }
-  force_update_ = false;
+  commit_update(out->resampled, plan.random_state_probability);
   out->updated = 1;
   return BB200_OK;
 }

@@ -27,6 +27,11 @@ class Amcl {
   int initialize_states(const double* states, const double* weights, uint64_t n);
   void force_update() { force_update_ = true; }
   int update(const double control[4], const double* points_xy, uint64_t n_points, bb200_update_result* out);
+  /// Host half of update(): policies, control window, recovery estimator -> what to run this step.
+  int plan_update(const double control[4], bb200_step_plan* plan);
+  /// Closes a planned step (estimator reset after injection, force_update flag).
+  void commit_update(int resampled, double random_state_probability);
+  bool sharded() const { return params_.shard_capacity != 0; }
 
  private:
   bb200_amcl_param params_;
@@ -45,6 +50,7 @@ class Amcl {
   int window_size_{0};
 
   bool force_update_{true};
+  bool initialized_{false};
   uint32_t step_{0};
 };
 

@@ -135,6 +135,27 @@ int bb200_filter_resample(bb200_filter* f, const bb200_resample_opts* o, uint64_
   BB_REQUIRE(f && o);
   return f->impl.resample(*o, new_size);
 }
+int bb200_filter_resample_range(bb200_filter* f, const bb200_resample_opts* o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin,
+                                uint64_t slot_end) {
+  BB_REQUIRE(f && o);
+  return f->impl.resample_range(*o, global_total, cdf_offset, slot_begin, slot_end);
+}
+int bb200_filter_adopt(bb200_filter* f, uint64_t n, int from_staging) {
+  BB_REQUIRE(f);
+  return f->impl.adopt(n, from_staging);
+}
+int bb200_systematic_comb(uint64_t seed, uint32_t step, uint64_t global_total, uint64_t total_slots, uint64_t* stride, uint64_t* offset) {
+  BB_REQUIRE(stride && offset && total_slots > 0);
+  *stride = global_total / total_slots;
+  *offset = bb200::mulhi64(bb200::counter_draw(seed, 0, step, bb200::kStreamSystematic).a, *stride);
+  return BB200_OK;
+}
+int bb200_estimate_from_moments(const double moments[9], const double pivot_xy[2], bb200_estimate* out) {
+  BB_REQUIRE(moments && pivot_xy && out);
+  // Pure host arithmetic (estimation.hpp:436-475 from raw moments); needs no device.
+  bb200::Filter::estimate_from_moments_static(moments, pivot_xy, out);
+  return BB200_OK;
+}
 int bb200_filter_ancestors(bb200_filter* f, int64_t* out, uint64_t capacity) {
   BB_REQUIRE(f && out);
   return f->impl.ancestors(out, capacity);
@@ -154,6 +175,11 @@ int bb200_filter_moments(bb200_filter* f, const double pivot_xy[2], double out[9
 int bb200_filter_set_timing(bb200_filter* f, int enabled) {
   BB_REQUIRE(f);
   f->impl.set_timing(enabled != 0);
+  return BB200_OK;
+}
+int bb200_filter_clear_timings(bb200_filter* f) {
+  BB_REQUIRE(f);
+  f->impl.clear_timings();
   return BB200_OK;
 }
 int bb200_filter_last_timings(const bb200_filter* f, const char** names, float* ms, int capacity) {
@@ -178,6 +204,10 @@ int bb200_amcl_create(const bb200_amcl_param* p, const bb200_diff_drive_param* m
     return BB200_ERR_INVALID_ARGUMENT;
   }
   *out = nullptr;
+  if (p->shard_capacity != 0 && (p->shard_first_index + p->shard_capacity > p->max_particles || p->min_particles != p->max_particles)) {
+    g_create_error = "a shard must lie inside [0, max_particles) and use min_particles == max_particles";
+    return BB200_ERR_INVALID_ARGUMENT;
+  }
   if (p->max_particles == 0 || p->min_particles > p->max_particles) {
     g_create_error = "need 0 < min_particles <= max_particles";
     return BB200_ERR_INVALID_ARGUMENT;
@@ -219,6 +249,13 @@ int bb200_amcl_update(bb200_amcl* a, const double control_pose[4], const double*
   BB_REQUIRE(a && control_pose && out && (points_xy || n_points == 0));
   static const double kNoPoints[2] = {0.0, 0.0};
   return a->impl.update(control_pose, points_xy != nullptr ? points_xy : kNoPoints, n_points, out);
+}
+int bb200_amcl_plan_update(bb200_amcl* a, const double control_pose[4], bb200_step_plan* plan) {
+  BB_REQUIRE(a && control_pose && plan);
+  return a->impl.plan_update(control_pose, plan);
+}
+void bb200_amcl_commit_update(bb200_amcl* a, int resampled, double random_state_probability) {
+  if (a != nullptr) a->impl.commit_update(resampled, random_state_probability);
 }
 int bb200_diff_drive_sampling_from_control(const bb200_diff_drive_param* p, const double pose[4], const double previous_pose[4], bb200_diff_drive_sampling* out) {
   BB_REQUIRE(p && pose && previous_pose && out);

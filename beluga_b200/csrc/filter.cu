@@ -207,7 +207,6 @@ void Filter::finish_marks() {
   }
   if (std::string(marks_.back().name) != "end") mark("end");
   cudaEventSynchronize(marks_.back().event);
-  timings_.clear();
   for (size_t i = 0; i + 1 < marks_.size(); ++i) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, marks_[i].event, marks_[i + 1].event);
@@ -543,7 +542,7 @@ int Filter::ensure_cdf_ready() {
   return build_cdf(-1.0, nullptr, nullptr);
 }
 
-void Filter::estimate_from_moments(const double m[kMomentCount], bb200_estimate* out) const {
+void Filter::estimate_from_moments_static(const double m[kMomentCount], const double pivot[2], bb200_estimate* out) {
   // estimation.hpp:436-475 from raw moments about the pivot: normalised weights w/S,
   // mean of (cos, sin, x, y); cov = (E[d d^T] - E[d] E[d]^T) / (1 - sum (w/S)^2).
   const double sum = m[0];
@@ -554,8 +553,8 @@ void Filter::estimate_from_moments(const double m[kMomentCount], bb200_estimate*
   out->cov[1] = (m[7] / sum - mdx * mdy) / correction;
   out->cov[3] = out->cov[1];
   out->cov[4] = (m[8] / sum - mdy * mdy) / correction;
-  out->mean[2] = pivot_[0] + mdx;
-  out->mean[3] = pivot_[1] + mdy;
+  out->mean[2] = pivot[0] + mdx;
+  out->mean[3] = pivot[1] + mdy;
   const double norm = std::sqrt(mc * mc + ms * ms);
   if (norm < std::numeric_limits<double>::epsilon()) {
     out->cov[8] = std::numeric_limits<double>::infinity();
@@ -568,6 +567,8 @@ void Filter::estimate_from_moments(const double m[kMomentCount], bb200_estimate*
     out->mean[1] = ms / len;
   }
 }
+
+void Filter::estimate_from_moments(const double m[kMomentCount], bb200_estimate* out) const { estimate_from_moments_static(m, pivot_, out); }
 
 int Filter::moments(const double pivot[2], double out[9]) {
   if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
@@ -646,6 +647,45 @@ int Filter::resample(const bb200_resample_opts& o, uint64_t* new_size) {
   ancestors_n_ = n_;
   cdf_valid_ = false;
   if (new_size != nullptr) *new_size = n_;
+  return BB200_OK;
+}
+
+int Filter::resample_range(const bb200_resample_opts& o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin, uint64_t slot_end) {
+  // Sharded filter: this rank produces the output slots [slot_begin, slot_end) -- exactly those whose
+  // comb position falls inside its span of the global CDF -- into the staging buffer, in slot order.
+  if (!cdf_valid_) return fail(BB200_ERR_STATE, "build_cdf must run before resample_range");
+  if (o.scheme != BB200_RESAMPLE_SYSTEMATIC || o.random_state_probability > 0.0 || o.min_particles < o.max_particles)
+    return fail(BB200_ERR_STATE, "sharded resampling supports the systematic comb without injection / KLD");
+  if (slot_end < slot_begin || slot_end - slot_begin > capacity_) return fail(BB200_ERR_CAPACITY, "slot range exceeds the staging buffer");
+  BB_CHECK(cudaSetDevice(config_.device));
+  if (slot_end > slot_begin) {
+    ResampleArgs a = make_resample_args(o, 0, slot_end - slot_begin, false);
+    a.slot_first = slot_begin;  // global slot index
+    a.global_total = global_total;
+    a.cdf_offset = cdf_offset;
+    a.weights_out = nullptr;  // the current weights stay untouched; adopt() writes the ones
+    mark("resample_range");
+    launch_resample(a, scalars_, partials_, stream_);
+    BB_LAUNCHED("resample_range");
+  }
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  finish_marks();
+  return BB200_OK;
+}
+
+int Filter::adopt(uint64_t n, int from_staging) {
+  // The caller has placed n particle states into the current (or staging) state buffer, e.g. through
+  // an all-to-all: make them the particle set with unit weights (make_from_state, particle_traits.hpp:105).
+  if (n > capacity_) return fail(BB200_ERR_CAPACITY, "more particles than the filter capacity");
+  BB_CHECK(cudaSetDevice(config_.device));
+  if (from_staging) cur_ ^= 1;
+  n_ = n;
+  cdf_valid_ = false;
+  if (n > 0) {
+    launch_fill(weights_, n, 1.0, stream_);
+    BB_LAUNCHED("fill_weights");
+  }
+  BB_CHECK(cudaStreamSynchronize(stream_));
   return BB200_OK;
 }
 

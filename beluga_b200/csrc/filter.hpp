@@ -38,10 +38,13 @@ class Filter {
   int normalize_by(uint64_t global_total, double* local_sum_sq);
   int normalize(double* factor, double* sum_sq);
   int resample(const bb200_resample_opts& o, uint64_t* new_size);
+  int resample_range(const bb200_resample_opts& o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin, uint64_t slot_end);
+  int adopt(uint64_t n, int from_staging);
   int ancestors(int64_t* out, uint64_t capacity);
   int cdf(uint64_t* out, uint64_t capacity);
   int estimate(bb200_estimate* out);
   int moments(const double pivot[2], double out[9]);
+  static void estimate_from_moments_static(const double m[kMomentCount], const double pivot[2], bb200_estimate* out);
 
   /// Fused single-GPU step: propagate | reweight | normalize | resample | estimate with one
   /// host synchronisation at the end (the composition Amcl::update performs every step).
@@ -52,6 +55,7 @@ class Filter {
   int device_pointer(int which, void** ptr, uint64_t* bytes);
 
   void set_timing(bool on) { timing_ = on; }
+  void clear_timings() { timings_.clear(); }
   int last_timings(const char** names, float* ms, int capacity) const;
   uint64_t launch_count() const { return launches_; }
   const char* last_error() const { return error_.c_str(); }

@@ -836,7 +836,7 @@ __device__ __forceinline__ void store_block_moments(double* m, double* scratch, 
 
 __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, const Scalars* __restrict__ scalars, double* __restrict__ moment_partials) {
   __shared__ double s_red[kRsThreads / kWarp];
-  const unsigned long long total = scalars->total;
+  const unsigned long long total = a.global_total != 0 ? a.global_total : scalars->total;
   unsigned long long stride = 0, offset = 0;
   if (a.scheme == 1) {
     // Systematic comb: stride = T / M, offset uniform in [0, stride).
@@ -869,12 +869,12 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, co
                  (a.grid_origin.s * lx + a.grid_origin.c * ly) + a.grid_origin.y};
     } else {
       const unsigned long long t = a.scheme == 1 ? offset + j * stride : mulhi64(d.b, total);
-      const uint64_t idx = cdf_upper_bound(a.cdf, a.n_in, t);
+      const uint64_t idx = cdf_upper_bound(a.cdf, a.n_in, t - a.cdf_offset);  // the caller guarantees t lies in this shard's span
       ancestor = static_cast<long long>(idx);
       st = load_pose(a.states_in + idx);
     }
     store_pose(a.states_out + local, st);
-    a.weights_out[local] = 1.0;  // make_from_state (particle_traits.hpp:105)
+    if (a.weights_out != nullptr) a.weights_out[local] = 1.0;  // make_from_state (particle_traits.hpp:105)
     if (a.ancestors != nullptr) a.ancestors[local] = ancestor;
     if (a.hashes != nullptr) a.hashes[local] = spatial_hash(st, a.hash_resolution[0], a.hash_resolution[1], a.hash_resolution[2]);
     accumulate_moments(m, st, 1.0, a.pivot_x, a.pivot_y);
@@ -904,6 +904,10 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
   for (uint32_t r = threadIdx.x; r < n_partials; r += 256) v = v + partials[static_cast<size_t>(r) * width + k];
   const double total = block_sum<256>(v, s_red);
   if (threadIdx.x == 0) out[k] = total;
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(double* __restrict__ out, uint64_t n, double value) {
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * 256) out[i] = value;
 }
 
 int ceil_log2_u64(uint64_t n) {
@@ -1034,6 +1038,11 @@ uint32_t moments_block_count(uint64_t n) {
 void launch_moments(const Pose2* states, const double* weights, uint64_t n, double pivot_x, double pivot_y, double* moment_partials,
                     cudaStream_t stream) {
   moments_kernel<<<moments_block_count(n), kStreamThreads, 0, stream>>>(states, weights, n, pivot_x, pivot_y, moment_partials);
+}
+
+void launch_fill(double* out, uint64_t n, double value, cudaStream_t stream) {
+  if (n == 0) return;
+  fill_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n + 255) / 256, kStreamMaxBlocks)), 256, 0, stream>>>(out, n, value);
 }
 
 void launch_reduce_partials(const double* partials, uint32_t n_partials, int width, double* out, cudaStream_t stream) {

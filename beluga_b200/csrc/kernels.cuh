@@ -122,6 +122,8 @@ struct ResampleArgs {
   uint64_t slot_first;    // global index of local output slot 0
   uint64_t slot_count;    // local output slots
   uint64_t total_slots;   // M: the comb of systematic resampling spans all global slots
+  unsigned long long global_total;  // fixed-point total over all ranks (0: scalars->total, single shard)
+  unsigned long long cdf_offset;    // sum of the totals of the lower ranks: local position = t - cdf_offset
   int scheme;
   uint64_t seed;
   uint32_t step;
@@ -142,6 +144,7 @@ void launch_resample(const ResampleArgs& args, const Scalars* scalars, double* m
 uint32_t moments_block_count(uint64_t n);
 void launch_moments(const Pose2* states, const double* weights, uint64_t n, double pivot_x, double pivot_y, double* moment_partials,
                     cudaStream_t stream);
+void launch_fill(double* out, uint64_t n, double value, cudaStream_t stream);
 /// Sums `n_partials` rows of kMomentCount doubles in a fixed order into out[kMomentCount].
 void launch_reduce_partials(const double* partials, uint32_t n_partials, int width, double* out, cudaStream_t stream);
 

@@ -1,0 +1,190 @@
+"""One MCL filter sharded over several GPUs: one process per GPU, torch.distributed for the plumbing.
+
+Particles are split into contiguous global index ranges, `shard` particles per rank; the map and
+the scan are replicated.  Every per-particle kernel runs on the local shard unchanged (the counter
+RNG is keyed by the GLOBAL particle index, so a particle draws the same numbers on any rank count).
+A step needs four small collectives and one redistribution:
+
+    all_reduce(MAX)   largest weight            -> common fixed-point exponent
+    all_gather        per-rank fixed-point totals -> CDF offsets (exclusive prefix) and the global total
+    all_to_all        post-resample particle states (32 B each) to the ranks that own the output slots
+    all_reduce(SUM)   9 raw moments             -> pose estimate (and sum w^2 when ESS is needed)
+
+Because the CDF is an INTEGER prefix sum, offsets + local CDFs equal the single-GPU CDF exactly, so the
+resample indices -- and with them every later step -- are identical for 1, 2, 4 or 8 ranks.
+
+With systematic resampling the comb positions grow with the slot index, so the output slots whose
+position falls into rank r's CDF span form ONE contiguous slot range [ja_r, jb_r); rank r produces
+exactly those particles (local search, local gather) and the all-to-all hands each destination the
+contiguous pieces in rank order, which is already slot order.  `slot_ranges` / `split_counts` below
+are that bookkeeping (pure integer arithmetic, tested on CPU with gloo in tests/test_sharding_cpu.py).
+
+Scope: systematic resampling without recovery injection or KLD (the 100M-particle configuration of
+BASELINE.json); other combinations raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+
+# ---- shard bookkeeping (host integers only) ---------------------------------------------------------
+
+def slot_boundaries(total_slots: int, world: int) -> list[int]:
+    """Output slot d*M//R .. (d+1)*M//R belongs to rank d."""
+    return [d * total_slots // world for d in range(world + 1)]
+
+
+def cdf_offsets(totals) -> list[int]:
+    """Exclusive prefix of the per-rank fixed-point totals (python ints: no overflow)."""
+    out, acc = [], 0
+    for t in totals:
+        out.append(acc)
+        acc += int(t)
+    out.append(acc)
+    return out
+
+
+def slot_ranges(offsets, stride: int, comb_offset: int, total_slots: int):
+    """[ja_r, jb_r): the slots j whose comb position comb_offset + j*stride lies in [offsets[r], offsets[r+1])."""
+    def first_slot_at_or_after(position: int) -> int:
+        if position <= comb_offset:
+            return 0
+        j = -((comb_offset - position) // stride)  # ceil((position - comb_offset) / stride)
+        return min(j, total_slots)
+
+    edges = [first_slot_at_or_after(o) for o in offsets]
+    edges[-1] = total_slots  # the last position is below the global total by construction
+    return [(edges[r], edges[r + 1]) for r in range(len(offsets) - 1)]
+
+
+def split_counts(ranges, boundaries, rank: int):
+    """(send_counts, recv_counts) of the all-to-all for `rank`: overlaps of produced ranges with owned slots."""
+    world = len(ranges)
+
+    def overlap(a, b):
+        return max(0, min(a[1], b[1]) - max(a[0], b[0]))
+
+    owned = [(boundaries[d], boundaries[d + 1]) for d in range(world)]
+    send = [overlap(ranges[rank], owned[d]) for d in range(world)]
+    recv = [overlap(ranges[s], owned[rank]) for s in range(world)]
+    return send, recv
+
+
+# ---- device buffer views ------------------------------------------------------------------------------
+
+class _DeviceArray:
+    """Minimal __cuda_array_interface__ carrier so torch can alias a buffer owned by the filter."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _state_view(filter_, which: int, count: int):
+    import torch
+
+    ptr, nbytes = filter_.device_pointer(which)
+    assert count * 32 <= nbytes
+    return torch.as_tensor(_DeviceArray(ptr, (max(count, 1), 4), "<f8"), device="cuda")[:count]
+
+
+class ShardedAmcl:
+    """beluga::Amcl (algorithm/amcl_core.hpp:81-233) over `world` GPUs; call from every rank in lock step."""
+
+    def __init__(self, motion, params, shard: int, process_group=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import Amcl, AmclParams  # noqa: F401
+
+        self.dist = dist
+        self.torch = torch
+        self.group = process_group
+        self.rank = dist.get_rank(process_group)
+        self.world = dist.get_world_size(process_group)
+        self.shard = shard
+        self.total = shard * self.world
+        if params.resample_scheme != _capi.RESAMPLE_SYSTEMATIC:
+            raise ValueError("ShardedAmcl supports systematic resampling")
+        params.max_particles = self.total
+        params.min_particles = self.total
+        params.shard_capacity = shard
+        params.shard_first_index = self.rank * shard
+        self.params = params
+        self.amcl = Amcl(motion, params)
+        self.filter = self.amcl.filter
+        self.boundaries = slot_boundaries(self.total, self.world)
+        self.pivot = np.zeros(2)
+        self.comm_ms = 0.0
+
+    def update_map(self, sensor, sensor_params, grid):
+        self.amcl.update_map(sensor, sensor_params, grid)
+
+    def initialize(self, mean_xytheta, cov):
+        self.amcl.initialize(mean_xytheta, cov)
+        self.pivot = np.asarray(mean_xytheta[:2], dtype=np.float64).copy()
+
+    def _all_reduce(self, values, op):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op, group=self.group)
+        return t.cpu().numpy()
+
+    def update(self, control_pose, points):
+        """Returns None (std::nullopt) or (mean[4], cov[3x3], info)."""
+        torch, dist = self.torch, self.dist
+        plan = self.amcl.plan_update(control_pose)
+        if not plan.update:
+            return None
+        f = self.filter
+        f.propagate_reweight(plan.sampling, plan.step, points)
+
+        # 1. common exponent from the global largest weight
+        wmax = float(self._all_reduce([f.max_weight()], dist.ReduceOp.MAX)[0])
+        local_total, exponent = f.build_cdf(wmax)
+        # 2. CDF offsets
+        totals = torch.zeros(self.world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(totals, torch.tensor([local_total], dtype=torch.int64, device="cuda"), group=self.group)
+        offsets = cdf_offsets(totals.cpu().tolist())
+        global_total = offsets[-1]
+        weight_sum = float(np.ldexp(float(global_total), -exponent))
+
+        resample = bool(plan.resample)
+        if plan.needs_ess:
+            sum_sq = float(self._all_reduce([f.normalize_by(global_total)], dist.ReduceOp.SUM)[0])
+            ess = 1.0 / sum_sq if sum_sq > 0 else 0.0
+            resample = ess < 0.5 * self.total  # on_effective_size_drop.hpp:45-49
+        elif not resample:
+            f.normalize_by(global_total)
+
+        if resample:
+            if plan.random_state_probability > 0.0:
+                raise NotImplementedError("recovery injection on a sharded filter")
+            stride, comb = _systematic_comb(self.params.seed, plan.step, global_total, self.total)
+            ranges = slot_ranges(offsets, stride, comb, self.total)
+            ja, jb = ranges[self.rank]
+            f.resample_range(plan.opts, global_total, offsets[self.rank], ja, jb)  # -> staging buffer, slot order
+            send_counts, recv_counts = split_counts(ranges, self.boundaries, self.rank)
+            send = _state_view(f, 3, jb - ja)
+            recv = _state_view(f, 0, self.shard)
+            assert sum(recv_counts) == self.shard
+            dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=self.group)
+            torch.cuda.synchronize()
+            f.adopt(self.shard, from_staging=False)
+
+        # 3. estimate from globally summed raw moments
+        moments = self._all_reduce(f.moments(self.pivot).tolist(), dist.ReduceOp.SUM)
+        from . import estimate_from_moments
+
+        mean, cov = estimate_from_moments(moments, self.pivot)
+        self.pivot = mean[2:4].copy()
+        self.amcl.commit_update(resample, plan.random_state_probability)
+        return mean, cov, {"resampled": resample, "weight_sum": weight_sum, "n_particles": self.total}
+
+
+def _systematic_comb(seed, step, global_total, total_slots):
+    from . import systematic_comb
+
+    return systematic_comb(seed, step, global_total, total_slots)

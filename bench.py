@@ -119,6 +119,15 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one reweight_lfm launch from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "lfm_traffic.json")
+    try:
+        return json.load(open(path))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def cpu_reference_steps_per_s(args, scenario, n_full, sample_particles, steps=3):
     """The reference algorithm (oracle port, counter-RNG mode, propagate/reweight/normalize threaded
     like std::execution::par) on a bounded sample; linear extrapolation to the full particle count."""
@@ -186,12 +195,10 @@ def run_native(args):
     scenario = make_workload(args)
     n = args.particles
     n_total = n * world
-    # Independent shards: rank r owns global particles [r*n, (r+1)*n) of one filter (weak scaling).
-    params = bb.AmclParams(min_particles=n, max_particles=n, resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=1, device=local_rank)
-    amcl = bb.Amcl(bb.DifferentialDriveModelParam(*MOTION), params)
-    amcl.update_map(bb.SENSOR_LIKELIHOOD_FIELD, bb.LikelihoodFieldModelParam(**LFM), bb.OccupancyGrid(scenario.cells, scenario.resolution))
-    amcl.initialize(scenario.initial_mean, scenario.initial_cov)
-    amcl.filter.set_timing(True)
+    lfm = bb.LikelihoodFieldModelParam(**LFM)
+    grid = bb.OccupancyGrid(scenario.cells, scenario.resolution)
+    poses = [bb.se2(*scenario.poses[k % PATH_STEPS]) for k in range(args.warmup + args.steps + 1)]
+    scans = [np.ascontiguousarray(scenario.scans[k % PATH_STEPS]) for k in range(args.warmup + args.steps + 1)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > L2 (126 MB)
 
     def sync_all():
@@ -200,39 +207,68 @@ def run_native(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    poses = [bb.se2(*scenario.poses[k % PATH_STEPS]) for k in range(args.warmup + args.steps + 1)]
-    scans = [np.ascontiguousarray(scenario.scans[k % PATH_STEPS]) for k in range(args.warmup + args.steps + 1)]
-    for k in range(args.warmup):
-        r = amcl.update(poses[k], scans[k])
-        assert r.updated == 1
+    if world == 1:
+        params = bb.AmclParams(min_particles=n, max_particles=n, resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=1, device=local_rank)
+        amcl = bb.Amcl(bb.DifferentialDriveModelParam(*MOTION), params)
+        filt = amcl.filter
 
-    launches0 = amcl.filter.launch_count()
+        def step(k):
+            r = amcl.update(poses[k], scans[k])  # synchronous: the estimate is read back inside
+            assert r.updated == 1 and r.resampled == 1
+            return np.array(r.estimate.mean)
+    else:
+        # ONE filter of world*n particles sharded over the ranks (weak scaling): per step an all_reduce(MAX) of the
+        # largest weight, an all_gather of the fixed-point totals, the all-to-all of resampled states, an all_reduce of moments.
+        from beluga_b200.distributed import ShardedAmcl
+
+        params = bb.AmclParams(resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=1, device=local_rank)
+        amcl = ShardedAmcl(bb.DifferentialDriveModelParam(*MOTION), params, shard=n)
+        filt = amcl.filter
+
+        def step(k):
+            out = amcl.update(poses[k], scans[k])
+            assert out is not None and out[2]["resampled"]
+            return out[0]
+
+    amcl.update_map(bb.SENSOR_LIKELIHOOD_FIELD, lfm, grid)
+    amcl.initialize(scenario.initial_mean, scenario.initial_cov)
+    filt.set_timing(True)
+    for k in range(args.warmup):
+        step(k)
+
+    launches0 = filt.launch_count()
     device_ms, wall_ms, kernel_ms = [], [], {}
     sync_all()
     with ClockSampler(local_rank) as clocks:
         for k in range(args.warmup, args.warmup + args.steps):
             flush.zero_()  # evict L2 between timed steps
-            torch.cuda.synchronize()
+            sync_all()
+            filt.clear_timings()
             t0 = time.perf_counter()
-            r = amcl.update(poses[k], scans[k])  # synchronous: the estimate is read back inside
+            mean = step(k)
+            if world > 1:
+                torch.cuda.synchronize()
             wall_ms.append((time.perf_counter() - t0) * 1e3)
-            assert r.updated == 1 and r.resampled == 1
-            step_kernels = amcl.filter.last_timings()
+            step_kernels = filt.last_timings()
             device_ms.append(sum(ms for _, ms in step_kernels))
+            per_step = {}
             for name, ms in step_kernels:
+                per_step[name] = per_step.get(name, 0.0) + ms
+            for name, ms in per_step.items():
                 kernel_ms.setdefault(name, []).append(ms)
         sync_all()
-    launches = amcl.filter.launch_count() - launches0
+    launches = filt.launch_count() - launches0
 
-    dev_total = torch.tensor([sum(device_ms), sum(wall_ms)], dtype=torch.float64, device="cuda")
+    # N = 1: device time of the fused step (CUDA events on the filter stream).  N > 1: the step is host-orchestrated
+    # (collectives between kernels), so the step time is the host clock between synchronisation points; max over ranks.
+    totals = torch.tensor([sum(device_ms) if world == 1 else sum(wall_ms), sum(wall_ms)], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(dev_total, op=dist.ReduceOp.MAX)  # max over ranks
-    dev_total_ms, wall_total_ms = dev_total.tolist()
+        dist.all_reduce(totals, op=dist.ReduceOp.MAX)
+    dev_total_ms, wall_total_ms = totals.tolist()
 
     if rank == 0:
-        est = r.estimate
-        err = float(np.hypot(est.mean[2] - scenario.poses[(args.warmup + args.steps - 1) % PATH_STEPS][0],
-                             est.mean[3] - scenario.poses[(args.warmup + args.steps - 1) % PATH_STEPS][1]))
+        last = (args.warmup + args.steps - 1) % PATH_STEPS
+        err = float(np.hypot(mean[2] - scenario.poses[last][0], mean[3] - scenario.poses[last][1]))
         value = args.steps / (dev_total_ms * 1e-3)
         e2e = args.steps / (wall_total_ms * 1e-3)
         peak, peak_src = measured_peak_gbs()
@@ -241,22 +277,26 @@ def run_native(args):
         # SURVEY 8(d) per-unit figures for the reweight launch: 32 B state read + 8 B weight read + 8 B weight write
         # per particle, one 4-byte field value per beam lookup, the field once.
         k1_bytes = n * (48 + 4 * args.beams) + 4 * g
-        step_bytes = n * (216 + 4 * args.beams) + 4 * g
+        step_bytes = n_total * (216 + 4 * args.beams) + 4 * g * world
         achieved = k1_bytes / (k1 * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(args, n_total), "particles_per_gpu": n, "parallelism": f"shard{world}",
-                       "l2": "256 MiB device write between timed steps (flushes the 126 MB L2)", "timing": "CUDA events on the filter stream, per step, max over ranks",
+                       "l2": "256 MiB device write between timed steps (flushes the 126 MB L2)",
+                       "timing": ("CUDA events on the filter stream around the fused step" if world == 1 else
+                                  "host clock between cuda synchronize + barrier, per step, max over ranks (collectives are host-driven)"),
                        "final_position_error_m": err},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(scans[0].nbytes + 32), "d2h_bytes_per_step": int(9 * 8 + 128),
                     "ms_per_step": wall_total_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "reweight_lfm_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
+                         "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
                          "kernel_ms": k1, "kernel_share_of_step": k1 / (dev_total_ms / args.steps),
-                         "step_achieved_gbs": step_bytes / (dev_total_ms / args.steps * 1e-3) / 1e9},
+                         "step_achieved_gbs": step_bytes / (dev_total_ms / args.steps * 1e-3) / 1e9,
+                         "note": "the lookups are served by L1/L2 (field is L2 resident); the kernel is co-limited by the FP64 pipe, "
+                                 "the L1 tag stage and instruction issue, see profiles/ and DESIGN.md"},
             "kernels_ms": {name: float(np.mean(v)) for name, v in kernel_ms.items()},
             "clocks": clocks.summary(),
         }

@@ -191,6 +191,20 @@ typedef struct bb200_resample_opts {
   double random_state_probability;  /* recovery injection probability */
 } bb200_resample_opts;
 int bb200_filter_resample(bb200_filter* f, const bb200_resample_opts* o, uint64_t* new_size);
+/* Sharded filter (one rank per GPU, contiguous global index ranges):
+ * produce the output slots [slot_begin, slot_end) -- those whose systematic-comb position lies in this
+ * rank's span [cdf_offset, cdf_offset + local_total) of the global fixed-point CDF -- in slot order
+ * into the staging state buffer (bb200_filter_device_pointer(f, 3)).  The caller moves them to the
+ * ranks that own the slots (all-to-all) and then calls bb200_filter_adopt on the receivers. */
+int bb200_filter_resample_range(bb200_filter* f, const bb200_resample_opts* o, uint64_t global_total, uint64_t cdf_offset,
+                                uint64_t slot_begin, uint64_t slot_end);
+/* Declare that n particle states have been written into the current (from_staging = 0) or staging
+ * (from_staging = 1) state buffer: they become the particle set with weights 1. */
+int bb200_filter_adopt(bb200_filter* f, uint64_t n, int from_staging);
+/* Host helpers of the sharded step: the systematic comb (stride = total / slots, offset in [0, stride)
+ * from the counter RNG) and beluga::estimate from globally summed raw moments (bb200_filter_moments). */
+int bb200_systematic_comb(uint64_t seed, uint32_t step, uint64_t global_total, uint64_t total_slots, uint64_t* stride, uint64_t* offset);
+int bb200_estimate_from_moments(const double moments[9], const double pivot_xy[2], bb200_estimate* out);
 /* Ancestor index of every particle produced by the last resample (-1: injected random state). */
 int bb200_filter_ancestors(bb200_filter* f, int64_t* out, uint64_t capacity);
 /* The local fixed-point CDF built by the last build_cdf / normalize (parity hook). */
@@ -203,9 +217,10 @@ int bb200_filter_estimate(bb200_filter* f, bb200_estimate* out);
  * with (dx, dy) = (x, y) - pivot. */
 int bb200_filter_moments(bb200_filter* f, const double pivot_xy[2], double out[9]);
 
-/* Device-side timing of the kernels launched by the last call on this filter (milliseconds,
- * CUDA events on the filter's stream); names[i] are static strings.  Returns the count. */
+/* Device-side timing (milliseconds, CUDA events on the filter's stream) of the kernels launched
+ * since bb200_filter_clear_timings; names[i] are static strings.  Returns the count. */
 int bb200_filter_set_timing(bb200_filter* f, int enabled);
+int bb200_filter_clear_timings(bb200_filter* f);
 int bb200_filter_last_timings(const bb200_filter* f, const char** names, float* ms, int capacity);
 /* Total number of kernel launches issued by this filter since creation. */
 uint64_t bb200_filter_launch_count(const bb200_filter* f);
@@ -237,7 +252,24 @@ typedef struct bb200_amcl_param {
   uint64_t seed;
   int device;
   int record_ancestors;
+  /* Sharding (both 0: single GPU).  max_particles is then the GLOBAL count; this rank holds
+   * shard_capacity particles starting at global index shard_first_index. */
+  uint64_t shard_first_index;
+  uint64_t shard_capacity;
 } bb200_amcl_param;
+
+/* What Amcl::update decided on the host for this step (policies, control window, recovery
+ * estimator; amcl_core.hpp:166-190) -- lets a sharded caller run the device part with collectives
+ * in between (see beluga_b200/distributed.py). */
+typedef struct bb200_step_plan {
+  int update;                         /* 0: std::nullopt, nothing to do */
+  int resample;                       /* every_n fired */
+  int needs_ess;                      /* selective resampling: resample only if ESS < N/2 */
+  uint32_t step;
+  double random_state_probability;
+  bb200_diff_drive_sampling sampling;
+  bb200_resample_opts opts;
+} bb200_step_plan;
 
 typedef struct bb200_update_result {
   int updated;                 /* 0: std::nullopt (no motion / no particles) */
@@ -262,6 +294,9 @@ void bb200_amcl_force_update(bb200_amcl* a);
 /* Amcl::update(control_action, measurement) -- amcl_core.hpp:165-201.  `points_xy` is the
  * measurement_type std::vector<std::pair<double,double>> flattened (x0, y0, x1, y1, ...). */
 int bb200_amcl_update(bb200_amcl* a, const double control_pose[4], const double* points_xy, uint64_t n_points, bb200_update_result* out);
+/* The two host halves of bb200_amcl_update for callers that drive the filter themselves. */
+int bb200_amcl_plan_update(bb200_amcl* a, const double control_pose[4], bb200_step_plan* plan);
+void bb200_amcl_commit_update(bb200_amcl* a, int resampled, double random_state_probability);
 /* DifferentialDriveModel::operator()(control) host part -- differential_drive_model.hpp:129-154. */
 int bb200_diff_drive_sampling_from_control(const bb200_diff_drive_param* p, const double pose[4], const double previous_pose[4], bb200_diff_drive_sampling* out);
 

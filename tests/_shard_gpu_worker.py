@@ -1,0 +1,64 @@
+"""Worker of tests/test_gpu_sharded.py: one rank (one GPU) of a sharded filter; rank 0 also runs the
+same filter on a single GPU and compares -- results must not depend on the number of ranks."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import beluga_b200 as bb  # noqa: E402
+from beluga_b200 import synthetic  # noqa: E402
+from beluga_b200.distributed import ShardedAmcl  # noqa: E402
+
+
+def main():
+    local_rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    shard, steps = int(sys.argv[1]), int(sys.argv[2])
+    total = shard * world
+    sc = synthetic.make_scenario(grid_size=200, n_beams=181, steps=steps + 1)
+    motion = bb.DifferentialDriveModelParam(0.1, 0.05, 0.1, 0.05)
+    lfm = bb.LikelihoodFieldModelParam(max_obstacle_distance=2.0, max_laser_distance=100.0)
+    grid = bb.OccupancyGrid(sc.cells, sc.resolution)
+
+    sharded = ShardedAmcl(motion, bb.AmclParams(resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=21, device=local_rank), shard=shard)
+    sharded.update_map(bb.SENSOR_LIKELIHOOD_FIELD, lfm, grid)
+    sharded.initialize(sc.initial_mean, sc.initial_cov)
+    single = None
+    if rank == 0:
+        single = bb.Amcl(motion, bb.AmclParams(min_particles=total, max_particles=total, resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=21, device=0))
+        single.update_map(bb.SENSOR_LIKELIHOOD_FIELD, lfm, grid)
+        single.initialize(sc.initial_mean, sc.initial_cov)
+
+    for k in range(steps):
+        pose = bb.se2(*sc.poses[k])
+        out = sharded.update(pose, sc.scans[k])
+        assert out is not None
+        mean, cov, info = out
+        # gather the sharded particle set on rank 0
+        states, weights = sharded.filter.particles()
+        gathered = [torch.zeros(shard, 4, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(states).cuda())
+        if rank == 0:
+            r = single.update(pose, sc.scans[k])
+            ref_states, ref_w = single.particles()
+            all_states = torch.cat(gathered).cpu().numpy()
+            assert np.array_equal(all_states, ref_states), f"step {k}: sharded particle set differs from the single-GPU one"
+            assert np.all(weights == 1.0) and np.all(ref_w == 1.0)
+            assert info["weight_sum"] == r.weight_sum
+            assert np.abs(mean - np.array(r.estimate.mean)).max() < 1e-12
+            assert np.abs(cov - np.array(r.estimate.cov).reshape(3, 3)).max() < 1e-12
+    dist.barrier()
+    if rank == 0:
+        print("SHARD_GPU_WORKER_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
