@@ -16,7 +16,8 @@ resample indices -- and with them every later step -- are identical for 1, 2, 4 
 With systematic resampling the comb positions grow with the slot index, so the output slots whose
 position falls into rank r's CDF span form ONE contiguous slot range [ja_r, jb_r); rank r produces
 exactly those particles (local search, local gather) and the all-to-all hands each destination the
-contiguous pieces in rank order, which is already slot order.  `slot_ranges` / `split_counts` below
+contiguous pieces in rank order, which is already slot order.  A rank holding more than 1/R of the weight
+produces more than a shard of slots; the exchange then runs in rounds of at most one shard per rank.  `slot_ranges` / `split_counts` below
 are that bookkeeping (pure integer arithmetic, tested on CPU with gloo in tests/test_sharding_cpu.py).
 
 Scope: systematic resampling without recovery injection or KLD (the 100M-particle configuration of
@@ -118,7 +119,8 @@ class ShardedAmcl:
         self.filter = self.amcl.filter
         self.boundaries = slot_boundaries(self.total, self.world)
         self.pivot = np.zeros(2)
-        self.comm_ms = 0.0
+        self._new_states = None
+        self._recv_tmp = None
 
     def update_map(self, sensor, sensor_params, grid):
         self.amcl.update_map(sensor, sensor_params, grid)
@@ -126,6 +128,35 @@ class ShardedAmcl:
     def initialize(self, mean_xytheta, cov):
         self.amcl.initialize(mean_xytheta, cov)
         self.pivot = np.asarray(mean_xytheta[:2], dtype=np.float64).copy()
+
+    def _redistribute(self, plan, ranges, global_total: int, cdf_offset: int):
+        """Produce the slots of this rank's CDF span and move them to their owners.  A rank whose shard
+        carries more than 1/world of the weight produces more slots than a shard holds, so the exchange
+        runs in rounds of at most `shard` produced slots per rank (usually one)."""
+        torch, dist, f = self.torch, self.dist, self.filter
+        if self._new_states is None:
+            self._new_states = torch.empty(self.shard, 4, dtype=torch.float64, device="cuda")
+            self._recv_tmp = torch.empty(self.shard, 4, dtype=torch.float64, device="cuda")
+        my_lo = self.boundaries[self.rank]
+        rounds = max(1, max(-(-(jb - ja) // self.shard) for ja, jb in ranges))
+        for k in range(rounds):
+            pieces = round_pieces(ranges, self.boundaries, self.shard, k)
+            ja, jb = pieces[self.rank]
+            f.resample_range(plan.opts, global_total, cdf_offset, ja, jb)  # -> staging buffer, slot order
+            send_counts, recv_counts = split_counts(pieces, self.boundaries, self.rank)
+            send = _state_view(f, 3, jb - ja)
+            recv = self._recv_tmp[: sum(recv_counts)]
+            dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=self.group)
+            pos = 0
+            for s, count in enumerate(recv_counts):  # pieces arrive grouped by source; place each at its slots
+                if count:
+                    first_slot = max(pieces[s][0], my_lo)
+                    self._new_states[first_slot - my_lo: first_slot - my_lo + count] = recv[pos: pos + count]
+                    pos += count
+            torch.cuda.synchronize()
+        _state_view(f, 0, self.shard).copy_(self._new_states)
+        torch.cuda.synchronize()
+        f.adopt(self.shard, from_staging=False)
 
     def _all_reduce(self, values, op):
         t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
@@ -164,15 +195,7 @@ class ShardedAmcl:
                 raise NotImplementedError("recovery injection on a sharded filter")
             stride, comb = _systematic_comb(self.params.seed, plan.step, global_total, self.total)
             ranges = slot_ranges(offsets, stride, comb, self.total)
-            ja, jb = ranges[self.rank]
-            f.resample_range(plan.opts, global_total, offsets[self.rank], ja, jb)  # -> staging buffer, slot order
-            send_counts, recv_counts = split_counts(ranges, self.boundaries, self.rank)
-            send = _state_view(f, 3, jb - ja)
-            recv = _state_view(f, 0, self.shard)
-            assert sum(recv_counts) == self.shard
-            dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=self.group)
-            torch.cuda.synchronize()
-            f.adopt(self.shard, from_staging=False)
+            self._redistribute(plan, ranges, global_total, offsets[self.rank])
 
         # 3. estimate from globally summed raw moments
         moments = self._all_reduce(f.moments(self.pivot).tolist(), dist.ReduceOp.SUM)
@@ -182,6 +205,15 @@ class ShardedAmcl:
         self.pivot = mean[2:4].copy()
         self.amcl.commit_update(resample, plan.random_state_probability)
         return mean, cov, {"resampled": resample, "weight_sum": weight_sum, "n_particles": self.total}
+
+
+def round_pieces(ranges, boundaries, capacity: int, round_index: int):
+    """Sub-ranges produced in one round: every source handles at most `capacity` slots per round."""
+    out = []
+    for (ja, jb) in ranges:
+        lo = min(jb, ja + round_index * capacity)
+        out.append((lo, min(jb, lo + capacity)))
+    return out
 
 
 def _systematic_comb(seed, step, global_total, total_slots):

@@ -39,3 +39,25 @@ def test_slot_range_bookkeeping():
     assert send0 == [10, 0, 0, 0] and recv0 == [10, 0, 0, 0]
     # a comb position exactly on a span boundary belongs to the upper span
     assert sh.slot_ranges([0, 30, 60], stride=10, comb_offset=0, total_slots=6) == [(0, 3), (3, 6)]
+
+
+def test_round_pieces_cover_unbalanced_ranges():
+    """A rank with most of the weight produces more than one shard of slots: the rounds partition its range."""
+    from beluga_b200 import distributed as sh
+
+    ranges, bounds, cap = [(0, 7), (7, 40)], sh.slot_boundaries(40, 2), 20
+    rounds = max(-(-(b - a) // cap) for a, b in ranges)
+    assert rounds == 2
+    covered = [[], []]
+    received = [0, 0]
+    for k in range(rounds):
+        pieces = sh.round_pieces(ranges, bounds, cap, k)
+        for r, (a, b) in enumerate(pieces):
+            assert b - a <= cap
+            covered[r].extend(range(a, b))
+        for r in range(2):
+            send, recv = sh.split_counts(pieces, bounds, r)
+            assert sum(send) == pieces[r][1] - pieces[r][0]
+            received[r] += sum(recv)
+    assert covered[0] == list(range(0, 7)) and covered[1] == list(range(7, 40))
+    assert received == [20, 20]
