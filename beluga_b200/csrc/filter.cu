@@ -507,7 +507,9 @@ int Filter::build_cdf(double global_wmax, uint64_t* local_total, int* exponent) 
   cdf_valid_ = true;
   if (local_total != nullptr) *local_total = scalars_host_->total;
   if (exponent != nullptr) *exponent = scalars_host_->exponent;
-  if (scalars_host_->valid == 0) return fail(BB200_ERR_STATE, "no positive finite weight (uniform CDF substituted)");
+  // No positive finite weight (the reference would divide by zero in normalize.hpp:82): a uniform CDF
+  // has been substituted and the weights are left as they are; reported through last_error only.
+  if (scalars_host_->valid == 0) error_ = "no positive finite weight (uniform CDF substituted)";
   return BB200_OK;
 }
 
