@@ -160,6 +160,7 @@ Filter::~Filter() {
   cudaFree(table_);
   cudaFree(tiled_);
   cudaFree(occupancy_);
+  cudaFree(free_distance_);
   cudaFree(free_cells_);
   if (stream_ != nullptr) cudaStreamDestroy(stream_);
 }
@@ -313,7 +314,13 @@ int Filter::set_beam_map(const bb200_beam_param& p, const bb200_occupancy_grid& 
   occupancy_ = nullptr;
   BB_CHECK(dev_alloc(&occupancy_, count));
   BB_CHECK(cudaMemcpy(occupancy_, g.cells, count, cudaMemcpyHostToDevice));
+  const std::vector<uint8_t> free_distance = make_free_distance(g);
+  cudaFree(free_distance_);
+  free_distance_ = nullptr;
+  BB_CHECK(dev_alloc(&free_distance_, count));
+  BB_CHECK(cudaMemcpy(free_distance_, free_distance.data(), count, cudaMemcpyHostToDevice));
   occupancy_view_.cells = occupancy_;
+  occupancy_view_.free_distance = free_distance_;
   occupancy_view_.width = g.width;
   occupancy_view_.height = g.height;
   occupancy_view_.resolution = g.resolution;

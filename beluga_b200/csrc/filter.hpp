@@ -135,6 +135,7 @@ class Filter {
   double* tiled_{nullptr};
   FieldView field_{};
   int8_t* occupancy_{nullptr};
+  uint8_t* free_distance_{nullptr};
   OccupancyView occupancy_view_{};
   BeamParams beam_{};
   uint32_t* free_cells_{nullptr};

@@ -277,7 +277,11 @@ constexpr uint32_t kChunkBeams = 2048; // beams staged per shared-memory chunk (
 
 /// floor(g) as int32 for |g| < 2^31 through one round-down add: g + 1.5*2^52 has ulp 1, so the low
 /// mantissa word of the sum is floor(g) in two's complement.
+#ifndef BB200_RW_MAGIC_FLOOR  // default: F2I.FLOOR (saturating); -DBB200_RW_MAGIC_FLOOR selects the round-down-add variant
+__device__ __forceinline__ int floor_to_int_fast(double g) { return __double2int_rd(g); }
+#else
 __device__ __forceinline__ int floor_to_int_fast(double g) { return __double2loint(__dadd_rd(g, 6755399441055744.0)); }
+#endif
 
 template <bool kFast, bool kTiled>
 __device__ __forceinline__ double field_lookup(const FieldView& f, double px, double py, double c, double s, double tx, double ty) {
@@ -419,7 +423,11 @@ struct BeamRay {
   double z;             // measured range (beam_model.hpp:116)
 };
 
-__device__ __forceinline__ int cell_near(double p, double inv_resolution) { return static_cast<int>(floor(p * inv_resolution)); }
+/// regular_grid.hpp:75-78.  Clamped to +-2^28 cells so that spans of far-away end points cannot
+/// overflow 32-bit integers (the reference's cast<int>() is undefined out there).
+__device__ __forceinline__ int cell_near(double p, double inv_resolution) {
+  return max(-(1 << 28), min(1 << 28, __double2int_rd(p * inv_resolution)));
+}
 
 /// Distance in metres from the source cell centroid to the first non-free cell, or -1 on a miss.
 __device__ __forceinline__ double cast_ray(const OccupancyView& g, int sx, int sy, int fx, int fy, double max_range) {
@@ -443,23 +451,29 @@ __device__ __forceinline__ double cast_ray(const OccupancyView& g, int sx, int s
   }
   const int dxspan = 2 * xspan, dyspan = 2 * yspan;
   int error = xspan;
-  for (int step = 0; step <= xspan; ++step) {
+  int step = 0;
+  for (;;) {
     const int cx = reversed ? y : x, cy = reversed ? x : y;
     if (!(static_cast<unsigned>(cx) < static_cast<unsigned>(g.width) && static_cast<unsigned>(cy) < static_cast<unsigned>(g.height)))
       return -1.0;  // take_while(cell_is_valid), raycasting.hpp:86-87
-    if (__ldg(g.cells + (static_cast<size_t>(cy) * static_cast<size_t>(g.width) + static_cast<size_t>(cx))) != 0) {  // !free_at
+    const int d = __ldg(g.free_distance + (static_cast<size_t>(cy) * static_cast<size_t>(g.width) + static_cast<size_t>(cx)));
+    if (d == 0) {  // !free_at: first non-free cell on the line
       const double dxm = (static_cast<double>(cx) + 0.5) * g.resolution - (static_cast<double>(sx) + 0.5) * g.resolution;
       const double dym = (static_cast<double>(cy) + 0.5) * g.resolution - (static_cast<double>(sy) + 0.5) * g.resolution;
       return fmin(sqrt(dxm * dxm + dym * dym), max_range);
     }
-    x += xstep;
-    error += dyspan;
-    if (error > dxspan) {
-      y += ystep;
-      error -= dxspan;
-    }
+    // Every cell within Chebyshev distance d - 1 is free and the line moves at most one cell per step
+    // in each axis, so the next d - 1 cells cannot stop the ray: advance d steps of the iterator
+    // (bresenham.hpp:122-160, standard variant) in closed form.  error stays in (0, dxspan].
+    const int k = min(d, xspan - step);
+    if (k == 0) return -1.0;  // the far end cell was free too: sentinel reached (bresenham.hpp:179)
+    step += k;
+    x += k * xstep;
+    const long long t = static_cast<long long>(error) + static_cast<long long>(k) * dyspan;
+    const int m = static_cast<int>((t - 1) / dxspan);
+    y += m * ystep;
+    error = static_cast<int>(t - static_cast<long long>(m) * dxspan);
   }
-  return -1.0;
 }
 
 __device__ __forceinline__ double beam_pz3(const BeamParams& p, double z, double z_mean, double n) {

@@ -31,6 +31,7 @@ struct FieldView {
 /// Device view of the occupancy grid (beam model).
 struct OccupancyView {
   const int8_t* cells;
+  const uint8_t* free_distance;  // Chebyshev distance to the nearest non-free / outside cell (map_host.hpp)
   int width, height;
   double resolution, inv_resolution;
   Pose2 world_to_grid;  // grid.origin().inverse()

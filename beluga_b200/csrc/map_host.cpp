@@ -107,6 +107,38 @@ std::vector<float> make_likelihood_field(const bb200_likelihood_field_param& p, 
   return sq;
 }
 
+std::vector<uint8_t> make_free_distance(const bb200_occupancy_grid& g) {
+  const int w = g.width, h = g.height;
+  std::vector<int> d(static_cast<size_t>(w) * h);
+  const int cap = 255;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const size_t i = static_cast<size_t>(y) * w + x;
+      const int border = std::min(std::min(x + 1, y + 1), std::min(w - x, h - y));  // distance to the outside
+      d[i] = g.cells[i] != kFree ? 0 : std::min(cap, border);
+    }
+  // Two-pass chamfer with unit weights on the 8-neighbourhood: exact for the Chebyshev metric.
+  auto relax = [&](size_t i, int x, int y, int dx, int dy) {
+    const int nx = x + dx, ny = y + dy;
+    if (nx < 0 || ny < 0 || nx >= w || ny >= h) return;
+    const int v = d[static_cast<size_t>(ny) * w + nx] + 1;
+    if (v < d[i]) d[i] = v;
+  };
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const size_t i = static_cast<size_t>(y) * w + x;
+      relax(i, x, y, -1, 0), relax(i, x, y, -1, -1), relax(i, x, y, 0, -1), relax(i, x, y, 1, -1);
+    }
+  for (int y = h - 1; y >= 0; --y)
+    for (int x = w - 1; x >= 0; --x) {
+      const size_t i = static_cast<size_t>(y) * w + x;
+      relax(i, x, y, 1, 0), relax(i, x, y, 1, 1), relax(i, x, y, 0, 1), relax(i, x, y, -1, 1);
+    }
+  std::vector<uint8_t> out(d.size());
+  for (size_t i = 0; i < d.size(); ++i) out[i] = static_cast<uint8_t>(std::min(d[i], cap));
+  return out;
+}
+
 std::vector<uint32_t> make_free_cells(const bb200_occupancy_grid& g) {
   std::vector<uint32_t> out;
   const size_t count = static_cast<size_t>(g.width) * static_cast<size_t>(g.height);

@@ -24,6 +24,13 @@ namespace bb200 {
 /// ValueGrid2<float> contents, row-major.
 std::vector<float> make_likelihood_field(const bb200_likelihood_field_param& params, const bb200_occupancy_grid& grid);
 
+/// Chebyshev distance (in cells, capped at 255) from every cell to the nearest cell that is not
+/// free or lies outside the grid; 0 for non-free cells.  A Bresenham line moves at most one cell
+/// per step in each axis, so from a cell with distance d the next d - 1 cells of any ray are free:
+/// the beam-model ray cast jumps d steps at a time and still stops at exactly the cell the
+/// reference's cell-by-cell walk (algorithm/raycasting.hpp:97-107) stops at.
+std::vector<uint8_t> make_free_distance(const bb200_occupancy_grid& grid);
+
 /// Cell indices whose value is free (0), ascending.
 std::vector<uint32_t> make_free_cells(const bb200_occupancy_grid& grid);
 

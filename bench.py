@@ -85,7 +85,7 @@ class ClockSampler:
                     self.samples.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._thread.start()
