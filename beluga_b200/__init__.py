@@ -290,6 +290,27 @@ class Filter:
     def adopt(self, n: int, from_staging: bool = False):
         self._check(self._lib.bb200_filter_adopt(self._h, n, int(from_staging)))
 
+    # stream-ordered variants (sharded filters; see distributed.py)
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.bb200_filter_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def enqueue_propagate_reweight(self, sampling, step: int, points):
+        s = self._sampling(sampling)
+        pts = _f64(points).reshape(-1, 2)
+        self._check(self._lib.bb200_filter_enqueue_propagate_reweight(self._h, C.byref(s), step, _dptr(pts), len(pts)))
+
+    def enqueue_build_cdf(self):
+        self._check(self._lib.bb200_filter_enqueue_build_cdf(self._h))
+
+    def enqueue_resample_range(self, opts: _capi.ResampleOpts, global_total: int, cdf_offset: int, slot_begin: int, slot_end: int):
+        self._check(self._lib.bb200_filter_enqueue_resample_range(self._h, C.byref(opts), global_total, cdf_offset, slot_begin, slot_end))
+
+    def enqueue_adopt(self, n: int):
+        self._check(self._lib.bb200_filter_enqueue_adopt(self._h, n))
+
+    def enqueue_moments(self, pivot):
+        self._check(self._lib.bb200_filter_enqueue_moments(self._h, _dptr(_f64(pivot))))
+
     def ancestors(self) -> np.ndarray:
         out = np.zeros(self.size(), dtype=np.int64)
         self._check(self._lib.bb200_filter_ancestors(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), len(out)))

@@ -107,6 +107,12 @@ SIGNATURES = {
     "bb200_filter_adopt": (C.c_int, [_vp, C.c_uint64, C.c_int]),
     "bb200_systematic_comb": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _P(C.c_uint64), _P(C.c_uint64)]),
     "bb200_estimate_from_moments": (C.c_int, [_dbl, _dbl, _P(Estimate)]),
+    "bb200_filter_set_stream": (C.c_int, [_vp, _vp]),
+    "bb200_filter_enqueue_propagate_reweight": (C.c_int, [_vp, _P(DiffDriveSampling), C.c_uint32, _dbl, C.c_uint64]),
+    "bb200_filter_enqueue_build_cdf": (C.c_int, [_vp]),
+    "bb200_filter_enqueue_resample_range": (C.c_int, [_vp, _P(ResampleOpts), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "bb200_filter_enqueue_adopt": (C.c_int, [_vp, C.c_uint64]),
+    "bb200_filter_enqueue_moments": (C.c_int, [_vp, _dbl]),
     "bb200_filter_ancestors": (C.c_int, [_vp, _P(C.c_int64), C.c_uint64]),
     "bb200_filter_cdf": (C.c_int, [_vp, _P(C.c_uint64), C.c_uint64]),
     "bb200_filter_estimate": (C.c_int, [_vp, _P(Estimate)]),

@@ -156,6 +156,31 @@ int bb200_estimate_from_moments(const double moments[9], const double pivot_xy[2
   bb200::Filter::estimate_from_moments_static(moments, pivot_xy, out);
   return BB200_OK;
 }
+int bb200_filter_set_stream(bb200_filter* f, void* cuda_stream) {
+  BB_REQUIRE(f);
+  return f->impl.set_stream(cuda_stream);
+}
+int bb200_filter_enqueue_propagate_reweight(bb200_filter* f, const bb200_diff_drive_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points) {
+  BB_REQUIRE(f && s && points_xy);
+  return f->impl.enqueue_propagate_reweight(s, step, points_xy, n_points);
+}
+int bb200_filter_enqueue_build_cdf(bb200_filter* f) {
+  BB_REQUIRE(f);
+  return f->impl.enqueue_build_cdf();
+}
+int bb200_filter_enqueue_resample_range(bb200_filter* f, const bb200_resample_opts* o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin,
+                                        uint64_t slot_end) {
+  BB_REQUIRE(f && o);
+  return f->impl.enqueue_resample_range(*o, global_total, cdf_offset, slot_begin, slot_end);
+}
+int bb200_filter_enqueue_adopt(bb200_filter* f, uint64_t n) {
+  BB_REQUIRE(f);
+  return f->impl.enqueue_adopt(n);
+}
+int bb200_filter_enqueue_moments(bb200_filter* f, const double pivot_xy[2]) {
+  BB_REQUIRE(f && pivot_xy);
+  return f->impl.enqueue_moments(pivot_xy);
+}
 int bb200_filter_ancestors(bb200_filter* f, int64_t* out, uint64_t capacity) {
   BB_REQUIRE(f && out);
   return f->impl.ancestors(out, capacity);

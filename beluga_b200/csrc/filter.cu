@@ -162,7 +162,7 @@ Filter::~Filter() {
   cudaFree(occupancy_);
   cudaFree(free_distance_);
   cudaFree(free_cells_);
-  if (stream_ != nullptr) cudaStreamDestroy(stream_);
+  if (stream_ != nullptr && owns_stream_) cudaStreamDestroy(stream_);
 }
 
 int Filter::fail(int status, const std::string& message) {
@@ -226,9 +226,89 @@ int Filter::last_timings(const char** names, float* ms, int capacity) const {
   return static_cast<int>(timings_.size());
 }
 
+int Filter::set_stream(void* stream) {
+  BB_CHECK(cudaSetDevice(config_.device));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  if (owns_stream_ && stream_ != nullptr) cudaStreamDestroy(stream_);
+  stream_ = static_cast<cudaStream_t>(stream);
+  owns_stream_ = false;
+  return BB200_OK;
+}
+
+int Filter::enqueue_propagate_reweight(const bb200_diff_drive_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  if (points_xy == nullptr || sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set / no points");
+  BB_CHECK(cudaSetDevice(config_.device));
+  int st = upload_points(points_xy, n_points);  // the caller synchronised at the end of the previous step
+  if (st != BB200_OK) return st;
+  DiffDriveSampling s{};
+  if (sampling != nullptr) s = DiffDriveSampling{sampling->rot1_mean, sampling->rot1_std, sampling->trans_mean, sampling->trans_std, sampling->rot2_mean, sampling->rot2_std};
+  mark("begin_step");
+  launch_begin_step(scalars_, stream_);
+  BB_LAUNCHED("begin_step");
+  st = enqueue_propagate_reweight(sampling != nullptr ? &s : nullptr, step, true, n_points);
+  cdf_valid_ = false;
+  return st;
+}
+
+int Filter::enqueue_build_cdf() {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  BB_CHECK(cudaSetDevice(config_.device));
+  mark("prepare_cdf");
+  launch_prepare_cdf(scalars_, -1.0, config_.global_count, tile_state_, scan_tile_count(n_), stream_);
+  BB_LAUNCHED("prepare_cdf");
+  mark("quantize_scan");
+  launch_quantize_scan(weights_, n_, cdf_, scalars_, tile_state_, stream_);
+  BB_LAUNCHED("quantize_scan");
+  cdf_valid_ = true;
+  return BB200_OK;
+}
+
+int Filter::enqueue_resample_range(const bb200_resample_opts& o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin, uint64_t slot_end) {
+  if (!cdf_valid_) return fail(BB200_ERR_STATE, "build_cdf must run before resample_range");
+  if (o.scheme != BB200_RESAMPLE_SYSTEMATIC || o.random_state_probability > 0.0 || o.min_particles < o.max_particles)
+    return fail(BB200_ERR_STATE, "sharded resampling supports the systematic comb without injection / KLD");
+  if (slot_end < slot_begin || slot_end - slot_begin > capacity_) return fail(BB200_ERR_CAPACITY, "slot range exceeds the staging buffer");
+  BB_CHECK(cudaSetDevice(config_.device));
+  if (slot_end > slot_begin) {
+    ResampleArgs a = make_resample_args(o, 0, slot_end - slot_begin, false);
+    a.slot_first = slot_begin;
+    a.global_total = global_total;
+    a.cdf_offset = cdf_offset;
+    a.weights_out = nullptr;
+    mark("resample_range");
+    launch_resample(a, scalars_, partials_, stream_);
+    BB_LAUNCHED("resample_range");
+  }
+  return BB200_OK;
+}
+
+int Filter::enqueue_adopt(uint64_t n) {
+  if (n > capacity_) return fail(BB200_ERR_CAPACITY, "more particles than the filter capacity");
+  BB_CHECK(cudaSetDevice(config_.device));
+  n_ = n;
+  cdf_valid_ = false;
+  mark("fill_weights");
+  launch_fill(weights_, n, 1.0, stream_);
+  BB_LAUNCHED("fill_weights");
+  return BB200_OK;
+}
+
+int Filter::enqueue_moments(const double pivot[2]) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  BB_CHECK(cudaSetDevice(config_.device));
+  mark("moments");
+  launch_moments(states_[cur_], weights_, n_, pivot[0], pivot[1], partials_, stream_);
+  BB_LAUNCHED("moments");
+  launch_reduce_partials(partials_, moments_block_count(n_), kMomentCount, results_, stream_);
+  BB_LAUNCHED("reduce_partials");
+  return BB200_OK;
+}
+
 int Filter::synchronize() {
   BB_CHECK(cudaSetDevice(config_.device));
   BB_CHECK(cudaStreamSynchronize(stream_));
+  finish_marks();
   return BB200_OK;
 }
 
@@ -238,6 +318,8 @@ int Filter::device_pointer(int which, void** ptr, uint64_t* bytes) {
     case 1: *ptr = weights_; *bytes = capacity_ * sizeof(double); return BB200_OK;
     case 2: *ptr = cdf_; *bytes = capacity_ * sizeof(unsigned long long); return BB200_OK;
     case 3: *ptr = states_[cur_ ^ 1]; *bytes = capacity_ * sizeof(Pose2); return BB200_OK;
+    case 4: *ptr = scalars_; *bytes = sizeof(Scalars); return BB200_OK;
+    case 5: *ptr = results_; *bytes = 16 * sizeof(double); return BB200_OK;
     default: return fail(BB200_ERR_INVALID_ARGUMENT, "unknown device pointer id");
   }
 }

@@ -51,6 +51,15 @@ class Filter {
   int step_resample(const bb200_diff_drive_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points,
                     const bb200_resample_opts& o, bb200_estimate* est, double* weight_sum, uint64_t* new_size);
 
+  // Stream-ordered variants for callers that interleave collectives on the same stream (sharded
+  // filters): nothing here synchronises with the host or reads results back.
+  int set_stream(void* stream);
+  int enqueue_propagate_reweight(const bb200_diff_drive_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points);
+  int enqueue_build_cdf();                      // exponent from the wmax in the device scalars (all-reduced by the caller)
+  int enqueue_resample_range(const bb200_resample_opts& o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin, uint64_t slot_end);
+  int enqueue_adopt(uint64_t n);
+  int enqueue_moments(const double pivot[2]);   // raw moments stay in the device result block
+
   int synchronize();
   int device_pointer(int which, void** ptr, uint64_t* bytes);
 
@@ -80,6 +89,7 @@ class Filter {
   int create_status_{BB200_OK};
   std::string error_;
   cudaStream_t stream_{nullptr};
+  bool owns_stream_{true};
 
   // particle set (ping-pong states for the resample gather)
   uint64_t capacity_{0}, n_{0};

@@ -121,6 +121,11 @@ class ShardedAmcl:
         self.pivot = np.zeros(2)
         self._new_states = None
         self._recv_tmp = None
+        # Kernels and collectives share torch's current stream: everything is stream-ordered and a step
+        # needs two host synchronisations (the CDF totals, the estimate).
+        self.filter.set_stream(torch.cuda.current_stream().cuda_stream)
+        self._scalars = None
+        self._results = None
 
     def update_map(self, sensor, sensor_params, grid):
         self.amcl.update_map(sensor, sensor_params, grid)
@@ -129,7 +134,7 @@ class ShardedAmcl:
         self.amcl.initialize(mean_xytheta, cov)
         self.pivot = np.asarray(mean_xytheta[:2], dtype=np.float64).copy()
 
-    def _redistribute(self, plan, ranges, global_total: int, cdf_offset: int):
+    def _redistribute(self, plan, ranges, global_total: int, cdf_offset: int, streamed: bool):
         """Produce the slots of this rank's CDF span and move them to their owners.  A rank whose shard
         carries more than 1/world of the weight produces more slots than a shard holds, so the exchange
         runs in rounds of at most `shard` produced slots per rank (usually one)."""
@@ -142,7 +147,10 @@ class ShardedAmcl:
         for k in range(rounds):
             pieces = round_pieces(ranges, self.boundaries, self.shard, k)
             ja, jb = pieces[self.rank]
-            f.resample_range(plan.opts, global_total, cdf_offset, ja, jb)  # -> staging buffer, slot order
+            if streamed:
+                f.enqueue_resample_range(plan.opts, global_total, cdf_offset, ja, jb)  # -> staging buffer, slot order
+            else:
+                f.resample_range(plan.opts, global_total, cdf_offset, ja, jb)
             send_counts, recv_counts = split_counts(pieces, self.boundaries, self.rank)
             send = _state_view(f, 3, jb - ja)
             recv = self._recv_tmp[: sum(recv_counts)]
@@ -153,22 +161,73 @@ class ShardedAmcl:
                     first_slot = max(pieces[s][0], my_lo)
                     self._new_states[first_slot - my_lo: first_slot - my_lo + count] = recv[pos: pos + count]
                     pos += count
-            torch.cuda.synchronize()
+            if not streamed:
+                torch.cuda.synchronize()
         _state_view(f, 0, self.shard).copy_(self._new_states)
-        torch.cuda.synchronize()
-        f.adopt(self.shard, from_staging=False)
+        if streamed:
+            f.enqueue_adopt(self.shard)
+        else:
+            torch.cuda.synchronize()
+            f.adopt(self.shard, from_staging=False)
 
     def _all_reduce(self, values, op):
         t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
         self.dist.all_reduce(t, op=op, group=self.group)
         return t.cpu().numpy()
 
+    def _device_blocks(self):
+        if self._scalars is None:
+            torch = self.torch
+            ptr, _ = self.filter.device_pointer(4)
+            self._scalars = torch.as_tensor(_DeviceArray(ptr, (8,), "<i8"), device="cuda")  # [0] wmax bits, [2] total, [3] exponent | valid << 32
+            ptr, _ = self.filter.device_pointer(5)
+            self._results = torch.as_tensor(_DeviceArray(ptr, (16,), "<f8"), device="cuda")
+            self._totals = torch.zeros(self.world + 1, dtype=torch.int64, device="cuda")
+        return self._scalars, self._results
+
     def update(self, control_pose, points):
         """Returns None (std::nullopt) or (mean[4], cov[3x3], info)."""
-        torch, dist = self.torch, self.dist
         plan = self.amcl.plan_update(control_pose)
         if not plan.update:
             return None
+        if plan.resample and not plan.needs_ess:
+            return self._update_streamed(plan, points)
+        return self._update_stepwise(plan, points)
+
+    def _update_streamed(self, plan, points):
+        """Resampling step with everything enqueued on one stream; two host synchronisations."""
+        torch, dist, f = self.torch, self.dist, self.filter
+        if plan.random_state_probability > 0.0:
+            raise NotImplementedError("recovery injection on a sharded filter")
+        scalars, results = self._device_blocks()
+        f.enqueue_propagate_reweight(plan.sampling, plan.step, points)
+        # positive doubles order like their bit patterns: MAX over the int64 view is the largest weight
+        dist.all_reduce(scalars[0:1], op=dist.ReduceOp.MAX, group=self.group)
+        f.enqueue_build_cdf()
+        dist.all_gather_into_tensor(self._totals[: self.world], scalars[2:3], group=self.group)
+        self._totals[self.world: self.world + 1] = scalars[3:4]
+        host = self._totals.cpu().tolist()  # synchronisation 1
+        exponent = int(np.int32(host[self.world] & 0xFFFFFFFF))
+        offsets = cdf_offsets(host[: self.world])
+        global_total = offsets[-1]
+        weight_sum = float(np.ldexp(float(global_total), -exponent))
+
+        stride, comb = _systematic_comb(self.params.seed, plan.step, global_total, self.total)
+        ranges = slot_ranges(offsets, stride, comb, self.total)
+        self._redistribute(plan, ranges, global_total, offsets[self.rank], streamed=True)
+        f.enqueue_moments(self.pivot)
+        dist.all_reduce(results[0:9], op=dist.ReduceOp.SUM, group=self.group)
+        moments = results[0:9].cpu().numpy()  # synchronisation 2
+        f.synchronize()  # closes the timing marks; the stream is already idle
+        from . import estimate_from_moments
+
+        mean, cov = estimate_from_moments(moments, self.pivot)
+        self.pivot = mean[2:4].copy()
+        self.amcl.commit_update(True, plan.random_state_probability)
+        return mean, cov, {"resampled": True, "weight_sum": weight_sum, "n_particles": self.total}
+
+    def _update_stepwise(self, plan, points):
+        torch, dist = self.torch, self.dist
         f = self.filter
         f.propagate_reweight(plan.sampling, plan.step, points)
 
@@ -195,7 +254,7 @@ class ShardedAmcl:
                 raise NotImplementedError("recovery injection on a sharded filter")
             stride, comb = _systematic_comb(self.params.seed, plan.step, global_total, self.total)
             ranges = slot_ranges(offsets, stride, comb, self.total)
-            self._redistribute(plan, ranges, global_total, offsets[self.rank])
+            self._redistribute(plan, ranges, global_total, offsets[self.rank], streamed=False)
 
         # 3. estimate from globally summed raw moments
         moments = self._all_reduce(f.moments(self.pivot).tolist(), dist.ReduceOp.SUM)

@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU (weak scaling)")
     ap.add_argument("--beams", type=int, default=1080)
     ap.add_argument("--grid", type=int, default=2000)
-    ap.add_argument("--cpu-sample", type=int, default=50_000, help="particles in the bounded CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=100_000, help="particles in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -128,26 +128,46 @@ def ncu_traffic_bytes():
         return None
 
 
+def usable_cpus() -> int:
+    """CPUs this process can really use: the affinity mask capped by the cgroup CPU quota (the GPU box
+    shows 128 logical CPUs but grants 16; 128 OpenMP threads on 16 CPUs run 16x slower than 32)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference_steps_per_s(args, scenario, n_full, sample_particles, steps=3):
     """The reference algorithm (oracle port, counter-RNG mode, propagate/reweight/normalize threaded
-    like std::execution::par) on a bounded sample; linear extrapolation to the full particle count."""
+    like std::execution::par) on a bounded sample; linear extrapolation to the full particle count.
+    Thread count: the better of 1x and 2x the usable CPUs (what the host can give the reference)."""
     from oracle import pyoracle as orc
 
-    threads = os.cpu_count() or 1
     n = min(sample_particles, n_full)
-    o = orc.Amcl(orc.AmclParam(min_particles=n, max_particles=n, scheme=orc.SYSTEMATIC, seed=1, rng_mode=1, threads=threads),
-                 orc.MotionParam(*MOTION))
-    o.set_map(orc.LFM, orc.LfmParam(**LFM), orc.Grid(scenario.cells, scenario.resolution))
-    o.initialize_normal(scenario.initial_mean, scenario.initial_cov)
-    o.update(orc.se2(*scenario.poses[0]), scenario.scans[0])  # warm-up
-    t0 = time.perf_counter()
-    for k in range(1, steps + 1):
-        o.update(orc.se2(*scenario.poses[k]), scenario.scans[k])
-    dt = (time.perf_counter() - t0) / steps
+    best = None
+    cpus = usable_cpus()
+    for threads in sorted({cpus, 2 * cpus}):
+        o = orc.Amcl(orc.AmclParam(min_particles=n, max_particles=n, scheme=orc.SYSTEMATIC, seed=1, rng_mode=1, threads=threads),
+                     orc.MotionParam(*MOTION))
+        o.set_map(orc.LFM, orc.LfmParam(**LFM), orc.Grid(scenario.cells, scenario.resolution))
+        o.initialize_normal(scenario.initial_mean, scenario.initial_cov)
+        o.update(orc.se2(*scenario.poses[0]), scenario.scans[0])  # warm-up
+        t0 = time.perf_counter()
+        for k in range(1, steps + 1):
+            o.update(orc.se2(*scenario.poses[k]), scenario.scans[k])
+        dt = (time.perf_counter() - t0) / steps
+        if best is None or dt < best[0]:
+            best = (dt, threads)
+    dt, threads = best
     full_step_s = dt * (n_full / n)
     return {
-        "value": 1.0 / full_step_s, "unit": UNIT, "cores": threads, "kind": "port",
-        "sample": f"{steps} steps of {n} particles x {args.beams} beams on the same map/scans, {dt * 1e3:.1f} ms/step, scaled x{n_full / n:.0f} to {n_full} particles",
+        "value": 1.0 / full_step_s, "unit": UNIT, "cores": threads, "kind": "port", "usable_cpus": cpus,
+        "sample": f"{steps} steps of {n} particles x {args.beams} beams on the same map/scans, {dt * 1e3:.1f} ms/step with {threads} OpenMP threads "
+                  f"({cpus} usable CPUs), scaled x{n_full / n:.0f} to {n_full} particles",
     }
 
 

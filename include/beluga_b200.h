@@ -205,6 +205,19 @@ int bb200_filter_adopt(bb200_filter* f, uint64_t n, int from_staging);
  * from the counter RNG) and beluga::estimate from globally summed raw moments (bb200_filter_moments). */
 int bb200_systematic_comb(uint64_t seed, uint32_t step, uint64_t global_total, uint64_t total_slots, uint64_t* stride, uint64_t* offset);
 int bb200_estimate_from_moments(const double moments[9], const double pivot_xy[2], bb200_estimate* out);
+/* Stream-ordered variants for sharded callers that put collectives on the same CUDA stream
+ * (bb200_filter_set_stream, e.g. torch's current stream): they only enqueue work -- no host
+ * synchronisation, no read-back; intermediate scalars stay on the device (device pointers 4 and 5).
+ *   enqueue_propagate_reweight: begin_step | propagate | schedule | reweight; the shard's largest weight is left in scalars.wmax_bits
+ *   enqueue_build_cdf:          exponent from scalars.wmax_bits (all-reduce it with MAX first), fixed-point scan; total in scalars.total
+ *   enqueue_resample_range / enqueue_adopt / enqueue_moments: as the synchronous calls above. */
+int bb200_filter_set_stream(bb200_filter* f, void* cuda_stream);
+int bb200_filter_enqueue_propagate_reweight(bb200_filter* f, const bb200_diff_drive_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points);
+int bb200_filter_enqueue_build_cdf(bb200_filter* f);
+int bb200_filter_enqueue_resample_range(bb200_filter* f, const bb200_resample_opts* o, uint64_t global_total, uint64_t cdf_offset,
+                                        uint64_t slot_begin, uint64_t slot_end);
+int bb200_filter_enqueue_adopt(bb200_filter* f, uint64_t n);
+int bb200_filter_enqueue_moments(bb200_filter* f, const double pivot_xy[2]);
 /* Ancestor index of every particle produced by the last resample (-1: injected random state). */
 int bb200_filter_ancestors(bb200_filter* f, int64_t* out, uint64_t capacity);
 /* The local fixed-point CDF built by the last build_cdf / normalize (parity hook). */
@@ -227,7 +240,8 @@ uint64_t bb200_filter_launch_count(const bb200_filter* f);
 /* Block until everything enqueued on the filter's stream has finished. */
 int bb200_filter_synchronize(bb200_filter* f);
 /* Raw device pointers (for torch.distributed / peer access plumbing): which = 0 states (double4),
- * 1 weights (double), 2 cdf (uint64), 3 staging states buffer (double4). */
+ * 1 weights (double), 2 cdf (uint64), 3 staging states buffer (double4), 4 the scalar block
+ * {u64 wmax_bits, u64 ticket, u64 total, i32 exponent, i32 valid, ...}, 5 the result block (9 raw moments). */
 int bb200_filter_device_pointer(bb200_filter* f, int which, void** ptr, uint64_t* bytes);
 
 /* ---------------------------------------------------------------------------------------------
