@@ -30,7 +30,8 @@ from ._capi import (RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC, SENSOR_BEAM, SENS
                     SENSOR_LIKELIHOOD_FIELD_PROB)
 
 __all__ = [
-    "Amcl", "AmclParams", "BeamModelParam", "DifferentialDriveModelParam", "Filter", "LikelihoodFieldModelParam",
+    "Amcl", "AmclParams", "BeamModelParam", "DifferentialDriveModelParam", "OmnidirectionalDriveModelParam", "StationaryModelParam",
+    "Filter", "LikelihoodFieldModelParam", "motion_sampling",
     "OccupancyGrid", "BelugaB200Error", "device_count", "se2",
     "RESAMPLE_MULTINOMIAL", "RESAMPLE_SYSTEMATIC", "SENSOR_BEAM", "SENSOR_LIKELIHOOD_FIELD", "SENSOR_LIKELIHOOD_FIELD_PROB",
 ]
@@ -93,6 +94,45 @@ class DifferentialDriveModelParam:
         return _capi.DiffDriveParam(self.rotation_noise_from_rotation, self.rotation_noise_from_translation,
                                     self.translation_noise_from_translation, self.translation_noise_from_rotation,
                                     self.distance_threshold)
+
+
+    def c_motion(self) -> _capi.MotionParam:
+        return _capi.MotionParam(_capi.MOTION_DIFFERENTIAL, self.rotation_noise_from_rotation, self.rotation_noise_from_translation,
+                                 self.translation_noise_from_translation, self.translation_noise_from_rotation, 0.0, self.distance_threshold)
+
+
+@dataclass
+class OmnidirectionalDriveModelParam:
+    """beluga::OmnidirectionalDriveModelParam (motion/omnidirectional_drive_model.hpp:36-68)."""
+    rotation_noise_from_rotation: float = 0.0
+    rotation_noise_from_translation: float = 0.0
+    translation_noise_from_translation: float = 0.0
+    translation_noise_from_rotation: float = 0.0
+    strafe_noise_from_translation: float = 0.0
+    distance_threshold: float = 0.01
+
+    def c_motion(self) -> _capi.MotionParam:
+        return _capi.MotionParam(_capi.MOTION_OMNIDIRECTIONAL, self.rotation_noise_from_rotation, self.rotation_noise_from_translation,
+                                 self.translation_noise_from_translation, self.translation_noise_from_rotation,
+                                 self.strafe_noise_from_translation, self.distance_threshold)
+
+
+@dataclass
+class StationaryModelParam:
+    """beluga::StationaryModel (motion/stationary_model.hpp:39-62) has no parameters."""
+
+    def c_motion(self) -> _capi.MotionParam:
+        return _capi.MotionParam(_capi.MOTION_STATIONARY, 0.0, 0.0, 0.0, 0.0, 0.0, 0.01)
+
+
+def motion_sampling(motion, pose, previous_pose) -> _capi.MotionSampling:
+    """MotionModel::operator()(control): the per-step sampling parameters of any of the three models."""
+    out = _capi.MotionSampling()
+    p = motion.c_motion()
+    st = _capi.load().bb200_motion_sampling_from_control(C.byref(p), _dptr(_f64(pose)), _dptr(_f64(previous_pose)), C.byref(out))
+    if st != _capi.OK:
+        raise BelugaB200Error(st, "bb200_motion_sampling_from_control")
+    return out
 
 
 @dataclass
@@ -240,8 +280,15 @@ class Filter:
 
     # per-step operations
     @staticmethod
-    def _sampling(s) -> _capi.DiffDriveSampling:
-        return s if isinstance(s, _capi.DiffDriveSampling) else _capi.DiffDriveSampling(*[float(v) for v in s])
+    def _sampling(s) -> _capi.MotionSampling:
+        """Accepts a MotionSampling or the six differential-drive scalars (rot1, trans, rot2 mean/std pairs)."""
+        if isinstance(s, _capi.MotionSampling):
+            return s
+        if isinstance(s, _capi.DiffDriveSampling):
+            s = [s.rot1_mean, s.rot1_std, s.trans_mean, s.trans_std, s.rot2_mean, s.rot2_std]
+        v = [float(x) for x in s]
+        return _capi.MotionSampling(_capi.MOTION_DIFFERENTIAL, (C.c_double * 3)(v[0], v[2], v[4]), (C.c_double * 3)(v[1], v[3], v[5]),
+                                    (C.c_double * 2)(1.0, 0.0))
 
     def propagate(self, sampling, step: int):
         s = self._sampling(sampling)
@@ -359,11 +406,12 @@ class Filter:
 class Amcl:
     """bb200_amcl: beluga::Amcl (algorithm/amcl_core.hpp:81-233) with the particle set on the GPU."""
 
-    def __init__(self, motion: DifferentialDriveModelParam, params: AmclParams):
+    def __init__(self, motion, params: AmclParams):
+        """`motion`: DifferentialDriveModelParam, OmnidirectionalDriveModelParam or StationaryModelParam."""
         self._lib = _capi.load()
-        p, m = params.c(), motion.c()
+        p, m = params.c(), motion.c_motion()
         h = C.c_void_p()
-        st = self._lib.bb200_amcl_create(C.byref(p), C.byref(m), C.byref(h))
+        st = self._lib.bb200_amcl_create_with_motion(C.byref(p), C.byref(m), C.byref(h))
         if st != _capi.OK:
             raise BelugaB200Error(st, self._lib.bb200_create_error().decode())
         self._h = h

@@ -28,6 +28,19 @@ class DiffDriveSampling(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("rot1_mean", "rot1_std", "trans_mean", "trans_std", "rot2_mean", "rot2_std")]
 
 
+MOTION_DIFFERENTIAL, MOTION_OMNIDIRECTIONAL, MOTION_STATIONARY = 0, 1, 2
+
+
+class MotionParam(C.Structure):
+    _fields_ = [("model", C.c_int)] + [(n, C.c_double) for n in (
+        "rotation_noise_from_rotation", "rotation_noise_from_translation", "translation_noise_from_translation",
+        "translation_noise_from_rotation", "strafe_noise_from_translation", "distance_threshold")]
+
+
+class MotionSampling(C.Structure):
+    _fields_ = [("model", C.c_int), ("mean", C.c_double * 3), ("stddev", C.c_double * 3), ("first_rotation", C.c_double * 2)]
+
+
 class LikelihoodFieldParam(C.Structure):
     _fields_ = [("max_obstacle_distance", C.c_double), ("max_laser_distance", C.c_double), ("z_hit", C.c_double),
                 ("z_random", C.c_double), ("sigma_hit", C.c_double), ("model_unknown_space", C.c_int),
@@ -68,7 +81,7 @@ class AmclParam(C.Structure):
 
 class StepPlan(C.Structure):
     _fields_ = [("update", C.c_int), ("resample", C.c_int), ("needs_ess", C.c_int), ("step", C.c_uint32),
-                ("random_state_probability", C.c_double), ("sampling", DiffDriveSampling), ("opts", ResampleOpts)]
+                ("random_state_probability", C.c_double), ("sampling", MotionSampling), ("opts", ResampleOpts)]
 
 
 class UpdateResult(C.Structure):
@@ -95,9 +108,9 @@ SIGNATURES = {
     "bb200_filter_size": (C.c_int, [_vp, _P(C.c_uint64)]),
     "bb200_filter_get_particles": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64]),
     "bb200_filter_initialize_normal": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64]),
-    "bb200_filter_propagate": (C.c_int, [_vp, _P(DiffDriveSampling), C.c_uint32]),
+    "bb200_filter_propagate": (C.c_int, [_vp, _P(MotionSampling), C.c_uint32]),
     "bb200_filter_reweight": (C.c_int, [_vp, _dbl, C.c_uint64]),
-    "bb200_filter_propagate_reweight": (C.c_int, [_vp, _P(DiffDriveSampling), C.c_uint32, _dbl, C.c_uint64]),
+    "bb200_filter_propagate_reweight": (C.c_int, [_vp, _P(MotionSampling), C.c_uint32, _dbl, C.c_uint64]),
     "bb200_filter_max_weight": (C.c_int, [_vp, _dbl]),
     "bb200_filter_build_cdf": (C.c_int, [_vp, C.c_double, _P(C.c_uint64), _P(C.c_int)]),
     "bb200_filter_normalize_by": (C.c_int, [_vp, C.c_uint64, _dbl]),
@@ -108,7 +121,7 @@ SIGNATURES = {
     "bb200_systematic_comb": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _P(C.c_uint64), _P(C.c_uint64)]),
     "bb200_estimate_from_moments": (C.c_int, [_dbl, _dbl, _P(Estimate)]),
     "bb200_filter_set_stream": (C.c_int, [_vp, _vp]),
-    "bb200_filter_enqueue_propagate_reweight": (C.c_int, [_vp, _P(DiffDriveSampling), C.c_uint32, _dbl, C.c_uint64]),
+    "bb200_filter_enqueue_propagate_reweight": (C.c_int, [_vp, _P(MotionSampling), C.c_uint32, _dbl, C.c_uint64]),
     "bb200_filter_enqueue_build_cdf": (C.c_int, [_vp]),
     "bb200_filter_enqueue_resample_range": (C.c_int, [_vp, _P(ResampleOpts), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "bb200_filter_enqueue_adopt": (C.c_int, [_vp, C.c_uint64]),
@@ -133,6 +146,8 @@ SIGNATURES = {
     "bb200_amcl_update": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64, _P(UpdateResult)]),
     "bb200_amcl_plan_update": (C.c_int, [_vp, _dbl, _P(StepPlan)]),
     "bb200_amcl_commit_update": (None, [_vp, C.c_int, C.c_double]),
+    "bb200_amcl_create_with_motion": (C.c_int, [_P(AmclParam), _P(MotionParam), _P(_vp)]),
+    "bb200_motion_sampling_from_control": (C.c_int, [_P(MotionParam), _dbl, _dbl, _P(MotionSampling)]),
     "bb200_diff_drive_sampling_from_control": (C.c_int, [_P(DiffDriveParam), _dbl, _dbl, _P(DiffDriveSampling)]),
 }
 

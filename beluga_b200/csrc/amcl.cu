@@ -44,7 +44,48 @@ bb200_diff_drive_sampling diff_drive_sampling(const bb200_diff_drive_param& p, c
   return s;
 }
 
-Amcl::Amcl(const bb200_amcl_param& p, const bb200_diff_drive_param& motion) : params_(p), motion_(motion) {
+bb200_motion_sampling motion_sampling(const bb200_motion_param& p, const Pose2& pose, const Pose2& prev) {
+  bb200_motion_sampling out{};
+  out.model = p.model;
+  out.first_rotation[0] = 1.0;
+  out.first_rotation[1] = 0.0;
+  if (p.model == BB200_MOTION_STATIONARY) {  // stationary_model.hpp:55: N(0, 0.02) for theta, x, y
+    for (int k = 0; k < 3; ++k) {
+      out.mean[k] = 0.0;
+      out.stddev[k] = 0.02;
+    }
+    return out;
+  }
+  if (p.model == BB200_MOTION_OMNIDIRECTIONAL) {  // omnidirectional_drive_model.hpp:101-129
+    const double tx = pose.x - prev.x, ty = pose.y - prev.y;
+    const double distance = std::sqrt(tx * tx + ty * ty);
+    const double distance_variance = distance * distance;
+    const Rot2 previous_orientation{prev.c, prev.s};
+    const Rot2 current_orientation{pose.c, pose.s};
+    const Rot2 rotation = rot_mul(current_orientation, rot_inverse(previous_orientation));
+    const Rot2 heading_rotation = rot_exp(std::atan2(ty, tx));
+    const Rot2 first_rotation = distance > p.distance_threshold ? rot_mul(heading_rotation, rot_inverse(previous_orientation)) : Rot2{1.0, 0.0};
+    const double rv = rotation_variance(rotation);
+    out.mean[0] = rot_log(rotation);
+    out.stddev[0] = std::sqrt(p.rotation_noise_from_rotation * rv + p.rotation_noise_from_translation * distance_variance);
+    out.mean[1] = distance;
+    out.stddev[1] = std::sqrt(p.translation_noise_from_translation * distance_variance + p.translation_noise_from_rotation * rv);
+    out.mean[2] = 0.0;
+    out.stddev[2] = std::sqrt(p.strafe_noise_from_translation * distance_variance + p.translation_noise_from_rotation * rv);
+    out.first_rotation[0] = first_rotation.c;
+    out.first_rotation[1] = first_rotation.s;
+    return out;
+  }
+  const bb200_diff_drive_param d{p.rotation_noise_from_rotation, p.rotation_noise_from_translation, p.translation_noise_from_translation,
+                                 p.translation_noise_from_rotation, p.distance_threshold};
+  const bb200_diff_drive_sampling s = diff_drive_sampling(d, pose, prev);
+  out.mean[0] = s.rot1_mean, out.stddev[0] = s.rot1_std;
+  out.mean[1] = s.trans_mean, out.stddev[1] = s.trans_std;
+  out.mean[2] = s.rot2_mean, out.stddev[2] = s.rot2_std;
+  return out;
+}
+
+Amcl::Amcl(const bb200_amcl_param& p, const bb200_motion_param& motion) : params_(p), motion_(motion) {
   bb200_filter_config c{};
   c.device = p.device;
   c.capacity = p.shard_capacity != 0 ? p.shard_capacity : p.max_particles;
@@ -102,7 +143,7 @@ int Amcl::plan_update(const double control[4], bb200_step_plan* plan) {
   window_[0] = pose;
   window_size_ = std::min(window_size_ + 1, 2);
   const Pose2& previous = window_[std::min(1, window_size_ - 1)];
-  plan->sampling = diff_drive_sampling(motion_, window_[0], previous);
+  plan->sampling = motion_sampling(motion_, window_[0], previous);
   plan->step = ++step_;
 
   // random_probability_estimator_(particles_) (thrun_recovery_probability_estimator.hpp:69-89) on the

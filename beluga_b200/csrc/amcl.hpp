@@ -13,10 +13,12 @@ namespace bb200 {
 
 /// DifferentialDriveModel::sampling_fn_2d host part -- motion/differential_drive_model.hpp:129-154.
 bb200_diff_drive_sampling diff_drive_sampling(const bb200_diff_drive_param& p, const Pose2& pose, const Pose2& previous_pose);
+/// MotionModel::operator()(control) host part for the three motion models.
+bb200_motion_sampling motion_sampling(const bb200_motion_param& p, const Pose2& pose, const Pose2& previous_pose);
 
 class Amcl {
  public:
-  Amcl(const bb200_amcl_param& p, const bb200_diff_drive_param& motion);
+  Amcl(const bb200_amcl_param& p, const bb200_motion_param& motion);
 
   Filter& filter() { return *filter_; }
   bool ok() const { return filter_ && filter_->ok(); }
@@ -35,7 +37,7 @@ class Amcl {
 
  private:
   bb200_amcl_param params_;
-  bb200_diff_drive_param motion_;
+  bb200_motion_param motion_;
   std::unique_ptr<Filter> filter_;
   std::string error_;
 

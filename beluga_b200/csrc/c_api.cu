@@ -17,7 +17,7 @@ struct bb200_filter {
 struct bb200_amcl {
   Amcl impl;
   bb200_filter* filter_view;  // non-owning alias handed out by bb200_amcl_filter
-  bb200_amcl(const bb200_amcl_param& p, const bb200_diff_drive_param& m) : impl(p, m), filter_view(nullptr) {}
+  bb200_amcl(const bb200_amcl_param& p, const bb200_motion_param& m) : impl(p, m), filter_view(nullptr) {}
 };
 
 namespace {
@@ -101,7 +101,7 @@ int bb200_filter_initialize_normal(bb200_filter* f, const double mean_xytheta[3]
   BB_REQUIRE(f && mean_xytheta && cov);
   return f->impl.initialize_normal(mean_xytheta, cov, n);
 }
-int bb200_filter_propagate(bb200_filter* f, const bb200_diff_drive_sampling* s, uint32_t step) {
+int bb200_filter_propagate(bb200_filter* f, const bb200_motion_sampling* s, uint32_t step) {
   BB_REQUIRE(f && s);
   return f->impl.propagate_reweight(s, step, nullptr, 0);
 }
@@ -110,7 +110,7 @@ int bb200_filter_reweight(bb200_filter* f, const double* points_xy, uint64_t n_p
   static const double kNoPoints[2] = {0.0, 0.0};
   return f->impl.propagate_reweight(nullptr, 0, points_xy != nullptr ? points_xy : kNoPoints, n_points);
 }
-int bb200_filter_propagate_reweight(bb200_filter* f, const bb200_diff_drive_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points) {
+int bb200_filter_propagate_reweight(bb200_filter* f, const bb200_motion_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points) {
   BB_REQUIRE(f && s && (points_xy || n_points == 0));
   static const double kNoPoints[2] = {0.0, 0.0};
   return f->impl.propagate_reweight(s, step, points_xy != nullptr ? points_xy : kNoPoints, n_points);
@@ -160,7 +160,7 @@ int bb200_filter_set_stream(bb200_filter* f, void* cuda_stream) {
   BB_REQUIRE(f);
   return f->impl.set_stream(cuda_stream);
 }
-int bb200_filter_enqueue_propagate_reweight(bb200_filter* f, const bb200_diff_drive_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points) {
+int bb200_filter_enqueue_propagate_reweight(bb200_filter* f, const bb200_motion_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points) {
   BB_REQUIRE(f && s && points_xy);
   return f->impl.enqueue_propagate_reweight(s, step, points_xy, n_points);
 }
@@ -223,12 +223,16 @@ int bb200_filter_device_pointer(bb200_filter* f, int which, void** ptr, uint64_t
 
 // ---- amcl ---------------------------------------------------------------------------------------
 
-int bb200_amcl_create(const bb200_amcl_param* p, const bb200_diff_drive_param* motion, bb200_amcl** out) {
+int bb200_amcl_create_with_motion(const bb200_amcl_param* p, const bb200_motion_param* motion, bb200_amcl** out) {
   if (p == nullptr || motion == nullptr || out == nullptr) {
     g_create_error = "null argument";
     return BB200_ERR_INVALID_ARGUMENT;
   }
   *out = nullptr;
+  if (motion->model < BB200_MOTION_DIFFERENTIAL || motion->model > BB200_MOTION_STATIONARY) {
+    g_create_error = "unknown motion model";
+    return BB200_ERR_INVALID_ARGUMENT;
+  }
   if (p->shard_capacity != 0 && (p->shard_first_index + p->shard_capacity > p->max_particles || p->min_particles != p->max_particles)) {
     g_create_error = "a shard must lie inside [0, max_particles) and use min_particles == max_particles";
     return BB200_ERR_INVALID_ARGUMENT;
@@ -256,6 +260,15 @@ int bb200_amcl_create(const bb200_amcl_param* p, const bb200_diff_drive_param* m
   *out = a;
   return BB200_OK;
 }
+int bb200_amcl_create(const bb200_amcl_param* p, const bb200_diff_drive_param* motion, bb200_amcl** out) {
+  if (motion == nullptr) {
+    g_create_error = "null argument";
+    return BB200_ERR_INVALID_ARGUMENT;
+  }
+  const bb200_motion_param m{BB200_MOTION_DIFFERENTIAL, motion->rotation_noise_from_rotation, motion->rotation_noise_from_translation,
+                             motion->translation_noise_from_translation, motion->translation_noise_from_rotation, 0.0, motion->distance_threshold};
+  return bb200_amcl_create_with_motion(p, &m, out);
+}
 void bb200_amcl_destroy(bb200_amcl* a) { delete a; }
 const char* bb200_amcl_last_error(const bb200_amcl* a) { return a != nullptr ? a->impl.last_error() : "null amcl"; }
 bb200_filter* bb200_amcl_filter(bb200_amcl* a) { return a != nullptr ? a->filter_view : nullptr; }
@@ -281,6 +294,12 @@ int bb200_amcl_plan_update(bb200_amcl* a, const double control_pose[4], bb200_st
 }
 void bb200_amcl_commit_update(bb200_amcl* a, int resampled, double random_state_probability) {
   if (a != nullptr) a->impl.commit_update(resampled, random_state_probability);
+}
+int bb200_motion_sampling_from_control(const bb200_motion_param* p, const double pose[4], const double previous_pose[4], bb200_motion_sampling* out) {
+  BB_REQUIRE(p && pose && previous_pose && out);
+  *out = bb200::motion_sampling(*p, bb200::Pose2{pose[0], pose[1], pose[2], pose[3]},
+                                bb200::Pose2{previous_pose[0], previous_pose[1], previous_pose[2], previous_pose[3]});
+  return BB200_OK;
 }
 int bb200_diff_drive_sampling_from_control(const bb200_diff_drive_param* p, const double pose[4], const double previous_pose[4], bb200_diff_drive_sampling* out) {
   BB_REQUIRE(p && pose && previous_pose && out);

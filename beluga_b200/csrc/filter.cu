@@ -19,6 +19,18 @@ cudaError_t dev_alloc(T** p, size_t count) {
 
 Pose2 pose_from_array(const double* d) { return Pose2{d[0], d[1], d[2], d[3]}; }
 
+MotionSampling to_kernel_sampling(const bb200_motion_sampling& s) {
+  MotionSampling m{};
+  m.model = s.model;
+  for (int k = 0; k < 3; ++k) {
+    m.mean[k] = s.mean[k];
+    m.stddev[k] = s.stddev[k];
+  }
+  m.first_c = s.first_rotation[0];
+  m.first_s = s.first_rotation[1];
+  return m;
+}
+
 }  // namespace
 
 bool normal_transform(const double cov[9], double transform[9], std::string* error) {
@@ -235,14 +247,14 @@ int Filter::set_stream(void* stream) {
   return BB200_OK;
 }
 
-int Filter::enqueue_propagate_reweight(const bb200_diff_drive_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points) {
+int Filter::enqueue_propagate_reweight(const bb200_motion_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points) {
   if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
   if (points_xy == nullptr || sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set / no points");
   BB_CHECK(cudaSetDevice(config_.device));
   int st = upload_points(points_xy, n_points);  // the caller synchronised at the end of the previous step
   if (st != BB200_OK) return st;
-  DiffDriveSampling s{};
-  if (sampling != nullptr) s = DiffDriveSampling{sampling->rot1_mean, sampling->rot1_std, sampling->trans_mean, sampling->trans_std, sampling->rot2_mean, sampling->rot2_std};
+  MotionSampling s{};
+  if (sampling != nullptr) s = to_kernel_sampling(*sampling);
   mark("begin_step");
   launch_begin_step(scalars_, stream_);
   BB_LAUNCHED("begin_step");
@@ -508,11 +520,11 @@ int Filter::upload_points(const double* points_xy, uint64_t n_points) {
   return BB200_OK;
 }
 
-int Filter::enqueue_propagate_reweight(const DiffDriveSampling* sampling, uint32_t step, bool do_reweight, uint64_t n_points) {
+int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t step, bool do_reweight, uint64_t n_points) {
   const bool scheduled = do_reweight && schedule_enabled_ && n_ >= kScheduleMinParticles;
   if (sampling != nullptr || scheduled) {
     mark("propagate");
-    launch_propagate(states_[cur_], n_, sampling != nullptr, sampling != nullptr ? *sampling : DiffDriveSampling{}, config_.seed, step,
+    launch_propagate(states_[cur_], n_, sampling != nullptr, sampling != nullptr ? *sampling : MotionSampling{}, config_.seed, step,
                      config_.first_index, scheduled ? sched_ : nullptr, stream_);
     BB_LAUNCHED_N("propagate", scheduled ? 2 : 1);
   }
@@ -537,7 +549,7 @@ int Filter::enqueue_propagate_reweight(const DiffDriveSampling* sampling, uint32
   return BB200_OK;
 }
 
-int Filter::propagate_reweight(const bb200_diff_drive_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points) {
+int Filter::propagate_reweight(const bb200_motion_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points) {
   if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
   const bool do_reweight = points_xy != nullptr;
   if (do_reweight && sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set");
@@ -548,8 +560,8 @@ int Filter::propagate_reweight(const bb200_diff_drive_sampling* sampling, uint32
     const int st = upload_points(points_xy, n_points);
     if (st != BB200_OK) return st;
   }
-  DiffDriveSampling s{};
-  if (sampling != nullptr) s = DiffDriveSampling{sampling->rot1_mean, sampling->rot1_std, sampling->trans_mean, sampling->trans_std, sampling->rot2_mean, sampling->rot2_std};
+  MotionSampling s{};
+  if (sampling != nullptr) s = to_kernel_sampling(*sampling);
   mark("begin_step");
   launch_begin_step(scalars_, stream_);
   BB_LAUNCHED("begin_step");
@@ -817,7 +829,7 @@ int Filter::resample_kld(const bb200_resample_opts& o, uint64_t* accepted) {
   return BB200_OK;
 }
 
-int Filter::step_resample(const bb200_diff_drive_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points,
+int Filter::step_resample(const bb200_motion_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points,
                           const bb200_resample_opts& o, bb200_estimate* est, double* weight_sum, uint64_t* new_size) {
   if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
   if (sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set");
@@ -827,7 +839,7 @@ int Filter::step_resample(const bb200_diff_drive_sampling& sampling, uint32_t st
   BB_CHECK(cudaSetDevice(config_.device));
   int st = upload_points(points_xy, n_points);
   if (st != BB200_OK) return st;
-  const DiffDriveSampling s{sampling.rot1_mean, sampling.rot1_std, sampling.trans_mean, sampling.trans_std, sampling.rot2_mean, sampling.rot2_std};
+  const MotionSampling s = to_kernel_sampling(sampling);
 
   mark("begin_step");
   launch_begin_step(scalars_, stream_);

@@ -32,7 +32,7 @@ class Filter {
   int initialize_normal(const double mean[3], const double cov[9], uint64_t n);
   uint64_t size() const { return n_; }
 
-  int propagate_reweight(const bb200_diff_drive_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points);
+  int propagate_reweight(const bb200_motion_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points);
   int max_weight(double* wmax);
   int build_cdf(double global_wmax, uint64_t* local_total, int* exponent);
   int normalize_by(uint64_t global_total, double* local_sum_sq);
@@ -48,13 +48,13 @@ class Filter {
 
   /// Fused single-GPU step: propagate | reweight | normalize | resample | estimate with one
   /// host synchronisation at the end (the composition Amcl::update performs every step).
-  int step_resample(const bb200_diff_drive_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points,
+  int step_resample(const bb200_motion_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points,
                     const bb200_resample_opts& o, bb200_estimate* est, double* weight_sum, uint64_t* new_size);
 
   // Stream-ordered variants for callers that interleave collectives on the same stream (sharded
   // filters): nothing here synchronises with the host or reads results back.
   int set_stream(void* stream);
-  int enqueue_propagate_reweight(const bb200_diff_drive_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points);
+  int enqueue_propagate_reweight(const bb200_motion_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points);
   int enqueue_build_cdf();                      // exponent from the wmax in the device scalars (all-reduced by the caller)
   int enqueue_resample_range(const bb200_resample_opts& o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin, uint64_t slot_end);
   int enqueue_adopt(uint64_t n);
@@ -75,7 +75,7 @@ class Filter {
   int fail(int status, const std::string& message);
   int check(cudaError_t e, const char* what);
   int upload_points(const double* points_xy, uint64_t n_points);
-  int enqueue_propagate_reweight(const DiffDriveSampling* sampling, uint32_t step, bool do_reweight, uint64_t n_points);
+  int enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t step, bool do_reweight, uint64_t n_points);
   int ensure_cdf_ready();
   int resample_kld(const bb200_resample_opts& o, uint64_t* accepted);
   ResampleArgs make_resample_args(const bb200_resample_opts& o, uint64_t slot_begin, uint64_t slot_end, bool with_hashes) const;

@@ -161,18 +161,18 @@ __device__ __forceinline__ void store_pose(Pose2* p, const Pose2& v) {
   *(reinterpret_cast<double2*>(p) + 1) = make_double2(v.x, v.y);
 }
 
-__device__ __forceinline__ Pose2 propagate_one(const Pose2& st, const DiffDriveSampling& p, uint64_t seed, uint64_t index, uint32_t step) {
+__device__ __forceinline__ Pose2 propagate_one(const Pose2& st, const MotionSampling& p, uint64_t seed, uint64_t index, uint32_t step) {
   double z0, z1, z2, unused;
   box_muller(counter_draw(seed, index, step, kStreamMotion0), z0, z1);
   box_muller(counter_draw(seed, index, step, kStreamMotion1), z2, unused);
   // std::normal_distribution: ret * stddev + mean (libstdc++ bits/random.tcc:1843)
-  const double rot1 = z0 * p.rot1_std + p.rot1_mean;
-  const double trans = z1 * p.trans_std + p.trans_mean;
-  const double rot2 = z2 * p.rot2_std + p.rot2_mean;
-  return diff_drive_apply(st, rot1, trans, rot2);
+  const double d0 = z0 * p.stddev[0] + p.mean[0];
+  const double d1 = z1 * p.stddev[1] + p.mean[1];
+  const double d2 = z2 * p.stddev[2] + p.mean[2];
+  return motion_apply(p.model, st, d0, d1, d2, Rot2{p.first_c, p.first_s});
 }
 
-__global__ void __launch_bounds__(kPrThreads) propagate_kernel(Pose2* __restrict__ states, uint64_t n, int do_propagate, DiffDriveSampling sampling,
+__global__ void __launch_bounds__(kPrThreads) propagate_kernel(Pose2* __restrict__ states, uint64_t n, int do_propagate, MotionSampling sampling,
                                                                uint64_t seed, uint32_t step, uint64_t first_index, Schedule* __restrict__ sched) {
   __shared__ double s_red[kPrThreads / kWarp];
   const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kPrThreads + threadIdx.x;
@@ -947,7 +947,7 @@ void launch_initialize_normal(Pose2* states, double* weights, uint64_t n, const 
   initialize_normal_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(states, weights, n, p, seed, first_index);
 }
 
-void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const DiffDriveSampling& sampling, uint64_t seed, uint32_t step,
+void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const MotionSampling& sampling, uint64_t seed, uint32_t step,
                       uint64_t first_index, Schedule* sched, cudaStream_t stream) {
   if (n == 0) return;
   if (sched != nullptr) schedule_reset_kernel<<<1, 1, 0, stream>>>(sched);

@@ -41,8 +41,12 @@ struct BeamParams {
   double z_hit, z_short, z_max, z_rand, sigma_hit, lambda_short, beam_max_range;
 };
 
-struct DiffDriveSampling {
-  double rot1_mean, rot1_std, trans_mean, trans_std, rot2_mean, rot2_std;
+/// Mirrors bb200_motion_sampling (include/beluga_b200.h).
+struct MotionSampling {
+  int model;
+  double mean[3];
+  double stddev[3];
+  double first_c, first_s;
 };
 
 /// Per-filter device scalars (one cache line; zeroed by launch_begin_step).
@@ -83,7 +87,7 @@ struct Schedule {
 };
 
 /// propagate (or only accumulate the cloud moments when do_propagate is false).  sched may be null.
-void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const DiffDriveSampling& sampling, uint64_t seed, uint32_t step,
+void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const MotionSampling& sampling, uint64_t seed, uint32_t step,
                       uint64_t first_index, Schedule* sched, cudaStream_t stream);
 uint32_t schedule_max_bins();
 uint32_t schedule_tile_count();

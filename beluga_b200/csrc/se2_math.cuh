@@ -80,6 +80,24 @@ BB_HD Pose2 diff_drive_apply(const Pose2& st, double rot1, double trans, double 
   return pose_mul(a, Pose2{r2.c, r2.s, trans, 0.0});
 }
 
+/// The per-particle composition of the three motion models given their three sampled scalars.
+///   0 differential   (differential_drive_model.hpp:158-162)
+///   1 omnidirectional (omnidirectional_drive_model.hpp:138-144): second = SO2(d0) * first^-1,
+///     translation = (d1, -d2), state * SE2(first, 0) * SE2(second, translation)
+///   2 stationary     (stationary_model.hpp:56-58): state * SE2(SO2(d0), (d1, d2))
+BB_HD Pose2 motion_apply(int model, const Pose2& st, double d0, double d1, double d2, const Rot2& first) {
+  if (model == 1) {
+    const Rot2 second = rot_mul(rot_exp(d0), rot_inverse(first));
+    const Pose2 a = pose_mul(st, Pose2{first.c, first.s, 0.0, 0.0});
+    return pose_mul(a, Pose2{second.c, second.s, d1, -d2});
+  }
+  if (model == 2) {
+    const Rot2 r = rot_exp(d0);
+    return pose_mul(st, Pose2{r.c, r.s, d1, d2});
+  }
+  return diff_drive_apply(st, d0, d1, d2);
+}
+
 // ---- counter RNG -------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11).
 // Counter = (index lo, index hi, step, stream); key = seed.  A draw yields two 64-bit words.

@@ -64,6 +64,37 @@ typedef struct bb200_diff_drive_sampling {
   double rot2_mean, rot2_std;
 } bb200_diff_drive_sampling;
 
+/* The motion models of beluga_ros::Amcl::motion_model_variant (beluga_ros/include/beluga_ros/amcl.hpp:108-111). */
+typedef enum bb200_motion_model {
+  BB200_MOTION_DIFFERENTIAL = 0,    /* motion/differential_drive_model.hpp */
+  BB200_MOTION_OMNIDIRECTIONAL = 1, /* motion/omnidirectional_drive_model.hpp */
+  BB200_MOTION_STATIONARY = 2       /* motion/stationary_model.hpp */
+} bb200_motion_model;
+
+/* DifferentialDriveModelParam / OmnidirectionalDriveModelParam (omnidirectional_drive_model.hpp:36-68)
+ * in one block; strafe_noise_from_translation is only read by the omnidirectional model. */
+typedef struct bb200_motion_param {
+  int model; /* bb200_motion_model */
+  double rotation_noise_from_rotation;
+  double rotation_noise_from_translation;
+  double translation_noise_from_translation;
+  double translation_noise_from_rotation;
+  double strafe_noise_from_translation;
+  double distance_threshold; /* default 0.01 */
+} bb200_motion_param;
+
+/* What a motion model derives from one control action: three normal distributions, drawn per
+ * particle in this order, and (omnidirectional only) the deterministic first rotation.
+ *   differential:     (rot1, trans, rot2)            state * SE2(rot1, 0) * SE2(rot2, (trans, 0))
+ *   omnidirectional:  (rotation, translation, strafe) state * SE2(first, 0) * SE2(SO2(rotation) * first^-1, (translation, -strafe))
+ *   stationary:       (theta, x, y) ~ N(0, 0.02)      state * SE2(theta, (x, y)) */
+typedef struct bb200_motion_sampling {
+  int model;
+  double mean[3];
+  double stddev[3];
+  double first_rotation[2]; /* {cos, sin} */
+} bb200_motion_sampling;
+
 /* beluga::LikelihoodFieldModelBaseParam -- sensor/likelihood_field_model_base.hpp:42-64 */
 typedef struct bb200_likelihood_field_param {
   double max_obstacle_distance; /* default 100.0 */
@@ -160,11 +191,11 @@ int bb200_filter_initialize_normal(bb200_filter* f, const double mean_xytheta[3]
 /* actions::propagate(model(control)) (actions/propagate.hpp:57-79) for DifferentialDriveModel:
  * per particle 3 normals (counter RNG keyed by seed / global index / step) and the SE2 compose of
  * differential_drive_model.hpp:156-163. */
-int bb200_filter_propagate(bb200_filter* f, const bb200_diff_drive_sampling* s, uint32_t step);
+int bb200_filter_propagate(bb200_filter* f, const bb200_motion_sampling* s, uint32_t step);
 /* actions::reweight(sensor_model(points)) (actions/reweight.hpp:54-60): w *= L(state). */
 int bb200_filter_reweight(bb200_filter* f, const double* points_xy, uint64_t n_points);
 /* Fused propagate | reweight (one pass over the particle set). */
-int bb200_filter_propagate_reweight(bb200_filter* f, const bb200_diff_drive_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points);
+int bb200_filter_propagate_reweight(bb200_filter* f, const bb200_motion_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points);
 
 /* Weight statistics of the local shard after reweight: the largest weight and, once an exponent
  * is fixed, the fixed-point total.  Single GPU: bb200_filter_normalize does all of it. */
@@ -212,7 +243,7 @@ int bb200_estimate_from_moments(const double moments[9], const double pivot_xy[2
  *   enqueue_build_cdf:          exponent from scalars.wmax_bits (all-reduce it with MAX first), fixed-point scan; total in scalars.total
  *   enqueue_resample_range / enqueue_adopt / enqueue_moments: as the synchronous calls above. */
 int bb200_filter_set_stream(bb200_filter* f, void* cuda_stream);
-int bb200_filter_enqueue_propagate_reweight(bb200_filter* f, const bb200_diff_drive_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points);
+int bb200_filter_enqueue_propagate_reweight(bb200_filter* f, const bb200_motion_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points);
 int bb200_filter_enqueue_build_cdf(bb200_filter* f);
 int bb200_filter_enqueue_resample_range(bb200_filter* f, const bb200_resample_opts* o, uint64_t global_total, uint64_t cdf_offset,
                                         uint64_t slot_begin, uint64_t slot_end);
@@ -281,7 +312,7 @@ typedef struct bb200_step_plan {
   int needs_ess;                      /* selective resampling: resample only if ESS < N/2 */
   uint32_t step;
   double random_state_probability;
-  bb200_diff_drive_sampling sampling;
+  bb200_motion_sampling sampling;
   bb200_resample_opts opts;
 } bb200_step_plan;
 
@@ -311,6 +342,11 @@ int bb200_amcl_update(bb200_amcl* a, const double control_pose[4], const double*
 /* The two host halves of bb200_amcl_update for callers that drive the filter themselves. */
 int bb200_amcl_plan_update(bb200_amcl* a, const double control_pose[4], bb200_step_plan* plan);
 void bb200_amcl_commit_update(bb200_amcl* a, int resampled, double random_state_probability);
+/* Amcl with any of the three motion models (bb200_amcl_create is the differential-drive shorthand). */
+int bb200_amcl_create_with_motion(const bb200_amcl_param* p, const bb200_motion_param* motion, bb200_amcl** out);
+/* MotionModel::operator()(control) host part for any model (differential_drive_model.hpp:129-154,
+ * omnidirectional_drive_model.hpp:101-129, stationary_model.hpp:52). */
+int bb200_motion_sampling_from_control(const bb200_motion_param* p, const double pose[4], const double previous_pose[4], bb200_motion_sampling* out);
 /* DifferentialDriveModel::operator()(control) host part -- differential_drive_model.hpp:129-154. */
 int bb200_diff_drive_sampling_from_control(const bb200_diff_drive_param* p, const double pose[4], const double previous_pose[4], bb200_diff_drive_sampling* out);
 

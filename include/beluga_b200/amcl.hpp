@@ -78,8 +78,8 @@ class Amcl {
     p.resample_scheme = params.resample_scheme;
     p.seed = params.seed;
     p.device = params.device;
-    const bb200_diff_drive_param m = motion_model_.c_param();
-    const int st = bb200_amcl_create(&p, &m, &handle_);
+    const bb200_motion_param m = motion_model_.c_motion_param();
+    const int st = bb200_amcl_create_with_motion(&p, &m, &handle_);
     if (st != BB200_OK) throw Error(st, bb200_create_error());
     check(sensor_model_.attach(bb200_amcl_filter(handle_)));
   }

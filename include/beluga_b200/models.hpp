@@ -113,11 +113,50 @@ class DifferentialDriveModel {
                                   params_.translation_noise_from_translation, params_.translation_noise_from_rotation,
                                   params_.distance_threshold};
   }
+  [[nodiscard]] bb200_motion_param c_motion_param() const {
+    return bb200_motion_param{BB200_MOTION_DIFFERENTIAL, params_.rotation_noise_from_rotation, params_.rotation_noise_from_translation,
+                              params_.translation_noise_from_translation, params_.translation_noise_from_rotation, 0.0, params_.distance_threshold};
+  }
 
  private:
   param_type params_;
 };
 using DifferentialDriveModel2d = DifferentialDriveModel;
+
+/// Same members and defaults as beluga::OmnidirectionalDriveModelParam (omnidirectional_drive_model.hpp:36-68).
+struct OmnidirectionalDriveModelParam {
+  double rotation_noise_from_rotation;
+  double rotation_noise_from_translation;
+  double translation_noise_from_translation;
+  double translation_noise_from_rotation;
+  double strafe_noise_from_translation;
+  double distance_threshold = 0.01;
+};
+
+/// beluga::OmnidirectionalDriveModel (omnidirectional_drive_model.hpp:78-158).
+class OmnidirectionalDriveModel {
+ public:
+  using state_type = SE2d;
+  using control_type = std::tuple<state_type, state_type>;
+  using param_type = OmnidirectionalDriveModelParam;
+  explicit OmnidirectionalDriveModel(const param_type& params) : params_{params} {}
+  [[nodiscard]] bb200_motion_param c_motion_param() const {
+    return bb200_motion_param{BB200_MOTION_OMNIDIRECTIONAL, params_.rotation_noise_from_rotation, params_.rotation_noise_from_translation,
+                              params_.translation_noise_from_translation, params_.translation_noise_from_rotation,
+                              params_.strafe_noise_from_translation, params_.distance_threshold};
+  }
+
+ private:
+  param_type params_;
+};
+
+/// beluga::StationaryModel (stationary_model.hpp:39-62).
+class StationaryModel {
+ public:
+  using state_type = SE2d;
+  using control_type = std::tuple<state_type, state_type>;
+  [[nodiscard]] bb200_motion_param c_motion_param() const { return bb200_motion_param{BB200_MOTION_STATIONARY, 0, 0, 0, 0, 0, 0.01}; }
+};
 
 // ---- maps ----------------------------------------------------------------------------------------
 

@@ -59,7 +59,8 @@ struct UpdateResult {
 
 class Amcl {
  public:
-  Amcl(const AmclParams& p, const DifferentialDriveParam& motion) : params_(p), motion_(motion), thrun_(p.alpha_slow, p.alpha_fast), engine_(p.seed) {
+  Amcl(const AmclParams& p, const DifferentialDriveParam& motion, int motion_model = 0, const OmnidirectionalDriveParam& omni = {})
+      : params_(p), motion_(motion), motion_model_(motion_model), omni_(omni), thrun_(p.alpha_slow, p.alpha_fast), engine_(p.seed) {
     update_policy_.min_distance = p.update_min_d;
     update_policy_.min_angle = p.update_min_a;
     every_n_.count = p.resample_interval;
@@ -116,7 +117,9 @@ class Amcl {
     if (!update_policy_(control_action) && !force_update_) return out;
 
     window_.push(control_action);
-    const DiffDriveSampling sampling = diff_drive_sampling(motion_, window_[0], window_[1]);
+    const MotionSampling sampling = motion_model_ == 1   ? omni_drive_sampling(omni_, window_[0], window_[1])
+                                    : motion_model_ == 2 ? stationary_sampling()
+                                                         : to_motion_sampling(diff_drive_sampling(motion_, window_[0], window_[1]));
     ++step_;
 
     propagate(sampling);
@@ -152,16 +155,16 @@ class Amcl {
   }
 
  private:
-  void propagate(const DiffDriveSampling& sampling) {
+  void propagate(const MotionSampling& sampling) {
     if (params_.rng_mode == RngMode::kCounter) {
       const std::int64_t n = static_cast<std::int64_t>(states_.size());
 #pragma omp parallel for num_threads(params_.threads) schedule(static) if (params_.threads > 1)
       for (std::int64_t i = 0; i < n; ++i) {
         states_[static_cast<std::size_t>(i)] =
-            diff_drive_sample_counter(states_[static_cast<std::size_t>(i)], sampling, params_.seed, static_cast<std::uint64_t>(i), step_);
+            motion_sample_counter(states_[static_cast<std::size_t>(i)], sampling, params_.seed, static_cast<std::uint64_t>(i), step_);
       }
     } else {
-      diff_drive_propagate_std(states_, sampling, motion_distribution_, engine_);
+      motion_propagate_std(states_, sampling, motion_distribution_, engine_);
     }
   }
 
@@ -267,6 +270,8 @@ class Amcl {
 
   AmclParams params_;
   DifferentialDriveParam motion_;
+  int motion_model_{0};
+  OmnidirectionalDriveParam omni_;
   ThrunRecoveryProbabilityEstimator thrun_;
   OnMotionPolicy update_policy_{};
   EveryNPolicy every_n_{};

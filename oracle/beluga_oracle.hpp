@@ -529,6 +529,77 @@ inline SE2 diff_drive_apply(const SE2& state, double rot1, double trans, double 
   return state * SE2{first_rotation, 0.0, 0.0} * SE2{second_rotation, trans, 0.0};
 }
 
+/// Generic form of what a motion model derives from a control action: three normal distributions
+/// and (omnidirectional only) the deterministic first rotation.  model: 0 differential,
+/// 1 omnidirectional, 2 stationary.
+struct MotionSampling {
+  int model{0};
+  double mean[3]{0, 0, 0};
+  double stddev[3]{0, 0, 0};
+  SO2 first_rotation{};
+};
+
+/// motion/omnidirectional_drive_model.hpp:36-68
+struct OmnidirectionalDriveParam {
+  double rotation_noise_from_rotation{0.0};
+  double rotation_noise_from_translation{0.0};
+  double translation_noise_from_translation{0.0};
+  double translation_noise_from_rotation{0.0};
+  double strafe_noise_from_translation{0.0};
+  double distance_threshold{0.01};
+};
+
+inline MotionSampling to_motion_sampling(const DiffDriveSampling& d) {
+  MotionSampling m;
+  m.model = 0;
+  m.mean[0] = d.rot1_mean, m.stddev[0] = d.rot1_std;
+  m.mean[1] = d.trans_mean, m.stddev[1] = d.trans_std;
+  m.mean[2] = d.rot2_mean, m.stddev[2] = d.rot2_std;
+  return m;
+}
+
+/// motion/omnidirectional_drive_model.hpp:101-129 (host part).
+inline MotionSampling omni_drive_sampling(const OmnidirectionalDriveParam& params, const SE2& pose, const SE2& previous_pose) {
+  const double tx = pose.x - previous_pose.x;
+  const double ty = pose.y - previous_pose.y;
+  const double distance = std::sqrt(tx * tx + ty * ty);
+  const double distance_variance = distance * distance;
+  const SO2& previous_orientation = previous_pose.r;
+  const SO2& current_orientation = pose.r;
+  const SO2 rotation = current_orientation * previous_orientation.inverse();
+  const SO2 heading_rotation{std::atan2(ty, tx)};
+  const SO2 first_rotation = distance > params.distance_threshold ? heading_rotation * previous_orientation.inverse() : SO2{};
+  MotionSampling m;
+  m.model = 1;
+  m.mean[0] = rotation.log();
+  m.stddev[0] = std::sqrt(params.rotation_noise_from_rotation * rotation_variance(rotation) + params.rotation_noise_from_translation * distance_variance);
+  m.mean[1] = distance;
+  m.stddev[1] = std::sqrt(params.translation_noise_from_translation * distance_variance + params.translation_noise_from_rotation * rotation_variance(rotation));
+  m.mean[2] = 0.0;
+  m.stddev[2] = std::sqrt(params.strafe_noise_from_translation * distance_variance + params.translation_noise_from_rotation * rotation_variance(rotation));
+  m.first_rotation = first_rotation;
+  return m;
+}
+
+/// motion/stationary_model.hpp:52-60: three draws from N(0, 0.02).
+inline MotionSampling stationary_sampling() {
+  MotionSampling m;
+  m.model = 2;
+  for (int k = 0; k < 3; ++k) m.stddev[k] = 0.02;
+  return m;
+}
+
+/// The per-particle composition given the three sampled scalars (in draw order):
+/// differential_drive_model.hpp:158-162, omnidirectional_drive_model.hpp:138-144, stationary_model.hpp:56-58.
+inline SE2 motion_apply(const MotionSampling& m, const SE2& state, double d0, double d1, double d2) {
+  if (m.model == 1) {
+    const SO2 second_rotation = SO2{d0} * m.first_rotation.inverse();
+    return state * SE2{m.first_rotation, 0.0, 0.0} * SE2{second_rotation, d1, -d2};
+  }
+  if (m.model == 2) return state * SE2{SO2{d0}, d1, d2};
+  return diff_drive_apply(state, d0, d1, d2);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Counter-mode RNG ("mode B"): Philox4x32-10 (Salmon et al., SC'11; Random123 constants).
 // The GPU kernels use the same counters, so draws are reproducible per (seed, step, slot).
@@ -604,6 +675,28 @@ inline SE2 diff_drive_sample_counter(const SE2& state, const DiffDriveSampling& 
   const double trans = z1 * p.trans_std + p.trans_mean;
   const double rot2 = z2 * p.rot2_std + p.rot2_mean;
   return diff_drive_apply(state, rot1, trans, rot2);
+}
+
+/// Mode-B propagate for any motion model.
+inline SE2 motion_sample_counter(const SE2& state, const MotionSampling& m, std::uint64_t seed, std::uint64_t index, std::uint32_t step) {
+  double z0, z1, z2, unused;
+  box_muller(counter_draw(seed, index, step, kStreamMotion0), z0, z1);
+  box_muller(counter_draw(seed, index, step, kStreamMotion1), z2, unused);
+  return motion_apply(m, state, z0 * m.stddev[0] + m.mean[0], z1 * m.stddev[1] + m.mean[1], z2 * m.stddev[2] + m.mean[2]);
+}
+
+/// Mode-A propagate for any motion model: one shared std::normal_distribution like the reference's
+/// `static thread_local auto distribution` in each model's lambda.
+template <class URNG>
+void motion_propagate_std(std::vector<SE2>& states, const MotionSampling& m, std::normal_distribution<double>& distribution, URNG& gen) {
+  using Param = std::normal_distribution<double>::param_type;
+  const Param p0{m.mean[0], m.stddev[0]}, p1{m.mean[1], m.stddev[1]}, p2{m.mean[2], m.stddev[2]};
+  for (auto& s : states) {
+    const double d0 = distribution(gen, p0);
+    const double d1 = distribution(gen, p1);
+    const double d2 = distribution(gen, p2);
+    s = motion_apply(m, s, d0, d1, d2);
+  }
 }
 
 /// Mode-A propagate: actions/propagate.hpp:57-79 with the thread-local normal_distribution of

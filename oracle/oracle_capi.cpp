@@ -209,6 +209,44 @@ void orc_diff_drive_propagate(const double* sampling6, int mode, std::uint64_t s
   }
 }
 
+struct orc_omni_param {
+  double alpha1, alpha2, alpha3, alpha4, alpha5, distance_threshold;
+};
+
+/// Sampling parameters of any motion model: out10 = {mean[3], stddev[3], first_rotation cos, sin, model, 0}.
+void orc_motion_sampling(int model, const orc_omni_param* p, const double* pose, const double* previous_pose, double* out10) {
+  MotionSampling m;
+  if (model == 1) {
+    m = omni_drive_sampling(OmnidirectionalDriveParam{p->alpha1, p->alpha2, p->alpha3, p->alpha4, p->alpha5, p->distance_threshold}, se2_from_data(pose),
+                            se2_from_data(previous_pose));
+  } else if (model == 2) {
+    m = stationary_sampling();
+  } else {
+    m = to_motion_sampling(diff_drive_sampling(DifferentialDriveParam{p->alpha1, p->alpha2, p->alpha3, p->alpha4, p->distance_threshold},
+                                               se2_from_data(pose), se2_from_data(previous_pose)));
+  }
+  for (int k = 0; k < 3; ++k) out10[k] = m.mean[k], out10[3 + k] = m.stddev[k];
+  out10[6] = m.first_rotation.c, out10[7] = m.first_rotation.s, out10[8] = m.model, out10[9] = 0.0;
+}
+
+/// Propagate n states with a generic sampling block (layout of orc_motion_sampling); mode 0 std, 1 counter.
+void orc_motion_propagate(const double* sampling10, int mode, std::uint64_t seed, std::uint32_t step, std::uint64_t first_index, double* states, std::uint64_t n) {
+  MotionSampling m;
+  for (int k = 0; k < 3; ++k) m.mean[k] = sampling10[k], m.stddev[k] = sampling10[3 + k];
+  m.first_rotation = SO2::raw(sampling10[6], sampling10[7]);
+  m.model = static_cast<int>(sampling10[8]);
+  std::vector<SE2> v(n);
+  for (std::uint64_t i = 0; i < n; ++i) v[i] = se2_from_data(states + 4 * i);
+  if (mode == 0) {
+    std::mt19937_64 gen(seed);
+    std::normal_distribution<double> dist;
+    motion_propagate_std(v, m, dist, gen);
+  } else {
+    for (std::uint64_t i = 0; i < n; ++i) v[i] = motion_sample_counter(v[i], m, seed, first_index + i, step);
+  }
+  for (std::uint64_t i = 0; i < n; ++i) states[4 * i] = v[i].r.c, states[4 * i + 1] = v[i].r.s, states[4 * i + 2] = v[i].x, states[4 * i + 3] = v[i].y;
+}
+
 double orc_normalize(double* weights, std::uint64_t n) {
   std::vector<double> w(weights, weights + n);
   const double f = normalize(w);
@@ -278,7 +316,14 @@ struct orc_amcl {
   Amcl impl;
 };
 
+orc_amcl* orc_amcl_create_motion(const orc_amcl_param* p, int motion_model, const orc_omni_param* m);
+
 orc_amcl* orc_amcl_create(const orc_amcl_param* p, const orc_motion_param* m) {
+  const orc_omni_param o{m->alpha1, m->alpha2, m->alpha3, m->alpha4, 0.0, m->distance_threshold};
+  return orc_amcl_create_motion(p, 0, &o);
+}
+
+orc_amcl* orc_amcl_create_motion(const orc_amcl_param* p, int motion_model, const orc_omni_param* m) {
   AmclParams a;
   a.update_min_d = p->update_min_d;
   a.update_min_a = p->update_min_a;
@@ -297,7 +342,8 @@ orc_amcl* orc_amcl_create(const orc_amcl_param* p, const orc_motion_param* m) {
   a.scheme = static_cast<ResampleScheme>(p->scheme);
   a.seed = p->seed;
   a.threads = p->threads;
-  return new (std::nothrow) orc_amcl{Amcl{a, to_motion(m)}};
+  return new (std::nothrow) orc_amcl{Amcl{a, DifferentialDriveParam{m->alpha1, m->alpha2, m->alpha3, m->alpha4, m->distance_threshold}, motion_model,
+                                          OmnidirectionalDriveParam{m->alpha1, m->alpha2, m->alpha3, m->alpha4, m->alpha5, m->distance_threshold}}};
 }
 void orc_amcl_destroy(orc_amcl* a) { delete a; }
 

@@ -62,6 +62,19 @@ class MotionParam(C.Structure):
         super().__init__(alpha1, alpha2, alpha3, alpha4, distance_threshold)
 
 
+class OmniParam(C.Structure):
+    """oracle::OmnidirectionalDriveParam (reference: motion/omnidirectional_drive_model.hpp:36-68); also carries
+    the differential-drive alphas (alpha5 unused) and nothing for the stationary model."""
+
+    _fields_ = [(n, C.c_double) for n in ("alpha1", "alpha2", "alpha3", "alpha4", "alpha5", "distance_threshold")]
+
+    def __init__(self, alpha1=0.0, alpha2=0.0, alpha3=0.0, alpha4=0.0, alpha5=0.0, distance_threshold=0.01):
+        super().__init__(alpha1, alpha2, alpha3, alpha4, alpha5, distance_threshold)
+
+
+DIFFERENTIAL, OMNIDIRECTIONAL, STATIONARY = 0, 1, 2
+
+
 class AmclParam(C.Structure):
     """oracle::AmclParams (reference: algorithm/amcl_core.hpp:34-55 + backend knobs)."""
 
@@ -123,6 +136,7 @@ def lib() -> C.CDLL:
         _lib.orc_kld_take_count.restype = C.c_uint64
         _lib.orc_bresenham.restype = C.c_uint64
         _lib.orc_amcl_create.restype = C.c_void_p
+        _lib.orc_amcl_create_motion.restype = C.c_void_p
         _lib.orc_amcl_size.restype = C.c_uint64
         _lib.orc_amcl_last_indices.restype = C.c_uint64
     return _lib
@@ -250,6 +264,20 @@ def diff_drive_propagate(sampling6, states, mode: int, seed: int, step: int = 1,
     return st
 
 
+def motion_sampling(model: int, param: OmniParam, pose, previous_pose) -> np.ndarray:
+    """{mean[3], stddev[3], first_rotation cos, sin, model, 0} of any motion model."""
+    out = np.zeros(10)
+    lib().orc_motion_sampling(C.c_int(model), C.byref(param), _p(_f64(pose), C.c_double), _p(_f64(previous_pose), C.c_double), _p(out, C.c_double))
+    return out
+
+
+def motion_propagate(sampling10, states, mode: int, seed: int, step: int = 1, first_index: int = 0) -> np.ndarray:
+    st = _f64(states).reshape(-1, 4).copy()
+    lib().orc_motion_propagate(_p(_f64(sampling10), C.c_double), C.c_int(mode), C.c_uint64(seed), C.c_uint32(step), C.c_uint64(first_index),
+                               _p(st, C.c_double), C.c_uint64(len(st)))
+    return st
+
+
 def normalize(weights):
     w = _f64(weights).copy()
     f = lib().orc_normalize(_p(w, C.c_double), C.c_uint64(len(w)))
@@ -326,8 +354,10 @@ def resample_indices_std(weights, seed: int, m: int) -> np.ndarray:
 class Amcl:
     """oracle::Amcl -- the CPU restatement of beluga::Amcl (algorithm/amcl_core.hpp:81-233)."""
 
-    def __init__(self, param: AmclParam, motion: MotionParam):
-        self._h = C.c_void_p(lib().orc_amcl_create(C.byref(param), C.byref(motion)))
+    def __init__(self, param: AmclParam, motion, motion_model: int = DIFFERENTIAL):
+        if isinstance(motion, MotionParam):
+            motion = OmniParam(motion.alpha1, motion.alpha2, motion.alpha3, motion.alpha4, 0.0, motion.distance_threshold)
+        self._h = C.c_void_p(lib().orc_amcl_create_motion(C.byref(param), C.c_int(motion_model), C.byref(motion)))
         self._grid = None
 
     def __del__(self):

@@ -113,6 +113,18 @@ void TestRandomParticlesInserting() {
     ASSERT_TRUE(n >= 2 && n <= 100);
   }
 }
+void OtherMotionModelsCanBeUsed() {  // beluga_ros::Amcl::motion_model_variant (beluga_ros/amcl.hpp:108-111)
+  constexpr bool F = false;
+  const auto map = Grid{{F, F, F, F, F, F, F, F, F, F, F, F, F, F, F, F, F, F, F, F, F, F, F, F, F}, 0.5};
+  beluga_b200::Amcl omni{beluga_b200::OmnidirectionalDriveModel{beluga_b200::OmnidirectionalDriveModelParam{0.1, 0.1, 0.1, 0.1, 0.1}},
+                         beluga_b200::LikelihoodFieldModel<Grid>{beluga_b200::LikelihoodFieldModelParam{}, map}, beluga_b200::AmclParams{}};
+  omni.initialize(beluga_b200::SE2d{}, kIdentityCov);
+  ASSERT_TRUE(omni.update(beluga_b200::SE2d{0.1, 0.5, 0.2}, kDummyMeasurement).has_value());
+  beluga_b200::Amcl still{beluga_b200::StationaryModel{}, beluga_b200::LikelihoodFieldModel<Grid>{beluga_b200::LikelihoodFieldModelParam{}, map},
+                          beluga_b200::AmclParams{}};
+  still.initialize(beluga_b200::SE2d{}, kIdentityCov);
+  ASSERT_TRUE(still.update(kDummyControl, kDummyMeasurement).has_value());
+}
 void InvalidCovarianceThrows() {  // multivariate_normal_distribution.hpp:114-116
   auto amcl = make_amcl();
   bool thrown = false;
@@ -134,6 +146,7 @@ int main() {
   LikelihoodFieldModelCanBeUsed();
   SelectiveResampleCanBeConstructed();
   TestRandomParticlesInserting();
+  OtherMotionModelsCanBeUsed();
   InvalidCovarianceThrows();
   if (g_failures == 0) std::printf("CPP_ADAPTORS_OK\n");
   return g_failures == 0 ? 0 : 1;

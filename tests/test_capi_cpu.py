@@ -76,3 +76,18 @@ def test_diff_drive_sampling_matches_oracle(lib, orc, pose, prev):
     got = np.array([out.rot1_mean, out.rot1_std, out.trans_mean, out.trans_std, out.rot2_mean, out.rot2_std])
     exp = orc.diff_drive_sampling(orc.MotionParam(*alphas), a, b)
     assert np.array_equal(got, exp)  # same libm, same operation order: bit-identical
+
+
+@pytest.mark.parametrize("model", [0, 1, 2])
+@pytest.mark.parametrize("pose,prev", [((1.0, 0.5, 0.3), (0.0, 0.0, 0.0)), ((0.001, 0.002, 1.4), (0.0, 0.0, 1.0)), ((-2.0, 3.0, -2.5), (-1.5, 2.0, 3.0))])
+def test_motion_sampling_matches_oracle(lib, orc, model, pose, prev):
+    """Host part of the three motion models (differential / omnidirectional / stationary)."""
+    import beluga_b200 as bb
+
+    alphas = (0.1, 0.05, 0.1, 0.05, 0.02)
+    motion = [bb.DifferentialDriveModelParam(*alphas[:4]), bb.OmnidirectionalDriveModelParam(*alphas), bb.StationaryModelParam()][model]
+    a, b = orc.se2(*pose), orc.se2(*prev)
+    got = bb.motion_sampling(motion, a, b)
+    exp = orc.motion_sampling(model, orc.OmniParam(*alphas), a, b)
+    assert got.model == model
+    assert np.array_equal(np.array(list(got.mean) + list(got.stddev) + list(got.first_rotation)), exp[:8])

@@ -188,6 +188,38 @@ def test_propagate_matches_oracle(bb, orc):
     assert np.abs(np.hypot(got[:, 0], got[:, 1]) - 1.0).max() < 1e-15
 
 
+@pytest.mark.parametrize("model", [1, 2])
+def test_propagate_other_motion_models(bb, orc, model):
+    """OmnidirectionalDriveModel / StationaryModel (motion/omnidirectional_drive_model.hpp:131-145, stationary_model.hpp:54-59)."""
+    rng = np.random.default_rng(12)
+    states = random_states(orc, rng, 3000, 10.0)
+    alphas = (0.1, 0.05, 0.1, 0.05, 0.02)
+    motion = bb.OmnidirectionalDriveModelParam(*alphas) if model == 1 else bb.StationaryModelParam()
+    pose, prev = orc.se2(1.3, 0.4, 0.3), orc.se2(1.0, 0.2, 0.1)
+    f = bb.Filter(capacity=len(states), seed=99, first_index=500)
+    f.set_particles(states)
+    f.propagate(bb.motion_sampling(motion, pose, prev), step=4)
+    exp = orc.motion_propagate(orc.motion_sampling(model, orc.OmniParam(*alphas), pose, prev), states, mode=1, seed=99, step=4, first_index=500)
+    assert np.allclose(f.particles()[0], exp, rtol=0.0, atol=1e-12)
+
+
+def test_trajectory_omnidirectional(bb, orc, scene):
+    n = 6000
+    alphas = (0.1, 0.05, 0.1, 0.05, 0.02)
+    lfm = dict(max_obstacle_distance=2.0, max_laser_distance=100.0, z_hit=0.5, z_random=0.5, sigma_hit=0.2)
+    g = bb.Amcl(bb.OmnidirectionalDriveModelParam(*alphas), bb.AmclParams(min_particles=n, max_particles=n, resample_scheme=1, seed=8, record_ancestors=True))
+    o = orc.Amcl(orc.AmclParam(min_particles=n, max_particles=n, scheme=1, seed=8, rng_mode=1), orc.OmniParam(*alphas), motion_model=orc.OMNIDIRECTIONAL)
+    g.update_map(0, bb.LikelihoodFieldModelParam(**lfm), bb.OccupancyGrid(scene.cells, scene.resolution))
+    o.set_map(0, orc.LfmParam(**lfm), orc.Grid(scene.cells, scene.resolution))
+    g.initialize(scene.initial_mean, scene.initial_cov)
+    o.initialize_normal(scene.initial_mean, scene.initial_cov)
+    for k in range(8):
+        pose = orc.se2(*scene.poses[k])
+        rg, ro = g.update(pose, scene.scans[k]), o.update(pose, scene.scans[k])
+        assert np.array_equal(g.filter.ancestors(), o.last_indices())
+        assert np.abs(np.array(rg.estimate.mean) - np.array(ro.mean)).max() < 1e-10
+
+
 def test_initialize_normal_matches_oracle(bb, orc):
     mean = np.array([3.0, -2.0, 0.7])
     cov = np.array([[0.25, 0.05, 0.0], [0.05, 0.16, 0.01], [0.0, 0.01, 0.0685]])

@@ -425,3 +425,54 @@ def test_resample_zero_weights_never_selected(orc):
     for scheme in (0, 1):
         idx, _, _ = orc.resample_indices(weights, scheme, seed=1, step=3, m=10000)
         assert set(np.unique(idx).tolist()) == {1, 3}
+
+
+# ---- motion/test_omnidirectional_drive_model.cpp ------------------------------------------------
+def _omni_zero_noise(orc, control, previous, state, mode):
+    s = orc.motion_sampling(orc.OMNIDIRECTIONAL, orc.OmniParam(0.0, 0.0, 0.0, 0.0, 0.0), control, previous)
+    return orc.motion_propagate(s, [state], mode, seed=5)[0]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_omni_zero_noise(orc, mode):  # :53-100
+    se2 = orc.se2
+    near = lambda a, b: np.abs(np.asarray(a) - np.asarray(b)).max() <= 0.001  # noqa: E731
+    pose = se2(2.0, 5.0, PI / 3)
+    assert near(_omni_zero_noise(orc, se2(1.0, -2.0, PI), se2(1.0, -2.0, PI), pose, mode), pose)  # OneUpdate
+    ctl = (se2(1.0, 0.0, 0.0), se2(0.0, 0.0, 0.0))  # Translate
+    assert near(_omni_zero_noise(orc, *ctl, se2(2.0, 0.0, 0.0), mode), se2(3.0, 0.0, 0.0))
+    assert near(_omni_zero_noise(orc, *ctl, se2(0.0, 3.0, 0.0), mode), se2(1.0, 3.0, 0.0))
+    ctl = (se2(0.0, 1.0, PI / 2), se2(0.0, 0.0, 0.0))  # RotateTranslate
+    assert near(_omni_zero_noise(orc, *ctl, se2(0.0, 0.0, 0.0), mode), se2(0.0, 1.0, PI / 2))
+    assert near(_omni_zero_noise(orc, *ctl, se2(2.0, 3.0, -PI / 2), mode), se2(3.0, 3.0, 0.0))
+    ctl = (se2(0.0, 0.0, PI / 4), se2(0.0, 0.0, 0.0))  # Rotate
+    assert near(_omni_zero_noise(orc, *ctl, se2(0.0, 0.0, PI), mode), se2(0.0, 0.0, PI * 5 / 4))
+    assert near(_omni_zero_noise(orc, *ctl, se2(0.0, 0.0, -PI / 2), mode), se2(0.0, 0.0, -PI / 4))
+    ctl = (se2(0.0, 1.0, 0.0), se2(0.0, 0.0, 0.0))  # TranslateStrafe
+    assert near(_omni_zero_noise(orc, *ctl, se2(0.0, 0.0, 0.0), mode), se2(0.0, 1.0, 0.0))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_omni_sample_statistics(orc, mode):  # :116-178
+    n, alpha = 100_000, 0.2
+    s = orc.motion_sampling(orc.OMNIDIRECTIONAL, orc.OmniParam(0.0, 0.0, alpha, 0.0, 0.0), orc.se2(3.0, 0.0, 0.0), orc.se2(0.0, 0.0, 0.0))
+    out = orc.motion_propagate(s, np.tile(orc.se2(5.0, 0.0, 0.0), (n, 1)), mode, seed=3)
+    assert out[:, 2].mean() == pytest.approx(8.0, abs=0.015)
+    assert out[:, 2].std() == pytest.approx(math.sqrt(alpha * 9.0), abs=0.015)
+    motion_angle, initial_angle = PI / 4, PI / 6
+    s = orc.motion_sampling(orc.OMNIDIRECTIONAL, orc.OmniParam(alpha, 0.0, 0.0, 0.0, 0.0), orc.se2(0.0, 0.0, motion_angle), orc.se2(0.0, 0.0, 0.0))
+    out = orc.motion_propagate(s, np.tile(orc.se2(0.0, 0.0, initial_angle), (n, 1)), mode, seed=4)
+    ang = np.arctan2(out[:, 1], out[:, 0])
+    assert ang.mean() == pytest.approx(initial_angle + motion_angle, abs=0.01)
+    assert ang.std() == pytest.approx(math.sqrt(alpha * motion_angle**2), abs=0.01)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_stationary_model(orc, mode):  # motion/stationary_model.hpp:52-60: N(0, 0.02) jitter on theta, x, y
+    n = 100_000
+    s = orc.motion_sampling(orc.STATIONARY, orc.OmniParam(), orc.se2(9.0, 9.0, 1.0), orc.se2(0.0, 0.0, 0.0))  # control is ignored
+    out = orc.motion_propagate(s, np.tile(orc.se2(1.0, -2.0, 0.5), (n, 1)), mode, seed=6)
+    ang = np.arctan2(out[:, 1], out[:, 0])
+    assert ang.mean() == pytest.approx(0.5, abs=5e-4) and ang.std() == pytest.approx(0.02, abs=5e-4)
+    assert out[:, 2].mean() == pytest.approx(1.0, abs=5e-4) and out[:, 2].std() == pytest.approx(0.02, abs=5e-4)
+    assert out[:, 3].mean() == pytest.approx(-2.0, abs=5e-4) and out[:, 3].std() == pytest.approx(0.02, abs=5e-4)
