@@ -31,7 +31,7 @@ from ._capi import (RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC, SENSOR_BEAM, SENS
 
 __all__ = [
     "Amcl", "AmclParams", "BeamModelParam", "DifferentialDriveModelParam", "OmnidirectionalDriveModelParam", "StationaryModelParam",
-    "Filter", "LikelihoodFieldModelParam", "motion_sampling",
+    "Filter", "LikelihoodFieldModelParam", "motion_sampling", "scan_to_points", "take_evenly_indices",
     "OccupancyGrid", "BelugaB200Error", "device_count", "se2",
     "RESAMPLE_MULTINOMIAL", "RESAMPLE_SYSTEMATIC", "SENSOR_BEAM", "SENSOR_LIKELIHOOD_FIELD", "SENSOR_LIKELIHOOD_FIELD_PROB",
 ]
@@ -71,6 +71,37 @@ def estimate_from_moments(moments, pivot):
     if st != _capi.OK:
         raise BelugaB200Error(st, "bb200_estimate_from_moments")
     return np.array(e.mean), np.array(e.cov).reshape(3, 3)
+
+
+def take_evenly_indices(size: int, count: int) -> np.ndarray:
+    """beluga::views::take_evenly (views/take_evenly.hpp): indices kept out of `size` elements."""
+    out = np.zeros(max(size, 1), dtype=np.uint64)
+    n = C.c_uint64()
+    st = _capi.load().bb200_take_evenly_indices(size, count, out.ctypes.data_as(C.POINTER(C.c_uint64)), len(out), C.byref(n))
+    if st != _capi.OK:
+        raise BelugaB200Error(st, "bb200_take_evenly_indices")
+    return out[: n.value].astype(np.int64)
+
+
+def _laser_scan(ranges, angle_min, angle_increment, min_range, max_range, max_beams, laser_origin):
+    r = np.ascontiguousarray(ranges, dtype=np.float32)
+    origin = None if laser_origin is None else _f64(laser_origin).reshape(12)
+    scan = _capi.LaserScan(r.ctypes.data_as(C.POINTER(C.c_float)), len(r), angle_min, angle_increment, min_range, max_range, max_beams,
+                           None if origin is None else origin.ctypes.data_as(C.POINTER(C.c_double)))
+    return scan, (r, origin)  # keep the arrays alive
+
+
+def scan_to_points(ranges, angle_min: float, angle_increment: float, min_range: float = 0.0, max_range: float = float("inf"),
+                   max_beams: int = 0, laser_origin=None) -> np.ndarray:
+    """beluga_ros::LaserScan + BaseLaserScan::points_in_cartesian_coordinates + laser-to-base transform
+    (beluga_ros/laser_scan.hpp:69-80, beluga/sensor/data/laser_scan.hpp:64-91, beluga_ros/src/amcl.cpp:57-62)."""
+    scan, keep = _laser_scan(ranges, angle_min, angle_increment, min_range, max_range, max_beams, laser_origin)
+    out = np.zeros((len(keep[0]) + 1, 2))
+    n = C.c_uint64()
+    st = _capi.load().bb200_scan_to_points(C.byref(scan), _dptr(out), len(out), C.byref(n))
+    if st != _capi.OK:
+        raise BelugaB200Error(st, "bb200_scan_to_points")
+    return out[: n.value]
 
 
 def _dptr(a: np.ndarray):
@@ -451,6 +482,14 @@ class Amcl:
 
     def particles(self):
         return self.filter.particles()
+
+    def update_scan(self, control_pose, ranges, angle_min: float, angle_increment: float, min_range: float = 0.0,
+                    max_range: float = float("inf"), max_beams: int = 0, laser_origin=None) -> _capi.UpdateResult:
+        """Amcl::update(base_pose_in_odom, laser_scan) (beluga_ros/src/amcl.cpp:54-64)."""
+        scan, keep = _laser_scan(ranges, angle_min, angle_increment, min_range, max_range, max_beams, laser_origin)
+        res = _capi.UpdateResult()
+        self._check(self._lib.bb200_amcl_update_scan(self._h, _dptr(_f64(control_pose)), C.byref(scan), C.byref(res)))
+        return res
 
     def plan_update(self, control_pose) -> _capi.StepPlan:
         """Host half of Amcl::update (policies, control window, recovery estimator)."""

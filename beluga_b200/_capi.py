@@ -84,6 +84,11 @@ class StepPlan(C.Structure):
                 ("random_state_probability", C.c_double), ("sampling", MotionSampling), ("opts", ResampleOpts)]
 
 
+class LaserScan(C.Structure):
+    _fields_ = [("ranges", C.POINTER(C.c_float)), ("n_ranges", C.c_uint64), ("angle_min", C.c_float), ("angle_increment", C.c_float),
+                ("min_range", C.c_double), ("max_range", C.c_double), ("max_beams", C.c_uint64), ("laser_origin", C.POINTER(C.c_double))]
+
+
 class UpdateResult(C.Structure):
     _fields_ = [("updated", C.c_int), ("resampled", C.c_int), ("n_particles", C.c_uint64), ("estimate", Estimate),
                 ("random_state_probability", C.c_double), ("weight_sum", C.c_double)]
@@ -144,6 +149,9 @@ SIGNATURES = {
     "bb200_amcl_initialize_states": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64]),
     "bb200_amcl_force_update": (None, [_vp]),
     "bb200_amcl_update": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64, _P(UpdateResult)]),
+    "bb200_scan_to_points": (C.c_int, [_P(LaserScan), _dbl, C.c_uint64, _P(C.c_uint64)]),
+    "bb200_take_evenly_indices": (C.c_int, [C.c_uint64, C.c_uint64, _P(C.c_uint64), C.c_uint64, _P(C.c_uint64)]),
+    "bb200_amcl_update_scan": (C.c_int, [_vp, _dbl, _P(LaserScan), _P(UpdateResult)]),
     "bb200_amcl_plan_update": (C.c_int, [_vp, _dbl, _P(StepPlan)]),
     "bb200_amcl_commit_update": (None, [_vp, C.c_int, C.c_double]),
     "bb200_amcl_create_with_motion": (C.c_int, [_P(AmclParam), _P(MotionParam), _P(_vp)]),

@@ -1,6 +1,8 @@
 // extern "C" surface of libbeluga_b200.so (declared in include/beluga_b200.h).
+#include <cmath>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/beluga_b200.h"
 #include "amcl.hpp"
@@ -288,6 +290,68 @@ int bb200_amcl_update(bb200_amcl* a, const double control_pose[4], const double*
   static const double kNoPoints[2] = {0.0, 0.0};
   return a->impl.update(control_pose, points_xy != nullptr ? points_xy : kNoPoints, n_points, out);
 }
+int bb200_take_evenly_indices(uint64_t size, uint64_t count, uint64_t* indices, uint64_t capacity, uint64_t* n_indices) {
+  BB_REQUIRE(indices && n_indices);
+  // take_evenly_view::size() and compute_offset() (views/take_evenly.hpp:47-57,118-145)
+  uint64_t kept = size == 0 ? 0 : (count > size ? size : count);
+  if (kept > capacity) return BB200_ERR_CAPACITY;
+  for (uint64_t pos = 0; pos < kept; ++pos) {
+    uint64_t idx;
+    if (count > size) {
+      idx = pos;
+    } else if (pos == 0) {
+      idx = 0;
+    } else {  // count >= 2 here: pos < kept <= count
+      const uint64_t a = pos * (size - 1), b = count - 1;
+      idx = a / b + ((a % b == 0) ? 0 : 1);
+    }
+    indices[pos] = idx;
+  }
+  *n_indices = kept;
+  return BB200_OK;
+}
+
+int bb200_scan_to_points(const bb200_laser_scan* scan, double* points_xy, uint64_t capacity, uint64_t* n_points) {
+  BB_REQUIRE(scan && points_xy && n_points && (scan->ranges || scan->n_ranges == 0));
+  const uint64_t size = scan->n_ranges;
+  const uint64_t count = scan->max_beams == 0 ? size : scan->max_beams;
+  const uint64_t kept = size == 0 ? 0 : (count > size ? size : count);
+  uint64_t n = 0;
+  for (uint64_t pos = 0; pos < kept; ++pos) {
+    uint64_t i = pos;
+    if (count <= size && pos != 0) {
+      const uint64_t a = pos * (size - 1), b = count - 1;
+      i = a / b + ((a % b == 0) ? 0 : 1);
+    }
+    const double range = static_cast<double>(scan->ranges[i]);
+    // beluga_ros/laser_scan.hpp:73-74: float arithmetic, then widened.
+    const double theta = static_cast<double>(scan->angle_min + static_cast<float>(static_cast<int>(i)) * scan->angle_increment);
+    if (std::isnan(range) || !(range >= scan->min_range) || !(range <= scan->max_range)) continue;  // laser_scan.hpp:80-84
+    const double x = range * std::cos(theta), y = range * std::sin(theta);                           // laser_scan.hpp:66-69
+    double px = x, py = y;
+    if (scan->laser_origin != nullptr) {  // origin * (x, y, 0), keep (x, y)  (beluga_ros/src/amcl.cpp:59-61)
+      const double* m = scan->laser_origin;
+      px = m[0] * x + m[1] * y + m[3];
+      py = m[4] * x + m[5] * y + m[7];
+    }
+    if (n >= capacity) return BB200_ERR_CAPACITY;
+    points_xy[2 * n] = px;
+    points_xy[2 * n + 1] = py;
+    ++n;
+  }
+  *n_points = n;
+  return BB200_OK;
+}
+
+int bb200_amcl_update_scan(bb200_amcl* a, const double control_pose[4], const bb200_laser_scan* scan, bb200_update_result* out) {
+  BB_REQUIRE(a && control_pose && scan && out);
+  std::vector<double> points(2 * (scan->n_ranges + 1));
+  uint64_t n = 0;
+  const int st = bb200_scan_to_points(scan, points.data(), scan->n_ranges + 1, &n);
+  if (st != BB200_OK) return st;
+  return bb200_amcl_update(a, control_pose, points.data(), n, out);
+}
+
 int bb200_amcl_plan_update(bb200_amcl* a, const double control_pose[4], bb200_step_plan* plan) {
   BB_REQUIRE(a && control_pose && plan);
   return a->impl.plan_update(control_pose, plan);

@@ -339,6 +339,28 @@ void bb200_amcl_force_update(bb200_amcl* a);
 /* Amcl::update(control_action, measurement) -- amcl_core.hpp:165-201.  `points_xy` is the
  * measurement_type std::vector<std::pair<double,double>> flattened (x0, y0, x1, y1, ...). */
 int bb200_amcl_update(bb200_amcl* a, const double control_pose[4], const double* points_xy, uint64_t n_points, bb200_update_result* out);
+/* Scan preprocessing in front of the path: what beluga_ros does between the sensor message
+ * and Amcl::update -- beluga_ros::LaserScan (beluga_ros/include/beluga_ros/laser_scan.hpp:69-80:
+ * take_evenly(max_beams) over ranges and angles, angle = float(angle_min + float(i) * angle_increment)),
+ * BaseLaserScan::points_in_polar/cartesian_coordinates (beluga/sensor/data/laser_scan.hpp:64-91: drop
+ * NaN and out-of-[min_range, max_range] readings, x = r cos a, y = r sin a) and the laser-to-base
+ * transform of beluga_ros/src/amcl.cpp:57-62.  `laser_origin` is the 3x4 row-major [R | t] of the
+ * laser frame in the base frame (NULL: identity); only x and y of the transformed point are kept. */
+typedef struct bb200_laser_scan {
+  const float* ranges;
+  uint64_t n_ranges;
+  float angle_min, angle_increment;
+  double min_range, max_range; /* already combined with the message's range_min / range_max */
+  uint64_t max_beams;          /* take_evenly count; 0 or >= n_ranges keeps every reading */
+  const double* laser_origin;  /* 12 doubles or NULL */
+} bb200_laser_scan;
+/* Writes at most `capacity` points (x, y pairs) and their count. */
+int bb200_scan_to_points(const bb200_laser_scan* scan, double* points_xy, uint64_t capacity, uint64_t* n_points);
+/* take_evenly (beluga/views/take_evenly.hpp:118-145): the indices kept out of `size` elements. */
+int bb200_take_evenly_indices(uint64_t size, uint64_t count, uint64_t* indices, uint64_t capacity, uint64_t* n_indices);
+/* Amcl::update(base_pose_in_odom, laser_scan) -- beluga_ros/src/amcl.cpp:54-64. */
+int bb200_amcl_update_scan(bb200_amcl* a, const double control_pose[4], const bb200_laser_scan* scan, bb200_update_result* out);
+
 /* The two host halves of bb200_amcl_update for callers that drive the filter themselves. */
 int bb200_amcl_plan_update(bb200_amcl* a, const double control_pose[4], bb200_step_plan* plan);
 void bb200_amcl_commit_update(bb200_amcl* a, int resampled, double random_state_probability);

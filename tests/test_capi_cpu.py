@@ -91,3 +91,32 @@ def test_motion_sampling_matches_oracle(lib, orc, model, pose, prev):
     exp = orc.motion_sampling(model, orc.OmniParam(*alphas), a, b)
     assert got.model == model
     assert np.array_equal(np.array(list(got.mean) + list(got.stddev) + list(got.first_rotation)), exp[:8])
+
+
+@pytest.mark.parametrize(
+    "size,count,expected",
+    [(0, 0, []), (0, 1, []), (4, 0, []), (4, 1, [0]), (4, 10, [0, 1, 2, 3]), (4, 2, [0, 3]), (5, 3, [0, 2, 4]), (6, 3, [0, 3, 5]),
+     (9, 3, [0, 4, 8]), (4, 3, [0, 2, 3]), (10, 6, [0, 2, 4, 6, 8, 9])],
+)
+def test_take_evenly_known_answers(lib, size, count, expected):
+    """views/test_take_evenly.cpp:72-147 (inputs there are 1..size, so expected values are index + 1)."""
+    import beluga_b200 as bb
+
+    assert bb.take_evenly_indices(size, count).tolist() == expected
+
+
+def test_scan_to_points(lib):
+    """beluga_ros/test/test_laser_scan.cpp idea: range filter, NaN drop, beam subsampling, laser origin."""
+    import beluga_b200 as bb
+
+    ranges = np.array([0.05, 1.0, np.nan, 2.0, 50.0, 3.0, 4.0], dtype=np.float32)
+    pts = bb.scan_to_points(ranges, angle_min=-0.5, angle_increment=0.25, min_range=0.1, max_range=10.0)
+    keep = [1, 3, 5, 6]
+    ang = (np.float32(-0.5) + np.arange(7, dtype=np.float32) * np.float32(0.25)).astype(np.float64)[keep]
+    r = ranges[keep].astype(np.float64)
+    assert np.array_equal(pts, np.stack([r * np.cos(ang), r * np.sin(ang)], axis=1))
+    sub = bb.scan_to_points(ranges, -0.5, 0.25, 0.1, 10.0, max_beams=3)  # take_evenly(3) of 7 -> indices 0, 3, 6; index 0 is below min_range
+    assert len(sub) == 2 and np.allclose(sub[0], [2.0 * np.cos(0.25), 2.0 * np.sin(0.25)])
+    origin = np.array([[0.0, -1.0, 0.0, 0.3], [1.0, 0.0, 0.0, -0.2], [0.0, 0.0, 1.0, 0.5]])  # yaw 90 deg, offset
+    moved = bb.scan_to_points(ranges, -0.5, 0.25, 0.1, 10.0, laser_origin=origin)
+    assert np.allclose(moved, np.stack([-pts[:, 1] + 0.3, pts[:, 0] - 0.2], axis=1))

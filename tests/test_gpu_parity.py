@@ -460,6 +460,23 @@ def test_update_policy_and_force_update(bb, orc, scene):
     assert g.update(orc.se2(*scene.poses[1]), scene.scans[1]).updated == 1  # moved 0.4 m > update_min_d
 
 
+def test_update_scan_equals_update_with_points(bb, orc, scene):
+    """Amcl::update(pose, laser_scan) (beluga_ros/src/amcl.cpp:54-64) == update(pose, converted points)."""
+    n = 2000
+    mk = lambda: bb.Amcl(bb.DifferentialDriveModelParam(0.1, 0.05, 0.1, 0.05), bb.AmclParams(min_particles=n, max_particles=n, seed=4))  # noqa: E731
+    a, b = mk(), mk()
+    for f in (a, b):
+        f.update_map(0, bb.LikelihoodFieldModelParam(max_laser_distance=100.0), bb.OccupancyGrid(scene.cells, scene.resolution))
+        f.initialize(scene.initial_mean, scene.initial_cov)
+    ranges = np.hypot(scene.scans[0][:, 0], scene.scans[0][:, 1]).astype(np.float32)
+    args = dict(angle_min=-PI, angle_increment=2 * PI / len(ranges), min_range=0.1, max_range=25.0, max_beams=60)
+    ra = a.update_scan(bb.se2(*scene.poses[0]), ranges, **args)
+    rb = b.update(bb.se2(*scene.poses[0]), bb.scan_to_points(ranges, **args))
+    assert ra.updated == rb.updated == 1
+    assert np.array_equal(np.array(ra.estimate.mean), np.array(rb.estimate.mean))
+    assert np.array_equal(a.particles()[0], b.particles()[0])
+
+
 def test_large_scale_properties(bb):
     """BASELINE config 2 shapes (1M particles x 1080 beams) through size-independent properties:
     weights reset to 1, ancestors sorted for the systematic comb, states stay unit-norm, and the
