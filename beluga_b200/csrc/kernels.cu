@@ -57,6 +57,34 @@ __device__ __forceinline__ double block_sum(double v, double* scratch /* kThread
   return total;  // valid in thread 0
 }
 
+/// Fixed-order block sums of K values at once: warp tree per value, one shared-memory round for all
+/// of them, then thread 0 adds the per-warp partials in warp order.  Two barriers instead of 2K.
+template <int kThreads, int K>
+__device__ __forceinline__ void block_sum_many(double* v /* K values, in/out: totals valid in thread 0 */, double* scratch /* K * kThreads/32 */) {
+  constexpr int kWarps = kThreads / kWarp;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int off = kWarp / 2; off > 0; off >>= 1) v[k] = v[k] + __shfl_down_sync(0xffffffffu, v[k], off);
+  }
+  const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) scratch[k * kWarps + warp] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double total = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) total = total + scratch[k * kWarps + w];
+      v[k] = total;
+    }
+  }
+}
+
 template <int kThreads>
 __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* scratch) {
 #pragma unroll
@@ -174,7 +202,7 @@ __device__ __forceinline__ Pose2 propagate_one(const Pose2& st, const MotionSamp
 
 __global__ void __launch_bounds__(kPrThreads) propagate_kernel(Pose2* __restrict__ states, uint64_t n, int do_propagate, MotionSampling sampling,
                                                                uint64_t seed, uint32_t step, uint64_t first_index, Schedule* __restrict__ sched) {
-  __shared__ double s_red[kPrThreads / kWarp];
+  __shared__ double s_red[6 * kPrThreads / kWarp];
   const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kPrThreads + threadIdx.x;
   double m[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (i < n) {
@@ -186,10 +214,10 @@ __global__ void __launch_bounds__(kPrThreads) propagate_kernel(Pose2* __restrict
     m[0] = st.c, m[1] = st.s, m[2] = st.x, m[3] = st.y, m[4] = st.x * st.x, m[5] = st.y * st.y;
   }
   if (sched != nullptr) {
+    block_sum_many<kPrThreads, 6>(m, s_red);
+    if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const double total = block_sum<kPrThreads>(m[k], s_red);
-      if (threadIdx.x == 0) atomicAdd(&sched->sums[k], total);
+      for (int k = 0; k < 6; ++k) atomicAdd(&sched->sums[k], m[k]);
     }
   }
 }
@@ -202,7 +230,7 @@ __global__ void __launch_bounds__(kPrThreads) propagate_kernel(Pose2* __restrict
 // of a counting sort over a 3-D grid of pose bins.  This only permutes WHICH THREAD handles a
 // particle: weights are written back to the particle's own slot, so every result is independent of it.
 
-constexpr uint32_t kMaxBins = 1u << 20;
+constexpr uint32_t kMaxBins = 1u << 18;  // 16 particles per bin up to 4M particles per shard
 
 __global__ void schedule_reset_kernel(Schedule* sched) {
   for (int k = 0; k < 6; ++k) sched->sums[k] = 0.0;
@@ -840,16 +868,16 @@ __device__ __forceinline__ void accumulate_moments(double* m, const Pose2& st, d
 }
 
 template <int kThreads>
-__device__ __forceinline__ void store_block_moments(double* m, double* scratch, double* __restrict__ partials_row) {
+__device__ __forceinline__ void store_block_moments(double* m, double* scratch /* kMomentCount * kThreads/32 */, double* __restrict__ partials_row) {
+  block_sum_many<kThreads, kMomentCount>(m, scratch);
+  if (threadIdx.x == 0) {
 #pragma unroll
-  for (int k = 0; k < kMomentCount; ++k) {
-    const double total = block_sum<kThreads>(m[k], scratch);
-    if (threadIdx.x == 0) partials_row[k] = total;
+    for (int k = 0; k < kMomentCount; ++k) partials_row[k] = m[k];
   }
 }
 
 __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, const Scalars* __restrict__ scalars, double* __restrict__ moment_partials) {
-  __shared__ double s_red[kRsThreads / kWarp];
+  __shared__ double s_red[kMomentCount * kRsThreads / kWarp];
   const unsigned long long total = a.global_total != 0 ? a.global_total : scalars->total;
   unsigned long long stride = 0, offset = 0;
   if (a.scheme == 1) {
@@ -900,7 +928,7 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, co
 
 __global__ void __launch_bounds__(kStreamThreads) moments_kernel(const Pose2* __restrict__ states, const double* __restrict__ weights, uint64_t n,
                                                                  double px, double py, double* __restrict__ moment_partials) {
-  __shared__ double s_red[kStreamThreads / kWarp];
+  __shared__ double s_red[kMomentCount * kStreamThreads / kWarp];
   double m[kMomentCount];
 #pragma unroll
   for (int k = 0; k < kMomentCount; ++k) m[k] = 0.0;
