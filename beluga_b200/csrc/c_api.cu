@@ -183,6 +183,27 @@ int bb200_filter_enqueue_moments(bb200_filter* f, const double pivot_xy[2]) {
   BB_REQUIRE(f && pivot_xy);
   return f->impl.enqueue_moments(pivot_xy);
 }
+int bb200_filter_ipc_handles(bb200_filter* f, void* out128) {
+  BB_REQUIRE(f && out128);
+  return f->impl.ipc_handles(out128);
+}
+int bb200_filter_open_peers(bb200_filter* f, int world, int rank, const void* handles) {
+  BB_REQUIRE(f && handles);
+  return f->impl.open_peers(world, rank, handles);
+}
+int bb200_filter_enqueue_resample_push(bb200_filter* f, const bb200_resample_opts* o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin,
+                                       uint64_t slot_end, uint64_t shard, const double pivot_xy[2]) {
+  BB_REQUIRE(f && o && pivot_xy && slot_end >= slot_begin && shard > 0);
+  return f->impl.enqueue_resample_push(*o, global_total, cdf_offset, slot_begin, slot_end, shard, pivot_xy);
+}
+int bb200_filter_enqueue_reduce_moments(bb200_filter* f) {
+  BB_REQUIRE(f);
+  return f->impl.enqueue_reduce_moments();
+}
+int bb200_filter_enqueue_flip_adopt(bb200_filter* f, uint64_t n) {
+  BB_REQUIRE(f);
+  return f->impl.enqueue_flip_adopt(n);
+}
 int bb200_filter_ancestors(bb200_filter* f, int64_t* out, uint64_t capacity) {
   BB_REQUIRE(f && out);
   return f->impl.ancestors(out, capacity);

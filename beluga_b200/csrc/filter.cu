@@ -295,6 +295,74 @@ int Filter::enqueue_resample_range(const bb200_resample_opts& o, uint64_t global
   return BB200_OK;
 }
 
+int Filter::ipc_handles(void* out128) {
+  BB_CHECK(cudaSetDevice(config_.device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "two IPC handles are exported as 128 bytes");
+  cudaIpcMemHandle_t h[2];
+  BB_CHECK(cudaIpcGetMemHandle(&h[0], states_[0]));
+  BB_CHECK(cudaIpcGetMemHandle(&h[1], states_[1]));
+  std::memcpy(out128, h, sizeof(h));
+  return BB200_OK;
+}
+
+int Filter::open_peers(int world, int rank, const void* handles) {
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(BB200_ERR_INVALID_ARGUMENT, "peer groups hold 1..8 ranks");
+  BB_CHECK(cudaSetDevice(config_.device));
+  const auto* all = static_cast<const cudaIpcMemHandle_t*>(handles);
+  for (int r = 0; r < world; ++r) {
+    for (int b = 0; b < 2; ++b) {
+      if (r == rank) {
+        peer_states_[b][r] = states_[b];
+      } else {
+        void* p = nullptr;
+        BB_CHECK(cudaIpcOpenMemHandle(&p, all[2 * r + b], cudaIpcMemLazyEnablePeerAccess));
+        peer_states_[b][r] = static_cast<Pose2*>(p);
+      }
+    }
+  }
+  peer_world_ = world;
+  peer_rank_ = rank;
+  return BB200_OK;
+}
+
+int Filter::enqueue_resample_push(const bb200_resample_opts& o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin, uint64_t slot_end,
+                                  uint64_t shard, const double pivot[2]) {
+  if (peer_world_ == 0) return fail(BB200_ERR_STATE, "open_peers must run before resample_push");
+  if (!cdf_valid_) return fail(BB200_ERR_STATE, "build_cdf must run before resample_push");
+  if (o.scheme != BB200_RESAMPLE_SYSTEMATIC || o.random_state_probability > 0.0 || o.min_particles < o.max_particles)
+    return fail(BB200_ERR_STATE, "sharded resampling supports the systematic comb without injection / KLD");
+  BB_CHECK(cudaSetDevice(config_.device));
+  ResampleArgs a = make_resample_args(o, 0, slot_end - slot_begin, false);
+  a.slot_first = slot_begin;
+  a.global_total = global_total;
+  a.cdf_offset = cdf_offset;
+  a.weights_out = nullptr;
+  a.ancestors = nullptr;
+  a.peer_count = peer_world_;
+  a.peer_shard = shard;
+  a.pivot_x = pivot[0];
+  a.pivot_y = pivot[1];
+  for (int r = 0; r < peer_world_; ++r) a.peer_out[r] = peer_states_[cur_ ^ 1][r];
+  mark("resample_push");
+  // slot_count may be 0 (a shard without weight): the kernel still writes its (zero) moment partials.
+  launch_resample(a, scalars_, partials_, stream_);
+  BB_LAUNCHED("resample_push");
+  pushed_blocks_ = resample_block_count(a.slot_count);
+  return BB200_OK;
+}
+
+int Filter::enqueue_reduce_moments() {
+  BB_CHECK(cudaSetDevice(config_.device));
+  launch_reduce_partials(partials_, pushed_blocks_, kMomentCount, results_, stream_);
+  BB_LAUNCHED("reduce_partials");
+  return BB200_OK;
+}
+
+int Filter::enqueue_flip_adopt(uint64_t n) {
+  cur_ ^= 1;  // the staging buffer, filled by the peers, becomes the particle set
+  return enqueue_adopt(n);
+}
+
 int Filter::enqueue_adopt(uint64_t n) {
   if (n > capacity_) return fail(BB200_ERR_CAPACITY, "more particles than the filter capacity");
   BB_CHECK(cudaSetDevice(config_.device));

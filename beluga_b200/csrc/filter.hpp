@@ -58,6 +58,14 @@ class Filter {
   int enqueue_build_cdf();                      // exponent from the wmax in the device scalars (all-reduced by the caller)
   int enqueue_resample_range(const bb200_resample_opts& o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin, uint64_t slot_end);
   int enqueue_adopt(uint64_t n);
+  // Peer-to-peer redistribution (one process per GPU; CUDA IPC): handles of the two state buffers,
+  // mapping of the peers' buffers, and the fused produce-and-store step.
+  int ipc_handles(void* out128);
+  int open_peers(int world, int rank, const void* handles /* world x 128 bytes */);
+  int enqueue_resample_push(const bb200_resample_opts& o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin, uint64_t slot_end,
+                            uint64_t shard, const double pivot[2]);
+  int enqueue_flip_adopt(uint64_t n);
+  int enqueue_reduce_moments();
   int enqueue_moments(const double pivot[2]);   // raw moments stay in the device result block
 
   int synchronize();
@@ -90,6 +98,9 @@ class Filter {
   std::string error_;
   cudaStream_t stream_{nullptr};
   bool owns_stream_{true};
+  int peer_world_{0}, peer_rank_{0};
+  uint32_t pushed_blocks_{1};
+  Pose2* peer_states_[2][8]{};  // [buffer][rank]: the peers' ping-pong state buffers mapped into this process
 
   // particle set (ping-pong states for the resample gather)
   uint64_t capacity_{0}, n_{0};

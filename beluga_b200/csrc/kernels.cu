@@ -915,7 +915,12 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, co
       ancestor = static_cast<long long>(idx);
       st = load_pose(a.states_in + idx);
     }
-    store_pose(a.states_out + local, st);
+    if (a.peer_count > 0) {
+      const uint64_t owner = j / a.peer_shard;  // P2P store over NVLink (or a local store when owner == this rank)
+      store_pose(a.peer_out[owner] + (j - owner * a.peer_shard), st);
+    } else {
+      store_pose(a.states_out + local, st);
+    }
     if (a.weights_out != nullptr) a.weights_out[local] = 1.0;  // make_from_state (particle_traits.hpp:105)
     if (a.ancestors != nullptr) a.ancestors[local] = ancestor;
     if (a.hashes != nullptr) a.hashes[local] = spatial_hash(st, a.hash_resolution[0], a.hash_resolution[1], a.hash_resolution[2]);

@@ -129,6 +129,12 @@ struct ResampleArgs {
   uint64_t total_slots;   // M: the comb of systematic resampling spans all global slots
   unsigned long long global_total;  // fixed-point total over all ranks (0: scalars->total, single shard)
   unsigned long long cdf_offset;    // sum of the totals of the lower ranks: local position = t - cdf_offset
+  // Fused redistribution over NVLink peer memory: when peer_count > 0 the state of global slot j is
+  // stored straight into the staging buffer of the rank that owns the slot (peer_out[j / peer_shard]
+  // at j % peer_shard) instead of states_out[local].
+  int peer_count;
+  uint64_t peer_shard;
+  Pose2* peer_out[8];
   int scheme;
   uint64_t seed;
   uint32_t step;

@@ -95,7 +95,7 @@ def _state_view(filter_, which: int, count: int):
 class ShardedAmcl:
     """beluga::Amcl (algorithm/amcl_core.hpp:81-233) over `world` GPUs; call from every rank in lock step."""
 
-    def __init__(self, motion, params, shard: int, process_group=None):
+    def __init__(self, motion, params, shard: int, process_group=None, p2p: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -126,6 +126,13 @@ class ShardedAmcl:
         self.filter.set_stream(torch.cuda.current_stream().cuda_stream)
         self._scalars = None
         self._results = None
+        # Fused resample + redistribution: map every rank's state buffers (CUDA IPC) so that the resample
+        # kernel stores each new particle straight into its owner's buffer over NVLink.
+        self.p2p = p2p and 1 < self.world <= 8
+        if self.p2p:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.filter.ipc_handles(), group=process_group)
+            self.filter.open_peers(self.world, self.rank, b"".join(handles))
 
     def update_map(self, sensor, sensor_params, grid):
         self.amcl.update_map(sensor, sensor_params, grid)
@@ -214,9 +221,17 @@ class ShardedAmcl:
 
         stride, comb = _systematic_comb(self.params.seed, plan.step, global_total, self.total)
         ranges = slot_ranges(offsets, stride, comb, self.total)
-        self._redistribute(plan, ranges, global_total, offsets[self.rank], streamed=True)
-        f.enqueue_moments(self.pivot)
-        dist.all_reduce(results[0:9], op=dist.ReduceOp.SUM, group=self.group)
+        if self.p2p:
+            # One kernel: CDF search + gather + peer stores into the owners' buffers + moments of what it produced.
+            ja, jb = ranges[self.rank]
+            f.enqueue_resample_push(plan.opts, global_total, offsets[self.rank], ja, jb, self.shard, self.pivot)
+            f.enqueue_reduce_moments()
+            dist.all_reduce(results[0:9], op=dist.ReduceOp.SUM, group=self.group)  # also the barrier: all peer stores are done
+            f.enqueue_flip_adopt(self.shard)
+        else:
+            self._redistribute(plan, ranges, global_total, offsets[self.rank], streamed=True)
+            f.enqueue_moments(self.pivot)
+            dist.all_reduce(results[0:9], op=dist.ReduceOp.SUM, group=self.group)
         moments = results[0:9].cpu().numpy()  # synchronisation 2
         f.synchronize()  # closes the timing marks; the stream is already idle
         from . import estimate_from_moments

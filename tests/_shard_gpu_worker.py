@@ -21,13 +21,14 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rank, world = dist.get_rank(), dist.get_world_size()
     shard, steps = int(sys.argv[1]), int(sys.argv[2])
+    p2p = len(sys.argv) > 3 and sys.argv[3] == "p2p"
     total = shard * world
     sc = synthetic.make_scenario(grid_size=200, n_beams=181, steps=steps + 1)
     motion = bb.DifferentialDriveModelParam(0.1, 0.05, 0.1, 0.05)
     lfm = bb.LikelihoodFieldModelParam(max_obstacle_distance=2.0, max_laser_distance=100.0)
     grid = bb.OccupancyGrid(sc.cells, sc.resolution)
 
-    sharded = ShardedAmcl(motion, bb.AmclParams(resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=21, device=local_rank), shard=shard)
+    sharded = ShardedAmcl(motion, bb.AmclParams(resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=21, device=local_rank), shard=shard, p2p=p2p)
     sharded.update_map(bb.SENSOR_LIKELIHOOD_FIELD, lfm, grid)
     sharded.initialize(sc.initial_mean, sc.initial_cov)
     single = None

@@ -1,5 +1,6 @@
 """Multi-GPU parity: a filter sharded over 2 GPUs (NCCL) must produce the SAME particle set, weight sum and
-estimate as the single-GPU filter with the same total particle count, step after step."""
+estimate as the single-GPU filter with the same total particle count, step after step -- both with
+the NCCL all-to-all redistribution and with the fused kernel that stores over NVLink peer memory."""
 import os
 import subprocess
 import sys
@@ -10,7 +11,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_gpu_shards_match_single_gpu():
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+def test_two_gpu_shards_match_single_gpu(mode):
     import beluga_b200 as bb
     from beluga_b200 import build as bb_build
 
@@ -18,7 +20,7 @@ def test_two_gpu_shards_match_single_gpu():
     if bb.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29711", os.path.join(ROOT, "tests", "_shard_gpu_worker.py"), "40000", "6"]
+           "--master-port", "29711" if mode == "nccl" else "29713", os.path.join(ROOT, "tests", "_shard_gpu_worker.py"), "40000", "6", mode]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "SHARD_GPU_WORKER_OK" in out.stdout
