@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "amcl_oracle.hpp"
+#include "cluster_oracle.hpp"
 
 using namespace oracle;
 
@@ -274,6 +275,64 @@ void orc_estimate(const double* states, const double* weights, std::uint64_t n, 
   std::vector<SE2> s(n);
   for (std::uint64_t i = 0; i < n; ++i) s[i] = se2_from_data(states + 4 * i);
   const Estimate e = estimate(s, std::vector<double>(weights, weights + n));
+  mean4[0] = e.mean.r.c, mean4[1] = e.mean.r.s, mean4[2] = e.mean.x, mean4[3] = e.mean.y;
+  std::memcpy(cov9, e.cov, sizeof(e.cov));
+}
+
+// ---- cluster-based estimate (cluster_oracle.hpp) ----------------------------------------------
+
+double orc_percentile_threshold(const double* values, std::uint64_t n, double percentile) {
+  return calculate_percentile_threshold(std::vector<double>(values, values + n), percentile);
+}
+
+static std::vector<SE2> states_from_data(const double* states, std::uint64_t n) {
+  std::vector<SE2> s(n);
+  for (std::uint64_t i = 0; i < n; ++i) s[i] = se2_from_data(states + 4 * i);
+  return s;
+}
+
+void orc_cluster_ids(const double* states, const double* weights, std::uint64_t n, double linear, double angular, double percentile,
+                     std::uint64_t* ids_out) {
+  const auto ids = ParticleClusterizer{ParticleClusterizerParam{linear, angular, percentile}}(states_from_data(states, n),
+                                                                                              std::vector<double>(weights, weights + n));
+  for (std::uint64_t i = 0; i < n; ++i) ids_out[i] = ids[i];
+}
+
+/// assign_clusters on a hand-made map (one cell per entry, inserted with emplace in the given order,
+/// as test_cluster_based_estimation.cpp:171-176 does); n_neighbors = 4 (the test's own neighbour
+/// function, :178-189) or 6 (ParticleClusterizer::neighbors).
+void orc_assign_clusters(const double* states, const double* cell_weights, std::uint64_t n, double linear, double angular, int n_neighbors,
+                         std::uint64_t* ids_out) {
+  const ParticleClusterizer c{ParticleClusterizerParam{linear, angular, 0.9}};
+  const auto s = states_from_data(states, n);
+  ClusterMap map;
+  for (std::uint64_t i = 0; i < n; ++i) map.emplace(c.hash(s[i]), ClusterCell{s[i], cell_weights[i], 0, std::nullopt});
+  assign_clusters(map, [&](const SE2& pose) {
+    auto all = c.neighbors(pose);
+    all.resize(static_cast<std::size_t>(n_neighbors));
+    return all;
+  });
+  for (std::uint64_t i = 0; i < n; ++i) ids_out[i] = map[c.hash(s[i])].cluster_id.value();
+}
+
+std::uint64_t orc_estimate_clusters(const double* states, const double* weights, const std::uint64_t* clusters, std::uint64_t n,
+                                    std::uint64_t max_out, double* weight_out, double* mean4_out, double* cov9_out, std::uint64_t* id_out) {
+  const auto per = estimate_clusters(states_from_data(states, n), std::vector<double>(weights, weights + n),
+                                     std::vector<std::size_t>(clusters, clusters + n));
+  for (std::size_t k = 0; k < per.size() && k < max_out; ++k) {
+    weight_out[k] = per[k].weight;
+    const Estimate& e = per[k].estimate;
+    mean4_out[4 * k + 0] = e.mean.r.c, mean4_out[4 * k + 1] = e.mean.r.s, mean4_out[4 * k + 2] = e.mean.x, mean4_out[4 * k + 3] = e.mean.y;
+    std::memcpy(cov9_out + 9 * k, e.cov, sizeof(e.cov));
+    id_out[k] = per[k].cluster;
+  }
+  return per.size();
+}
+
+void orc_cluster_based_estimate(const double* states, const double* weights, std::uint64_t n, double linear, double angular, double percentile,
+                                double* mean4, double* cov9) {
+  const Estimate e = cluster_based_estimate(states_from_data(states, n), std::vector<double>(weights, weights + n),
+                                            ParticleClusterizerParam{linear, angular, percentile});
   mean4[0] = e.mean.r.c, mean4[1] = e.mean.r.s, mean4[2] = e.mean.x, mean4[3] = e.mean.y;
   std::memcpy(cov9, e.cov, sizeof(e.cov));
 }

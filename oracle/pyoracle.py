@@ -319,6 +319,57 @@ def estimate(states, weights):
     return mean, cov.reshape(3, 3)
 
 
+# ---- cluster-based estimate ---------------------------------------------------------------------
+
+def percentile_threshold(values, percentile: float) -> float:
+    v = _f64(values)
+    fn = lib().orc_percentile_threshold
+    fn.restype = C.c_double
+    return fn(_p(v, C.c_double), C.c_uint64(len(v)), C.c_double(percentile))
+
+
+def cluster_ids(states, weights, linear=0.2, angular=0.524, percentile=0.9) -> np.ndarray:
+    st = _f64(states).reshape(-1, 4)
+    w = _f64(weights)
+    out = np.zeros(len(st), dtype=np.uint64)
+    lib().orc_cluster_ids(_p(st, C.c_double), _p(w, C.c_double), C.c_uint64(len(st)), C.c_double(linear), C.c_double(angular),
+                          C.c_double(percentile), _p(out, C.c_uint64))
+    return out
+
+
+def assign_clusters(cell_states, cell_weights, linear: float, angular: float, n_neighbors: int = 6) -> np.ndarray:
+    st = _f64(cell_states).reshape(-1, 4)
+    w = _f64(cell_weights)
+    out = np.zeros(len(st), dtype=np.uint64)
+    lib().orc_assign_clusters(_p(st, C.c_double), _p(w, C.c_double), C.c_uint64(len(st)), C.c_double(linear), C.c_double(angular),
+                              C.c_int(n_neighbors), _p(out, C.c_uint64))
+    return out
+
+
+def estimate_clusters(states, weights, clusters):
+    """-> list of (cluster id, total weight, mean[4], cov[3,3]) for clusters with more than one particle."""
+    st = _f64(states).reshape(-1, 4)
+    w = _f64(weights)
+    c = np.ascontiguousarray(clusters, dtype=np.uint64)
+    cap = len(st)
+    wt, mean, cov, ids = np.zeros(cap), np.zeros((cap, 4)), np.zeros((cap, 9)), np.zeros(cap, dtype=np.uint64)
+    fn = lib().orc_estimate_clusters
+    fn.restype = C.c_uint64
+    k = fn(_p(st, C.c_double), _p(w, C.c_double), _p(c, C.c_uint64), C.c_uint64(len(st)), C.c_uint64(cap), _p(wt, C.c_double),
+           _p(mean, C.c_double), _p(cov, C.c_double), _p(ids, C.c_uint64))
+    return [(int(ids[i]), float(wt[i]), mean[i].copy(), cov[i].reshape(3, 3).copy()) for i in range(k)]
+
+
+def cluster_based_estimate(states, weights, linear=0.2, angular=0.524, percentile=0.9):
+    st = _f64(states).reshape(-1, 4)
+    w = _f64(weights)
+    mean = np.zeros(4)
+    cov = np.zeros(9)
+    lib().orc_cluster_based_estimate(_p(st, C.c_double), _p(w, C.c_double), C.c_uint64(len(st)), C.c_double(linear), C.c_double(angular),
+                                     C.c_double(percentile), _p(mean, C.c_double), _p(cov, C.c_double))
+    return mean, cov.reshape(3, 3)
+
+
 def normal_transform(cov) -> np.ndarray:
     c = _f64(cov).reshape(9)
     out = np.zeros(9)
