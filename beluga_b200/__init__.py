@@ -423,6 +423,19 @@ class Filter:
         self._check(self._lib.bb200_filter_estimate(self._h, C.byref(e)))
         return np.array(e.mean), np.array(e.cov).reshape(3, 3)
 
+    def cluster_estimate(self, linear: float = 0.20, angular: float = 0.524, percentile: float = 0.90, with_ids: bool = False):
+        """beluga::cluster_based_estimate (algorithm/cluster_based_estimation.hpp:415-432) -> (mean[4], cov[3,3]);
+        with_ids adds (cluster id per particle, number of occupied cells, number of clusters)."""
+        e = _capi.Estimate()
+        p = _capi.ClusterParam(linear, angular, percentile)
+        ids = np.zeros(self.size if with_ids else 0, dtype=np.uint32)
+        cells, clusters = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.bb200_filter_cluster_estimate(
+            self._h, C.byref(p), C.byref(e), ids.ctypes.data_as(C.POINTER(C.c_uint32)) if with_ids else None, ids.size,
+            C.byref(cells), C.byref(clusters)))
+        est = (np.array(e.mean), np.array(e.cov).reshape(3, 3))
+        return (*est, ids, cells.value, clusters.value) if with_ids else est
+
     def moments(self, pivot=(0.0, 0.0)) -> np.ndarray:
         out = np.zeros(9)
         self._check(self._lib.bb200_filter_moments(self._h, _dptr(_f64(pivot)), _dptr(out)))

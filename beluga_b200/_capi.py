@@ -60,6 +60,10 @@ class Estimate(C.Structure):
     _fields_ = [("mean", C.c_double * 4), ("cov", C.c_double * 9)]
 
 
+class ClusterParam(C.Structure):
+    _fields_ = [("linear_hash_resolution", C.c_double), ("angular_hash_resolution", C.c_double), ("weight_cap_percentile", C.c_double)]
+
+
 class FilterConfig(C.Structure):
     _fields_ = [("device", C.c_int), ("capacity", C.c_uint64), ("seed", C.c_uint64), ("first_index", C.c_uint64),
                 ("global_count", C.c_uint64), ("record_ancestors", C.c_int)]
@@ -139,6 +143,8 @@ SIGNATURES = {
     "bb200_filter_ancestors": (C.c_int, [_vp, _P(C.c_int64), C.c_uint64]),
     "bb200_filter_cdf": (C.c_int, [_vp, _P(C.c_uint64), C.c_uint64]),
     "bb200_filter_estimate": (C.c_int, [_vp, _P(Estimate)]),
+    "bb200_cluster_param_default": (None, [_P(ClusterParam)]),
+    "bb200_filter_cluster_estimate": (C.c_int, [_vp, _P(ClusterParam), _P(Estimate), _P(C.c_uint32), C.c_uint64, _P(C.c_uint32), _P(C.c_uint32)]),
     "bb200_filter_moments": (C.c_int, [_vp, _dbl, _dbl]),
     "bb200_filter_set_timing": (C.c_int, [_vp, C.c_int]),
     "bb200_filter_clear_timings": (C.c_int, [_vp]),

@@ -216,6 +216,17 @@ int bb200_filter_estimate(bb200_filter* f, bb200_estimate* out) {
   BB_REQUIRE(f && out);
   return f->impl.estimate(out);
 }
+void bb200_cluster_param_default(bb200_cluster_param* p) {
+  if (p == nullptr) return;
+  p->linear_hash_resolution = 0.20;
+  p->angular_hash_resolution = 0.524;
+  p->weight_cap_percentile = 0.90;
+}
+int bb200_filter_cluster_estimate(bb200_filter* f, const bb200_cluster_param* p, bb200_estimate* out, uint32_t* cluster_ids, uint64_t ids_capacity,
+                                  uint32_t* n_cells, uint32_t* n_clusters) {
+  BB_REQUIRE(f && p);
+  return f->impl.cluster_estimate(*p, out, cluster_ids, ids_capacity, n_cells, n_clusters);
+}
 int bb200_filter_moments(bb200_filter* f, const double pivot_xy[2], double out[9]) {
   BB_REQUIRE(f && pivot_xy && out);
   return f->impl.moments(pivot_xy, out);

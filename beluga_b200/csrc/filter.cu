@@ -6,6 +6,7 @@
 #include <cstring>
 #include <limits>
 
+#include "cluster_host.hpp"
 #include "map_host.hpp"
 
 namespace bb200 {
@@ -163,6 +164,21 @@ Filter::~Filter() {
   cudaFree(partials_);
   cudaFree(results_);
   cudaFreeHost(results_host_);
+  cudaFree(cluster_.hashes);
+  cudaFree(cluster_.keys);
+  cudaFree(cluster_.first);
+  cudaFree(cluster_.slot_of);
+  cudaFree(cluster_.flags);
+  cudaFree(cluster_.cell_of);
+  cudaFree(cluster_.starts);
+  cudaFree(cluster_.keys_a);
+  cudaFree(cluster_.keys_b);
+  cudaFree(cluster_.idx_a);
+  cudaFree(cluster_.idx_b);
+  cudaFree(cluster_.histogram);
+  cudaFree(cluster_.tile_state);
+  cudaFree(cluster_.words);
+  cudaFree(cluster_.records);
   cudaFree(kld_keys_);
   cudaFree(kld_vals_);
   cudaFree(kld_flags_);
@@ -763,6 +779,88 @@ int Filter::estimate(bb200_estimate* out) {
   estimate_from_moments(m, out);
   pivot_[0] = out->mean[2];
   pivot_[1] = out->mean[3];
+  return BB200_OK;
+}
+
+// ---- cluster-based estimate ---------------------------------------------------------------------
+
+int Filter::ensure_cluster_scratch(uint32_t cells) {
+  ClusterScratch& c = cluster_;
+  if (c.capacity == 0) {
+    if (capacity_ >= (1ull << 31)) return fail(BB200_ERR_CAPACITY, "cluster estimate: more than 2^31 particles per filter");
+    uint64_t table = 2;
+    while (table < 2 * capacity_) table <<= 1;
+    const uint32_t tiles = cluster_sort_tiles(capacity_);
+    BB_CHECK(dev_alloc(&c.hashes, capacity_));
+    BB_CHECK(dev_alloc(&c.keys, table));
+    BB_CHECK(dev_alloc(&c.first, table));
+    BB_CHECK(dev_alloc(&c.slot_of, capacity_));
+    BB_CHECK(dev_alloc(&c.flags, capacity_));
+    BB_CHECK(dev_alloc(&c.cell_of, capacity_));
+    BB_CHECK(dev_alloc(&c.starts, capacity_ + 1));
+    BB_CHECK(dev_alloc(&c.keys_a, capacity_));
+    BB_CHECK(dev_alloc(&c.keys_b, capacity_));
+    BB_CHECK(dev_alloc(&c.idx_a, capacity_));
+    BB_CHECK(dev_alloc(&c.idx_b, capacity_));
+    BB_CHECK(dev_alloc(&c.histogram, static_cast<size_t>(256) * tiles));
+    BB_CHECK(dev_alloc(&c.tile_state, static_cast<size_t>(scan_tile_count(std::max<uint64_t>(capacity_ + 1, 256ull * tiles)) + 1)));
+    BB_CHECK(dev_alloc(&c.words, 4));
+    c.table_size = table;
+    c.capacity = capacity_;
+  }
+  if (cells > c.records_capacity) {
+    cudaFree(c.records);
+    c.records = nullptr;
+    c.records_capacity = 0;
+    const uint64_t want = std::min<uint64_t>(capacity_, std::max<uint64_t>(1024, 2ull * cells));
+    BB_CHECK(dev_alloc(&c.records, want));
+    c.records_capacity = want;
+  }
+  return BB200_OK;
+}
+
+int Filter::cluster_estimate(const bb200_cluster_param& p, bb200_estimate* out, uint32_t* cluster_ids, uint64_t ids_capacity, uint32_t* n_cells,
+                             uint32_t* n_clusters) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  if (!(p.linear_hash_resolution > 0.0) || !(p.angular_hash_resolution > 0.0) || !(p.weight_cap_percentile >= 0.0) ||
+      !(p.weight_cap_percentile < 1.0))
+    return fail(BB200_ERR_INVALID_ARGUMENT, "cluster parameters: resolutions must be positive and the percentile in [0, 1)");
+  if (cluster_ids != nullptr && ids_capacity < n_) return fail(BB200_ERR_CAPACITY, "cluster id buffer too small");
+  BB_CHECK(cudaSetDevice(config_.device));
+  {
+    const int st = ensure_cluster_scratch(0);
+    if (st != BB200_OK) return st;
+  }
+  mark("cluster_cells");
+  launch_cluster_cells_begin(states_[cur_], n_, p.linear_hash_resolution, p.angular_hash_resolution, cluster_, stream_);
+  BB_LAUNCHED_N("cluster_cells_begin", 3);
+  unsigned long long cells64 = 0;
+  BB_CHECK(cudaMemcpyAsync(&cells64, cluster_.words + 1, sizeof(cells64), cudaMemcpyDeviceToHost, stream_));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  const uint32_t cells = static_cast<uint32_t>(cells64);
+  {
+    const int st = ensure_cluster_scratch(cells);
+    if (st != BB200_OK) return st;
+  }
+  mark("cluster_sort");
+  const uint32_t* sorted = launch_cluster_cells_finish(states_[cur_], weights_, n_, cells, pivot_[0], pivot_[1], cluster_, stream_);
+  (void)sorted;
+  BB_LAUNCHED_N("cluster_cells_finish", 3 + 2 * std::max(1, (static_cast<int>(std::ceil(std::log2(std::max<double>(cells, 2)))) + 7) / 8));
+  std::vector<HostCell> host(cells);
+  static_assert(sizeof(HostCell) == sizeof(CellRecord), "record layouts must agree");
+  BB_CHECK(cudaMemcpyAsync(host.data(), cluster_.records, static_cast<size_t>(cells) * sizeof(CellRecord), cudaMemcpyDeviceToHost, stream_));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  finish_marks();
+
+  const ClusterSelection sel = select_cluster(host.data(), host.size(), n_, p.linear_hash_resolution, p.angular_hash_resolution, p.weight_cap_percentile);
+  if (out != nullptr) estimate_from_moments(sel.moments, out);
+  if (n_cells != nullptr) *n_cells = cells;
+  if (n_clusters != nullptr) *n_clusters = sel.clusters;
+  if (cluster_ids != nullptr) {
+    std::vector<uint32_t> cell_of(n_);
+    BB_CHECK(cudaMemcpy(cell_of.data(), cluster_.cell_of, n_ * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < n_; ++i) cluster_ids[i] = sel.cluster_of_cell[cell_of[i]];
+  }
   return BB200_OK;
 }
 

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/beluga_b200.h"
+#include "cluster.cuh"
 #include "kernels.cuh"
 
 namespace bb200 {
@@ -44,6 +45,10 @@ class Filter {
   int cdf(uint64_t* out, uint64_t capacity);
   int estimate(bb200_estimate* out);
   int moments(const double pivot[2], double out[9]);
+  /// beluga::cluster_based_estimate (algorithm/cluster_based_estimation.hpp:415-432); cluster_ids
+  /// (optional, one per particle) is the parity hook for ParticleClusterizer::operator() (:304-316).
+  int cluster_estimate(const bb200_cluster_param& p, bb200_estimate* out, uint32_t* cluster_ids, uint64_t ids_capacity, uint32_t* n_cells,
+                       uint32_t* n_clusters);
   static void estimate_from_moments_static(const double m[kMomentCount], const double pivot[2], bb200_estimate* out);
 
   /// Fused single-GPU step: propagate | reweight | normalize | resample | estimate with one
@@ -123,6 +128,10 @@ class Filter {
   uint32_t partials_rows_{0};
   double* results_{nullptr};       // device: kMomentCount + extras
   double* results_host_{nullptr};  // pinned
+
+  // clusterizer scratch (allocated on first use)
+  int ensure_cluster_scratch(uint32_t cells);
+  ClusterScratch cluster_{};
 
   // KLD scratch
   unsigned long long* kld_keys_{nullptr};

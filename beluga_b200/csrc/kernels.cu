@@ -1070,6 +1070,15 @@ void launch_kld_chunk(const KldArgs& a, unsigned long long* keys, unsigned int* 
   kld_check_kernel<<<blocks, 256, 0, stream>>>(flags, exclusive, a.n, a.slot_base, a.k_before, a.min_particles, 2 * a.epsilon, a.z, scalars);
 }
 
+void launch_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, unsigned long long* ticket, unsigned long long* tile_state,
+                     unsigned long long* total_out, cudaStream_t stream) {
+  if (n == 0) return;
+  const uint32_t tiles = (n + kScanTile - 1) / kScanTile;
+  cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream);
+  cudaMemsetAsync(tile_state, 0, static_cast<size_t>(tiles) * sizeof(unsigned long long), stream);
+  scan_u32_kernel<<<tiles, kScanThreads, 0, stream>>>(in, out, n, ticket, tile_state, total_out);
+}
+
 uint32_t resample_block_count(uint64_t slots) {
   return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>((slots + kRsThreads - 1) / kRsThreads, 148 * 16)));
 }

@@ -107,6 +107,10 @@ void launch_max_weight(const double* weights, uint64_t n, Scalars* scalars, cuda
 /// Sets scalars->exponent from wmax (device value when host_wmax < 0) and resets the scan state.
 void launch_prepare_cdf(Scalars* scalars, double host_wmax, uint64_t global_count, unsigned long long* tile_state, uint32_t n_tiles,
                         cudaStream_t stream);
+/// Exclusive prefix sum of n u32 values (in and out may alias); *total_out (optional) receives the sum.
+/// `ticket` is one device word, `tile_state` holds scan_tile_count(n) words; both are reset here.
+void launch_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, unsigned long long* ticket, unsigned long long* tile_state,
+                     unsigned long long* total_out, cudaStream_t stream);
 uint32_t scan_tile_count(uint64_t n);
 /// Fixed-point quantisation + single-pass inclusive scan (decoupled look-back).
 void launch_quantize_scan(const double* weights, uint64_t n, unsigned long long* cdf, Scalars* scalars, unsigned long long* tile_state,

@@ -269,6 +269,21 @@ int bb200_filter_cdf(bb200_filter* f, uint64_t* out, uint64_t capacity);
 
 /* beluga::estimate(states, weights) (algorithm/estimation.hpp:436-475). */
 int bb200_filter_estimate(bb200_filter* f, bb200_estimate* out);
+/* beluga::ParticleClusterizerParam (algorithm/cluster_based_estimation.hpp:259-276), same defaults
+ * when filled by bb200_cluster_param_default. */
+typedef struct bb200_cluster_param {
+  double linear_hash_resolution;  /* 0.20 */
+  double angular_hash_resolution; /* 0.524 */
+  double weight_cap_percentile;   /* 0.90 */
+} bb200_cluster_param;
+void bb200_cluster_param_default(bb200_cluster_param* p);
+/* beluga::cluster_based_estimate(states, weights, parameters) (cluster_based_estimation.hpp:415-432),
+ * what beluga_ros::Amcl::update returns (beluga_ros/src/amcl.cpp:125): mean and covariance of the
+ * heaviest cluster with more than one particle, or of the whole set when there is none.
+ * Optional outputs (may be NULL): cluster_ids[i] = ParticleClusterizer::operator() (:304-316) for
+ * particle i (ids_capacity >= particle count), the number of occupied cells and of clusters. */
+int bb200_filter_cluster_estimate(bb200_filter* f, const bb200_cluster_param* p, bb200_estimate* out, uint32_t* cluster_ids,
+                                  uint64_t ids_capacity, uint32_t* n_cells, uint32_t* n_clusters);
 /* Raw weighted moments of the local shard for a multi-rank estimate:
  * {sum w, sum w^2, sum w*cos, sum w*sin, sum w*dx, sum w*dy, sum w*dx^2, sum w*dx*dy, sum w*dy^2}
  * with (dx, dy) = (x, y) - pivot. */
