@@ -428,7 +428,7 @@ class Filter:
         with_ids adds (cluster id per particle, number of occupied cells, number of clusters)."""
         e = _capi.Estimate()
         p = _capi.ClusterParam(linear, angular, percentile)
-        ids = np.zeros(self.size if with_ids else 0, dtype=np.uint32)
+        ids = np.zeros(self.size() if with_ids else 0, dtype=np.uint32)
         cells, clusters = C.c_uint32(0), C.c_uint32(0)
         self._check(self._lib.bb200_filter_cluster_estimate(
             self._h, C.byref(p), C.byref(e), ids.ctypes.data_as(C.POINTER(C.c_uint32)) if with_ids else None, ids.size,

@@ -151,4 +151,28 @@ class Amcl {
 template <class MotionModel, class SensorModel>
 Amcl(MotionModel, SensorModel, const AmclParams&) -> Amcl<MotionModel, SensorModel>;
 
+/// beluga::ParticleClusterizerParam (algorithm/cluster_based_estimation.hpp:259-276).
+struct ParticleClusterizerParam {
+  double linear_hash_resolution = 0.20;
+  double angular_hash_resolution = 0.524;
+  double weight_cap_percentile = 0.90;
+};
+
+/// beluga::cluster_based_estimate(states, weights, parameters) (cluster_based_estimation.hpp:415-432)
+/// over the filter's device-resident particle set: what beluga_ros::Amcl::update returns
+/// (beluga_ros/src/amcl.cpp:125).  Throws Error when the filter holds no particles.
+template <class MotionModel, class SensorModel, class ExecutionPolicy>
+[[nodiscard]] std::pair<SE2d, Matrix3d> cluster_based_estimate(
+    const Amcl<MotionModel, SensorModel, ExecutionPolicy>& amcl,
+    ParticleClusterizerParam parameters = {}) {
+  const bb200_cluster_param p{parameters.linear_hash_resolution, parameters.angular_hash_resolution, parameters.weight_cap_percentile};
+  bb200_estimate e{};
+  bb200_filter* f = bb200_amcl_filter(amcl.handle());
+  const int st = bb200_filter_cluster_estimate(f, &p, &e, nullptr, 0, nullptr, nullptr);
+  if (st != BB200_OK) throw Error(st, bb200_last_error(f));
+  Matrix3d cov;
+  for (int i = 0; i < 9; ++i) cov[i] = e.cov[i];
+  return std::make_pair(SE2d::from_data(e.mean), cov);
+}
+
 }  // namespace beluga_b200

@@ -125,6 +125,23 @@ void OtherMotionModelsCanBeUsed() {  // beluga_ros::Amcl::motion_model_variant (
   still.initialize(beluga_b200::SE2d{}, kIdentityCov);
   ASSERT_TRUE(still.update(kDummyControl, kDummyMeasurement).has_value());
 }
+void ClusterBasedEstimateCanBeUsed() {  // beluga_ros/src/amcl.cpp:125
+  auto amcl = make_amcl();
+  bool thrown = false;
+  try {
+    (void)beluga_b200::cluster_based_estimate(amcl);
+  } catch (const beluga_b200::Error&) {
+    thrown = true;  // no particles yet
+  }
+  ASSERT_TRUE(thrown);
+  amcl.initialize(beluga_b200::SE2d{0.3, 1.0, 1.0}, beluga_b200::Matrix3d{0.01, 0, 0, 0, 0.01, 0, 0, 0, 0.01});
+  const auto plain = amcl.update(kDummyControl, kDummyMeasurement);
+  ASSERT_TRUE(plain.has_value());
+  const auto [pose, covariance] = beluga_b200::cluster_based_estimate(amcl, beluga_b200::ParticleClusterizerParam{});
+  // one tight blob: the heaviest cluster is (nearly) the whole set
+  ASSERT_TRUE(std::abs(pose.x() - plain->first.x()) < 0.1 && std::abs(pose.y() - plain->first.y()) < 0.1);
+  ASSERT_TRUE(covariance[0] > 0.0 && covariance[4] > 0.0);
+}
 void InvalidCovarianceThrows() {  // multivariate_normal_distribution.hpp:114-116
   auto amcl = make_amcl();
   bool thrown = false;
@@ -147,6 +164,7 @@ int main() {
   SelectiveResampleCanBeConstructed();
   TestRandomParticlesInserting();
   OtherMotionModelsCanBeUsed();
+  ClusterBasedEstimateCanBeUsed();
   InvalidCovarianceThrows();
   if (g_failures == 0) std::printf("CPP_ADAPTORS_OK\n");
   return g_failures == 0 ? 0 : 1;
