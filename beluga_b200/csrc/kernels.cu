@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(512) max_weight_kernel(const double* __restric
 // associative, so the CDF is identical for any scan order, tile size or number of ranks.
 
 constexpr int kScanThreads = 512;
-constexpr int kScanItems = 4;
+constexpr int kScanItems = 8;
 constexpr uint32_t kScanTile = kScanThreads * kScanItems;
 // tile_state word: [63:62] flag (0 empty, 1 aggregate, 2 inclusive prefix), [61:0] value
 constexpr unsigned long long kFlagAggregate = 1ull << 62, kFlagPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1;
@@ -651,27 +651,36 @@ __device__ __forceinline__ unsigned long long block_inclusive_scan_u64(unsigned 
 }
 
 /// Decoupled look-back: returns the exclusive prefix of this tile and publishes its inclusive one.
+/// Warp 0 inspects 32 predecessors per round (one coalesced read of the tile words) instead of walking
+/// them one L2 round trip at a time.
 __device__ __forceinline__ unsigned long long lookback_exclusive_prefix(unsigned long long* tile_state, uint32_t tile,
                                                                          unsigned long long tile_total, unsigned long long* s_prefix) {
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < kWarp) {
+    const int lane = threadIdx.x;
     unsigned long long exclusive = 0;
     if (tile == 0) {
-      atomicExch(&tile_state[0], kFlagPrefix | tile_total);
+      if (lane == 0) atomicExch(&tile_state[0], kFlagPrefix | tile_total);
     } else {
-      atomicExch(&tile_state[tile], kFlagAggregate | tile_total);
-      int32_t look = static_cast<int32_t>(tile) - 1;
-      while (true) {
+      if (lane == 0) atomicExch(&tile_state[tile], kFlagAggregate | tile_total);
+      int32_t window = static_cast<int32_t>(tile) - 1;  // newest predecessor of this round
+      for (;;) {
+        const int32_t look = window - lane;
         unsigned long long word;
-        do {
-          word = *reinterpret_cast<volatile unsigned long long*>(&tile_state[look]);
-        } while ((word >> 62) == 0);
-        exclusive += word & kValueMask;
-        if ((word >> 62) == 2) break;
-        --look;
+        do {  // tiles before tile 0 count as a published prefix of zero
+          word = look >= 0 ? *reinterpret_cast<volatile unsigned long long*>(&tile_state[look]) : (2ull << 62);
+        } while (__any_sync(0xffffffffu, (word >> 62) == 0));
+        const unsigned prefixes = __ballot_sync(0xffffffffu, (word >> 62) == 2);
+        const int last = prefixes != 0 ? __ffs(prefixes) - 1 : kWarp - 1;  // nearest tile that already knows its prefix
+        unsigned long long v = lane <= last ? (word & kValueMask) : 0ull;
+#pragma unroll
+        for (int off = kWarp / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        exclusive += v;
+        if (prefixes != 0) break;
+        window -= kWarp;
       }
-      atomicExch(&tile_state[tile], kFlagPrefix | (exclusive + tile_total));
+      if (lane == 0) atomicExch(&tile_state[tile], kFlagPrefix | (exclusive + tile_total));
     }
-    *s_prefix = exclusive;
+    if (lane == 0) *s_prefix = exclusive;
   }
   __syncthreads();
   return *s_prefix;
