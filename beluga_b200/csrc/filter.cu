@@ -108,6 +108,7 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   if (config_.global_count == 0) config_.global_count = config_.capacity;
   if (const char* v = std::getenv("BB200_SCHEDULE")) schedule_enabled_ = std::atoi(v) != 0;  // development knob: 0 disables the pose-sorted schedule
   if (const char* v = std::getenv("BB200_TILED")) tiled_layout_ = std::atoi(v) != 0;         // development knob: table layout
+  if (const char* v = std::getenv("BB200_FIXED")) fixed_lookup_ = std::atoi(v) != 0;         // development knob: fixed-point lookup kernel
   if (const char* v = std::getenv("BB200_PER_BIN")) schedule_per_bin_ = std::atof(v);        // development knob: particles per pose bin
   capacity_ = config.capacity;
 #define BB_TRY(expr)                                \
@@ -187,6 +188,7 @@ Filter::~Filter() {
   cudaFreeHost(points_host_);
   cudaFree(table_);
   cudaFree(tiled_);
+  cudaFree(bordered_);
   cudaFree(occupancy_);
   cudaFree(free_distance_);
   cudaFree(free_cells_);
@@ -455,6 +457,26 @@ int Filter::set_likelihood_field_map(const bb200_likelihood_field_param& p, cons
   BB_CHECK(dev_alloc(&tiled_, tiled.size()));
   BB_CHECK(cudaMemcpyAsync(tiled_, tiled.data(), tiled.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
   BB_CHECK(cudaStreamSynchronize(stream_));
+  // Bordered tile layout for the fixed-point kernel.
+  field_.use_fixed = 0;
+  field_.bordered = nullptr;
+  cudaFree(bordered_);
+  bordered_ = nullptr;
+  if (fixed_lookup_ && g.width + 2 <= kFixedMaxSide && g.height + 2 <= kFixedMaxSide) {
+    int kx = 0;
+    while ((1 << kx) < (g.width + 2 + 3) / 4) ++kx;
+    const size_t tile_rows = static_cast<size_t>((g.height + 2 + 3) / 4);
+    std::vector<double> bordered((tile_rows << (kx + 4)), unknown);
+    for (int yi = 0; yi < g.height; ++yi)
+      for (int xi = 0; xi < g.width; ++xi)
+        bordered[bordered_index(static_cast<uint32_t>(xi + 1), static_cast<uint32_t>(yi + 1), kx)] = table[static_cast<size_t>(yi) * g.width + xi];
+    BB_CHECK(dev_alloc(&bordered_, bordered.size()));
+    BB_CHECK(cudaMemcpyAsync(bordered_, bordered.data(), bordered.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    BB_CHECK(cudaStreamSynchronize(stream_));
+    field_.bordered = bordered_;
+    field_.border_kx = kx;
+    field_.use_fixed = 1;
+  }
   field_.tiled = tiled_;
   field_.tiles_x = tiles_x;
   field_.use_tiled = tiled_layout_ ? 1 : 0;

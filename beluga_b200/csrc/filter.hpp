@@ -151,6 +151,7 @@ class Filter {
   static constexpr uint64_t kScheduleMinParticles = 32768;
   bool schedule_enabled_{true};
   bool tiled_layout_{true};
+  bool fixed_lookup_{true};
   double schedule_per_bin_{16.0};
   Schedule* sched_{nullptr};
   uint32_t* bins_{nullptr};
@@ -163,6 +164,7 @@ class Filter {
   std::vector<float> field_host_;
   double* table_{nullptr};
   double* tiled_{nullptr};
+  double* bordered_{nullptr};
   FieldView field_{};
   int8_t* occupancy_{nullptr};
   uint8_t* free_distance_{nullptr};

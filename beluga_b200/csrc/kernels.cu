@@ -440,6 +440,132 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
   publish_weight_max(active ? weight_order_bits(w) : 0ull, &s_max, &s_arrived, kRwThreads / kWarp, scalars);
 }
 
+// ---- reweight, fixed-point cell lookup ----------------------------------------------------------------
+// Same result as reweight_lfm_kernel, fewer instructions per beam.  The reference rounds after every
+// operation of   x = (px*c - py*s) + tx;  cell = floor(x * inv_resolution)   (4 mul, 4 add, 2 mul and
+// 2 floor conversions per beam, all on the FP64 pipe).  The CELL is all that matters, so the kernel
+// evaluates   g = fma(px, c*inv, fma(-py, s*inv, tx*inv + 1))   (2 fma per coordinate; the +1 is the
+// border cell), which differs from the reference's value by d < 2^-36 cells, and adds 1.5*2^36: the
+// sum's low mantissa word is then round-to-nearest(g * 2^16) as a signed 16.16 fixed-point number.
+// If its 16 fraction bits are not all zero, |g - integer| >= 2^-17 > d and floor(reference value) is
+// the integer part, exactly.  If they are all zero (probability 2^-16 per coordinate) the warp redoes
+// the four beams of that group with the reference's own operation sequence.  Out-of-grid end points
+// clamp to the one-cell border holding the unknown-space value, so the load is unconditional.
+// y is carried scaled by 4 so that its bits fall where the 4x4-tile index wants them.
+
+constexpr double kFixedMagic = 103079215104.0;  // 1.5 * 2^36: ulp = 2^-16 for |g| < 2^35
+
+struct FixedParticle {
+  double cx, sx, ox;     // gx + 1   = px*cx - py*sx + ox
+  double sy4, cy4, oy4;  // 4(gy + 1) = px*sy4 + py*cy4 + oy4
+  uint32_t x_max, y_max; // upper clamp of the fixed-point words (as unsigned: negative words clamp there too)
+  uint32_t row_pitch;    // 2^kx: tiles per row
+};
+
+/// `margin` collects the smallest distance-to-cell-edge word seen (0 = an ambiguous coordinate).
+__device__ __forceinline__ double fixed_lookup(const double* __restrict__ bordered, const FixedParticle& q, double px, double py, uint32_t& margin) {
+  const double gx = fma(px, q.cx, fma(-py, q.sx, q.ox)) + kFixedMagic;
+  const double gy = fma(px, q.sy4, fma(py, q.cy4, q.oy4)) + kFixedMagic;
+  const uint32_t wx = static_cast<uint32_t>(__double2loint(gx)), wy = static_cast<uint32_t>(__double2loint(gy));
+  margin = __vimin3_u32(margin, wx << 16, wy << 14);  // zero iff the 16 (x) / 18 (y) fraction bits are all zero
+  // Both borders hold the unknown-space value, so a negative word (huge as unsigned) may clamp to the far one.
+  const uint32_t ux = min(wx, q.x_max) >> 16;  // padded x
+  const uint32_t uy = min(wy, q.y_max) >> 16;  // 4 * padded y + 2 fraction bits
+  const uint32_t a = ux + 3u * (ux & ~3u);     // (x & 3) | ((x >> 2) << 4)
+  const uint32_t idx = (uy & ~0xFu) * q.row_pitch + (a | (uy & 0xCu));
+  return __ldg(bordered + idx);
+}
+
+/// The reference's operation sequence (field_lookup) against the bordered layout.
+__device__ __forceinline__ double bordered_lookup_exact(const FieldView& f, double px, double py, double c, double s, double tx, double ty) {
+  const double x = (px * c - py * s) + tx;
+  const double y = (px * s + py * c) + ty;
+  const double fx = floor(x * f.inv_resolution), fy = floor(y * f.inv_resolution);
+  // saturating: anything outside [-1, side] (NaN included) lands on the border
+  const int xi = (fx >= 0.0 && fx < static_cast<double>(f.width)) ? static_cast<int>(fx) : -1;
+  const int yi = (fy >= 0.0 && fy < static_cast<double>(f.height)) ? static_cast<int>(fy) : -1;
+  return __ldg(f.bordered + bordered_index(static_cast<uint32_t>(xi + 1), static_cast<uint32_t>(yi + 1), f.border_kx));
+}
+
+__global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
+    reweight_lfm_fixed_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
+                              FieldView field, const double2* __restrict__ points, uint32_t n_points, double points_radius,
+                              Scalars* __restrict__ scalars) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* s_pts = reinterpret_cast<double2*>(smem_raw);
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ unsigned long long s_max;
+  __shared__ unsigned int s_arrived;
+
+  const uint64_t slot = static_cast<uint64_t>(blockIdx.x) * kRwThreads + threadIdx.x;
+  const bool active = slot < n;
+  const uint64_t i = active ? (perm != nullptr ? perm[slot] : slot) : 0;
+  if (threadIdx.x == 0) {
+    s_max = 0ull;
+    s_arrived = 0u;
+    mbarrier_init(&s_bar, 1);
+    mbarrier_init_fence();
+  }
+  Pose2 st{1.0, 0.0, 0.0, 0.0};  // idle threads of the last block walk the beams with a dummy pose (full-warp votes below)
+  double w = 0.0;
+  if (active) {
+    st = load_pose(states + i);
+    w = weights[i];
+  }
+  const Pose2 t = pose_mul(field.world_to_field, st);  // likelihood_field_model.hpp:70-74
+  const double inv = field.inv_resolution;
+  // 16.16 fixed point with y scaled by 4: every |cell coordinate| must stay below 2^13.
+  const double reach = (points_radius + fmax(fabs(t.x), fabs(t.y))) * inv + 2.0;
+  const bool in_reach = reach < 8100.0;  // false for NaN
+  FixedParticle q;
+  q.cx = t.c * inv, q.sx = t.s * inv, q.ox = t.x * inv + 1.0;
+  q.sy4 = 4.0 * (t.s * inv), q.cy4 = 4.0 * (t.c * inv), q.oy4 = 4.0 * (t.y * inv + 1.0);
+  q.x_max = (static_cast<uint32_t>(field.width + 1) << 16) | 0xFFFFu;
+  q.y_max = (static_cast<uint32_t>(4 * (field.height + 1) + 3) << 16) | 0xFFFFu;
+  q.row_pitch = 1u << field.border_kx;
+
+  double acc = field.init;
+  uint32_t phase = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_points; base += kChunkBeams) {
+    const uint32_t count = min(kChunkBeams, n_points - base);
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = count * static_cast<uint32_t>(sizeof(double2));
+      mbarrier_expect_tx(&s_bar, bytes);
+      bulk_copy_g2s(s_pts, points + base, bytes, &s_bar);
+    }
+    mbarrier_wait(&s_bar, phase);
+    phase ^= 1u;
+    uint32_t b = 0;
+#pragma unroll kRwUnroll
+    for (; b + 4 <= count; b += 4) {  // libstdc++ transform_reduce groups of four (numeric:439-462)
+      const double2 p0 = s_pts[b], p1 = s_pts[b + 1], p2 = s_pts[b + 2], p3 = s_pts[b + 3];
+      uint32_t margin = in_reach ? 0xFFFFFFFFu : 0u;
+      double f0 = fixed_lookup(field.bordered, q, p0.x, p0.y, margin);
+      double f1 = fixed_lookup(field.bordered, q, p1.x, p1.y, margin);
+      double f2 = fixed_lookup(field.bordered, q, p2.x, p2.y, margin);
+      double f3 = fixed_lookup(field.bordered, q, p3.x, p3.y, margin);
+      if (__any_sync(0xffffffffu, margin == 0u)) {  // some lane sits within 2^-17 cells of a cell edge (or is out of reach)
+        if (margin == 0u) {
+          f0 = bordered_lookup_exact(field, p0.x, p0.y, t.c, t.s, t.x, t.y);
+          f1 = bordered_lookup_exact(field, p1.x, p1.y, t.c, t.s, t.x, t.y);
+          f2 = bordered_lookup_exact(field, p2.x, p2.y, t.c, t.s, t.x, t.y);
+          f3 = bordered_lookup_exact(field, p3.x, p3.y, t.c, t.s, t.x, t.y);
+        }
+      }
+      acc = acc + ((f0 + f1) + (f2 + f3));
+    }
+    for (; b < count; ++b) acc = acc + bordered_lookup_exact(field, s_pts[b].x, s_pts[b].y, t.c, t.s, t.x, t.y);
+    if (base + kChunkBeams < n_points) __syncthreads();
+  }
+  if (active) {
+    const double likelihood = field.exp_epilogue ? exp(acc) : acc;
+    w = w * likelihood;
+    weights[i] = w;
+  }
+  publish_weight_max(active ? weight_order_bits(w) : 0ull, &s_max, &s_arrived, kRwThreads / kWarp, scalars);
+}
+
 // ---- reweight (beam model; a4 + a5) -----------------------------------------------------------
 // BeamSensorModel (sensor/beam_model.hpp:104-150): one thread per particle, beams in the inner
 // loop, so the lanes of a warp (neighbouring particles, same beam) walk rays of similar length.
@@ -1017,7 +1143,10 @@ void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const
   if (n == 0) return;
   const unsigned blocks = static_cast<unsigned>((n + kRwThreads - 1) / kRwThreads);
   const size_t smem = static_cast<size_t>(n_points < kChunkBeams ? n_points : kChunkBeams) * sizeof(double2);
-  if (field.use_tiled) {
+  if (field.use_fixed) {
+    reweight_lfm_fixed_kernel<<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, reinterpret_cast<const double2*>(points_xy_device),
+                                                                    n_points, points_radius, scalars);
+  } else if (field.use_tiled) {
     reweight_lfm_kernel<true><<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, reinterpret_cast<const double2*>(points_xy_device),
                                                                     n_points, points_radius, scalars);
   } else {

@@ -26,7 +26,20 @@ struct FieldView {
   double init;            // transform_reduce init: 1.0 (LFM) or 0.0 (prob)
   int exp_epilogue;       // prob model: weight = exp(sum)
   Pose2 world_to_field;   // grid.origin().inverse()
+  // Bordered 4x4-tile layout for the fixed-point lookup kernel (reweight_lfm_fixed_kernel): the grid
+  // with a one-cell border of unknown_value, cell (xi, yi) stored at padded coordinates
+  // (px, py) = (xi + 1, yi + 1), index bordered_index(px, py, border_kx); 2^border_kx tiles per row.
+  const double* bordered;
+  int border_kx;
+  int use_fixed;          // launch the fixed-point kernel (map small enough for 16.16 cell coordinates)
 };
+
+/// Offset of padded cell (px, py) in the bordered tile layout.
+BB_HD uint32_t bordered_index(uint32_t px, uint32_t py, int kx) {
+  return (((py >> 2) << (kx + 4)) | ((px >> 2) << 4)) | ((py & 3u) << 2) | (px & 3u);
+}
+/// Largest padded grid side the fixed-point kernel accepts (16.16 signed, y pre-scaled by 4).
+constexpr int kFixedMaxSide = 8000;
 
 /// Device view of the occupancy grid (beam model).
 struct OccupancyView {

@@ -140,7 +140,8 @@ def test_reweight_lfm_bit_exact(bb, orc, scene, n_points, sensor):
 
 def test_reweight_far_away_particles(bb, orc, scene):
     """Coordinates beyond the fast floor range take the general path; all land out of the grid."""
-    states = np.array([orc.se2(1e12, -3e11, 0.3), orc.se2(-1e300, 1e300, 1.0), orc.se2(2.0, 2.0, 0.0), orc.se2(5e9, 5e9, 0.0)])
+    states = np.array([orc.se2(1e12, -3e11, 0.3), orc.se2(-1e300, 1e300, 1.0), orc.se2(2.0, 2.0, 0.0), orc.se2(5e9, 5e9, 0.0),
+                       orc.se2(450.0, -430.0, 2.0), orc.se2(-404.9, 3.0, -1.0), orc.se2(3.0, 409.0, 0.5), orc.se2(float("nan"), 1.0, 0.0)])
     pts = np.array([[1.0, 0.5], [2.0, -1.0], [0.1, 0.1], [3.0, 3.0], [0.0, 0.0]])
     params = dict(max_obstacle_distance=2.0, max_laser_distance=100.0, z_hit=0.5, z_random=0.5, sigma_hit=0.2)
     got = gpu_weights(bb, 0, bb.LikelihoodFieldModelParam(**params), scene.cells, scene.resolution, orc.IDENTITY, pts, states)
