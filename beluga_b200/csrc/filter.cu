@@ -108,6 +108,7 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   if (config_.global_count == 0) config_.global_count = config_.capacity;
   if (const char* v = std::getenv("BB200_SCHEDULE")) schedule_enabled_ = std::atoi(v) != 0;  // development knob: 0 disables the pose-sorted schedule
   if (const char* v = std::getenv("BB200_TILED")) tiled_layout_ = std::atoi(v) != 0;         // development knob: table layout
+  if (const char* v = std::getenv("BB200_PARAM_POINTS")) param_points_ = std::atoi(v) != 0;  // development knob: scan as kernel parameters
   if (const char* v = std::getenv("BB200_FIXED")) fixed_lookup_ = std::atoi(v) != 0;         // development knob: fixed-point lookup kernel
   if (const char* v = std::getenv("BB200_PER_BIN")) schedule_per_bin_ = std::atof(v);        // development knob: particles per pose bin
   capacity_ = config.capacity;
@@ -475,6 +476,7 @@ int Filter::set_likelihood_field_map(const bb200_likelihood_field_param& p, cons
     BB_CHECK(cudaStreamSynchronize(stream_));
     field_.bordered = bordered_;
     field_.border_kx = kx;
+    field_.border_pitch = 1u << kx;
     field_.use_fixed = 1;
   }
   field_.tiled = tiled_;
@@ -648,7 +650,8 @@ int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t 
       BB_LAUNCHED("reweight_beam");
     } else {
       mark("reweight_lfm");
-      launch_reweight_lfm(states_[cur_], weights_, n_, perm, field_, points_, static_cast<uint32_t>(n_points), points_radius_, scalars_, stream_);
+      launch_reweight_lfm(states_[cur_], weights_, n_, perm, field_, points_, param_points_ ? points_host_ : nullptr, static_cast<uint32_t>(n_points),
+                          points_radius_, scalars_, stream_);
       BB_LAUNCHED("reweight_lfm");
     }
   }

@@ -152,6 +152,7 @@ class Filter {
   bool schedule_enabled_{true};
   bool tiled_layout_{true};
   bool fixed_lookup_{true};
+  bool param_points_{true};
   double schedule_per_bin_{16.0};
   Schedule* sched_{nullptr};
   uint32_t* bins_{nullptr};

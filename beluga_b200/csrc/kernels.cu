@@ -17,6 +17,8 @@
 // reference's operation order without FMA contraction (the file is compiled with -fmad=false).
 #include "kernels.cuh"
 
+#include <cstring>
+
 // Tuning knobs of the reweight kernel (overridable with -D from beluga_b200/build.py).
 #ifndef BB200_RW_THREADS
 #define BB200_RW_THREADS 256
@@ -467,12 +469,14 @@ __device__ __forceinline__ double fixed_lookup(const double* __restrict__ border
   const double gx = fma(px, q.cx, fma(-py, q.sx, q.ox)) + kFixedMagic;
   const double gy = fma(px, q.sy4, fma(py, q.cy4, q.oy4)) + kFixedMagic;
   const uint32_t wx = static_cast<uint32_t>(__double2loint(gx)), wy = static_cast<uint32_t>(__double2loint(gy));
-  margin = __vimin3_u32(margin, wx << 16, wy << 14);  // zero iff the 16 (x) / 18 (y) fraction bits are all zero
+  // Low halfword = the 16 fraction bits (y: the low 16 of its 18 -- a superset of the ambiguous cases).
+  // One packed-halfword min3 tracks the smallest fraction word seen; the high halfwords are ignored.
+  margin = __vimin3_u16x2(margin, wx, wy);
   // Both borders hold the unknown-space value, so a negative word (huge as unsigned) may clamp to the far one.
   const uint32_t ux = min(wx, q.x_max) >> 16;  // padded x
   const uint32_t uy = min(wy, q.y_max) >> 16;  // 4 * padded y + 2 fraction bits
   const uint32_t a = ux + 3u * (ux & ~3u);     // (x & 3) | ((x >> 2) << 4)
-  const uint32_t idx = (uy & ~0xFu) * q.row_pitch + (a | (uy & 0xCu));
+  const uint32_t idx = __umul24(uy & ~0xFu, q.row_pitch) + (a | (uy & 0xCu));
   return __ldg(bordered + idx);
 }
 
@@ -487,10 +491,38 @@ __device__ __forceinline__ double bordered_lookup_exact(const FieldView& f, doub
   return __ldg(f.bordered + bordered_index(static_cast<uint32_t>(xi + 1), static_cast<uint32_t>(yi + 1), f.border_kx));
 }
 
+/// Scan points as a kernel parameter: they sit in the constant bank, where the FP64 instructions read
+/// them as direct operands -- no shared-memory load per beam and no L1 data-pipe traffic.  30 KB of
+/// the 32 KB parameter space; longer scans take the shared-memory (TMA) variant.
+constexpr uint32_t kParamBeams = 1920;
+struct ScanParam {
+  double2 p[kParamBeams];
+};
+
+#define BB200_FIXED_GROUP(P0, P1, P2, P3)                                                                   \
+  do {                                                                                                      \
+    const double2 p0 = (P0), p1 = (P1), p2 = (P2), p3 = (P3);                                               \
+    uint32_t margin = in_reach ? 0xFFFFFFFFu : 0u;                                                          \
+    double f0 = fixed_lookup(field.bordered, q, p0.x, p0.y, margin);                                        \
+    double f1 = fixed_lookup(field.bordered, q, p1.x, p1.y, margin);                                        \
+    double f2 = fixed_lookup(field.bordered, q, p2.x, p2.y, margin);                                        \
+    double f3 = fixed_lookup(field.bordered, q, p3.x, p3.y, margin);                                        \
+    if (__any_sync(0xffffffffu, (margin & 0xFFFFu) == 0u)) { /* a lane within 2^-17 cells of an edge, or out of reach */ \
+      if ((margin & 0xFFFFu) == 0u) {                                                                                \
+        f0 = bordered_lookup_exact(field, p0.x, p0.y, t.c, t.s, t.x, t.y);                                  \
+        f1 = bordered_lookup_exact(field, p1.x, p1.y, t.c, t.s, t.x, t.y);                                  \
+        f2 = bordered_lookup_exact(field, p2.x, p2.y, t.c, t.s, t.x, t.y);                                  \
+        f3 = bordered_lookup_exact(field, p3.x, p3.y, t.c, t.s, t.x, t.y);                                  \
+      }                                                                                                     \
+    }                                                                                                       \
+    acc = acc + ((f0 + f1) + (f2 + f3)); /* libstdc++ transform_reduce groups of four (numeric:439-462) */  \
+  } while (0)
+
+template <bool kFromParams>
 __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     reweight_lfm_fixed_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
                               FieldView field, const double2* __restrict__ points, uint32_t n_points, double points_radius,
-                              Scalars* __restrict__ scalars) {
+                              Scalars* __restrict__ scalars, const __grid_constant__ ScanParam scan) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* s_pts = reinterpret_cast<double2*>(smem_raw);
   __shared__ __align__(8) uint64_t s_bar;
@@ -503,8 +535,10 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
   if (threadIdx.x == 0) {
     s_max = 0ull;
     s_arrived = 0u;
-    mbarrier_init(&s_bar, 1);
-    mbarrier_init_fence();
+    if (!kFromParams) {
+      mbarrier_init(&s_bar, 1);
+      mbarrier_init_fence();
+    }
   }
   Pose2 st{1.0, 0.0, 0.0, 0.0};  // idle threads of the last block walk the beams with a dummy pose (full-warp votes below)
   double w = 0.0;
@@ -522,41 +556,32 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
   q.sy4 = 4.0 * (t.s * inv), q.cy4 = 4.0 * (t.c * inv), q.oy4 = 4.0 * (t.y * inv + 1.0);
   q.x_max = (static_cast<uint32_t>(field.width + 1) << 16) | 0xFFFFu;
   q.y_max = (static_cast<uint32_t>(4 * (field.height + 1) + 3) << 16) | 0xFFFFu;
-  q.row_pitch = 1u << field.border_kx;
+  q.row_pitch = field.border_pitch;
 
   double acc = field.init;
-  uint32_t phase = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < n_points; base += kChunkBeams) {
-    const uint32_t count = min(kChunkBeams, n_points - base);
-    if (threadIdx.x == 0) {
-      const uint32_t bytes = count * static_cast<uint32_t>(sizeof(double2));
-      mbarrier_expect_tx(&s_bar, bytes);
-      bulk_copy_g2s(s_pts, points + base, bytes, &s_bar);
-    }
-    mbarrier_wait(&s_bar, phase);
-    phase ^= 1u;
+  __syncthreads();  // s_max (and the barrier) initialised
+  if (kFromParams) {
     uint32_t b = 0;
 #pragma unroll kRwUnroll
-    for (; b + 4 <= count; b += 4) {  // libstdc++ transform_reduce groups of four (numeric:439-462)
-      const double2 p0 = s_pts[b], p1 = s_pts[b + 1], p2 = s_pts[b + 2], p3 = s_pts[b + 3];
-      uint32_t margin = in_reach ? 0xFFFFFFFFu : 0u;
-      double f0 = fixed_lookup(field.bordered, q, p0.x, p0.y, margin);
-      double f1 = fixed_lookup(field.bordered, q, p1.x, p1.y, margin);
-      double f2 = fixed_lookup(field.bordered, q, p2.x, p2.y, margin);
-      double f3 = fixed_lookup(field.bordered, q, p3.x, p3.y, margin);
-      if (__any_sync(0xffffffffu, margin == 0u)) {  // some lane sits within 2^-17 cells of a cell edge (or is out of reach)
-        if (margin == 0u) {
-          f0 = bordered_lookup_exact(field, p0.x, p0.y, t.c, t.s, t.x, t.y);
-          f1 = bordered_lookup_exact(field, p1.x, p1.y, t.c, t.s, t.x, t.y);
-          f2 = bordered_lookup_exact(field, p2.x, p2.y, t.c, t.s, t.x, t.y);
-          f3 = bordered_lookup_exact(field, p3.x, p3.y, t.c, t.s, t.x, t.y);
-        }
+    for (; b + 4 <= n_points; b += 4) BB200_FIXED_GROUP(scan.p[b], scan.p[b + 1], scan.p[b + 2], scan.p[b + 3]);
+    for (; b < n_points; ++b) acc = acc + bordered_lookup_exact(field, scan.p[b].x, scan.p[b].y, t.c, t.s, t.x, t.y);
+  } else {
+    uint32_t phase = 0;
+    for (uint32_t base = 0; base < n_points; base += kChunkBeams) {
+      const uint32_t count = min(kChunkBeams, n_points - base);
+      if (threadIdx.x == 0) {
+        const uint32_t bytes = count * static_cast<uint32_t>(sizeof(double2));
+        mbarrier_expect_tx(&s_bar, bytes);
+        bulk_copy_g2s(s_pts, points + base, bytes, &s_bar);
       }
-      acc = acc + ((f0 + f1) + (f2 + f3));
+      mbarrier_wait(&s_bar, phase);
+      phase ^= 1u;
+      uint32_t b = 0;
+#pragma unroll kRwUnroll
+      for (; b + 4 <= count; b += 4) BB200_FIXED_GROUP(s_pts[b], s_pts[b + 1], s_pts[b + 2], s_pts[b + 3]);
+      for (; b < count; ++b) acc = acc + bordered_lookup_exact(field, s_pts[b].x, s_pts[b].y, t.c, t.s, t.x, t.y);
+      if (base + kChunkBeams < n_points) __syncthreads();
     }
-    for (; b < count; ++b) acc = acc + bordered_lookup_exact(field, s_pts[b].x, s_pts[b].y, t.c, t.s, t.x, t.y);
-    if (base + kChunkBeams < n_points) __syncthreads();
   }
   if (active) {
     const double likelihood = field.exp_epilogue ? exp(acc) : acc;
@@ -565,6 +590,7 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
   }
   publish_weight_max(active ? weight_order_bits(w) : 0ull, &s_max, &s_arrived, kRwThreads / kWarp, scalars);
 }
+#undef BB200_FIXED_GROUP
 
 // ---- reweight (beam model; a4 + a5) -----------------------------------------------------------
 // BeamSensorModel (sensor/beam_model.hpp:104-150): one thread per particle, beams in the inner
@@ -1139,19 +1165,24 @@ void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uin
 }
 
 void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const FieldView& field,
-                         const double* points_xy_device, uint32_t n_points, double points_radius, Scalars* scalars, cudaStream_t stream) {
+                         const double* points_xy_device, const double* points_xy_host, uint32_t n_points, double points_radius, Scalars* scalars,
+                         cudaStream_t stream) {
   if (n == 0) return;
   const unsigned blocks = static_cast<unsigned>((n + kRwThreads - 1) / kRwThreads);
   const size_t smem = static_cast<size_t>(n_points < kChunkBeams ? n_points : kChunkBeams) * sizeof(double2);
+  const double2* points = reinterpret_cast<const double2*>(points_xy_device);
   if (field.use_fixed) {
-    reweight_lfm_fixed_kernel<<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, reinterpret_cast<const double2*>(points_xy_device),
-                                                                    n_points, points_radius, scalars);
+    static thread_local ScanParam scan;  // launch parameters are copied at launch time
+    if (points_xy_host != nullptr && n_points <= kParamBeams) {
+      std::memcpy(scan.p, points_xy_host, static_cast<size_t>(n_points) * sizeof(double2));
+      reweight_lfm_fixed_kernel<true><<<blocks, kRwThreads, 0, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars, scan);
+    } else {
+      reweight_lfm_fixed_kernel<false><<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars, scan);
+    }
   } else if (field.use_tiled) {
-    reweight_lfm_kernel<true><<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, reinterpret_cast<const double2*>(points_xy_device),
-                                                                    n_points, points_radius, scalars);
+    reweight_lfm_kernel<true><<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars);
   } else {
-    reweight_lfm_kernel<false><<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, reinterpret_cast<const double2*>(points_xy_device),
-                                                                     n_points, points_radius, scalars);
+    reweight_lfm_kernel<false><<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars);
   }
 }
 
