@@ -111,6 +111,7 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   if (const char* v = std::getenv("BB200_PARAM_POINTS")) param_points_ = std::atoi(v) != 0;  // development knob: scan as kernel parameters
   if (const char* v = std::getenv("BB200_FIXED")) fixed_lookup_ = std::atoi(v) != 0;         // development knob: fixed-point lookup kernel
   if (const char* v = std::getenv("BB200_PER_BIN")) schedule_per_bin_ = std::atof(v);        // development knob: particles per pose bin
+  if (const char* v = std::getenv("BB200_LEVER")) schedule_lever_ = std::atof(v);            // development knob: heading lever arm / mean range
   capacity_ = config.capacity;
 #define BB_TRY(expr)                                \
   do {                                              \
@@ -477,6 +478,8 @@ int Filter::set_likelihood_field_map(const bb200_likelihood_field_param& p, cons
     field_.bordered = bordered_;
     field_.border_kx = kx;
     field_.border_pitch = 1u << kx;
+    field_.border_x_max = (static_cast<uint32_t>(g.width + 1) << 16) | 0xFFFFu;
+    field_.border_y_max = (static_cast<uint32_t>(4 * (g.height + 1) + 3) << 16) | 0xFFFFu;
     field_.use_fixed = 1;
   }
   field_.tiled = tiled_;
@@ -639,7 +642,7 @@ int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t 
   const uint32_t* perm = nullptr;
   if (scheduled) {
     mark("schedule");
-    launch_build_schedule(states_[cur_], n_, sched_, bins_, counters_, perm_, sched_tiles_, points_mean_range_, 0.5 * grid_resolution_, schedule_per_bin_, stream_);
+    launch_build_schedule(states_[cur_], n_, sched_, bins_, counters_, perm_, sched_tiles_, schedule_lever_ * points_mean_range_, 0.5 * grid_resolution_, schedule_per_bin_, stream_);
     BB_LAUNCHED_N("schedule", 4);
     perm = perm_;
   }

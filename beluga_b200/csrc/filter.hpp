@@ -154,6 +154,7 @@ class Filter {
   bool fixed_lookup_{true};
   bool param_points_{true};
   double schedule_per_bin_{16.0};
+  double schedule_lever_{1.0};
   Schedule* sched_{nullptr};
   uint32_t* bins_{nullptr};
   uint32_t* perm_{nullptr};

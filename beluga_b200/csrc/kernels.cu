@@ -27,7 +27,7 @@
 #define BB200_RW_UNROLL 2
 #endif
 #ifndef BB200_RW_BLOCKS
-#define BB200_RW_BLOCKS 3
+#define BB200_RW_BLOCKS 4
 #endif
 
 #include <algorithm>
@@ -453,21 +453,23 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
 // the integer part, exactly.  If they are all zero (probability 2^-16 per coordinate) the warp redoes
 // the four beams of that group with the reference's own operation sequence.  Out-of-grid end points
 // clamp to the one-cell border holding the unknown-space value, so the load is unconditional.
-// y is carried scaled by 4 so that its bits fall where the 4x4-tile index wants them.
+// y uses 18 fraction bits (magic 1.5*2^34), so its word reads as 4*y in 16.16 and its bits fall where
+// the 4x4-tile index wants them.
 
-constexpr double kFixedMagic = 103079215104.0;  // 1.5 * 2^36: ulp = 2^-16 for |g| < 2^35
+constexpr double kFixedMagicX = 103079215104.0;  // 1.5 * 2^36: ulp 2^-16 -> low word = 16.16 fixed point
+constexpr double kFixedMagicY = 25769803776.0;   // 1.5 * 2^34: ulp 2^-18 -> low word = 14.18, i.e. 4*y as 16.16
 
 struct FixedParticle {
-  double cx, sx, ox;     // gx + 1   = px*cx - py*sx + ox
-  double sy4, cy4, oy4;  // 4(gy + 1) = px*sy4 + py*cy4 + oy4
+  double cx, sx;         // cos, sin of the field-frame heading, times 1/resolution
+  double ox, oy;         // field-frame position in cells, plus the border cell
   uint32_t x_max, y_max; // upper clamp of the fixed-point words (as unsigned: negative words clamp there too)
   uint32_t row_pitch;    // 2^kx: tiles per row
 };
 
 /// `margin` collects the smallest distance-to-cell-edge word seen (0 = an ambiguous coordinate).
 __device__ __forceinline__ double fixed_lookup(const double* __restrict__ bordered, const FixedParticle& q, double px, double py, uint32_t& margin) {
-  const double gx = fma(px, q.cx, fma(-py, q.sx, q.ox)) + kFixedMagic;
-  const double gy = fma(px, q.sy4, fma(py, q.cy4, q.oy4)) + kFixedMagic;
+  const double gx = fma(px, q.cx, fma(-py, q.sx, q.ox)) + kFixedMagicX;  // gx + 1
+  const double gy = fma(px, q.sx, fma(py, q.cx, q.oy)) + kFixedMagicY;   // gy + 1
   const uint32_t wx = static_cast<uint32_t>(__double2loint(gx)), wy = static_cast<uint32_t>(__double2loint(gy));
   // Low halfword = the 16 fraction bits (y: the low 16 of its 18 -- a superset of the ambiguous cases).
   // One packed-halfword min3 tracks the smallest fraction word seen; the high halfwords are ignored.
@@ -491,6 +493,11 @@ __device__ __forceinline__ double bordered_lookup_exact(const FieldView& f, doub
   return __ldg(f.bordered + bordered_index(static_cast<uint32_t>(xi + 1), static_cast<uint32_t>(yi + 1), f.border_kx));
 }
 
+/// transform = world_to_likelihood_field * state (likelihood_field_model.hpp:70-74); idle threads use the identity.
+__device__ __forceinline__ Pose2 field_frame_pose(const FieldView& f, const Pose2* __restrict__ states, uint64_t i, bool active) {
+  return pose_mul(f.world_to_field, active ? load_pose(states + i) : Pose2{1.0, 0.0, 0.0, 0.0});
+}
+
 /// Scan points as a kernel parameter: they sit in the constant bank, where the FP64 instructions read
 /// them as direct operands -- no shared-memory load per beam and no L1 data-pipe traffic.  30 KB of
 /// the 32 KB parameter space; longer scans take the shared-memory (TMA) variant.
@@ -502,17 +509,18 @@ struct ScanParam {
 #define BB200_FIXED_GROUP(P0, P1, P2, P3)                                                                   \
   do {                                                                                                      \
     const double2 p0 = (P0), p1 = (P1), p2 = (P2), p3 = (P3);                                               \
-    uint32_t margin = in_reach ? 0xFFFFFFFFu : 0u;                                                          \
+    uint32_t margin = margin_start;                                                                         \
     double f0 = fixed_lookup(field.bordered, q, p0.x, p0.y, margin);                                        \
     double f1 = fixed_lookup(field.bordered, q, p1.x, p1.y, margin);                                        \
     double f2 = fixed_lookup(field.bordered, q, p2.x, p2.y, margin);                                        \
     double f3 = fixed_lookup(field.bordered, q, p3.x, p3.y, margin);                                        \
     if (__any_sync(0xffffffffu, (margin & 0xFFFFu) == 0u)) { /* a lane within 2^-17 cells of an edge, or out of reach */ \
       if ((margin & 0xFFFFu) == 0u) {                                                                                \
-        f0 = bordered_lookup_exact(field, p0.x, p0.y, t.c, t.s, t.x, t.y);                                  \
-        f1 = bordered_lookup_exact(field, p1.x, p1.y, t.c, t.s, t.x, t.y);                                  \
-        f2 = bordered_lookup_exact(field, p2.x, p2.y, t.c, t.s, t.x, t.y);                                  \
-        f3 = bordered_lookup_exact(field, p3.x, p3.y, t.c, t.s, t.x, t.y);                                  \
+        const Pose2 te = field_frame_pose(field, states, i, active);                                        \
+        f0 = bordered_lookup_exact(field, p0.x, p0.y, te.c, te.s, te.x, te.y);                              \
+        f1 = bordered_lookup_exact(field, p1.x, p1.y, te.c, te.s, te.x, te.y);                              \
+        f2 = bordered_lookup_exact(field, p2.x, p2.y, te.c, te.s, te.x, te.y);                              \
+        f3 = bordered_lookup_exact(field, p3.x, p3.y, te.c, te.s, te.x, te.y);                              \
       }                                                                                                     \
     }                                                                                                       \
     acc = acc + ((f0 + f1) + (f2 + f3)); /* libstdc++ transform_reduce groups of four (numeric:439-462) */  \
@@ -540,23 +548,21 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
       mbarrier_init_fence();
     }
   }
-  Pose2 st{1.0, 0.0, 0.0, 0.0};  // idle threads of the last block walk the beams with a dummy pose (full-warp votes below)
-  double w = 0.0;
-  if (active) {
-    st = load_pose(states + i);
-    w = weights[i];
-  }
-  const Pose2 t = pose_mul(field.world_to_field, st);  // likelihood_field_model.hpp:70-74
-  const double inv = field.inv_resolution;
-  // 16.16 fixed point with y scaled by 4: every |cell coordinate| must stay below 2^13.
-  const double reach = (points_radius + fmax(fabs(t.x), fabs(t.y))) * inv + 2.0;
-  const bool in_reach = reach < 8100.0;  // false for NaN
+  // Idle threads of the last block walk the beams with a dummy pose (the votes below are full-warp).
+  bool in_reach;
   FixedParticle q;
-  q.cx = t.c * inv, q.sx = t.s * inv, q.ox = t.x * inv + 1.0;
-  q.sy4 = 4.0 * (t.s * inv), q.cy4 = 4.0 * (t.c * inv), q.oy4 = 4.0 * (t.y * inv + 1.0);
-  q.x_max = (static_cast<uint32_t>(field.width + 1) << 16) | 0xFFFFu;
-  q.y_max = (static_cast<uint32_t>(4 * (field.height + 1) + 3) << 16) | 0xFFFFu;
+  {
+    const Pose2 t = field_frame_pose(field, states, i, active);
+    const double inv = field.inv_resolution;
+    // 16.16 fixed point with y scaled by 4: every |cell coordinate| must stay below 2^13.
+    const double reach = (points_radius + fmax(fabs(t.x), fabs(t.y))) * inv + 2.0;
+    in_reach = reach < 8100.0;  // false for NaN
+    q.cx = t.c * inv, q.sx = t.s * inv, q.ox = t.x * inv + 1.0, q.oy = t.y * inv + 1.0;
+  }
+  q.x_max = field.border_x_max;
+  q.y_max = field.border_y_max;
   q.row_pitch = field.border_pitch;
+  const uint32_t margin_start = in_reach ? 0xFFFFFFFFu : 0u;
 
   double acc = field.init;
   __syncthreads();  // s_max (and the barrier) initialised
@@ -564,7 +570,10 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     uint32_t b = 0;
 #pragma unroll kRwUnroll
     for (; b + 4 <= n_points; b += 4) BB200_FIXED_GROUP(scan.p[b], scan.p[b + 1], scan.p[b + 2], scan.p[b + 3]);
-    for (; b < n_points; ++b) acc = acc + bordered_lookup_exact(field, scan.p[b].x, scan.p[b].y, t.c, t.s, t.x, t.y);
+    if (b < n_points) {
+      const Pose2 te = field_frame_pose(field, states, i, active);
+      for (; b < n_points; ++b) acc = acc + bordered_lookup_exact(field, scan.p[b].x, scan.p[b].y, te.c, te.s, te.x, te.y);
+    }
   } else {
     uint32_t phase = 0;
     for (uint32_t base = 0; base < n_points; base += kChunkBeams) {
@@ -579,13 +588,17 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
       uint32_t b = 0;
 #pragma unroll kRwUnroll
       for (; b + 4 <= count; b += 4) BB200_FIXED_GROUP(s_pts[b], s_pts[b + 1], s_pts[b + 2], s_pts[b + 3]);
-      for (; b < count; ++b) acc = acc + bordered_lookup_exact(field, s_pts[b].x, s_pts[b].y, t.c, t.s, t.x, t.y);
+      if (b < count) {
+        const Pose2 te = field_frame_pose(field, states, i, active);
+        for (; b < count; ++b) acc = acc + bordered_lookup_exact(field, s_pts[b].x, s_pts[b].y, te.c, te.s, te.x, te.y);
+      }
       if (base + kChunkBeams < n_points) __syncthreads();
     }
   }
+  double w = 0.0;
   if (active) {
     const double likelihood = field.exp_epilogue ? exp(acc) : acc;
-    w = w * likelihood;
+    w = weights[i] * likelihood;  // actions/reweight.hpp:54-60
     weights[i] = w;
   }
   publish_weight_max(active ? weight_order_bits(w) : 0ull, &s_max, &s_arrived, kRwThreads / kWarp, scalars);

@@ -32,6 +32,8 @@ struct FieldView {
   const double* bordered;
   int border_kx;
   uint32_t border_pitch;  // 2^border_kx
+  uint32_t border_x_max;  // ((width + 1) << 16) | 0xFFFF: largest 16.16 word of a padded x
+  uint32_t border_y_max;  // ((4 (height + 1) + 3) << 16) | 0xFFFF: same for 4 * padded y
   int use_fixed;          // launch the fixed-point kernel (map small enough for 16.16 cell coordinates)
 };
 
