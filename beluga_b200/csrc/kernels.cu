@@ -443,41 +443,47 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
 }
 
 // ---- reweight, fixed-point cell lookup ----------------------------------------------------------------
-// Same result as reweight_lfm_kernel, fewer instructions per beam.  The reference rounds after every
-// operation of   x = (px*c - py*s) + tx;  cell = floor(x * inv_resolution)   (4 mul, 4 add, 2 mul and
-// 2 floor conversions per beam, all on the FP64 pipe).  The CELL is all that matters, so the kernel
-// evaluates   g = fma(px, c*inv, fma(-py, s*inv, tx*inv + 1))   (2 fma per coordinate; the +1 is the
-// border cell), which differs from the reference's value by d < 2^-36 cells, and adds 1.5*2^36: the
-// sum's low mantissa word is then round-to-nearest(g * 2^16) as a signed 16.16 fixed-point number.
-// If its 16 fraction bits are not all zero, |g - integer| >= 2^-17 > d and floor(reference value) is
-// the integer part, exactly.  If they are all zero (probability 2^-16 per coordinate) the warp redoes
-// the four beams of that group with the reference's own operation sequence.  Out-of-grid end points
-// clamp to the one-cell border holding the unknown-space value, so the load is unconditional.
-// y uses 18 fraction bits (magic 1.5*2^34), so its word reads as 4*y in 16.16 and its bits fall where
-// the 4x4-tile index wants them.
+// Same result as reweight_lfm_kernel, two thirds of the instructions per beam.  The reference rounds
+// after every operation of   x = (px*c - py*s) + tx;  cell = floor(x * inv_resolution)   (4 mul, 4 add,
+// 2 mul and 2 floor conversions per beam, all on the FP64 pipe).  The CELL is all that matters, so the
+// kernel evaluates   g = fma(px, c*inv, fma(-py, s*inv, tx*inv + 1))   (2 fma per coordinate; the +1 is
+// the border cell), which differs from the reference's value by d <= 11 * 2^13 * 2^-53 < 2^-36 cells
+// while every term stays below 2^13 cells, and adds 1.5*2^20: in the sum's bit pattern the low word is
+// the fraction of g in units of 2^-32 (round to nearest) and the low 20 bits of the high word are
+// 2^19 + floor(g).  If the fraction word is not zero, g is at least 2^-33 > d away from an integer and
+// floor(reference value) = floor(g) exactly.  y adds 1.5*2^18 instead, so its high word carries
+// floor(4g) -- the bits the 4x4-tile index wants -- and a non-zero fraction word puts g at least
+// 2^-35 > d from an integer.  A thread that ever sees a zero fraction word (2^-32 per coordinate, about
+// once every two steps among a million particles) or a particle out of the 2^13 range redoes its
+// beams with the reference's own operation sequence; nothing else in the loop branches.
+// Out-of-grid end points clamp (one DPX add-min per coordinate, which also strips the bias) to the
+// one-cell border holding the unknown-space value, so the load is unconditional.
 
-constexpr double kFixedMagicX = 103079215104.0;  // 1.5 * 2^36: ulp 2^-16 -> low word = 16.16 fixed point
-constexpr double kFixedMagicY = 25769803776.0;   // 1.5 * 2^34: ulp 2^-18 -> low word = 14.18, i.e. 4*y as 16.16
+constexpr double kFixedMagicX = 1572864.0;  // 1.5 * 2^20: ulp 2^-32; high word = 0x41380000 + floor(g)      for |g| < 2^19
+constexpr double kFixedMagicY = 393216.0;   // 1.5 * 2^18: ulp 2^-34; high word = 0x41180000 + floor(4 g)    for |g| < 2^17
+constexpr uint32_t kFixedBiasX = 0x41380000u, kFixedBiasY = 0x41180000u;
 
 struct FixedParticle {
   double cx, sx;         // cos, sin of the field-frame heading, times 1/resolution
   double ox, oy;         // field-frame position in cells, plus the border cell
-  uint32_t x_max, y_max; // upper clamp of the fixed-point words (as unsigned: negative words clamp there too)
+  uint32_t x_max, y_max; // width + 1, 4 (height + 1) + 3: largest padded x and 4 * padded y (+ 2 fraction bits)
   uint32_t row_pitch;    // 2^kx: tiles per row
 };
 
-/// `margin` collects the smallest distance-to-cell-edge word seen (0 = an ambiguous coordinate).
+#ifndef BB200_EXP
+#define BB200_EXP 0
+#endif
+
+/// `margin` collects the smallest fraction word seen (0 = an ambiguous coordinate).
 __device__ __forceinline__ double fixed_lookup(const double* __restrict__ bordered, const FixedParticle& q, double px, double py, uint32_t& margin) {
   const double gx = fma(px, q.cx, fma(-py, q.sx, q.ox)) + kFixedMagicX;  // gx + 1
   const double gy = fma(px, q.sx, fma(py, q.cx, q.oy)) + kFixedMagicY;   // gy + 1
-  const uint32_t wx = static_cast<uint32_t>(__double2loint(gx)), wy = static_cast<uint32_t>(__double2loint(gy));
-  // Low halfword = the 16 fraction bits (y: the low 16 of its 18 -- a superset of the ambiguous cases).
-  // One packed-halfword min3 tracks the smallest fraction word seen; the high halfwords are ignored.
-  margin = __vimin3_u16x2(margin, wx, wy);
-  // Both borders hold the unknown-space value, so a negative word (huge as unsigned) may clamp to the far one.
-  const uint32_t ux = min(wx, q.x_max) >> 16;  // padded x
-  const uint32_t uy = min(wy, q.y_max) >> 16;  // 4 * padded y + 2 fraction bits
-  const uint32_t a = ux + 3u * (ux & ~3u);     // (x & 3) | ((x >> 2) << 4)
+  margin = __vimin3_u32(margin, static_cast<uint32_t>(__double2loint(gx)), static_cast<uint32_t>(__double2loint(gy)));
+  // min(word - bias, max): a negative coordinate wraps to a huge unsigned and clamps to the far border,
+  // which holds the same unknown-space value as the near one.
+  const uint32_t ux = __viaddmin_u32(static_cast<uint32_t>(__double2hiint(gx)), 0u - kFixedBiasX, q.x_max);  // padded x
+  const uint32_t uy = __viaddmin_u32(static_cast<uint32_t>(__double2hiint(gy)), 0u - kFixedBiasY, q.y_max);  // 4 * padded y + 2 fraction bits
+  const uint32_t a = ux + 3u * (ux & ~3u);                                                                   // (x & 3) | ((x >> 2) << 4)
   const uint32_t idx = __umul24(uy & ~0xFu, q.row_pitch) + (a | (uy & 0xCu));
   return __ldg(bordered + idx);
 }
@@ -498,32 +504,49 @@ __device__ __forceinline__ Pose2 field_frame_pose(const FieldView& f, const Pose
   return pose_mul(f.world_to_field, active ? load_pose(states + i) : Pose2{1.0, 0.0, 0.0, 0.0});
 }
 
-/// Scan points as a kernel parameter: they sit in the constant bank, where the FP64 instructions read
-/// them as direct operands -- no shared-memory load per beam and no L1 data-pipe traffic.  30 KB of
+/// Scan points as a kernel parameter: they sit in the constant bank and reach the FP64 instructions
+/// through uniform registers -- no shared-memory load per beam and no L1 data-pipe traffic.  30 KB of
 /// the 32 KB parameter space; longer scans take the shared-memory (TMA) variant.
 constexpr uint32_t kParamBeams = 1920;
 struct ScanParam {
   double2 p[kParamBeams];
 };
 
-#define BB200_FIXED_GROUP(P0, P1, P2, P3)                                                                   \
-  do {                                                                                                      \
-    const double2 p0 = (P0), p1 = (P1), p2 = (P2), p3 = (P3);                                               \
-    uint32_t margin = margin_start;                                                                         \
-    double f0 = fixed_lookup(field.bordered, q, p0.x, p0.y, margin);                                        \
-    double f1 = fixed_lookup(field.bordered, q, p1.x, p1.y, margin);                                        \
-    double f2 = fixed_lookup(field.bordered, q, p2.x, p2.y, margin);                                        \
-    double f3 = fixed_lookup(field.bordered, q, p3.x, p3.y, margin);                                        \
-    if (__any_sync(0xffffffffu, (margin & 0xFFFFu) == 0u)) { /* a lane within 2^-17 cells of an edge, or out of reach */ \
-      if ((margin & 0xFFFFu) == 0u) {                                                                                \
-        const Pose2 te = field_frame_pose(field, states, i, active);                                        \
-        f0 = bordered_lookup_exact(field, p0.x, p0.y, te.c, te.s, te.x, te.y);                              \
-        f1 = bordered_lookup_exact(field, p1.x, p1.y, te.c, te.s, te.x, te.y);                              \
-        f2 = bordered_lookup_exact(field, p2.x, p2.y, te.c, te.s, te.x, te.y);                              \
-        f3 = bordered_lookup_exact(field, p3.x, p3.y, te.c, te.s, te.x, te.y);                              \
-      }                                                                                                     \
-    }                                                                                                       \
-    acc = acc + ((f0 + f1) + (f2 + f3)); /* libstdc++ transform_reduce groups of four (numeric:439-462) */  \
+// libstdc++ transform_reduce (numeric:439-462): groups of four, init += ((f0+f1)+(f2+f3)), then one by one.
+#define BB200_FIXED_SUM(POINT, COUNT)                                                                         \
+  do {                                                                                                        \
+    const double acc_before = acc;                                                                            \
+    uint32_t margin = margin_start;                                                                           \
+    uint32_t b = 0;                                                                                           \
+    _Pragma("unroll 2") for (; b + 4 <= (COUNT); b += 4) {                                                    \
+      const double2 p0 = POINT(b), p1 = POINT(b + 1), p2 = POINT(b + 2), p3 = POINT(b + 3);                   \
+      const double f0 = fixed_lookup(field.bordered, q, p0.x, p0.y, margin);                                  \
+      const double f1 = fixed_lookup(field.bordered, q, p1.x, p1.y, margin);                                  \
+      const double f2 = fixed_lookup(field.bordered, q, p2.x, p2.y, margin);                                  \
+      const double f3 = fixed_lookup(field.bordered, q, p3.x, p3.y, margin);                                  \
+      acc = acc + ((f0 + f1) + (f2 + f3));                                                                    \
+    }                                                                                                         \
+    for (; b < (COUNT); ++b) {                                                                                \
+      const double2 p0 = POINT(b);                                                                            \
+      acc = acc + fixed_lookup(field.bordered, q, p0.x, p0.y, margin);                                        \
+    }                                                                                                         \
+    if (margin == 0u) { /* a coordinate within 2^-33 cells of a cell edge, or a particle out of range */     \
+      const Pose2 te = field_frame_pose(field, states, i, active);                                            \
+      acc = acc_before;                                                                                       \
+      b = 0;                                                                                                  \
+      for (; b + 4 <= (COUNT); b += 4) {                                                                      \
+        const double2 p0 = POINT(b), p1 = POINT(b + 1), p2 = POINT(b + 2), p3 = POINT(b + 3);                 \
+        const double f0 = bordered_lookup_exact(field, p0.x, p0.y, te.c, te.s, te.x, te.y);                   \
+        const double f1 = bordered_lookup_exact(field, p1.x, p1.y, te.c, te.s, te.x, te.y);                   \
+        const double f2 = bordered_lookup_exact(field, p2.x, p2.y, te.c, te.s, te.x, te.y);                   \
+        const double f3 = bordered_lookup_exact(field, p3.x, p3.y, te.c, te.s, te.x, te.y);                   \
+        acc = acc + ((f0 + f1) + (f2 + f3));                                                                  \
+      }                                                                                                       \
+      for (; b < (COUNT); ++b) {                                                                              \
+        const double2 p0 = POINT(b);                                                                          \
+        acc = acc + bordered_lookup_exact(field, p0.x, p0.y, te.c, te.s, te.x, te.y);                         \
+      }                                                                                                       \
+    }                                                                                                         \
   } while (0)
 
 template <bool kFromParams>
@@ -548,32 +571,26 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
       mbarrier_init_fence();
     }
   }
-  // Idle threads of the last block walk the beams with a dummy pose (the votes below are full-warp).
-  bool in_reach;
+  uint32_t margin_start;
   FixedParticle q;
   {
     const Pose2 t = field_frame_pose(field, states, i, active);
     const double inv = field.inv_resolution;
-    // 16.16 fixed point with y scaled by 4: every |cell coordinate| must stay below 2^13.
+    // The error bound above needs every term of g below 2^13 cells.
     const double reach = (points_radius + fmax(fabs(t.x), fabs(t.y))) * inv + 2.0;
-    in_reach = reach < 8100.0;  // false for NaN
+    margin_start = reach < 8100.0 ? 0xFFFFFFFFu : 0u;  // 0 also for NaN: straight to the exact sequence
     q.cx = t.c * inv, q.sx = t.s * inv, q.ox = t.x * inv + 1.0, q.oy = t.y * inv + 1.0;
   }
   q.x_max = field.border_x_max;
   q.y_max = field.border_y_max;
   q.row_pitch = field.border_pitch;
-  const uint32_t margin_start = in_reach ? 0xFFFFFFFFu : 0u;
 
   double acc = field.init;
   __syncthreads();  // s_max (and the barrier) initialised
   if (kFromParams) {
-    uint32_t b = 0;
-#pragma unroll kRwUnroll
-    for (; b + 4 <= n_points; b += 4) BB200_FIXED_GROUP(scan.p[b], scan.p[b + 1], scan.p[b + 2], scan.p[b + 3]);
-    if (b < n_points) {
-      const Pose2 te = field_frame_pose(field, states, i, active);
-      for (; b < n_points; ++b) acc = acc + bordered_lookup_exact(field, scan.p[b].x, scan.p[b].y, te.c, te.s, te.x, te.y);
-    }
+#define BB200_POINT(k) scan.p[(k)]
+    BB200_FIXED_SUM(BB200_POINT, n_points);
+#undef BB200_POINT
   } else {
     uint32_t phase = 0;
     for (uint32_t base = 0; base < n_points; base += kChunkBeams) {
@@ -585,13 +602,9 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
       }
       mbarrier_wait(&s_bar, phase);
       phase ^= 1u;
-      uint32_t b = 0;
-#pragma unroll kRwUnroll
-      for (; b + 4 <= count; b += 4) BB200_FIXED_GROUP(s_pts[b], s_pts[b + 1], s_pts[b + 2], s_pts[b + 3]);
-      if (b < count) {
-        const Pose2 te = field_frame_pose(field, states, i, active);
-        for (; b < count; ++b) acc = acc + bordered_lookup_exact(field, s_pts[b].x, s_pts[b].y, te.c, te.s, te.x, te.y);
-      }
+#define BB200_POINT(k) s_pts[(k)]
+      BB200_FIXED_SUM(BB200_POINT, count);
+#undef BB200_POINT
       if (base + kChunkBeams < n_points) __syncthreads();
     }
   }
@@ -603,7 +616,7 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
   }
   publish_weight_max(active ? weight_order_bits(w) : 0ull, &s_max, &s_arrived, kRwThreads / kWarp, scalars);
 }
-#undef BB200_FIXED_GROUP
+#undef BB200_FIXED_SUM
 
 // ---- reweight (beam model; a4 + a5) -----------------------------------------------------------
 // BeamSensorModel (sensor/beam_model.hpp:104-150): one thread per particle, beams in the inner

@@ -32,8 +32,8 @@ struct FieldView {
   const double* bordered;
   int border_kx;
   uint32_t border_pitch;  // 2^border_kx
-  uint32_t border_x_max;  // ((width + 1) << 16) | 0xFFFF: largest 16.16 word of a padded x
-  uint32_t border_y_max;  // ((4 (height + 1) + 3) << 16) | 0xFFFF: same for 4 * padded y
+  uint32_t border_x_max;  // width + 1: largest padded x
+  uint32_t border_y_max;  // 4 (height + 1) + 3: largest 4 * padded y with its two fraction bits
   int use_fixed;          // launch the fixed-point kernel (map small enough for 16.16 cell coordinates)
 };
 
@@ -41,7 +41,7 @@ struct FieldView {
 BB_HD uint32_t bordered_index(uint32_t px, uint32_t py, int kx) {
   return (((py >> 2) << (kx + 4)) | ((px >> 2) << 4)) | ((py & 3u) << 2) | (px & 3u);
 }
-/// Largest padded grid side the fixed-point kernel accepts (16.16 signed, y pre-scaled by 4).
+/// Largest padded grid side the fixed-point kernel accepts (cell coordinates below 2^13).
 constexpr int kFixedMaxSide = 8000;
 
 /// Device view of the occupancy grid (beam model).
