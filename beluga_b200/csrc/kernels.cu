@@ -470,10 +470,6 @@ struct FixedParticle {
   uint32_t row_pitch;    // 2^kx: tiles per row
 };
 
-#ifndef BB200_EXP
-#define BB200_EXP 0
-#endif
-
 /// `margin` collects the smallest fraction word seen (0 = an ambiguous coordinate).
 __device__ __forceinline__ double fixed_lookup(const double* __restrict__ bordered, const FixedParticle& q, double px, double py, uint32_t& margin) {
   const double gx = fma(px, q.cx, fma(-py, q.sx, q.ox)) + kFixedMagicX;  // gx + 1
@@ -512,13 +508,15 @@ struct ScanParam {
   double2 p[kParamBeams];
 };
 
+#define BB200_PRAGMA_STR(x) _Pragma(#x)
+#define BB200_PRAGMA_UNROLL(n) BB200_PRAGMA_STR(unroll n)
 // libstdc++ transform_reduce (numeric:439-462): groups of four, init += ((f0+f1)+(f2+f3)), then one by one.
 #define BB200_FIXED_SUM(POINT, COUNT)                                                                         \
   do {                                                                                                        \
     const double acc_before = acc;                                                                            \
     uint32_t margin = margin_start;                                                                           \
     uint32_t b = 0;                                                                                           \
-    _Pragma("unroll 2") for (; b + 4 <= (COUNT); b += 4) {                                                    \
+    BB200_PRAGMA_UNROLL(BB200_RW_UNROLL) for (; b + 4 <= (COUNT); b += 4) {                                   \
       const double2 p0 = POINT(b), p1 = POINT(b + 1), p2 = POINT(b + 2), p3 = POINT(b + 3);                   \
       const double f0 = fixed_lookup(field.bordered, q, p0.x, p0.y, margin);                                  \
       const double f1 = fixed_lookup(field.bordered, q, p1.x, p1.y, margin);                                  \

@@ -8,8 +8,8 @@ run() {
 import json,sys
 d=json.loads(sys.stdin.read()); print('   steps/s', round(d['value'],1), 'reweight_ms', round(d['kernels_ms']['reweight_lfm'],4))"
 }
-for blocks in 3 4; do
-  for unroll in 1 2 3; do
+for blocks in 3 4 5; do
+  for unroll in 1 2 4; do
     BB200_RW_BLOCKS=$blocks BB200_RW_UNROLL=$unroll python -m beluga_b200.build --force > /dev/null 2>&1
     echo "blocks=$blocks unroll=$unroll param=1" | tee -a $log
     run | tee -a $log
