@@ -21,13 +21,13 @@
 
 // Tuning knobs of the reweight kernel (overridable with -D from beluga_b200/build.py).
 #ifndef BB200_RW_THREADS
-#define BB200_RW_THREADS 256
+#define BB200_RW_THREADS 64
 #endif
 #ifndef BB200_RW_UNROLL
 #define BB200_RW_UNROLL 2
 #endif
 #ifndef BB200_RW_BLOCKS
-#define BB200_RW_BLOCKS 4
+#define BB200_RW_BLOCKS 18
 #endif
 
 #include <algorithm>
@@ -547,11 +547,77 @@ struct ScanParam {
     }                                                                                                         \
   } while (0)
 
-template <bool kFromParams>
+/// Per-particle constants of the fixed-point evaluation.
+__device__ __forceinline__ void fixed_particle_setup(const FieldView& field, const Pose2* __restrict__ states, uint64_t i, bool active,
+                                                     double points_radius, FixedParticle& q, uint32_t& margin_start) {
+  const Pose2 t = field_frame_pose(field, states, i, active);
+  const double inv = field.inv_resolution;
+  // The error bound above needs every term of g below 2^13 cells.
+  const double reach = (points_radius + fmax(fabs(t.x), fabs(t.y))) * inv + 2.0;
+  margin_start = reach < 8100.0 ? 0xFFFFFFFFu : 0u;  // 0 also for NaN: straight to the exact sequence
+  q.cx = t.c * inv, q.sx = t.s * inv, q.ox = t.x * inv + 1.0, q.oy = t.y * inv + 1.0;
+  q.x_max = field.border_x_max;
+  q.y_max = field.border_y_max;
+  q.row_pitch = field.border_pitch;
+}
+
+/// Scan in the constant bank: nothing is shared between the warps of a CTA, so the grid is persistent
+/// (CTAs/SM x SM count) and every WARP draws the next 32 particles of the schedule from a global
+/// ticket counter.  A CTA-per-256-particles grid loses 10-13 % to its slowest warp (each CTA holds its
+/// SM slot until the last of its warps is through 1080 beams) and to the partial last wave.
+__global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
+    reweight_lfm_fixed_param_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
+                                    FieldView field, uint32_t n_points, double points_radius, Scalars* __restrict__ scalars,
+                                    const __grid_constant__ ScanParam scan) {
+  const int lane = threadIdx.x % kWarp;
+  const unsigned long long n_tasks = (n + kWarp - 1) / kWarp;
+  unsigned long long* ticket_counter = &scalars->work_ticket;
+  unsigned long long ticket = lane == 0 ? atomicAdd(ticket_counter, 1ull) : 0ull;
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  unsigned long long best = 0ull;
+  while (ticket < n_tasks) {
+    // Draw the next ticket now; its round trip to L2 hides behind this task's beams.
+    const unsigned long long next = lane == 0 ? atomicAdd(ticket_counter, 1ull) : 0ull;
+    const uint64_t slot = ticket * kWarp + lane;
+    const bool active = slot < n;  // idle lanes of the last task walk the beams with a dummy pose
+    const uint64_t i = active ? (perm != nullptr ? perm[slot] : slot) : 0;
+    uint32_t margin_start;
+    FixedParticle q;
+    fixed_particle_setup(field, states, i, active, points_radius, q, margin_start);
+    double acc = field.init;
+#define BB200_POINT(k) scan.p[(k)]
+    BB200_FIXED_SUM(BB200_POINT, n_points);
+#undef BB200_POINT
+    if (active) {
+      const double likelihood = field.exp_epilogue ? exp(acc) : acc;
+      const double w = weights[i] * likelihood;  // actions/reweight.hpp:54-60
+      weights[i] = w;
+      const unsigned long long bits = weight_order_bits(w);
+      best = bits > best ? bits : best;
+    }
+    ticket = __shfl_sync(0xffffffffu, next, 0);
+  }
+#pragma unroll
+  for (int off = kWarp / 2; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_down_sync(0xffffffffu, best, off);
+    best = o > best ? o : best;
+  }
+  if (lane == 0) {
+    if (best != 0ull) atomicMax(&scalars->wmax_bits, best);
+    // The last warp out rewinds the ticket counter for the next launch.
+    const unsigned long long warps = static_cast<unsigned long long>(gridDim.x) * (kRwThreads / kWarp);
+    if (atomicAdd(&scalars->work_done, 1ull) + 1ull == warps) {
+      scalars->work_done = 0ull;
+      *ticket_counter = 0ull;
+    }
+  }
+}
+
+/// Scan staged in shared memory by TMA (scans longer than kParamBeams points): one CTA per kRwThreads particles.
 __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     reweight_lfm_fixed_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
                               FieldView field, const double2* __restrict__ points, uint32_t n_points, double points_radius,
-                              Scalars* __restrict__ scalars, const __grid_constant__ ScanParam scan) {
+                              Scalars* __restrict__ scalars) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* s_pts = reinterpret_cast<double2*>(smem_raw);
   __shared__ __align__(8) uint64_t s_bar;
@@ -564,47 +630,29 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
   if (threadIdx.x == 0) {
     s_max = 0ull;
     s_arrived = 0u;
-    if (!kFromParams) {
-      mbarrier_init(&s_bar, 1);
-      mbarrier_init_fence();
-    }
+    mbarrier_init(&s_bar, 1);
+    mbarrier_init_fence();
   }
   uint32_t margin_start;
   FixedParticle q;
-  {
-    const Pose2 t = field_frame_pose(field, states, i, active);
-    const double inv = field.inv_resolution;
-    // The error bound above needs every term of g below 2^13 cells.
-    const double reach = (points_radius + fmax(fabs(t.x), fabs(t.y))) * inv + 2.0;
-    margin_start = reach < 8100.0 ? 0xFFFFFFFFu : 0u;  // 0 also for NaN: straight to the exact sequence
-    q.cx = t.c * inv, q.sx = t.s * inv, q.ox = t.x * inv + 1.0, q.oy = t.y * inv + 1.0;
-  }
-  q.x_max = field.border_x_max;
-  q.y_max = field.border_y_max;
-  q.row_pitch = field.border_pitch;
+  fixed_particle_setup(field, states, i, active, points_radius, q, margin_start);
 
   double acc = field.init;
-  __syncthreads();  // s_max (and the barrier) initialised
-  if (kFromParams) {
-#define BB200_POINT(k) scan.p[(k)]
-    BB200_FIXED_SUM(BB200_POINT, n_points);
-#undef BB200_POINT
-  } else {
-    uint32_t phase = 0;
-    for (uint32_t base = 0; base < n_points; base += kChunkBeams) {
-      const uint32_t count = min(kChunkBeams, n_points - base);
-      if (threadIdx.x == 0) {
-        const uint32_t bytes = count * static_cast<uint32_t>(sizeof(double2));
-        mbarrier_expect_tx(&s_bar, bytes);
-        bulk_copy_g2s(s_pts, points + base, bytes, &s_bar);
-      }
-      mbarrier_wait(&s_bar, phase);
-      phase ^= 1u;
-#define BB200_POINT(k) s_pts[(k)]
-      BB200_FIXED_SUM(BB200_POINT, count);
-#undef BB200_POINT
-      if (base + kChunkBeams < n_points) __syncthreads();
+  __syncthreads();  // s_max and the barrier initialised
+  uint32_t phase = 0;
+  for (uint32_t base = 0; base < n_points; base += kChunkBeams) {
+    const uint32_t count = min(kChunkBeams, n_points - base);
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = count * static_cast<uint32_t>(sizeof(double2));
+      mbarrier_expect_tx(&s_bar, bytes);
+      bulk_copy_g2s(s_pts, points + base, bytes, &s_bar);
     }
+    mbarrier_wait(&s_bar, phase);
+    phase ^= 1u;
+#define BB200_POINT(k) s_pts[(k)]
+    BB200_FIXED_SUM(BB200_POINT, count);
+#undef BB200_POINT
+    if (base + kChunkBeams < n_points) __syncthreads();
   }
   double w = 0.0;
   if (active) {
@@ -1188,6 +1236,17 @@ void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uin
   schedule_scatter_kernel<<<blocks, 256, 0, stream>>>(bins, n, counters, perm);
 }
 
+int sm_count() {
+  static thread_local int cached_device = -1, cached = 0;
+  int device = 0;
+  cudaGetDevice(&device);
+  if (device != cached_device) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, device);
+    cached_device = device;
+  }
+  return cached > 0 ? cached : 148;
+}
+
 void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const FieldView& field,
                          const double* points_xy_device, const double* points_xy_host, uint32_t n_points, double points_radius, Scalars* scalars,
                          cudaStream_t stream) {
@@ -1199,9 +1258,11 @@ void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const
     static thread_local ScanParam scan;  // launch parameters are copied at launch time
     if (points_xy_host != nullptr && n_points <= kParamBeams) {
       std::memcpy(scan.p, points_xy_host, static_cast<size_t>(n_points) * sizeof(double2));
-      reweight_lfm_fixed_kernel<true><<<blocks, kRwThreads, 0, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars, scan);
+      const unsigned tasks = static_cast<unsigned>((n + kWarp - 1) / kWarp);
+      const unsigned persistent = std::min<unsigned>(static_cast<unsigned>(sm_count()) * kRwBlocksPerSm, (tasks + kRwThreads / kWarp - 1) / (kRwThreads / kWarp));
+      reweight_lfm_fixed_param_kernel<<<persistent, kRwThreads, 0, stream>>>(states, weights, n, perm, field, n_points, points_radius, scalars, scan);
     } else {
-      reweight_lfm_fixed_kernel<false><<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars, scan);
+      reweight_lfm_fixed_kernel<<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars);
     }
   } else if (field.use_tiled) {
     reweight_lfm_kernel<true><<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars);

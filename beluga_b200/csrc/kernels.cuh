@@ -65,7 +65,7 @@ struct MotionSampling {
   double first_c, first_s;
 };
 
-/// Per-filter device scalars (one cache line; zeroed by launch_begin_step).
+/// Per-filter device scalars (zeroed at creation; the per-step fields are reset by launch_begin_step).
 struct Scalars {
   unsigned long long wmax_bits;   // bit pattern of the largest weight (positive doubles order like integers)
   unsigned long long tile_ticket; // decoupled look-back: next tile id
@@ -74,6 +74,8 @@ struct Scalars {
   int valid;                      // 0 when no positive finite weight exists
   unsigned long long kld_cutoff;  // first slot (1-based count) at which the KLD condition fails
   unsigned long long pad[3];
+  unsigned long long work_ticket;  // persistent reweight kernel: next 32-particle task (rewound by the last warp out)
+  unsigned long long work_done;    // warps that have left that kernel
 };
 
 constexpr int kMomentCount = 9;  // sum w, sum w^2, sum w c, sum w s, sum w dx, sum w dy, sum w dx^2, sum w dx dy, sum w dy^2

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 log=gpurun_out/sweep_threads.log
 : > $log
-for cfg in "128 8" "256 4" "512 2" "1024 1"; do
+for cfg in "64 18" "128 9" "256 4" "32 32"; do
   set -- $cfg
   BB200_RW_THREADS=$1 BB200_RW_BLOCKS=$2 python -m beluga_b200.build --force > /dev/null 2>&1
   echo -n "threads=$1 blocks=$2 " | tee -a $log
