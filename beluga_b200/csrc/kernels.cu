@@ -1276,11 +1276,6 @@ void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const
     static thread_local ScanParam scan;  // launch parameters are copied at launch time
     if (points_xy_host != nullptr && n_points <= kParamBeams) {
       std::memcpy(scan.p, points_xy_host, static_cast<size_t>(n_points) * sizeof(double2));
-      static thread_local bool carveout_set = false;
-      if (!carveout_set) {  // no shared memory to speak of: give the gather all of the L1
-        cudaFuncSetAttribute(reweight_lfm_fixed_param_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-        carveout_set = true;
-      }
       const unsigned ctas_needed = static_cast<unsigned>((n + kRwThreads - 1) / kRwThreads);
       const unsigned persistent = std::min<unsigned>(static_cast<unsigned>(sm_count()) * kRwBlocksPerSm, ctas_needed);
       reweight_lfm_fixed_param_kernel<<<persistent, kRwThreads, 0, stream>>>(states, weights, n, perm, field, n_points, points_radius, scalars, scan);
