@@ -21,16 +21,16 @@
 
 // Tuning knobs of the reweight kernel (overridable with -D from beluga_b200/build.py).
 #ifndef BB200_RW_THREADS
-#define BB200_RW_THREADS 64
+#define BB200_RW_THREADS 256
 #endif
 #ifndef BB200_RW_UNROLL
 #define BB200_RW_UNROLL 2
 #endif
 #ifndef BB200_RW_BLOCK_TICKETS
-#define BB200_RW_BLOCK_TICKETS 1
+#define BB200_RW_BLOCK_TICKETS 0
 #endif
 #ifndef BB200_RW_BLOCKS
-#define BB200_RW_BLOCKS 18
+#define BB200_RW_BLOCKS 4
 #endif
 
 #include <algorithm>
