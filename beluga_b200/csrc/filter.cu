@@ -141,12 +141,6 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   BB_TRY(dev_alloc(&perm_, capacity_));
   BB_TRY(dev_alloc(&counters_, schedule_max_bins()));
   BB_TRY(dev_alloc(&sched_tiles_, schedule_tile_count()));
-  BB_TRY(dev_alloc(&queues_, 1));
-  {
-    WorkQueues host;
-    init_work_queues_host(&host);
-    BB_TRY(cudaMemcpy(queues_, &host, sizeof(host), cudaMemcpyHostToDevice));
-  }
   BB_TRY(cudaMemsetAsync(scalars_, 0, sizeof(Scalars), stream_));
   BB_TRY(cudaStreamSynchronize(stream_));
 #undef BB_TRY
@@ -173,7 +167,6 @@ Filter::~Filter() {
   cudaFree(partials_);
   cudaFree(results_);
   cudaFreeHost(results_host_);
-  cudaFree(queues_);
   cudaFree(cluster_.hashes);
   cudaFree(cluster_.keys);
   cudaFree(cluster_.first);
@@ -661,7 +654,7 @@ int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t 
     } else {
       mark("reweight_lfm");
       launch_reweight_lfm(states_[cur_], weights_, n_, perm, field_, points_, param_points_ ? points_host_ : nullptr, static_cast<uint32_t>(n_points),
-                          points_radius_, scalars_, queues_, stream_);
+                          points_radius_, scalars_, stream_);
       BB_LAUNCHED("reweight_lfm");
     }
   }

@@ -122,7 +122,6 @@ class Filter {
   // scratch
   Scalars* scalars_{nullptr};
   Scalars* scalars_host_{nullptr};  // pinned
-  WorkQueues* queues_{nullptr};
   unsigned long long* tile_state_{nullptr};
   uint32_t tile_capacity_{0};
   double* partials_{nullptr};

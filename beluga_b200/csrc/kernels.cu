@@ -27,7 +27,7 @@
 #define BB200_RW_UNROLL 2
 #endif
 #ifndef BB200_RW_BLOCK_TICKETS
-#define BB200_RW_BLOCK_TICKETS 2
+#define BB200_RW_BLOCK_TICKETS 0
 #endif
 #ifndef BB200_RW_BLOCKS
 #define BB200_RW_BLOCKS 4
@@ -306,8 +306,7 @@ __global__ void __launch_bounds__(256) schedule_scatter_kernel(const uint32_t* _
 constexpr int kRwThreads = BB200_RW_THREADS;  // x kRwBlocksPerSm CTAs per SM
 constexpr int kRwBlocksPerSm = BB200_RW_BLOCKS;
 constexpr int kRwUnroll = BB200_RW_UNROLL;
-constexpr bool kRwBlockTickets = BB200_RW_BLOCK_TICKETS == 1;  // persistent kernel: tasks drawn per CTA (1), per warp (0) ...
-constexpr bool kRwSmQueues = BB200_RW_BLOCK_TICKETS == 2;     // ... or per warp from its SM's chunk of the schedule (2)  // groups of four beams in flight per thread
+constexpr bool kRwBlockTickets = BB200_RW_BLOCK_TICKETS != 0;  // persistent kernel: tasks per CTA (1) or per warp (0)  // groups of four beams in flight per thread
 constexpr uint32_t kChunkBeams = 2048; // beams staged per shared-memory chunk (32 KB), multiple of 4
 
 /// floor(g) as int32 for |g| < 2^31 through one round-down add: g + 1.5*2^52 has ulp 1, so the low
@@ -566,39 +565,6 @@ __device__ __forceinline__ void fixed_particle_setup(const FieldView& field, con
   q.row_pitch = field.border_pitch;
 }
 
-constexpr uint32_t kChunkTasks = 32;  // tasks per SM-local chunk: one per resident warp
-constexpr uint32_t kChunkInvalid = 0xFFFFFFFEu, kChunkFinished = 0xFFFFFFFFu;
-constexpr unsigned long long kQueueEmpty = (static_cast<unsigned long long>(kChunkInvalid) << 32) | kChunkTasks;
-
-/// Next task for this warp from its SM's queue (lane 0 only); ~0 when the schedule is exhausted.
-/// A warp that finds the SM's chunk used up refills it from the global chunk counter under the SM's lock.
-__device__ __forceinline__ unsigned long long draw_sm_local(WorkQueues* wq, unsigned long long* global_chunk, unsigned long long n_tasks) {
-  uint32_t smid;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  smid &= 255u;
-  const unsigned long long n_chunks = (n_tasks + kChunkTasks - 1) / kChunkTasks;
-  for (;;) {
-    const unsigned long long s = atomicAdd(&wq->slot[smid], 1ull);
-    const uint32_t chunk = static_cast<uint32_t>(s >> 32), off = static_cast<uint32_t>(s);
-    if (chunk == kChunkFinished) return ~0ull;
-    if (chunk != kChunkInvalid && off < kChunkTasks) {
-      const unsigned long long task = static_cast<unsigned long long>(chunk) * kChunkTasks + off;
-      if (task < n_tasks) return task;
-    }
-    if (atomicCAS(&wq->lock[smid], 0u, 1u) == 0u) {
-      const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&wq->slot[smid]);
-      if (static_cast<uint32_t>(cur >> 32) == chunk) {  // still the used-up chunk: nobody refilled in between
-        const unsigned long long fresh = atomicAdd(global_chunk, 1ull);
-        atomicExch(&wq->slot[smid], fresh < n_chunks ? (fresh << 32) : ((static_cast<unsigned long long>(kChunkFinished) << 32) | kChunkTasks));
-      }
-      __threadfence();
-      atomicExch(&wq->lock[smid], 0u);
-    } else {
-      __nanosleep(100);
-    }
-  }
-}
-
 /// Scan in the constant bank: nothing is shared between the warps of a CTA, so the grid is persistent
 /// (CTAs/SM x SM count) and every WARP draws the next 32 particles of the schedule from a global
 /// ticket counter.  A CTA-per-256-particles grid loses 10-13 % to its slowest warp (each CTA holds its
@@ -606,7 +572,7 @@ __device__ __forceinline__ unsigned long long draw_sm_local(WorkQueues* wq, unsi
 __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     reweight_lfm_fixed_param_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
                                     FieldView field, uint32_t n_points, double points_radius, Scalars* __restrict__ scalars,
-                                    WorkQueues* __restrict__ queues, const __grid_constant__ ScanParam scan) {
+                                    const __grid_constant__ ScanParam scan) {
   // A task = the next kTaskThreads particles of the schedule, drawn by a whole CTA (kRwBlockTickets: its
   // warps then gather from neighbouring cells and share L1 lines) or by each warp on its own.
   constexpr int kTaskThreads = kRwBlockTickets ? kRwThreads : kWarp;
@@ -624,15 +590,11 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     return __shfl_sync(0xffffffffu, mine, 0);
   };
   int parity = 0;
-  auto draw = [&]() -> unsigned long long {
-    if (!drawer) return 0ull;
-    return kRwSmQueues ? draw_sm_local(queues, ticket_counter, n_tasks) : atomicAdd(ticket_counter, 1ull);
-  };
-  unsigned long long ticket = share(draw(), parity);
+  unsigned long long ticket = share(drawer ? atomicAdd(ticket_counter, 1ull) : 0ull, parity);
   unsigned long long best = 0ull;
   while (ticket < n_tasks) {
-    // Global tickets: draw the next one now, its round trip to L2 hides behind this task's beams.
-    const unsigned long long next = kRwSmQueues ? 0ull : draw();
+    // Draw the next ticket now; its round trip to L2 hides behind this task's beams.
+    const unsigned long long next = drawer ? atomicAdd(ticket_counter, 1ull) : 0ull;
     const uint64_t slot = ticket * kTaskThreads + (kRwBlockTickets ? threadIdx.x : lane);
     const bool active = slot < n;  // idle lanes of the last task walk the beams with a dummy pose
     const uint64_t i = active ? (perm != nullptr ? perm[slot] : slot) : 0;
@@ -651,7 +613,7 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
       best = bits > best ? bits : best;
     }
     parity ^= 1;
-    ticket = share(kRwSmQueues ? draw() : next, parity);
+    ticket = share(next, parity);
   }
 #pragma unroll
   for (int off = kWarp / 2; off > 0; off >>= 1) {
@@ -665,9 +627,6 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     if (atomicAdd(&scalars->work_done, 1ull) + 1ull == warps) {
       scalars->work_done = 0ull;
       *ticket_counter = 0ull;
-      if (kRwSmQueues) {
-        for (int k = 0; k < 256; ++k) queues->slot[k] = kQueueEmpty;
-      }
     }
   }
 }
@@ -1295,13 +1254,6 @@ void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uin
   schedule_scatter_kernel<<<blocks, 256, 0, stream>>>(bins, n, counters, perm);
 }
 
-void init_work_queues_host(WorkQueues* host) {
-  for (int k = 0; k < 256; ++k) {
-    host->slot[k] = kQueueEmpty;
-    host->lock[k] = 0u;
-  }
-}
-
 int sm_count() {
   static thread_local int cached_device = -1, cached = 0;
   int device = 0;
@@ -1315,7 +1267,7 @@ int sm_count() {
 
 void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const FieldView& field,
                          const double* points_xy_device, const double* points_xy_host, uint32_t n_points, double points_radius, Scalars* scalars,
-                         WorkQueues* queues, cudaStream_t stream) {
+                         cudaStream_t stream) {
   if (n == 0) return;
   const unsigned blocks = static_cast<unsigned>((n + kRwThreads - 1) / kRwThreads);
   const size_t smem = static_cast<size_t>(n_points < kChunkBeams ? n_points : kChunkBeams) * sizeof(double2);
@@ -1326,7 +1278,7 @@ void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const
       std::memcpy(scan.p, points_xy_host, static_cast<size_t>(n_points) * sizeof(double2));
       const unsigned ctas_needed = static_cast<unsigned>((n + kRwThreads - 1) / kRwThreads);
       const unsigned persistent = std::min<unsigned>(static_cast<unsigned>(sm_count()) * kRwBlocksPerSm, ctas_needed);
-      reweight_lfm_fixed_param_kernel<<<persistent, kRwThreads, 0, stream>>>(states, weights, n, perm, field, n_points, points_radius, scalars, queues, scan);
+      reweight_lfm_fixed_param_kernel<<<persistent, kRwThreads, 0, stream>>>(states, weights, n, perm, field, n_points, points_radius, scalars, scan);
     } else {
       reweight_lfm_fixed_kernel<<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars);
     }

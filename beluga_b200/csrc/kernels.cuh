@@ -78,15 +78,6 @@ struct Scalars {
   unsigned long long work_done;    // warps that have left that kernel
 };
 
-/// Per-SM work queues of the persistent reweight kernel: slot = (chunk id << 32) | next task offset in
-/// the chunk; a chunk is kChunkTasks consecutive 32-particle tasks of the schedule, so the warps of one
-/// SM gather from neighbouring cells.  Indexed by %smid; reset by the kernel's last warp.
-struct WorkQueues {
-  unsigned long long slot[256];
-  unsigned int lock[256];
-};
-void init_work_queues_host(WorkQueues* host);
-
 constexpr int kMomentCount = 9;  // sum w, sum w^2, sum w c, sum w s, sum w dx, sum w dy, sum w dx^2, sum w dx dy, sum w dy^2
 
 // ---- launchers (all asynchronous on `stream`) ---------------------------------------------------
@@ -126,7 +117,7 @@ void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uin
 /// kernel parameters (constant bank) instead of being staged through shared memory.
 void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const FieldView& field,
                          const double* points_xy_device, const double* points_xy_host, uint32_t n_points, double points_radius, Scalars* scalars,
-                         WorkQueues* queues, cudaStream_t stream);
+                         cudaStream_t stream);
 /// reweight with the beam model (Bresenham ray casting) in schedule order | block max.
 void launch_reweight_beam(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const OccupancyView& grid,
                           const BeamParams& params, const double* points_xy_device, uint32_t n_points, Scalars* scalars, cudaStream_t stream);
