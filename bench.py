@@ -311,7 +311,7 @@ def run_native(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(scans[0].nbytes + 32), "d2h_bytes_per_step": int(9 * 8 + 128),
                     "ms_per_step": wall_total_ms / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "reweight_lfm_fixed_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "reweight_lfm_fixed_param_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
                          "kernel_ms": k1, "kernel_share_of_step": k1 / (dev_total_ms / args.steps),
                          "step_achieved_gbs": step_bytes / (dev_total_ms / args.steps * 1e-3) / 1e9,
