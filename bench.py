@@ -264,13 +264,17 @@ def run_native(args):
             flush.zero_()  # evict L2 between timed steps
             sync_all()
             filt.clear_timings()
+            if world > 1:  # the sharded step runs on torch's current stream (kernels and NCCL collectives alike)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             t0 = time.perf_counter()
             mean = step(k)
             if world > 1:
+                ev1.record()
                 torch.cuda.synchronize()
             wall_ms.append((time.perf_counter() - t0) * 1e3)
             step_kernels = filt.last_timings()
-            device_ms.append(sum(ms for _, ms in step_kernels))
+            device_ms.append(ev0.elapsed_time(ev1) if world > 1 else sum(ms for _, ms in step_kernels))
             per_step = {}
             for name, ms in step_kernels:
                 per_step[name] = per_step.get(name, 0.0) + ms
@@ -279,9 +283,10 @@ def run_native(args):
         sync_all()
     launches = filt.launch_count() - launches0
 
-    # N = 1: device time of the fused step (CUDA events on the filter stream).  N > 1: the step is host-orchestrated
-    # (collectives between kernels), so the step time is the host clock between synchronisation points; max over ranks.
-    totals = torch.tensor([sum(device_ms) if world == 1 else sum(wall_ms), sum(wall_ms)], dtype=torch.float64, device="cuda")
+    # Device time from CUDA events on the stream the step runs on: N = 1 the filter's own events around its kernels,
+    # N > 1 one event pair around the whole sharded step (kernels + collectives + the waits between them); max over ranks.
+    # e2e: host clock around the same public call (scan upload and estimate read-back inside).
+    totals = torch.tensor([sum(device_ms), sum(wall_ms)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(totals, op=dist.ReduceOp.MAX)
     dev_total_ms, wall_total_ms = totals.tolist()
