@@ -298,8 +298,9 @@ int Filter::enqueue_build_cdf() {
 
 int Filter::enqueue_resample_range(const bb200_resample_opts& o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin, uint64_t slot_end) {
   if (!cdf_valid_) return fail(BB200_ERR_STATE, "build_cdf must run before resample_range");
-  if (o.scheme != BB200_RESAMPLE_SYSTEMATIC || o.random_state_probability > 0.0 || o.min_particles < o.max_particles)
-    return fail(BB200_ERR_STATE, "sharded resampling supports the systematic comb without injection / KLD");
+  if (o.scheme != BB200_RESAMPLE_SYSTEMATIC || o.min_particles < o.max_particles)
+    return fail(BB200_ERR_STATE, "range resampling supports the systematic comb without KLD (multinomial: bb200_filter_enqueue_resample_push)");
+  if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
   if (slot_end < slot_begin || slot_end - slot_begin > capacity_) return fail(BB200_ERR_CAPACITY, "slot range exceeds the staging buffer");
   BB_CHECK(cudaSetDevice(config_.device));
   if (slot_end > slot_begin) {
@@ -349,11 +350,18 @@ int Filter::enqueue_resample_push(const bb200_resample_opts& o, uint64_t global_
                                   uint64_t shard, const double pivot[2]) {
   if (peer_world_ == 0) return fail(BB200_ERR_STATE, "open_peers must run before resample_push");
   if (!cdf_valid_) return fail(BB200_ERR_STATE, "build_cdf must run before resample_push");
-  if (o.scheme != BB200_RESAMPLE_SYSTEMATIC || o.random_state_probability > 0.0 || o.min_particles < o.max_particles)
-    return fail(BB200_ERR_STATE, "sharded resampling supports the systematic comb without injection / KLD");
+  if (o.min_particles < o.max_particles) return fail(BB200_ERR_STATE, "sharded resampling does not support KLD");
+  if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
+  if (o.scheme != BB200_RESAMPLE_SYSTEMATIC && (slot_begin != 0 || slot_end != o.max_particles))
+    return fail(BB200_ERR_INVALID_ARGUMENT, "multinomial push walks all global slots: pass [0, max_particles)");
   BB_CHECK(cudaSetDevice(config_.device));
   ResampleArgs a = make_resample_args(o, 0, slot_end - slot_begin, false);
   a.slot_first = slot_begin;
+  if (o.scheme != BB200_RESAMPLE_SYSTEMATIC) {  // draws are independent: every rank filters the global slots by its CDF span
+    a.span_filter = 1;
+    a.owner_first = config_.first_index;
+    a.owner_count = shard;
+  }
   a.global_total = global_total;
   a.cdf_offset = cdf_offset;
   a.weights_out = nullptr;
@@ -951,8 +959,9 @@ int Filter::resample_range(const bb200_resample_opts& o, uint64_t global_total, 
   // Sharded filter: this rank produces the output slots [slot_begin, slot_end) -- exactly those whose
   // comb position falls inside its span of the global CDF -- into the staging buffer, in slot order.
   if (!cdf_valid_) return fail(BB200_ERR_STATE, "build_cdf must run before resample_range");
-  if (o.scheme != BB200_RESAMPLE_SYSTEMATIC || o.random_state_probability > 0.0 || o.min_particles < o.max_particles)
-    return fail(BB200_ERR_STATE, "sharded resampling supports the systematic comb without injection / KLD");
+  if (o.scheme != BB200_RESAMPLE_SYSTEMATIC || o.min_particles < o.max_particles)
+    return fail(BB200_ERR_STATE, "range resampling supports the systematic comb without KLD (multinomial: bb200_filter_enqueue_resample_push)");
+  if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
   if (slot_end < slot_begin || slot_end - slot_begin > capacity_) return fail(BB200_ERR_CAPACITY, "slot range exceeds the staging buffer");
   BB_CHECK(cudaSetDevice(config_.device));
   if (slot_end > slot_begin) {

@@ -1149,6 +1149,12 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, co
     Draw d{0, 0};
     if (a.random_state_probability > 0.0 || a.scheme == 0) d = counter_draw(a.seed, j, a.step, kStreamResample);
     if (a.random_state_probability > 0.0) inject = uniform01(d.a) < a.random_state_probability;  // random_intersperse.hpp:93-100
+    unsigned long long t = 0;
+    if (!inject) t = a.scheme == 1 ? offset + j * stride : mulhi64(d.b, total);
+    if (a.span_filter != 0) {
+      const bool mine = inject ? (j >= a.owner_first && j - a.owner_first < a.owner_count) : (t >= a.cdf_offset && t - a.cdf_offset < scalars->total);
+      if (!mine) continue;
+    }
     if (inject) {
       // MultivariateUniformDistribution<SE2d, OccupancyGrid> (multivariate_uniform_distribution.hpp:143-160)
       const Draw r = counter_draw(a.seed, j, a.step, kStreamRandomState);
@@ -1161,7 +1167,6 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, co
       st = Pose2{rot.c, rot.s, (a.grid_origin.c * lx - a.grid_origin.s * ly) + a.grid_origin.x,
                  (a.grid_origin.s * lx + a.grid_origin.c * ly) + a.grid_origin.y};
     } else {
-      const unsigned long long t = a.scheme == 1 ? offset + j * stride : mulhi64(d.b, total);
       const uint64_t idx = cdf_upper_bound(a.cdf, a.n_in, t - a.cdf_offset);  // the caller guarantees t lies in this shard's span
       ancestor = static_cast<long long>(idx);
       st = load_pose(a.states_in + idx);

@@ -160,6 +160,11 @@ struct ResampleArgs {
   int peer_count;
   uint64_t peer_shard;
   Pose2* peer_out[8];
+  // Sharded multinomial sampling: the launch walks ALL global slots and keeps those whose draw lands in
+  // this rank's span of the global CDF [cdf_offset, cdf_offset + local total); an injected random state
+  // is produced by the rank that owns the slot ([owner_first, owner_first + owner_count)).
+  int span_filter;
+  uint64_t owner_first, owner_count;
   int scheme;
   uint64_t seed;
   uint32_t step;

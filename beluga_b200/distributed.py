@@ -108,8 +108,6 @@ class ShardedAmcl:
         self.world = dist.get_world_size(process_group)
         self.shard = shard
         self.total = shard * self.world
-        if params.resample_scheme != _capi.RESAMPLE_SYSTEMATIC:
-            raise ValueError("ShardedAmcl supports systematic resampling")
         params.max_particles = self.total
         params.min_particles = self.total
         params.shard_capacity = shard
@@ -129,6 +127,9 @@ class ShardedAmcl:
         # Fused resample + redistribution: map every rank's state buffers (CUDA IPC) so that the resample
         # kernel stores each new particle straight into its owner's buffer over NVLink.
         self.p2p = p2p and 1 < self.world <= 8
+        self.multinomial = params.resample_scheme != _capi.RESAMPLE_SYSTEMATIC
+        if self.multinomial and not self.p2p:
+            raise ValueError("sharded multinomial resampling needs the peer-memory path (p2p=True, 2..8 ranks)")
         if self.p2p:
             handles = [None] * self.world
             dist.all_gather_object(handles, self.filter.ipc_handles(), group=process_group)
@@ -192,20 +193,25 @@ class ShardedAmcl:
             self._totals = torch.zeros(self.world + 1, dtype=torch.int64, device="cuda")
         return self._scalars, self._results
 
-    def update(self, control_pose, points):
-        """Returns None (std::nullopt) or (mean[4], cov[3x3], info)."""
+    def update(self, control_pose, points, random_state_probability=None):
+        """Returns None (std::nullopt) or (mean[4], cov[3x3], info).
+
+        random_state_probability overrides the recovery estimator's output for this step.  (The reference feeds
+        the estimator normalised weights, whose mean is 1/N: with the fixed particle count of a sharded filter it
+        never fires on its own; the override exercises views::random_intersperse on shards.)"""
         plan = self.amcl.plan_update(control_pose)
         if not plan.update:
             return None
-        if plan.resample and not plan.needs_ess:
+        if random_state_probability is not None:
+            plan.random_state_probability = float(random_state_probability)
+            plan.opts.random_state_probability = float(random_state_probability)
+        if plan.resample and not plan.needs_ess and (self.p2p or not self.multinomial):
             return self._update_streamed(plan, points)
         return self._update_stepwise(plan, points)
 
     def _update_streamed(self, plan, points):
         """Resampling step with everything enqueued on one stream; two host synchronisations."""
         torch, dist, f = self.torch, self.dist, self.filter
-        if plan.random_state_probability > 0.0:
-            raise NotImplementedError("recovery injection on a sharded filter")
         scalars, results = self._device_blocks()
         f.enqueue_propagate_reweight(plan.sampling, plan.step, points)
         # positive doubles order like their bit patterns: MAX over the int64 view is the largest weight
@@ -219,11 +225,16 @@ class ShardedAmcl:
         global_total = offsets[-1]
         weight_sum = float(np.ldexp(float(global_total), -exponent))
 
-        stride, comb = _systematic_comb(self.params.seed, plan.step, global_total, self.total)
-        ranges = slot_ranges(offsets, stride, comb, self.total)
+        if self.multinomial:
+            ranges = None
+        else:
+            stride, comb = _systematic_comb(self.params.seed, plan.step, global_total, self.total)
+            ranges = slot_ranges(offsets, stride, comb, self.total)
         if self.p2p:
             # One kernel: CDF search + gather + peer stores into the owners' buffers + moments of what it produced.
-            ja, jb = ranges[self.rank]
+            # Systematic: this rank's contiguous slot range.  Multinomial: the draws are independent, so the kernel
+            # walks all global slots and keeps those landing in this rank's span of the global CDF.
+            ja, jb = (0, self.total) if self.multinomial else ranges[self.rank]
             f.enqueue_resample_push(plan.opts, global_total, offsets[self.rank], ja, jb, self.shard, self.pivot)
             f.enqueue_reduce_moments()
             dist.all_reduce(results[0:9], op=dist.ReduceOp.SUM, group=self.group)  # also the barrier: all peer stores are done
@@ -265,8 +276,8 @@ class ShardedAmcl:
             f.normalize_by(global_total)
 
         if resample:
-            if plan.random_state_probability > 0.0:
-                raise NotImplementedError("recovery injection on a sharded filter")
+            if self.multinomial:
+                raise NotImplementedError("selective resampling with sharded multinomial sampling")
             stride, comb = _systematic_comb(self.params.seed, plan.step, global_total, self.total)
             ranges = slot_ranges(offsets, stride, comb, self.total)
             self._redistribute(plan, ranges, global_total, offsets[self.rank], streamed=False)

@@ -21,25 +21,28 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rank, world = dist.get_rank(), dist.get_world_size()
     shard, steps = int(sys.argv[1]), int(sys.argv[2])
-    p2p = len(sys.argv) > 3 and sys.argv[3] == "p2p"
+    mode = sys.argv[3] if len(sys.argv) > 3 else "nccl"
+    p2p = mode != "nccl"
+    scheme = bb.RESAMPLE_MULTINOMIAL if mode == "p2p-multinomial" else bb.RESAMPLE_SYSTEMATIC
+    inject = 0.03 if mode.endswith("recovery") or mode == "p2p-multinomial" else None  # random_intersperse probability
     total = shard * world
     sc = synthetic.make_scenario(grid_size=200, n_beams=181, steps=steps + 1)
     motion = bb.DifferentialDriveModelParam(0.1, 0.05, 0.1, 0.05)
     lfm = bb.LikelihoodFieldModelParam(max_obstacle_distance=2.0, max_laser_distance=100.0)
     grid = bb.OccupancyGrid(sc.cells, sc.resolution)
 
-    sharded = ShardedAmcl(motion, bb.AmclParams(resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=21, device=local_rank), shard=shard, p2p=p2p)
+    sharded = ShardedAmcl(motion, bb.AmclParams(resample_scheme=scheme, seed=21, device=local_rank, shard=shard, p2p=p2p)
     sharded.update_map(bb.SENSOR_LIKELIHOOD_FIELD, lfm, grid)
     sharded.initialize(sc.initial_mean, sc.initial_cov)
     single = None
     if rank == 0:
-        single = bb.Amcl(motion, bb.AmclParams(min_particles=total, max_particles=total, resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=21, device=0))
+        single = bb.Amcl(motion, bb.AmclParams(min_particles=total, max_particles=total, resample_scheme=scheme, seed=21, device=0)
         single.update_map(bb.SENSOR_LIKELIHOOD_FIELD, lfm, grid)
         single.initialize(sc.initial_mean, sc.initial_cov)
 
     for k in range(steps):
         pose = bb.se2(*sc.poses[k])
-        out = sharded.update(pose, sc.scans[k])
+        out = sharded.update(pose, sc.scans[k], random_state_probability=inject)
         assert out is not None
         mean, cov, info = out
         # gather the sharded particle set on rank 0
@@ -47,14 +50,25 @@ def main():
         gathered = [torch.zeros(shard, 4, dtype=torch.float64, device="cuda") for _ in range(world)]
         dist.all_gather(gathered, torch.from_numpy(states).cuda())
         if rank == 0:
-            r = single.update(pose, sc.scans[k])
+            if inject is None:
+                r = single.update(pose, sc.scans[k])
+                ref_sum, ref_mean, ref_cov = r.weight_sum, np.array(r.estimate.mean), np.array(r.estimate.cov).reshape(3, 3)
+            else:  # the same step composed from the filter-level calls, with the injection probability forced
+                plan = single.plan_update(pose)
+                sf = single.filter
+                sf.propagate_reweight(plan.sampling, plan.step, sc.scans[k])
+                factor, _ = sf.normalize()
+                ref_sum = factor
+                sf.resample(scheme, plan.step, total, random_state_probability=inject)
+                ref_mean, ref_cov = sf.estimate()
+                single.commit_update(True, inject)
             ref_states, ref_w = single.particles()
             all_states = torch.cat(gathered).cpu().numpy()
             assert np.array_equal(all_states, ref_states), f"step {k}: sharded particle set differs from the single-GPU one"
             assert np.all(weights == 1.0) and np.all(ref_w == 1.0)
-            assert info["weight_sum"] == r.weight_sum
-            assert np.abs(mean - np.array(r.estimate.mean)).max() < 1e-12
-            assert np.abs(cov - np.array(r.estimate.cov).reshape(3, 3)).max() < 1e-12
+            assert info["weight_sum"] == ref_sum
+            assert np.abs(mean - ref_mean).max() < 1e-12
+            assert np.abs(cov - ref_cov).max() < 1e-12
     dist.barrier()
     if rank == 0:
         print("SHARD_GPU_WORKER_OK")
