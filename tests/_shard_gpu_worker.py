@@ -22,7 +22,7 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     shard, steps = int(sys.argv[1]), int(sys.argv[2])
     mode = sys.argv[3] if len(sys.argv) > 3 else "nccl"
-    p2p = mode != "nccl"
+    p2p = mode.startswith("p2p")
     scheme = bb.RESAMPLE_MULTINOMIAL if mode == "p2p-multinomial" else bb.RESAMPLE_SYSTEMATIC
     inject = 0.03 if mode.endswith("recovery") or mode == "p2p-multinomial" else None  # random_intersperse probability
     total = shard * world
@@ -31,12 +31,12 @@ def main():
     lfm = bb.LikelihoodFieldModelParam(max_obstacle_distance=2.0, max_laser_distance=100.0)
     grid = bb.OccupancyGrid(sc.cells, sc.resolution)
 
-    sharded = ShardedAmcl(motion, bb.AmclParams(resample_scheme=scheme, seed=21, device=local_rank, shard=shard, p2p=p2p)
+    sharded = ShardedAmcl(motion, bb.AmclParams(resample_scheme=scheme, seed=21, device=local_rank), shard=shard, p2p=p2p)
     sharded.update_map(bb.SENSOR_LIKELIHOOD_FIELD, lfm, grid)
     sharded.initialize(sc.initial_mean, sc.initial_cov)
     single = None
     if rank == 0:
-        single = bb.Amcl(motion, bb.AmclParams(min_particles=total, max_particles=total, resample_scheme=scheme, seed=21, device=0)
+        single = bb.Amcl(motion, bb.AmclParams(min_particles=total, max_particles=total, resample_scheme=scheme, seed=21, device=0))
         single.update_map(bb.SENSOR_LIKELIHOOD_FIELD, lfm, grid)
         single.initialize(sc.initial_mean, sc.initial_cov)
 
