@@ -398,6 +398,10 @@ class Filter:
         buf = C.create_string_buffer(handles, len(handles))
         self._check(self._lib.bb200_filter_open_peers(self._h, world, rank, buf))
 
+    def enqueue_resample_push_device(self, opts: _capi.ResampleOpts, rank_totals_ptr: int, rank: int, world: int, shard: int, pivot):
+        self._check(self._lib.bb200_filter_enqueue_resample_push_device(self._h, C.byref(opts), C.c_void_p(rank_totals_ptr), rank, world, shard,
+                                                                        _dptr(_f64(pivot))))
+
     def enqueue_resample_push(self, opts: _capi.ResampleOpts, global_total: int, cdf_offset: int, slot_begin: int, slot_end: int, shard: int, pivot):
         self._check(self._lib.bb200_filter_enqueue_resample_push(self._h, C.byref(opts), global_total, cdf_offset, slot_begin, slot_end, shard,
                                                                  _dptr(_f64(pivot))))

@@ -137,6 +137,7 @@ SIGNATURES = {
     "bb200_filter_enqueue_moments": (C.c_int, [_vp, _dbl]),
     "bb200_filter_ipc_handles": (C.c_int, [_vp, _vp]),
     "bb200_filter_open_peers": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "bb200_filter_enqueue_resample_push_device": (C.c_int, [_vp, _P(ResampleOpts), C.c_void_p, C.c_int, C.c_int, C.c_uint64, _dbl]),
     "bb200_filter_enqueue_resample_push": (C.c_int, [_vp, _P(ResampleOpts), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _dbl]),
     "bb200_filter_enqueue_reduce_moments": (C.c_int, [_vp]),
     "bb200_filter_enqueue_flip_adopt": (C.c_int, [_vp, C.c_uint64]),

@@ -196,6 +196,11 @@ int bb200_filter_enqueue_resample_push(bb200_filter* f, const bb200_resample_opt
   BB_REQUIRE(f && o && pivot_xy && slot_end >= slot_begin && shard > 0);
   return f->impl.enqueue_resample_push(*o, global_total, cdf_offset, slot_begin, slot_end, shard, pivot_xy);
 }
+int bb200_filter_enqueue_resample_push_device(bb200_filter* f, const bb200_resample_opts* o, const uint64_t* rank_totals_device, int rank, int world,
+                                              uint64_t shard, const double pivot_xy[2]) {
+  BB_REQUIRE(f && o && rank_totals_device && pivot_xy && shard > 0);
+  return f->impl.enqueue_resample_push_device(*o, rank_totals_device, rank, world, shard, pivot_xy);
+}
 int bb200_filter_enqueue_reduce_moments(bb200_filter* f) {
   BB_REQUIRE(f);
   return f->impl.enqueue_reduce_moments();

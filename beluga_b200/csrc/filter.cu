@@ -379,6 +379,41 @@ int Filter::enqueue_resample_push(const bb200_resample_opts& o, uint64_t global_
   return BB200_OK;
 }
 
+int Filter::enqueue_resample_push_device(const bb200_resample_opts& o, const uint64_t* rank_totals_device, int rank, int world, uint64_t shard,
+                                         const double pivot[2]) {
+  if (peer_world_ == 0) return fail(BB200_ERR_STATE, "open_peers must run before resample_push");
+  if (!cdf_valid_) return fail(BB200_ERR_STATE, "build_cdf must run before resample_push");
+  if (o.min_particles < o.max_particles) return fail(BB200_ERR_STATE, "sharded resampling does not support KLD");
+  if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
+  if (rank_totals_device == nullptr || world != peer_world_ || rank < 0 || rank >= world) return fail(BB200_ERR_INVALID_ARGUMENT, "rank totals / rank / world");
+  BB_CHECK(cudaSetDevice(config_.device));
+  // Systematic: the kernel derives this rank's slot range from the totals; the grid is sized for a shard and strides.
+  // Multinomial: all global slots, filtered by this rank's span.
+  const bool systematic = o.scheme == BB200_RESAMPLE_SYSTEMATIC;
+  ResampleArgs a = make_resample_args(o, 0, systematic ? shard : o.max_particles, false);
+  a.slot_first = 0;
+  a.weights_out = nullptr;
+  a.ancestors = nullptr;
+  a.peer_count = peer_world_;
+  a.peer_shard = shard;
+  a.pivot_x = pivot[0];
+  a.pivot_y = pivot[1];
+  a.rank_totals = reinterpret_cast<const unsigned long long*>(rank_totals_device);
+  a.rank = rank;
+  a.world = world;
+  if (!systematic) {
+    a.span_filter = 1;
+    a.owner_first = config_.first_index;
+    a.owner_count = shard;
+  }
+  for (int r = 0; r < peer_world_; ++r) a.peer_out[r] = peer_states_[cur_ ^ 1][r];
+  mark("resample_push");
+  launch_resample(a, scalars_, partials_, stream_);  // a.slot_count only sizes the grid here
+  BB_LAUNCHED("resample_push");
+  pushed_blocks_ = resample_block_count(a.slot_count);
+  return BB200_OK;
+}
+
 int Filter::enqueue_reduce_moments() {
   BB_CHECK(cudaSetDevice(config_.device));
   launch_reduce_partials(partials_, pushed_blocks_, kMomentCount, results_, stream_);

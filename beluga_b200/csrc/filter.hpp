@@ -69,6 +69,8 @@ class Filter {
   int open_peers(int world, int rank, const void* handles /* world x 128 bytes */);
   int enqueue_resample_push(const bb200_resample_opts& o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin, uint64_t slot_end,
                             uint64_t shard, const double pivot[2]);
+  int enqueue_resample_push_device(const bb200_resample_opts& o, const uint64_t* rank_totals_device, int rank, int world, uint64_t shard,
+                                   const double pivot[2]);
   int enqueue_flip_adopt(uint64_t n);
   int enqueue_reduce_moments();
   int enqueue_moments(const double pivot[2]);   // raw moments stay in the device result block

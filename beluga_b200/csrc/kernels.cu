@@ -1129,20 +1129,43 @@ __device__ __forceinline__ void store_block_moments(double* m, double* scratch /
 
 __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, const Scalars* __restrict__ scalars, double* __restrict__ moment_partials) {
   __shared__ double s_red[kMomentCount * kRsThreads / kWarp];
-  const unsigned long long total = a.global_total != 0 ? a.global_total : scalars->total;
+  unsigned long long total = a.global_total != 0 ? a.global_total : scalars->total;
+  unsigned long long cdf_offset = a.cdf_offset, span_end = 0;
+  uint64_t slot_first = a.slot_first, slot_count = a.slot_count;
+  if (a.rank_totals != nullptr) {  // offsets = exclusive prefix of the ranks' totals (distributed.py: cdf_offsets)
+    total = 0;
+    cdf_offset = 0;
+    for (int r = 0; r < a.world; ++r) {
+      const unsigned long long t = a.rank_totals[r];
+      if (r < a.rank) cdf_offset += t;
+      total += t;
+    }
+    span_end = cdf_offset + a.rank_totals[a.rank];
+  }
   unsigned long long stride = 0, offset = 0;
   if (a.scheme == 1) {
     // Systematic comb: stride = T / M, offset uniform in [0, stride).
     stride = total / a.total_slots;
     offset = mulhi64(counter_draw(a.seed, 0, a.step, kStreamSystematic).a, stride);
+    if (a.rank_totals != nullptr) {
+      // The slots whose comb position offset + j*stride lies in [cdf_offset, span_end) (distributed.py: slot_ranges).
+      auto first_slot_at_or_after = [&](unsigned long long position) -> uint64_t {
+        if (position <= offset) return 0;
+        const unsigned long long j = (position - offset + stride - 1) / stride;
+        return j < a.total_slots ? j : a.total_slots;
+      };
+      slot_first = first_slot_at_or_after(cdf_offset);
+      const uint64_t slot_end = a.rank + 1 == a.world ? a.total_slots : first_slot_at_or_after(span_end);
+      slot_count = slot_end - slot_first;
+    }
   }
   double m[kMomentCount];
 #pragma unroll
   for (int k = 0; k < kMomentCount; ++k) m[k] = 0.0;
 
-  for (uint64_t local = static_cast<uint64_t>(blockIdx.x) * kRsThreads + threadIdx.x; local < a.slot_count;
+  for (uint64_t local = static_cast<uint64_t>(blockIdx.x) * kRsThreads + threadIdx.x; local < slot_count;
        local += static_cast<uint64_t>(gridDim.x) * kRsThreads) {
-    const uint64_t j = a.slot_first + local;
+    const uint64_t j = slot_first + local;
     Pose2 st;
     long long ancestor = -1;
     bool inject = false;
@@ -1152,7 +1175,7 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, co
     unsigned long long t = 0;
     if (!inject) t = a.scheme == 1 ? offset + j * stride : mulhi64(d.b, total);
     if (a.span_filter != 0) {
-      const bool mine = inject ? (j >= a.owner_first && j - a.owner_first < a.owner_count) : (t >= a.cdf_offset && t - a.cdf_offset < scalars->total);
+      const bool mine = inject ? (j >= a.owner_first && j - a.owner_first < a.owner_count) : (t >= cdf_offset && t - cdf_offset < scalars->total);
       if (!mine) continue;
     }
     if (inject) {
@@ -1167,7 +1190,7 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, co
       st = Pose2{rot.c, rot.s, (a.grid_origin.c * lx - a.grid_origin.s * ly) + a.grid_origin.x,
                  (a.grid_origin.s * lx + a.grid_origin.c * ly) + a.grid_origin.y};
     } else {
-      const uint64_t idx = cdf_upper_bound(a.cdf, a.n_in, t - a.cdf_offset);  // the caller guarantees t lies in this shard's span
+      const uint64_t idx = cdf_upper_bound(a.cdf, a.n_in, t - cdf_offset);  // the caller guarantees t lies in this shard's span
       ancestor = static_cast<long long>(idx);
       st = load_pose(a.states_in + idx);
     }

@@ -165,6 +165,11 @@ struct ResampleArgs {
   // is produced by the rank that owns the slot ([owner_first, owner_first + owner_count)).
   int span_filter;
   uint64_t owner_first, owner_count;
+  // Device-side bookkeeping of a sharded resample: when rank_totals is set (the all-gathered fixed-point
+  // totals of the ranks, in device memory) the kernel derives the global total, this rank's CDF offset and --
+  // for the systematic comb -- its slot range itself, so the host does not have to read the totals back first.
+  const unsigned long long* rank_totals;
+  int rank, world;
   int scheme;
   uint64_t seed;
   uint32_t step;

@@ -191,6 +191,7 @@ class ShardedAmcl:
             ptr, _ = self.filter.device_pointer(5)
             self._results = torch.as_tensor(_DeviceArray(ptr, (16,), "<f8"), device="cuda")
             self._totals = torch.zeros(self.world + 1, dtype=torch.int64, device="cuda")
+            self._packed = torch.zeros(9 + self.world + 1, dtype=torch.float64, device="cuda")
         return self._scalars, self._results
 
     def update(self, control_pose, points, random_state_probability=None):
@@ -219,31 +220,32 @@ class ShardedAmcl:
         f.enqueue_build_cdf()
         dist.all_gather_into_tensor(self._totals[: self.world], scalars[2:3], group=self.group)
         self._totals[self.world: self.world + 1] = scalars[3:4]
-        host = self._totals.cpu().tolist()  # synchronisation 1
-        exponent = int(np.int32(host[self.world] & 0xFFFFFFFF))
-        offsets = cdf_offsets(host[: self.world])
-        global_total = offsets[-1]
-        weight_sum = float(np.ldexp(float(global_total), -exponent))
-
-        if self.multinomial:
-            ranges = None
-        else:
-            stride, comb = _systematic_comb(self.params.seed, plan.step, global_total, self.total)
-            ranges = slot_ranges(offsets, stride, comb, self.total)
         if self.p2p:
-            # One kernel: CDF search + gather + peer stores into the owners' buffers + moments of what it produced.
-            # Systematic: this rank's contiguous slot range.  Multinomial: the draws are independent, so the kernel
-            # walks all global slots and keeps those landing in this rank's span of the global CDF.
-            ja, jb = (0, self.total) if self.multinomial else ranges[self.rank]
-            f.enqueue_resample_push(plan.opts, global_total, offsets[self.rank], ja, jb, self.shard, self.pivot)
+            # One kernel: CDF search + gather + peer stores into the owners' buffers + moments of what it produced.  It
+            # derives the CDF offsets and (systematic) this rank's contiguous slot range from the gathered totals on the
+            # device; multinomial draws are independent, so there it walks all global slots and keeps those landing in
+            # this rank's span of the global CDF.  No host read-back before the launch: one synchronisation per step.
+            f.enqueue_resample_push_device(plan.opts, self._totals.data_ptr(), self.rank, self.world, self.shard, self.pivot)
             f.enqueue_reduce_moments()
             dist.all_reduce(results[0:9], op=dist.ReduceOp.SUM, group=self.group)  # also the barrier: all peer stores are done
             f.enqueue_flip_adopt(self.shard)
+            self._packed[0:9] = results[0:9]
+            self._packed[9:] = self._totals.view(torch.float64)
+            packed = self._packed.cpu()  # the synchronisation of the step
+            moments = packed[0:9].numpy()
+            host = packed[9:].view(torch.int64).tolist()
         else:
-            self._redistribute(plan, ranges, global_total, offsets[self.rank], streamed=True)
+            host = self._totals.cpu().tolist()  # synchronisation 1
+            offsets = cdf_offsets(host[: self.world])
+            stride, comb = _systematic_comb(self.params.seed, plan.step, offsets[-1], self.total)
+            ranges = slot_ranges(offsets, stride, comb, self.total)
+            self._redistribute(plan, ranges, offsets[-1], offsets[self.rank], streamed=True)
             f.enqueue_moments(self.pivot)
             dist.all_reduce(results[0:9], op=dist.ReduceOp.SUM, group=self.group)
-        moments = results[0:9].cpu().numpy()  # synchronisation 2
+            moments = results[0:9].cpu().numpy()  # synchronisation 2
+        exponent = int(np.int32(host[self.world] & 0xFFFFFFFF))
+        global_total = cdf_offsets(host[: self.world])[-1]
+        weight_sum = float(np.ldexp(float(global_total), -exponent))
         f.synchronize()  # closes the timing marks; the stream is already idle
         from . import estimate_from_moments
 

@@ -260,6 +260,12 @@ int bb200_filter_ipc_handles(bb200_filter* f, void* out128);
 int bb200_filter_open_peers(bb200_filter* f, int world, int rank, const void* handles);
 int bb200_filter_enqueue_resample_push(bb200_filter* f, const bb200_resample_opts* o, uint64_t global_total, uint64_t cdf_offset,
                                        uint64_t slot_begin, uint64_t slot_end, uint64_t shard, const double pivot_xy[2]);
+/* The same with the bookkeeping on the device: rank_totals_device points at the `world` all-gathered
+ * fixed-point totals (uint64, device memory, rank order).  The kernel derives the global total, this
+ * rank's CDF offset and (systematic) its slot range from them, so the host need not read the totals
+ * back before launching -- one host synchronisation per step instead of two. */
+int bb200_filter_enqueue_resample_push_device(bb200_filter* f, const bb200_resample_opts* o, const uint64_t* rank_totals_device, int rank,
+                                              int world, uint64_t shard, const double pivot_xy[2]);
 int bb200_filter_enqueue_reduce_moments(bb200_filter* f);
 int bb200_filter_enqueue_flip_adopt(bb200_filter* f, uint64_t n);
 /* Ancestor index of every particle produced by the last resample (-1: injected random state). */
