@@ -3,11 +3,13 @@
 Particles are split into contiguous global index ranges, `shard` particles per rank; the map and
 the scan are replicated.  Every per-particle kernel runs on the local shard unchanged (the counter
 RNG is keyed by the GLOBAL particle index, so a particle draws the same numbers on any rank count).
-A step needs four small collectives and one redistribution:
+A step needs three small collectives and one redistribution:
 
     all_reduce(MAX)   largest weight            -> common fixed-point exponent
     all_gather        per-rank fixed-point totals -> CDF offsets (exclusive prefix) and the global total
-    all_to_all        post-resample particle states (32 B each) to the ranks that own the output slots
+    redistribution    post-resample particle states (32 B each) to the ranks that own the output slots:
+                      peer stores from the resample kernel itself (CUDA IPC over NVLink, up to 8 ranks),
+                      or resample_range + all_to_all in rounds when there is no peer access
     all_reduce(SUM)   9 raw moments             -> pose estimate (and sum w^2 when ESS is needed)
 
 Because the CDF is an INTEGER prefix sum, offsets + local CDFs equal the single-GPU CDF exactly, so the
@@ -20,8 +22,13 @@ contiguous pieces in rank order, which is already slot order.  A rank holding mo
 produces more than a shard of slots; the exchange then runs in rounds of at most one shard per rank.  `slot_ranges` / `split_counts` below
 are that bookkeeping (pure integer arithmetic, tested on CPU with gloo in tests/test_sharding_cpu.py).
 
-Scope: systematic resampling without recovery injection or KLD (the 100M-particle configuration of
-BASELINE.json); other combinations raise.
+With peer access the kernel also derives the CDF offsets and its slot range from the gathered totals on the
+device, so a resampling step has ONE host synchronisation (the estimate).  Multinomial sampling draws every
+slot independently: each rank walks all global slots and keeps those whose draw lands in its span of the CDF.
+Injected random states (views::random_intersperse) are produced by whichever rank handles the slot.
+
+Scope: systematic and (peer path) multinomial resampling, recovery injection; no KLD on shards (the particle
+count of a sharded filter is fixed); selective resampling only with the systematic comb.
 """
 from __future__ import annotations
 
@@ -211,7 +218,7 @@ class ShardedAmcl:
         return self._update_stepwise(plan, points)
 
     def _update_streamed(self, plan, points):
-        """Resampling step with everything enqueued on one stream; two host synchronisations."""
+        """Resampling step with everything enqueued on one stream: one host synchronisation with peer access, two without."""
         torch, dist, f = self.torch, self.dist, self.filter
         scalars, results = self._device_blocks()
         f.enqueue_propagate_reweight(plan.sampling, plan.step, points)
