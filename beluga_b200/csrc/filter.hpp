@@ -119,7 +119,6 @@ class Filter {
   uint64_t ancestors_n_{0};
   unsigned long long* hashes_{nullptr};
   bool cdf_valid_{false};
-  bool weights_uniform_{false};
 
   // scratch
   Scalars* scalars_{nullptr};

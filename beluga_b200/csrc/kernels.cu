@@ -26,9 +26,6 @@
 #ifndef BB200_RW_UNROLL
 #define BB200_RW_UNROLL 2
 #endif
-#ifndef BB200_RW_BLOCK_TICKETS
-#define BB200_RW_BLOCK_TICKETS 0
-#endif
 #ifndef BB200_RW_BLOCKS
 #define BB200_RW_BLOCKS 4
 #endif
@@ -305,17 +302,11 @@ __global__ void __launch_bounds__(256) schedule_scatter_kernel(const uint32_t* _
 
 constexpr int kRwThreads = BB200_RW_THREADS;  // x kRwBlocksPerSm CTAs per SM
 constexpr int kRwBlocksPerSm = BB200_RW_BLOCKS;
-constexpr int kRwUnroll = BB200_RW_UNROLL;
-constexpr bool kRwBlockTickets = BB200_RW_BLOCK_TICKETS != 0;  // persistent kernel: tasks per CTA (1) or per warp (0)  // groups of four beams in flight per thread
+constexpr int kRwUnroll = BB200_RW_UNROLL;  // groups of four beams in flight per thread
 constexpr uint32_t kChunkBeams = 2048; // beams staged per shared-memory chunk (32 KB), multiple of 4
 
-/// floor(g) as int32 for |g| < 2^31 through one round-down add: g + 1.5*2^52 has ulp 1, so the low
-/// mantissa word of the sum is floor(g) in two's complement.
-#ifndef BB200_RW_MAGIC_FLOOR  // default: F2I.FLOOR (saturating); -DBB200_RW_MAGIC_FLOOR selects the round-down-add variant
+/// floor(g) as int32 for |g| < 2^31: one F2I.F64.FLOOR (saturating).
 __device__ __forceinline__ int floor_to_int_fast(double g) { return __double2int_rd(g); }
-#else
-__device__ __forceinline__ int floor_to_int_fast(double g) { return __double2loint(__dadd_rd(g, 6755399441055744.0)); }
-#endif
 
 template <bool kFast, bool kTiled>
 __device__ __forceinline__ double field_lookup(const FieldView& f, double px, double py, double c, double s, double tx, double ty) {
@@ -573,29 +564,15 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     reweight_lfm_fixed_param_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
                                     FieldView field, uint32_t n_points, double points_radius, Scalars* __restrict__ scalars,
                                     const __grid_constant__ ScanParam scan) {
-  // A task = the next kTaskThreads particles of the schedule, drawn by a whole CTA (kRwBlockTickets: its
-  // warps then gather from neighbouring cells and share L1 lines) or by each warp on its own.
-  constexpr int kTaskThreads = kRwBlockTickets ? kRwThreads : kWarp;
-  __shared__ unsigned long long s_ticket[2];
   const int lane = threadIdx.x % kWarp;
-  const bool drawer = kRwBlockTickets ? threadIdx.x == 0 : lane == 0;
-  const unsigned long long n_tasks = (n + kTaskThreads - 1) / kTaskThreads;
+  const unsigned long long n_tasks = (n + kWarp - 1) / kWarp;  // a task = the next 32 particles of the schedule
   unsigned long long* ticket_counter = &scalars->work_ticket;
-  auto share = [&](unsigned long long mine, int parity) -> unsigned long long {
-    if (kRwBlockTickets) {
-      if (threadIdx.x == 0) s_ticket[parity] = mine;
-      __syncthreads();
-      return s_ticket[parity];
-    }
-    return __shfl_sync(0xffffffffu, mine, 0);
-  };
-  int parity = 0;
-  unsigned long long ticket = share(drawer ? atomicAdd(ticket_counter, 1ull) : 0ull, parity);
+  unsigned long long ticket = __shfl_sync(0xffffffffu, lane == 0 ? atomicAdd(ticket_counter, 1ull) : 0ull, 0);
   unsigned long long best = 0ull;
   while (ticket < n_tasks) {
     // Draw the next ticket now; its round trip to L2 hides behind this task's beams.
-    const unsigned long long next = drawer ? atomicAdd(ticket_counter, 1ull) : 0ull;
-    const uint64_t slot = ticket * kTaskThreads + (kRwBlockTickets ? threadIdx.x : lane);
+    const unsigned long long next = lane == 0 ? atomicAdd(ticket_counter, 1ull) : 0ull;
+    const uint64_t slot = ticket * kWarp + lane;
     const bool active = slot < n;  // idle lanes of the last task walk the beams with a dummy pose
     const uint64_t i = active ? (perm != nullptr ? perm[slot] : slot) : 0;
     uint32_t margin_start;
@@ -612,8 +589,7 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
       const unsigned long long bits = weight_order_bits(w);
       best = bits > best ? bits : best;
     }
-    parity ^= 1;
-    ticket = share(next, parity);
+    ticket = __shfl_sync(0xffffffffu, next, 0);
   }
 #pragma unroll
   for (int off = kWarp / 2; off > 0; off >>= 1) {

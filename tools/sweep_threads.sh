@@ -3,10 +3,10 @@
 mkdir -p gpurun_out
 log=gpurun_out/sweep_threads.log
 : > $log
-for cfg in "64 18 1" "128 9 1" "256 4 1" "64 16 1" "256 4 0" "512 2 0"; do
+for cfg in "128 8" "256 4" "512 2" "1024 1"; do
   set -- $cfg
-  BB200_RW_THREADS=$1 BB200_RW_BLOCKS=$2 BB200_RW_BLOCK_TICKETS=$3 python -m beluga_b200.build --force > /dev/null 2>&1
-  echo -n "threads=$1 blocks=$2 block_tickets=$3 " | tee -a $log
+  BB200_RW_THREADS=$1 BB200_RW_BLOCKS=$2 python -m beluga_b200.build --force > /dev/null 2>&1
+  echo -n "threads=$1 blocks=$2 " | tee -a $log
   python bench.py --steps 12 --warmup 4 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('steps/s', round(d['value'],1), 'reweight_ms', round(d['kernels_ms']['reweight_lfm'],4))" | tee -a $log
