@@ -63,6 +63,26 @@ def systematic_comb(seed: int, step: int, global_total: int, total_slots: int):
     return stride.value, offset.value
 
 
+def cluster_select_host(cells, n_particles: int, linear: float = 0.20, angular: float = 0.524, percentile: float = 0.90):
+    """Host half of the cluster-based estimate (bb200_cluster_select_host) on a list of cell records
+    (representative[4], hash, first_index, count, weight, moments[9]) in first-occurrence order.
+    -> (cluster id per cell, number of clusters, found, best, moments[9])."""
+    lib = _capi.load()
+    arr = (_capi.ClusterCell * max(len(cells), 1))()
+    for k, (rep, h, first, count, weight, moments) in enumerate(cells):
+        arr[k].representative[:] = list(rep)
+        arr[k].hash, arr[k].first_index, arr[k].count, arr[k].weight = int(h), int(first), int(count), float(weight)
+        arr[k].moments[:] = list(moments)
+    ids = (C.c_uint32 * max(len(cells), 1))()
+    n_clusters, found, best = C.c_uint32(0), C.c_int(0), C.c_uint32(0)
+    out = np.zeros(9)
+    p = _capi.ClusterParam(linear, angular, percentile)
+    st = lib.bb200_cluster_select_host(arr, len(cells), n_particles, C.byref(p), ids, C.byref(n_clusters), C.byref(found), C.byref(best), _dptr(out))
+    if st != 0:
+        raise RuntimeError(f"bb200_cluster_select_host: status {st}")
+    return np.array(ids[: len(cells)], dtype=np.uint32), n_clusters.value, bool(found.value), best.value, out
+
+
 def estimate_from_moments(moments, pivot):
     """beluga::estimate (algorithm/estimation.hpp:436-475) from globally summed raw moments."""
     e = _capi.Estimate()

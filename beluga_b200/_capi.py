@@ -64,6 +64,11 @@ class ClusterParam(C.Structure):
     _fields_ = [("linear_hash_resolution", C.c_double), ("angular_hash_resolution", C.c_double), ("weight_cap_percentile", C.c_double)]
 
 
+class ClusterCell(C.Structure):
+    _fields_ = [("representative", C.c_double * 4), ("hash", C.c_uint64), ("first_index", C.c_uint32), ("count", C.c_uint32),
+                ("weight", C.c_double), ("moments", C.c_double * 9)]
+
+
 class FilterConfig(C.Structure):
     _fields_ = [("device", C.c_int), ("capacity", C.c_uint64), ("seed", C.c_uint64), ("first_index", C.c_uint64),
                 ("global_count", C.c_uint64), ("record_ancestors", C.c_int)]
@@ -145,6 +150,8 @@ SIGNATURES = {
     "bb200_filter_cdf": (C.c_int, [_vp, _P(C.c_uint64), C.c_uint64]),
     "bb200_filter_estimate": (C.c_int, [_vp, _P(Estimate)]),
     "bb200_cluster_param_default": (None, [_P(ClusterParam)]),
+    "bb200_cluster_select_host": (C.c_int, [_P(ClusterCell), C.c_uint64, C.c_uint64, _P(ClusterParam), _P(C.c_uint32), _P(C.c_uint32), _P(C.c_int),
+                                            _P(C.c_uint32), _dbl]),
     "bb200_filter_cluster_estimate": (C.c_int, [_vp, _P(ClusterParam), _P(Estimate), _P(C.c_uint32), C.c_uint64, _P(C.c_uint32), _P(C.c_uint32)]),
     "bb200_filter_moments": (C.c_int, [_vp, _dbl, _dbl]),
     "bb200_filter_set_timing": (C.c_int, [_vp, C.c_int]),

@@ -6,6 +6,7 @@
 
 #include "../../include/beluga_b200.h"
 #include "amcl.hpp"
+#include "cluster_host.hpp"
 #include "filter.hpp"
 
 using bb200::Amcl;
@@ -231,6 +232,23 @@ int bb200_filter_cluster_estimate(bb200_filter* f, const bb200_cluster_param* p,
                                   uint32_t* n_cells, uint32_t* n_clusters) {
   BB_REQUIRE(f && p);
   return f->impl.cluster_estimate(*p, out, cluster_ids, ids_capacity, n_cells, n_clusters);
+}
+int bb200_cluster_select_host(const bb200_cluster_cell* cells, uint64_t n_cells, uint64_t n_particles, const bb200_cluster_param* p,
+                              uint32_t* cluster_of_cell, uint32_t* n_clusters, int* found, uint32_t* best, double moments_out[9]) {
+  if ((cells == nullptr && n_cells > 0) || p == nullptr || !(p->linear_hash_resolution > 0.0) || !(p->angular_hash_resolution > 0.0) ||
+      !(p->weight_cap_percentile >= 0.0) || !(p->weight_cap_percentile < 1.0))
+    return BB200_ERR_INVALID_ARGUMENT;
+  static_assert(sizeof(bb200_cluster_cell) == sizeof(bb200::HostCell), "public and internal cell records must agree");
+  const bb200::ClusterSelection sel = bb200::select_cluster(reinterpret_cast<const bb200::HostCell*>(cells), n_cells, n_particles,
+                                                            p->linear_hash_resolution, p->angular_hash_resolution, p->weight_cap_percentile);
+  if (cluster_of_cell != nullptr)
+    for (uint64_t k = 0; k < n_cells; ++k) cluster_of_cell[k] = sel.cluster_of_cell[k];
+  if (n_clusters != nullptr) *n_clusters = sel.clusters;
+  if (found != nullptr) *found = sel.found ? 1 : 0;
+  if (best != nullptr) *best = sel.best;
+  if (moments_out != nullptr)
+    for (int j = 0; j < 9; ++j) moments_out[j] = sel.moments[j];
+  return BB200_OK;
 }
 int bb200_filter_moments(bb200_filter* f, const double pivot_xy[2], double out[9]) {
   BB_REQUIRE(f && pivot_xy && out);

@@ -290,6 +290,23 @@ void bb200_cluster_param_default(bb200_cluster_param* p);
  * particle i (ids_capacity >= particle count), the number of occupied cells and of clusters. */
 int bb200_filter_cluster_estimate(bb200_filter* f, const bb200_cluster_param* p, bb200_estimate* out, uint32_t* cluster_ids,
                                   uint64_t ids_capacity, uint32_t* n_cells, uint32_t* n_clusters);
+/* The per-CELL half of the cluster-based estimate, host only (no device needed): what
+ * bb200_filter_cluster_estimate runs on the cell records its kernels produce.  cells[] lists the occupied
+ * spatial-hash cells in the order in which the particle sequence first touches them
+ * (clusterizer_detail::make_cluster_map, cluster_based_estimation.hpp:141-161).  Outputs: the cluster id of
+ * every cell (assign_clusters, :205-253), the number of clusters, whether a cluster with more than one
+ * particle exists and, if so, the id of the heaviest (cluster_based_estimate, :420-431), and the raw moments
+ * to estimate from (that cluster's, else the whole set's). */
+typedef struct bb200_cluster_cell {
+  double representative[4]; /* state of the first particle in the cell {cos, sin, x, y} */
+  uint64_t hash;            /* spatial_hash<SE2d>{linear, linear, angular}(representative) */
+  uint32_t first_index;     /* index of that first particle */
+  uint32_t count;           /* particles in the cell */
+  double weight;            /* sum of their weights, in particle order */
+  double moments[9];        /* raw moments of the cell's particles (layout of bb200_filter_moments) */
+} bb200_cluster_cell;
+int bb200_cluster_select_host(const bb200_cluster_cell* cells, uint64_t n_cells, uint64_t n_particles, const bb200_cluster_param* p,
+                              uint32_t* cluster_of_cell, uint32_t* n_clusters, int* found, uint32_t* best, double moments_out[9]);
 /* Raw weighted moments of the local shard for a multi-rank estimate:
  * {sum w, sum w^2, sum w*cos, sum w*sin, sum w*dx, sum w*dy, sum w*dx^2, sum w*dx*dy, sum w*dy^2}
  * with (dx, dy) = (x, y) - pivot. */
