@@ -109,6 +109,7 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   if (const char* v = std::getenv("BB200_SCHEDULE")) schedule_enabled_ = std::atoi(v) != 0;  // development knob: 0 disables the pose-sorted schedule
   if (const char* v = std::getenv("BB200_TILED")) tiled_layout_ = std::atoi(v) != 0;         // development knob: table layout
   if (const char* v = std::getenv("BB200_PARAM_POINTS")) param_points_ = std::atoi(v) != 0;  // development knob: scan as kernel parameters
+  if (const char* v = std::getenv("BB200_BEAM_ETA_TABLE")) beam_eta_table_ = std::atoi(v) != 0;  // development knob: tabulated beam normalisers
   if (const char* v = std::getenv("BB200_FIXED")) fixed_lookup_ = std::atoi(v) != 0;         // development knob: fixed-point lookup kernel
   if (const char* v = std::getenv("BB200_PER_BIN")) schedule_per_bin_ = std::atof(v);        // development knob: particles per pose bin
   if (const char* v = std::getenv("BB200_LEVER")) schedule_lever_ = std::atof(v);            // development knob: heading lever arm / mean range
@@ -191,6 +192,7 @@ Filter::~Filter() {
   cudaFree(table_);
   cudaFree(tiled_);
   cudaFree(bordered_);
+  cudaFree(beam_eta_);
   cudaFree(occupancy_);
   cudaFree(free_distance_);
   cudaFree(free_cells_);
@@ -574,7 +576,17 @@ int Filter::set_beam_map(const bb200_beam_param& p, const bb200_occupancy_grid& 
   occupancy_view_.resolution = g.resolution;
   occupancy_view_.inv_resolution = 1. / g.resolution;
   occupancy_view_.world_to_grid = pose_inverse(pose_from_array(g.origin));
-  beam_ = BeamParams{p.z_hit, p.z_short, p.z_max, p.z_rand, p.sigma_hit, p.lambda_short, p.beam_max_range};
+  beam_ = BeamParams{p.z_hit, p.z_short, p.z_max, p.z_rand, p.sigma_hit, p.lambda_short, p.beam_max_range, nullptr, 0};
+  cudaFree(beam_eta_);
+  beam_eta_ = nullptr;
+  if (const uint32_t entries = beam_eta_table_ ? beam_eta_entries(p.beam_max_range, g.resolution) : 0u) {
+    BB_CHECK(dev_alloc(&beam_eta_, entries));
+    launch_beam_eta_table(beam_, g.resolution, beam_eta_, entries, stream_);
+    BB_LAUNCHED("beam_eta_table");
+    BB_CHECK(cudaStreamSynchronize(stream_));
+    beam_.eta = beam_eta_;
+    beam_.eta_entries = entries;
+  }
   sensor_ = BB200_SENSOR_BEAM;
   field_host_.clear();
 

@@ -173,6 +173,8 @@ class Filter {
   uint8_t* free_distance_{nullptr};
   OccupancyView occupancy_view_{};
   BeamParams beam_{};
+  double2* beam_eta_{nullptr};
+  bool beam_eta_table_{true};
   uint32_t* free_cells_{nullptr};
   uint64_t n_free_{0};
   int grid_width_{0};

@@ -667,6 +667,7 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
 struct BeamRay {
   double far_x, far_y;  // bearing.unit_complex() * max_range  (raycasting.hpp:83)
   double z;             // measured range (beam_model.hpp:116)
+  double short_decay;   // exp(-lambda_short * z) of the short-reading term (:137-141)
 };
 
 /// regular_grid.hpp:75-78.  Clamped to +-2^28 cells so that spans of far-away end points cannot
@@ -675,8 +676,9 @@ __device__ __forceinline__ int cell_near(double p, double inv_resolution) {
   return max(-(1 << 28), min(1 << 28, __double2int_rd(p * inv_resolution)));
 }
 
-/// Distance in metres from the source cell centroid to the first non-free cell, or -1 on a miss.
-__device__ __forceinline__ double cast_ray(const OccupancyView& g, int sx, int sy, int fx, int fy, double max_range) {
+/// Distance in metres from the source cell centroid to the first non-free cell, or -1 on a miss;
+/// d2 = squared cell distance of that cell (only meaningful on a hit).
+__device__ __forceinline__ double cast_ray(const OccupancyView& g, int sx, int sy, int fx, int fy, double max_range, unsigned long long& d2) {
   int xspan = fx - sx, xstep = 1;
   if (xspan < 0) {
     xspan = -xspan;
@@ -706,6 +708,8 @@ __device__ __forceinline__ double cast_ray(const OccupancyView& g, int sx, int s
     if (d == 0) {  // !free_at: first non-free cell on the line
       const double dxm = (static_cast<double>(cx) + 0.5) * g.resolution - (static_cast<double>(sx) + 0.5) * g.resolution;
       const double dym = (static_cast<double>(cy) + 0.5) * g.resolution - (static_cast<double>(sy) + 0.5) * g.resolution;
+      const long long ix = static_cast<long long>(cx) - sx, iy = static_cast<long long>(cy) - sy;
+      d2 = static_cast<unsigned long long>(ix * ix + iy * iy);
       return fmin(sqrt(dxm * dxm + dym * dym), max_range);
     }
     // Every cell within Chebyshev distance d - 1 is free and the line moves at most one cell per step
@@ -722,15 +726,19 @@ __device__ __forceinline__ double cast_ray(const OccupancyView& g, int sx, int s
   }
 }
 
-__device__ __forceinline__ double beam_pz3(const BeamParams& p, double z, double z_mean, double n) {
+/// beam_model.hpp:128-135: the two normalisers as functions of z_mean.
+__device__ __forceinline__ double2 beam_normalisers(const BeamParams& p, double z_mean) {
   const double sqrt2 = sqrt(2.);
   const double eta_hit = 2. / (erf((p.beam_max_range - z_mean) / (sqrt2 * p.sigma_hit)) - erf(-z_mean / (sqrt2 * p.sigma_hit)));
+  const double eta_short = 1. / (1. - exp(-p.lambda_short * z_mean));
+  return make_double2(eta_hit, eta_short);
+}
+
+/// The four-term mixture cubed (beam_model.hpp:125-147); short_decay = exp(-lambda_short * z), a per-beam constant.
+__device__ __forceinline__ double beam_pz3(const BeamParams& p, double z, double short_decay, double z_mean, double n, double eta_hit, double eta_short) {
   const double d = (z - z_mean) / p.sigma_hit;
   double pz = p.z_hit * eta_hit * n * exp(-(d * d) / 2.);
-  if (z < z_mean) {
-    const double eta_short = 1. / (1. - exp(-p.lambda_short * z_mean));
-    pz += p.z_short * p.lambda_short * eta_short * exp(-p.lambda_short * z);
-  }
+  if (z < z_mean) pz += p.z_short * p.lambda_short * eta_short * short_decay;
   if (z < p.beam_max_range) {
     pz += p.z_rand / p.beam_max_range;
   } else {
@@ -739,10 +747,21 @@ __device__ __forceinline__ double beam_pz3(const BeamParams& p, double z, double
   return pz * pz * pz;
 }
 
-constexpr int kBeamThreads = 256;
-constexpr uint32_t kBeamChunk = 1024;  // rays staged per shared-memory chunk (24 KB), multiple of 4
+__global__ void __launch_bounds__(256) beam_eta_table_kernel(BeamParams p, double resolution, double2* __restrict__ table, uint32_t entries) {
+  const uint32_t k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= entries) return;
+  const double z_mean = k + 1 == entries ? p.beam_max_range : fmin(sqrt(static_cast<double>(k)) * resolution, p.beam_max_range);
+  table[k] = beam_normalisers(p, z_mean);
+}
 
-__global__ void __launch_bounds__(kBeamThreads)
+#ifndef BB200_BEAM_BLOCKS
+#define BB200_BEAM_BLOCKS 3
+#endif
+constexpr int kBeamThreads = 256;
+constexpr int kBeamBlocksPerSm = BB200_BEAM_BLOCKS;
+constexpr uint32_t kBeamChunk = 1024;  // rays staged per shared-memory chunk (32 KB), multiple of 4
+
+__global__ void __launch_bounds__(kBeamThreads, kBeamBlocksPerSm)
     reweight_beam_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
                          OccupancyView grid, BeamParams params, const double2* __restrict__ points, uint32_t n_points,
                          Scalars* __restrict__ scalars) {
@@ -768,9 +787,18 @@ __global__ void __launch_bounds__(kBeamThreads)
     const double ex = (src.c * ray.far_x - src.s * ray.far_y) + src.x;
     const double ey = (src.s * ray.far_x + src.c * ray.far_y) + src.y;
     const int fx = cell_near(ex, grid.inv_resolution), fy = cell_near(ey, grid.inv_resolution);
-    const double hit = cast_ray(grid, sx, sy, fx, fy, params.beam_max_range);
+    unsigned long long d2 = 0;
+    const double hit = cast_ray(grid, sx, sy, fx, fy, params.beam_max_range, d2);
     const double z_mean = hit >= 0.0 ? hit : params.beam_max_range;  // value_or(beam_max_range)
-    return beam_pz3(params, ray.z, z_mean, n_norm);
+    double2 eta;
+    if (params.eta != nullptr) {
+      // hit within range: the entry of its cell distance; miss or clamped to the range: the last entry
+      const bool in_table = hit >= 0.0 && hit < params.beam_max_range && d2 + 1 < params.eta_entries;
+      eta = __ldg(params.eta + (in_table ? static_cast<uint32_t>(d2) : params.eta_entries - 1u));
+    } else {
+      eta = beam_normalisers(params, z_mean);
+    }
+    return beam_pz3(params, ray.z, ray.short_decay, z_mean, n_norm, eta.x, eta.y);
   };
 
   double acc = 0.0;
@@ -781,7 +809,7 @@ __global__ void __launch_bounds__(kBeamThreads)
       const double2 p = points[base + b];
       const double z = sqrt(p.x * p.x + p.y * p.y);                      // beam_model.hpp:116
       const double bx = p.x / z, by = p.y / z;                            // :120-123
-      s_rays[b] = BeamRay{bx * params.beam_max_range, by * params.beam_max_range, z};
+      s_rays[b] = BeamRay{bx * params.beam_max_range, by * params.beam_max_range, z, exp(-params.lambda_short * z)};
     }
     __syncthreads();
     if (active) {
@@ -1291,6 +1319,17 @@ void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const
   } else {
     reweight_lfm_kernel<false><<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars);
   }
+}
+
+uint32_t beam_eta_entries(double beam_max_range, double resolution) {
+  const double cells = beam_max_range / resolution + 2.0;
+  const double entries = cells * cells + 2.0;
+  return (entries > 0.0 && entries < 8.0e6) ? static_cast<uint32_t>(entries) : 0u;  // <= 128 MB; beyond that: per-beam evaluation
+}
+
+void launch_beam_eta_table(const BeamParams& params, double resolution, double2* table, uint32_t entries, cudaStream_t stream) {
+  if (entries == 0) return;
+  beam_eta_table_kernel<<<(entries + 255) / 256, 256, 0, stream>>>(params, resolution, table, entries);
 }
 
 void launch_reweight_beam(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const OccupancyView& grid,

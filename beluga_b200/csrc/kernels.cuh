@@ -55,7 +55,16 @@ struct OccupancyView {
 
 struct BeamParams {
   double z_hit, z_short, z_max, z_rand, sigma_hit, lambda_short, beam_max_range;
+  // Normalisers of the hit and short terms (beam_model.hpp:128-141) tabulated over the squared cell
+  // distance d2 = dx^2 + dy^2 of the ray's end cell: eta[d2] = {eta_hit, eta_short} at z_mean =
+  // sqrt(d2) * resolution; the last entry is z_mean = beam_max_range (miss, or a hit beyond the range).
+  // Null: evaluate them per beam (two erf and one exp more).
+  const double2* eta;
+  uint32_t eta_entries;
 };
+/// Entries of the normaliser table, 0 when the range/resolution ratio makes it too large to be worth it.
+uint32_t beam_eta_entries(double beam_max_range, double resolution);
+void launch_beam_eta_table(const BeamParams& params, double resolution, double2* table, uint32_t entries, cudaStream_t stream);
 
 /// Mirrors bb200_motion_sampling (include/beluga_b200.h).
 struct MotionSampling {
