@@ -158,10 +158,7 @@ __global__ void __launch_bounds__(kCellThreads) cluster_cells_kernel(const Pose2
 #pragma unroll
   for (int k = 0; k < kMomentCount; ++k) m[k] = 0.0;
   bool unit = true;
-  for (uint32_t p = begin + lane; p < end; p += kWarp) {
-    const uint32_t i = sorted_idx[p];
-    const double w = weights[i];
-    const Pose2 st = load_state(states + i);
+  auto add = [&](const Pose2& st, double w) {
     const double dx = st.x - px, dy = st.y - py;
     m[0] += w;
     m[1] += w * w;
@@ -173,6 +170,20 @@ __global__ void __launch_bounds__(kCellThreads) cluster_cells_kernel(const Pose2
     m[7] += w * dx * dy;
     m[8] += w * dy * dy;
     unit = unit && w == 1.0;
+  };
+  uint32_t p = begin + lane;
+  for (; p + 3 * kWarp < end; p += 4 * kWarp) {  // four gathers in flight per lane
+    const uint32_t i0 = sorted_idx[p], i1 = sorted_idx[p + kWarp], i2 = sorted_idx[p + 2 * kWarp], i3 = sorted_idx[p + 3 * kWarp];
+    const double w0 = weights[i0], w1 = weights[i1], w2 = weights[i2], w3 = weights[i3];
+    const Pose2 s0 = load_state(states + i0), s1 = load_state(states + i1), s2 = load_state(states + i2), s3 = load_state(states + i3);
+    add(s0, w0);
+    add(s1, w1);
+    add(s2, w2);
+    add(s3, w3);
+  }
+  for (; p < end; p += kWarp) {
+    const uint32_t i = sorted_idx[p];
+    add(load_state(states + i), weights[i]);
   }
 #pragma unroll
   for (int k = 0; k < kMomentCount; ++k) {
@@ -187,11 +198,13 @@ __global__ void __launch_bounds__(kCellThreads) cluster_cells_kernel(const Pose2
   double total = static_cast<double>(end - begin);
   if (!unit) {
     total = 0.0;
+    double w = begin + lane < end ? weights[sorted_idx[begin + lane]] : 0.0;
     for (uint32_t base = begin; base < end; base += kWarp) {
-      const uint32_t p = base + lane;
-      const double w = p < end ? weights[sorted_idx[p]] : 0.0;
+      const uint32_t q = base + kWarp + lane;  // the next 32 weights travel while this batch is added up
+      const double w_next = q < end ? weights[sorted_idx[q]] : 0.0;
       const int valid = static_cast<int>(min(static_cast<uint32_t>(kWarp), end - base));
       for (int k = 0; k < valid; ++k) total = total + __shfl_sync(0xffffffffu, w, k);
+      w = w_next;
     }
   }
   if (lane == 0) {
@@ -228,8 +241,7 @@ void launch_cluster_cells_begin(const Pose2* states, uint64_t n, double linear_r
   launch_scan_u32(s.flags, s.flags, static_cast<uint32_t>(n), s.words + 0, s.tile_state, s.words + 1, stream);
 }
 
-const uint32_t* launch_cluster_cells_finish(const Pose2* states, const double* weights, uint64_t n, uint32_t cells, double pivot_x, double pivot_y,
-                                            const ClusterScratch& s, cudaStream_t stream) {
+const uint32_t* launch_cluster_sort(uint64_t n, uint32_t cells, const ClusterScratch& s, cudaStream_t stream, int* launches) {
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   const uint32_t n32 = static_cast<uint32_t>(n);
   cudaMemsetAsync(s.starts, 0, (static_cast<size_t>(cells) + 1) * sizeof(uint32_t), stream);
@@ -251,9 +263,14 @@ const uint32_t* launch_cluster_cells_finish(const Pose2* states, const double* w
     keys_out = keys_out == s.keys_a ? s.keys_b : s.keys_a;
     idx_out = idx_out == s.idx_a ? s.idx_b : s.idx_a;
   }
-  const unsigned cell_blocks = static_cast<unsigned>((static_cast<uint64_t>(cells) * kWarp + kCellThreads - 1) / kCellThreads);
-  cluster_cells_kernel<<<cell_blocks, kCellThreads, 0, stream>>>(states, weights, s.hashes, idx_in, s.starts, cells, pivot_x, pivot_y, s.records);
+  if (launches != nullptr) *launches = 2 + 3 * passes;
   return idx_in;
+}
+
+void launch_cluster_records(const Pose2* states, const double* weights, const uint32_t* sorted_idx, uint32_t cells, double pivot_x, double pivot_y,
+                            const ClusterScratch& s, cudaStream_t stream) {
+  const unsigned cell_blocks = static_cast<unsigned>((static_cast<uint64_t>(cells) * kWarp + kCellThreads - 1) / kCellThreads);
+  cluster_cells_kernel<<<cell_blocks, kCellThreads, 0, stream>>>(states, weights, s.hashes, sorted_idx, s.starts, cells, pivot_x, pivot_y, s.records);
 }
 
 }  // namespace bb200

@@ -56,10 +56,12 @@ uint32_t cluster_sort_tiles(uint64_t n);
 void launch_cluster_cells_begin(const Pose2* states, uint64_t n, double linear_resolution, double angular_resolution, const ClusterScratch& s,
                                 cudaStream_t stream);
 
-/// Cell id per particle, cell sizes, stable sort of the particle indices by cell (particle order
-/// preserved inside a cell) and one CellRecord per cell.  `cells` = value read back from words[1].
-/// Returns the buffer holding the sorted particle indices.
-const uint32_t* launch_cluster_cells_finish(const Pose2* states, const double* weights, uint64_t n, uint32_t cells, double pivot_x, double pivot_y,
-                                            const ClusterScratch& s, cudaStream_t stream);
+/// Cell id per particle, cell sizes and the stable sort of the particle indices by cell (particle order
+/// preserved inside a cell).  `cells` = value read back from words[1].  Returns the buffer holding the
+/// sorted particle indices and the number of kernels launched.
+const uint32_t* launch_cluster_sort(uint64_t n, uint32_t cells, const ClusterScratch& s, cudaStream_t stream, int* launches);
+/// One CellRecord per cell from the sorted indices.
+void launch_cluster_records(const Pose2* states, const double* weights, const uint32_t* sorted_idx, uint32_t cells, double pivot_x, double pivot_y,
+                            const ClusterScratch& s, cudaStream_t stream);
 
 }  // namespace bb200

@@ -926,9 +926,12 @@ int Filter::cluster_estimate(const bb200_cluster_param& p, bb200_estimate* out, 
     if (st != BB200_OK) return st;
   }
   mark("cluster_sort");
-  const uint32_t* sorted = launch_cluster_cells_finish(states_[cur_], weights_, n_, cells, pivot_[0], pivot_[1], cluster_, stream_);
-  (void)sorted;
-  BB_LAUNCHED_N("cluster_cells_finish", 3 + 2 * std::max(1, (static_cast<int>(std::ceil(std::log2(std::max<double>(cells, 2)))) + 7) / 8));
+  int sort_launches = 0;
+  const uint32_t* sorted = launch_cluster_sort(n_, cells, cluster_, stream_, &sort_launches);
+  BB_LAUNCHED_N("cluster_sort", sort_launches);
+  mark("cluster_records");
+  launch_cluster_records(states_[cur_], weights_, sorted, cells, pivot_[0], pivot_[1], cluster_, stream_);
+  BB_LAUNCHED("cluster_records");
   std::vector<HostCell> host(cells);
   static_assert(sizeof(HostCell) == sizeof(CellRecord), "record layouts must agree");
   BB_CHECK(cudaMemcpyAsync(host.data(), cluster_.records, static_cast<size_t>(cells) * sizeof(CellRecord), cudaMemcpyDeviceToHost, stream_));
