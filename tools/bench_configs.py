@@ -49,7 +49,7 @@ def main():
                       bb.AmclParams(min_particles=n, max_particles=n, resample_scheme=bb.RESAMPLE_MULTINOMIAL, seed=1), steps=20)
         from oracle import pyoracle as orc
 
-        for threads, tag in ((1, "cpu_seq"), (os.cpu_count(), "cpu_par")):
+        for threads, tag in ((1, "cpu_seq"), (min(os.cpu_count() or 1, 16), "cpu_par")):
             o = orc.Amcl(orc.AmclParam(min_particles=n, max_particles=n, scheme=0, seed=1, rng_mode=1, threads=threads), orc.MotionParam(*MOTION))
             o.set_map(0, orc.LfmParam(**LFM), orc.Grid(sc.cells, sc.resolution))
             o.initialize_normal(sc.initial_mean, sc.initial_cov)
@@ -71,8 +71,13 @@ def main():
                                              bb.AmclParams(min_particles=100_000, max_particles=10_000_000, resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=1,
                                                            spatial_resolution=(0.05, 0.05, float(np.deg2rad(1.0)))), steps=6, warmup=1)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
-    print(json.dumps(out, indent=1))
+    path = os.path.join(ROOT, "gpurun_out", "configs.json")
+    merged = json.load(open(path)) if os.path.exists(path) else {}
+    tag = os.environ.get("BB200_CONFIG_TAG", "")
+    merged.update({k + tag: v for k, v in out.items()})
+    json.dump(merged, open(path, "w"), indent=1)
+    for k, v in out.items():
+        print(k + tag, "e2e ms/step", round(v["ms_per_step_e2e"], 3), "kernels", v["kernels_ms"])
 
 
 if __name__ == "__main__":
