@@ -320,8 +320,8 @@ def run_native(args):
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
                          "kernel_ms": k1, "kernel_share_of_step": k1 / (dev_total_ms / args.steps),
                          "step_achieved_gbs": step_bytes / (dev_total_ms / args.steps * 1e-3) / 1e9,
-                         "note": "the lookups are served by L1/L2 (field is L2 resident); the kernel is co-limited by the FP64 pipe, "
-                                 "the L1 tag stage and instruction issue, see profiles/ and DESIGN.md"},
+                         "note": "the lookups are served by L1/L2 (the field is L2 resident, DRAM traffic = `traffic`); the kernel is bound by "
+                                 "instruction issue (71 %), the L1 data pipe (69 %) and the latency of the gather, see profiles/ and DESIGN.md"},
             "kernels_ms": {name: float(np.mean(v)) for name, v in kernel_ms.items()},
             "clocks": clocks.summary(),
         }
