@@ -698,6 +698,8 @@ __device__ __forceinline__ double cast_ray(const OccupancyView& g, int sx, int s
     reversed = true;
   }
   const int dxspan = 2 * xspan, dyspan = 2 * yspan;
+  const bool small_span = xspan < (1 << 22);  // then error + 255 * dyspan stays below 2^31
+  const double inv_dxspan = 1.0 / static_cast<double>(dxspan);
   int error = xspan;
   int step = 0;
   for (;;) {
@@ -720,7 +722,17 @@ __device__ __forceinline__ double cast_ray(const OccupancyView& g, int sx, int s
     step += k;
     x += k * xstep;
     const long long t = static_cast<long long>(error) + static_cast<long long>(k) * dyspan;
-    const int m = static_cast<int>((t - 1) / dxspan);
+    int m;  // floor((t - 1) / dxspan)
+    if (small_span) {
+      // t - 1 < 2^31 here: the product with the rounded reciprocal is within one of the quotient; one
+      // correction step makes it exact (a 64-bit integer division costs more than the rest of the loop).
+      const long long tm1 = t - 1;
+      m = __double2int_rd(static_cast<double>(tm1) * inv_dxspan);
+      const long long r = tm1 - static_cast<long long>(m) * dxspan;
+      m += r >= dxspan ? 1 : (r < 0 ? -1 : 0);
+    } else {
+      m = static_cast<int>((t - 1) / dxspan);
+    }
     y += m * ystep;
     error = static_cast<int>(t - static_cast<long long>(m) * dxspan);
   }
