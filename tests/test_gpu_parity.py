@@ -138,6 +138,36 @@ def test_reweight_lfm_bit_exact(bb, orc, scene, n_points, sensor):
         assert np.allclose(got[~normal], exp[~normal], rtol=1e-6, atol=1e-320)
 
 
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 255, 257])
+@pytest.mark.parametrize("n_points", [7, 1920, 1921])
+def test_reweight_ragged_particle_counts(bb, orc, scene, n, n_points):
+    """Particle counts around the 32-particle task size of the persistent kernel, and scans on either side of
+    the kernel-parameter limit (1920 points: constant bank; 1921: TMA + shared memory)."""
+    rng = np.random.default_rng(100 * n + n_points)
+    extent = scene.cells.shape[0] * scene.resolution
+    states = random_states(orc, rng, n, extent)
+    pts = rng.uniform(-6.0, 6.0, (n_points, 2))
+    params = dict(max_obstacle_distance=2.0, max_laser_distance=100.0, z_hit=0.5, z_random=0.5, sigma_hit=0.2)
+    got = gpu_weights(bb, 0, bb.LikelihoodFieldModelParam(**params), scene.cells, scene.resolution, orc.IDENTITY, pts, states)
+    exp = orc.sensor_weights(0, orc.LfmParam(**params), orc.Grid(scene.cells, scene.resolution), pts, states)
+    assert np.array_equal(got, exp)
+
+
+def test_reweight_twice_reuses_the_ticket_counter(bb, orc, scene):
+    """Two launches in a row on one filter: the persistent kernel's last warp must rewind its ticket counter."""
+    rng = np.random.default_rng(8)
+    states = random_states(orc, rng, 5000, scene.cells.shape[0] * scene.resolution)
+    pts = rng.uniform(-6.0, 6.0, (64, 2))
+    params = dict(max_obstacle_distance=2.0, max_laser_distance=100.0, z_hit=0.5, z_random=0.5, sigma_hit=0.2)
+    f = bb.Filter(capacity=len(states))
+    f.set_likelihood_field_map(bb.LikelihoodFieldModelParam(**params), bb.OccupancyGrid(scene.cells, scene.resolution, orc.IDENTITY))
+    f.set_particles(states)
+    f.reweight(pts)
+    f.reweight(pts)
+    once = orc.sensor_weights(0, orc.LfmParam(**params), orc.Grid(scene.cells, scene.resolution), pts, states)
+    assert np.array_equal(f.particles()[1], once * once)
+
+
 def test_reweight_far_away_particles(bb, orc, scene):
     """Coordinates beyond the fast floor range take the general path; all land out of the grid."""
     states = np.array([orc.se2(1e12, -3e11, 0.3), orc.se2(-1e300, 1e300, 1.0), orc.se2(2.0, 2.0, 0.0), orc.se2(5e9, 5e9, 0.0),
