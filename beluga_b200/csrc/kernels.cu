@@ -17,6 +17,7 @@
 // reference's operation order without FMA contraction (the file is compiled with -fmad=false).
 #include "kernels.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 // Tuning knobs of the reweight kernel (overridable with -D from beluga_b200/build.py).
@@ -1224,6 +1225,84 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, co
   store_block_moments<kRsThreads>(m, s_red, moment_partials + static_cast<size_t>(blockIdx.x) * kMomentCount);
 }
 
+// ---- resample, scatter form (systematic comb on one GPU) ----------------------------------------------
+// With the comb t_j = offset + j * stride the slots that pick particle i are exactly those with
+// cdf[i-1] <= t_j < cdf[i]: a contiguous slot range [ja, jb) that follows from two integer divisions.
+// So instead of a binary search per SLOT (20 dependent probes of the CDF) every PARTICLE reads its two
+// CDF entries and stores its state jb - ja times.  Same ancestors as resample_kernel by construction
+// (the parity tests compare them with the oracle's lower_bound search); the raw moments are summed per
+// particle (count * term) instead of per slot, which moves the estimate at rounding level only.
+
+__device__ __forceinline__ uint64_t comb_slots_before(unsigned long long position, unsigned long long offset, unsigned long long stride,
+                                                     uint64_t total_slots) {
+  if (position <= offset) return 0;  // number of slots j with offset + j * stride < position
+  const unsigned long long j = (position - offset + stride - 1) / stride;
+  return j < total_slots ? j : total_slots;
+}
+
+__global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleArgs a, const Scalars* __restrict__ scalars,
+                                                                     double* __restrict__ moment_partials) {
+  __shared__ double s_red[kMomentCount * kRsThreads / kWarp];
+  const unsigned long long total = scalars->total;
+  const unsigned long long stride = total / a.total_slots;
+  const unsigned long long offset = mulhi64(counter_draw(a.seed, 0, a.step, kStreamSystematic).a, stride);
+  const int lane = threadIdx.x % kWarp;
+  double m[kMomentCount];
+#pragma unroll
+  for (int k = 0; k < kMomentCount; ++k) m[k] = 0.0;
+
+  const uint64_t n_padded = (a.n_in + kWarp - 1) / kWarp * kWarp;  // whole warps stay in the loop for the cooperative stores
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kRsThreads + threadIdx.x; i < n_padded; i += static_cast<uint64_t>(gridDim.x) * kRsThreads) {
+    uint64_t ja = 0, jb = 0;
+    if (i < a.n_in) {
+      ja = comb_slots_before(i > 0 ? a.cdf[i - 1] : 0ull, offset, stride, a.total_slots);
+      jb = comb_slots_before(a.cdf[i], offset, stride, a.total_slots);
+    }
+    const uint64_t copies = jb - ja;
+    Pose2 st{1.0, 0.0, 0.0, 0.0};
+    if (copies > 0) {
+      st = load_pose(a.states_in + i);
+      const double c = static_cast<double>(copies), dx = st.x - a.pivot_x, dy = st.y - a.pivot_y;
+      m[0] += c;  // every copy has weight 1: sum w = sum w^2 = copies
+      m[1] += c;
+      m[2] += c * st.c;
+      m[3] += c * st.s;
+      m[4] += c * dx;
+      m[5] += c * dy;
+      m[6] += c * (dx * dx);
+      m[7] += c * (dx * dy);
+      m[8] += c * (dy * dy);
+    }
+    constexpr uint64_t kOwnCopies = 4;  // up to this many copies a thread stores itself
+    if (copies <= kOwnCopies) {
+      for (uint64_t j = ja; j < jb; ++j) {
+        store_pose(a.states_out + j, st);
+        if (a.weights_out != nullptr) a.weights_out[j] = 1.0;  // make_from_state (particle_traits.hpp:105)
+        if (a.ancestors != nullptr) a.ancestors[j] = static_cast<long long>(i);
+      }
+    }
+    // Heavy particles: the warp stores their copies together, 32 slots per round.
+    unsigned heavy = __ballot_sync(0xffffffffu, copies > kOwnCopies);
+    while (heavy != 0u) {
+      const int src = __ffs(heavy) - 1;
+      heavy &= heavy - 1u;
+      const uint64_t hja = __shfl_sync(0xffffffffu, ja, src), hjb = __shfl_sync(0xffffffffu, jb, src);
+      const uint64_t hi = __shfl_sync(0xffffffffu, i, src);
+      Pose2 hs;
+      hs.c = __shfl_sync(0xffffffffu, st.c, src);
+      hs.s = __shfl_sync(0xffffffffu, st.s, src);
+      hs.x = __shfl_sync(0xffffffffu, st.x, src);
+      hs.y = __shfl_sync(0xffffffffu, st.y, src);
+      for (uint64_t j = hja + lane; j < hjb; j += kWarp) {
+        store_pose(a.states_out + j, hs);
+        if (a.weights_out != nullptr) a.weights_out[j] = 1.0;
+        if (a.ancestors != nullptr) a.ancestors[j] = static_cast<long long>(hi);
+      }
+    }
+  }
+  store_block_moments<kRsThreads>(m, s_red, moment_partials + static_cast<size_t>(blockIdx.x) * kMomentCount);
+}
+
 // ---- moments / reductions -------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(kStreamThreads) moments_kernel(const Pose2* __restrict__ states, const double* __restrict__ weights, uint64_t n,
@@ -1296,6 +1375,14 @@ void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uin
   schedule_histogram_kernel<<<blocks, 256, 0, stream>>>(states, n, sched, bins, counters);
   scan_u32_kernel<<<schedule_tile_count(), kScanThreads, 0, stream>>>(counters, counters, kMaxBins, &sched->tile_ticket, tile_state, nullptr);
   schedule_scatter_kernel<<<blocks, 256, 0, stream>>>(bins, n, counters, perm);
+}
+
+bool scatter_resample_enabled() {
+  static const bool enabled = [] {
+    const char* v = std::getenv("BB200_SCATTER_RESAMPLE");  // development knob
+    return v == nullptr || std::atoi(v) != 0;
+  }();
+  return enabled;
 }
 
 int sm_count() {
@@ -1411,6 +1498,14 @@ uint32_t resample_block_count(uint64_t slots) {
 }
 
 void launch_resample(const ResampleArgs& args, const Scalars* scalars, double* moment_partials, cudaStream_t stream) {
+  // The whole set on one GPU with the systematic comb and nothing per slot to draw: scatter form.
+  const bool scatter = args.scheme == 1 && args.random_state_probability <= 0.0 && args.hashes == nullptr && args.peer_count == 0 &&
+                       args.rank_totals == nullptr && args.span_filter == 0 && args.global_total == 0 && args.cdf_offset == 0 &&
+                       args.slot_first == 0 && args.slot_count == args.total_slots && scatter_resample_enabled();
+  if (scatter) {
+    resample_scatter_kernel<<<resample_block_count(args.slot_count), kRsThreads, 0, stream>>>(args, scalars, moment_partials);
+    return;
+  }
   resample_kernel<<<resample_block_count(args.slot_count), kRsThreads, 0, stream>>>(args, scalars, moment_partials);
 }
 

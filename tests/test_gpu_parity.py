@@ -297,6 +297,35 @@ def test_cdf_and_indices_bit_exact(bb, orc, n):
         assert np.all(w[anc] > 0.0)
 
 
+@pytest.mark.parametrize("case", ["collapse", "few_heavy", "resize_up", "resize_down"])
+def test_systematic_resample_degenerate_weights(bb, orc, case):
+    """The scatter-form systematic resample: one particle taking (almost) every slot, a handful of heavy
+    particles among dust, and output sizes different from the input size."""
+    rng = np.random.default_rng(5)
+    n = 20_000
+    m = {"resize_up": 50_000, "resize_down": 3_000}.get(case, n)
+    w = np.full(n, 1e-12)
+    if case == "collapse":
+        w[12_345] = 1.0
+    elif case == "few_heavy":
+        w[rng.integers(0, n, 7)] = rng.uniform(0.5, 2.0, 7)
+    else:
+        w = rng.gamma(0.3, 1.0, n) + 1e-9
+    states = np.tile(orc.IDENTITY, (n, 1))
+    states[:, 2] = np.arange(n)
+    f = bb.Filter(capacity=max(n, m), seed=77, record_ancestors=True)
+    f.set_particles(states, w)
+    f.build_cdf()
+    idx, _, _ = orc.resample_indices(w, bb.RESAMPLE_SYSTEMATIC, seed=77, step=9, m=m, n_total=max(n, m))  # the exponent follows the capacity
+    assert f.resample(bb.RESAMPLE_SYSTEMATIC, step=9, max_particles=m) == m
+    assert np.array_equal(f.ancestors(), idx)
+    new_states, new_w = f.particles()
+    assert np.array_equal(new_states[:, 2], idx.astype(np.float64)) and np.all(new_w == 1.0)
+    mean, cov = f.estimate()
+    want_mean, want_cov = orc.estimate(states[idx], np.ones(m))
+    assert np.allclose(mean, want_mean, atol=1e-9) and np.allclose(cov[:2, :2], want_cov[:2, :2], rtol=1e-9, atol=1e-9)
+
+
 def test_normalize_and_ess(bb, orc):
     rng = np.random.default_rng(8)
     n = 50_000
