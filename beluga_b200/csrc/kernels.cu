@@ -1243,7 +1243,17 @@ __device__ __forceinline__ uint64_t comb_slots_before(unsigned long long positio
 __global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleArgs a, const Scalars* __restrict__ scalars,
                                                                      double* __restrict__ moment_partials) {
   __shared__ double s_red[kMomentCount * kRsThreads / kWarp];
-  const unsigned long long total = scalars->total;
+  // One GPU: the local CDF is the global one.  Sharded (rank_totals set): positions shift by the totals of
+  // the lower ranks and every copy goes to the rank that owns its slot, over NVLink peer memory.
+  unsigned long long total = scalars->total, cdf_offset = 0;
+  if (a.rank_totals != nullptr) {
+    total = 0;
+    for (int r = 0; r < a.world; ++r) {
+      const unsigned long long t = a.rank_totals[r];
+      if (r < a.rank) cdf_offset += t;
+      total += t;
+    }
+  }
   const unsigned long long stride = total / a.total_slots;
   const unsigned long long offset = mulhi64(counter_draw(a.seed, 0, a.step, kStreamSystematic).a, stride);
   const int lane = threadIdx.x % kWarp;
@@ -1251,12 +1261,23 @@ __global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleAr
 #pragma unroll
   for (int k = 0; k < kMomentCount; ++k) m[k] = 0.0;
 
+  auto store_copy = [&](uint64_t j, const Pose2& st, uint64_t ancestor) {
+    if (a.peer_count > 0) {
+      const uint64_t owner = j / a.peer_shard;
+      store_pose(a.peer_out[owner] + (j - owner * a.peer_shard), st);
+    } else {
+      store_pose(a.states_out + j, st);
+      if (a.weights_out != nullptr) a.weights_out[j] = 1.0;  // make_from_state (particle_traits.hpp:105)
+      if (a.ancestors != nullptr) a.ancestors[j] = static_cast<long long>(ancestor);
+    }
+  };
+
   const uint64_t n_padded = (a.n_in + kWarp - 1) / kWarp * kWarp;  // whole warps stay in the loop for the cooperative stores
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kRsThreads + threadIdx.x; i < n_padded; i += static_cast<uint64_t>(gridDim.x) * kRsThreads) {
     uint64_t ja = 0, jb = 0;
     if (i < a.n_in) {
-      ja = comb_slots_before(i > 0 ? a.cdf[i - 1] : 0ull, offset, stride, a.total_slots);
-      jb = comb_slots_before(a.cdf[i], offset, stride, a.total_slots);
+      ja = comb_slots_before(cdf_offset + (i > 0 ? a.cdf[i - 1] : 0ull), offset, stride, a.total_slots);
+      jb = comb_slots_before(cdf_offset + a.cdf[i], offset, stride, a.total_slots);
     }
     const uint64_t copies = jb - ja;
     Pose2 st{1.0, 0.0, 0.0, 0.0};
@@ -1275,11 +1296,7 @@ __global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleAr
     }
     constexpr uint64_t kOwnCopies = 4;  // up to this many copies a thread stores itself
     if (copies <= kOwnCopies) {
-      for (uint64_t j = ja; j < jb; ++j) {
-        store_pose(a.states_out + j, st);
-        if (a.weights_out != nullptr) a.weights_out[j] = 1.0;  // make_from_state (particle_traits.hpp:105)
-        if (a.ancestors != nullptr) a.ancestors[j] = static_cast<long long>(i);
-      }
+      for (uint64_t j = ja; j < jb; ++j) store_copy(j, st, i);
     }
     // Heavy particles: the warp stores their copies together, 32 slots per round.
     unsigned heavy = __ballot_sync(0xffffffffu, copies > kOwnCopies);
@@ -1293,11 +1310,7 @@ __global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleAr
       hs.s = __shfl_sync(0xffffffffu, st.s, src);
       hs.x = __shfl_sync(0xffffffffu, st.x, src);
       hs.y = __shfl_sync(0xffffffffu, st.y, src);
-      for (uint64_t j = hja + lane; j < hjb; j += kWarp) {
-        store_pose(a.states_out + j, hs);
-        if (a.weights_out != nullptr) a.weights_out[j] = 1.0;
-        if (a.ancestors != nullptr) a.ancestors[j] = static_cast<long long>(hi);
-      }
+      for (uint64_t j = hja + lane; j < hjb; j += kWarp) store_copy(j, hs, hi);
     }
   }
   store_block_moments<kRsThreads>(m, s_red, moment_partials + static_cast<size_t>(blockIdx.x) * kMomentCount);
@@ -1499,9 +1512,11 @@ uint32_t resample_block_count(uint64_t slots) {
 
 void launch_resample(const ResampleArgs& args, const Scalars* scalars, double* moment_partials, cudaStream_t stream) {
   // The whole set on one GPU with the systematic comb and nothing per slot to draw: scatter form.
-  const bool scatter = args.scheme == 1 && args.random_state_probability <= 0.0 && args.hashes == nullptr && args.peer_count == 0 &&
-                       args.rank_totals == nullptr && args.span_filter == 0 && args.global_total == 0 && args.cdf_offset == 0 &&
-                       args.slot_first == 0 && args.slot_count == args.total_slots && scatter_resample_enabled();
+  // (Sharded with peer memory and device-side totals: the same, every copy stored into its owner's buffer.)
+  const bool plain = args.scheme == 1 && args.random_state_probability <= 0.0 && args.hashes == nullptr && args.span_filter == 0 &&
+                     args.global_total == 0 && args.cdf_offset == 0 && args.slot_first == 0 && scatter_resample_enabled();
+  const bool scatter = plain && ((args.peer_count == 0 && args.rank_totals == nullptr && args.slot_count == args.total_slots) ||
+                                 (args.peer_count > 0 && args.rank_totals != nullptr));
   if (scatter) {
     resample_scatter_kernel<<<resample_block_count(args.slot_count), kRsThreads, 0, stream>>>(args, scalars, moment_partials);
     return;
