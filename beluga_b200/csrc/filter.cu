@@ -150,6 +150,11 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
 
 Filter::~Filter() {
   if (stream_ != nullptr) cudaStreamSynchronize(stream_);
+  for (int r = 0; r < peer_world_; ++r) {  // unmap the peers' state buffers (CUDA IPC)
+    if (r == peer_rank_) continue;
+    for (int b = 0; b < 2; ++b)
+      if (peer_states_[b][r] != nullptr) cudaIpcCloseMemHandle(peer_states_[b][r]);
+  }
   for (auto& e : event_pool_) cudaEventDestroy(e);
   cudaFree(states_[0]);
   cudaFree(states_[1]);
@@ -331,6 +336,7 @@ int Filter::ipc_handles(void* out128) {
 int Filter::open_peers(int world, int rank, const void* handles) {
   if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(BB200_ERR_INVALID_ARGUMENT, "peer groups hold 1..8 ranks");
   BB_CHECK(cudaSetDevice(config_.device));
+  if (peer_world_ != 0) return fail(BB200_ERR_STATE, "the peers' buffers are already mapped");
   const auto* all = static_cast<const cudaIpcMemHandle_t*>(handles);
   for (int r = 0; r < world; ++r) {
     for (int b = 0; b < 2; ++b) {
