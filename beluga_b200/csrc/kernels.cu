@@ -149,6 +149,8 @@ __global__ void begin_step_kernel(Scalars* s) {
   s->exponent = 0;
   s->valid = 0;
   s->kld_cutoff = ~0ull;
+  s->work_ticket = 0;  // normally rewound by the persistent reweight kernel itself; a step starts clean regardless
+  s->work_done = 0;
 }
 
 // ---- initialize_normal (a16) ---------------------------------------------------------------------
