@@ -32,6 +32,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# The CPU reference runs OpenMP teams on a CPU quota (cgroup): spinning idle threads burn the quota and get the
+# whole process throttled (8 threads on 20k particles: 264 ms/step spinning, 33 ms/step sleeping).  Must be set
+# before libgomp initialises.
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
 METRIC = "MCL filter-steps/sec at 1M particles x 1080 beams (likelihood field, 2000x2000 grid, systematic resample)"
 UNIT = "steps/s"
