@@ -151,6 +151,7 @@ def cpu_reference_steps_per_s(args, scenario, n_full, sample_particles, steps=3)
     Thread count: the better of 1x and 2x the usable CPUs (what the host can give the reference)."""
     from oracle import pyoracle as orc
 
+    native = orc.use_native_build()  # -O3 -march=native on this host (SURVEY 8d); same results as the portable build
     n = min(sample_particles, n_full)
     best = None
     cpus = usable_cpus()
@@ -169,7 +170,7 @@ def cpu_reference_steps_per_s(args, scenario, n_full, sample_particles, steps=3)
     dt, threads = best
     full_step_s = dt * (n_full / n)
     return {
-        "value": 1.0 / full_step_s, "unit": UNIT, "cores": threads, "kind": "port", "usable_cpus": cpus,
+        "value": 1.0 / full_step_s, "unit": UNIT, "cores": threads, "kind": "port", "usable_cpus": cpus, "build": "-O3 -march=native" if native else "-O3",
         "sample": f"{steps} steps of {n} particles x {args.beams} beams on the same map/scans, {dt * 1e3:.1f} ms/step with {threads} OpenMP threads "
                   f"({cpus} usable CPUs), scaled x{n_full / n:.0f} to {n_full} particles",
     }

@@ -16,13 +16,52 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
 
+_SOURCES = ("oracle_capi.cpp", "amcl_oracle.hpp", "beluga_oracle.hpp", "cluster_oracle.hpp", "se2.hpp", "Makefile")
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with the recipe committed in oracle/Makefile."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "amcl_oracle.hpp", "beluga_oracle.hpp", "se2.hpp", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in _SOURCES]
     stale = force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if stale:
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     return _LIB_PATH
+
+
+def _cpu_stamp() -> str:
+    """Identifies the host CPU: a -march=native build must not run on another machine."""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                import hashlib
+
+                return hashlib.sha1(line.encode()).hexdigest()[:16]
+    except OSError:
+        pass
+    return "unknown"
+
+
+def use_native_build() -> bool:
+    """Timing legs only (bench.py): switch to a -march=native build of the same sources, compiled on this machine
+    (make native).  Must run before the first oracle call.  Returns False (and keeps the portable build) if the
+    library is already loaded or the build fails."""
+    global _LIB_PATH
+    if _lib is not None:
+        return False
+    native = os.path.join(_HERE, "_build", "native", "liboracle.so")
+    stamp_path = native + ".cpu"
+    stamp = _cpu_stamp()
+    srcs = [os.path.join(_HERE, f) for f in _SOURCES]
+    fresh = (os.path.exists(native) and os.path.exists(stamp_path) and open(stamp_path).read() == stamp and
+             all(os.path.getmtime(s) <= os.path.getmtime(native) for s in srcs))
+    if not fresh:
+        if subprocess.run(["make", "-C", _HERE, "-s", "-B", "native"]).returncode != 0:
+            return False
+        with open(stamp_path, "w") as f:
+            f.write(stamp)
+    _LIB_PATH = native
+    globals()["build"] = lambda force=False: native  # lib() must not fall back to rebuilding the portable library
+    return True
 
 
 class LfmParam(C.Structure):

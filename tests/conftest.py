@@ -17,5 +17,7 @@ def orc():
     """The CPU parity oracle (test infrastructure; see oracle/)."""
     from oracle import pyoracle
 
+    if os.environ.get("BB200_ORACLE_NATIVE"):  # check that the -march=native timing build gives the same answers
+        assert pyoracle.use_native_build()
     pyoracle.build()
     return pyoracle
