@@ -136,6 +136,48 @@ def test_lfm_grid_updates(orc):  # :160-203
     assert lfm_weight(orc, grid5(orc, []), [(1.0, 1.0)], orc.IDENTITY) == pytest.approx(1.0, abs=1e-3)
 
 
+# ---- sensor/test_lfm_with_unknown_space.cpp ----------------------------------------------------
+U, O = -1, 100  # unknown, occupied
+
+
+def unknown_params(orc, max_laser_distance, strict=False):
+    return orc.LfmParam(2.0, max_laser_distance, 0.5, 0.5, 0.2, True, strict)
+
+
+def test_unknown_space_likelihood_field(orc):  # LikelihoodField :34-95
+    grid = orc.Grid(np.array([[U, U, U, O, O], [U, 0, 0, 0, O], [U, 0, 0, 0, O], [O, 0, 0, 0, O], [O, O, O, O, O]], dtype=np.int8), 0.5)
+    k = 1 / 20.0  # kUnknownSpaceLikelihood
+    expected = [k, k, k, 1.022, 1.022, k, 0.025, 0.027, 0.069, 1.022, k, 0.027, 0.025, 0.069, 1.022,
+                1.022, 0.069, 0.069, 0.069, 1.022, 1.022, 1.022, 1.022, 1.022, 1.022]
+    assert orc.likelihood_field(unknown_params(orc, 20.0), grid).reshape(-1) == pytest.approx(expected, abs=0.003)
+    expected_strict = [k, k, k, 1.022, k, k, 0.025, 0.027, 0.069, 1.022, k, 0.027, 0.025, 0.069, 1.022,
+                       1.022, 0.069, 0.069, 0.069, 1.022, k, 1.022, 1.022, 1.022, k]  # kPreProcessThickWalls
+    assert orc.likelihood_field(unknown_params(orc, 20.0, strict=True), grid).reshape(-1) == pytest.approx(expected_strict, abs=0.003)
+
+
+def test_unknown_space_likelihood_field_2(orc):  # LikelihoodField2 :97-138
+    grid = orc.Grid(np.array([[U, U, U, O, O], [U, U, U, 0, 0], [U, U, U, 0, 0], [U, U, U, 0, 0], [U, U, U, O, O]], dtype=np.int8), 0.5)
+    k = 1 / 100.0
+    expected = [k, k, k, 1.002, 1.002, k, k, k, 0.049, 0.049, k, k, k, 0.005, 0.005, k, k, k, 0.049, 0.049, k, k, k, 1.002, 1.002]
+    assert orc.likelihood_field(unknown_params(orc, 100.0), grid).reshape(-1) == pytest.approx(expected, abs=0.003)
+
+
+def test_unknown_space_importance_weight(orc):  # ImportanceWeight :140-198
+    grid = orc.Grid(np.array([[U, U, U, 0, 0], [U, 0, 0, 0, 0], [U, 0, O, 0, U], [0, 0, 0, 0, U], [0, 0, U, U, U]], dtype=np.int8), 0.5)
+    p = unknown_params(orc, 20.0)
+    k3 = (1 / 20.0) ** 3
+
+    def weight(points, state):
+        return orc.sensor_weights(0, p, grid, points, [state])[0]
+
+    assert weight([(0.0, 0.0)], grid.origin) == pytest.approx(1.000 + k3, abs=0.003)
+    assert weight([(1.25, 1.25)], grid.origin) == pytest.approx(2.068, abs=0.003)
+    assert weight([(2.25, 2.25)], grid.origin) == pytest.approx(1.000 + k3, abs=0.003)
+    assert weight([(-50.0, 50.0)], grid.origin) == pytest.approx(1.000, abs=0.003)
+    assert weight([(1.20, 1.20), (1.25, 1.25), (1.30, 1.30)], grid.origin) == pytest.approx(4.205, abs=0.01)
+    assert weight([(0.0, 0.0)], orc.se2(1.25, 1.25, 0.0)) == pytest.approx(2.068, abs=0.003)
+
+
 # ---- sensor/test_likelihood_field_prob_model.cpp:160-195 --------------------------------------
 def test_lfm_prob_grid_updates(orc):
     assert lfm_weight(orc, grid5(orc, [(2, 2)]), [(1.0, 1.0)], orc.IDENTITY, kind=1) == pytest.approx(1.0223556756973267, abs=1e-6)
