@@ -518,3 +518,40 @@ def test_stationary_model(orc, mode):  # motion/stationary_model.hpp:52-60: N(0,
     assert ang.mean() == pytest.approx(0.5, abs=5e-4) and ang.std() == pytest.approx(0.02, abs=5e-4)
     assert out[:, 2].mean() == pytest.approx(1.0, abs=5e-4) and out[:, 2].std() == pytest.approx(0.02, abs=5e-4)
     assert out[:, 3].mean() == pytest.approx(-2.0, abs=5e-4) and out[:, 3].std() == pytest.approx(0.02, abs=5e-4)
+
+
+# ---- policies/test_on_motion.cpp:24-42, test_every_n.cpp:23-45 -- through oracle::Amcl::update --------
+def policy_filter(orc, **kw):
+    o = orc.Amcl(orc.AmclParam(min_particles=50, max_particles=50, seed=3, rng_mode=1, **kw), orc.MotionParam(0.1, 0.05, 0.1, 0.05))
+    o.set_map(orc.LFM, orc.LfmParam(2.0, 20.0, 0.5, 0.5, 0.2), grid5(orc, [(2, 2)]))
+    o.initialize_normal([1.0, 1.0, 0.0], np.diag([0.01, 0.01, 0.01]))
+    return o
+
+
+POINTS = [(0.5, 0.5)]
+
+
+def test_on_motion_policy_triggers_on_motion(orc):  # TriggerOnMotion2D
+    o = policy_filter(orc, update_min_d=0.1, update_min_a=0.05)
+    pose1, pose2 = orc.se2(1.0, 2.0, 0.2), orc.se2(1.2, 2.2, 0.25)
+    assert o.update(pose1, POINTS).updated == 1  # the first pose triggers the policy
+    assert o.update(pose1, POINTS).updated == 0  # the same pose does not
+    assert o.update(pose2, POINTS).updated == 1
+
+
+def test_on_motion_policy_ignores_small_motion(orc):  # NoTriggerWithoutMotion2D
+    o = policy_filter(orc, update_min_d=0.1, update_min_a=0.05)
+    assert o.update(orc.se2(1.0, 2.0, 0.1), POINTS).updated == 1
+    assert o.update(orc.se2(1.05, 2.05, 0.1), POINTS).updated == 0
+
+
+@pytest.mark.parametrize("n,expected", [(3, [0, 0, 1]), (4, [0, 0, 0]), (2, [0, 1, 0, 1])])
+def test_every_n_policy(orc, n, expected):  # TriggerOnNthCall, NoTriggerBeforeN, TriggerOnMultipleN
+    o = policy_filter(orc, resample_interval=n)
+    got = []
+    for k in range(len(expected)):
+        o.force_update()
+        r = o.update(orc.se2(1.0 + 0.01 * k, 1.0, 0.0), POINTS)
+        assert r.updated == 1
+        got.append(int(r.resampled))
+    assert got == expected
