@@ -330,7 +330,7 @@ def run_native(args):
             "kernels_ms": {name: float(np.mean(v)) for name, v in kernel_ms.items()},
             "clocks": clocks.summary(),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # timed beside the GPU arm on rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_reference_steps_per_s(args, scenario, n_total, args.cpu_sample)
         print(json.dumps(line), flush=True)
     if world > 1:
