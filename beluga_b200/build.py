@@ -67,8 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.run([nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-ccbin", "/usr/bin/g++"],
-                   check=True)
+    subprocess.run([nvcc(), "-shared", "-cudart", "static", "-o", LIB, *objs, "-ccbin", "/usr/bin/g++"], check=True)
     return LIB
 
 
