@@ -33,8 +33,17 @@ ClusterSelection select_cluster(const HostCell* cells, std::size_t n_cells, std:
   // The same container, reserve and insertion sequence as make_cluster_map (:143-158): with
   // libstdc++ the iteration order of the map -- which seeds the heap below and therefore decides
   // between equally heavy cells -- is a function of exactly that sequence.
-  std::unordered_map<std::size_t, Node> map;
-  map.reserve(static_cast<std::size_t>(n_particles / 5));
+  // The map is kept between calls (per thread) and emptied key by key at the end: an emptied map with the same
+  // bucket count is indistinguishable from a freshly reserved one, and neither the allocation nor the zeroing of
+  // n/5 buckets (1.6 MB at 1M particles) has to be paid again.
+  thread_local std::unordered_map<std::size_t, Node> map;
+  thread_local std::size_t reserved_for = static_cast<std::size_t>(-1);
+  const std::size_t want = static_cast<std::size_t>(n_particles / 5);
+  if (reserved_for != want || !map.empty()) {
+    std::unordered_map<std::size_t, Node>().swap(map);
+    map.reserve(want);
+    reserved_for = want;
+  }
   for (std::size_t k = 0; k < n_cells; ++k) {
     // normalize_and_cap_weights, first loop (:181-184)
     map.try_emplace(static_cast<std::size_t>(cells[k].hash), Node{cells[k].weight / static_cast<double>(cells[k].count), static_cast<uint32_t>(k), -1});
@@ -97,6 +106,7 @@ ClusterSelection select_cluster(const HostCell* cells, std::size_t n_cells, std:
       out.found = true;
     }
   }
+  for (std::size_t k = 0; k < n_cells; ++k) map.erase(static_cast<std::size_t>(cells[k].hash));  // leave it empty for the next call
   if (out.found) {
     for (int j = 0; j < 9; ++j) out.moments[j] = moments[static_cast<std::size_t>(out.best) * 9 + j];
   } else {  // "maybe the particles are too fragmented": the overall estimate (:422-425)

@@ -77,6 +77,22 @@ def test_random_cloud_with_tied_cells(orc, unit):
     check(orc, states, weights)
 
 
+def test_repeated_calls_reuse_the_map(orc):
+    """The host pass keeps its unordered_map between calls; results must not depend on what ran before."""
+    import beluga_b200 as bb
+
+    rng = np.random.default_rng(9)
+    clouds = []
+    for n in (3000, 3000, 500, 3000):
+        th = rng.uniform(-PI, PI) + 0.2 * rng.standard_normal(n)
+        states = np.stack([np.cos(th), np.sin(th), rng.uniform(-5, 5) + 0.5 * rng.standard_normal(n), 0.5 * rng.standard_normal(n)], axis=1)
+        clouds.append((states, np.ones(n)))
+    first = [check(orc, s, w)[2].copy() for s, w in clouds]
+    again = [check(orc, s, w)[2] for s, w in reversed(clouds)]
+    for a, b in zip(first, reversed(again)):
+        assert np.array_equal(a, b)
+
+
 def test_argument_checks():
     import beluga_b200 as bb
 
