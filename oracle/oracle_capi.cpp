@@ -279,6 +279,16 @@ void orc_estimate(const double* states, const double* weights, std::uint64_t n, 
   std::memcpy(cov9, e.cov, sizeof(e.cov));
 }
 
+/// ExponentialFilter (algorithm/exponential_filter.hpp:35-44): out[i] = filter(values[i]); reset() before sample reset_before (or never: -1).
+void orc_exponential_filter(double alpha, const double* values, std::uint64_t n, std::int64_t reset_before, double* out) {
+  ExponentialFilter f;
+  f.alpha = alpha;
+  for (std::uint64_t i = 0; i < n; ++i) {
+    if (static_cast<std::int64_t>(i) == reset_before) f.reset();
+    out[i] = f(values[i]);
+  }
+}
+
 // ---- cluster-based estimate (cluster_oracle.hpp) ----------------------------------------------
 
 double orc_percentile_threshold(const double* values, std::uint64_t n, double percentile) {

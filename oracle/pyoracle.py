@@ -358,6 +358,13 @@ def estimate(states, weights):
     return mean, cov.reshape(3, 3)
 
 
+def exponential_filter(alpha: float, values, reset_before: int = -1) -> np.ndarray:
+    v = _f64(values)
+    out = np.zeros(len(v))
+    lib().orc_exponential_filter(C.c_double(alpha), _p(v, C.c_double), C.c_uint64(len(v)), C.c_int64(reset_before), _p(out, C.c_double))
+    return out
+
+
 # ---- cluster-based estimate ---------------------------------------------------------------------
 
 def percentile_threshold(values, percentile: float) -> float:

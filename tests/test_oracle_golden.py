@@ -555,3 +555,10 @@ def test_every_n_policy(orc, n, expected):  # TriggerOnNthCall, NoTriggerBeforeN
         assert r.updated == 1
         got.append(int(r.resampled))
     assert got == expected
+
+
+# ---- algorithm/test_exponential_filter.cpp:20-43 -------------------------------------------------
+def test_exponential_filter(orc):
+    assert orc.exponential_filter(0.1, [1, 2, 3, 0]) == pytest.approx([1.000, 1.100, 1.290, 1.161], abs=1e-5)  # Update
+    assert orc.exponential_filter(1.0, [1, 2, 3, 0]) == pytest.approx([1.0, 2.0, 3.0, 0.0], abs=1e-5)  # Passthrough
+    assert orc.exponential_filter(0.1, [1, 2, 3], reset_before=2) == pytest.approx([1.0, 1.1, 3.0], abs=1e-5)  # Reset
