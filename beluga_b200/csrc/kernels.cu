@@ -1190,7 +1190,8 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, co
     bool inject = false;
     Draw d{0, 0};
     if (a.random_state_probability > 0.0 || a.scheme == 0) d = counter_draw(a.seed, j, a.step, kStreamResample);
-    if (a.random_state_probability > 0.0) inject = uniform01(d.a) < a.random_state_probability;  // random_intersperse.hpp:93-100
+    // random_intersperse.hpp:93-100: one coin per ADVANCE of the view -- slot 0, the element begin() yields, is never injected
+    if (a.random_state_probability > 0.0) inject = j > 0 && uniform01(d.a) < a.random_state_probability;
     unsigned long long t = 0;
     if (!inject) t = a.scheme == 1 ? offset + j * stride : mulhi64(d.b, total);
     if (a.span_filter != 0) {

@@ -1112,9 +1112,11 @@ struct CounterResampler {
     if (scheme == ResampleScheme::kSystematic) return offset + j * stride;
     return mulhi64(counter_draw(seed, j, step, kStreamResample).b, total);
   }
-  /// Bernoulli(p) for slot j (views/random_intersperse.hpp:93-100 in counter form).
+  /// Bernoulli(p) for slot j (views/random_intersperse.hpp:93-100 in counter form).  The coin is tossed on every
+  /// ADVANCE of the view, so the first element always comes from the input range
+  /// (test_random_intersperse.cpp: GuaranteedIntersperseFirstElement).
   [[nodiscard]] bool inject(std::uint64_t j, double p) const {
-    return uniform01(counter_draw(seed, j, step, kStreamResample).a) < p;
+    return j > 0 && uniform01(counter_draw(seed, j, step, kStreamResample).a) < p;
   }
 };
 

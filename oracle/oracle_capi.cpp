@@ -279,6 +279,12 @@ void orc_estimate(const double* states, const double* weights, std::uint64_t n, 
   std::memcpy(cov9, e.cov, sizeof(e.cov));
 }
 
+/// Mode-B coin of views::random_intersperse for output slots 0..m-1 (CounterResampler::inject).
+void orc_inject_flags(std::uint64_t seed, std::uint32_t step, double probability, std::uint64_t m, std::uint8_t* out) {
+  const CounterResampler rs{seed, step, ResampleScheme::kMultinomial, 1ull << 40, m};
+  for (std::uint64_t j = 0; j < m; ++j) out[j] = rs.inject(j, probability) ? 1 : 0;
+}
+
 /// ExponentialFilter (algorithm/exponential_filter.hpp:35-44): out[i] = filter(values[i]); reset() before sample reset_before (or never: -1).
 void orc_exponential_filter(double alpha, const double* values, std::uint64_t n, std::int64_t reset_before, double* out) {
   ExponentialFilter f;

@@ -358,6 +358,12 @@ def estimate(states, weights):
     return mean, cov.reshape(3, 3)
 
 
+def inject_flags(seed: int, step: int, probability: float, m: int) -> np.ndarray:
+    out = np.zeros(m, dtype=np.uint8)
+    lib().orc_inject_flags(C.c_uint64(seed), C.c_uint32(step), C.c_double(probability), C.c_uint64(m), _p(out, C.c_uint8))
+    return out
+
+
 def exponential_filter(alpha: float, values, reset_before: int = -1) -> np.ndarray:
     v = _f64(values)
     out = np.zeros(len(v))

@@ -326,6 +326,22 @@ def test_systematic_resample_degenerate_weights(bb, orc, case):
     assert np.allclose(mean, want_mean, atol=1e-9) and np.allclose(cov[:2, :2], want_cov[:2, :2], rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("scheme", [0, 1])
+def test_injection_never_replaces_the_first_slot(bb, orc, scene, scheme):
+    """views::random_intersperse tosses its coin when the view ADVANCES: with probability 1 the output is one
+    sampled particle followed by random states only (test_random_intersperse.cpp:88-117)."""
+    n = 64
+    f = bb.Filter(capacity=n, seed=9, record_ancestors=True)
+    f.set_likelihood_field_map(bb.LikelihoodFieldModelParam(max_obstacle_distance=2.0, max_laser_distance=100.0),
+                               bb.OccupancyGrid(scene.cells, scene.resolution, orc.IDENTITY))  # the free cells the random states come from
+    f.set_particles(np.tile(orc.IDENTITY, (n, 1)), np.ones(n))
+    f.build_cdf()
+    assert f.resample(scheme, step=4, max_particles=n, random_state_probability=1.0) == n
+    anc = f.ancestors()
+    assert anc[0] >= 0 and np.all(anc[1:] == -1)
+    assert np.array_equal(anc < 0, orc.inject_flags(seed=9, step=4, probability=1.0, m=n).astype(bool))
+
+
 def test_normalize_and_ess(bb, orc):
     rng = np.random.default_rng(8)
     n = 50_000

@@ -562,3 +562,12 @@ def test_exponential_filter(orc):
     assert orc.exponential_filter(0.1, [1, 2, 3, 0]) == pytest.approx([1.000, 1.100, 1.290, 1.161], abs=1e-5)  # Update
     assert orc.exponential_filter(1.0, [1, 2, 3, 0]) == pytest.approx([1.0, 2.0, 3.0, 0.0], abs=1e-5)  # Passthrough
     assert orc.exponential_filter(0.1, [1, 2, 3], reset_before=2) == pytest.approx([1.0, 1.1, 3.0], abs=1e-5)  # Reset
+
+
+# ---- views/test_random_intersperse.cpp:88-117: the first element always comes from the input range ----
+def test_random_intersperse_never_replaces_the_first_element(orc):
+    flags = orc.inject_flags(seed=9, step=4, probability=1.0, m=6)
+    assert flags.tolist() == [0, 1, 1, 1, 1, 1]  # ElementsAre(10, 4, 4, 4, 4) in the reference's test
+    assert not orc.inject_flags(seed=9, step=4, probability=0.0, m=64).any()
+    rate = orc.inject_flags(seed=9, step=4, probability=0.25, m=200_000)[1:].mean()
+    assert abs(rate - 0.25) < 0.005
