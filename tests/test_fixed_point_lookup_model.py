@@ -1,0 +1,117 @@
+"""Executable version of the argument behind reweight_lfm_fixed_*_kernel (csrc/kernels.cu): the kernel finds the
+likelihood-field CELL of a beam end point with two FMAs per coordinate and a magic-number add instead of the
+reference's rounded operation sequence, and claims the same cell whenever the fraction word it reads is non-zero.
+
+This test replays both evaluations on the CPU -- IEEE doubles for the reference sequence, exact rationals rounded
+once for the FMAs -- on random and adversarial (cell-edge) inputs and checks the claim, plus how often the
+fallback would be taken.  CPU only; it models the arithmetic, it does not run the kernel."""
+import math
+import struct
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+MAGIC_X, MAGIC_Y = 1572864.0, 393216.0  # 1.5 * 2^20, 1.5 * 2^18 (kFixedMagicX / kFixedMagicY)
+BIAS_X, BIAS_Y = 0x41380000, 0x41180000
+
+
+def fma(a: float, b: float, c: float) -> float:
+    return float(Fraction(a) * Fraction(b) + Fraction(c))  # one rounding, to nearest even
+
+
+def words(t: float):
+    bits = struct.unpack("<Q", struct.pack("<d", t))[0]
+    return bits >> 32, bits & 0xFFFFFFFF
+
+
+def reference_cells(px, py, c, s, tx, ty, inv):
+    x = (px * c - py * s) + tx  # likelihood_field_model.hpp:82-83, every operation rounded
+    y = (px * s + py * c) + ty
+    return math.floor(x * inv), math.floor(y * inv)  # regular_grid.hpp:75-78
+
+
+def kernel_cells(px, py, c, s, tx, ty, inv):
+    """-> (cell x, cell y, ambiguous) as fixed_lookup computes them (before clamping to the border)."""
+    cx, sx = c * inv, s * inv
+    ox, oy = tx * inv + 1.0, ty * inv + 1.0
+    gx = fma(px, cx, fma(-py, sx, ox)) + MAGIC_X
+    gy = fma(px, sx, fma(py, cx, oy)) + MAGIC_Y
+    hx, lx = words(gx)
+    hy, ly = words(gy)
+    ux = (hx - BIAS_X) & 0xFFFFFFFF  # padded x = cell + 1 (for cells >= -1)
+    uy = (hy - BIAS_Y) & 0xFFFFFFFF  # 4 * padded y + 2 fraction bits
+    to_signed = lambda u: u - (1 << 32) if u >= (1 << 31) else u  # noqa: E731
+    return to_signed(ux) - 1, (to_signed(uy) >> 2) - 1, (lx == 0 or ly == 0)
+
+
+def random_case(rng, res):
+    theta = rng.uniform(-math.pi, math.pi)
+    c, s = math.cos(theta), math.sin(theta)
+    tx, ty = rng.uniform(-20.0, 120.0, 2)
+    r = rng.uniform(0.0, 100.0)
+    a = rng.uniform(-math.pi, math.pi)
+    return r * math.cos(a), r * math.sin(a), c, s, float(tx), float(ty), 1.0 / res
+
+
+@pytest.mark.parametrize("res", [0.05, 0.025, 0.1, 1.0 / 3.0])
+def test_random_end_points(res):
+    rng = np.random.default_rng(int(res * 1e6))
+    ambiguous = 0
+    for _ in range(6000):
+        case = random_case(rng, res)
+        xr, yr = reference_cells(*case)
+        xk, yk, amb = kernel_cells(*case)
+        ambiguous += amb
+        if not amb:
+            assert (xk, yk) == (xr, yr), case
+    assert ambiguous <= 1  # 2^-32 per coordinate
+
+
+def test_end_points_on_and_around_cell_edges():
+    """Axis-aligned and quarter-turn poses with end points exactly on cell edges, one ulp either side, and a few
+    thousand ulps away: the fraction word must flag every case it cannot decide, and decide the others right."""
+    rng = np.random.default_rng(1)
+    res = 0.05
+    inv = 1.0 / res
+    flagged = decided = 0
+    for theta in (0.0, math.pi / 2, math.pi, -math.pi / 2):
+        c, s = math.cos(theta), math.sin(theta)
+        for _ in range(400):
+            tx, ty = float(rng.integers(0, 2000)) * res, float(rng.integers(0, 2000)) * res
+            # px on a cell edge (before the +-k ulp nudges), py well inside a cell; the quarter turns swap their roles,
+            # so both the x word (16.. fraction bits after 1.5*2^20) and the y word (after 1.5*2^18) meet edges
+            px = float(rng.integers(-400, 400)) * res
+            py = (float(rng.integers(-400, 400)) + float(rng.uniform(0.2, 0.8))) * res  # y: well inside a cell
+            for k in (0, 1, -1, 3, -3, 4096, -4096):
+                ppx = px
+                for _ in range(abs(k)) if abs(k) < 10 else ():
+                    ppx = math.nextafter(ppx, math.inf if k > 0 else -math.inf)
+                if abs(k) >= 10:
+                    ppx = px + k * math.ulp(px if px != 0.0 else res)
+                case = (ppx, py, c, s, tx, ty, inv)
+                xr, yr = reference_cells(*case)
+                xk, yk, amb = kernel_cells(*case)
+                if amb:
+                    flagged += 1
+                else:
+                    decided += 1
+                    assert (xk, yk) == (xr, yr), case
+    assert flagged > 100 and decided > 100  # both branches exercised
+
+
+def test_range_limit_of_the_argument():
+    """The kernel only trusts the fixed-point words while every term stays below 2^13 cells (reach < 8100)."""
+    rng = np.random.default_rng(3)
+    res = 0.05
+    for _ in range(3000):
+        theta = rng.uniform(-math.pi, math.pi)
+        c, s = math.cos(theta), math.sin(theta)
+        tx, ty = rng.uniform(-200.0, 200.0, 2)  # up to 4000 cells
+        r = rng.uniform(0.0, 200.0)  # plus up to 4000 cells of beam: reach <= 8000
+        a = rng.uniform(-math.pi, math.pi)
+        case = (r * math.cos(a), r * math.sin(a), c, s, float(tx), float(ty), 1.0 / res)
+        xr, yr = reference_cells(*case)
+        xk, yk, amb = kernel_cells(*case)
+        if not amb:
+            assert (xk, yk) == (xr, yr), case
