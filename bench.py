@@ -42,6 +42,11 @@ UNIT = "steps/s"
 MOTION = (0.1, 0.05, 0.1, 0.05)  # likelihood_params.yaml:6-12
 LFM = dict(max_obstacle_distance=2.0, max_laser_distance=100.0, z_hit=0.5, z_random=0.5, sigma_hit=0.2)  # :55-65
 PATH_STEPS = 100
+SCALING = "strong"  # the metric is quoted "at 1M particles": N GPUs shard the SAME filter (--weak: --particles per GPU instead)
+
+
+def reference_particles(args):
+    return args.particles * (args.gpus if args.weak else 1)
 
 
 def parse_args():
@@ -50,10 +55,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU (weak scaling)")
+    ap.add_argument("--particles", type=int, default=1_000_000, help="particles of the filter (with --weak: per GPU)")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: --particles per GPU, one filter of N x particles")
     ap.add_argument("--beams", type=int, default=1080)
     ap.add_argument("--grid", type=int, default=2000)
-    ap.add_argument("--cpu-sample", type=int, default=100_000, help="particles in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -145,34 +150,56 @@ def usable_cpus() -> int:
     return n
 
 
-def cpu_reference_steps_per_s(args, scenario, n_full, sample_particles, steps=3):
-    """The reference algorithm (oracle port, counter-RNG mode, propagate/reweight/normalize threaded
-    like std::execution::par) on a bounded sample; linear extrapolation to the full particle count.
-    Thread count: the better of 1x and 2x the usable CPUs (what the host can give the reference)."""
+def cpu_reference_steps_per_s(args, scenario, n_full, steps, warmup=1, seq_particles=100_000):
+    """The reference algorithm (oracle port, counter-RNG mode, propagate/reweight/normalize threaded like
+    std::execution::par) on the FULL particle count for `steps` steps -- no extrapolation.  Thread count: the better of
+    1x and 2x the usable CPUs, picked on one probe step each; both are reported.  `seq` is the same port on ONE thread
+    (std::execution::seq), timed on a bounded particle sample because a full sequential step costs ~5 s per million."""
     from oracle import pyoracle as orc
 
     native = orc.use_native_build()  # -O3 -march=native on this host (SURVEY 8d); same results as the portable build
-    n = min(sample_particles, n_full)
-    best = None
     cpus = usable_cpus()
-    for threads in sorted({cpus, 2 * cpus}):
+    affinity = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+    def make(n, threads):
         o = orc.Amcl(orc.AmclParam(min_particles=n, max_particles=n, scheme=orc.SYSTEMATIC, seed=1, rng_mode=1, threads=threads),
                      orc.MotionParam(*MOTION))
         o.set_map(orc.LFM, orc.LfmParam(**LFM), orc.Grid(scenario.cells, scenario.resolution))
         o.initialize_normal(scenario.initial_mean, scenario.initial_cov)
-        o.update(orc.se2(*scenario.poses[0]), scenario.scans[0])  # warm-up
+        return o
+
+    def run(o, first, count):
         t0 = time.perf_counter()
-        for k in range(1, steps + 1):
-            o.update(orc.se2(*scenario.poses[k]), scenario.scans[k])
-        dt = (time.perf_counter() - t0) / steps
-        if best is None or dt < best[0]:
-            best = (dt, threads)
-    dt, threads = best
-    full_step_s = dt * (n_full / n)
+        for k in range(first, first + count):
+            r = o.update(orc.se2(*scenario.poses[k % PATH_STEPS]), scenario.scans[k % PATH_STEPS])
+            assert r.updated == 1
+        return (time.perf_counter() - t0) / count
+
+    probes = {}
+    for threads in sorted({cpus, 2 * cpus}):
+        o = make(n_full, threads)
+        run(o, 0, 1)  # first touch of the buffers
+        probes[threads] = min(run(o, 1, 1), run(o, 2, 1))
+        del o
+    threads = min(probes, key=probes.get)
+    o = make(n_full, threads)
+    run(o, 0, max(1, warmup))
+    dt = run(o, max(1, warmup), steps)
+    del o
+    n_seq = min(seq_particles, n_full)
+    o = make(n_seq, 1)
+    run(o, 0, 1)
+    dt_seq = run(o, 1, 2)
+    del o
     return {
-        "value": 1.0 / full_step_s, "unit": UNIT, "cores": threads, "kind": "port", "usable_cpus": cpus, "build": "-O3 -march=native" if native else "-O3",
-        "sample": f"{steps} steps of {n} particles x {args.beams} beams on the same map/scans, {dt * 1e3:.1f} ms/step with {threads} OpenMP threads "
-                  f"({cpus} usable CPUs), scaled x{n_full / n:.0f} to {n_full} particles",
+        "value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port", "usable_cpus": cpus, "affinity_cpus": affinity,
+        "omp_wait_policy": os.environ.get("OMP_WAIT_POLICY"), "build": "-O3 -march=native" if native else "-O3",
+        "par": {"steps_per_s": 1.0 / dt, "ms_per_step": dt * 1e3, "threads": threads, "particles": n_full, "steps": steps, "extrapolated": False,
+                "probe_ms_per_step": {str(t): v * 1e3 for t, v in probes.items()}},
+        "seq": {"steps_per_s": 1.0 / (dt_seq * (n_full / n_seq)), "ms_per_step_sample": dt_seq * 1e3, "threads": 1, "particles": n_seq,
+                "extrapolated": n_seq != n_full, "scale": n_full / n_seq},
+        "sample": f"{steps} steps of the full {n_full} particles x {args.beams} beams (no extrapolation), {dt * 1e3:.1f} ms/step with {threads} OpenMP "
+                  f"threads ({cpus} usable CPUs of {affinity} in the affinity mask); seq: {dt_seq * 1e3:.1f} ms/step for {n_seq} particles on 1 thread",
     }
 
 
@@ -181,13 +208,13 @@ def run_reference(args):
     if rank != 0:
         return
     scenario = make_workload(args)
-    n_total = args.particles * args.gpus
-    base = cpu_reference_steps_per_s(args, scenario, n_total, args.cpu_sample, steps=max(1, min(args.steps, 5)))
+    n_total = reference_particles(args)
+    base = cpu_reference_steps_per_s(args, scenario, n_total, steps=args.steps, warmup=max(1, min(args.warmup, 3)))
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, n_total), "particles_per_gpu": args.particles, "parallelism": f"cpu-omp{base['cores']}"},
+        "config": {"workload": workload_name(args, n_total), "particles": n_total, "parallelism": f"cpu-omp{base['cores']}"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -331,7 +358,7 @@ def run_native(args):
             "clocks": clocks.summary(),
         }
         if not args.no_cpu_baseline and world == 1:  # timed beside the GPU arm on rank 0 at N = 1 only
-            line["cpu_baseline"] = cpu_reference_steps_per_s(args, scenario, n_total, args.cpu_sample)
+            line["cpu_baseline"] = cpu_reference_steps_per_s(args, scenario, n_total, steps=5)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
