@@ -100,7 +100,7 @@ class LaserScan(C.Structure):
 
 class UpdateResult(C.Structure):
     _fields_ = [("updated", C.c_int), ("resampled", C.c_int), ("n_particles", C.c_uint64), ("estimate", Estimate),
-                ("random_state_probability", C.c_double), ("weight_sum", C.c_double)]
+                ("random_state_probability", C.c_double), ("weight_sum", C.c_double), ("weights_degenerate", C.c_int)]
 
 
 _P = C.POINTER

@@ -181,7 +181,30 @@ void Amcl::commit_update(int resampled, double random_state_probability) {
   force_update_ = false;
 }
 
+Amcl::HostState Amcl::snapshot() const {
+  return HostState{latest_pose_, every_n_current_, slow_output_, fast_output_, {window_[0], window_[1]}, window_size_, force_update_, step_};
+}
+
+void Amcl::restore(const HostState& s) {
+  latest_pose_ = s.latest_pose;
+  every_n_current_ = s.every_n_current;
+  slow_output_ = s.slow_output;
+  fast_output_ = s.fast_output;
+  window_[0] = s.window[0];
+  window_[1] = s.window[1];
+  window_size_ = s.window_size;
+  force_update_ = s.force_update;
+  step_ = s.step;
+}
+
 int Amcl::update(const double control[4], const double* points_xy, uint64_t n_points, bb200_update_result* out) {
+  const HostState before = snapshot();
+  const int st = update_device(control, points_xy, n_points, out);
+  if (st != BB200_OK) restore(before);  // policies, control window and recovery estimator as if the call had not happened
+  return st;
+}
+
+int Amcl::update_device(const double control[4], const double* points_xy, uint64_t n_points, bb200_update_result* out) {
   *out = bb200_update_result{};
   bb200_step_plan plan;
   int st = plan_update(control, &plan);
@@ -219,6 +242,7 @@ int Amcl::update(const double control[4], const double* points_xy, uint64_t n_po
     if (st != BB200_OK) return st;
     out->n_particles = filter_->size();
   }
+  out->weights_degenerate = filter_->last_weights_valid() ? 0 : 1;
   commit_update(out->resampled, plan.random_state_probability);
   out->updated = 1;
   return BB200_OK;

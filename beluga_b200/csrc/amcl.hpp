@@ -24,6 +24,7 @@ class Amcl {
   bool ok() const { return filter_ && filter_->ok(); }
   int create_status() const { return filter_ ? filter_->create_status() : BB200_ERR_CUDA; }
   const char* last_error() const { return error_.empty() ? filter_->last_error() : error_.c_str(); }
+  void record_error(const std::string& message) const { error_ = message; }  // the C-ABI exception guard
 
   int initialize(const double mean[3], const double cov[9]);
   int initialize_states(const double* states, const double* weights, uint64_t n);
@@ -39,7 +40,7 @@ class Amcl {
   bb200_amcl_param params_;
   bb200_motion_param motion_;
   std::unique_ptr<Filter> filter_;
-  std::string error_;
+  mutable std::string error_;
 
   // policies/on_motion.hpp:121-133
   std::optional<Pose2> latest_pose_;
@@ -54,6 +55,21 @@ class Amcl {
   bool force_update_{true};
   bool initialized_{false};
   uint32_t step_{0};
+
+  /// Everything plan_update() advances.  The reference's update() is atomic: when the device half of a step
+  /// fails, the host half is rolled back so that a retry sees the same motion delta, every_n phase and filters.
+  struct HostState {
+    std::optional<Pose2> latest_pose;
+    uint64_t every_n_current;
+    double slow_output, fast_output;
+    Pose2 window[2];
+    int window_size;
+    bool force_update;
+    uint32_t step;
+  };
+  HostState snapshot() const;
+  void restore(const HostState& s);
+  int update_device(const double control[4], const double* points_xy, uint64_t n_points, bb200_update_result* out);
 };
 
 }  // namespace bb200

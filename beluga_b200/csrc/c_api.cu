@@ -29,6 +29,41 @@ thread_local std::string g_create_error;
 // bb200_filter is layout-compatible with its only member, so the Amcl-owned Filter can be viewed
 // through the same handle type without a second allocation.
 static_assert(sizeof(bb200_filter) == sizeof(Filter), "bb200_filter must wrap Filter exactly");
+
+// Nothing throws across the C boundary: the host side allocates (std::vector, std::string, unordered_map), so every
+// entry point runs its body under this guard and turns an exception into a status + last_error message.
+template <class Context, class Body>
+int guarded(Context& context, Body&& body) noexcept {
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    try {
+      context.record_error("out of host memory");
+    } catch (...) {
+    }
+    return BB200_ERR_CAPACITY;
+  } catch (const std::exception& e) {
+    try {
+      context.record_error(std::string("internal error: ") + e.what());
+    } catch (...) {
+    }
+    return BB200_ERR_STATE;
+  } catch (...) {
+    try {
+      context.record_error("internal error: unknown exception");
+    } catch (...) {
+    }
+    return BB200_ERR_STATE;
+  }
+}
+struct CreateErrorContext {
+  void record_error(const std::string& m) { g_create_error = m; }
+};
+template <class Body>
+int guarded_create(Body&& body) noexcept {
+  CreateErrorContext c;
+  return guarded(c, body);
+}
 }  // namespace
 
 extern "C" {
@@ -52,19 +87,17 @@ int bb200_filter_create(const bb200_filter_config* config, bb200_filter** out) {
     return BB200_ERR_INVALID_ARGUMENT;
   }
   *out = nullptr;
-  bb200_filter* f = new (std::nothrow) bb200_filter(*config);
-  if (f == nullptr) {
-    g_create_error = "out of host memory";
-    return BB200_ERR_CUDA;
-  }
-  if (!f->impl.ok()) {
-    g_create_error = f->impl.last_error();
-    const int st = f->impl.create_status();
-    delete f;
-    return st;
-  }
-  *out = f;
-  return BB200_OK;
+  return guarded_create([&] {
+    bb200_filter* f = new bb200_filter(*config);
+    if (!f->impl.ok()) {
+      g_create_error = f->impl.last_error();
+      const int st = f->impl.create_status();
+      delete f;
+      return st;
+    }
+    *out = f;
+    return static_cast<int>(BB200_OK);
+  });
 }
 
 void bb200_filter_destroy(bb200_filter* f) { delete f; }
@@ -77,19 +110,19 @@ const char* bb200_last_error(const bb200_filter* f) { return f != nullptr ? f->i
 
 int bb200_filter_set_likelihood_field_map(bb200_filter* f, const bb200_likelihood_field_param* p, const bb200_occupancy_grid* grid, int prob) {
   BB_REQUIRE(f && p && grid);
-  return f->impl.set_likelihood_field_map(*p, *grid, prob != 0);
+  return guarded(f->impl, [&] { return f->impl.set_likelihood_field_map(*p, *grid, prob != 0); });
 }
 int bb200_filter_set_beam_map(bb200_filter* f, const bb200_beam_param* p, const bb200_occupancy_grid* grid) {
   BB_REQUIRE(f && p && grid);
-  return f->impl.set_beam_map(*p, *grid);
+  return guarded(f->impl, [&] { return f->impl.set_beam_map(*p, *grid); });
 }
 int bb200_filter_get_likelihood_field(const bb200_filter* f, float* out, uint64_t capacity) {
   BB_REQUIRE(f && out);
-  return f->impl.get_likelihood_field(out, capacity);
+  return guarded(f->impl, [&] { return f->impl.get_likelihood_field(out, capacity); });
 }
 int bb200_filter_set_particles(bb200_filter* f, const double* states, const double* weights, uint64_t n) {
   BB_REQUIRE(f);
-  return f->impl.set_particles(states, weights, n);
+  return guarded(f->impl, [&] { return f->impl.set_particles(states, weights, n); });
 }
 int bb200_filter_size(const bb200_filter* f, uint64_t* n) {
   BB_REQUIRE(f && n);
@@ -98,54 +131,54 @@ int bb200_filter_size(const bb200_filter* f, uint64_t* n) {
 }
 int bb200_filter_get_particles(bb200_filter* f, double* states, double* weights, uint64_t capacity) {
   BB_REQUIRE(f);
-  return f->impl.get_particles(states, weights, capacity);
+  return guarded(f->impl, [&] { return f->impl.get_particles(states, weights, capacity); });
 }
 int bb200_filter_initialize_normal(bb200_filter* f, const double mean_xytheta[3], const double cov[9], uint64_t n) {
   BB_REQUIRE(f && mean_xytheta && cov);
-  return f->impl.initialize_normal(mean_xytheta, cov, n);
+  return guarded(f->impl, [&] { return f->impl.initialize_normal(mean_xytheta, cov, n); });
 }
 int bb200_filter_propagate(bb200_filter* f, const bb200_motion_sampling* s, uint32_t step) {
   BB_REQUIRE(f && s);
-  return f->impl.propagate_reweight(s, step, nullptr, 0);
+  return guarded(f->impl, [&] { return f->impl.propagate_reweight(s, step, nullptr, 0); });
 }
 int bb200_filter_reweight(bb200_filter* f, const double* points_xy, uint64_t n_points) {
   BB_REQUIRE(f && (points_xy || n_points == 0));
   static const double kNoPoints[2] = {0.0, 0.0};
-  return f->impl.propagate_reweight(nullptr, 0, points_xy != nullptr ? points_xy : kNoPoints, n_points);
+  return guarded(f->impl, [&] { return f->impl.propagate_reweight(nullptr, 0, points_xy != nullptr ? points_xy : kNoPoints, n_points); });
 }
 int bb200_filter_propagate_reweight(bb200_filter* f, const bb200_motion_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points) {
   BB_REQUIRE(f && s && (points_xy || n_points == 0));
   static const double kNoPoints[2] = {0.0, 0.0};
-  return f->impl.propagate_reweight(s, step, points_xy != nullptr ? points_xy : kNoPoints, n_points);
+  return guarded(f->impl, [&] { return f->impl.propagate_reweight(s, step, points_xy != nullptr ? points_xy : kNoPoints, n_points); });
 }
 int bb200_filter_max_weight(bb200_filter* f, double* wmax) {
   BB_REQUIRE(f && wmax);
-  return f->impl.max_weight(wmax);
+  return guarded(f->impl, [&] { return f->impl.max_weight(wmax); });
 }
 int bb200_filter_build_cdf(bb200_filter* f, double global_wmax, uint64_t* local_total, int* exponent) {
   BB_REQUIRE(f);
-  return f->impl.build_cdf(global_wmax, local_total, exponent);
+  return guarded(f->impl, [&] { return f->impl.build_cdf(global_wmax, local_total, exponent); });
 }
 int bb200_filter_normalize_by(bb200_filter* f, uint64_t global_total, double* local_sum_sq) {
   BB_REQUIRE(f);
-  return f->impl.normalize_by(global_total, local_sum_sq);
+  return guarded(f->impl, [&] { return f->impl.normalize_by(global_total, local_sum_sq); });
 }
 int bb200_filter_normalize(bb200_filter* f, double* factor, double* sum_sq) {
   BB_REQUIRE(f);
-  return f->impl.normalize(factor, sum_sq);
+  return guarded(f->impl, [&] { return f->impl.normalize(factor, sum_sq); });
 }
 int bb200_filter_resample(bb200_filter* f, const bb200_resample_opts* o, uint64_t* new_size) {
   BB_REQUIRE(f && o);
-  return f->impl.resample(*o, new_size);
+  return guarded(f->impl, [&] { return f->impl.resample(*o, new_size); });
 }
 int bb200_filter_resample_range(bb200_filter* f, const bb200_resample_opts* o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin,
                                 uint64_t slot_end) {
   BB_REQUIRE(f && o);
-  return f->impl.resample_range(*o, global_total, cdf_offset, slot_begin, slot_end);
+  return guarded(f->impl, [&] { return f->impl.resample_range(*o, global_total, cdf_offset, slot_begin, slot_end); });
 }
 int bb200_filter_adopt(bb200_filter* f, uint64_t n, int from_staging) {
   BB_REQUIRE(f);
-  return f->impl.adopt(n, from_staging);
+  return guarded(f->impl, [&] { return f->impl.adopt(n, from_staging); });
 }
 int bb200_systematic_comb(uint64_t seed, uint32_t step, uint64_t global_total, uint64_t total_slots, uint64_t* stride, uint64_t* offset) {
   BB_REQUIRE(stride && offset && total_slots > 0);
@@ -161,66 +194,66 @@ int bb200_estimate_from_moments(const double moments[9], const double pivot_xy[2
 }
 int bb200_filter_set_stream(bb200_filter* f, void* cuda_stream) {
   BB_REQUIRE(f);
-  return f->impl.set_stream(cuda_stream);
+  return guarded(f->impl, [&] { return f->impl.set_stream(cuda_stream); });
 }
 int bb200_filter_enqueue_propagate_reweight(bb200_filter* f, const bb200_motion_sampling* s, uint32_t step, const double* points_xy, uint64_t n_points) {
   BB_REQUIRE(f && s && points_xy);
-  return f->impl.enqueue_propagate_reweight(s, step, points_xy, n_points);
+  return guarded(f->impl, [&] { return f->impl.enqueue_propagate_reweight(s, step, points_xy, n_points); });
 }
 int bb200_filter_enqueue_build_cdf(bb200_filter* f) {
   BB_REQUIRE(f);
-  return f->impl.enqueue_build_cdf();
+  return guarded(f->impl, [&] { return f->impl.enqueue_build_cdf(); });
 }
 int bb200_filter_enqueue_resample_range(bb200_filter* f, const bb200_resample_opts* o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin,
                                         uint64_t slot_end) {
   BB_REQUIRE(f && o);
-  return f->impl.enqueue_resample_range(*o, global_total, cdf_offset, slot_begin, slot_end);
+  return guarded(f->impl, [&] { return f->impl.enqueue_resample_range(*o, global_total, cdf_offset, slot_begin, slot_end); });
 }
 int bb200_filter_enqueue_adopt(bb200_filter* f, uint64_t n) {
   BB_REQUIRE(f);
-  return f->impl.enqueue_adopt(n);
+  return guarded(f->impl, [&] { return f->impl.enqueue_adopt(n); });
 }
 int bb200_filter_enqueue_moments(bb200_filter* f, const double pivot_xy[2]) {
   BB_REQUIRE(f && pivot_xy);
-  return f->impl.enqueue_moments(pivot_xy);
+  return guarded(f->impl, [&] { return f->impl.enqueue_moments(pivot_xy); });
 }
 int bb200_filter_ipc_handles(bb200_filter* f, void* out128) {
   BB_REQUIRE(f && out128);
-  return f->impl.ipc_handles(out128);
+  return guarded(f->impl, [&] { return f->impl.ipc_handles(out128); });
 }
 int bb200_filter_open_peers(bb200_filter* f, int world, int rank, const void* handles) {
   BB_REQUIRE(f && handles);
-  return f->impl.open_peers(world, rank, handles);
+  return guarded(f->impl, [&] { return f->impl.open_peers(world, rank, handles); });
 }
 int bb200_filter_enqueue_resample_push(bb200_filter* f, const bb200_resample_opts* o, uint64_t global_total, uint64_t cdf_offset, uint64_t slot_begin,
                                        uint64_t slot_end, uint64_t shard, const double pivot_xy[2]) {
   BB_REQUIRE(f && o && pivot_xy && slot_end >= slot_begin && shard > 0);
-  return f->impl.enqueue_resample_push(*o, global_total, cdf_offset, slot_begin, slot_end, shard, pivot_xy);
+  return guarded(f->impl, [&] { return f->impl.enqueue_resample_push(*o, global_total, cdf_offset, slot_begin, slot_end, shard, pivot_xy); });
 }
 int bb200_filter_enqueue_resample_push_device(bb200_filter* f, const bb200_resample_opts* o, const uint64_t* rank_totals_device, int rank, int world,
                                               uint64_t shard, const double pivot_xy[2]) {
   BB_REQUIRE(f && o && rank_totals_device && pivot_xy && shard > 0);
-  return f->impl.enqueue_resample_push_device(*o, rank_totals_device, rank, world, shard, pivot_xy);
+  return guarded(f->impl, [&] { return f->impl.enqueue_resample_push_device(*o, rank_totals_device, rank, world, shard, pivot_xy); });
 }
 int bb200_filter_enqueue_reduce_moments(bb200_filter* f) {
   BB_REQUIRE(f);
-  return f->impl.enqueue_reduce_moments();
+  return guarded(f->impl, [&] { return f->impl.enqueue_reduce_moments(); });
 }
 int bb200_filter_enqueue_flip_adopt(bb200_filter* f, uint64_t n) {
   BB_REQUIRE(f);
-  return f->impl.enqueue_flip_adopt(n);
+  return guarded(f->impl, [&] { return f->impl.enqueue_flip_adopt(n); });
 }
 int bb200_filter_ancestors(bb200_filter* f, int64_t* out, uint64_t capacity) {
   BB_REQUIRE(f && out);
-  return f->impl.ancestors(out, capacity);
+  return guarded(f->impl, [&] { return f->impl.ancestors(out, capacity); });
 }
 int bb200_filter_cdf(bb200_filter* f, uint64_t* out, uint64_t capacity) {
   BB_REQUIRE(f && out);
-  return f->impl.cdf(out, capacity);
+  return guarded(f->impl, [&] { return f->impl.cdf(out, capacity); });
 }
 int bb200_filter_estimate(bb200_filter* f, bb200_estimate* out) {
   BB_REQUIRE(f && out);
-  return f->impl.estimate(out);
+  return guarded(f->impl, [&] { return f->impl.estimate(out); });
 }
 void bb200_cluster_param_default(bb200_cluster_param* p) {
   if (p == nullptr) return;
@@ -231,7 +264,7 @@ void bb200_cluster_param_default(bb200_cluster_param* p) {
 int bb200_filter_cluster_estimate(bb200_filter* f, const bb200_cluster_param* p, bb200_estimate* out, uint32_t* cluster_ids, uint64_t ids_capacity,
                                   uint32_t* n_cells, uint32_t* n_clusters) {
   BB_REQUIRE(f && p);
-  return f->impl.cluster_estimate(*p, out, cluster_ids, ids_capacity, n_cells, n_clusters);
+  return guarded(f->impl, [&] { return f->impl.cluster_estimate(*p, out, cluster_ids, ids_capacity, n_cells, n_clusters); });
 }
 int bb200_cluster_select_host(const bb200_cluster_cell* cells, uint64_t n_cells, uint64_t n_particles, const bb200_cluster_param* p,
                               uint32_t* cluster_of_cell, uint32_t* n_clusters, int* found, uint32_t* best, double moments_out[9]) {
@@ -239,20 +272,22 @@ int bb200_cluster_select_host(const bb200_cluster_cell* cells, uint64_t n_cells,
       !(p->weight_cap_percentile >= 0.0) || !(p->weight_cap_percentile < 1.0))
     return BB200_ERR_INVALID_ARGUMENT;
   static_assert(sizeof(bb200_cluster_cell) == sizeof(bb200::HostCell), "public and internal cell records must agree");
-  const bb200::ClusterSelection sel = bb200::select_cluster(reinterpret_cast<const bb200::HostCell*>(cells), n_cells, n_particles,
-                                                            p->linear_hash_resolution, p->angular_hash_resolution, p->weight_cap_percentile);
-  if (cluster_of_cell != nullptr)
-    for (uint64_t k = 0; k < n_cells; ++k) cluster_of_cell[k] = sel.cluster_of_cell[k];
-  if (n_clusters != nullptr) *n_clusters = sel.clusters;
-  if (found != nullptr) *found = sel.found ? 1 : 0;
-  if (best != nullptr) *best = sel.best;
-  if (moments_out != nullptr)
-    for (int j = 0; j < 9; ++j) moments_out[j] = sel.moments[j];
-  return BB200_OK;
+  return guarded_create([&] {
+    const bb200::ClusterSelection sel = bb200::select_cluster(reinterpret_cast<const bb200::HostCell*>(cells), n_cells, n_particles,
+                                                              p->linear_hash_resolution, p->angular_hash_resolution, p->weight_cap_percentile);
+    if (cluster_of_cell != nullptr)
+      for (uint64_t k = 0; k < n_cells; ++k) cluster_of_cell[k] = sel.cluster_of_cell[k];
+    if (n_clusters != nullptr) *n_clusters = sel.clusters;
+    if (found != nullptr) *found = sel.found ? 1 : 0;
+    if (best != nullptr) *best = sel.best;
+    if (moments_out != nullptr)
+      for (int j = 0; j < 9; ++j) moments_out[j] = sel.moments[j];
+    return static_cast<int>(BB200_OK);
+  });
 }
 int bb200_filter_moments(bb200_filter* f, const double pivot_xy[2], double out[9]) {
   BB_REQUIRE(f && pivot_xy && out);
-  return f->impl.moments(pivot_xy, out);
+  return guarded(f->impl, [&] { return f->impl.moments(pivot_xy, out); });
 }
 int bb200_filter_set_timing(bb200_filter* f, int enabled) {
   BB_REQUIRE(f);
@@ -266,16 +301,16 @@ int bb200_filter_clear_timings(bb200_filter* f) {
 }
 int bb200_filter_last_timings(const bb200_filter* f, const char** names, float* ms, int capacity) {
   if (f == nullptr) return 0;
-  return f->impl.last_timings(names, ms, capacity);
+  return guarded(f->impl, [&] { return f->impl.last_timings(names, ms, capacity); });
 }
 uint64_t bb200_filter_launch_count(const bb200_filter* f) { return f != nullptr ? f->impl.launch_count() : 0; }
 int bb200_filter_synchronize(bb200_filter* f) {
   BB_REQUIRE(f);
-  return f->impl.synchronize();
+  return guarded(f->impl, [&] { return f->impl.synchronize(); });
 }
 int bb200_filter_device_pointer(bb200_filter* f, int which, void** ptr, uint64_t* bytes) {
   BB_REQUIRE(f && ptr && bytes);
-  return f->impl.device_pointer(which, ptr, bytes);
+  return guarded(f->impl, [&] { return f->impl.device_pointer(which, ptr, bytes); });
 }
 
 // ---- amcl ---------------------------------------------------------------------------------------
@@ -302,20 +337,18 @@ int bb200_amcl_create_with_motion(const bb200_amcl_param* p, const bb200_motion_
     g_create_error = "need 0 <= alpha_slow <= alpha_fast";
     return BB200_ERR_INVALID_ARGUMENT;
   }
-  bb200_amcl* a = new (std::nothrow) bb200_amcl(*p, *motion);
-  if (a == nullptr) {
-    g_create_error = "out of host memory";
-    return BB200_ERR_CUDA;
-  }
-  if (!a->impl.ok()) {
-    g_create_error = a->impl.last_error();
-    const int st = a->impl.create_status();
-    delete a;
-    return st;
-  }
-  a->filter_view = reinterpret_cast<bb200_filter*>(&a->impl.filter());
-  *out = a;
-  return BB200_OK;
+  return guarded_create([&] {
+    bb200_amcl* a = new bb200_amcl(*p, *motion);
+    if (!a->impl.ok()) {
+      g_create_error = a->impl.last_error();
+      const int st = a->impl.create_status();
+      delete a;
+      return st;
+    }
+    a->filter_view = reinterpret_cast<bb200_filter*>(&a->impl.filter());
+    *out = a;
+    return static_cast<int>(BB200_OK);
+  });
 }
 int bb200_amcl_create(const bb200_amcl_param* p, const bb200_diff_drive_param* motion, bb200_amcl** out) {
   if (motion == nullptr) {
@@ -331,11 +364,11 @@ const char* bb200_amcl_last_error(const bb200_amcl* a) { return a != nullptr ? a
 bb200_filter* bb200_amcl_filter(bb200_amcl* a) { return a != nullptr ? a->filter_view : nullptr; }
 int bb200_amcl_initialize(bb200_amcl* a, const double mean_xytheta[3], const double cov[9]) {
   BB_REQUIRE(a && mean_xytheta && cov);
-  return a->impl.initialize(mean_xytheta, cov);
+  return guarded(a->impl, [&] { return a->impl.initialize(mean_xytheta, cov); });
 }
 int bb200_amcl_initialize_states(bb200_amcl* a, const double* states, const double* weights, uint64_t n) {
   BB_REQUIRE(a);
-  return a->impl.initialize_states(states, weights, n);
+  return guarded(a->impl, [&] { return a->impl.initialize_states(states, weights, n); });
 }
 void bb200_amcl_force_update(bb200_amcl* a) {
   if (a != nullptr) a->impl.force_update();
@@ -343,7 +376,7 @@ void bb200_amcl_force_update(bb200_amcl* a) {
 int bb200_amcl_update(bb200_amcl* a, const double control_pose[4], const double* points_xy, uint64_t n_points, bb200_update_result* out) {
   BB_REQUIRE(a && control_pose && out && (points_xy || n_points == 0));
   static const double kNoPoints[2] = {0.0, 0.0};
-  return a->impl.update(control_pose, points_xy != nullptr ? points_xy : kNoPoints, n_points, out);
+  return guarded(a->impl, [&] { return a->impl.update(control_pose, points_xy != nullptr ? points_xy : kNoPoints, n_points, out); });
 }
 int bb200_take_evenly_indices(uint64_t size, uint64_t count, uint64_t* indices, uint64_t capacity, uint64_t* n_indices) {
   BB_REQUIRE(indices && n_indices);
@@ -400,16 +433,18 @@ int bb200_scan_to_points(const bb200_laser_scan* scan, double* points_xy, uint64
 
 int bb200_amcl_update_scan(bb200_amcl* a, const double control_pose[4], const bb200_laser_scan* scan, bb200_update_result* out) {
   BB_REQUIRE(a && control_pose && scan && out);
-  std::vector<double> points(2 * (scan->n_ranges + 1));
-  uint64_t n = 0;
-  const int st = bb200_scan_to_points(scan, points.data(), scan->n_ranges + 1, &n);
-  if (st != BB200_OK) return st;
-  return bb200_amcl_update(a, control_pose, points.data(), n, out);
+  return guarded(a->impl, [&] {
+    std::vector<double> points(2 * (scan->n_ranges + 1));
+    uint64_t n = 0;
+    const int st = bb200_scan_to_points(scan, points.data(), scan->n_ranges + 1, &n);
+    if (st != BB200_OK) return st;
+    return bb200_amcl_update(a, control_pose, points.data(), n, out);
+  });
 }
 
 int bb200_amcl_plan_update(bb200_amcl* a, const double control_pose[4], bb200_step_plan* plan) {
   BB_REQUIRE(a && control_pose && plan);
-  return a->impl.plan_update(control_pose, plan);
+  return guarded(a->impl, [&] { return a->impl.plan_update(control_pose, plan); });
 }
 void bb200_amcl_commit_update(bb200_amcl* a, int resampled, double random_state_probability) {
   if (a != nullptr) a->impl.commit_update(resampled, random_state_probability);

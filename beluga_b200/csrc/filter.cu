@@ -277,6 +277,7 @@ int Filter::set_stream(void* stream) {
 int Filter::enqueue_propagate_reweight(const bb200_motion_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points) {
   if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
   if (points_xy == nullptr || sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set / no points");
+  if (n_points > 0xffffffffull) return fail(BB200_ERR_INVALID_ARGUMENT, "too many points");
   BB_CHECK(cudaSetDevice(config_.device));
   int st = upload_points(points_xy, n_points);  // the caller synchronised at the end of the previous step
   if (st != BB200_OK) return st;
@@ -633,6 +634,10 @@ int Filter::set_particles(const double* states, const double* weights, uint64_t 
   }
   n_ = n;
   cdf_valid_ = false;
+  if (n > 0) {  // the covariance is accumulated about the pivot: keep it inside the cloud (no cancellation for far-away sets)
+    pivot_[0] = states[2];
+    pivot_[1] = states[3];
+  }
   return BB200_OK;
 }
 
@@ -783,7 +788,8 @@ int Filter::build_cdf(double global_wmax, uint64_t* local_total, int* exponent) 
   if (exponent != nullptr) *exponent = scalars_host_->exponent;
   // No positive finite weight (the reference would divide by zero in normalize.hpp:82): a uniform CDF
   // has been substituted and the weights are left as they are; reported through last_error only.
-  if (scalars_host_->valid == 0) error_ = "no positive finite weight (uniform CDF substituted)";
+  weights_valid_ = scalars_host_->valid != 0;
+  if (!weights_valid_) error_ = "no positive finite weight (uniform CDF substituted)";
   return BB200_OK;
 }
 
@@ -1053,6 +1059,7 @@ int Filter::adopt(uint64_t n, int from_staging) {
 
 int Filter::resample_kld(const bb200_resample_opts& o, uint64_t* accepted) {
   if (config_.global_count != capacity_ || config_.first_index != 0) return fail(BB200_ERR_STATE, "KLD-adaptive resampling runs on a single shard");
+  if (o.max_particles >= (1ull << 32)) return fail(BB200_ERR_CAPACITY, "KLD-adaptive resampling keeps 32-bit slot indices: max_particles must be below 2^32");
   if (hashes_ == nullptr) {
     BB_CHECK(dev_alloc(&hashes_, capacity_));
     BB_CHECK(dev_alloc(&kld_flags_, capacity_));
@@ -1094,6 +1101,7 @@ int Filter::step_resample(const bb200_motion_sampling& sampling, uint32_t step, 
   if (sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set");
   if (o.max_particles == 0 || o.max_particles > capacity_) return fail(BB200_ERR_CAPACITY, "max_particles exceeds the filter capacity");
   if (o.min_particles < o.max_particles) return fail(BB200_ERR_STATE, "the fused step does not run KLD; use resample()");
+  if (n_points > 0xffffffffull) return fail(BB200_ERR_INVALID_ARGUMENT, "too many points");
   if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
   BB_CHECK(cudaSetDevice(config_.device));
   int st = upload_points(points_xy, n_points);
@@ -1132,6 +1140,8 @@ int Filter::step_resample(const bb200_motion_sampling& sampling, uint32_t step, 
   cdf_valid_ = false;
   if (new_size != nullptr) *new_size = n_;
   if (weight_sum != nullptr) *weight_sum = std::ldexp(static_cast<double>(scalars_host_->total), -scalars_host_->exponent);
+  weights_valid_ = scalars_host_->valid != 0;
+  if (!weights_valid_) error_ = "no positive finite weight (uniform CDF substituted)";
   if (est != nullptr) {
     estimate_from_moments(results_host_, est);
     pivot_[0] = est->mean[2];

@@ -82,7 +82,10 @@ class Filter {
   void clear_timings() { timings_.clear(); }
   int last_timings(const char** names, float* ms, int capacity) const;
   uint64_t launch_count() const { return launches_; }
+  /// False when the last CDF was built from a weight set without any positive finite weight (uniform CDF substituted).
+  bool last_weights_valid() const { return weights_valid_; }
   const char* last_error() const { return error_.c_str(); }
+  void record_error(const std::string& message) const { error_ = message; }  // the C-ABI exception guard
   bool ok() const { return created_; }
   int create_status() const { return create_status_; }
 
@@ -102,7 +105,7 @@ class Filter {
   bb200_filter_config config_{};
   bool created_{false};
   int create_status_{BB200_OK};
-  std::string error_;
+  mutable std::string error_;
   cudaStream_t stream_{nullptr};
   bool owns_stream_{true};
   int peer_world_{0}, peer_rank_{0};
@@ -119,6 +122,7 @@ class Filter {
   uint64_t ancestors_n_{0};
   unsigned long long* hashes_{nullptr};
   bool cdf_valid_{false};
+  bool weights_valid_{true};
 
   // scratch
   Scalars* scalars_{nullptr};

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BB200_ABI_VERSION 1
+#define BB200_ABI_VERSION 2
 
 typedef enum bb200_status {
   BB200_OK = 0,
@@ -374,6 +374,8 @@ typedef struct bb200_update_result {
   bb200_estimate estimate;
   double random_state_probability;
   double weight_sum;           /* normalisation factor S of this step */
+  int weights_degenerate;      /* 1: no particle had a positive finite weight after the reweight (the reference would
+                                  divide by zero in normalize.hpp:82); a uniform CDF was substituted, weights left as they were */
 } bb200_update_result;
 
 int bb200_amcl_create(const bb200_amcl_param* p, const bb200_diff_drive_param* motion, bb200_amcl** out);

@@ -146,10 +146,17 @@ int orc_sensor_weights(
     std::uint64_t visited = 0;
     if (kind == 2) {
       const BeamModelParam bp = to_beam(static_cast<const orc_beam_param*>(param));
-      for (std::uint64_t i = 0; i < n; ++i) weights[i] = beam_weight(bp, grid, se2_from_data(states + 4 * i), points, &visited);
+      // particles are independent (the reference runs them under std::execution::par): threaded to keep the big parity cases short
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : visited)
+      for (std::int64_t i = 0; i < static_cast<std::int64_t>(n); ++i) {
+        std::uint64_t v = 0;
+        weights[i] = beam_weight(bp, grid, se2_from_data(states + 4 * i), points, &v);
+        visited += v;
+      }
     } else {
       const LikelihoodFieldModel model{to_lfm(static_cast<const orc_lfm_param*>(param)), grid};
-      for (std::uint64_t i = 0; i < n; ++i) {
+#pragma omp parallel for schedule(static)
+      for (std::int64_t i = 0; i < static_cast<std::int64_t>(n); ++i) {
         const SE2 s = se2_from_data(states + 4 * i);
         weights[i] = kind == 0 ? model.weight(s, points) : model.weight_prob(s, points);
       }

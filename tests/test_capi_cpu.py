@@ -36,7 +36,7 @@ def test_header_symbols_are_exported(lib):
     missing = [s for s in declared if s not in exported]
     assert not missing, f"declared in include/beluga_b200.h but not exported: {missing}"
     assert set(_capi.SIGNATURES) == set(declared), "ctypes table and header disagree"
-    assert lib.bb200_abi_version() == 1
+    assert lib.bb200_abi_version() == 2
 
 
 def test_no_cpu_fallback(lib):
