@@ -329,6 +329,10 @@ class Filter:
     def initialize_normal(self, mean_xytheta, cov, n: int):
         self._check(self._lib.bb200_filter_initialize_normal(self._h, _dptr(_f64(mean_xytheta)), _dptr(_f64(cov).reshape(9)), n))
 
+    def initialize_uniform(self, n: int):
+        """n particles uniform over the free cells of the current map (MultivariateUniformDistribution<SE2d, OccupancyGrid>)."""
+        self._check(self._lib.bb200_filter_initialize_uniform(self._h, n))
+
     # per-step operations
     @staticmethod
     def _sampling(s) -> _capi.MotionSampling:
@@ -527,6 +531,10 @@ class Amcl:
 
     def initialize(self, mean_xytheta, cov):
         self._check(self._lib.bb200_amcl_initialize(self._h, _dptr(_f64(mean_xytheta)), _dptr(_f64(cov).reshape(9))))
+
+    def initialize_from_map(self):
+        """beluga_ros::Amcl::initialize_from_map (beluga_ros/include/beluga_ros/amcl.hpp:209): global localisation start."""
+        self._check(self._lib.bb200_amcl_initialize_from_map(self._h))
 
     def initialize_states(self, states, weights=None):
         st = _f64(states).reshape(-1, 4)

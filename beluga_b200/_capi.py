@@ -122,6 +122,7 @@ SIGNATURES = {
     "bb200_filter_size": (C.c_int, [_vp, _P(C.c_uint64)]),
     "bb200_filter_get_particles": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64]),
     "bb200_filter_initialize_normal": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64]),
+    "bb200_filter_initialize_uniform": (C.c_int, [_vp, C.c_uint64]),
     "bb200_filter_propagate": (C.c_int, [_vp, _P(MotionSampling), C.c_uint32]),
     "bb200_filter_reweight": (C.c_int, [_vp, _dbl, C.c_uint64]),
     "bb200_filter_propagate_reweight": (C.c_int, [_vp, _P(MotionSampling), C.c_uint32, _dbl, C.c_uint64]),
@@ -166,6 +167,7 @@ SIGNATURES = {
     "bb200_amcl_filter": (_vp, [_vp]),
     "bb200_amcl_initialize": (C.c_int, [_vp, _dbl, _dbl]),
     "bb200_amcl_initialize_states": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64]),
+    "bb200_amcl_initialize_from_map": (C.c_int, [_vp]),
     "bb200_amcl_force_update": (None, [_vp]),
     "bb200_amcl_update": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64, _P(UpdateResult)]),
     "bb200_scan_to_points": (C.c_int, [_P(LaserScan), _dbl, C.c_uint64, _P(C.c_uint64)]),

@@ -107,6 +107,16 @@ int Amcl::initialize(const double mean[3], const double cov[9]) {
   return st;
 }
 
+int Amcl::initialize_from_map() {
+  error_.clear();
+  const int st = filter_->initialize_uniform(sharded() ? params_.shard_capacity : params_.max_particles);
+  if (st == BB200_OK) {
+    force_update_ = true;  // beluga_ros/include/beluga_ros/amcl.hpp:193-199
+    initialized_ = true;
+  }
+  return st;
+}
+
 int Amcl::initialize_states(const double* states, const double* weights, uint64_t n) {
   error_.clear();
   const int st = filter_->set_particles(states, weights, n);

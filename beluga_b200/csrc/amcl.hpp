@@ -27,6 +27,7 @@ class Amcl {
   void record_error(const std::string& message) const { error_ = message; }  // the C-ABI exception guard
 
   int initialize(const double mean[3], const double cov[9]);
+  int initialize_from_map();
   int initialize_states(const double* states, const double* weights, uint64_t n);
   void force_update() { force_update_ = true; }
   int update(const double control[4], const double* points_xy, uint64_t n_points, bb200_update_result* out);

@@ -137,6 +137,10 @@ int bb200_filter_initialize_normal(bb200_filter* f, const double mean_xytheta[3]
   BB_REQUIRE(f && mean_xytheta && cov);
   return guarded(f->impl, [&] { return f->impl.initialize_normal(mean_xytheta, cov, n); });
 }
+int bb200_filter_initialize_uniform(bb200_filter* f, uint64_t n) {
+  BB_REQUIRE(f);
+  return guarded(f->impl, [&] { return f->impl.initialize_uniform(n); });
+}
 int bb200_filter_propagate(bb200_filter* f, const bb200_motion_sampling* s, uint32_t step) {
   BB_REQUIRE(f && s);
   return guarded(f->impl, [&] { return f->impl.propagate_reweight(s, step, nullptr, 0); });
@@ -365,6 +369,10 @@ bb200_filter* bb200_amcl_filter(bb200_amcl* a) { return a != nullptr ? a->filter
 int bb200_amcl_initialize(bb200_amcl* a, const double mean_xytheta[3], const double cov[9]) {
   BB_REQUIRE(a && mean_xytheta && cov);
   return guarded(a->impl, [&] { return a->impl.initialize(mean_xytheta, cov); });
+}
+int bb200_amcl_initialize_from_map(bb200_amcl* a) {
+  BB_REQUIRE(a);
+  return guarded(a->impl, [&] { return a->impl.initialize_from_map(); });
 }
 int bb200_amcl_initialize_states(bb200_amcl* a, const double* states, const double* weights, uint64_t n) {
   BB_REQUIRE(a);

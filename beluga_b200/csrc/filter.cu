@@ -557,6 +557,7 @@ int Filter::set_likelihood_field_map(const bb200_likelihood_field_param& p, cons
   BB_CHECK(dev_alloc(&free_cells_, free.size()));
   if (!free.empty()) BB_CHECK(cudaMemcpy(free_cells_, free.data(), free.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   grid_width_ = g.width;
+  grid_height_ = g.height;
   grid_resolution_ = g.resolution;
   grid_origin_ = pose_from_array(g.origin);
   return BB200_OK;
@@ -604,6 +605,7 @@ int Filter::set_beam_map(const bb200_beam_param& p, const bb200_occupancy_grid& 
   BB_CHECK(dev_alloc(&free_cells_, free.size()));
   if (!free.empty()) BB_CHECK(cudaMemcpy(free_cells_, free.data(), free.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   grid_width_ = g.width;
+  grid_height_ = g.height;
   grid_resolution_ = g.resolution;
   grid_origin_ = pose_from_array(g.origin);
   return BB200_OK;
@@ -663,6 +665,24 @@ int Filter::initialize_normal(const double mean[3], const double cov[9], uint64_
   cdf_valid_ = false;
   pivot_[0] = mean[0];
   pivot_[1] = mean[1];
+  return BB200_OK;
+}
+
+int Filter::initialize_uniform(uint64_t n) {
+  if (n > capacity_) return fail(BB200_ERR_CAPACITY, "more particles than the filter capacity");
+  if (sensor_ < 0) return fail(BB200_ERR_STATE, "initialize_from_map needs a map (set_*_map first)");
+  if (n_free_ == 0) return fail(BB200_ERR_STATE, "the map has no free cell to sample from");
+  BB_CHECK(cudaSetDevice(config_.device));
+  launch_initialize_uniform(states_[cur_], weights_, n, free_cells_, n_free_, grid_width_, grid_resolution_, grid_origin_, config_.seed,
+                            config_.first_index, stream_);
+  BB_LAUNCHED("initialize_uniform");
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  n_ = n;
+  cdf_valid_ = false;
+  // pivot of the raw moments: the middle of the map in the global frame
+  const double cx = 0.5 * grid_width_ * grid_resolution_, cy = 0.5 * grid_height_ * grid_resolution_;
+  pivot_[0] = (grid_origin_.c * cx - grid_origin_.s * cy) + grid_origin_.x;
+  pivot_[1] = (grid_origin_.s * cx + grid_origin_.c * cy) + grid_origin_.y;
   return BB200_OK;
 }
 

@@ -31,6 +31,8 @@ class Filter {
   int set_particles(const double* states, const double* weights, uint64_t n);
   int get_particles(double* states, double* weights, uint64_t capacity);
   int initialize_normal(const double mean[3], const double cov[9], uint64_t n);
+  /// n samples of MultivariateUniformDistribution over the free cells of the current map (initialize_from_map).
+  int initialize_uniform(uint64_t n);
   uint64_t size() const { return n_; }
 
   int propagate_reweight(const bb200_motion_sampling* sampling, uint32_t step, const double* points_xy, uint64_t n_points);
@@ -181,7 +183,7 @@ class Filter {
   bool beam_eta_table_{true};
   uint32_t* free_cells_{nullptr};
   uint64_t n_free_{0};
-  int grid_width_{0};
+  int grid_width_{0}, grid_height_{0};
   double grid_resolution_{1.0};
   Pose2 grid_origin_{1.0, 0.0, 0.0, 0.0};
 

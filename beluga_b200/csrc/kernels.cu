@@ -140,6 +140,16 @@ __device__ __forceinline__ void mbarrier_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+__device__ __forceinline__ Pose2 load_pose(const Pose2* p) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+  return Pose2{a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ void store_pose(Pose2* p, const Pose2& v) {
+  *reinterpret_cast<double2*>(p) = make_double2(v.c, v.s);
+  *(reinterpret_cast<double2*>(p) + 1) = make_double2(v.x, v.y);
+}
+
 // ---- begin_step ----------------------------------------------------------------------------------
 
 __global__ void begin_step_kernel(Scalars* s) {
@@ -177,22 +187,42 @@ __global__ void __launch_bounds__(256) initialize_normal_kernel(Pose2* states, d
   weights[i] = 1.0;
 }
 
+/// MultivariateUniformDistribution<SE2d, OccupancyGrid> (random/multivariate_uniform_distribution.hpp:143-160): a free
+/// cell drawn uniformly, its centroid in the global frame (occupancy_grid.hpp:150-156,166-172), yaw ~ U[-pi, pi).
+struct FreeSpace {
+  const uint32_t* cells;  // row-major indices of the free cells
+  uint64_t n;
+  int grid_width;
+  double resolution;
+  Pose2 origin;
+};
+
+__device__ __forceinline__ Pose2 random_free_state(const FreeSpace& fs, const Draw& r) {
+  const uint32_t cell = fs.cells[mulhi64(r.a, fs.n)];
+  const double pi = 3.14159265358979323846;
+  const double yaw = uniform01(r.b) * (pi - (-pi)) + (-pi);
+  const double lx = (static_cast<double>(static_cast<int>(cell % static_cast<uint32_t>(fs.grid_width))) + 0.5) * fs.resolution;
+  const double ly = (static_cast<double>(static_cast<int>(cell / static_cast<uint32_t>(fs.grid_width))) + 0.5) * fs.resolution;
+  const Rot2 rot = rot_exp(yaw);
+  return Pose2{rot.c, rot.s, (fs.origin.c * lx - fs.origin.s * ly) + fs.origin.x, (fs.origin.s * lx + fs.origin.c * ly) + fs.origin.y};
+}
+
+// initialize_from_map (a16; beluga_ros/include/beluga_ros/amcl.hpp:192-209): max_particles samples of the map
+// distribution, weights 1.  Counter stream 6 at step 0, keyed by the global particle index.
+__global__ void __launch_bounds__(256) initialize_uniform_kernel(Pose2* states, double* weights, uint64_t n, FreeSpace fs, uint64_t seed,
+                                                                 uint64_t first_index) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  store_pose(states + i, random_free_state(fs, counter_draw(seed, first_index + i, 0, kStreamRandomState)));
+  weights[i] = 1.0;
+}
+
 // ---- propagate (a2 + a6) --------------------------------------------------------------------------
 // One thread per particle, original order.  Also accumulates the first and second moments of the
 // propagated cloud (block reduction + double atomics); they only feed the execution schedule below,
 // never a result, so their summation order does not matter.
 
 constexpr int kPrThreads = 256;
-
-__device__ __forceinline__ Pose2 load_pose(const Pose2* p) {
-  const double2 a = *reinterpret_cast<const double2*>(p);
-  const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
-  return Pose2{a.x, a.y, b.x, b.y};
-}
-__device__ __forceinline__ void store_pose(Pose2* p, const Pose2& v) {
-  *reinterpret_cast<double2*>(p) = make_double2(v.c, v.s);
-  *(reinterpret_cast<double2*>(p) + 1) = make_double2(v.x, v.y);
-}
 
 __device__ __forceinline__ Pose2 propagate_one(const Pose2& st, const MotionSampling& p, uint64_t seed, uint64_t index, uint32_t step) {
   double z0, z1, z2, unused;
@@ -1199,16 +1229,8 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, co
       if (!mine) continue;
     }
     if (inject) {
-      // MultivariateUniformDistribution<SE2d, OccupancyGrid> (multivariate_uniform_distribution.hpp:143-160)
-      const Draw r = counter_draw(a.seed, j, a.step, kStreamRandomState);
-      const uint32_t cell = a.free_cells[mulhi64(r.a, a.n_free)];
-      const double pi = 3.14159265358979323846;
-      const double yaw = uniform01(r.b) * (pi - (-pi)) + (-pi);
-      const double lx = (static_cast<double>(static_cast<int>(cell % static_cast<uint32_t>(a.grid_width))) + 0.5) * a.grid_resolution;
-      const double ly = (static_cast<double>(static_cast<int>(cell / static_cast<uint32_t>(a.grid_width))) + 0.5) * a.grid_resolution;
-      const Rot2 rot = rot_exp(yaw);
-      st = Pose2{rot.c, rot.s, (a.grid_origin.c * lx - a.grid_origin.s * ly) + a.grid_origin.x,
-                 (a.grid_origin.s * lx + a.grid_origin.c * ly) + a.grid_origin.y};
+      st = random_free_state(FreeSpace{a.free_cells, a.n_free, a.grid_width, a.grid_resolution, a.grid_origin},
+                             counter_draw(a.seed, j, a.step, kStreamRandomState));
     } else {
       const uint64_t idx = cdf_upper_bound(a.cdf, a.n_in, t - cdf_offset);  // the caller guarantees t lies in this shard's span
       ancestor = static_cast<long long>(idx);
@@ -1368,6 +1390,13 @@ void launch_initialize_normal(Pose2* states, double* weights, uint64_t n, const 
   for (int i = 0; i < 3; ++i) p.mean[i] = mean[i];
   for (int i = 0; i < 9; ++i) p.t[i] = transform[i];
   initialize_normal_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(states, weights, n, p, seed, first_index);
+}
+
+void launch_initialize_uniform(Pose2* states, double* weights, uint64_t n, const uint32_t* free_cells, uint64_t n_free, int grid_width,
+                               double grid_resolution, const Pose2& grid_origin, uint64_t seed, uint64_t first_index, cudaStream_t stream) {
+  if (n == 0) return;
+  const FreeSpace fs{free_cells, n_free, grid_width, grid_resolution, grid_origin};
+  initialize_uniform_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(states, weights, n, fs, seed, first_index);
 }
 
 void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const MotionSampling& sampling, uint64_t seed, uint32_t step,

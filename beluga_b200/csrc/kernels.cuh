@@ -96,6 +96,10 @@ void launch_begin_step(Scalars* scalars, cudaStream_t stream);
 void launch_initialize_normal(Pose2* states, double* weights, uint64_t n, const double mean[3], const double transform[9],
                               uint64_t seed, uint64_t first_index, cudaStream_t stream);
 
+/// initialize_from_map: n states uniform over the free cells (centroids, global frame), yaw uniform, weights 1.
+void launch_initialize_uniform(Pose2* states, double* weights, uint64_t n, const uint32_t* free_cells, uint64_t n_free, int grid_width,
+                               double grid_resolution, const Pose2& grid_origin, uint64_t seed, uint64_t first_index, cudaStream_t stream);
+
 /// Offset of cell (xi, yi) in the tiled table.
 BB_HD size_t tiled_index(int xi, int yi, int tiles_x) {
   const unsigned x = static_cast<unsigned>(xi), y = static_cast<unsigned>(yi);

@@ -187,6 +187,11 @@ int bb200_filter_get_particles(bb200_filter* f, double* states, double* weights,
  * MultivariateNormalDistribution<SE2d> (random/multivariate_normal_distribution.hpp:96-126):
  * n particles ~ N(mean {x, y, theta}, cov 3x3), weights 1. */
 int bb200_filter_initialize_normal(bb200_filter* f, const double mean_xytheta[3], const double cov[9], uint64_t n);
+/* Global localisation: n particles from MultivariateUniformDistribution<SE2d, OccupancyGrid>
+ * (random/multivariate_uniform_distribution.hpp:127-161) over the map set by bb200_filter_set_*_map: a free cell drawn
+ * uniformly, its centroid in the global frame, yaw ~ U[-pi, pi); weights 1.  Counter RNG stream 6 at step 0,
+ * keyed by the global particle index (same generator as the recovery injection of bb200_filter_resample). */
+int bb200_filter_initialize_uniform(bb200_filter* f, uint64_t n);
 
 /* actions::propagate(model(control)) (actions/propagate.hpp:57-79) for DifferentialDriveModel:
  * per particle 3 normals (counter RNG keyed by seed / global index / step) and the SE2 compose of
@@ -385,6 +390,9 @@ const char* bb200_amcl_last_error(const bb200_amcl* a);
 bb200_filter* bb200_amcl_filter(bb200_amcl* a);
 /* Amcl::initialize(pose, covariance) -- amcl_core.hpp:145-147 (max_particles samples). */
 int bb200_amcl_initialize(bb200_amcl* a, const double mean_xytheta[3], const double cov[9]);
+/* beluga_ros::Amcl::initialize_from_map() (beluga_ros/include/beluga_ros/amcl.hpp:192-209): max_particles samples of the
+ * map distribution (uniform over the free cells), weights 1, next update forced. */
+int bb200_amcl_initialize_from_map(bb200_amcl* a);
 /* Amcl::initialize from explicit states (tests / custom distributions, amcl_core.hpp:131-137). */
 int bb200_amcl_initialize_states(bb200_amcl* a, const double* states, const double* weights, uint64_t n);
 /* Amcl::force_update -- amcl_core.hpp:204 */

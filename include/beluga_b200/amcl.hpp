@@ -110,6 +110,9 @@ class Amcl {
     check(bb200_amcl_initialize(handle_, mean, covariance.data()));
   }
   /// amcl_core.hpp:131-137 with an explicit state list instead of a distribution.
+  /// beluga_ros::Amcl::initialize_from_map() (beluga_ros/include/beluga_ros/amcl.hpp:209): max_particles samples of the
+  /// map distribution -- uniform over the free cells of the sensor model's map.
+  void initialize_from_map() { check(bb200_amcl_initialize_from_map(handle_)); }
   void initialize(const std::vector<state_type>& states) {
     check(bb200_amcl_initialize_states(handle_, states.empty() ? nullptr : reinterpret_cast<const double*>(states.data()), nullptr, states.size()));
   }

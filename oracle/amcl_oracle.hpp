@@ -98,6 +98,27 @@ class Amcl {
     force_update_ = true;
   }
 
+  /// beluga_ros::Amcl::initialize_from_map (beluga_ros/include/beluga_ros/amcl.hpp:192-209): max_particles samples of
+  /// MultivariateUniformDistribution<SE2d, OccupancyGrid> (random/multivariate_uniform_distribution.hpp:127-161).
+  void initialize_from_map() {
+    if (free_.empty()) throw std::runtime_error("initialize_from_map: the map has no free cell");
+    states_.resize(params_.max_particles);
+    weights_.assign(params_.max_particles, 1.0);
+    if (params_.rng_mode == RngMode::kCounter) {
+      for (std::size_t i = 0; i < states_.size(); ++i) states_[i] = random_state_counter(grid_, free_, params_.seed, i, 0);
+    } else {
+      // operator()(engine): SO2d::sampleUniform(engine) first, then the free-state index (:143-145)
+      std::uniform_int_distribution<std::size_t> pick(0, free_.size() - 1);
+      const double pi = 3.14159265358979323846;
+      std::uniform_real_distribution<double> yaw(-pi, pi);
+      for (auto& s : states_) {
+        const double theta = yaw(engine_);
+        s = free_cell_state(grid_, free_[pick(engine_)], theta);
+      }
+    }
+    force_update_ = true;
+  }
+
   void set_particles(const std::vector<SE2>& states, const std::vector<double>& weights) {
     states_ = states;
     weights_ = weights;

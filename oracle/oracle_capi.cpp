@@ -461,6 +461,16 @@ int orc_amcl_initialize_normal(orc_amcl* a, const double* mean_xyt, const double
   }
 }
 
+int orc_amcl_initialize_from_map(orc_amcl* a) {
+  try {
+    a->impl.initialize_from_map();
+    return 0;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
 void orc_amcl_set_particles(orc_amcl* a, const double* states, const double* weights, std::uint64_t n) {
   std::vector<SE2> s(n);
   for (std::uint64_t i = 0; i < n; ++i) s[i] = se2_from_data(states + 4 * i);

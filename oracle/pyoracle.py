@@ -483,6 +483,10 @@ class Amcl:
         if lib().orc_amcl_initialize_normal(self._h, _p(_f64(mean_xyt), C.c_double), _p(_f64(cov).reshape(9), C.c_double)) != 0:
             raise RuntimeError(lib().orc_last_error().decode())
 
+    def initialize_from_map(self):
+        if lib().orc_amcl_initialize_from_map(self._h) != 0:
+            raise RuntimeError(lib().orc_last_error().decode())
+
     def set_particles(self, states, weights):
         st = _f64(states).reshape(-1, 4)
         w = _f64(weights)

@@ -138,6 +138,41 @@ def test_reweight_lfm_bit_exact(bb, orc, scene, n_points, sensor):
         assert np.allclose(got[~normal], exp[~normal], rtol=1e-6, atol=1e-320)
 
 
+def test_initialize_from_map_matches_oracle(bb, orc, scene):
+    """initialize_from_map (beluga_ros/include/beluga_ros/amcl.hpp:192-209): the free cell and yaw of every particle are the
+    oracle's (counter stream 6), the first update is forced, and the reference's known answers hold on the GPU
+    (test_multivariate_uniform_distribution.cpp:56-124)."""
+    n = 50_000
+    cells = scene.cells.copy()
+    cells[20:40, 20:60] = -1  # unknown space is not free
+    g = bb.Amcl(bb.DifferentialDriveModelParam(0.1, 0.05, 0.1, 0.05), bb.AmclParams(min_particles=n, max_particles=n, seed=21))
+    o = orc.Amcl(orc.AmclParam(min_particles=n, max_particles=n, seed=21, rng_mode=1), orc.MotionParam(0.1, 0.05, 0.1, 0.05))
+    origin = orc.se2(-3.0, 1.5, 0.3)
+    g.update_map(0, bb.LikelihoodFieldModelParam(max_laser_distance=100.0), bb.OccupancyGrid(cells, scene.resolution, origin))
+    o.set_map(0, orc.LfmParam(max_laser_distance=100.0), orc.Grid(cells, scene.resolution, origin))
+    g.initialize_from_map()
+    o.initialize_from_map()
+    sg, wg = g.particles()
+    so, wo = o.particles()
+    assert np.all(wg == 1.0) and len(sg) == n
+    assert np.array_equal(sg[:, 2:4], so[:, 2:4])  # cell centroids: plain arithmetic, bit-identical
+    assert np.abs(sg[:, 0:2] - so[:, 0:2]).max() < 1e-15
+    assert g.update(orc.se2(0.0, 0.0, 0.0), scene.scans[0]).updated == 1  # force_update_ = true
+    # GridSomeFreeSlots on the device
+    f = bb.Filter(capacity=100_000, seed=4)
+    f.set_likelihood_field_map(bb.LikelihoodFieldModelParam(), bb.OccupancyGrid(np.array([[100, 0, 100], [0, 100, 0], [100, 0, 100]], dtype=np.int8), 1.0))
+    f.initialize_uniform(100_000)
+    st, _ = f.particles()
+    buckets, counts = np.unique(st[:, 2:4], axis=0, return_counts=True)
+    assert sorted(map(tuple, buckets)) == [(0.5, 1.5), (1.5, 0.5), (1.5, 2.5), (2.5, 1.5)]
+    assert np.abs(counts / 100_000 - 0.25).max() < 0.01
+    # no free cell: an error, not a crash
+    f2 = bb.Filter(capacity=8)
+    f2.set_likelihood_field_map(bb.LikelihoodFieldModelParam(), bb.OccupancyGrid(np.full((3, 3), 100, dtype=np.int8), 1.0))
+    with pytest.raises(bb.BelugaB200Error):
+        f2.initialize_uniform(8)
+
+
 @pytest.mark.parametrize("n", [1, 31, 32, 33, 255, 257])
 @pytest.mark.parametrize("n_points", [7, 1920, 1921])
 def test_reweight_ragged_particle_counts(bb, orc, scene, n, n_points):

@@ -571,3 +571,40 @@ def test_random_intersperse_never_replaces_the_first_element(orc):
     assert not orc.inject_flags(seed=9, step=4, probability=0.0, m=64).any()
     rate = orc.inject_flags(seed=9, step=4, probability=0.25, m=200_000)[1:].mean()
     assert abs(rate - 0.25) < 0.005
+
+
+# ---- random/test_multivariate_uniform_distribution.cpp:56-124 (what initialize_from_map samples) -------------
+def _uniform_states(orc, cells, resolution, origin, n, mode, seed=3):
+    o = orc.Amcl(orc.AmclParam(min_particles=n, max_particles=n, seed=seed, rng_mode=mode), orc.MotionParam())
+    o.set_map(orc.LFM, orc.LfmParam(), orc.Grid(np.asarray(cells, dtype=bool), resolution, origin))
+    o.initialize_from_map()
+    st, w = o.particles()
+    assert np.all(w == 1.0)
+    return st
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_uniform_distribution_single_slot(orc, mode):  # GridSingleSlot :56-65
+    st = _uniform_states(orc, [[F]], 0.5, orc.se2(1.0, 2.0, 0.0), 16, mode)
+    assert np.abs(st[:, 2] - 1.25).max() < 1e-3 and np.abs(st[:, 3] - 2.25).max() < 1e-3
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_uniform_distribution_single_free_slot(orc, mode):  # GridSingleFreeSlot :67-82
+    cells = np.ones((5, 5), dtype=bool)
+    cells[2, 2] = False
+    st = _uniform_states(orc, cells, 1.0, orc.IDENTITY, 16, mode)
+    assert np.abs(st[:, 2] - 2.5).max() < 1e-3 and np.abs(st[:, 3] - 2.5).max() < 1e-3
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_uniform_distribution_some_free_slots(orc, mode):  # GridSomeFreeSlots :84-124, 100k samples, tolerance 0.01
+    cells = [[T, F, T], [F, T, F], [T, F, T]]
+    st = _uniform_states(orc, cells, 1.0, orc.IDENTITY, 100_000, mode)
+    buckets, counts = np.unique(st[:, 2:4], axis=0, return_counts=True)
+    assert len(buckets) == 4
+    got = {tuple(b): c / 100_000 for b, c in zip(buckets, counts)}
+    for key in [(1.5, 0.5), (0.5, 1.5), (2.5, 1.5), (1.5, 2.5)]:
+        assert got[key] == pytest.approx(0.25, abs=0.01)
+    yaw = np.arctan2(st[:, 1], st[:, 0])  # SO2d::sampleUniform: uniform over [-pi, pi)
+    assert yaw.min() < -3.1 and yaw.max() > 3.1 and abs(yaw.mean()) < 0.02
