@@ -237,12 +237,14 @@ class AmclParams:
     record_ancestors: bool = False
     shard_first_index: int = 0  # sharded filters: global index of this rank's first particle
     shard_capacity: int = 0     # ... and its particle count (0: single GPU); max_particles is then the global count
+    recovery_probability_override: float = 0.0  # > 0: random_intersperse with this probability instead of the estimator's
 
     def c(self) -> _capi.AmclParam:
         return _capi.AmclParam(self.update_min_d, self.update_min_a, self.resample_interval, int(self.selective_resampling),
                                self.min_particles, self.max_particles, self.alpha_slow, self.alpha_fast, self.kld_epsilon,
                                self.kld_z, (C.c_double * 3)(*self.spatial_resolution), self.resample_scheme, self.seed,
-                               self.device, int(self.record_ancestors), self.shard_first_index, self.shard_capacity)
+                               self.device, int(self.record_ancestors), self.shard_first_index, self.shard_capacity,
+                               self.recovery_probability_override)
 
 
 @dataclass
@@ -555,6 +557,20 @@ class Amcl:
         self._check(self._lib.bb200_amcl_update_scan(self._h, _dptr(_f64(control_pose)), C.byref(scan), C.byref(res)))
         return res
 
+    def export_shard(self) -> bytes:
+        """192 bytes of CUDA IPC handles (two state buffers + mail block) for the peer ranks of a sharded filter."""
+        buf = C.create_string_buffer(192)
+        self._check(self._lib.bb200_amcl_export_shard(self._h, buf))
+        return buf.raw
+
+    def join_shards(self, world: int, rank: int, handles: bytes):
+        """Map every rank's exported buffers (world x 192 bytes, rank order); update() then runs in lock step with the peers."""
+        assert len(handles) == 192 * world
+        self._check(self._lib.bb200_amcl_join_shards(self._h, world, rank, C.create_string_buffer(handles, len(handles))))
+
+    def leave_shards(self):
+        self._check(self._lib.bb200_amcl_leave_shards(self._h))
+
     def plan_update(self, control_pose) -> _capi.StepPlan:
         """Host half of Amcl::update (policies, control window, recovery estimator)."""
         plan = _capi.StepPlan()
@@ -570,3 +586,67 @@ class Amcl:
         res = _capi.UpdateResult()
         self._check(self._lib.bb200_amcl_update(self._h, _dptr(_f64(control_pose)), _dptr(pts), len(pts), C.byref(res)))
         return res
+
+
+class ShardedAmcl:
+    """bb200_sharded_amcl: ONE filter over several shards driven by one host thread (include/beluga_b200.h).
+
+    `devices[r]` is the CUDA ordinal of shard r; ordinals may repeat (several shards on one device -- how the
+    single-GPU tests exercise the sharded kernels).  params.max_particles is the GLOBAL particle count."""
+
+    def __init__(self, motion, params: AmclParams, devices):
+        self._lib = _capi.load()
+        p, m = params.c(), motion.c_motion()
+        dev = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        st = self._lib.bb200_sharded_amcl_create(C.byref(p), C.byref(m), len(devices), dev, C.byref(h))
+        if st != _capi.OK:
+            raise BelugaB200Error(st, self._lib.bb200_create_error().decode())
+        self._h = h
+        self.params = params
+        self.shards = [Filter(_handle=self._lib.bb200_amcl_filter(self._lib.bb200_sharded_amcl_shard(self._h, r)), _owner=self)
+                       for r in range(len(devices))]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for f in self.shards:
+                f._h = None
+            self._lib.bb200_sharded_amcl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, st: int):
+        if st != _capi.OK:
+            raise BelugaB200Error(st, self._lib.bb200_sharded_amcl_last_error(self._h).decode())
+
+    def update_map(self, sensor: int, params, grid: OccupancyGrid):
+        g = grid.c()
+        p = params.c()
+        if sensor == SENSOR_BEAM:
+            self._check(self._lib.bb200_sharded_amcl_set_beam_map(self._h, C.byref(p), C.byref(g)))
+        else:
+            self._check(self._lib.bb200_sharded_amcl_set_likelihood_field_map(self._h, C.byref(p), C.byref(g), int(sensor == SENSOR_LIKELIHOOD_FIELD_PROB)))
+
+    def initialize(self, mean_xytheta, cov):
+        self._check(self._lib.bb200_sharded_amcl_initialize(self._h, _dptr(_f64(mean_xytheta)), _dptr(_f64(cov).reshape(9))))
+
+    def initialize_from_map(self):
+        self._check(self._lib.bb200_sharded_amcl_initialize_from_map(self._h))
+
+    def force_update(self):
+        self._lib.bb200_sharded_amcl_force_update(self._h)
+
+    def update(self, control_pose, points) -> _capi.UpdateResult:
+        pts = _f64(points).reshape(-1, 2)
+        res = _capi.UpdateResult()
+        self._check(self._lib.bb200_sharded_amcl_update(self._h, _dptr(_f64(control_pose)), _dptr(pts) if len(pts) else None, len(pts), C.byref(res)))
+        return res
+
+    def particles(self):
+        n = self.params.max_particles
+        st = np.zeros((n, 4))
+        w = np.zeros(n)
+        self._check(self._lib.bb200_sharded_amcl_get_particles(self._h, _dptr(st), _dptr(w), n))
+        return st, w

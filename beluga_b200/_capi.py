@@ -85,7 +85,8 @@ class AmclParam(C.Structure):
                 ("selective_resampling", C.c_int), ("min_particles", C.c_uint64), ("max_particles", C.c_uint64),
                 ("alpha_slow", C.c_double), ("alpha_fast", C.c_double), ("kld_epsilon", C.c_double), ("kld_z", C.c_double),
                 ("spatial_resolution", C.c_double * 3), ("resample_scheme", C.c_int), ("seed", C.c_uint64), ("device", C.c_int),
-                ("record_ancestors", C.c_int), ("shard_first_index", C.c_uint64), ("shard_capacity", C.c_uint64)]
+                ("record_ancestors", C.c_int), ("shard_first_index", C.c_uint64), ("shard_capacity", C.c_uint64),
+                ("recovery_probability_override", C.c_double)]
 
 
 class StepPlan(C.Structure):
@@ -173,6 +174,23 @@ SIGNATURES = {
     "bb200_scan_to_points": (C.c_int, [_P(LaserScan), _dbl, C.c_uint64, _P(C.c_uint64)]),
     "bb200_take_evenly_indices": (C.c_int, [C.c_uint64, C.c_uint64, _P(C.c_uint64), C.c_uint64, _P(C.c_uint64)]),
     "bb200_amcl_update_scan": (C.c_int, [_vp, _dbl, _P(LaserScan), _P(UpdateResult)]),
+    "bb200_sharded_amcl_create": (C.c_int, [_P(AmclParam), _P(MotionParam), C.c_int, _P(C.c_int), _P(_vp)]),
+    "bb200_sharded_amcl_destroy": (None, [_vp]),
+    "bb200_sharded_amcl_last_error": (C.c_char_p, [_vp]),
+    "bb200_sharded_amcl_shards": (C.c_int, [_vp]),
+    "bb200_sharded_amcl_shard": (_vp, [_vp, C.c_int]),
+    "bb200_sharded_amcl_set_likelihood_field_map": (C.c_int, [_vp, _P(LikelihoodFieldParam), _P(OccupancyGrid), C.c_int]),
+    "bb200_sharded_amcl_set_beam_map": (C.c_int, [_vp, _P(BeamParam), _P(OccupancyGrid)]),
+    "bb200_sharded_amcl_initialize": (C.c_int, [_vp, _dbl, _dbl]),
+    "bb200_sharded_amcl_initialize_from_map": (C.c_int, [_vp]),
+    "bb200_sharded_amcl_force_update": (None, [_vp]),
+    "bb200_sharded_amcl_update": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64, _P(UpdateResult)]),
+    "bb200_sharded_amcl_get_particles": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64]),
+    "bb200_amcl_export_shard": (C.c_int, [_vp, _vp]),
+    "bb200_amcl_join_shards": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "bb200_amcl_leave_shards": (C.c_int, [_vp]),
+    "bb200_filter_export_shard": (C.c_int, [_vp, _vp]),
+    "bb200_filter_join_shards": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "bb200_amcl_plan_update": (C.c_int, [_vp, _dbl, _P(StepPlan)]),
     "bb200_amcl_commit_update": (None, [_vp, C.c_int, C.c_double]),
     "bb200_amcl_create_with_motion": (C.c_int, [_P(AmclParam), _P(MotionParam), _P(_vp)]),

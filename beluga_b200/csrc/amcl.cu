@@ -2,7 +2,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <initializer_list>
 #include <limits>
+#include <vector>
 
 namespace bb200 {
 
@@ -165,6 +167,7 @@ int Amcl::plan_update(const double control[4], bb200_step_plan* plan) {
   if (!(std::fabs(slow_average) < std::numeric_limits<double>::epsilon())) {
     random_state_probability = std::clamp(1.0 - fast_average / slow_average, 0.0, 1.0);
   }
+  if (params_.recovery_probability_override > 0.0) random_state_probability = std::min(params_.recovery_probability_override, 1.0);
   plan->random_state_probability = random_state_probability;
 
   // resample_policy_: every_n (every_n.hpp:47-50); on_effective_size_drop is applied by the caller
@@ -207,7 +210,99 @@ void Amcl::restore(const HostState& s) {
   step_ = s.step;
 }
 
+int Amcl::update_group(Amcl* const* ranks, int count, const double control[4], const double* points_xy, uint64_t n_points,
+                       bb200_update_result* out) {
+  *out = bb200_update_result{};
+  if (ranks == nullptr || count < 1 || count > kMaxShards) return BB200_ERR_INVALID_ARGUMENT;
+  Amcl& lead = *ranks[0];
+  if (lead.params_.min_particles < lead.params_.max_particles)
+    return lead.filter_->fail_with(BB200_ERR_STATE, "KLD-adaptive resampling is not available on a sharded filter");
+  for (int r = 0; r < count; ++r)
+    if (ranks[r]->sharded() && ranks[r]->filter_->shard_world() <= 1)
+      return ranks[r]->filter_->fail_with(BB200_ERR_STATE, "this shard has not joined its peers (bb200_amcl_join_shards / bb200_sharded_amcl_create)");
+  std::vector<HostState> before;
+  before.reserve(static_cast<size_t>(count));
+  for (int r = 0; r < count; ++r) before.push_back(ranks[r]->snapshot());
+  auto rollback = [&](int st) {
+    for (int r = 0; r < count; ++r) {
+      ranks[r]->restore(before[static_cast<size_t>(r)]);
+      ranks[r]->filter_->step_abort();
+    }
+    return st;
+  };
+  // The host half is the same arithmetic on every shard (policies, control window, recovery estimator).
+  bb200_step_plan plan{};
+  for (int r = 0; r < count; ++r) {
+    bb200_step_plan p{};
+    const int st = ranks[r]->plan_update(control, &p);
+    if (st != BB200_OK) return rollback(st);
+    if (r == 0) plan = p;
+    if (p.update != plan.update || p.step != plan.step) return rollback(lead.filter_->fail_with(BB200_ERR_STATE, "the shards of a filter disagree on the step plan"));
+  }
+  if (!plan.update) return BB200_OK;
+  out->random_state_probability = plan.random_state_probability;
+
+  auto run_phases = [&](std::initializer_list<int> phases) {
+    for (const int phase : phases)
+      for (int r = 0; r < count; ++r) {
+        const int st = ranks[r]->filter_->step_phase(phase);
+        if (st != BB200_OK) return st;
+      }
+    return static_cast<int>(BB200_OK);
+  };
+  auto close_batch = [&](double* sum_sq) {
+    for (int r = 0; r < count; ++r) {
+      bb200_estimate est{};
+      double weight_sum = 0.0, sq = 0.0;
+      uint64_t n = 0;
+      const int st = ranks[r]->filter_->step_end(&est, &weight_sum, &n, &sq);
+      if (st != BB200_OK) return st;
+      if (r == 0) {  // the exchanged sums are the same bits on every shard
+        out->estimate = est;
+        out->weight_sum = weight_sum;
+        out->n_particles = n;
+        if (sum_sq != nullptr) *sum_sq = sq;
+      }
+    }
+    return static_cast<int>(BB200_OK);
+  };
+
+  for (int r = 0; r < count; ++r) {
+    const int st = ranks[r]->filter_->step_begin(plan.sampling, plan.step, points_xy, n_points, plan.opts);
+    if (st != BB200_OK) return rollback(st);
+  }
+  const bool resample_now = plan.resample != 0 && plan.needs_ess == 0;
+  int st = resample_now ? run_phases({Filter::kPhaseReweight, Filter::kPhaseCdf, Filter::kPhaseResample, Filter::kPhaseFinish})
+                        : run_phases({Filter::kPhaseReweight, Filter::kPhaseCdf, Filter::kPhaseNormalize, Filter::kPhaseFinish});
+  double sum_sq = 0.0;
+  if (st == BB200_OK) st = close_batch(&sum_sq);
+  if (st != BB200_OK) return rollback(st);
+  bool resampled = resample_now;
+  if (!resample_now && plan.resample != 0) {
+    // on_effective_size_drop (on_effective_size_drop.hpp:45-49): ESS = 1 / sum w~^2 < N / 2
+    const double ess = sum_sq > 0.0 ? 1.0 / sum_sq : 0.0;
+    if (ess < static_cast<double>(lead.params_.max_particles) * 0.5) {
+      st = run_phases({Filter::kPhaseResample, Filter::kPhaseFinish});
+      if (st == BB200_OK) st = close_batch(nullptr);
+      if (st != BB200_OK) return rollback(st);
+      resampled = true;
+    }
+  }
+  out->resampled = resampled ? 1 : 0;
+  out->weights_degenerate = lead.filter_->last_weights_valid() ? 0 : 1;
+  for (int r = 0; r < count; ++r) {
+    ranks[r]->filter_->step_abort();
+    ranks[r]->commit_update(out->resampled, plan.random_state_probability);
+  }
+  out->updated = 1;
+  return BB200_OK;
+}
+
 int Amcl::update(const double control[4], const double* points_xy, uint64_t n_points, bb200_update_result* out) {
+  if (sharded()) {  // this process drives one shard; the peers call update() themselves
+    Amcl* self = this;
+    return update_group(&self, 1, control, points_xy, n_points, out);
+  }
   const HostState before = snapshot();
   const int st = update_device(control, points_xy, n_points, out);
   if (st != BB200_OK) restore(before);  // policies, control window and recovery estimator as if the call had not happened

@@ -36,6 +36,12 @@ class Amcl {
   /// Closes a planned step (estimator reset after injection, force_update flag).
   void commit_update(int resampled, double random_state_probability);
   bool sharded() const { return params_.shard_capacity != 0; }
+  const bb200_amcl_param& params() const { return params_; }
+  /// Amcl::update over the `count` shards of ONE filter held by this thread (count == 1: this process drives one shard
+  /// and the other ranks call update() themselves, in lock step).  Every phase of the step is enqueued on all shards
+  /// before the next one, the exchanges between the shards happen on the devices (csrc/kernels.cuh: ShardMail).
+  static int update_group(Amcl* const* ranks, int count, const double control[4], const double* points_xy, uint64_t n_points,
+                          bb200_update_result* out);
 
  private:
   bb200_amcl_param params_;

@@ -1,5 +1,7 @@
 // extern "C" surface of libbeluga_b200.so (declared in include/beluga_b200.h).
+#include <algorithm>
 #include <cmath>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -21,6 +23,16 @@ struct bb200_amcl {
   Amcl impl;
   bb200_filter* filter_view;  // non-owning alias handed out by bb200_amcl_filter
   bb200_amcl(const bb200_amcl_param& p, const bb200_motion_param& m) : impl(p, m), filter_view(nullptr) {}
+};
+
+/// One filter over several shards driven by ONE host thread (the shape of beluga_ros's single-process node).
+struct bb200_sharded_amcl {
+  std::vector<bb200_amcl*> ranks;
+  mutable std::string error;
+  void record_error(const std::string& m) const { error = m; }
+  ~bb200_sharded_amcl() {
+    for (bb200_amcl* a : ranks) delete a;
+  }
 };
 
 namespace {
@@ -447,6 +459,137 @@ int bb200_amcl_update_scan(bb200_amcl* a, const double control_pose[4], const bb
     const int st = bb200_scan_to_points(scan, points.data(), scan->n_ranges + 1, &n);
     if (st != BB200_OK) return st;
     return bb200_amcl_update(a, control_pose, points.data(), n, out);
+  });
+}
+
+// ---- sharded filters ---------------------------------------------------------------------------------
+
+int bb200_amcl_export_shard(bb200_amcl* a, void* out192) {
+  BB_REQUIRE(a && out192);
+  return guarded(a->impl, [&] { return a->impl.filter().export_shard(out192); });
+}
+int bb200_amcl_join_shards(bb200_amcl* a, int world, int rank, const void* handles) {
+  BB_REQUIRE(a && handles);
+  return guarded(a->impl, [&] { return a->impl.filter().join_shards_ipc(world, rank, handles); });
+}
+int bb200_amcl_leave_shards(bb200_amcl* a) {
+  BB_REQUIRE(a);
+  return guarded(a->impl, [&] { return a->impl.filter().leave_shards(); });
+}
+int bb200_filter_export_shard(bb200_filter* f, void* out192) {
+  BB_REQUIRE(f && out192);
+  return guarded(f->impl, [&] { return f->impl.export_shard(out192); });
+}
+int bb200_filter_join_shards(bb200_filter* f, int world, int rank, const void* handles) {
+  BB_REQUIRE(f && handles);
+  return guarded(f->impl, [&] { return f->impl.join_shards_ipc(world, rank, handles); });
+}
+
+int bb200_sharded_amcl_create(const bb200_amcl_param* p, const bb200_motion_param* motion, int n_shards, const int* devices, bb200_sharded_amcl** out) {
+  if (p == nullptr || motion == nullptr || out == nullptr || devices == nullptr) {
+    g_create_error = "null argument";
+    return BB200_ERR_INVALID_ARGUMENT;
+  }
+  *out = nullptr;
+  if (n_shards < 1 || n_shards > bb200::kMaxShards || p->max_particles == 0 || p->max_particles % static_cast<uint64_t>(n_shards) != 0) {
+    g_create_error = "a filter splits into 1..8 equal shards: max_particles must be a multiple of n_shards";
+    return BB200_ERR_INVALID_ARGUMENT;
+  }
+  return guarded_create([&] {
+    auto group = std::make_unique<bb200_sharded_amcl>();
+    const uint64_t shard = p->max_particles / static_cast<uint64_t>(n_shards);
+    std::vector<bb200::Filter*> filters;
+    for (int r = 0; r < n_shards; ++r) {
+      bb200_amcl_param q = *p;
+      q.min_particles = q.max_particles;  // the particle count of a sharded filter is fixed
+      q.device = devices[r];
+      q.shard_capacity = shard;
+      q.shard_first_index = static_cast<uint64_t>(r) * shard;
+      bb200_amcl* a = nullptr;
+      const int st = bb200_amcl_create_with_motion(&q, motion, &a);
+      if (st != BB200_OK) return st;
+      group->ranks.push_back(a);
+      filters.push_back(&a->impl.filter());
+    }
+    if (p->min_particles != p->max_particles) {
+      g_create_error = "KLD-adaptive resampling is not available on a sharded filter (min_particles must equal max_particles)";
+      return static_cast<int>(BB200_ERR_INVALID_ARGUMENT);
+    }
+    const int st = bb200::Filter::join_shards_local(filters.data(), n_shards);
+    if (st != BB200_OK) {
+      g_create_error = "joining the shards failed (peer access between the devices?)";
+      for (bb200::Filter* f : filters)
+        if (f->last_error()[0] != '\0') g_create_error = f->last_error();
+      return st;
+    }
+    *out = group.release();
+    return static_cast<int>(BB200_OK);
+  });
+}
+void bb200_sharded_amcl_destroy(bb200_sharded_amcl* g) { delete g; }
+const char* bb200_sharded_amcl_last_error(const bb200_sharded_amcl* g) {
+  if (g == nullptr) return "null sharded amcl";
+  if (!g->error.empty()) return g->error.c_str();
+  for (const bb200_amcl* a : g->ranks)
+    if (a->impl.last_error()[0] != '\0') return a->impl.last_error();
+  return "";
+}
+int bb200_sharded_amcl_shards(const bb200_sharded_amcl* g) { return g != nullptr ? static_cast<int>(g->ranks.size()) : 0; }
+bb200_amcl* bb200_sharded_amcl_shard(bb200_sharded_amcl* g, int rank) {
+  return (g != nullptr && rank >= 0 && rank < static_cast<int>(g->ranks.size())) ? g->ranks[static_cast<size_t>(rank)] : nullptr;
+}
+#define BB_EACH_SHARD(call)                                   \
+  BB_REQUIRE(g);                                              \
+  g->error.clear();                                           \
+  return guarded(*g, [&] {                                    \
+    for (bb200_amcl* a : g->ranks) {                          \
+      const int st = (call);                                  \
+      if (st != BB200_OK) return st;                          \
+    }                                                         \
+    return static_cast<int>(BB200_OK);                        \
+  })
+int bb200_sharded_amcl_set_likelihood_field_map(bb200_sharded_amcl* g, const bb200_likelihood_field_param* p, const bb200_occupancy_grid* grid, int prob) {
+  BB_REQUIRE(p && grid);
+  BB_EACH_SHARD(a->impl.filter().set_likelihood_field_map(*p, *grid, prob != 0));
+}
+int bb200_sharded_amcl_set_beam_map(bb200_sharded_amcl* g, const bb200_beam_param* p, const bb200_occupancy_grid* grid) {
+  BB_REQUIRE(p && grid);
+  BB_EACH_SHARD(a->impl.filter().set_beam_map(*p, *grid));
+}
+int bb200_sharded_amcl_initialize(bb200_sharded_amcl* g, const double mean_xytheta[3], const double cov[9]) {
+  BB_REQUIRE(mean_xytheta && cov);
+  BB_EACH_SHARD(a->impl.initialize(mean_xytheta, cov));
+}
+int bb200_sharded_amcl_initialize_from_map(bb200_sharded_amcl* g) { BB_EACH_SHARD(a->impl.initialize_from_map()); }
+#undef BB_EACH_SHARD
+void bb200_sharded_amcl_force_update(bb200_sharded_amcl* g) {
+  if (g != nullptr)
+    for (bb200_amcl* a : g->ranks) a->impl.force_update();
+}
+int bb200_sharded_amcl_update(bb200_sharded_amcl* g, const double control_pose[4], const double* points_xy, uint64_t n_points, bb200_update_result* out) {
+  BB_REQUIRE(g && control_pose && out && (points_xy || n_points == 0));
+  static const double kNoPoints[2] = {0.0, 0.0};
+  g->error.clear();
+  return guarded(*g, [&] {
+    std::vector<Amcl*> ranks;
+    for (bb200_amcl* a : g->ranks) ranks.push_back(&a->impl);
+    return Amcl::update_group(ranks.data(), static_cast<int>(ranks.size()), control_pose, points_xy != nullptr ? points_xy : kNoPoints, n_points, out);
+  });
+}
+int bb200_sharded_amcl_get_particles(bb200_sharded_amcl* g, double* states, double* weights, uint64_t capacity) {
+  BB_REQUIRE(g);
+  g->error.clear();
+  return guarded(*g, [&] {
+    uint64_t done = 0;
+    for (bb200_amcl* a : g->ranks) {  // rank order is global particle order
+      Filter& f = a->impl.filter();
+      const uint64_t n = std::min<uint64_t>(f.size(), capacity - done);
+      const int st = f.get_particles(states != nullptr ? states + 4 * done : nullptr, weights != nullptr ? weights + done : nullptr, n);
+      if (st != BB200_OK) return st;
+      done += n;
+      if (done >= capacity) break;
+    }
+    return static_cast<int>(BB200_OK);
   });
 }
 

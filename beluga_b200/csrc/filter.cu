@@ -142,6 +142,12 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   BB_TRY(dev_alloc(&perm_, capacity_));
   BB_TRY(dev_alloc(&counters_, schedule_max_bins()));
   BB_TRY(dev_alloc(&sched_tiles_, schedule_tile_count()));
+  BB_TRY(dev_alloc(&mail_, 1));  // its own allocation: exported to peer processes through CUDA IPC
+  BB_TRY(dev_alloc(&shard_totals_, kMaxShards));
+  BB_TRY(dev_alloc(&summary_, 1));
+  BB_TRY(cudaMallocHost(reinterpret_cast<void**>(&summary_host_), sizeof(StepSummary)));
+  BB_TRY(cudaMemsetAsync(mail_, 0, sizeof(ShardMail), stream_));
+  BB_TRY(cudaMemsetAsync(summary_, 0, sizeof(StepSummary), stream_));
   BB_TRY(cudaMemsetAsync(scalars_, 0, sizeof(Scalars), stream_));
   BB_TRY(cudaStreamSynchronize(stream_));
 #undef BB_TRY
@@ -150,12 +156,12 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
 
 Filter::~Filter() {
   if (stream_ != nullptr) cudaStreamSynchronize(stream_);
-  for (int r = 0; r < peer_world_; ++r) {  // unmap the peers' state buffers (CUDA IPC)
-    if (r == peer_rank_) continue;
-    for (int b = 0; b < 2; ++b)
-      if (peer_states_[b][r] != nullptr) cudaIpcCloseMemHandle(peer_states_[b][r]);
-  }
+  release_peers();
   for (auto& e : event_pool_) cudaEventDestroy(e);
+  cudaFree(mail_);
+  cudaFree(shard_totals_);
+  cudaFree(summary_);
+  cudaFreeHost(summary_host_);
   cudaFree(states_[0]);
   cudaFree(states_[1]);
   cudaFree(weights_);
@@ -352,6 +358,337 @@ int Filter::open_peers(int world, int rank, const void* handles) {
   }
   peer_world_ = world;
   peer_rank_ = rank;
+  peers_ipc_ = true;
+  return BB200_OK;
+}
+
+void Filter::release_peers() {
+  if (peers_ipc_) {  // unmap what cudaIpcOpenMemHandle mapped; local peers are plain pointers owned by their filters
+    for (int r = 0; r < peer_world_; ++r) {
+      if (r == peer_rank_) continue;
+      for (int b = 0; b < 2; ++b)
+        if (peer_states_[b][r] != nullptr) cudaIpcCloseMemHandle(peer_states_[b][r]);
+      if (peer_mail_[r] != nullptr) cudaIpcCloseMemHandle(peer_mail_[r]);
+    }
+  }
+  for (int r = 0; r < kMaxShards; ++r) {
+    peer_states_[0][r] = peer_states_[1][r] = nullptr;
+    peer_mail_[r] = nullptr;
+  }
+  peer_world_ = 0;
+  peers_ipc_ = false;
+}
+
+int Filter::leave_shards() {
+  BB_CHECK(cudaSetDevice(config_.device));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  release_peers();
+  return BB200_OK;
+}
+
+int Filter::export_shard(void* out192) {
+  BB_CHECK(cudaSetDevice(config_.device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "three IPC handles are exported as 192 bytes");
+  cudaIpcMemHandle_t h[3];
+  BB_CHECK(cudaIpcGetMemHandle(&h[0], states_[0]));
+  BB_CHECK(cudaIpcGetMemHandle(&h[1], states_[1]));
+  BB_CHECK(cudaIpcGetMemHandle(&h[2], mail_));
+  std::memcpy(out192, h, sizeof(h));
+  return BB200_OK;
+}
+
+int Filter::join_shards_ipc(int world, int rank, const void* handles) {
+  if (world < 1 || world > kMaxShards || rank < 0 || rank >= world) return fail(BB200_ERR_INVALID_ARGUMENT, "shard groups hold 1..8 ranks");
+  if (peer_world_ != 0) return fail(BB200_ERR_STATE, "the peers' buffers are already mapped");
+  if (config_.first_index != static_cast<uint64_t>(rank) * capacity_ || config_.global_count != static_cast<uint64_t>(world) * capacity_)
+    return fail(BB200_ERR_INVALID_ARGUMENT, "shard r of R holds the global indices [r * capacity, (r + 1) * capacity) of R * capacity particles");
+  BB_CHECK(cudaSetDevice(config_.device));
+  const auto* all = static_cast<const cudaIpcMemHandle_t*>(handles);
+  peers_ipc_ = true;
+  peer_world_ = world;
+  peer_rank_ = rank;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      peer_states_[0][r] = states_[0];
+      peer_states_[1][r] = states_[1];
+      peer_mail_[r] = mail_;
+      continue;
+    }
+    void* p[3] = {nullptr, nullptr, nullptr};
+    for (int b = 0; b < 3; ++b) {
+      const int st = check(cudaIpcOpenMemHandle(&p[b], all[3 * r + b], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+      if (st != BB200_OK) {
+        peer_states_[0][r] = static_cast<Pose2*>(p[0]);
+        peer_states_[1][r] = static_cast<Pose2*>(p[1]);
+        release_peers();
+        return st;
+      }
+    }
+    peer_states_[0][r] = static_cast<Pose2*>(p[0]);
+    peer_states_[1][r] = static_cast<Pose2*>(p[1]);
+    peer_mail_[r] = static_cast<ShardMail*>(p[2]);
+  }
+  split_posts_ = false;  // every rank has its own host thread: post and wait travel in one launch
+  return BB200_OK;
+}
+
+int Filter::join_shards_local(Filter* const* filters, int world) {
+  if (filters == nullptr || world < 1 || world > kMaxShards) return BB200_ERR_INVALID_ARGUMENT;
+  for (int r = 0; r < world; ++r) {
+    Filter* f = filters[r];
+    if (f == nullptr || !f->ok()) return BB200_ERR_INVALID_ARGUMENT;
+    if (f->peer_world_ != 0) return f->fail(BB200_ERR_STATE, "the peers' buffers are already mapped");
+    if (f->capacity_ != filters[0]->capacity_ || f->config_.first_index != static_cast<uint64_t>(r) * f->capacity_ ||
+        f->config_.global_count != static_cast<uint64_t>(world) * f->capacity_ || f->config_.seed != filters[0]->config_.seed)
+      return f->fail(BB200_ERR_INVALID_ARGUMENT, "shard r of R holds the global indices [r * capacity, (r + 1) * capacity) of R * capacity particles, same seed");
+  }
+  for (int a = 0; a < world; ++a) {
+    Filter* fa = filters[a];
+    for (int b = 0; b < world; ++b) {
+      const Filter* fb = filters[b];
+      if (fa->config_.device != fb->config_.device) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, fa->config_.device, fb->config_.device) != cudaSuccess || !can)
+          return fa->fail(BB200_ERR_CUDA, "no peer access between the devices of two shards");
+        if (fa->check(cudaSetDevice(fa->config_.device), "cudaSetDevice") != BB200_OK) return BB200_ERR_CUDA;
+        const cudaError_t e = cudaDeviceEnablePeerAccess(fb->config_.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fa->check(e, "cudaDeviceEnablePeerAccess");
+        (void)cudaGetLastError();
+      }
+      fa->peer_states_[0][b] = fb->states_[0];
+      fa->peer_states_[1][b] = fb->states_[1];
+      fa->peer_mail_[b] = fb->mail_;
+    }
+    fa->peer_world_ = world;
+    fa->peer_rank_ = a;
+    fa->peers_ipc_ = false;
+    fa->split_posts_ = true;  // one thread enqueues all shards: every post must be enqueued before any wait that needs it
+  }
+  return BB200_OK;
+}
+
+int Filter::enqueue_exchange(int kind, bool post, bool wait) {
+  ShardExchangeArgs a{};
+  a.kind = kind;
+  a.post = post ? 1 : 0;
+  a.wait = wait ? 1 : 0;
+  a.rank = peer_rank_;
+  a.world = peer_world_;
+  a.epoch = epoch_;
+  for (int r = 0; r < peer_world_; ++r) a.peers[r] = peer_mail_[r];
+  a.scalars = scalars_;
+  a.results = results_;
+  a.summary = summary_;
+  a.rank_totals = shard_totals_;
+  a.ceil_log2_count = ceil_log2_count(config_.global_count);
+  a.tile_state = tile_state_;
+  a.n_tiles = scan_tile_count(n_);
+  launch_shard_exchange(a, stream_);
+  BB_LAUNCHED("shard_exchange");
+  return BB200_OK;
+}
+
+int Filter::step_begin(const bb200_motion_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points, const bb200_resample_opts& o) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  if (sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set");
+  if (o.min_particles < o.max_particles) return fail(BB200_ERR_STATE, "the fused step does not run KLD; use resample()");
+  if (n_points > 0xffffffffull) return fail(BB200_ERR_INVALID_ARGUMENT, "too many points");
+  if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
+  const uint64_t world = peer_world_ > 1 ? static_cast<uint64_t>(peer_world_) : 1;
+  if (world > 1) {
+    if (n_ != capacity_ || o.max_particles != world * capacity_) return fail(BB200_ERR_STATE, "a sharded filter keeps `capacity` particles on every rank");
+  } else if (o.max_particles == 0 || o.max_particles > capacity_) {
+    return fail(BB200_ERR_CAPACITY, "max_particles exceeds the filter capacity");
+  }
+  BB_CHECK(cudaSetDevice(config_.device));
+  const int st = upload_points(points_xy, n_points);
+  if (st != BB200_OK) return st;
+  if (world > 1 && peer_mail_[0] == nullptr) return fail(BB200_ERR_STATE, "shards joined without mail blocks (legacy open_peers): use join_shards");
+  step_ = StepContext{};
+  step_.active = true;
+  step_.sampling = to_kernel_sampling(sampling);
+  step_.step = step;
+  step_.n_points = n_points;
+  step_.opts = o;
+  return BB200_OK;
+}
+
+void Filter::step_abort() { step_.active = false; }
+
+int Filter::step_phase(int phase) {
+  if (!step_.active) return fail(BB200_ERR_STATE, "step_begin must run first");
+  BB_CHECK(cudaSetDevice(config_.device));
+  const bool sharded = peer_world_ > 1;
+  const bb200_resample_opts& o = step_.opts;
+  int st = BB200_OK;
+  switch (phase) {
+    case kPhaseReweight: {
+      mark("begin_step");
+      launch_begin_step(scalars_, stream_);
+      BB_LAUNCHED("begin_step");
+      st = enqueue_propagate_reweight(&step_.sampling, step_.step, true, step_.n_points);
+      if (st != BB200_OK) return st;
+      if (sharded) {
+        ++epoch_;  // one sequence number per batch of exchanges
+        if (split_posts_) {
+          mark("exchange");
+          st = enqueue_exchange(kExchangeWmax, true, false);
+        }
+      }
+      return st;
+    }
+    case kPhaseCdf: {
+      if (sharded) {
+        mark("exchange");
+        st = enqueue_exchange(kExchangeWmax, !split_posts_, true);  // global largest weight -> exponent; resets the scan state
+        if (st != BB200_OK) return st;
+      } else {
+        mark("prepare_cdf");
+        launch_prepare_cdf(scalars_, -1.0, config_.global_count, tile_state_, scan_tile_count(n_), stream_);
+        BB_LAUNCHED("prepare_cdf");
+      }
+      mark("quantize_scan");
+      launch_quantize_scan(weights_, n_, cdf_, scalars_, tile_state_, stream_);
+      BB_LAUNCHED("quantize_scan");
+      if (sharded) {
+        if (split_posts_) {
+          mark("exchange");
+          st = enqueue_exchange(kExchangeTotal, true, false);
+        }
+      }
+      return st;
+    }
+    case kPhaseResample: {
+      if (step_.resampled) return fail(BB200_ERR_STATE, "this step has already resampled");
+      ResampleArgs a;
+      if (sharded) {
+        if (!step_.totals_exchanged) {
+          mark("exchange");
+          st = enqueue_exchange(kExchangeTotal, !split_posts_, true);  // every rank's fixed-point total -> CDF offsets
+          if (st != BB200_OK) return st;
+          step_.totals_exchanged = true;
+        }
+        const bool systematic = o.scheme == BB200_RESAMPLE_SYSTEMATIC;
+        a = make_resample_args(o, 0, systematic ? capacity_ : o.max_particles, false);
+        a.slot_first = 0;
+        a.weights_out = nullptr;
+        a.ancestors = nullptr;
+        a.peer_count = peer_world_;
+        a.peer_shard = capacity_;
+        a.rank_totals = shard_totals_;
+        a.rank = peer_rank_;
+        a.world = peer_world_;
+        if (!systematic) {  // draws are independent: walk all global slots, keep those landing in this rank's CDF span
+          a.span_filter = 1;
+          a.owner_first = config_.first_index;
+          a.owner_count = capacity_;
+        }
+        for (int r = 0; r < peer_world_; ++r) a.peer_out[r] = peer_states_[cur_ ^ 1][r];
+        mark("fill_weights");
+        launch_fill(weights_, capacity_, 1.0, stream_);  // the CDF holds what sampling needs; every new particle weighs 1
+        BB_LAUNCHED("fill_weights");
+        mark("resample_push");
+      } else {
+        a = make_resample_args(o, 0, o.max_particles, false);
+        mark("resample");
+      }
+      launch_resample(a, scalars_, partials_, stream_);
+      BB_LAUNCHED("resample");
+      step_.resampled = true;
+      step_.partial_rows = resample_block_count(a.slot_count);
+      mark("reduce_partials");
+      launch_reduce_partials(partials_, step_.partial_rows, kMomentCount, results_, stream_);
+      BB_LAUNCHED("reduce_partials");
+      if (sharded && split_posts_) {
+        mark("exchange");
+        st = enqueue_exchange(kExchangeMoments, true, false);
+      }
+      return st;
+    }
+    case kPhaseFinish: {
+      if (sharded) {
+        mark("exchange");
+        st = enqueue_exchange(kExchangeMoments, !split_posts_, true);  // also the barrier: the peers' stores into this rank's buffer are complete
+        if (st != BB200_OK) return st;
+        mark("readback");
+        BB_CHECK(cudaMemcpyAsync(summary_host_, summary_, sizeof(StepSummary), cudaMemcpyDeviceToHost, stream_));
+      } else {
+        mark("readback");
+        BB_CHECK(cudaMemcpyAsync(results_host_, results_, kMomentCount * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        BB_CHECK(cudaMemcpyAsync(scalars_host_, scalars_, sizeof(Scalars), cudaMemcpyDeviceToHost, stream_));
+      }
+      mark("end");
+      return BB200_OK;
+    }
+    case kPhaseNormalize: {
+      if (step_.normalized) return fail(BB200_ERR_STATE, "the weights of this step are already normalised");
+      if (sharded) {
+        mark("exchange");
+        st = enqueue_exchange(kExchangeTotal, !split_posts_, true);
+        if (st != BB200_OK) return st;
+        step_.totals_exchanged = true;
+      }
+      uint32_t rows = 0;
+      mark("normalize");
+      launch_normalize(weights_, n_, scalars_, sharded ? ~0ull : 0ull, partials_, &rows, stream_);  // actions/normalize.hpp:82
+      BB_LAUNCHED("normalize");
+      mark("moments");
+      launch_moments(states_[cur_], weights_, n_, pivot_[0], pivot_[1], partials_, stream_);
+      BB_LAUNCHED("moments");
+      launch_reduce_partials(partials_, moments_block_count(n_), kMomentCount, results_, stream_);
+      BB_LAUNCHED("reduce_partials");
+      step_.normalized = true;
+      if (sharded && split_posts_) {
+        mark("exchange");
+        st = enqueue_exchange(kExchangeMoments, true, false);
+      }
+      return st;
+    }
+    default:
+      return fail(BB200_ERR_INVALID_ARGUMENT, "unknown step phase");
+  }
+}
+
+int Filter::step_end(bb200_estimate* est, double* weight_sum, uint64_t* new_size, double* sum_sq) {
+  if (!step_.active) return fail(BB200_ERR_STATE, "step_begin must run first");
+  BB_CHECK(cudaSetDevice(config_.device));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  finish_marks();
+  const bool sharded = peer_world_ > 1;
+  const double* moments = results_host_;
+  if (sharded) {
+    if (summary_host_->error != 0) {
+      step_.active = false;
+      return fail(BB200_ERR_STATE, "shard exchange timed out: a peer rank never posted its value for this step");
+    }
+    moments = summary_host_->moments;
+    step_.total = summary_host_->total;
+    step_.exponent = summary_host_->exponent;
+    weights_valid_ = summary_host_->valid != 0;
+  } else {
+    step_.total = scalars_host_->total;
+    step_.exponent = scalars_host_->exponent;
+    weights_valid_ = scalars_host_->valid != 0;
+  }
+  if (step_.resampled) {
+    cur_ ^= 1;
+    n_ = sharded ? capacity_ : step_.opts.max_particles;
+    ancestors_n_ = n_;
+    cdf_valid_ = false;
+    step_.active = false;
+  } else {
+    cdf_valid_ = true;  // kPhaseResample may still follow (selective resampling)
+    ++epoch_;           // ... as a new batch of exchanges
+  }
+  if (new_size != nullptr) *new_size = sharded ? config_.global_count : n_;
+  if (weight_sum != nullptr) *weight_sum = std::ldexp(static_cast<double>(step_.total), -step_.exponent);
+  if (sum_sq != nullptr) *sum_sq = moments[1];
+  if (!weights_valid_) error_ = "no positive finite weight (uniform CDF substituted)";
+  if (est != nullptr) {
+    estimate_from_moments(moments, est);
+    pivot_[0] = est->mean[2];
+    pivot_[1] = est->mean[3];
+  }
   return BB200_OK;
 }
 
@@ -1117,57 +1454,13 @@ int Filter::resample_kld(const bb200_resample_opts& o, uint64_t* accepted) {
 
 int Filter::step_resample(const bb200_motion_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points,
                           const bb200_resample_opts& o, bb200_estimate* est, double* weight_sum, uint64_t* new_size) {
-  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
-  if (sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set");
-  if (o.max_particles == 0 || o.max_particles > capacity_) return fail(BB200_ERR_CAPACITY, "max_particles exceeds the filter capacity");
-  if (o.min_particles < o.max_particles) return fail(BB200_ERR_STATE, "the fused step does not run KLD; use resample()");
-  if (n_points > 0xffffffffull) return fail(BB200_ERR_INVALID_ARGUMENT, "too many points");
-  if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
-  BB_CHECK(cudaSetDevice(config_.device));
-  int st = upload_points(points_xy, n_points);
-  if (st != BB200_OK) return st;
-  const MotionSampling s = to_kernel_sampling(sampling);
-
-  mark("begin_step");
-  launch_begin_step(scalars_, stream_);
-  BB_LAUNCHED("begin_step");
-  st = enqueue_propagate_reweight(&s, step, true, n_points);
-  if (st != BB200_OK) return st;
-  mark("prepare_cdf");
-  launch_prepare_cdf(scalars_, -1.0, config_.global_count, tile_state_, scan_tile_count(n_), stream_);
-  BB_LAUNCHED("prepare_cdf");
-  mark("quantize_scan");
-  launch_quantize_scan(weights_, n_, cdf_, scalars_, tile_state_, stream_);
-  BB_LAUNCHED("quantize_scan");
-
-  const ResampleArgs a = make_resample_args(o, 0, o.max_particles, false);
-  mark("resample");
-  launch_resample(a, scalars_, partials_, stream_);
-  BB_LAUNCHED("resample");
-  mark("reduce_partials");
-  launch_reduce_partials(partials_, resample_block_count(a.slot_count), kMomentCount, results_, stream_);
-  BB_LAUNCHED("reduce_partials");
-  mark("readback");
-  BB_CHECK(cudaMemcpyAsync(results_host_, results_, kMomentCount * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-  BB_CHECK(cudaMemcpyAsync(scalars_host_, scalars_, sizeof(Scalars), cudaMemcpyDeviceToHost, stream_));
-  mark("end");
-  BB_CHECK(cudaStreamSynchronize(stream_));
-  finish_marks();
-
-  cur_ ^= 1;
-  n_ = o.max_particles;
-  ancestors_n_ = n_;
-  cdf_valid_ = false;
-  if (new_size != nullptr) *new_size = n_;
-  if (weight_sum != nullptr) *weight_sum = std::ldexp(static_cast<double>(scalars_host_->total), -scalars_host_->exponent);
-  weights_valid_ = scalars_host_->valid != 0;
-  if (!weights_valid_) error_ = "no positive finite weight (uniform CDF substituted)";
-  if (est != nullptr) {
-    estimate_from_moments(results_host_, est);
-    pivot_[0] = est->mean[2];
-    pivot_[1] = est->mean[3];
+  int st = step_begin(sampling, step, points_xy, n_points, o);
+  for (int phase = kPhaseReweight; st == BB200_OK && phase <= kPhaseFinish; ++phase) st = step_phase(phase);
+  if (st != BB200_OK) {
+    step_.active = false;
+    return st;
   }
-  return BB200_OK;
+  return step_end(est, weight_sum, new_size, nullptr);
 }
 
 int Filter::ancestors(int64_t* out, uint64_t capacity) {

@@ -75,6 +75,34 @@ class Filter {
                                    const double pivot[2]);
   int enqueue_flip_adopt(uint64_t n);
   int enqueue_reduce_moments();
+
+  // ---- one filter over several shards, exchanges through peer memory (no NCCL, no host round trip) ----
+  /// CUDA IPC handles of the two state buffers and the mail block (3 x 64 bytes) for peers in OTHER processes.
+  int export_shard(void* out192);
+  /// Map the peers' buffers from their exported handles (world x 192 bytes, rank order); one process per GPU.
+  int join_shards_ipc(int world, int rank, const void* handles);
+  /// Shards living in THIS process (one per device, or several on one device): direct pointers, peer access enabled
+  /// between distinct devices.  filters[r] becomes rank r.
+  static int join_shards_local(Filter* const* filters, int world);
+  int shard_world() const { return peer_world_; }
+  /// Unmaps the peers' buffers (before any rank frees its own: CUDA IPC requires importers to close first).
+  int leave_shards();
+  /// The fused resampling step (propagate | reweight | normalize | resample | estimate), any number of shards.
+  /// step_begin validates and stages the inputs; step_phase(1..4) only enqueues; step_end synchronises once.
+  /// A driver holding several shards in one thread enqueues phase k of every shard before phase k+1 of any.
+  int step_begin(const bb200_motion_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points, const bb200_resample_opts& o);
+  enum StepPhase : int {
+    kPhaseReweight = 1,   // begin_step | propagate | schedule | reweight                      (posts the shard's largest weight)
+    kPhaseCdf = 2,        // common exponent | fixed-point CDF                                 (posts the shard's total)
+    kPhaseResample = 3,   // resample (+ redistribution over peer memory) | moments of the new set (posts them)
+    kPhaseFinish = 4,     // global moments, read-back
+    kPhaseNormalize = 5   // instead of kPhaseResample on a step that keeps its particles: w /= S | moments
+  };
+  int step_phase(int phase);
+  void step_abort();
+  /// Synchronises and closes the batch of phases enqueued so far.  After kPhaseNormalize a caller may still run
+  /// kPhaseResample + kPhaseFinish + step_end (selective resampling: the decision needs the effective sample size).
+  int step_end(bb200_estimate* est, double* weight_sum, uint64_t* new_size, double* sum_sq);
   int enqueue_moments(const double pivot[2]);   // raw moments stay in the device result block
 
   int synchronize();
@@ -88,6 +116,7 @@ class Filter {
   bool last_weights_valid() const { return weights_valid_; }
   const char* last_error() const { return error_.c_str(); }
   void record_error(const std::string& message) const { error_ = message; }  // the C-ABI exception guard
+  int fail_with(int status, const std::string& message) { return fail(status, message); }
   bool ok() const { return created_; }
   int create_status() const { return create_status_; }
 
@@ -104,6 +133,23 @@ class Filter {
   void finish_marks();
   bool use_device() const;
 
+  struct StepContext {
+    bool active{false};
+    MotionSampling sampling{};
+    uint32_t step{0};
+    uint64_t n_points{0};
+    bb200_resample_opts opts{};
+    uint32_t partial_rows{1};
+    bool resampled{false};   // kPhaseResample ran in the batch being closed
+    bool normalized{false};  // kPhaseNormalize ran (weights are normalised, the CDF stays valid)
+    bool totals_exchanged{false};  // the ranks' totals of this step are in shard_totals_
+    unsigned long long total{0};
+    int exponent{0};
+  };
+  StepContext step_{};
+  int enqueue_exchange(int kind, bool post, bool wait);
+  void release_peers();
+
   bb200_filter_config config_{};
   bool created_{false};
   int create_status_{BB200_OK};
@@ -113,6 +159,14 @@ class Filter {
   int peer_world_{0}, peer_rank_{0};
   uint32_t pushed_blocks_{1};
   Pose2* peer_states_[2][8]{};  // [buffer][rank]: the peers' ping-pong state buffers mapped into this process
+  ShardMail* mail_{nullptr};                 // this rank's mail block
+  ShardMail* peer_mail_[kMaxShards]{};       // every rank's mail block as seen from here ([rank] = mail_)
+  bool peers_ipc_{false};                    // the peer pointers came from cudaIpcOpenMemHandle
+  bool split_posts_{false};                  // post and wait as separate launches (several shards enqueued by one thread)
+  unsigned long long epoch_{0};              // sequence number of the next exchange (all ranks count alike)
+  unsigned long long* shard_totals_{nullptr};  // device: the ranks' fixed-point totals of this step
+  StepSummary* summary_{nullptr};            // device
+  StepSummary* summary_host_{nullptr};       // pinned
 
   // particle set (ping-pong states for the resample gather)
   uint64_t capacity_{0}, n_{0};

@@ -896,18 +896,22 @@ constexpr uint32_t kScanTile = kScanThreads * kScanItems;
 // tile_state word: [63:62] flag (0 empty, 1 aggregate, 2 inclusive prefix), [61:0] value
 constexpr unsigned long long kFlagAggregate = 1ull << 62, kFlagPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1;
 
+__device__ __forceinline__ void prepare_cdf_scalars(Scalars* s, double wmax, int ceil_log2_count) {
+  int ex = 0;
+  const bool ok = wmax > 0.0 && wmax <= DBL_MAX;
+  if (ok) (void)frexp(wmax, &ex);
+  const int p = min(52, 62 - ceil_log2_count);
+  s->exponent = p - ex;
+  s->valid = ok ? 1 : 0;
+  s->tile_ticket = 0;
+  s->total = 0;
+}
+
 __global__ void prepare_cdf_kernel(Scalars* s, double host_wmax, int ceil_log2_count, unsigned long long* tile_state, uint32_t n_tiles) {
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) tile_state[t] = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    double wmax = host_wmax >= 0.0 ? host_wmax : __longlong_as_double(static_cast<long long>(s->wmax_bits));
-    int ex = 0;
-    const bool ok = wmax > 0.0 && wmax <= DBL_MAX;
-    if (ok) (void)frexp(wmax, &ex);
-    const int p = min(52, 62 - ceil_log2_count);
-    s->exponent = p - ex;
-    s->valid = ok ? 1 : 0;
-    s->tile_ticket = 0;
-    s->total = 0;
+    const double wmax = host_wmax >= 0.0 ? host_wmax : __longlong_as_double(static_cast<long long>(s->wmax_bits));
+    prepare_cdf_scalars(s, wmax, ceil_log2_count);
   }
 }
 
@@ -1120,7 +1124,8 @@ __global__ void __launch_bounds__(kStreamThreads) normalize_kernel(double* __res
                                                                    unsigned long long global_total, double* __restrict__ partials) {
   __shared__ double s_red[kStreamThreads / kWarp];
   // S = T * 2^-e: the normalisation factor derived from the exact integer total.
-  const unsigned long long t = global_total != 0 ? global_total : scalars->total;  // 0: single GPU, total is on the device
+  // 0: single GPU, the total is on the device; ~0: sharded, the sum of the ranks' totals is on the device
+  const unsigned long long t = global_total == ~0ull ? scalars->global_total : (global_total != 0 ? global_total : scalars->total);
   const double factor = scalbn(static_cast<double>(t), -scalars->exponent);
   const bool valid = scalars->valid != 0 && factor > 0.0;
   double sq = 0.0;
@@ -1369,6 +1374,94 @@ __global__ void __launch_bounds__(256) fill_kernel(double* __restrict__ out, uin
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * 256) out[i] = value;
 }
 
+// ---- shard exchange ------------------------------------------------------------------------------------
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+constexpr unsigned long long kExchangeTimeoutNs = 4000000000ull;  // 4 s: a peer that has not posted by then never will
+
+__global__ void __launch_bounds__(256) shard_exchange_kernel(ShardExchangeArgs a) {
+  __shared__ unsigned long long s_u[kMaxShards];
+  __shared__ double s_d[kMaxShards][kMomentCount];
+  __shared__ int s_timeout;
+  const int t = threadIdx.x;
+  if (t == 0) s_timeout = 0;
+  __syncthreads();
+  if (a.post && t < a.world) {
+    // my value -> entry [kind][my rank] of rank t's block
+    volatile ShardMailEntry* dst = &a.peers[t]->e[a.kind][a.rank];
+    if (a.kind == kExchangeWmax) {
+      dst->u[0] = a.scalars->wmax_bits;
+    } else if (a.kind == kExchangeTotal) {
+      dst->u[0] = a.scalars->total;
+    } else if (a.kind == kExchangeMoments) {
+#pragma unroll
+      for (int k = 0; k < kMomentCount; ++k) dst->d[k] = a.results[k];
+    }
+    __threadfence_system();  // the payload -- and every earlier store of this stream, e.g. the states pushed to the peers -- before the flag
+    dst->seq = a.epoch;
+  }
+  if (a.wait) {
+    if (t < a.world) {
+      const volatile ShardMailEntry* src = &a.peers[a.rank]->e[a.kind][t];
+      const unsigned long long t0 = global_timer_ns();
+      bool ok = true;
+      while (src->seq != a.epoch) {
+        if (global_timer_ns() - t0 > kExchangeTimeoutNs) {
+          ok = false;
+          break;
+        }
+        __nanosleep(64);
+      }
+      __threadfence_system();
+      if (!ok) atomicExch(&s_timeout, 1);
+      s_u[t] = src->u[0];
+      if (a.kind == kExchangeMoments) {
+#pragma unroll
+        for (int k = 0; k < kMomentCount; ++k) s_d[t][k] = src->d[k];
+      }
+    }
+    __syncthreads();
+    if (t == 0) {
+      if (s_timeout) {
+        a.scalars->exchange_error = 1;
+        a.summary->error = 1;
+      }
+      if (a.kind == kExchangeWmax) {
+        unsigned long long m = 0;
+        for (int r = 0; r < a.world; ++r) m = s_u[r] > m ? s_u[r] : m;  // positive doubles order like their bit patterns
+        a.scalars->wmax_bits = m;
+        prepare_cdf_scalars(a.scalars, __longlong_as_double(static_cast<long long>(m)), a.ceil_log2_count);
+        a.summary->exponent = a.scalars->exponent;
+        a.summary->valid = a.scalars->valid;
+      } else if (a.kind == kExchangeTotal) {
+        unsigned long long total = 0;
+        for (int r = 0; r < a.world; ++r) {
+          a.rank_totals[r] = s_u[r];
+          a.summary->rank_totals[r] = s_u[r];
+          total += s_u[r];
+        }
+        a.summary->total = total;
+        a.scalars->global_total = total;
+      } else if (a.kind == kExchangeMoments) {
+        for (int k = 0; k < kMomentCount; ++k) {  // rank order: the same sum on every rank
+          double v = 0.0;
+          for (int r = 0; r < a.world; ++r) v = v + s_d[r][k];
+          a.results[k] = v;
+          a.summary->moments[k] = v;
+        }
+      }
+    }
+    if (a.kind == kExchangeWmax && a.tile_state != nullptr) {
+      for (uint32_t k = t; k < a.n_tiles; k += blockDim.x) a.tile_state[k] = 0;
+    }
+  }
+}
+
 int ceil_log2_u64(uint64_t n) {
   int b = 0;
   while ((uint64_t{1} << b) < n) ++b;
@@ -1382,6 +1475,9 @@ constexpr uint32_t kStreamMaxBlocks = 148 * 8;
 // ---- launchers -------------------------------------------------------------------------------------
 
 void launch_begin_step(Scalars* scalars, cudaStream_t stream) { begin_step_kernel<<<1, 1, 0, stream>>>(scalars); }
+
+void launch_shard_exchange(const ShardExchangeArgs& args, cudaStream_t stream) { shard_exchange_kernel<<<1, 256, 0, stream>>>(args); }
+int ceil_log2_count(uint64_t n) { return ceil_log2_u64(n); }
 
 void launch_initialize_normal(Pose2* states, double* weights, uint64_t n, const double mean[3], const double transform[9], uint64_t seed,
                               uint64_t first_index, cudaStream_t stream) {

@@ -85,7 +85,54 @@ struct Scalars {
   unsigned long long pad[3];
   unsigned long long work_ticket;  // persistent reweight kernel: next 32-particle task (rewound by the last warp out)
   unsigned long long work_done;    // warps that have left that kernel
+  int exchange_error;              // sticky: a shard exchange timed out
+  int pad2;
+  unsigned long long global_total; // sharded filters: sum of the ranks' totals (set by the totals exchange)
 };
+
+// ---- sharded filters: exchange of step scalars through peer memory ---------------------------------------
+// One filter split over several GPUs needs three tiny exchanges per step (largest weight -> common fixed-point
+// exponent; fixed-point totals -> CDF offsets; raw moments -> estimate, which is also the barrier after which the
+// peers' state stores are visible).  Every rank owns a ShardMail block in its device memory; rank r writes its value
+// into entry [kind][r] of EVERY rank's block (peer stores over NVLink, or plain stores when the shards share a
+// device) followed by a system-scope fence and the step's sequence number; a reader spins on the sequence numbers
+// of its own block.  No NCCL, no host round trip: a post/wait costs one single-CTA kernel.
+constexpr int kMaxShards = 8;
+enum ShardExchangeKind : int { kExchangeWmax = 0, kExchangeTotal = 1, kExchangeMoments = 2, kExchangeKld = 3, kExchangeKinds = 4 };
+struct alignas(128) ShardMailEntry {
+  unsigned long long seq;   // written last, after a system-scope fence
+  unsigned long long u[3];
+  double d[12];
+};
+struct ShardMail {
+  ShardMailEntry e[kExchangeKinds][kMaxShards];
+};
+/// What the host reads back at the end of a fused step (one copy).
+struct StepSummary {
+  double moments[9];              // raw moments of the new particle set (all ranks)
+  unsigned long long total;       // global fixed-point total of the CDF
+  unsigned long long rank_totals[kMaxShards];
+  int exponent;
+  int valid;                      // 0: no positive finite weight anywhere
+  int error;                      // 1: a peer never posted (bounded spin ran out)
+  int pad;
+};
+struct ShardExchangeArgs {
+  int kind, post, wait;
+  int rank, world;
+  unsigned long long epoch;
+  ShardMail* peers[kMaxShards];  // every rank's mail block (peers[rank] is this rank's own)
+  struct Scalars* scalars;
+  double* results;               // kMomentCount local sums in, global sums out (kExchangeMoments)
+  StepSummary* summary;          // device copy, filled as the exchanges complete
+  unsigned long long* rank_totals;  // device array of kMaxShards totals (kExchangeTotal)
+  // kExchangeWmax also prepares the CDF build (what prepare_cdf does on one GPU)
+  int ceil_log2_count;
+  unsigned long long* tile_state;
+  uint32_t n_tiles;
+};
+void launch_shard_exchange(const ShardExchangeArgs& args, cudaStream_t stream);
+int ceil_log2_count(uint64_t n);
 
 constexpr int kMomentCount = 9;  // sum w, sum w^2, sum w c, sum w s, sum w dx, sum w dy, sum w dx^2, sum w dx dy, sum w dy^2
 
@@ -151,6 +198,7 @@ void launch_quantize_scan(const double* weights, uint64_t n, unsigned long long*
                           cudaStream_t stream);
 
 /// w /= S (S = global_total * 2^-exponent) and per-block partial sums of (w/S)^2.
+/// global_total == ~0: the sharded filter's total on the device (scalars->global_total).
 void launch_normalize(double* weights, uint64_t n, const Scalars* scalars, unsigned long long global_total, double* partials,
                       uint32_t* n_partials, cudaStream_t stream);
 

@@ -1,4 +1,13 @@
-"""One MCL filter sharded over several GPUs: one process per GPU, torch.distributed for the plumbing.
+"""One MCL filter sharded over several GPUs: one process per GPU.
+
+Default path (p2p=True, up to 8 ranks with peer access): the whole sharded step runs INSIDE the library behind
+bb200_amcl_update -- the three per-step exchanges (largest weight, fixed-point totals, raw moments) go through
+mail blocks in peer memory written and polled by single-CTA kernels, the resampled states are stored straight
+into the slot owner's buffer over NVLink by the resample kernel itself.  torch.distributed is used ONCE, at
+construction, to hand the 192-byte CUDA IPC handle blobs around (any transport would do).  No NCCL call, no
+host round trip inside a step; one host synchronisation per step.
+
+Fallback path (p2p=False, or more than 8 ranks / no peer access): NCCL collectives enqueued from here, described below.
 
 Particles are split into contiguous global index ranges, `shard` particles per rank; the map and
 the scan are replicated.  Every per-particle kernel runs on the local shard unchanged (the counter
@@ -126,21 +135,31 @@ class ShardedAmcl:
         self.pivot = np.zeros(2)
         self._new_states = None
         self._recv_tmp = None
-        # Kernels and collectives share torch's current stream: everything is stream-ordered and a step
-        # needs two host synchronisations (the CDF totals, the estimate).
-        self.filter.set_stream(torch.cuda.current_stream().cuda_stream)
         self._scalars = None
         self._results = None
-        # Fused resample + redistribution: map every rank's state buffers (CUDA IPC) so that the resample
-        # kernel stores each new particle straight into its owner's buffer over NVLink.
         self.p2p = p2p and 1 < self.world <= 8
         self.multinomial = params.resample_scheme != _capi.RESAMPLE_SYSTEMATIC
         if self.multinomial and not self.p2p:
             raise ValueError("sharded multinomial resampling needs the peer-memory path (p2p=True, 2..8 ranks)")
         if self.p2p:
+            # The only use of torch.distributed on this path: pass the IPC handle blobs around once.
             handles = [None] * self.world
-            dist.all_gather_object(handles, self.filter.ipc_handles(), group=process_group)
-            self.filter.open_peers(self.world, self.rank, b"".join(handles))
+            dist.all_gather_object(handles, self.amcl.export_shard(), group=process_group)
+            self.amcl.join_shards(self.world, self.rank, b"".join(handles))
+        else:
+            # Kernels and NCCL collectives share torch's current stream: everything is stream-ordered and a step
+            # needs two host synchronisations (the CDF totals, the estimate).
+            self.filter.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def close(self):
+        """Collective: unmap the peers' buffers, wait for every rank, then free (CUDA IPC: importers close before the exporter frees)."""
+        if getattr(self, "amcl", None) is None:
+            return
+        if self.p2p:
+            self.amcl.leave_shards()
+            self.dist.barrier(group=self.group)
+        self.amcl.close()
+        self.amcl = None
 
     def update_map(self, sensor, sensor_params, grid):
         self.amcl.update_map(sensor, sensor_params, grid)
@@ -207,18 +226,30 @@ class ShardedAmcl:
         random_state_probability overrides the recovery estimator's output for this step.  (The reference feeds
         the estimator normalised weights, whose mean is 1/N: with the fixed particle count of a sharded filter it
         never fires on its own; the override exercises views::random_intersperse on shards.)"""
+        if self.p2p:
+            # The C ABI runs the sharded step; every rank calls it in lock step (AmclParams.recovery_probability_override
+            # is the injection knob on this path).
+            if random_state_probability is not None:
+                raise ValueError("peer-memory path: set AmclParams.recovery_probability_override instead")
+            r = self.amcl.update(control_pose, points)
+            if not r.updated:
+                return None
+            mean = np.array(r.estimate.mean)
+            cov = np.array(r.estimate.cov).reshape(3, 3)
+            return mean, cov, {"resampled": bool(r.resampled), "weight_sum": r.weight_sum, "n_particles": int(r.n_particles),
+                               "random_state_probability": r.random_state_probability}
         plan = self.amcl.plan_update(control_pose)
         if not plan.update:
             return None
         if random_state_probability is not None:
             plan.random_state_probability = float(random_state_probability)
             plan.opts.random_state_probability = float(random_state_probability)
-        if plan.resample and not plan.needs_ess and (self.p2p or not self.multinomial):
+        if plan.resample and not plan.needs_ess:
             return self._update_streamed(plan, points)
         return self._update_stepwise(plan, points)
 
     def _update_streamed(self, plan, points):
-        """Resampling step with everything enqueued on one stream: one host synchronisation with peer access, two without."""
+        """NCCL fallback, resampling step with everything enqueued on one stream: two host synchronisations."""
         torch, dist, f = self.torch, self.dist, self.filter
         scalars, results = self._device_blocks()
         f.enqueue_propagate_reweight(plan.sampling, plan.step, points)
@@ -227,29 +258,14 @@ class ShardedAmcl:
         f.enqueue_build_cdf()
         dist.all_gather_into_tensor(self._totals[: self.world], scalars[2:3], group=self.group)
         self._totals[self.world: self.world + 1] = scalars[3:4]
-        if self.p2p:
-            # One kernel: CDF search + gather + peer stores into the owners' buffers + moments of what it produced.  It
-            # derives the CDF offsets and (systematic) this rank's contiguous slot range from the gathered totals on the
-            # device; multinomial draws are independent, so there it walks all global slots and keeps those landing in
-            # this rank's span of the global CDF.  No host read-back before the launch: one synchronisation per step.
-            f.enqueue_resample_push_device(plan.opts, self._totals.data_ptr(), self.rank, self.world, self.shard, self.pivot)
-            f.enqueue_reduce_moments()
-            dist.all_reduce(results[0:9], op=dist.ReduceOp.SUM, group=self.group)  # also the barrier: all peer stores are done
-            f.enqueue_flip_adopt(self.shard)
-            self._packed[0:9] = results[0:9]
-            self._packed[9:] = self._totals.view(torch.float64)
-            packed = self._packed.cpu()  # the synchronisation of the step
-            moments = packed[0:9].numpy()
-            host = packed[9:].view(torch.int64).tolist()
-        else:
-            host = self._totals.cpu().tolist()  # synchronisation 1
-            offsets = cdf_offsets(host[: self.world])
-            stride, comb = _systematic_comb(self.params.seed, plan.step, offsets[-1], self.total)
-            ranges = slot_ranges(offsets, stride, comb, self.total)
-            self._redistribute(plan, ranges, offsets[-1], offsets[self.rank], streamed=True)
-            f.enqueue_moments(self.pivot)
-            dist.all_reduce(results[0:9], op=dist.ReduceOp.SUM, group=self.group)
-            moments = results[0:9].cpu().numpy()  # synchronisation 2
+        host = self._totals.cpu().tolist()  # synchronisation 1
+        offsets = cdf_offsets(host[: self.world])
+        stride, comb = _systematic_comb(self.params.seed, plan.step, offsets[-1], self.total)
+        ranges = slot_ranges(offsets, stride, comb, self.total)
+        self._redistribute(plan, ranges, offsets[-1], offsets[self.rank], streamed=True)
+        f.enqueue_moments(self.pivot)
+        dist.all_reduce(results[0:9], op=dist.ReduceOp.SUM, group=self.group)
+        moments = results[0:9].cpu().numpy()  # synchronisation 2
         exponent = int(np.int32(host[self.world] & 0xFFFFFFFF))
         global_total = cdf_offsets(host[: self.world])[-1]
         weight_sum = float(np.ldexp(float(global_total), -exponent))

@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--beams", type=int, default=1080)
     ap.add_argument("--grid", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-weak-line", action="store_true", help="N > 1: skip the extra weak-scaling measurement (--particles per GPU)")
     return ap.parse_args()
 
 
@@ -245,12 +246,11 @@ def run_native(args):
     torch.cuda.set_device(local_rank)
 
     scenario = make_workload(args)
-    n = args.particles
-    n_total = n * world
     lfm = bb.LikelihoodFieldModelParam(**LFM)
     grid = bb.OccupancyGrid(scenario.cells, scenario.resolution)
-    poses = [bb.se2(*scenario.poses[k % PATH_STEPS]) for k in range(args.warmup + args.steps + 1)]
-    scans = [np.ascontiguousarray(scenario.scans[k % PATH_STEPS]) for k in range(args.warmup + args.steps + 1)]
+    n_steps = args.warmup + args.steps
+    poses = [bb.se2(*scenario.poses[k % PATH_STEPS]) for k in range(n_steps + 1)]
+    scans = [np.ascontiguousarray(scenario.scans[k % PATH_STEPS]) for k in range(n_steps + 1)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > L2 (126 MB)
 
     def sync_all():
@@ -259,104 +259,131 @@ def run_native(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    if world == 1:
-        params = bb.AmclParams(min_particles=n, max_particles=n, resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=1, device=local_rank)
-        amcl = bb.Amcl(bb.DifferentialDriveModelParam(*MOTION), params)
-        filt = amcl.filter
+    def measure(n_total, with_clocks):
+        """K timed steps of ONE filter of n_total particles over `world` GPUs.  Device time: CUDA events on the filter's
+        own stream from the first kernel of the step to the read-back (exchanges and the waits inside them included);
+        end to end: host clock around the public update call.  Max over ranks."""
+        shard = n_total // world
+        if shard * world != n_total:
+            raise SystemExit(f"bench.py: {n_total} particles do not split into {world} equal shards")
+        if world == 1:
+            params = bb.AmclParams(min_particles=n_total, max_particles=n_total, resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=1, device=local_rank)
+            amcl = bb.Amcl(bb.DifferentialDriveModelParam(*MOTION), params)
+            filt = amcl.filter
 
-        def step(k):
-            r = amcl.update(poses[k], scans[k])  # synchronous: the estimate is read back inside
-            assert r.updated == 1 and r.resampled == 1
-            return np.array(r.estimate.mean)
-    else:
-        # ONE filter of world*n particles sharded over the ranks (weak scaling): per step an all_reduce(MAX) of the
-        # largest weight, an all_gather of the fixed-point totals, the all-to-all of resampled states, an all_reduce of moments.
-        from beluga_b200.distributed import ShardedAmcl
+            def step(k):
+                r = amcl.update(poses[k], scans[k])  # bb200_amcl_update: synchronous, the estimate is read back inside
+                assert r.updated == 1 and r.resampled == 1
+                return np.array(r.estimate.mean)
+        else:
+            # ONE filter sharded over the ranks.  Each rank calls bb200_amcl_update on its shard; the exchanges (largest
+            # weight, fixed-point totals, moments) and the redistribution of resampled states run over NVLink peer memory
+            # inside the library's kernels -- no NCCL call inside a step (torch.distributed only carried the IPC handles).
+            from beluga_b200.distributed import ShardedAmcl
 
-        params = bb.AmclParams(resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=1, device=local_rank)
-        amcl = ShardedAmcl(bb.DifferentialDriveModelParam(*MOTION), params, shard=n)
-        filt = amcl.filter
+            params = bb.AmclParams(resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=1, device=local_rank)
+            amcl = ShardedAmcl(bb.DifferentialDriveModelParam(*MOTION), params, shard=shard)
+            filt = amcl.filter
 
-        def step(k):
-            out = amcl.update(poses[k], scans[k])
-            assert out is not None and out[2]["resampled"]
-            return out[0]
+            def step(k):
+                out = amcl.update(poses[k], scans[k])
+                assert out is not None and out[2]["resampled"]
+                return out[0]
 
-    amcl.update_map(bb.SENSOR_LIKELIHOOD_FIELD, lfm, grid)
-    amcl.initialize(scenario.initial_mean, scenario.initial_cov)
-    filt.set_timing(True)
-    for k in range(args.warmup):
-        step(k)
-
-    launches0 = filt.launch_count()
-    device_ms, wall_ms, kernel_ms = [], [], {}
-    sync_all()
-    with ClockSampler(local_rank) as clocks:
-        for k in range(args.warmup, args.warmup + args.steps):
-            flush.zero_()  # evict L2 between timed steps
-            sync_all()
-            filt.clear_timings()
-            if world > 1:  # the sharded step runs on torch's current stream (kernels and NCCL collectives alike)
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
-            t0 = time.perf_counter()
-            mean = step(k)
-            if world > 1:
-                ev1.record()
-                torch.cuda.synchronize()
-            wall_ms.append((time.perf_counter() - t0) * 1e3)
-            step_kernels = filt.last_timings()
-            device_ms.append(ev0.elapsed_time(ev1) if world > 1 else sum(ms for _, ms in step_kernels))
-            per_step = {}
-            for name, ms in step_kernels:
-                per_step[name] = per_step.get(name, 0.0) + ms
-            for name, ms in per_step.items():
-                kernel_ms.setdefault(name, []).append(ms)
+        amcl.update_map(bb.SENSOR_LIKELIHOOD_FIELD, lfm, grid)
+        amcl.initialize(scenario.initial_mean, scenario.initial_cov)
+        filt.set_timing(True)
+        for k in range(args.warmup):
+            step(k)
+        launches0 = filt.launch_count()
+        device_ms, wall_ms, kernel_ms = [], [], {}
         sync_all()
-    launches = filt.launch_count() - launches0
 
-    # Device time from CUDA events on the stream the step runs on: N = 1 the filter's own events around its kernels,
-    # N > 1 one event pair around the whole sharded step (kernels + collectives + the waits between them); max over ranks.
-    # e2e: host clock around the same public call (scan upload and estimate read-back inside).
-    totals = torch.tensor([sum(device_ms), sum(wall_ms)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(totals, op=dist.ReduceOp.MAX)
-    dev_total_ms, wall_total_ms = totals.tolist()
+        def timed_loop():
+            mean = None
+            for k in range(args.warmup, args.warmup + args.steps):
+                flush.zero_()  # evict L2 between timed steps
+                sync_all()
+                filt.clear_timings()
+                t0 = time.perf_counter()
+                mean = step(k)
+                wall_ms.append((time.perf_counter() - t0) * 1e3)
+                per_step = {}
+                for name, ms in filt.last_timings():
+                    per_step[name] = per_step.get(name, 0.0) + ms
+                device_ms.append(sum(per_step.values()))
+                for name, ms in per_step.items():
+                    kernel_ms.setdefault(name, []).append(ms)
+            sync_all()
+            return mean
 
-    if rank == 0:
+        if with_clocks:
+            with ClockSampler(local_rank) as clocks:
+                mean = timed_loop()
+            clock_summary = clocks.summary()
+        else:
+            mean = timed_loop()
+            clock_summary = None
+        launches = filt.launch_count() - launches0
+        totals = torch.tensor([sum(device_ms), sum(wall_ms)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(totals, op=dist.ReduceOp.MAX)
+        dev_total_ms, wall_total_ms = totals.tolist()
         last = (args.warmup + args.steps - 1) % PATH_STEPS
         err = float(np.hypot(mean[2] - scenario.poses[last][0], mean[3] - scenario.poses[last][1]))
-        value = args.steps / (dev_total_ms * 1e-3)
-        e2e = args.steps / (wall_total_ms * 1e-3)
+        if world > 1:
+            amcl.close()
+        del amcl
+        return {"n_total": n_total, "shard": shard, "dev_ms": dev_total_ms / args.steps, "wall_ms": wall_total_ms / args.steps,
+                "kernels_ms": {name: float(np.mean(v)) for name, v in kernel_ms.items()}, "launches": int(launches), "clocks": clock_summary,
+                "final_position_error_m": err}
+
+    n_total = reference_particles(args)
+    m = measure(n_total, with_clocks=True)
+    weak = None
+    if world > 1 and not args.weak and not args.no_weak_line:
+        weak = measure(args.particles * world, with_clocks=False)  # the same run at --particles PER GPU
+
+    if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        k1 = float(np.mean(kernel_ms["reweight_lfm"]))
         g = args.grid * args.grid
+        shard = m["shard"]
+        k1 = m["kernels_ms"]["reweight_lfm"]
         # SURVEY 8(d) per-unit figures for the reweight launch: 32 B state read + 8 B weight read + 8 B weight write
         # per particle, one 4-byte field value per beam lookup, the field once.
-        k1_bytes = n * (48 + 4 * args.beams) + 4 * g
+        k1_bytes = shard * (48 + 4 * args.beams) + 4 * g
         step_bytes = n_total * (216 + 4 * args.beams) + 4 * g * world
         achieved = k1_bytes / (k1 * 1e-3) / 1e9
+        value = 1e3 / m["dev_ms"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": m["dev_ms"], "higher_is_better": True, "scaling": "weak" if args.weak else SCALING, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(args, n_total), "particles_per_gpu": n, "parallelism": f"shard{world}",
+            "config": {"workload": workload_name(args, n_total), "particles": n_total, "particles_per_gpu": shard, "parallelism": f"shard{world}",
                        "l2": "256 MiB device write between timed steps (flushes the 126 MB L2)",
-                       "timing": ("CUDA events on the filter stream around the fused step" if world == 1 else
-                                  "host clock between cuda synchronize + barrier, per step, max over ranks (collectives are host-driven)"),
-                       "final_position_error_m": err},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(scans[0].nbytes + 32), "d2h_bytes_per_step": int(9 * 8 + 128),
-                    "ms_per_step": wall_total_ms / args.steps},
-            "gpu_launches": int(launches),
+                       "timing": "CUDA events on the filter's stream, first kernel of the step to the read-back (shard exchanges and their waits "
+                                 "included), per step, max over ranks",
+                       "exchange": "none (one GPU)" if world == 1 else "peer-memory mail blocks + peer stores inside the library's kernels (no NCCL in the step)",
+                       "final_position_error_m": m["final_position_error_m"]},
+            "e2e": {"value": 1e3 / m["wall_ms"], "unit": UNIT, "h2d_bytes_per_step": int(scans[0].nbytes + 32), "d2h_bytes_per_step": int(9 * 8 + 128),
+                    "ms_per_step": m["wall_ms"]},
+            "gpu_launches": m["launches"],
             "roofline": {"bound": "hbm", "kernel": "reweight_lfm_fixed_param_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
-                         "kernel_ms": k1, "kernel_share_of_step": k1 / (dev_total_ms / args.steps),
-                         "step_achieved_gbs": step_bytes / (dev_total_ms / args.steps * 1e-3) / 1e9,
+                         "kernel_ms": k1, "kernel_share_of_step": k1 / m["dev_ms"],
+                         "step_achieved_gbs": step_bytes / (m["dev_ms"] * 1e-3) / 1e9,
                          "note": "the lookups are served by L1/L2 (the field is L2 resident, DRAM traffic = `traffic`); the kernel is bound by "
-                                 "instruction issue (71 %), the L1 data pipe (69 %) and the latency of the gather, see profiles/ and DESIGN.md"},
-            "kernels_ms": {name: float(np.mean(v)) for name, v in kernel_ms.items()},
-            "clocks": clocks.summary(),
+                                 "instruction issue, the L1 data pipe and the latency of the gather, see profiles/ and DESIGN.md"},
+            "kernels_ms": m["kernels_ms"],
+            "clocks": m["clocks"],
         }
+        if weak is not None:
+            wk1 = weak["kernels_ms"]["reweight_lfm"]
+            wbytes = weak["shard"] * (48 + 4 * args.beams) + 4 * g
+            line["weak"] = {"particles": weak["n_total"], "particles_per_gpu": weak["shard"], "steps_per_s": 1e3 / weak["dev_ms"],
+                            "ms_per_step": weak["dev_ms"], "particle_steps_per_s": weak["n_total"] * 1e3 / weak["dev_ms"],
+                            "e2e_ms_per_step": weak["wall_ms"], "kernels_ms": weak["kernels_ms"],
+                            "roofline_frac": wbytes / (wk1 * 1e-3) / 1e9 / peak, "final_position_error_m": weak["final_position_error_m"]}
         if not args.no_cpu_baseline and world == 1:  # timed beside the GPU arm on rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_reference_steps_per_s(args, scenario, n_total, steps=5)
         print(json.dumps(line), flush=True)

@@ -357,6 +357,9 @@ typedef struct bb200_amcl_param {
    * shard_capacity particles starting at global index shard_first_index. */
   uint64_t shard_first_index;
   uint64_t shard_capacity;
+  /* > 0: views::random_intersperse runs with this probability on every resample instead of the recovery
+   * estimator's output (which is identically 0 while the particle count is constant); 0: the estimator. */
+  double recovery_probability_override;
 } bb200_amcl_param;
 
 /* What Amcl::update decided on the host for this step (policies, control window, recovery
@@ -421,6 +424,54 @@ int bb200_scan_to_points(const bb200_laser_scan* scan, double* points_xy, uint64
 int bb200_take_evenly_indices(uint64_t size, uint64_t count, uint64_t* indices, uint64_t capacity, uint64_t* n_indices);
 /* Amcl::update(base_pose_in_odom, laser_scan) -- beluga_ros/src/amcl.cpp:54-64. */
 int bb200_amcl_update_scan(bb200_amcl* a, const double control_pose[4], const bb200_laser_scan* scan, bb200_update_result* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * One filter over several GPUs.  Particles are split into equal contiguous global index
+ * ranges ("shards"); map and scan are replicated; the counter RNG is keyed by the GLOBAL particle /
+ * slot index and the CDF is an integer prefix sum, so the particle set does not depend on the number
+ * of shards.  The three exchanges of a step (largest weight, fixed-point totals, raw moments) and the
+ * post-resample redistribution all go through peer memory from inside the library's own kernels:
+ * no NCCL, no host round trip, one host synchronisation per step.
+ *
+ * (1) One process, several devices (or several shards on one device): bb200_sharded_amcl -- the shape
+ *     of beluga_ros::Amcl (one node, one thread calling update; beluga_ros/src/amcl.cpp:83-126).
+ * (2) One process per GPU (torchrun, MPI): every rank creates a bb200_amcl with shard_first_index /
+ *     shard_capacity set, exports 192 bytes of CUDA IPC handles (bb200_amcl_export_shard), gathers
+ *     the handles of all ranks by whatever transport it has, maps them (bb200_amcl_join_shards) and
+ *     from then on calls bb200_amcl_update in lock step with its peers.
+ * Policies: every_n resampling and selective resampling (on_effective_size_drop), systematic or
+ * multinomial, recovery injection; min_particles must equal max_particles.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bb200_sharded_amcl bb200_sharded_amcl;
+/* p->max_particles is the GLOBAL particle count (a multiple of n_shards); devices[r] is the CUDA ordinal of
+ * shard r (ordinals may repeat: several shards on one device). */
+int bb200_sharded_amcl_create(const bb200_amcl_param* p, const bb200_motion_param* motion, int n_shards, const int* devices,
+                              bb200_sharded_amcl** out);
+void bb200_sharded_amcl_destroy(bb200_sharded_amcl* g);
+const char* bb200_sharded_amcl_last_error(const bb200_sharded_amcl* g);
+int bb200_sharded_amcl_shards(const bb200_sharded_amcl* g);
+/* Shard r as a bb200_amcl (not owned by the caller): timings, per-shard particles, bb200_amcl_filter. */
+bb200_amcl* bb200_sharded_amcl_shard(bb200_sharded_amcl* g, int rank);
+int bb200_sharded_amcl_set_likelihood_field_map(bb200_sharded_amcl* g, const bb200_likelihood_field_param* p, const bb200_occupancy_grid* grid, int prob);
+int bb200_sharded_amcl_set_beam_map(bb200_sharded_amcl* g, const bb200_beam_param* p, const bb200_occupancy_grid* grid);
+int bb200_sharded_amcl_initialize(bb200_sharded_amcl* g, const double mean_xytheta[3], const double cov[9]);
+int bb200_sharded_amcl_initialize_from_map(bb200_sharded_amcl* g);
+void bb200_sharded_amcl_force_update(bb200_sharded_amcl* g);
+/* Amcl::update (amcl_core.hpp:165-201) over all shards. */
+int bb200_sharded_amcl_update(bb200_sharded_amcl* g, const double control_pose[4], const double* points_xy, uint64_t n_points,
+                              bb200_update_result* out);
+/* particles() in global index order (rank 0's shard first). */
+int bb200_sharded_amcl_get_particles(bb200_sharded_amcl* g, double* states, double* weights, uint64_t capacity);
+/* One process per GPU: CUDA IPC handles of this shard's two state buffers and mail block (192 bytes) ... */
+int bb200_amcl_export_shard(bb200_amcl* a, void* out192);
+/* ... and the mapping of all ranks' handles (world x 192 bytes, rank order).  shard_capacity * world must equal
+ * max_particles and shard_first_index must be rank * shard_capacity. */
+int bb200_amcl_join_shards(bb200_amcl* a, int world, int rank, const void* handles);
+/* Unmap the peers' buffers again.  CUDA IPC wants every importer to close before the exporter frees: call this on all
+ * ranks, synchronise the ranks (barrier), then destroy. */
+int bb200_amcl_leave_shards(bb200_amcl* a);
+int bb200_filter_export_shard(bb200_filter* f, void* out192);
+int bb200_filter_join_shards(bb200_filter* f, int world, int rank, const void* handles);
 
 /* The two host halves of bb200_amcl_update for callers that drive the filter themselves. */
 int bb200_amcl_plan_update(bb200_amcl* a, const double control_pose[4], bb200_step_plan* plan);

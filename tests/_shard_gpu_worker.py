@@ -31,7 +31,9 @@ def main():
     lfm = bb.LikelihoodFieldModelParam(max_obstacle_distance=2.0, max_laser_distance=100.0)
     grid = bb.OccupancyGrid(sc.cells, sc.resolution)
 
-    sharded = ShardedAmcl(motion, bb.AmclParams(resample_scheme=scheme, seed=21, device=local_rank), shard=shard, p2p=p2p)
+    override = inject if (p2p and inject is not None) else 0.0  # the peer-memory path takes the injection probability as a parameter
+    sharded = ShardedAmcl(motion, bb.AmclParams(resample_scheme=scheme, seed=21, device=local_rank, recovery_probability_override=override),
+                          shard=shard, p2p=p2p)
     sharded.update_map(bb.SENSOR_LIKELIHOOD_FIELD, lfm, grid)
     sharded.initialize(sc.initial_mean, sc.initial_cov)
     single = None
@@ -42,7 +44,7 @@ def main():
 
     for k in range(steps):
         pose = bb.se2(*sc.poses[k])
-        out = sharded.update(pose, sc.scans[k], random_state_probability=inject)
+        out = sharded.update(pose, sc.scans[k], random_state_probability=None if p2p else inject)
         assert out is not None
         mean, cov, info = out
         # gather the sharded particle set on rank 0
@@ -69,6 +71,7 @@ def main():
             assert info["weight_sum"] == ref_sum
             assert np.abs(mean - ref_mean).max() < 1e-12
             assert np.abs(cov - ref_cov).max() < 1e-12
+    sharded.close()
     dist.barrier()
     if rank == 0:
         print("SHARD_GPU_WORKER_OK")
