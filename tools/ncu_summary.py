@@ -36,5 +36,60 @@ def main(path, title=""):
                 print(f"  {k:85s} {r[hdr.index(k)]:>18s} {units[hdr.index(k)]}")
 
 
+def table(path):
+    """One line per kernel: duration, DRAM bytes and achieved GB/s, the busiest units, the top stall; then a JSON list."""
+    import json
+
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr = rows[0]
+    col = {k: hdr.index(k) for k in hdr}
+
+    def num(r, k):
+        try:
+            return float(r[col[k]].replace(",", ""))
+        except Exception:
+            return float("nan")
+
+    stalls = [k for k in hdr if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")]
+    peak = 6567.1
+    try:
+        import os
+        peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    recs = []
+    print(f"# {path}: one launch per kernel, ncu --set full --clock-control none; HBM peak {peak} GB/s (MEASURED_PEAKS.json)")
+    print(f"{'kernel':44s} {'us':>9s} {'dramMB':>9s} {'GB/s':>7s} {'%peak':>6s} {'dram%':>6s} {'l1tex%':>6s} {'lts%':>6s} {'issue%':>6s} {'fp64%':>6s} {'occ%':>5s} {'regs':>4s}  top stall")
+    for r in rows[2:]:
+        name = r[col["Kernel Name"]].split("(")[0]
+        dur_us = num(r, "gpu__time_duration.sum") / 1e3  # ns in the raw page
+        dram = num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum")
+        unit = rows[1][col["dram__bytes_read.sum"]]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+        dram *= scale
+        tunit = rows[1][col["gpu__time_duration.sum"]]
+        dur_us = num(r, "gpu__time_duration.sum") * {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}.get(tunit, 1e-3)
+        gbs = dram / (dur_us * 1e-6) / 1e9 if dur_us > 0 else float("nan")
+        top = max(stalls, key=lambda k: num(r, k) if num(r, k) == num(r, k) else -1.0) if stalls else ""
+        rec = {"kernel": name, "us": dur_us, "dram_bytes": dram, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak,
+               "dram_pct": num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+               "l1tex_pct": num(r, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+               "lts_pct": num(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+               "issue_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "fp64_pct": num(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+               "warps_active_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+               "registers": num(r, "launch__registers_per_thread"), "grid": num(r, "launch__grid_size"), "block": num(r, "launch__block_size"),
+               "top_stall": top.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""),
+               "top_stall_ratio": num(r, top) if top else float("nan"), "instructions": num(r, "smsp__inst_executed.sum")}
+        recs.append(rec)
+        print(f"{name[:44]:44s} {dur_us:9.1f} {dram / 1e6:9.2f} {gbs:7.0f} {100 * gbs / peak:6.1f} {rec['dram_pct']:6.1f} {rec['l1tex_pct']:6.1f} {rec['lts_pct']:6.1f} "
+              f"{rec['issue_pct']:6.1f} {rec['fp64_pct']:6.1f} {rec['warps_active_pct']:5.1f} {int(rec['registers']):4d}  {rec['top_stall']} ({rec['top_stall_ratio']:.1f})")
+    print("JSON " + json.dumps(recs))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1], " ".join(sys.argv[2:]))
+    if sys.argv[1] == "--table":
+        table(sys.argv[2])
+    else:
+        main(sys.argv[1], " ".join(sys.argv[2:]))
