@@ -111,6 +111,7 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   if (const char* v = std::getenv("BB200_PARAM_POINTS")) param_points_ = std::atoi(v) != 0;  // development knob: scan as kernel parameters
   if (const char* v = std::getenv("BB200_BEAM_ETA_TABLE")) beam_eta_table_ = std::atoi(v) != 0;  // development knob: tabulated beam normalisers
   if (const char* v = std::getenv("BB200_FIXED")) fixed_lookup_ = std::atoi(v) != 0;         // development knob: fixed-point lookup kernel
+  if (const char* v = std::getenv("BB200_PREDICT_SCHEDULE")) predict_schedule_ = std::atoi(v) != 0;  // development knob: host-predicted pose bins
   if (const char* v = std::getenv("BB200_PER_BIN")) schedule_per_bin_ = std::atof(v);        // development knob: particles per pose bin
   if (const char* v = std::getenv("BB200_LEVER")) schedule_lever_ = std::atof(v);            // development knob: heading lever arm / mean range
   capacity_ = config.capacity;
@@ -292,8 +293,9 @@ int Filter::enqueue_propagate_reweight(const bb200_motion_sampling* sampling, ui
   mark("begin_step");
   launch_begin_step(scalars_, stream_);
   BB_LAUNCHED("begin_step");
-  st = enqueue_propagate_reweight(sampling != nullptr ? &s : nullptr, step, true, n_points);
+  st = enqueue_propagate_reweight(sampling != nullptr ? &s : nullptr, step, true, n_points, false);
   cdf_valid_ = false;
+  cloud_known_ = false;
   return st;
 }
 
@@ -478,7 +480,7 @@ int Filter::enqueue_exchange(int kind, bool post, bool wait) {
   for (int r = 0; r < peer_world_; ++r) a.peers[r] = peer_mail_[r];
   a.scalars = scalars_;
   a.results = results_;
-  a.summary = summary_;
+  a.summary = summary_host_;  // pinned host memory: the step's results need no copy
   a.rank_totals = shard_totals_;
   a.ceil_log2_count = ceil_log2_count(config_.global_count);
   a.tile_state = tile_state_;
@@ -505,6 +507,7 @@ int Filter::step_begin(const bb200_motion_sampling& sampling, uint32_t step, con
   if (st != BB200_OK) return st;
   if (world > 1 && peer_mail_[0] == nullptr) return fail(BB200_ERR_STATE, "shards joined without mail blocks (legacy open_peers): use join_shards");
   step_ = StepContext{};
+  summary_host_->error = 0;
   step_.active = true;
   step_.sampling = to_kernel_sampling(sampling);
   step_.step = step;
@@ -524,9 +527,13 @@ int Filter::step_phase(int phase) {
   switch (phase) {
     case kPhaseReweight: {
       mark("begin_step");
-      launch_begin_step(scalars_, stream_);
-      BB_LAUNCHED("begin_step");
-      st = enqueue_propagate_reweight(&step_.sampling, step_.step, true, step_.n_points);
+      {
+        const bool scheduled = schedule_enabled_ && n_ >= kScheduleMinParticles;
+        launch_begin_fused_step(scalars_, tile_state_, scan_tile_count(n_), sched_, scheduled ? counters_ : nullptr, schedule_max_bins(), sched_tiles_,
+                                schedule_tile_count(), stream_);
+        BB_LAUNCHED("begin_step");
+        st = enqueue_propagate_reweight(&step_.sampling, step_.step, true, step_.n_points, scheduled);
+      }
       if (st != BB200_OK) return st;
       if (sharded) {
         ++epoch_;  // one sequence number per batch of exchanges
@@ -542,13 +549,11 @@ int Filter::step_phase(int phase) {
         mark("exchange");
         st = enqueue_exchange(kExchangeWmax, !split_posts_, true);  // global largest weight -> exponent; resets the scan state
         if (st != BB200_OK) return st;
-      } else {
-        mark("prepare_cdf");
-        launch_prepare_cdf(scalars_, -1.0, config_.global_count, tile_state_, scan_tile_count(n_), stream_);
-        BB_LAUNCHED("prepare_cdf");
       }
       mark("quantize_scan");
-      launch_quantize_scan(weights_, n_, cdf_, scalars_, tile_state_, stream_);
+      // one GPU: the exponent comes from the shard's own largest weight inside the kernel (scan state reset by begin_step);
+      // sharded: the exchange above has set the common exponent and reset the scan state
+      launch_quantize_scan(weights_, n_, cdf_, scalars_, tile_state_, stream_, !sharded, config_.global_count);
       BB_LAUNCHED("quantize_scan");
       if (sharded) {
         if (split_posts_) {
@@ -592,13 +597,10 @@ int Filter::step_phase(int phase) {
         a = make_resample_args(o, 0, o.max_particles, false);
         mark("resample");
       }
-      launch_resample(a, scalars_, partials_, stream_);
+      a.tail = StepTail{1, results_, sharded ? nullptr : summary_host_};  // the last block sums the moments (one GPU: straight into pinned host memory)
+      step_.partial_rows = launch_resample(a, scalars_, partials_, stream_);
       BB_LAUNCHED("resample");
       step_.resampled = true;
-      step_.partial_rows = resample_block_count(a.slot_count);
-      mark("reduce_partials");
-      launch_reduce_partials(partials_, step_.partial_rows, kMomentCount, results_, stream_);
-      BB_LAUNCHED("reduce_partials");
       if (sharded && split_posts_) {
         mark("exchange");
         st = enqueue_exchange(kExchangeMoments, true, false);
@@ -610,12 +612,10 @@ int Filter::step_phase(int phase) {
         mark("exchange");
         st = enqueue_exchange(kExchangeMoments, !split_posts_, true);  // also the barrier: the peers' stores into this rank's buffer are complete
         if (st != BB200_OK) return st;
+      } else if (!step_.resampled) {  // kPhaseNormalize left the moments in results_: hand them to the host block
         mark("readback");
-        BB_CHECK(cudaMemcpyAsync(summary_host_, summary_, sizeof(StepSummary), cudaMemcpyDeviceToHost, stream_));
-      } else {
-        mark("readback");
-        BB_CHECK(cudaMemcpyAsync(results_host_, results_, kMomentCount * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-        BB_CHECK(cudaMemcpyAsync(scalars_host_, scalars_, sizeof(Scalars), cudaMemcpyDeviceToHost, stream_));
+        launch_write_summary(results_, scalars_, summary_host_, stream_);
+        BB_LAUNCHED("write_summary");
       }
       mark("end");
       return BB200_OK;
@@ -655,21 +655,14 @@ int Filter::step_end(bb200_estimate* est, double* weight_sum, uint64_t* new_size
   BB_CHECK(cudaStreamSynchronize(stream_));
   finish_marks();
   const bool sharded = peer_world_ > 1;
-  const double* moments = results_host_;
-  if (sharded) {
-    if (summary_host_->error != 0) {
-      step_.active = false;
-      return fail(BB200_ERR_STATE, "shard exchange timed out: a peer rank never posted its value for this step");
-    }
-    moments = summary_host_->moments;
-    step_.total = summary_host_->total;
-    step_.exponent = summary_host_->exponent;
-    weights_valid_ = summary_host_->valid != 0;
-  } else {
-    step_.total = scalars_host_->total;
-    step_.exponent = scalars_host_->exponent;
-    weights_valid_ = scalars_host_->valid != 0;
+  if (summary_host_->error != 0) {
+    step_.active = false;
+    return fail(BB200_ERR_STATE, "shard exchange timed out: a peer rank never posted its value for this step");
   }
+  const double* moments = summary_host_->moments;
+  step_.total = summary_host_->total;
+  step_.exponent = summary_host_->exponent;
+  weights_valid_ = summary_host_->valid != 0;
   if (step_.resampled) {
     cur_ ^= 1;
     n_ = sharded ? capacity_ : step_.opts.max_particles;
@@ -684,11 +677,13 @@ int Filter::step_end(bb200_estimate* est, double* weight_sum, uint64_t* new_size
   if (weight_sum != nullptr) *weight_sum = std::ldexp(static_cast<double>(step_.total), -step_.exponent);
   if (sum_sq != nullptr) *sum_sq = moments[1];
   if (!weights_valid_) error_ = "no positive finite weight (uniform CDF substituted)";
-  if (est != nullptr) {
-    estimate_from_moments(moments, est);
-    pivot_[0] = est->mean[2];
-    pivot_[1] = est->mean[3];
-  }
+  bb200_estimate local{};
+  if (est == nullptr) est = &local;
+  estimate_from_moments(moments, est);
+  pivot_[0] = est->mean[2];
+  pivot_[1] = est->mean[3];
+  cloud_ = *est;
+  cloud_known_ = step_.resampled;  // unit weights: the estimate describes the raw cloud, the next step can predict its pose bins
   return BB200_OK;
 }
 
@@ -719,9 +714,8 @@ int Filter::enqueue_resample_push(const bb200_resample_opts& o, uint64_t global_
   for (int r = 0; r < peer_world_; ++r) a.peer_out[r] = peer_states_[cur_ ^ 1][r];
   mark("resample_push");
   // slot_count may be 0 (a shard without weight): the kernel still writes its (zero) moment partials.
-  launch_resample(a, scalars_, partials_, stream_);
+  pushed_blocks_ = launch_resample(a, scalars_, partials_, stream_);
   BB_LAUNCHED("resample_push");
-  pushed_blocks_ = resample_block_count(a.slot_count);
   return BB200_OK;
 }
 
@@ -754,9 +748,8 @@ int Filter::enqueue_resample_push_device(const bb200_resample_opts& o, const uin
   }
   for (int r = 0; r < peer_world_; ++r) a.peer_out[r] = peer_states_[cur_ ^ 1][r];
   mark("resample_push");
-  launch_resample(a, scalars_, partials_, stream_);  // a.slot_count only sizes the grid here
+  pushed_blocks_ = launch_resample(a, scalars_, partials_, stream_);  // a.slot_count only sizes the grid here
   BB_LAUNCHED("resample_push");
-  pushed_blocks_ = resample_block_count(a.slot_count);
   return BB200_OK;
 }
 
@@ -774,6 +767,7 @@ int Filter::enqueue_flip_adopt(uint64_t n) {
 
 int Filter::enqueue_adopt(uint64_t n) {
   if (n > capacity_) return fail(BB200_ERR_CAPACITY, "more particles than the filter capacity");
+  cloud_known_ = false;
   BB_CHECK(cudaSetDevice(config_.device));
   n_ = n;
   cdf_valid_ = false;
@@ -973,6 +967,7 @@ int Filter::set_particles(const double* states, const double* weights, uint64_t 
   }
   n_ = n;
   cdf_valid_ = false;
+  cloud_known_ = false;
   if (n > 0) {  // the covariance is accumulated about the pivot: keep it inside the cloud (no cancellation for far-away sets)
     pivot_[0] = states[2];
     pivot_[1] = states[3];
@@ -1002,6 +997,11 @@ int Filter::initialize_normal(const double mean[3], const double cov[9], uint64_
   cdf_valid_ = false;
   pivot_[0] = mean[0];
   pivot_[1] = mean[1];
+  {  // the cloud just drawn is N(mean, cov): the first step can predict its pose bins
+    const Pose2 m = pose_from_xytheta(mean[0], mean[1], mean[2]);
+    cloud_ = bb200_estimate{{m.c, m.s, m.x, m.y}, {cov[0], cov[1], cov[2], cov[3], cov[4], cov[5], cov[6], cov[7], cov[8]}};
+    cloud_known_ = true;
+  }
   return BB200_OK;
 }
 
@@ -1016,6 +1016,7 @@ int Filter::initialize_uniform(uint64_t n) {
   BB_CHECK(cudaStreamSynchronize(stream_));
   n_ = n;
   cdf_valid_ = false;
+  cloud_known_ = false;
   // pivot of the raw moments: the middle of the map in the global frame
   const double cx = 0.5 * grid_width_ * grid_resolution_, cy = 0.5 * grid_height_ * grid_resolution_;
   pivot_[0] = (grid_origin_.c * cx - grid_origin_.s * cy) + grid_origin_.x;
@@ -1054,16 +1055,45 @@ int Filter::upload_points(const double* points_xy, uint64_t n_points) {
   return BB200_OK;
 }
 
-int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t step, bool do_reweight, uint64_t n_points) {
+bool Filter::predict_schedule(const MotionSampling& s, Schedule* grid) const {
+  // The cloud after this step's propagate, from what the host already knows: the last estimate (the particles carry unit
+  // weights, so it describes the raw cloud) composed with the motion means, spread widened by the motion noise.
+  if (!cloud_known_ || !predict_schedule_) return false;
+  const bb200_estimate& e = cloud_;
+  const Pose2 mean = motion_apply(s.model, Pose2{e.mean[0], e.mean[1], e.mean[2], e.mean[3]}, s.mean[0], s.mean[1], s.mean[2], Rot2{s.first_c, s.first_s});
+  double var_theta = std::max(e.cov[8], 0.0) + s.stddev[0] * s.stddev[0];
+  double spread = s.stddev[1] * s.stddev[1];
+  if (s.model == BB200_MOTION_DIFFERENTIAL) var_theta += s.stddev[2] * s.stddev[2];
+  if (s.model != BB200_MOTION_DIFFERENTIAL) spread += s.stddev[2] * s.stddev[2];
+  if (s.model != BB200_MOTION_STATIONARY) spread += s.mean[1] * s.mean[1] * var_theta;
+  const double vx = e.cov[0] + spread, vy = e.cov[4] + spread;
+  if (!std::isfinite(var_theta) || !std::isfinite(vx) || !std::isfinite(vy) || !std::isfinite(mean.x) || !std::isfinite(mean.y)) return false;
+  const double r = std::exp(-0.5 * var_theta);
+  schedule_from_moments(*grid, r * mean.c, r * mean.s, mean.x, mean.y, vx, vy, static_cast<double>(n_), schedule_lever_ * points_mean_range_,
+                        0.5 * grid_resolution_, schedule_per_bin_);
+  return true;
+}
+
+int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t step, bool do_reweight, uint64_t n_points, bool counters_reset) {
   const bool scheduled = do_reweight && schedule_enabled_ && n_ >= kScheduleMinParticles;
-  if (sampling != nullptr || scheduled) {
+  Schedule grid{};
+  const uint32_t* perm = nullptr;
+  if (scheduled && counters_reset && sampling != nullptr && predict_schedule(*sampling, &grid)) {
+    // Bin grid predicted on the host: propagate histograms its own output, two more launches turn it into the order.
+    mark("propagate");
+    launch_propagate_binned(states_[cur_], n_, *sampling, config_.seed, step, config_.first_index, grid, bins_, counters_, stream_);
+    BB_LAUNCHED("propagate");
+    mark("schedule");
+    launch_finish_schedule(bins_, n_, grid.n_bins, sched_, counters_, perm_, sched_tiles_, stream_);
+    BB_LAUNCHED_N("schedule", 2);
+    perm = perm_;
+  } else if (sampling != nullptr || scheduled) {
     mark("propagate");
     launch_propagate(states_[cur_], n_, sampling != nullptr, sampling != nullptr ? *sampling : MotionSampling{}, config_.seed, step,
                      config_.first_index, scheduled ? sched_ : nullptr, stream_);
     BB_LAUNCHED_N("propagate", scheduled ? 2 : 1);
   }
-  const uint32_t* perm = nullptr;
-  if (scheduled) {
+  if (scheduled && perm == nullptr) {
     mark("schedule");
     launch_build_schedule(states_[cur_], n_, sched_, bins_, counters_, perm_, sched_tiles_, schedule_lever_ * points_mean_range_, 0.5 * grid_resolution_, schedule_per_bin_, stream_);
     BB_LAUNCHED_N("schedule", 4);
@@ -1100,9 +1130,10 @@ int Filter::propagate_reweight(const bb200_motion_sampling* sampling, uint32_t s
   mark("begin_step");
   launch_begin_step(scalars_, stream_);
   BB_LAUNCHED("begin_step");
-  const int st = enqueue_propagate_reweight(sampling != nullptr ? &s : nullptr, step, do_reweight, n_points);
+  const int st = enqueue_propagate_reweight(sampling != nullptr ? &s : nullptr, step, do_reweight, n_points, false);
   if (st != BB200_OK) return st;
   cdf_valid_ = false;
+  cloud_known_ = false;
   finish_marks();
   return BB200_OK;
 }
@@ -1367,6 +1398,7 @@ int Filter::resample(const bb200_resample_opts& o, uint64_t* new_size) {
   }
   finish_marks();
   cur_ ^= 1;
+  cloud_known_ = false;
   n_ = m;
   ancestors_n_ = n_;
   cdf_valid_ = false;
@@ -1404,6 +1436,7 @@ int Filter::adopt(uint64_t n, int from_staging) {
   if (n > capacity_) return fail(BB200_ERR_CAPACITY, "more particles than the filter capacity");
   BB_CHECK(cudaSetDevice(config_.device));
   if (from_staging) cur_ ^= 1;
+  cloud_known_ = false;
   n_ = n;
   cdf_valid_ = false;
   if (n > 0) {

@@ -124,7 +124,8 @@ class Filter {
   int fail(int status, const std::string& message);
   int check(cudaError_t e, const char* what);
   int upload_points(const double* points_xy, uint64_t n_points);
-  int enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t step, bool do_reweight, uint64_t n_points);
+  int enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t step, bool do_reweight, uint64_t n_points, bool counters_reset);
+  bool predict_schedule(const MotionSampling& s, Schedule* grid) const;
   int ensure_cdf_ready();
   int resample_kld(const bb200_resample_opts& o, uint64_t* accepted);
   ResampleArgs make_resample_args(const bb200_resample_opts& o, uint64_t slot_begin, uint64_t slot_end, bool with_hashes) const;
@@ -242,6 +243,9 @@ class Filter {
   Pose2 grid_origin_{1.0, 0.0, 0.0, 0.0};
 
   double pivot_[2]{0.0, 0.0};
+  bb200_estimate cloud_{};     // last estimate, when it describes the raw (unit-weight) cloud
+  bool cloud_known_{false};
+  bool predict_schedule_{true};
 
   // timing
   bool timing_{false};

@@ -161,6 +161,47 @@ __global__ void begin_step_kernel(Scalars* s) {
   s->kld_cutoff = ~0ull;
   s->work_ticket = 0;  // normally rewound by the persistent reweight kernel itself; a step starts clean regardless
   s->work_done = 0;
+  s->blocks_done = 0;
+}
+
+/// The fused step's reset: the scalars above plus the scan state of the CDF build and -- when the execution schedule
+/// is rebuilt this step -- the bin counters, the schedule's scan state and its moment sums.  One launch instead of a
+/// scalar kernel, two memsets and a reset kernel.
+struct StepReset {
+  Scalars* scalars;
+  unsigned long long* tile_state;
+  uint32_t n_tiles;
+  Schedule* sched;             // nullable
+  uint32_t* counters;          // nullable
+  uint32_t n_counters;
+  unsigned long long* sched_tiles;
+  uint32_t n_sched_tiles;
+};
+
+__global__ void __launch_bounds__(256) begin_fused_step_kernel(StepReset r) {
+  const uint32_t t = blockIdx.x * 256 + threadIdx.x, stride = gridDim.x * 256;
+  if (t == 0) {
+    Scalars* s = r.scalars;
+    s->wmax_bits = 0;
+    s->tile_ticket = 0;
+    s->total = 0;
+    s->exponent = 0;
+    s->valid = 0;
+    s->kld_cutoff = ~0ull;
+    s->work_ticket = 0;
+    s->work_done = 0;
+    s->blocks_done = 0;
+    if (r.sched != nullptr) {
+      for (int k = 0; k < 6; ++k) r.sched->sums[k] = 0.0;
+      r.sched->tile_ticket = 0;
+    }
+  }
+  for (uint32_t k = t; k < r.n_tiles; k += stride) r.tile_state[k] = 0;
+  if (r.counters != nullptr) {
+    uint4* c4 = reinterpret_cast<uint4*>(r.counters);  // cudaMalloc alignment; n_counters is a multiple of 4
+    for (uint32_t k = t; k < r.n_counters / 4; k += stride) c4[k] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t k = t; k < r.n_sched_tiles; k += stride) r.sched_tiles[k] = 0;
+  }
 }
 
 // ---- initialize_normal (a16) ---------------------------------------------------------------------
@@ -265,7 +306,7 @@ __global__ void __launch_bounds__(kPrThreads) propagate_kernel(Pose2* __restrict
 // of a counting sort over a 3-D grid of pose bins.  This only permutes WHICH THREAD handles a
 // particle: weights are written back to the particle's own slot, so every result is independent of it.
 
-constexpr uint32_t kMaxBins = 1u << 18;  // 16 particles per bin up to 4M particles per shard
+constexpr uint32_t kMaxBins = kScheduleMaxBins;
 
 __global__ void schedule_reset_kernel(Schedule* sched) {
   for (int k = 0; k < 6; ++k) sched->sums[k] = 0.0;
@@ -274,45 +315,32 @@ __global__ void schedule_reset_kernel(Schedule* sched) {
 
 __global__ void schedule_params_kernel(Schedule* sched, uint64_t n, double mean_range, double min_bin, double per_bin) {
   const double inv_n = 1.0 / static_cast<double>(n);
-  const double cbar = sched->sums[0] * inv_n, sbar = sched->sums[1] * inv_n;
   const double mx = sched->sums[2] * inv_n, my = sched->sums[3] * inv_n;
-  const double vx = fmax(sched->sums[4] * inv_n - mx * mx, 0.0), vy = fmax(sched->sums[5] * inv_n - my * my, 0.0);
-  const double r = hypot(cbar, sbar);
-  const double pi = 3.14159265358979323846;
-  double c0 = 1.0, s0 = 0.0, sigma_theta = pi;
-  if (r > 1e-9) {
-    c0 = cbar / r;
-    s0 = sbar / r;
-    sigma_theta = r < 1.0 ? sqrt(-2.0 * log(r)) : 0.0;
-  }
-  const double half_theta = fmin(pi, fmax(3.0 * sigma_theta, 1e-4));
-  const double half_x = fmax(3.0 * sqrt(vx), min_bin), half_y = fmax(3.0 * sqrt(vy), min_bin);
-  // Bins of equal physical edge q in (range * theta, x, y), about `per_bin` particles per bin.
-  const double ext_t = 2.0 * half_theta * fmax(mean_range, 1.0), ext_x = 2.0 * half_x, ext_y = 2.0 * half_y;
-  double q = cbrt(ext_t * ext_x * ext_y / fmax(static_cast<double>(n) / per_bin, 1.0));
-  q = fmax(q, min_bin);
-  uint32_t nt, nx, ny;
-  for (;;) {
-    nt = static_cast<uint32_t>(fmin(fmax(ceil(ext_t / q), 1.0), 65536.0));
-    nx = static_cast<uint32_t>(fmin(fmax(ceil(ext_x / q), 1.0), 65536.0));
-    ny = static_cast<uint32_t>(fmin(fmax(ceil(ext_y / q), 1.0), 65536.0));
-    if (static_cast<uint64_t>(nt) * nx * ny <= kMaxBins) break;
-    q = q * 1.3;
-  }
-  sched->c0 = c0, sched->s0 = s0;
-  sched->x0 = mx - half_x, sched->y0 = my - half_y, sched->half_theta = half_theta;
-  sched->scale_t = static_cast<double>(nt) / (2.0 * half_theta);
-  sched->scale_x = static_cast<double>(nx) / ext_x;
-  sched->scale_y = static_cast<double>(ny) / ext_y;
-  sched->nt = nt, sched->nx = nx, sched->ny = ny;
+  schedule_from_moments(*sched, sched->sums[0] * inv_n, sched->sums[1] * inv_n, mx, my, sched->sums[4] * inv_n - mx * mx,
+                        sched->sums[5] * inv_n - my * my, static_cast<double>(n), mean_range, min_bin, per_bin);
 }
 
 __device__ __forceinline__ uint32_t schedule_bin(const Schedule& g, const Pose2& st) {
-  const double dtheta = atan2(st.s * g.c0 - st.c * g.s0, st.c * g.c0 + st.s * g.s0);
-  const int bt = min(max(static_cast<int>((dtheta + g.half_theta) * g.scale_t), 0), static_cast<int>(g.nt) - 1);
-  const int bx = min(max(static_cast<int>((st.x - g.x0) * g.scale_x), 0), static_cast<int>(g.nx) - 1);
-  const int by = min(max(static_cast<int>((st.y - g.y0) * g.scale_y), 0), static_cast<int>(g.ny) - 1);
+  // heading relative to the mean as u = 2 tan(dtheta / 2): monotone in dtheta, one division instead of an atan2
+  const double cr = st.c * g.c0 + st.s * g.s0, sr = st.s * g.c0 - st.c * g.s0;
+  const double u = cr > -0.4 ? 2.0 * sr / (1.0 + cr) : (sr >= 0.0 ? 1e6 : -1e6);
+  const int bt = min(max(static_cast<int>(fmin(fmax((u + g.half_u) * g.scale_t, 0.0), 1e6)), 0), static_cast<int>(g.nt) - 1);
+  const int bx = min(max(static_cast<int>(fmin(fmax((st.x - g.x0) * g.scale_x, 0.0), 1e6)), 0), static_cast<int>(g.nx) - 1);
+  const int by = min(max(static_cast<int>(fmin(fmax((st.y - g.y0) * g.scale_y, 0.0), 1e6)), 0), static_cast<int>(g.ny) - 1);
   return (static_cast<uint32_t>(bt) * g.ny + static_cast<uint32_t>(by)) * g.nx + static_cast<uint32_t>(bx);
+}
+
+/// propagate with the histogram of the execution schedule fused in (the bin grid comes from the host's prediction).
+__global__ void __launch_bounds__(kPrThreads) propagate_binned_kernel(Pose2* __restrict__ states, uint64_t n, MotionSampling sampling, uint64_t seed,
+                                                                      uint32_t step, uint64_t first_index, Schedule grid,
+                                                                      uint32_t* __restrict__ bins, uint32_t* __restrict__ counters) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kPrThreads + threadIdx.x;
+  if (i >= n) return;
+  const Pose2 st = propagate_one(load_pose(states + i), sampling, seed, first_index + i, step);
+  store_pose(states + i, st);
+  const uint32_t b = schedule_bin(grid, st);
+  bins[i] = b;
+  atomicAdd(counters + b, 1u);
 }
 
 __global__ void __launch_bounds__(256) schedule_histogram_kernel(const Pose2* __restrict__ states, uint64_t n, const Schedule* __restrict__ sched,
@@ -915,12 +943,32 @@ __global__ void prepare_cdf_kernel(Scalars* s, double host_wmax, int ceil_log2_c
   }
 }
 
-__device__ __forceinline__ unsigned long long quantize(double w, int exponent) {
-  const double scaled = scalbn(w, exponent);
-  return scaled > 0.0 ? __double2ull_rd(scaled) : 0ull;  // zero / negative / NaN weights are never selected
+/// Inclusive scan of per-thread totals across the block (warp shuffles + one smem hop).
+template <int kThreads>
+__device__ __forceinline__ unsigned long long block_inclusive_scan_u64_n(unsigned long long v, unsigned long long* warp_sums,
+                                                                          unsigned long long& block_total) {
+  const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
+#pragma unroll
+  for (int off = 1; off < kWarp; off <<= 1) {
+    const unsigned long long o = __shfl_up_sync(0xffffffffu, v, off);
+    if (lane >= off) v += o;
+  }
+  if (lane == kWarp - 1) warp_sums[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long ws = lane < kThreads / kWarp ? warp_sums[lane] : 0ull;
+#pragma unroll
+    for (int off = 1; off < kWarp; off <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, ws, off);
+      if (lane >= off) ws += o;
+    }
+    if (lane < kThreads / kWarp) warp_sums[lane] = ws;
+  }
+  __syncthreads();
+  block_total = warp_sums[kThreads / kWarp - 1];
+  return v + (warp > 0 ? warp_sums[warp - 1] : 0ull);
 }
 
-/// Inclusive scan of per-thread totals across the block (warp shuffles + one smem hop).
 __device__ __forceinline__ unsigned long long block_inclusive_scan_u64(unsigned long long v, unsigned long long* warp_sums,
                                                                         unsigned long long& block_total) {
   const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
@@ -981,39 +1029,105 @@ __device__ __forceinline__ unsigned long long lookback_exclusive_prefix(unsigned
   return *s_prefix;
 }
 
-__global__ void __launch_bounds__(kScanThreads) quantize_scan_kernel(const double* __restrict__ weights, uint64_t n,
-                                                                     unsigned long long* __restrict__ cdf, Scalars* scalars,
-                                                                     unsigned long long* tile_state) {
-  __shared__ unsigned long long s_warp[kScanThreads / kWarp];
+// Tile of the CDF build: 256 threads x 8 consecutive weights (two 32-byte sectors per thread, read and written with
+// 16-byte accesses).  The quantisation is a multiplication by 2^e (exact, like scalbn, wherever the result is >= 1),
+// split into two power-of-two factors so that each stays a normal double for any exponent.
+constexpr int kQsThreads = 256;
+constexpr int kQsItems = 8;
+constexpr uint32_t kQsTile = kQsThreads * kQsItems;
+
+__device__ __forceinline__ double pow2_double(int e) {  // |e| <= 1000
+  return __longlong_as_double(static_cast<long long>(e + 1023) << 52);
+}
+__device__ __forceinline__ unsigned long long quantize_mul(double w, double f1, double f2) {
+  const double scaled = (w * f1) * f2;
+  return scaled > 0.0 ? __double2ull_rd(scaled) : 0ull;  // zero / negative / NaN weights are never selected
+}
+
+/// derive_exponent: the fused step -- the exponent comes from scalars->wmax_bits here (no prepare_cdf launch; the
+/// tile holding element 0 publishes exponent / valid for the host); otherwise scalars->exponent / valid are given.
+__global__ void __launch_bounds__(kQsThreads) quantize_scan_kernel(const double* __restrict__ weights, uint64_t n,
+                                                                   unsigned long long* __restrict__ cdf, Scalars* scalars,
+                                                                   unsigned long long* tile_state, int derive_exponent, int ceil_log2_count) {
+  __shared__ unsigned long long s_warp[kQsThreads / kWarp];
   __shared__ unsigned long long s_prefix;
   __shared__ uint32_t s_tile;
-  if (threadIdx.x == 0) s_tile = static_cast<uint32_t>(atomicAdd(&scalars->tile_ticket, 1ull));
+  __shared__ double s_factor[2];
+  __shared__ int s_valid;
+  if (threadIdx.x == 0) {
+    const uint32_t tile = static_cast<uint32_t>(atomicAdd(&scalars->tile_ticket, 1ull));
+    s_tile = tile;
+    int exponent, valid;
+    if (derive_exponent) {
+      const double wmax = __longlong_as_double(static_cast<long long>(scalars->wmax_bits));
+      int ex = 0;
+      const bool ok = wmax > 0.0 && wmax <= DBL_MAX;
+      if (ok) (void)frexp(wmax, &ex);
+      exponent = min(52, 62 - ceil_log2_count) - ex;
+      valid = ok ? 1 : 0;
+      if (tile == 0) {
+        scalars->exponent = exponent;
+        scalars->valid = valid;
+      }
+    } else {
+      exponent = scalars->exponent;
+      valid = scalars->valid;
+    }
+    const int e1 = exponent / 2;
+    s_factor[0] = pow2_double(e1);
+    s_factor[1] = pow2_double(exponent - e1);
+    s_valid = valid;
+  }
   __syncthreads();
   const uint32_t tile = s_tile;
-  const int exponent = scalars->exponent;
-  const bool valid = scalars->valid != 0;
+  const double f1 = s_factor[0], f2 = s_factor[1];
+  const bool valid = s_valid != 0;
 
-  const uint64_t base = static_cast<uint64_t>(tile) * kScanTile + static_cast<uint64_t>(threadIdx.x) * kScanItems;
-  unsigned long long q[kScanItems];
+  const uint64_t base = static_cast<uint64_t>(tile) * kQsTile + static_cast<uint64_t>(threadIdx.x) * kQsItems;
+  unsigned long long q[kQsItems];
   unsigned long long local = 0;
+  if (base + kQsItems <= n) {
+    const double2* src = reinterpret_cast<const double2*>(weights + base);
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    const uint64_t idx = base + k;
-    // Degenerate weight set (no positive finite weight): fall back to a uniform CDF.
-    q[k] = idx < n ? (valid ? quantize(weights[idx], exponent) : (1ull << 20)) : 0ull;
-    local += q[k];
+    for (int k = 0; k < kQsItems / 2; ++k) {
+      const double2 w = __ldcs(src + k);  // read once: streaming
+      // Degenerate weight set (no positive finite weight): fall back to a uniform CDF.
+      q[2 * k] = valid ? quantize_mul(w.x, f1, f2) : (1ull << 20);
+      q[2 * k + 1] = valid ? quantize_mul(w.y, f1, f2) : (1ull << 20);
+      local += q[2 * k] + q[2 * k + 1];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kQsItems; ++k) {
+      const uint64_t idx = base + k;
+      q[k] = idx < n ? (valid ? quantize_mul(weights[idx], f1, f2) : (1ull << 20)) : 0ull;
+      local += q[k];
+    }
   }
   unsigned long long tile_total;
-  const unsigned long long inclusive = block_inclusive_scan_u64(local, s_warp, tile_total);
+  const unsigned long long inclusive = block_inclusive_scan_u64_n<kQsThreads>(local, s_warp, tile_total);
   const unsigned long long prefix = lookback_exclusive_prefix(tile_state, tile, tile_total, &s_prefix);
   unsigned long long running = prefix + inclusive - local;
+  if (base + kQsItems <= n) {
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(cdf + base);
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    const uint64_t idx = base + k;
-    running += q[k];
-    if (idx < n) cdf[idx] = running;
+    for (int k = 0; k < kQsItems / 2; ++k) {
+      ulonglong2 v;
+      running += q[2 * k];
+      v.x = running;
+      running += q[2 * k + 1];
+      v.y = running;
+      dst[k] = v;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kQsItems; ++k) {
+      const uint64_t idx = base + k;
+      running += q[k];
+      if (idx < n) cdf[idx] = running;
+    }
   }
-  if (base <= n - 1 && n - 1 < base + kScanItems) scalars->total = prefix + inclusive;  // thread holding the last element
+  if (base <= n - 1 && n - 1 < base + kQsItems) scalars->total = prefix + inclusive;  // thread holding the last element
 }
 
 /// Exclusive prefix sum of u32 values (bin counters, KLD first-occurrence flags) with the same
@@ -1181,7 +1295,47 @@ __device__ __forceinline__ void store_block_moments(double* m, double* scratch /
   }
 }
 
-__global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, const Scalars* __restrict__ scalars, double* __restrict__ moment_partials) {
+/// Stores the block's raw moments and, when the launch carries a StepTail, lets the LAST block to arrive add the
+/// per-block rows up in a fixed order (thread-strided over the rows, then the block tree: the same sum for any
+/// arrival order) -- the reduce_partials launch and the read-back copies of the fused step folded into the resample.
+/// With tail.summary set (single GPU: pinned host memory, written straight over PCIe) the host finds the step's
+/// results after its one stream synchronisation.
+template <int kThreads>
+__device__ __forceinline__ void finish_block_moments(double* m, double* scratch, double* __restrict__ moment_partials, Scalars* scalars,
+                                                     const StepTail& tail) {
+  store_block_moments<kThreads>(m, scratch, moment_partials + static_cast<size_t>(blockIdx.x) * kMomentCount);
+  if (!tail.enabled) return;
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();  // the row above before the arrival count
+    s_last = atomicAdd(&scalars->blocks_done, 1u) + 1u == gridDim.x ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+#pragma unroll 1
+  for (int k = 0; k < kMomentCount; ++k) {
+    double v = 0.0;
+    for (uint32_t r = threadIdx.x; r < gridDim.x; r += kThreads) v = v + __ldcg(moment_partials + static_cast<size_t>(r) * kMomentCount + k);
+    const double total = block_sum<kThreads>(v, scratch);
+    if (threadIdx.x == 0) {
+      tail.results[k] = total;
+      if (tail.summary != nullptr) tail.summary->moments[k] = total;
+    }
+  }
+  if (threadIdx.x == 0) {
+    scalars->blocks_done = 0;
+    if (tail.summary != nullptr) {
+      tail.summary->total = scalars->total;
+      tail.summary->exponent = scalars->exponent;
+      tail.summary->valid = scalars->valid;
+      tail.summary->error = 0;
+      __threadfence_system();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, Scalars* __restrict__ scalars, double* __restrict__ moment_partials) {
   __shared__ double s_red[kMomentCount * kRsThreads / kWarp];
   unsigned long long total = a.global_total != 0 ? a.global_total : scalars->total;
   unsigned long long cdf_offset = a.cdf_offset, span_end = 0;
@@ -1252,7 +1406,7 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, co
     if (a.hashes != nullptr) a.hashes[local] = spatial_hash(st, a.hash_resolution[0], a.hash_resolution[1], a.hash_resolution[2]);
     accumulate_moments(m, st, 1.0, a.pivot_x, a.pivot_y);
   }
-  store_block_moments<kRsThreads>(m, s_red, moment_partials + static_cast<size_t>(blockIdx.x) * kMomentCount);
+  finish_block_moments<kRsThreads>(m, s_red, moment_partials, scalars, a.tail);
 }
 
 // ---- resample, scatter form (systematic comb on one GPU) ----------------------------------------------
@@ -1270,9 +1424,22 @@ __device__ __forceinline__ uint64_t comb_slots_before(unsigned long long positio
   return j < total_slots ? j : total_slots;
 }
 
-__global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleArgs a, const Scalars* __restrict__ scalars,
+/// The same with the division replaced by a multiplication with magic = floor((2^64 - 1) / stride): the high word of
+/// x * magic is the quotient or one below it (x < 2^64, so the error of the reciprocal costs less than 1); one
+/// remainder check makes it exact.  A 64-bit division is ~150 instructions; this is 8.
+__device__ __forceinline__ uint64_t comb_slots_before_magic(unsigned long long position, unsigned long long offset, unsigned long long stride,
+                                                           unsigned long long magic, uint64_t total_slots) {
+  if (position <= offset) return 0;
+  const unsigned long long x = position - offset + stride - 1;
+  unsigned long long j = __umul64hi(x, magic);
+  if (x - j * stride >= stride) ++j;
+  return j < total_slots ? j : total_slots;
+}
+
+__global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleArgs a, Scalars* __restrict__ scalars,
                                                                      double* __restrict__ moment_partials) {
   __shared__ double s_red[kMomentCount * kRsThreads / kWarp];
+  __shared__ unsigned long long s_comb[3];
   // One GPU: the local CDF is the global one.  Sharded (rank_totals set): positions shift by the totals of
   // the lower ranks and every copy goes to the rank that owns its slot, over NVLink peer memory.
   unsigned long long total = scalars->total, cdf_offset = 0;
@@ -1284,8 +1451,14 @@ __global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleAr
       total += t;
     }
   }
-  const unsigned long long stride = total / a.total_slots;
-  const unsigned long long offset = mulhi64(counter_draw(a.seed, 0, a.step, kStreamSystematic).a, stride);
+  if (threadIdx.x == 0) {  // the two 64-bit divisions of the comb, once per block
+    const unsigned long long st = total / a.total_slots;
+    s_comb[0] = st;
+    s_comb[1] = mulhi64(counter_draw(a.seed, 0, a.step, kStreamSystematic).a, st);
+    s_comb[2] = ~0ull / (st != 0 ? st : 1ull);
+  }
+  __syncthreads();
+  const unsigned long long stride = s_comb[0], offset = s_comb[1], magic = s_comb[2];
   const int lane = threadIdx.x % kWarp;
   double m[kMomentCount];
 #pragma unroll
@@ -1306,8 +1479,8 @@ __global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleAr
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kRsThreads + threadIdx.x; i < n_padded; i += static_cast<uint64_t>(gridDim.x) * kRsThreads) {
     uint64_t ja = 0, jb = 0;
     if (i < a.n_in) {
-      ja = comb_slots_before(cdf_offset + (i > 0 ? a.cdf[i - 1] : 0ull), offset, stride, a.total_slots);
-      jb = comb_slots_before(cdf_offset + a.cdf[i], offset, stride, a.total_slots);
+      ja = comb_slots_before_magic(cdf_offset + (i > 0 ? a.cdf[i - 1] : 0ull), offset, stride, magic, a.total_slots);
+      jb = comb_slots_before_magic(cdf_offset + a.cdf[i], offset, stride, magic, a.total_slots);
     }
     const uint64_t copies = jb - ja;
     Pose2 st{1.0, 0.0, 0.0, 0.0};
@@ -1343,7 +1516,7 @@ __global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleAr
       for (uint64_t j = hja + lane; j < hjb; j += kWarp) store_copy(j, hs, hi);
     }
   }
-  store_block_moments<kRsThreads>(m, s_red, moment_partials + static_cast<size_t>(blockIdx.x) * kMomentCount);
+  finish_block_moments<kRsThreads>(m, s_red, moment_partials, scalars, a.tail);
 }
 
 // ---- moments / reductions -------------------------------------------------------------------------
@@ -1462,6 +1635,17 @@ __global__ void __launch_bounds__(256) shard_exchange_kernel(ShardExchangeArgs a
   }
 }
 
+__global__ void write_summary_kernel(const double* __restrict__ results, const Scalars* __restrict__ scalars, StepSummary* summary) {
+  if (threadIdx.x < kMomentCount) summary->moments[threadIdx.x] = results[threadIdx.x];
+  if (threadIdx.x == 0) {
+    summary->total = scalars->total;
+    summary->exponent = scalars->exponent;
+    summary->valid = scalars->valid;
+    summary->error = 0;
+  }
+  __threadfence_system();
+}
+
 int ceil_log2_u64(uint64_t n) {
   int b = 0;
   while ((uint64_t{1} << b) < n) ++b;
@@ -1476,6 +1660,9 @@ constexpr uint32_t kStreamMaxBlocks = 148 * 8;
 
 void launch_begin_step(Scalars* scalars, cudaStream_t stream) { begin_step_kernel<<<1, 1, 0, stream>>>(scalars); }
 
+void launch_write_summary(const double* results, const Scalars* scalars, StepSummary* summary, cudaStream_t stream) {
+  write_summary_kernel<<<1, 32, 0, stream>>>(results, scalars, summary);
+}
 void launch_shard_exchange(const ShardExchangeArgs& args, cudaStream_t stream) { shard_exchange_kernel<<<1, 256, 0, stream>>>(args); }
 int ceil_log2_count(uint64_t n) { return ceil_log2_u64(n); }
 
@@ -1503,6 +1690,21 @@ void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const Motion
                                                                                                       seed, step, first_index, sched);
 }
 
+void launch_propagate_binned(Pose2* states, uint64_t n, const MotionSampling& sampling, uint64_t seed, uint32_t step, uint64_t first_index,
+                             const Schedule& grid, uint32_t* bins, uint32_t* counters, cudaStream_t stream) {
+  if (n == 0) return;
+  propagate_binned_kernel<<<static_cast<unsigned>((n + kPrThreads - 1) / kPrThreads), kPrThreads, 0, stream>>>(states, n, sampling, seed, step,
+                                                                                                             first_index, grid, bins, counters);
+}
+
+void launch_begin_fused_step(Scalars* scalars, unsigned long long* tile_state, uint32_t n_tiles, Schedule* sched, uint32_t* counters,
+                             uint32_t n_counters, unsigned long long* sched_tiles, uint32_t n_sched_tiles, cudaStream_t stream) {
+  const StepReset r{scalars, tile_state, n_tiles, sched, counters, (n_counters + 3u) & ~3u, sched_tiles, n_sched_tiles};
+  const uint32_t work = std::max(n_tiles, counters != nullptr ? r.n_counters / 4 : 0u);
+  const unsigned blocks = std::max(1u, std::min((work + 255u) / 256u, 148u));
+  begin_fused_step_kernel<<<blocks, 256, 0, stream>>>(r);
+}
+
 uint32_t schedule_max_bins() { return kMaxBins; }
 uint32_t schedule_tile_count() { return (kMaxBins + kScanTile - 1) / kScanTile; }
 
@@ -1515,6 +1717,15 @@ void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uin
   schedule_params_kernel<<<1, 1, 0, stream>>>(sched, n, mean_range, min_bin, per_bin);
   schedule_histogram_kernel<<<blocks, 256, 0, stream>>>(states, n, sched, bins, counters);
   scan_u32_kernel<<<schedule_tile_count(), kScanThreads, 0, stream>>>(counters, counters, kMaxBins, &sched->tile_ticket, tile_state, nullptr);
+  schedule_scatter_kernel<<<blocks, 256, 0, stream>>>(bins, n, counters, perm);
+}
+
+void launch_finish_schedule(const uint32_t* bins, uint64_t n, uint32_t n_bins, Schedule* sched, uint32_t* counters, uint32_t* perm,
+                            unsigned long long* tile_state, cudaStream_t stream) {
+  if (n == 0) return;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  const uint32_t tiles = (n_bins + kScanTile - 1) / kScanTile;
+  scan_u32_kernel<<<tiles, kScanThreads, 0, stream>>>(counters, counters, n_bins, &sched->tile_ticket, tile_state, nullptr);
   schedule_scatter_kernel<<<blocks, 256, 0, stream>>>(bins, n, counters, perm);
 }
 
@@ -1586,7 +1797,7 @@ void launch_max_weight(const double* weights, uint64_t n, Scalars* scalars, cuda
   max_weight_kernel<<<blocks, 512, 0, stream>>>(weights, n, scalars);
 }
 
-uint32_t scan_tile_count(uint64_t n) { return static_cast<uint32_t>((n + kScanTile - 1) / kScanTile); }
+uint32_t scan_tile_count(uint64_t n) { return static_cast<uint32_t>((n + kQsTile - 1) / kQsTile); }  // the smaller of the two tile sizes
 
 void launch_prepare_cdf(Scalars* scalars, double host_wmax, uint64_t global_count, unsigned long long* tile_state, uint32_t n_tiles,
                         cudaStream_t stream) {
@@ -1595,9 +1806,10 @@ void launch_prepare_cdf(Scalars* scalars, double host_wmax, uint64_t global_coun
 }
 
 void launch_quantize_scan(const double* weights, uint64_t n, unsigned long long* cdf, Scalars* scalars, unsigned long long* tile_state,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, bool derive_exponent, uint64_t global_count) {
   if (n == 0) return;
-  quantize_scan_kernel<<<scan_tile_count(n), kScanThreads, 0, stream>>>(weights, n, cdf, scalars, tile_state);
+  quantize_scan_kernel<<<static_cast<unsigned>((n + kQsTile - 1) / kQsTile), kQsThreads, 0, stream>>>(
+      weights, n, cdf, scalars, tile_state, derive_exponent ? 1 : 0, ceil_log2_u64(global_count));
 }
 
 void launch_normalize(double* weights, uint64_t n, const Scalars* scalars, unsigned long long global_total, double* partials,
@@ -1638,7 +1850,7 @@ uint32_t resample_block_count(uint64_t slots) {
   return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>((slots + kRsThreads - 1) / kRsThreads, 148 * 16)));
 }
 
-void launch_resample(const ResampleArgs& args, const Scalars* scalars, double* moment_partials, cudaStream_t stream) {
+uint32_t launch_resample(const ResampleArgs& args, Scalars* scalars, double* moment_partials, cudaStream_t stream) {
   // The whole set on one GPU with the systematic comb and nothing per slot to draw: scatter form.
   // (Sharded with peer memory and device-side totals: the same, every copy stored into its owner's buffer.)
   const bool plain = args.scheme == 1 && args.random_state_probability <= 0.0 && args.hashes == nullptr && args.span_filter == 0 &&
@@ -1646,10 +1858,14 @@ void launch_resample(const ResampleArgs& args, const Scalars* scalars, double* m
   const bool scatter = plain && ((args.peer_count == 0 && args.rank_totals == nullptr && args.slot_count == args.total_slots) ||
                                  (args.peer_count > 0 && args.rank_totals != nullptr));
   if (scatter) {
-    resample_scatter_kernel<<<resample_block_count(args.slot_count), kRsThreads, 0, stream>>>(args, scalars, moment_partials);
-    return;
+    // one pass over the input particles; a few particles per thread amortise the block reduction of the moments
+    const uint32_t blocks = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>((args.n_in + kRsThreads - 1) / kRsThreads, 148 * 4)));
+    resample_scatter_kernel<<<blocks, kRsThreads, 0, stream>>>(args, scalars, moment_partials);
+    return blocks;
   }
-  resample_kernel<<<resample_block_count(args.slot_count), kRsThreads, 0, stream>>>(args, scalars, moment_partials);
+  const uint32_t blocks = resample_block_count(args.slot_count);
+  resample_kernel<<<blocks, kRsThreads, 0, stream>>>(args, scalars, moment_partials);
+  return blocks;
 }
 
 uint32_t moments_block_count(uint64_t n) {

@@ -86,7 +86,7 @@ struct Scalars {
   unsigned long long work_ticket;  // persistent reweight kernel: next 32-particle task (rewound by the last warp out)
   unsigned long long work_done;    // warps that have left that kernel
   int exchange_error;              // sticky: a shard exchange timed out
-  int pad2;
+  unsigned int blocks_done;        // resample kernels: blocks that have stored their moment partials (the last one reduces them)
   unsigned long long global_total; // sharded filters: sum of the ranks' totals (set by the totals exchange)
 };
 
@@ -132,6 +132,8 @@ struct ShardExchangeArgs {
   uint32_t n_tiles;
 };
 void launch_shard_exchange(const ShardExchangeArgs& args, cudaStream_t stream);
+/// results (9 moments) + the CDF scalars -> the host's StepSummary block (pinned memory).
+void launch_write_summary(const double* results, const struct Scalars* scalars, StepSummary* summary, cudaStream_t stream);
 int ceil_log2_count(uint64_t n);
 
 constexpr int kMomentCount = 9;  // sum w, sum w^2, sum w c, sum w s, sum w dx, sum w dy, sum w dx^2, sum w dx dy, sum w dy^2
@@ -154,19 +156,67 @@ BB_HD size_t tiled_index(int xi, int yi, int tiles_x) {
   return tile * 16 + (((y & 3u) << 2) | (x & 3u));
 }
 
-/// Execution schedule state (device): cloud moments and the pose-bin grid derived from them.
+/// Execution schedule state: cloud moments and the pose-bin grid derived from them.
 struct Schedule {
-  double sums[6];  // sum cos, sin, x, y, x^2, y^2 of the propagated cloud
+  double sums[6];  // sum cos, sin, x, y, x^2, y^2 of the propagated cloud (device-built schedules only)
   unsigned long long tile_ticket;
   double c0, s0;            // mean heading (unit complex)
-  double x0, y0, half_theta;
+  double x0, y0, half_u;    // lower corner of the box; half extent of the heading coordinate u = 2 tan(dtheta / 2)
   double scale_t, scale_x, scale_y;
   uint32_t nt, nx, ny;
+  uint32_t n_bins;
 };
+constexpr uint32_t kScheduleMaxBins = 1u << 18;  // 16 particles per bin up to 4M particles per shard
+
+/// The pose-bin grid for a cloud with mean resultant (cbar, sbar), mean position (mx, my) and position variances
+/// (vx, vy): bins of equal physical edge in (range * heading, x, y) covering +-3 sigma, about `per_bin` particles each.
+/// Runs on the device (moments of the propagated cloud) or on the host (moments predicted from the last estimate and
+/// the motion means).  The schedule only decides WHICH THREAD handles a particle, never a result.
+BB_HD void schedule_from_moments(Schedule& g, double cbar, double sbar, double mx, double my, double vx, double vy, double n,
+                                 double mean_range, double min_bin, double per_bin) {
+  const double r = sqrt(cbar * cbar + sbar * sbar);
+  const double pi = 3.14159265358979323846;
+  double c0 = 1.0, s0 = 0.0, sigma_theta = pi;
+  if (r > 1e-9) {
+    c0 = cbar / r;
+    s0 = sbar / r;
+    sigma_theta = r < 1.0 ? sqrt(-2.0 * log(r)) : 0.0;
+  }
+  const double half_theta = fmin(2.0, fmax(3.0 * sigma_theta, 1e-4));  // beyond +-2 rad: the edge bins
+  const double half_u = 2.0 * tan(0.5 * half_theta);
+  const double half_x = fmax(3.0 * sqrt(fmax(vx, 0.0)), min_bin), half_y = fmax(3.0 * sqrt(fmax(vy, 0.0)), min_bin);
+  const double ext_t = 2.0 * half_u * fmax(mean_range, 1.0), ext_x = 2.0 * half_x, ext_y = 2.0 * half_y;
+  double q = cbrt(ext_t * ext_x * ext_y / fmax(n / per_bin, 1.0));
+  q = fmax(q, min_bin);
+  uint32_t nt, nx, ny;
+  for (;;) {
+    nt = static_cast<uint32_t>(fmin(fmax(ceil(ext_t / q), 1.0), 65536.0));
+    nx = static_cast<uint32_t>(fmin(fmax(ceil(ext_x / q), 1.0), 65536.0));
+    ny = static_cast<uint32_t>(fmin(fmax(ceil(ext_y / q), 1.0), 65536.0));
+    if (static_cast<uint64_t>(nt) * nx * ny <= kScheduleMaxBins) break;
+    q = q * 1.3;
+  }
+  g.c0 = c0, g.s0 = s0;
+  g.x0 = mx - half_x, g.y0 = my - half_y, g.half_u = half_u;
+  g.scale_t = static_cast<double>(nt) / (2.0 * half_u);
+  g.scale_x = static_cast<double>(nx) / ext_x;
+  g.scale_y = static_cast<double>(ny) / ext_y;
+  g.nt = nt, g.nx = nx, g.ny = ny;
+  g.n_bins = nt * nx * ny;
+}
 
 /// propagate (or only accumulate the cloud moments when do_propagate is false).  sched may be null.
 void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const MotionSampling& sampling, uint64_t seed, uint32_t step,
                       uint64_t first_index, Schedule* sched, cudaStream_t stream);
+/// propagate with the pose-bin histogram fused in: `grid` was predicted on the host, every particle's bin goes to
+/// bins[] and into the counters (zeroed by launch_begin_fused_step).  launch_finish_schedule turns them into perm.
+void launch_propagate_binned(Pose2* states, uint64_t n, const MotionSampling& sampling, uint64_t seed, uint32_t step, uint64_t first_index,
+                             const Schedule& grid, uint32_t* bins, uint32_t* counters, cudaStream_t stream);
+void launch_finish_schedule(const uint32_t* bins, uint64_t n, uint32_t n_bins, Schedule* sched, uint32_t* counters, uint32_t* perm,
+                            unsigned long long* tile_state, cudaStream_t stream);
+/// One launch resetting the per-step scalars, the CDF scan state and (counters != nullptr) the schedule's counters / scan state.
+void launch_begin_fused_step(Scalars* scalars, unsigned long long* tile_state, uint32_t n_tiles, Schedule* sched, uint32_t* counters,
+                             uint32_t n_counters, unsigned long long* sched_tiles, uint32_t n_sched_tiles, cudaStream_t stream);
 uint32_t schedule_max_bins();
 uint32_t schedule_tile_count();
 /// Counting sort of the particle indices over pose bins -> perm (needs launch_propagate's moments).
@@ -194,13 +244,23 @@ void launch_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, unsigned lon
                      unsigned long long* total_out, cudaStream_t stream);
 uint32_t scan_tile_count(uint64_t n);
 /// Fixed-point quantisation + single-pass inclusive scan (decoupled look-back).
+/// derive_exponent: take the exponent from scalars->wmax_bits inside the kernel (needs the scan state already reset,
+/// launch_begin_fused_step or the shard exchange) instead of scalars->exponent set by launch_prepare_cdf.
 void launch_quantize_scan(const double* weights, uint64_t n, unsigned long long* cdf, Scalars* scalars, unsigned long long* tile_state,
-                          cudaStream_t stream);
+                          cudaStream_t stream, bool derive_exponent = false, uint64_t global_count = 1);
 
 /// w /= S (S = global_total * 2^-exponent) and per-block partial sums of (w/S)^2.
 /// global_total == ~0: the sharded filter's total on the device (scalars->global_total).
 void launch_normalize(double* weights, uint64_t n, const Scalars* scalars, unsigned long long global_total, double* partials,
                       uint32_t* n_partials, cudaStream_t stream);
+
+/// Optional tail of a resample launch: the last block sums the per-block moment rows into `results` (device) and,
+/// when `summary` is set, writes the step's StepSummary there (pinned host memory on a single GPU).
+struct StepTail {
+  int enabled;
+  double* results;
+  StepSummary* summary;
+};
 
 struct ResampleArgs {
   const Pose2* states_in;
@@ -242,10 +302,12 @@ struct ResampleArgs {
   Pose2 grid_origin;
   double hash_resolution[3];
   double pivot_x, pivot_y;
+  StepTail tail;
 };
 uint32_t resample_block_count(uint64_t slots);
-/// sample | random_intersperse | (hash) | assign, plus per-block raw moments of the new set.
-void launch_resample(const ResampleArgs& args, const Scalars* scalars, double* moment_partials, cudaStream_t stream);
+/// sample | random_intersperse | (hash) | assign, plus per-block raw moments of the new set.  Returns the number of
+/// blocks launched (= rows of moment_partials written).
+uint32_t launch_resample(const ResampleArgs& args, Scalars* scalars, double* moment_partials, cudaStream_t stream);
 
 /// Per-block raw weighted moments of (states, weights).
 uint32_t moments_block_count(uint64_t n);

@@ -80,7 +80,7 @@ def compare_step(rg, ro, g, o, exact_indices=True):
     if rg.resampled and exact_indices:
         assert np.array_equal(g.filter.ancestors(), o.last_indices()), "resample indices differ from the oracle"
         assert np.abs(gm - om).max() < 1e-9 and np.abs(gc - oc).max() < 1e-9
-        assert rg.weight_sum == pytest.approx(ro.weight_sum, rel=1e-12)
+        assert rg.weight_sum == pytest.approx(ro.weight_sum, rel=1e-10)  # T * 2^-e: the integer total follows the states (libm ulps) at 10M particles
     return gm, om
 
 

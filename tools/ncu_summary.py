@@ -59,6 +59,7 @@ def table(path):
     except Exception:
         pass
     recs = []
+    print(f"# units: time '{rows[1][col['gpu__time_duration.sum']]}', dram '{rows[1][col['dram__bytes_read.sum']]}'")
     print(f"# {path}: one launch per kernel, ncu --set full --clock-control none; HBM peak {peak} GB/s (MEASURED_PEAKS.json)")
     print(f"{'kernel':44s} {'us':>9s} {'dramMB':>9s} {'GB/s':>7s} {'%peak':>6s} {'dram%':>6s} {'l1tex%':>6s} {'lts%':>6s} {'issue%':>6s} {'fp64%':>6s} {'occ%':>5s} {'regs':>4s}  top stall")
     for r in rows[2:]:
@@ -66,10 +67,10 @@ def table(path):
         dur_us = num(r, "gpu__time_duration.sum") / 1e3  # ns in the raw page
         dram = num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum")
         unit = rows[1][col["dram__bytes_read.sum"]]
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "B": 1.0, "KB": 1e3, "MB": 1e6, "GB": 1e9}.get(unit, 1.0)
         dram *= scale
         tunit = rows[1][col["gpu__time_duration.sum"]]
-        dur_us = num(r, "gpu__time_duration.sum") * {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}.get(tunit, 1e-3)
+        dur_us = num(r, "gpu__time_duration.sum") * {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}.get(tunit, 1e-3)
         gbs = dram / (dur_us * 1e-6) / 1e9 if dur_us > 0 else float("nan")
         top = max(stalls, key=lambda k: num(r, k) if num(r, k) == num(r, k) else -1.0) if stalls else ""
         rec = {"kernel": name, "us": dur_us, "dram_bytes": dram, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak,

@@ -11,6 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-fil
 ncu --set full --clock-control none --profile-from-start off -o gpurun_out/prof_all_${tag} -f \
     python tools/profile_workload.py ${sections} > gpurun_out/profile_workload_${tag}.log 2>&1
 python tools/ncu_summary.py --table gpurun_out/prof_all_${tag}.ncu-rep > gpurun_out/prof_all_${tag}.txt 2>&1
+rm -f gpurun_out/prof_all_${tag}.ncu-rep   # ~1 MB per kernel: over the 64 MiB that travel back; the table above is what is kept
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:reweight_lfm -o gpurun_out/prof_lfm_${tag} -f \
     python tools/profile_workload.py c2 > gpurun_out/profile_lfm_${tag}.log 2>&1
 ls -la gpurun_out | tail -8
