@@ -219,6 +219,7 @@ class Filter {
   double schedule_lever_{1.0};
   Schedule* sched_{nullptr};
   uint32_t* bins_{nullptr};
+  uint2* bin_rank_{nullptr};
   uint32_t* perm_{nullptr};
   uint32_t* counters_{nullptr};
   unsigned long long* sched_tiles_{nullptr};
@@ -229,6 +230,8 @@ class Filter {
   double* table_{nullptr};
   double* tiled_{nullptr};
   double* bordered_{nullptr};
+  float* bordered_f_{nullptr};
+  bool float_table_{true};
   FieldView field_{};
   int8_t* occupancy_{nullptr};
   uint8_t* free_distance_{nullptr};

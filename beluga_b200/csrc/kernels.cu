@@ -30,6 +30,9 @@
 #ifndef BB200_RW_BLOCKS
 #define BB200_RW_BLOCKS 4
 #endif
+#ifndef BB200_RS_UNROLL
+#define BB200_RS_UNROLL 4  // particles per thread and round in resample_scatter_kernel
+#endif
 
 #include <algorithm>
 #include <cfloat>
@@ -266,14 +269,14 @@ __global__ void __launch_bounds__(256) initialize_uniform_kernel(Pose2* states, 
 constexpr int kPrThreads = 256;
 
 __device__ __forceinline__ Pose2 propagate_one(const Pose2& st, const MotionSampling& p, uint64_t seed, uint64_t index, uint32_t step) {
-  double z0, z1, z2, unused;
-  box_muller(counter_draw(seed, index, step, kStreamMotion0), z0, z1);
-  box_muller(counter_draw(seed, index, step, kStreamMotion1), z2, unused);
+  double z0, z1;
+  box_muller_fast(counter_draw(seed, index, step, kStreamMotion0), z0, z1);
+  const double z2 = box_muller_first(counter_draw(seed, index, step, kStreamMotion1));
   // std::normal_distribution: ret * stddev + mean (libstdc++ bits/random.tcc:1843)
   const double d0 = z0 * p.stddev[0] + p.mean[0];
   const double d1 = z1 * p.stddev[1] + p.mean[1];
   const double d2 = z2 * p.stddev[2] + p.mean[2];
-  return motion_apply(p.model, st, d0, d1, d2, Rot2{p.first_c, p.first_s});
+  return motion_apply_fast(p.model, st, d0, d1, d2, Rot2{p.first_c, p.first_s});
 }
 
 __global__ void __launch_bounds__(kPrThreads) propagate_kernel(Pose2* __restrict__ states, uint64_t n, int do_propagate, MotionSampling sampling,
@@ -333,14 +336,24 @@ __device__ __forceinline__ uint32_t schedule_bin(const Schedule& g, const Pose2&
 /// propagate with the histogram of the execution schedule fused in (the bin grid comes from the host's prediction).
 __global__ void __launch_bounds__(kPrThreads) propagate_binned_kernel(Pose2* __restrict__ states, uint64_t n, MotionSampling sampling, uint64_t seed,
                                                                       uint32_t step, uint64_t first_index, Schedule grid,
-                                                                      uint32_t* __restrict__ bins, uint32_t* __restrict__ counters) {
+                                                                      uint2* __restrict__ bin_rank, uint32_t* __restrict__ counters) {
   const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kPrThreads + threadIdx.x;
   if (i >= n) return;
   const Pose2 st = propagate_one(load_pose(states + i), sampling, seed, first_index + i, step);
   store_pose(states + i, st);
   const uint32_t b = schedule_bin(grid, st);
-  bins[i] = b;
-  atomicAdd(counters + b, 1u);
+  // The particle's arrival rank inside its bin: the scatter pass then needs no second round of atomics.  (Which
+  // particle gets which rank varies from run to run; it only permutes the execution order inside a bin.)
+  const uint32_t rank = atomicAdd(counters + b, 1u);
+  bin_rank[i] = make_uint2(b, rank);
+}
+
+__global__ void __launch_bounds__(256) schedule_place_kernel(const uint2* __restrict__ bin_rank, uint64_t n, const uint32_t* __restrict__ offsets,
+                                                             uint32_t* __restrict__ perm) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint2 br = __ldcs(bin_rank + i);
+  perm[__ldg(offsets + br.x) + br.y] = static_cast<uint32_t>(i);
 }
 
 __global__ void __launch_bounds__(256) schedule_histogram_kernel(const Pose2* __restrict__ states, uint64_t n, const Schedule* __restrict__ sched,
@@ -540,6 +553,24 @@ __device__ __forceinline__ double fixed_lookup(const double* __restrict__ border
   return __ldg(bordered + idx);
 }
 
+/// The same against the FLOAT table (likelihood field values as the reference stores them, 4 bytes per cell) in
+/// 4 x 8-cell tiles: a 128-byte line then covers 32 cells instead of 16, so the 32 end points of a warp touch about
+/// a third fewer lines (the kernel's busiest unit is the L1 data pipe, one wavefront per line touched).  The cube is
+/// taken per lookup, (double(pz) * double(pz)) * double(pz) -- the very expression the 8-byte table tabulates -- at
+/// the price of one conversion and two multiplications on the half-idle FP64 pipe.  y's magic constant yields
+/// floor(4 g): (uy & ~31) is 32 x the tile row and (uy & 28) the row inside the tile times 4.
+__device__ __forceinline__ double fixed_lookup_float(const float* __restrict__ table, const FixedParticle& q, double px, double py, uint32_t& margin) {
+  const double gx = fma(px, q.cx, fma(-py, q.sx, q.ox)) + kFixedMagicX;
+  const double gy = fma(px, q.sx, fma(py, q.cx, q.oy)) + kFixedMagicY;
+  margin = __vimin3_u32(margin, static_cast<uint32_t>(__double2loint(gx)), static_cast<uint32_t>(__double2loint(gy)));
+  const uint32_t ux = __viaddmin_u32(static_cast<uint32_t>(__double2hiint(gx)), 0u - kFixedBiasX, q.x_max);
+  const uint32_t uy = __viaddmin_u32(static_cast<uint32_t>(__double2hiint(gy)), 0u - kFixedBiasY, q.y_max);
+  const uint32_t a = ux + 7u * (ux & ~3u);  // (x & 3) | ((x >> 2) << 5)
+  const uint32_t idx = __umul24(uy & ~0x1Fu, q.row_pitch) + (a | (uy & 0x1Cu));
+  const double pz = static_cast<double>(__ldg(table + idx));
+  return (pz * pz) * pz;
+}
+
 /// The reference's operation sequence (field_lookup) against the bordered layout.
 __device__ __forceinline__ double bordered_lookup_exact(const FieldView& f, double px, double py, double c, double s, double tx, double ty) {
   const double x = (px * c - py * s) + tx;
@@ -567,22 +598,22 @@ struct ScanParam {
 #define BB200_PRAGMA_STR(x) _Pragma(#x)
 #define BB200_PRAGMA_UNROLL(n) BB200_PRAGMA_STR(unroll n)
 // libstdc++ transform_reduce (numeric:439-462): groups of four, init += ((f0+f1)+(f2+f3)), then one by one.
-#define BB200_FIXED_SUM(POINT, COUNT)                                                                         \
+#define BB200_FIXED_SUM(POINT, COUNT, LOOKUP, TABLE)                                                                       \
   do {                                                                                                        \
     const double acc_before = acc;                                                                            \
     uint32_t margin = margin_start;                                                                           \
     uint32_t b = 0;                                                                                           \
     BB200_PRAGMA_UNROLL(BB200_RW_UNROLL) for (; b + 4 <= (COUNT); b += 4) {                                   \
       const double2 p0 = POINT(b), p1 = POINT(b + 1), p2 = POINT(b + 2), p3 = POINT(b + 3);                   \
-      const double f0 = fixed_lookup(field.bordered, q, p0.x, p0.y, margin);                                  \
-      const double f1 = fixed_lookup(field.bordered, q, p1.x, p1.y, margin);                                  \
-      const double f2 = fixed_lookup(field.bordered, q, p2.x, p2.y, margin);                                  \
-      const double f3 = fixed_lookup(field.bordered, q, p3.x, p3.y, margin);                                  \
+      const double f0 = LOOKUP(TABLE, q, p0.x, p0.y, margin);                                                 \
+      const double f1 = LOOKUP(TABLE, q, p1.x, p1.y, margin);                                                 \
+      const double f2 = LOOKUP(TABLE, q, p2.x, p2.y, margin);                                                 \
+      const double f3 = LOOKUP(TABLE, q, p3.x, p3.y, margin);                                                 \
       acc = acc + ((f0 + f1) + (f2 + f3));                                                                    \
     }                                                                                                         \
     for (; b < (COUNT); ++b) {                                                                                \
       const double2 p0 = POINT(b);                                                                            \
-      acc = acc + fixed_lookup(field.bordered, q, p0.x, p0.y, margin);                                        \
+      acc = acc + LOOKUP(TABLE, q, p0.x, p0.y, margin);                                                       \
     }                                                                                                         \
     if (margin == 0u) { /* a coordinate within 2^-33 cells of a cell edge, or a particle out of range */     \
       const Pose2 te = field_frame_pose(field, states, i, active);                                            \
@@ -621,6 +652,7 @@ __device__ __forceinline__ void fixed_particle_setup(const FieldView& field, con
 /// (CTAs/SM x SM count) and every WARP draws the next 32 particles of the schedule from a global
 /// ticket counter.  A CTA-per-256-particles grid loses 10-13 % to its slowest warp (each CTA holds its
 /// SM slot until the last of its warps is through 1080 beams) and to the partial last wave.
+template <bool kFloatTable>
 __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     reweight_lfm_fixed_param_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
                                     FieldView field, uint32_t n_points, double points_radius, Scalars* __restrict__ scalars,
@@ -641,7 +673,11 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     fixed_particle_setup(field, states, i, active, points_radius, q, margin_start);
     double acc = field.init;
 #define BB200_POINT(k) scan.p[(k)]
-    BB200_FIXED_SUM(BB200_POINT, n_points);
+    if constexpr (kFloatTable) {
+      BB200_FIXED_SUM(BB200_POINT, n_points, fixed_lookup_float, field.bordered_f);
+    } else {
+      BB200_FIXED_SUM(BB200_POINT, n_points, fixed_lookup, field.bordered);
+    }
 #undef BB200_POINT
     if (active) {
       const double likelihood = field.exp_epilogue ? exp(acc) : acc;
@@ -705,7 +741,7 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     mbarrier_wait(&s_bar, phase);
     phase ^= 1u;
 #define BB200_POINT(k) s_pts[(k)]
-    BB200_FIXED_SUM(BB200_POINT, count);
+    BB200_FIXED_SUM(BB200_POINT, count, fixed_lookup, field.bordered);
 #undef BB200_POINT
     if (base + kChunkBeams < n_points) __syncthreads();
   }
@@ -1218,10 +1254,20 @@ __global__ void __launch_bounds__(256) kld_check_kernel(const uint32_t* __restri
                                                         uint64_t slot_base, unsigned long long k_before, unsigned long long min_count,
                                                         double two_epsilon, double z, Scalars* scalars) {
   const uint64_t j = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (j >= n) return;
-  const unsigned long long count = slot_base + j + 1;
-  const unsigned long long k = k_before + exclusive[j] + flags[j];
-  if (!kld_count_allowed(count, k, min_count, two_epsilon, z)) atomicMin(&scalars->kld_cutoff, count);
+  unsigned long long failing = ~0ull;
+  if (j < n) {
+    const unsigned long long count = slot_base + j + 1;
+    const unsigned long long k = k_before + exclusive[j] + flags[j];
+    if (!kld_count_allowed(count, k, min_count, two_epsilon, z)) failing = count;
+  }
+  // Past the cutoff nearly every slot fails: one atomic per warp instead of one per thread on the same word.
+#pragma unroll
+  for (int off = kWarp / 2; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_down_sync(0xffffffffu, failing, off);
+    failing = o < failing ? o : failing;
+  }
+  if (threadIdx.x % kWarp == 0 && failing != ~0ull && failing < *reinterpret_cast<volatile unsigned long long*>(&scalars->kld_cutoff))
+    atomicMin(&scalars->kld_cutoff, failing);
 }
 
 __global__ void kld_reset_kernel(Scalars* scalars) {
@@ -1475,45 +1521,67 @@ __global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleAr
     }
   };
 
-  const uint64_t n_padded = (a.n_in + kWarp - 1) / kWarp * kWarp;  // whole warps stay in the loop for the cooperative stores
-  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kRsThreads + threadIdx.x; i < n_padded; i += static_cast<uint64_t>(gridDim.x) * kRsThreads) {
-    uint64_t ja = 0, jb = 0;
-    if (i < a.n_in) {
-      ja = comb_slots_before_magic(cdf_offset + (i > 0 ? a.cdf[i - 1] : 0ull), offset, stride, magic, a.total_slots);
-      jb = comb_slots_before_magic(cdf_offset + a.cdf[i], offset, stride, magic, a.total_slots);
+  // kRsUnroll particles per thread and round: their CDF reads, divisions and state loads are independent, so one thread keeps
+  // several 32-byte gathers in flight (the kernel is bound by the latency of cdf -> state -> store, not by bandwidth).
+  // Every thread runs the same number of rounds: whole warps stay together for the cooperative stores.
+  constexpr int kRsUnroll = BB200_RS_UNROLL;
+  constexpr uint64_t kOwnCopies = 4;  // up to this many copies a thread stores itself
+  const uint64_t per_round = static_cast<uint64_t>(gridDim.x) * kRsThreads * kRsUnroll;
+  const uint64_t rounds = (a.n_in + per_round - 1) / per_round;
+  for (uint64_t round = 0; round < rounds; ++round) {
+    const uint64_t first = round * per_round + static_cast<uint64_t>(blockIdx.x) * kRsThreads * kRsUnroll + threadIdx.x;
+    uint64_t ja[kRsUnroll], copies[kRsUnroll];
+#pragma unroll
+    for (int u = 0; u < kRsUnroll; ++u) {
+      const uint64_t i = first + static_cast<uint64_t>(u) * kRsThreads;
+      ja[u] = 0;
+      copies[u] = 0;
+      if (i < a.n_in) {
+        ja[u] = comb_slots_before_magic(cdf_offset + (i > 0 ? __ldg(a.cdf + i - 1) : 0ull), offset, stride, magic, a.total_slots);
+        copies[u] = comb_slots_before_magic(cdf_offset + __ldg(a.cdf + i), offset, stride, magic, a.total_slots) - ja[u];
+      }
     }
-    const uint64_t copies = jb - ja;
-    Pose2 st{1.0, 0.0, 0.0, 0.0};
-    if (copies > 0) {
-      st = load_pose(a.states_in + i);
-      const double c = static_cast<double>(copies), dx = st.x - a.pivot_x, dy = st.y - a.pivot_y;
-      m[0] += c;  // every copy has weight 1: sum w = sum w^2 = copies
-      m[1] += c;
-      m[2] += c * st.c;
-      m[3] += c * st.s;
-      m[4] += c * dx;
-      m[5] += c * dy;
-      m[6] += c * (dx * dx);
-      m[7] += c * (dx * dy);
-      m[8] += c * (dy * dy);
+    Pose2 st[kRsUnroll];
+#pragma unroll
+    for (int u = 0; u < kRsUnroll; ++u) {
+      st[u] = Pose2{1.0, 0.0, 0.0, 0.0};
+      if (copies[u] > 0) st[u] = load_pose(a.states_in + first + static_cast<uint64_t>(u) * kRsThreads);
     }
-    constexpr uint64_t kOwnCopies = 4;  // up to this many copies a thread stores itself
-    if (copies <= kOwnCopies) {
-      for (uint64_t j = ja; j < jb; ++j) store_copy(j, st, i);
+#pragma unroll
+    for (int u = 0; u < kRsUnroll; ++u) {
+      const uint64_t i = first + static_cast<uint64_t>(u) * kRsThreads;
+      if (copies[u] > 0) {
+        const double c = static_cast<double>(copies[u]), dx = st[u].x - a.pivot_x, dy = st[u].y - a.pivot_y;
+        m[0] += c;  // every copy has weight 1: sum w = sum w^2 = copies
+        m[1] += c;
+        m[2] += c * st[u].c;
+        m[3] += c * st[u].s;
+        m[4] += c * dx;
+        m[5] += c * dy;
+        m[6] += c * (dx * dx);
+        m[7] += c * (dx * dy);
+        m[8] += c * (dy * dy);
+      }
+      if (copies[u] <= kOwnCopies) {
+        for (uint64_t j = ja[u]; j < ja[u] + copies[u]; ++j) store_copy(j, st[u], i);
+      }
     }
     // Heavy particles: the warp stores their copies together, 32 slots per round.
-    unsigned heavy = __ballot_sync(0xffffffffu, copies > kOwnCopies);
-    while (heavy != 0u) {
-      const int src = __ffs(heavy) - 1;
-      heavy &= heavy - 1u;
-      const uint64_t hja = __shfl_sync(0xffffffffu, ja, src), hjb = __shfl_sync(0xffffffffu, jb, src);
-      const uint64_t hi = __shfl_sync(0xffffffffu, i, src);
-      Pose2 hs;
-      hs.c = __shfl_sync(0xffffffffu, st.c, src);
-      hs.s = __shfl_sync(0xffffffffu, st.s, src);
-      hs.x = __shfl_sync(0xffffffffu, st.x, src);
-      hs.y = __shfl_sync(0xffffffffu, st.y, src);
-      for (uint64_t j = hja + lane; j < hjb; j += kWarp) store_copy(j, hs, hi);
+#pragma unroll
+    for (int u = 0; u < kRsUnroll; ++u) {
+      unsigned heavy = __ballot_sync(0xffffffffu, copies[u] > kOwnCopies);
+      while (heavy != 0u) {
+        const int src = __ffs(heavy) - 1;
+        heavy &= heavy - 1u;
+        const uint64_t hja = __shfl_sync(0xffffffffu, ja[u], src), hcopies = __shfl_sync(0xffffffffu, copies[u], src);
+        const uint64_t hi = __shfl_sync(0xffffffffu, first + static_cast<uint64_t>(u) * kRsThreads, src);
+        Pose2 hs;
+        hs.c = __shfl_sync(0xffffffffu, st[u].c, src);
+        hs.s = __shfl_sync(0xffffffffu, st[u].s, src);
+        hs.x = __shfl_sync(0xffffffffu, st[u].x, src);
+        hs.y = __shfl_sync(0xffffffffu, st[u].y, src);
+        for (uint64_t j = hja + lane; j < hja + hcopies; j += kWarp) store_copy(j, hs, hi);
+      }
     }
   }
   finish_block_moments<kRsThreads>(m, s_red, moment_partials, scalars, a.tail);
@@ -1691,10 +1759,10 @@ void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const Motion
 }
 
 void launch_propagate_binned(Pose2* states, uint64_t n, const MotionSampling& sampling, uint64_t seed, uint32_t step, uint64_t first_index,
-                             const Schedule& grid, uint32_t* bins, uint32_t* counters, cudaStream_t stream) {
+                             const Schedule& grid, uint2* bin_rank, uint32_t* counters, cudaStream_t stream) {
   if (n == 0) return;
   propagate_binned_kernel<<<static_cast<unsigned>((n + kPrThreads - 1) / kPrThreads), kPrThreads, 0, stream>>>(states, n, sampling, seed, step,
-                                                                                                             first_index, grid, bins, counters);
+                                                                                                             first_index, grid, bin_rank, counters);
 }
 
 void launch_begin_fused_step(Scalars* scalars, unsigned long long* tile_state, uint32_t n_tiles, Schedule* sched, uint32_t* counters,
@@ -1720,13 +1788,13 @@ void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uin
   schedule_scatter_kernel<<<blocks, 256, 0, stream>>>(bins, n, counters, perm);
 }
 
-void launch_finish_schedule(const uint32_t* bins, uint64_t n, uint32_t n_bins, Schedule* sched, uint32_t* counters, uint32_t* perm,
+void launch_finish_schedule(const uint2* bin_rank, uint64_t n, uint32_t n_bins, Schedule* sched, uint32_t* counters, uint32_t* perm,
                             unsigned long long* tile_state, cudaStream_t stream) {
   if (n == 0) return;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   const uint32_t tiles = (n_bins + kScanTile - 1) / kScanTile;
   scan_u32_kernel<<<tiles, kScanThreads, 0, stream>>>(counters, counters, n_bins, &sched->tile_ticket, tile_state, nullptr);
-  schedule_scatter_kernel<<<blocks, 256, 0, stream>>>(bins, n, counters, perm);
+  schedule_place_kernel<<<blocks, 256, 0, stream>>>(bin_rank, n, counters, perm);
 }
 
 bool scatter_resample_enabled() {
@@ -1761,7 +1829,11 @@ void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const
       std::memcpy(scan.p, points_xy_host, static_cast<size_t>(n_points) * sizeof(double2));
       const unsigned ctas_needed = static_cast<unsigned>((n + kRwThreads - 1) / kRwThreads);
       const unsigned persistent = std::min<unsigned>(static_cast<unsigned>(sm_count()) * kRwBlocksPerSm, ctas_needed);
-      reweight_lfm_fixed_param_kernel<<<persistent, kRwThreads, 0, stream>>>(states, weights, n, perm, field, n_points, points_radius, scalars, scan);
+      if (field.use_float) {
+        reweight_lfm_fixed_param_kernel<true><<<persistent, kRwThreads, 0, stream>>>(states, weights, n, perm, field, n_points, points_radius, scalars, scan);
+      } else {
+        reweight_lfm_fixed_param_kernel<false><<<persistent, kRwThreads, 0, stream>>>(states, weights, n, perm, field, n_points, points_radius, scalars, scan);
+      }
     } else {
       reweight_lfm_fixed_kernel<<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars);
     }
@@ -1859,7 +1931,8 @@ uint32_t launch_resample(const ResampleArgs& args, Scalars* scalars, double* mom
                                  (args.peer_count > 0 && args.rank_totals != nullptr));
   if (scatter) {
     // one pass over the input particles; a few particles per thread amortise the block reduction of the moments
-    const uint32_t blocks = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>((args.n_in + kRsThreads - 1) / kRsThreads, 148 * 4)));
+    const uint32_t per_sm = BB200_RS_UNROLL >= 4 ? 2 : 3;  // resident CTAs at the kernel's register count
+    const uint32_t blocks = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>((args.n_in + kRsThreads - 1) / kRsThreads, 148 * per_sm)));
     resample_scatter_kernel<<<blocks, kRsThreads, 0, stream>>>(args, scalars, moment_partials);
     return blocks;
   }

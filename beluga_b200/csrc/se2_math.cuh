@@ -98,6 +98,58 @@ BB_HD Pose2 motion_apply(int model, const Pose2& st, double d0, double d1, doubl
   return diff_drive_apply(st, d0, d1, d2);
 }
 
+#if defined(__CUDACC__)
+// ---- device-only variants for the propagate kernel ------------------------------------------------
+// Same quantities as rot_make / rot_exp / rot_mul / pose_mul / box_muller above with fewer FP64 instructions:
+// sqrt(c^2 + s^2) instead of hypot (the arguments are within an ulp of the unit circle: no overflow guard needed),
+// one reciprocal and two multiplications instead of two divisions, sincos / sincospi instead of separate calls.
+// Each substitution moves a result by at most an ulp or two -- the size of the CUDA-vs-glibc libm difference the
+// states carry anyway (tests bound them at 1e-12, the north star at 1e-5); nothing downstream is bit-compared
+// against these values except through the likelihood-field CELL they select.
+__device__ __forceinline__ Rot2 rot_make_fast(double re, double im) {
+  const double inv = 1.0 / sqrt(re * re + im * im);
+  return Rot2{re * inv, im * inv};
+}
+__device__ __forceinline__ Rot2 rot_exp_fast(double theta) {
+  double sn, cs;
+  sincos(theta, &sn, &cs);
+  return rot_make_fast(cs, sn);
+}
+__device__ __forceinline__ Rot2 rot_mul_fast(const Rot2& a, const Rot2& b) {
+  double re = a.c * b.c - a.s * b.s;
+  double im = a.c * b.s + a.s * b.c;
+  const double sq = re * re + im * im;
+  if (sq != 1.0) {
+    const double scale = 2.0 / (1.0 + sq);
+    re = re * scale;
+    im = im * scale;
+  }
+  return rot_make_fast(re, im);
+}
+__device__ __forceinline__ Pose2 pose_mul_fast(const Pose2& a, const Pose2& b) {
+  const Rot2 r = rot_mul_fast(Rot2{a.c, a.s}, Rot2{b.c, b.s});
+  const double rx = a.c * b.x - a.s * b.y;
+  const double ry = a.s * b.x + a.c * b.y;
+  return Pose2{r.c, r.s, a.x + rx, a.y + ry};
+}
+__device__ __forceinline__ Pose2 motion_apply_fast(int model, const Pose2& st, double d0, double d1, double d2, const Rot2& first) {
+  if (model == 1) {
+    const Rot2 e = rot_exp_fast(d0);
+    const Rot2 second = rot_mul_fast(e, rot_make_fast(first.c, -first.s));
+    const Pose2 a = pose_mul_fast(st, Pose2{first.c, first.s, 0.0, 0.0});
+    return pose_mul_fast(a, Pose2{second.c, second.s, d1, -d2});
+  }
+  if (model == 2) {
+    const Rot2 r = rot_exp_fast(d0);
+    return pose_mul_fast(st, Pose2{r.c, r.s, d1, d2});
+  }
+  const Rot2 r1 = rot_exp_fast(d0);
+  const Rot2 r2 = rot_exp_fast(d2);
+  const Pose2 a = pose_mul_fast(st, Pose2{r1.c, r1.s, 0.0, 0.0});
+  return pose_mul_fast(a, Pose2{r2.c, r2.s, d1, 0.0});
+}
+#endif
+
 // ---- counter RNG -------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11).
 // Counter = (index lo, index hi, step, stream); key = seed.  A draw yields two 64-bit words.
@@ -158,6 +210,21 @@ BB_HD void box_muller(const Draw& d, double& z0, double& z1) {
   z0 = radius * cos(angle);
   z1 = radius * sin(angle);
 }
+
+#if defined(__CUDACC__)
+/// box_muller with the angle's range reduction done exactly (sincospi of 2u instead of sin/cos of the rounded 2 pi u).
+__device__ __forceinline__ void box_muller_fast(const Draw& d, double& z0, double& z1) {
+  const double radius = sqrt(-2.0 * log(uniform01(d.a)));
+  double sn, cs;
+  sincospi(2.0 * uniform01(d.b), &sn, &cs);
+  z0 = radius * cs;
+  z1 = radius * sn;
+}
+/// Only the first normal of the pair.
+__device__ __forceinline__ double box_muller_first(const Draw& d) {
+  return sqrt(-2.0 * log(uniform01(d.a))) * cospi(2.0 * uniform01(d.b));
+}
+#endif
 
 // ---- spatial hash (algorithm/spatial_hash.hpp:45-94,190-193) ------------------------------------
 BB_HD uint64_t floor_and_fibo_hash(double value, unsigned shift) {
