@@ -112,7 +112,6 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   if (const char* v = std::getenv("BB200_BEAM_ETA_TABLE")) beam_eta_table_ = std::atoi(v) != 0;  // development knob: tabulated beam normalisers
   if (const char* v = std::getenv("BB200_FIXED")) fixed_lookup_ = std::atoi(v) != 0;         // development knob: fixed-point lookup kernel
   if (const char* v = std::getenv("BB200_PREDICT_SCHEDULE")) predict_schedule_ = std::atoi(v) != 0;  // development knob: host-predicted pose bins
-  if (const char* v = std::getenv("BB200_FLOAT_TABLE")) float_table_ = std::atoi(v) != 0;    // development knob: 4-byte likelihood table
   if (const char* v = std::getenv("BB200_PER_BIN")) schedule_per_bin_ = std::atof(v);        // development knob: particles per pose bin
   if (const char* v = std::getenv("BB200_LEVER")) schedule_lever_ = std::atof(v);            // development knob: heading lever arm / mean range
   capacity_ = config.capacity;
@@ -207,7 +206,6 @@ Filter::~Filter() {
   cudaFree(table_);
   cudaFree(tiled_);
   cudaFree(bordered_);
-  cudaFree(bordered_f_);
   cudaFree(beam_eta_);
   cudaFree(occupancy_);
   cudaFree(free_distance_);
@@ -848,8 +846,6 @@ int Filter::set_likelihood_field_map(const bb200_likelihood_field_param& p, cons
   BB_CHECK(cudaStreamSynchronize(stream_));
   // Bordered tile layout for the fixed-point kernel.
   field_.use_fixed = 0;
-  field_.use_float = 0;
-  field_.bordered_f = nullptr;
   field_.bordered = nullptr;
   cudaFree(bordered_);
   bordered_ = nullptr;
@@ -864,24 +860,6 @@ int Filter::set_likelihood_field_map(const bb200_likelihood_field_param& p, cons
     BB_CHECK(dev_alloc(&bordered_, bordered.size()));
     BB_CHECK(cudaMemcpyAsync(bordered_, bordered.data(), bordered.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
     BB_CHECK(cudaStreamSynchronize(stream_));
-    // the float copy for LikelihoodFieldModel (1 + sum pz^3): same border, 4 x 8-cell tiles
-    field_.bordered_f = nullptr;
-    field_.use_float = 0;
-    cudaFree(bordered_f_);
-    bordered_f_ = nullptr;
-    if (float_table_ && !prob) {
-      const size_t tile_rows8 = static_cast<size_t>((g.height + 2 + 7) / 8);
-      const float unknown_f = static_cast<float>(1. / p.max_laser_distance);
-      std::vector<float> bordered_f((tile_rows8 << (kx + 5)), unknown_f);
-      for (int yi = 0; yi < g.height; ++yi)
-        for (int xi = 0; xi < g.width; ++xi)
-          bordered_f[bordered_index_float(static_cast<uint32_t>(xi + 1), static_cast<uint32_t>(yi + 1), kx)] = field_host_[static_cast<size_t>(yi) * g.width + xi];
-      BB_CHECK(dev_alloc(&bordered_f_, bordered_f.size()));
-      BB_CHECK(cudaMemcpyAsync(bordered_f_, bordered_f.data(), bordered_f.size() * sizeof(float), cudaMemcpyHostToDevice, stream_));
-      BB_CHECK(cudaStreamSynchronize(stream_));
-      field_.bordered_f = bordered_f_;
-      field_.use_float = 1;
-    }
     field_.bordered = bordered_;
     field_.border_kx = kx;
     field_.border_pitch = 1u << kx;
@@ -1105,11 +1083,11 @@ int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t 
   if (scheduled && counters_reset && sampling != nullptr && predict_schedule(*sampling, &grid)) {
     // Bin grid predicted on the host: propagate histograms its own output, two more launches turn it into the order.
     mark("propagate");
-    launch_propagate_binned(states_[cur_], n_, *sampling, config_.seed, step, config_.first_index, grid, bin_rank_, counters_, stream_);
+    launch_propagate_binned(states_[cur_], n_, *sampling, config_.seed, step, config_.first_index, grid, bin_rank_, counters_, sched_, stream_);
     BB_LAUNCHED("propagate");
     mark("schedule");
     launch_finish_schedule(bin_rank_, n_, grid.n_bins, sched_, counters_, perm_, sched_tiles_, stream_);
-    BB_LAUNCHED_N("schedule", 2);
+    BB_LAUNCHED("schedule");
     perm = perm_;
   } else if (sampling != nullptr || scheduled) {
     mark("propagate");

@@ -230,8 +230,6 @@ class Filter {
   double* table_{nullptr};
   double* tiled_{nullptr};
   double* bordered_{nullptr};
-  float* bordered_f_{nullptr};
-  bool float_table_{true};
   FieldView field_{};
   int8_t* occupancy_{nullptr};
   uint8_t* free_distance_{nullptr};

@@ -336,16 +336,71 @@ __device__ __forceinline__ uint32_t schedule_bin(const Schedule& g, const Pose2&
 /// propagate with the histogram of the execution schedule fused in (the bin grid comes from the host's prediction).
 __global__ void __launch_bounds__(kPrThreads) propagate_binned_kernel(Pose2* __restrict__ states, uint64_t n, MotionSampling sampling, uint64_t seed,
                                                                       uint32_t step, uint64_t first_index, Schedule grid,
-                                                                      uint2* __restrict__ bin_rank, uint32_t* __restrict__ counters) {
+                                                                      uint2* __restrict__ bin_rank, uint32_t* __restrict__ counters,
+                                                                      Schedule* __restrict__ sched) {
+  __shared__ uint32_t s_scan[kPrThreads / kWarp];
+  __shared__ int s_last;
   const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kPrThreads + threadIdx.x;
-  if (i >= n) return;
-  const Pose2 st = propagate_one(load_pose(states + i), sampling, seed, first_index + i, step);
-  store_pose(states + i, st);
-  const uint32_t b = schedule_bin(grid, st);
-  // The particle's arrival rank inside its bin: the scatter pass then needs no second round of atomics.  (Which
-  // particle gets which rank varies from run to run; it only permutes the execution order inside a bin.)
-  const uint32_t rank = atomicAdd(counters + b, 1u);
-  bin_rank[i] = make_uint2(b, rank);
+  if (i < n) {
+    const Pose2 st = propagate_one(load_pose(states + i), sampling, seed, first_index + i, step);
+    store_pose(states + i, st);
+    const uint32_t b = schedule_bin(grid, st);
+    // The particle's arrival rank inside its bin: the scatter pass then needs no second round of atomics.  (Which
+    // particle gets which rank varies from run to run; it only permutes the execution order inside a bin.)
+    const uint32_t rank = atomicAdd(counters + b, 1u);
+    bin_rank[i] = make_uint2(b, rank);
+  }
+  // The last block to finish turns the counters into bin offsets (exclusive prefix sum, 64 k values at most on one
+  // SM: a few microseconds, and one launch with its ticket / look-back machinery less).
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&sched->tile_ticket, 1ull) + 1ull == gridDim.x ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const uint32_t n_bins = grid.n_bins;
+  const uint32_t per_thread = ((n_bins + kPrThreads - 1) / kPrThreads + 3u) & ~3u;  // consecutive counters per thread, whole uint4s
+  const uint32_t begin = threadIdx.x * per_thread;
+  uint32_t sum = 0;
+  for (uint32_t k = begin; k < begin + per_thread && k < n_bins; k += 4) {
+    const uint4 c = __ldcg(reinterpret_cast<const uint4*>(counters + k));  // counters are padded to a multiple of 4 and zeroed
+    sum += c.x + c.y + c.z + c.w;
+  }
+  // block-wide exclusive scan of the per-thread sums
+  const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
+  uint32_t inc = sum;
+#pragma unroll
+  for (int off = 1; off < kWarp; off <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += o;
+  }
+  if (lane == kWarp - 1) s_scan[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t ws = lane < kPrThreads / kWarp ? s_scan[lane] : 0u;
+#pragma unroll
+    for (int off = 1; off < kWarp; off <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, ws, off);
+      if (lane >= off) ws += o;
+    }
+    if (lane < kPrThreads / kWarp) s_scan[lane] = ws;
+  }
+  __syncthreads();
+  uint32_t running = inc - sum + (warp > 0 ? s_scan[warp - 1] : 0u);
+  for (uint32_t k = begin; k < begin + per_thread && k < n_bins; k += 4) {
+    uint4* p = reinterpret_cast<uint4*>(counters + k);
+    const uint4 c = __ldcg(p);
+    uint4 e;
+    e.x = running;
+    e.y = e.x + c.x;
+    e.z = e.y + c.y;
+    e.w = e.z + c.z;
+    running = e.w + c.w;
+    *p = e;
+  }
+  if (threadIdx.x == 0) sched->tile_ticket = 0;
 }
 
 __global__ void __launch_bounds__(256) schedule_place_kernel(const uint2* __restrict__ bin_rank, uint64_t n, const uint32_t* __restrict__ offsets,
@@ -553,24 +608,6 @@ __device__ __forceinline__ double fixed_lookup(const double* __restrict__ border
   return __ldg(bordered + idx);
 }
 
-/// The same against the FLOAT table (likelihood field values as the reference stores them, 4 bytes per cell) in
-/// 4 x 8-cell tiles: a 128-byte line then covers 32 cells instead of 16, so the 32 end points of a warp touch about
-/// a third fewer lines (the kernel's busiest unit is the L1 data pipe, one wavefront per line touched).  The cube is
-/// taken per lookup, (double(pz) * double(pz)) * double(pz) -- the very expression the 8-byte table tabulates -- at
-/// the price of one conversion and two multiplications on the half-idle FP64 pipe.  y's magic constant yields
-/// floor(4 g): (uy & ~31) is 32 x the tile row and (uy & 28) the row inside the tile times 4.
-__device__ __forceinline__ double fixed_lookup_float(const float* __restrict__ table, const FixedParticle& q, double px, double py, uint32_t& margin) {
-  const double gx = fma(px, q.cx, fma(-py, q.sx, q.ox)) + kFixedMagicX;
-  const double gy = fma(px, q.sx, fma(py, q.cx, q.oy)) + kFixedMagicY;
-  margin = __vimin3_u32(margin, static_cast<uint32_t>(__double2loint(gx)), static_cast<uint32_t>(__double2loint(gy)));
-  const uint32_t ux = __viaddmin_u32(static_cast<uint32_t>(__double2hiint(gx)), 0u - kFixedBiasX, q.x_max);
-  const uint32_t uy = __viaddmin_u32(static_cast<uint32_t>(__double2hiint(gy)), 0u - kFixedBiasY, q.y_max);
-  const uint32_t a = ux + 7u * (ux & ~3u);  // (x & 3) | ((x >> 2) << 5)
-  const uint32_t idx = __umul24(uy & ~0x1Fu, q.row_pitch) + (a | (uy & 0x1Cu));
-  const double pz = static_cast<double>(__ldg(table + idx));
-  return (pz * pz) * pz;
-}
-
 /// The reference's operation sequence (field_lookup) against the bordered layout.
 __device__ __forceinline__ double bordered_lookup_exact(const FieldView& f, double px, double py, double c, double s, double tx, double ty) {
   const double x = (px * c - py * s) + tx;
@@ -652,7 +689,6 @@ __device__ __forceinline__ void fixed_particle_setup(const FieldView& field, con
 /// (CTAs/SM x SM count) and every WARP draws the next 32 particles of the schedule from a global
 /// ticket counter.  A CTA-per-256-particles grid loses 10-13 % to its slowest warp (each CTA holds its
 /// SM slot until the last of its warps is through 1080 beams) and to the partial last wave.
-template <bool kFloatTable>
 __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     reweight_lfm_fixed_param_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, const uint32_t* __restrict__ perm,
                                     FieldView field, uint32_t n_points, double points_radius, Scalars* __restrict__ scalars,
@@ -673,11 +709,7 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
     fixed_particle_setup(field, states, i, active, points_radius, q, margin_start);
     double acc = field.init;
 #define BB200_POINT(k) scan.p[(k)]
-    if constexpr (kFloatTable) {
-      BB200_FIXED_SUM(BB200_POINT, n_points, fixed_lookup_float, field.bordered_f);
-    } else {
-      BB200_FIXED_SUM(BB200_POINT, n_points, fixed_lookup, field.bordered);
-    }
+    BB200_FIXED_SUM(BB200_POINT, n_points, fixed_lookup, field.bordered);
 #undef BB200_POINT
     if (active) {
       const double likelihood = field.exp_epilogue ? exp(acc) : acc;
@@ -773,9 +805,21 @@ __device__ __forceinline__ int cell_near(double p, double inv_resolution) {
   return max(-(1 << 28), min(1 << 28, __double2int_rd(p * inv_resolution)));
 }
 
-/// Distance in metres from the source cell centroid to the first non-free cell, or -1 on a miss;
-/// d2 = squared cell distance of that cell (only meaningful on a hit).
-__device__ __forceinline__ double cast_ray(const OccupancyView& g, int sx, int sy, int fx, int fy, double max_range, unsigned long long& d2) {
+/// One ray of Ray2d::cast (raycasting.hpp:79-107) over the standard Bresenham2i iterator (bresenham.hpp:84-160) as a
+/// state machine, so that a thread can keep several rays in flight (ray_step is one dependent load of the
+/// free-distance map plus a closed-form advance of the iterator; the walk is bound by that load's latency).
+struct RayWalk {
+  int x, y;            // iterator position: x along the longer axis (swapped when `reversed`)
+  int xstep, ystep;
+  int xspan, dxspan, dyspan;
+  int error, step;
+  uint32_t recip;      // floor((2^32 - 1) / dxspan): quotients below 2^8 come out exact or one low
+  bool reversed, small_span, active;
+  int hit_x, hit_y;    // cell of the first non-free cell (valid when hit)
+  bool hit;
+};
+
+__device__ __forceinline__ void ray_begin(RayWalk& w, int sx, int sy, int fx, int fy) {
   int xspan = fx - sx, xstep = 1;
   if (xspan < 0) {
     xspan = -xspan;
@@ -786,53 +830,80 @@ __device__ __forceinline__ double cast_ray(const OccupancyView& g, int sx, int s
     yspan = -yspan;
     ystep = -1;
   }
-  int x = sx, y = sy;
-  bool reversed = false;
+  w.x = sx, w.y = sy;
+  w.reversed = false;
   if (xspan < yspan) {  // iterate along the longer axis (bresenham.hpp:99-105)
-    int t = x; x = y; y = t;
+    int t = w.x; w.x = w.y; w.y = t;
     t = xspan; xspan = yspan; yspan = t;
     t = xstep; xstep = ystep; ystep = t;
-    reversed = true;
+    w.reversed = true;
   }
-  const int dxspan = 2 * xspan, dyspan = 2 * yspan;
-  const bool small_span = xspan < (1 << 22);  // then error + 255 * dyspan stays below 2^31
-  const double inv_dxspan = 1.0 / static_cast<double>(dxspan);
-  int error = xspan;
-  int step = 0;
-  for (;;) {
-    const int cx = reversed ? y : x, cy = reversed ? x : y;
-    if (!(static_cast<unsigned>(cx) < static_cast<unsigned>(g.width) && static_cast<unsigned>(cy) < static_cast<unsigned>(g.height)))
-      return -1.0;  // take_while(cell_is_valid), raycasting.hpp:86-87
-    const int d = __ldg(g.free_distance + (static_cast<size_t>(cy) * static_cast<size_t>(g.width) + static_cast<size_t>(cx)));
-    if (d == 0) {  // !free_at: first non-free cell on the line
-      const double dxm = (static_cast<double>(cx) + 0.5) * g.resolution - (static_cast<double>(sx) + 0.5) * g.resolution;
-      const double dym = (static_cast<double>(cy) + 0.5) * g.resolution - (static_cast<double>(sy) + 0.5) * g.resolution;
-      const long long ix = static_cast<long long>(cx) - sx, iy = static_cast<long long>(cy) - sy;
-      d2 = static_cast<unsigned long long>(ix * ix + iy * iy);
-      return fmin(sqrt(dxm * dxm + dym * dym), max_range);
-    }
-    // Every cell within Chebyshev distance d - 1 is free and the line moves at most one cell per step
-    // in each axis, so the next d - 1 cells cannot stop the ray: advance d steps of the iterator
-    // (bresenham.hpp:122-160, standard variant) in closed form.  error stays in (0, dxspan].
-    const int k = min(d, xspan - step);
-    if (k == 0) return -1.0;  // the far end cell was free too: sentinel reached (bresenham.hpp:179)
-    step += k;
-    x += k * xstep;
-    const long long t = static_cast<long long>(error) + static_cast<long long>(k) * dyspan;
-    int m;  // floor((t - 1) / dxspan)
-    if (small_span) {
-      // t - 1 < 2^31 here: the product with the rounded reciprocal is within one of the quotient; one
-      // correction step makes it exact (a 64-bit integer division costs more than the rest of the loop).
-      const long long tm1 = t - 1;
-      m = __double2int_rd(static_cast<double>(tm1) * inv_dxspan);
-      const long long r = tm1 - static_cast<long long>(m) * dxspan;
-      m += r >= dxspan ? 1 : (r < 0 ? -1 : 0);
-    } else {
-      m = static_cast<int>((t - 1) / dxspan);
-    }
-    y += m * ystep;
-    error = static_cast<int>(t - static_cast<long long>(m) * dxspan);
+  w.xstep = xstep, w.ystep = ystep;
+  w.xspan = xspan, w.dxspan = 2 * xspan, w.dyspan = 2 * yspan;
+  w.small_span = xspan < (1 << 22);  // then error + 255 * dyspan stays below 2^32
+  w.recip = xspan > 0 ? 0xFFFFFFFFu / static_cast<uint32_t>(w.dxspan) : 0u;
+  w.error = xspan;
+  w.step = 0;
+  w.active = true;
+  w.hit = false;
+  w.hit_x = w.hit_y = 0;
+}
+
+/// One iteration: inspect the current cell, then jump as far as the free-distance map allows.
+__device__ __forceinline__ void ray_step(RayWalk& w, const OccupancyView& g) {
+  const int cx = w.reversed ? w.y : w.x, cy = w.reversed ? w.x : w.y;
+  if (!(static_cast<unsigned>(cx) < static_cast<unsigned>(g.width) && static_cast<unsigned>(cy) < static_cast<unsigned>(g.height))) {
+    w.active = false;  // take_while(cell_is_valid), raycasting.hpp:86-87: a miss
+    return;
   }
+  const int d = __ldg(g.free_distance + (static_cast<size_t>(cy) * static_cast<size_t>(g.width) + static_cast<size_t>(cx)));
+  if (d == 0) {  // !free_at: first non-free cell on the line
+    w.hit = true;
+    w.hit_x = cx, w.hit_y = cy;
+    w.active = false;
+    return;
+  }
+  // Every cell within Chebyshev distance d - 1 is free and the line moves at most one cell per step in each axis,
+  // so the next d - 1 cells cannot stop the ray: advance d steps of the iterator (bresenham.hpp:122-160, standard
+  // variant) in closed form.  error stays in (0, dxspan].
+  const int k = min(d, w.xspan - w.step);
+  if (k == 0) {  // the far end cell was free too: sentinel reached (bresenham.hpp:179)
+    w.active = false;
+    return;
+  }
+  w.step += k;
+  w.x += k * w.xstep;
+  int m;  // floor((t - 1) / dxspan) with t = error + k * dyspan
+  if (w.small_span) {
+    // 32-bit: t - 1 < 2^32 and the quotient is at most k <= 255, so the high word of (t - 1) * floor((2^32 - 1) / dxspan)
+    // is the quotient or one below it; one remainder check makes it exact.  (A 64-bit division costs more than the
+    // rest of the loop; an FP64 reciprocal needs two conversions on the quarter-rate pipe.)
+    const uint32_t tm1 = static_cast<uint32_t>(w.error) + static_cast<uint32_t>(k) * static_cast<uint32_t>(w.dyspan) - 1u;
+    uint32_t q = __umulhi(tm1, w.recip);
+    uint32_t r = tm1 - q * static_cast<uint32_t>(w.dxspan);
+    if (r >= static_cast<uint32_t>(w.dxspan)) {
+      ++q;
+      r -= static_cast<uint32_t>(w.dxspan);
+    }
+    m = static_cast<int>(q);
+    w.error = static_cast<int>(r) + 1;  // t - m * dxspan
+  } else {
+    const long long t = static_cast<long long>(w.error) + static_cast<long long>(k) * w.dyspan;
+    m = static_cast<int>((t - 1) / w.dxspan);
+    w.error = static_cast<int>(t - static_cast<long long>(m) * w.dxspan);
+  }
+  w.y += m * w.ystep;
+}
+
+/// Distance in metres from the source cell centroid to the ray's hit cell (clamped to max_range), or -1 on a miss;
+/// d2 = squared cell distance of that cell (only meaningful on a hit).
+__device__ __forceinline__ double ray_result(const RayWalk& w, const OccupancyView& g, int sx, int sy, double max_range, unsigned long long& d2) {
+  if (!w.hit) return -1.0;
+  const double dxm = (static_cast<double>(w.hit_x) + 0.5) * g.resolution - (static_cast<double>(sx) + 0.5) * g.resolution;
+  const double dym = (static_cast<double>(w.hit_y) + 0.5) * g.resolution - (static_cast<double>(sy) + 0.5) * g.resolution;
+  const long long ix = static_cast<long long>(w.hit_x) - sx, iy = static_cast<long long>(w.hit_y) - sy;
+  d2 = static_cast<unsigned long long>(ix * ix + iy * iy);
+  return fmin(sqrt(dxm * dxm + dym * dym), max_range);
 }
 
 /// beam_model.hpp:128-135: the two normalisers as functions of z_mean.
@@ -866,6 +937,10 @@ __global__ void __launch_bounds__(256) beam_eta_table_kernel(BeamParams p, doubl
 #ifndef BB200_BEAM_BLOCKS
 #define BB200_BEAM_BLOCKS 3
 #endif
+#ifndef BB200_BEAM_RAYS
+#define BB200_BEAM_RAYS 2  // rays a thread walks together (1, 2 or 4)
+#endif
+constexpr int kBeamRays = BB200_BEAM_RAYS;
 constexpr int kBeamThreads = 256;
 constexpr int kBeamBlocksPerSm = BB200_BEAM_BLOCKS;
 constexpr uint32_t kBeamChunk = 1024;  // rays staged per shared-memory chunk (32 KB), multiple of 4
@@ -891,13 +966,10 @@ __global__ void __launch_bounds__(kBeamThreads, kBeamBlocksPerSm)
   const int sx = cell_near(src.x, grid.inv_resolution), sy = cell_near(src.y, grid.inv_resolution);
   const double n_norm = 1. / (sqrt(2. * 3.14159265358979323846) * params.sigma_hit);  // beam_model.hpp:107
 
-  auto one_beam = [&](const BeamRay& ray) {
-    // far end = r1 * t2 + t1 (raycasting.hpp:81-85)
-    const double ex = (src.c * ray.far_x - src.s * ray.far_y) + src.x;
-    const double ey = (src.s * ray.far_x + src.c * ray.far_y) + src.y;
-    const int fx = cell_near(ex, grid.inv_resolution), fy = cell_near(ey, grid.inv_resolution);
+  // The mixture value of one beam given its ray walk (beam_model.hpp:116-147).
+  auto beam_value = [&](const BeamRay& ray, const RayWalk& walk) {
     unsigned long long d2 = 0;
-    const double hit = cast_ray(grid, sx, sy, fx, fy, params.beam_max_range, d2);
+    const double hit = ray_result(walk, grid, sx, sy, params.beam_max_range, d2);
     const double z_mean = hit >= 0.0 ? hit : params.beam_max_range;  // value_or(beam_max_range)
     double2 eta;
     if (params.eta != nullptr) {
@@ -908,6 +980,12 @@ __global__ void __launch_bounds__(kBeamThreads, kBeamBlocksPerSm)
       eta = beam_normalisers(params, z_mean);
     }
     return beam_pz3(params, ray.z, ray.short_decay, z_mean, n_norm, eta.x, eta.y);
+  };
+  auto begin_walk = [&](RayWalk& walk, const BeamRay& ray) {
+    // far end = r1 * t2 + t1 (raycasting.hpp:81-85)
+    const double ex = (src.c * ray.far_x - src.s * ray.far_y) + src.x;
+    const double ey = (src.s * ray.far_x + src.c * ray.far_y) + src.y;
+    ray_begin(walk, sx, sy, cell_near(ex, grid.inv_resolution), cell_near(ey, grid.inv_resolution));
   };
 
   double acc = 0.0;
@@ -924,10 +1002,34 @@ __global__ void __launch_bounds__(kBeamThreads, kBeamBlocksPerSm)
     if (active) {
       uint32_t b = 0;
       for (; b + 4 <= count; b += 4) {  // transform_reduce grouping (numeric:439-462)
-        const double f0 = one_beam(s_rays[b]), f1 = one_beam(s_rays[b + 1]), f2 = one_beam(s_rays[b + 2]), f3 = one_beam(s_rays[b + 3]);
-        acc = acc + ((f0 + f1) + (f2 + f3));
+        // The four rays of a group are walked together: their free-distance loads are independent, so the thread
+        // keeps kBeamRays of them in flight instead of waiting out one dependent chain after the other.
+        double f[4];
+#pragma unroll
+        for (int g0 = 0; g0 < 4; g0 += kBeamRays) {
+          RayWalk walk[kBeamRays];
+#pragma unroll
+          for (int r = 0; r < kBeamRays; ++r) begin_walk(walk[r], s_rays[b + g0 + r]);
+          bool any = true;
+          while (any) {
+            any = false;
+#pragma unroll
+            for (int r = 0; r < kBeamRays; ++r) {
+              if (walk[r].active) ray_step(walk[r], grid);
+              any |= walk[r].active;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < kBeamRays; ++r) f[g0 + r] = beam_value(s_rays[b + g0 + r], walk[r]);
+        }
+        acc = acc + ((f[0] + f[1]) + (f[2] + f[3]));
       }
-      for (; b < count; ++b) acc = acc + one_beam(s_rays[b]);
+      for (; b < count; ++b) {
+        RayWalk walk;
+        begin_walk(walk, s_rays[b]);
+        while (walk.active) ray_step(walk, grid);
+        acc = acc + beam_value(s_rays[b], walk);
+      }
     }
   }
   if (active) {
@@ -1069,8 +1171,9 @@ __device__ __forceinline__ unsigned long long lookback_exclusive_prefix(unsigned
 // 16-byte accesses).  The quantisation is a multiplication by 2^e (exact, like scalbn, wherever the result is >= 1),
 // split into two power-of-two factors so that each stays a normal double for any exponent.
 constexpr int kQsThreads = 256;
-constexpr int kQsItems = 8;
-constexpr uint32_t kQsTile = kQsThreads * kQsItems;
+constexpr int kQsItemsSmall = 8;   // up to a few million weights: more tiles than SM slots, shortest chain
+constexpr int kQsItemsLarge = 16;  // beyond: half the tiles (look-back words, barriers) per byte
+constexpr uint32_t kQsTile = kQsThreads * kQsItemsSmall;  // the smaller tile sizes the look-back state
 
 __device__ __forceinline__ double pow2_double(int e) {  // |e| <= 1000
   return __longlong_as_double(static_cast<long long>(e + 1023) << 52);
@@ -1082,6 +1185,7 @@ __device__ __forceinline__ unsigned long long quantize_mul(double w, double f1, 
 
 /// derive_exponent: the fused step -- the exponent comes from scalars->wmax_bits here (no prepare_cdf launch; the
 /// tile holding element 0 publishes exponent / valid for the host); otherwise scalars->exponent / valid are given.
+template <int kQsItems>
 __global__ void __launch_bounds__(kQsThreads) quantize_scan_kernel(const double* __restrict__ weights, uint64_t n,
                                                                    unsigned long long* __restrict__ cdf, Scalars* scalars,
                                                                    unsigned long long* tile_state, int derive_exponent, int ceil_log2_count) {
@@ -1119,7 +1223,7 @@ __global__ void __launch_bounds__(kQsThreads) quantize_scan_kernel(const double*
   const double f1 = s_factor[0], f2 = s_factor[1];
   const bool valid = s_valid != 0;
 
-  const uint64_t base = static_cast<uint64_t>(tile) * kQsTile + static_cast<uint64_t>(threadIdx.x) * kQsItems;
+  const uint64_t base = static_cast<uint64_t>(tile) * (kQsThreads * kQsItems) + static_cast<uint64_t>(threadIdx.x) * kQsItems;
   unsigned long long q[kQsItems];
   unsigned long long local = 0;
   if (base + kQsItems <= n) {
@@ -1359,14 +1463,20 @@ __device__ __forceinline__ void finish_block_moments(double* m, double* scratch,
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-#pragma unroll 1
-  for (int k = 0; k < kMomentCount; ++k) {
-    double v = 0.0;
-    for (uint32_t r = threadIdx.x; r < gridDim.x; r += kThreads) v = v + __ldcg(moment_partials + static_cast<size_t>(r) * kMomentCount + k);
-    const double total = block_sum<kThreads>(v, scratch);
-    if (threadIdx.x == 0) {
-      tail.results[k] = total;
-      if (tail.summary != nullptr) tail.summary->moments[k] = total;
+  double v[kMomentCount];
+#pragma unroll
+  for (int k = 0; k < kMomentCount; ++k) v[k] = 0.0;
+  for (uint32_t r = threadIdx.x; r < gridDim.x; r += kThreads) {
+    const double* row = moment_partials + static_cast<size_t>(r) * kMomentCount;
+#pragma unroll
+    for (int k = 0; k < kMomentCount; ++k) v[k] = v[k] + __ldcg(row + k);  // nine independent loads per row
+  }
+  block_sum_many<kThreads, kMomentCount>(v, scratch);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < kMomentCount; ++k) {
+      tail.results[k] = v[k];
+      if (tail.summary != nullptr) tail.summary->moments[k] = v[k];
     }
   }
   if (threadIdx.x == 0) {
@@ -1759,10 +1869,10 @@ void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const Motion
 }
 
 void launch_propagate_binned(Pose2* states, uint64_t n, const MotionSampling& sampling, uint64_t seed, uint32_t step, uint64_t first_index,
-                             const Schedule& grid, uint2* bin_rank, uint32_t* counters, cudaStream_t stream) {
+                             const Schedule& grid, uint2* bin_rank, uint32_t* counters, Schedule* sched, cudaStream_t stream) {
   if (n == 0) return;
-  propagate_binned_kernel<<<static_cast<unsigned>((n + kPrThreads - 1) / kPrThreads), kPrThreads, 0, stream>>>(states, n, sampling, seed, step,
-                                                                                                             first_index, grid, bin_rank, counters);
+  propagate_binned_kernel<<<static_cast<unsigned>((n + kPrThreads - 1) / kPrThreads), kPrThreads, 0, stream>>>(
+      states, n, sampling, seed, step, first_index, grid, bin_rank, counters, sched);
 }
 
 void launch_begin_fused_step(Scalars* scalars, unsigned long long* tile_state, uint32_t n_tiles, Schedule* sched, uint32_t* counters,
@@ -1791,9 +1901,8 @@ void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uin
 void launch_finish_schedule(const uint2* bin_rank, uint64_t n, uint32_t n_bins, Schedule* sched, uint32_t* counters, uint32_t* perm,
                             unsigned long long* tile_state, cudaStream_t stream) {
   if (n == 0) return;
+  (void)n_bins, (void)sched, (void)tile_state;  // the counters were scanned by the last block of propagate_binned_kernel
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-  const uint32_t tiles = (n_bins + kScanTile - 1) / kScanTile;
-  scan_u32_kernel<<<tiles, kScanThreads, 0, stream>>>(counters, counters, n_bins, &sched->tile_ticket, tile_state, nullptr);
   schedule_place_kernel<<<blocks, 256, 0, stream>>>(bin_rank, n, counters, perm);
 }
 
@@ -1829,11 +1938,7 @@ void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const
       std::memcpy(scan.p, points_xy_host, static_cast<size_t>(n_points) * sizeof(double2));
       const unsigned ctas_needed = static_cast<unsigned>((n + kRwThreads - 1) / kRwThreads);
       const unsigned persistent = std::min<unsigned>(static_cast<unsigned>(sm_count()) * kRwBlocksPerSm, ctas_needed);
-      if (field.use_float) {
-        reweight_lfm_fixed_param_kernel<true><<<persistent, kRwThreads, 0, stream>>>(states, weights, n, perm, field, n_points, points_radius, scalars, scan);
-      } else {
-        reweight_lfm_fixed_param_kernel<false><<<persistent, kRwThreads, 0, stream>>>(states, weights, n, perm, field, n_points, points_radius, scalars, scan);
-      }
+      reweight_lfm_fixed_param_kernel<<<persistent, kRwThreads, 0, stream>>>(states, weights, n, perm, field, n_points, points_radius, scalars, scan);
     } else {
       reweight_lfm_fixed_kernel<<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars);
     }
@@ -1880,8 +1985,14 @@ void launch_prepare_cdf(Scalars* scalars, double host_wmax, uint64_t global_coun
 void launch_quantize_scan(const double* weights, uint64_t n, unsigned long long* cdf, Scalars* scalars, unsigned long long* tile_state,
                           cudaStream_t stream, bool derive_exponent, uint64_t global_count) {
   if (n == 0) return;
-  quantize_scan_kernel<<<static_cast<unsigned>((n + kQsTile - 1) / kQsTile), kQsThreads, 0, stream>>>(
-      weights, n, cdf, scalars, tile_state, derive_exponent ? 1 : 0, ceil_log2_u64(global_count));
+  if (n > (4u << 20)) {
+    constexpr uint32_t tile = kQsThreads * kQsItemsLarge;
+    quantize_scan_kernel<kQsItemsLarge><<<static_cast<unsigned>((n + tile - 1) / tile), kQsThreads, 0, stream>>>(
+        weights, n, cdf, scalars, tile_state, derive_exponent ? 1 : 0, ceil_log2_u64(global_count));
+  } else {
+    quantize_scan_kernel<kQsItemsSmall><<<static_cast<unsigned>((n + kQsTile - 1) / kQsTile), kQsThreads, 0, stream>>>(
+        weights, n, cdf, scalars, tile_state, derive_exponent ? 1 : 0, ceil_log2_u64(global_count));
+  }
 }
 
 void launch_normalize(double* weights, uint64_t n, const Scalars* scalars, unsigned long long global_total, double* partials,

@@ -35,17 +35,7 @@ struct FieldView {
   uint32_t border_x_max;  // width + 1: largest padded x
   uint32_t border_y_max;  // 4 (height + 1) + 3: largest 4 * padded y with its two fraction bits
   int use_fixed;          // launch the fixed-point kernel (map small enough for 16.16 cell coordinates)
-  // The likelihood field itself (float, as the reference stores it) in the same bordered layout with 4 x 8-cell
-  // tiles (bordered_index_float): LikelihoodFieldModel's fixed-point kernel gathers 4-byte values from it and cubes
-  // them per lookup -- a 128-byte line then covers twice the cells of the 8-byte table.
-  const float* bordered_f;
-  int use_float;
 };
-
-/// Offset of padded cell (px, py) in the float tile layout (tiles 4 cells wide, 8 tall; 2^kx tiles per row).
-BB_HD uint32_t bordered_index_float(uint32_t px, uint32_t py, int kx) {
-  return (((py >> 3) << (kx + 5)) | ((px >> 2) << 5)) | ((py & 7u) << 2) | (px & 3u);
-}
 
 /// Offset of padded cell (px, py) in the bordered tile layout.
 BB_HD uint32_t bordered_index(uint32_t px, uint32_t py, int kx) {
@@ -221,7 +211,7 @@ void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const Motion
 /// propagate with the pose-bin histogram fused in: `grid` was predicted on the host, every particle's bin goes to
 /// bin_rank[] = {bin, arrival rank inside the bin} and into the counters (zeroed by launch_begin_fused_step).  launch_finish_schedule turns them into perm.
 void launch_propagate_binned(Pose2* states, uint64_t n, const MotionSampling& sampling, uint64_t seed, uint32_t step, uint64_t first_index,
-                             const Schedule& grid, uint2* bin_rank, uint32_t* counters, cudaStream_t stream);
+                             const Schedule& grid, uint2* bin_rank, uint32_t* counters, Schedule* sched, cudaStream_t stream);
 void launch_finish_schedule(const uint2* bin_rank, uint64_t n, uint32_t n_bins, Schedule* sched, uint32_t* counters, uint32_t* perm,
                             unsigned long long* tile_state, cudaStream_t stream);
 /// One launch resetting the per-step scalars, the CDF scan state and (counters != nullptr) the schedule's counters / scan state.

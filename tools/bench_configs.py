@@ -61,15 +61,36 @@ def main():
             res[tag + "_threads"] = threads
         out["c1_10k_x_180_lfm_500_multinomial"] = res
     if "c3" in which:
+        from oracle import pyoracle as orc
+
         sc = synthetic.make_scenario(grid_size=2000, n_beams=720, steps=100)
         n = 1_000_000
-        out["c3_1M_x_720_beam_2000"] = run_gpu(sc, bb.SENSOR_BEAM, bb.BeamModelParam(beam_max_range=60.0),
-                                               bb.AmclParams(min_particles=n, max_particles=n, resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=1), steps=5, warmup=1)
+        res = run_gpu(sc, bb.SENSOR_BEAM, bb.BeamModelParam(beam_max_range=60.0),
+                      bb.AmclParams(min_particles=n, max_particles=n, resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=1), steps=5, warmup=1)
+        # L-bar (cells the reference's Bresenham walk inspects per beam) and the CPU port on a posterior-like sample
+        rng = np.random.default_rng(3)
+        m = 4000
+        pose = sc.poses[3]
+        st = np.array([orc.se2(pose[0] + rng.normal(0, 0.3), pose[1] + rng.normal(0, 0.3), pose[2] + rng.normal(0, 0.25)) for _ in range(m)])
+        orc.use_native_build()
+        bp = orc.BeamParam(beam_max_range=60.0)
+        t0 = time.perf_counter()
+        _, visited = orc.sensor_weights(orc.BEAM, bp, orc.Grid(sc.cells, sc.resolution), sc.scans[3], st, return_visited=True)
+        cpu_s = time.perf_counter() - t0
+        lbar = visited / (m * 720)
+        k = res["kernels_ms"].get("reweight_beam", float("nan"))
+        # A = N * (48 + B * L-bar) bytes for the reweight launch (one occupancy byte per inspected cell)
+        a_bytes = n * (48 + 720 * lbar)
+        res.update({"cells_per_ray_reference": lbar, "algorithmic_bytes_reweight": a_bytes,
+                    "reweight_achieved_gbs": a_bytes / (k * 1e-3) / 1e9, "hbm_peak_gbs": 6567.1,
+                    "reweight_frac_of_hbm_peak": a_bytes / (k * 1e-3) / 1e9 / 6567.1,
+                    "cpu_reweight_ms_per_1M_particles": cpu_s * 1e3 * n / m, "cpu_sample": f"{m} particles x 720 beams, all OpenMP threads, scaled x{n // m} (extrapolated)"})
+        out["c3_1M_x_720_beam_2000"] = res
     if "c4" in which:
         sc = synthetic.make_scenario(grid_size=2000, n_beams=1080, steps=100)
         out["c4_kld_100k_10M_lfm"] = run_gpu(sc, bb.SENSOR_LIKELIHOOD_FIELD, bb.LikelihoodFieldModelParam(**LFM),
                                              bb.AmclParams(min_particles=100_000, max_particles=10_000_000, resample_scheme=bb.RESAMPLE_SYSTEMATIC, seed=1,
-                                                           spatial_resolution=(0.05, 0.05, float(np.deg2rad(1.0)))), steps=6, warmup=1)
+                                                           spatial_resolution=(0.5, 0.5, float(np.deg2rad(10.0)))), steps=6, warmup=1)  # beluga_ros defaults
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     path = os.path.join(ROOT, "gpurun_out", "configs.json")
     merged = json.load(open(path)) if os.path.exists(path) else {}
