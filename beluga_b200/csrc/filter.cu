@@ -1087,7 +1087,7 @@ int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t 
     BB_LAUNCHED("propagate");
     mark("schedule");
     launch_finish_schedule(bin_rank_, n_, grid.n_bins, sched_, counters_, perm_, sched_tiles_, stream_);
-    BB_LAUNCHED("schedule");
+    BB_LAUNCHED_N("schedule", 2);
     perm = perm_;
   } else if (sampling != nullptr || scheduled) {
     mark("propagate");

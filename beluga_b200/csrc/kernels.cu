@@ -336,10 +336,7 @@ __device__ __forceinline__ uint32_t schedule_bin(const Schedule& g, const Pose2&
 /// propagate with the histogram of the execution schedule fused in (the bin grid comes from the host's prediction).
 __global__ void __launch_bounds__(kPrThreads) propagate_binned_kernel(Pose2* __restrict__ states, uint64_t n, MotionSampling sampling, uint64_t seed,
                                                                       uint32_t step, uint64_t first_index, Schedule grid,
-                                                                      uint2* __restrict__ bin_rank, uint32_t* __restrict__ counters,
-                                                                      Schedule* __restrict__ sched) {
-  __shared__ uint32_t s_scan[kPrThreads / kWarp];
-  __shared__ int s_last;
+                                                                      uint2* __restrict__ bin_rank, uint32_t* __restrict__ counters) {
   const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kPrThreads + threadIdx.x;
   if (i < n) {
     const Pose2 st = propagate_one(load_pose(states + i), sampling, seed, first_index + i, step);
@@ -350,57 +347,6 @@ __global__ void __launch_bounds__(kPrThreads) propagate_binned_kernel(Pose2* __r
     const uint32_t rank = atomicAdd(counters + b, 1u);
     bin_rank[i] = make_uint2(b, rank);
   }
-  // The last block to finish turns the counters into bin offsets (exclusive prefix sum, 64 k values at most on one
-  // SM: a few microseconds, and one launch with its ticket / look-back machinery less).
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    s_last = atomicAdd(&sched->tile_ticket, 1ull) + 1ull == gridDim.x ? 1 : 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const uint32_t n_bins = grid.n_bins;
-  const uint32_t per_thread = ((n_bins + kPrThreads - 1) / kPrThreads + 3u) & ~3u;  // consecutive counters per thread, whole uint4s
-  const uint32_t begin = threadIdx.x * per_thread;
-  uint32_t sum = 0;
-  for (uint32_t k = begin; k < begin + per_thread && k < n_bins; k += 4) {
-    const uint4 c = __ldcg(reinterpret_cast<const uint4*>(counters + k));  // counters are padded to a multiple of 4 and zeroed
-    sum += c.x + c.y + c.z + c.w;
-  }
-  // block-wide exclusive scan of the per-thread sums
-  const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
-  uint32_t inc = sum;
-#pragma unroll
-  for (int off = 1; off < kWarp; off <<= 1) {
-    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
-    if (lane >= off) inc += o;
-  }
-  if (lane == kWarp - 1) s_scan[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t ws = lane < kPrThreads / kWarp ? s_scan[lane] : 0u;
-#pragma unroll
-    for (int off = 1; off < kWarp; off <<= 1) {
-      const uint32_t o = __shfl_up_sync(0xffffffffu, ws, off);
-      if (lane >= off) ws += o;
-    }
-    if (lane < kPrThreads / kWarp) s_scan[lane] = ws;
-  }
-  __syncthreads();
-  uint32_t running = inc - sum + (warp > 0 ? s_scan[warp - 1] : 0u);
-  for (uint32_t k = begin; k < begin + per_thread && k < n_bins; k += 4) {
-    uint4* p = reinterpret_cast<uint4*>(counters + k);
-    const uint4 c = __ldcg(p);
-    uint4 e;
-    e.x = running;
-    e.y = e.x + c.x;
-    e.z = e.y + c.y;
-    e.w = e.z + c.z;
-    running = e.w + c.w;
-    *p = e;
-  }
-  if (threadIdx.x == 0) sched->tile_ticket = 0;
 }
 
 __global__ void __launch_bounds__(256) schedule_place_kernel(const uint2* __restrict__ bin_rank, uint64_t n, const uint32_t* __restrict__ offsets,
@@ -938,7 +884,7 @@ __global__ void __launch_bounds__(256) beam_eta_table_kernel(BeamParams p, doubl
 #define BB200_BEAM_BLOCKS 3
 #endif
 #ifndef BB200_BEAM_RAYS
-#define BB200_BEAM_RAYS 2  // rays a thread walks together (1, 2 or 4)
+#define BB200_BEAM_RAYS 1  // rays a thread walks together (1, 2 or 4); measured at C3: 1 -> 29.5 ms, 2 -> 31.4 ms, 4 (2 CTAs/SM) -> 40.0 ms
 #endif
 constexpr int kBeamRays = BB200_BEAM_RAYS;
 constexpr int kBeamThreads = 256;
@@ -1869,10 +1815,10 @@ void launch_propagate(Pose2* states, uint64_t n, bool do_propagate, const Motion
 }
 
 void launch_propagate_binned(Pose2* states, uint64_t n, const MotionSampling& sampling, uint64_t seed, uint32_t step, uint64_t first_index,
-                             const Schedule& grid, uint2* bin_rank, uint32_t* counters, Schedule* sched, cudaStream_t stream) {
+                             const Schedule& grid, uint2* bin_rank, uint32_t* counters, Schedule* /*sched*/, cudaStream_t stream) {
   if (n == 0) return;
   propagate_binned_kernel<<<static_cast<unsigned>((n + kPrThreads - 1) / kPrThreads), kPrThreads, 0, stream>>>(
-      states, n, sampling, seed, step, first_index, grid, bin_rank, counters, sched);
+      states, n, sampling, seed, step, first_index, grid, bin_rank, counters);
 }
 
 void launch_begin_fused_step(Scalars* scalars, unsigned long long* tile_state, uint32_t n_tiles, Schedule* sched, uint32_t* counters,
@@ -1901,8 +1847,11 @@ void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uin
 void launch_finish_schedule(const uint2* bin_rank, uint64_t n, uint32_t n_bins, Schedule* sched, uint32_t* counters, uint32_t* perm,
                             unsigned long long* tile_state, cudaStream_t stream) {
   if (n == 0) return;
-  (void)n_bins, (void)sched, (void)tile_state;  // the counters were scanned by the last block of propagate_binned_kernel
+  // (Scanning the counters in the tail of propagate_binned_kernel -- its last block -- was tried: one SM reading 250 KB
+  // in dependent 16-byte steps takes 40 us; sixteen look-back tiles take 8.)
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  const uint32_t tiles = (n_bins + kScanTile - 1) / kScanTile;
+  scan_u32_kernel<<<tiles, kScanThreads, 0, stream>>>(counters, counters, n_bins, &sched->tile_ticket, tile_state, nullptr);
   schedule_place_kernel<<<blocks, 256, 0, stream>>>(bin_rank, n, counters, perm);
 }
 
