@@ -267,11 +267,11 @@ int Amcl::update_group(Amcl* const* ranks, int count, const double control[4], c
     return static_cast<int>(BB200_OK);
   };
 
+  const bool resample_now = plan.resample != 0 && plan.needs_ess == 0;
   for (int r = 0; r < count; ++r) {
-    const int st = ranks[r]->filter_->step_begin(plan.sampling, plan.step, points_xy, n_points, plan.opts);
+    const int st = ranks[r]->filter_->step_begin(plan.sampling, plan.step, points_xy, n_points, plan.opts, resample_now);
     if (st != BB200_OK) return rollback(st);
   }
-  const bool resample_now = plan.resample != 0 && plan.needs_ess == 0;
   int st = resample_now ? run_phases({Filter::kPhaseReweight, Filter::kPhaseCdf, Filter::kPhaseResample, Filter::kPhaseFinish})
                         : run_phases({Filter::kPhaseReweight, Filter::kPhaseCdf, Filter::kPhaseNormalize, Filter::kPhaseFinish});
   double sum_sq = 0.0;

@@ -112,6 +112,8 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   if (const char* v = std::getenv("BB200_BEAM_ETA_TABLE")) beam_eta_table_ = std::atoi(v) != 0;  // development knob: tabulated beam normalisers
   if (const char* v = std::getenv("BB200_FIXED")) fixed_lookup_ = std::atoi(v) != 0;         // development knob: fixed-point lookup kernel
   if (const char* v = std::getenv("BB200_PREDICT_SCHEDULE")) predict_schedule_ = std::atoi(v) != 0;  // development knob: host-predicted pose bins
+  if (const char* v = std::getenv("BB200_PREFETCH_TABLE")) prefetch_table_ = std::atoi(v) != 0;  // development knob: L2 prefetch of the likelihood table
+  if (const char* v = std::getenv("BB200_BEAM_TWO_PASS")) beam_two_pass_ = std::atoi(v) != 0;  // development knob: walk + mixture kernels
   if (const char* v = std::getenv("BB200_PER_BIN")) schedule_per_bin_ = std::atof(v);        // development knob: particles per pose bin
   if (const char* v = std::getenv("BB200_LEVER")) schedule_lever_ = std::atof(v);            // development knob: heading lever arm / mean range
   capacity_ = config.capacity;
@@ -207,6 +209,7 @@ Filter::~Filter() {
   cudaFree(tiled_);
   cudaFree(bordered_);
   cudaFree(beam_eta_);
+  cudaFree(beam_hits_);
   cudaFree(occupancy_);
   cudaFree(free_distance_);
   cudaFree(free_cells_);
@@ -492,7 +495,8 @@ int Filter::enqueue_exchange(int kind, bool post, bool wait) {
   return BB200_OK;
 }
 
-int Filter::step_begin(const bb200_motion_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points, const bb200_resample_opts& o) {
+int Filter::step_begin(const bb200_motion_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points, const bb200_resample_opts& o,
+                       bool resample_planned) {
   if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
   if (sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set");
   if (o.min_particles < o.max_particles) return fail(BB200_ERR_STATE, "the fused step does not run KLD; use resample()");
@@ -515,6 +519,7 @@ int Filter::step_begin(const bb200_motion_sampling& sampling, uint32_t step, con
   step_.step = step;
   step_.n_points = n_points;
   step_.opts = o;
+  step_.resample_planned = resample_planned;
   return BB200_OK;
 }
 
@@ -531,8 +536,9 @@ int Filter::step_phase(int phase) {
       mark("begin_step");
       {
         const bool scheduled = schedule_enabled_ && n_ >= kScheduleMinParticles;
+        const bool warm = prefetch_table_ && sensor_ != BB200_SENSOR_BEAM && field_.use_fixed && bordered_bytes_ <= (96ull << 20);
         launch_begin_fused_step(scalars_, tile_state_, scan_tile_count(n_), sched_, scheduled ? counters_ : nullptr, schedule_max_bins(), sched_tiles_,
-                                schedule_tile_count(), stream_);
+                                schedule_tile_count(), warm ? bordered_ : nullptr, bordered_bytes_, stream_);
         BB_LAUNCHED("begin_step");
         st = enqueue_propagate_reweight(&step_.sampling, step_.step, true, step_.n_points, scheduled);
       }
@@ -548,7 +554,7 @@ int Filter::step_phase(int phase) {
     }
     case kPhaseCdf: {
       if (sharded) {
-        mark("exchange");
+        mark("exchange_wmax");
         st = enqueue_exchange(kExchangeWmax, !split_posts_, true);  // global largest weight -> exponent; resets the scan state
         if (st != BB200_OK) return st;
       }
@@ -558,6 +564,12 @@ int Filter::step_phase(int phase) {
       launch_quantize_scan(weights_, n_, cdf_, scalars_, tile_state_, stream_, !sharded, config_.global_count);
       BB_LAUNCHED("quantize_scan");
       if (sharded) {
+        if (step_.resample_planned) {  // the CDF holds what sampling needs; every new particle weighs 1 (overlaps the wait for the peers' totals)
+          mark("fill_weights");
+          launch_fill(weights_, capacity_, 1.0, stream_);
+          BB_LAUNCHED("fill_weights");
+          step_.weights_filled = true;
+        }
         if (split_posts_) {
           mark("exchange");
           st = enqueue_exchange(kExchangeTotal, true, false);
@@ -570,7 +582,7 @@ int Filter::step_phase(int phase) {
       ResampleArgs a;
       if (sharded) {
         if (!step_.totals_exchanged) {
-          mark("exchange");
+          mark("exchange_total");
           st = enqueue_exchange(kExchangeTotal, !split_posts_, true);  // every rank's fixed-point total -> CDF offsets
           if (st != BB200_OK) return st;
           step_.totals_exchanged = true;
@@ -591,9 +603,12 @@ int Filter::step_phase(int phase) {
           a.owner_count = capacity_;
         }
         for (int r = 0; r < peer_world_; ++r) a.peer_out[r] = peer_states_[cur_ ^ 1][r];
-        mark("fill_weights");
-        launch_fill(weights_, capacity_, 1.0, stream_);  // the CDF holds what sampling needs; every new particle weighs 1
-        BB_LAUNCHED("fill_weights");
+        if (!step_.weights_filled) {
+          mark("fill_weights");
+          launch_fill(weights_, capacity_, 1.0, stream_);  // the CDF holds what sampling needs; every new particle weighs 1
+          BB_LAUNCHED("fill_weights");
+          step_.weights_filled = true;
+        }
         mark("resample_push");
       } else {
         a = make_resample_args(o, 0, o.max_particles, false);
@@ -611,7 +626,7 @@ int Filter::step_phase(int phase) {
     }
     case kPhaseFinish: {
       if (sharded) {
-        mark("exchange");
+        mark("exchange_moments");
         st = enqueue_exchange(kExchangeMoments, !split_posts_, true);  // also the barrier: the peers' stores into this rank's buffer are complete
         if (st != BB200_OK) return st;
       } else if (!step_.resampled) {  // kPhaseNormalize left the moments in results_: hand them to the host block
@@ -858,6 +873,7 @@ int Filter::set_likelihood_field_map(const bb200_likelihood_field_param& p, cons
       for (int xi = 0; xi < g.width; ++xi)
         bordered[bordered_index(static_cast<uint32_t>(xi + 1), static_cast<uint32_t>(yi + 1), kx)] = table[static_cast<size_t>(yi) * g.width + xi];
     BB_CHECK(dev_alloc(&bordered_, bordered.size()));
+    bordered_bytes_ = bordered.size() * sizeof(double);
     BB_CHECK(cudaMemcpyAsync(bordered_, bordered.data(), bordered.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
     BB_CHECK(cudaStreamSynchronize(stream_));
     field_.bordered = bordered_;
@@ -1104,8 +1120,35 @@ int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t 
   if (do_reweight) {
     if (sensor_ == BB200_SENSOR_BEAM) {
       mark("reweight_beam");
-      launch_reweight_beam(states_[cur_], weights_, n_, perm, occupancy_view_, beam_, points_, static_cast<uint32_t>(n_points), scalars_, stream_);
-      BB_LAUNCHED("reweight_beam");
+      uint64_t pass = 0;
+      if (beam_two_pass_ && n_points > 0 && occupancy_view_.width <= 65535 && occupancy_view_.height <= 65535) {
+        // hit words of one pass: at most 3 GiB, whole warps of particles
+        pass = std::min<uint64_t>(n_, std::max<uint64_t>(32, ((3ull << 30) / (4ull * n_points)) / 32 * 32));
+        const uint64_t words = beam_hit_words(pass, static_cast<uint32_t>(n_points));
+        if (words > beam_hits_words_) {
+          BB_CHECK(cudaStreamSynchronize(stream_));
+          cudaFree(beam_hits_);
+          beam_hits_ = nullptr;
+          beam_hits_words_ = 0;
+          // sized for the filter's capacity so that a growing particle count (KLD) does not reallocate every step
+          const uint64_t pass_cap = std::min<uint64_t>(capacity_, std::max<uint64_t>(32, ((3ull << 30) / (4ull * n_points)) / 32 * 32));
+          const uint64_t want = beam_hit_words(std::max(pass, pass_cap), static_cast<uint32_t>(n_points));
+          if (dev_alloc(&beam_hits_, want) == cudaSuccess) {
+            beam_hits_words_ = want;
+          } else {
+            (void)cudaGetLastError();  // no room for the intermediate: the fused kernel needs none
+            pass = 0;
+          }
+        }
+      }
+      if (pass > 0) {
+        launch_reweight_beam_two_pass(states_[cur_], weights_, n_, perm, occupancy_view_, beam_, points_, static_cast<uint32_t>(n_points), beam_hits_, pass,
+                                      scalars_, stream_);
+        BB_LAUNCHED_N("reweight_beam", 2 * static_cast<int>((n_ + pass - 1) / pass));
+      } else {
+        launch_reweight_beam(states_[cur_], weights_, n_, perm, occupancy_view_, beam_, points_, static_cast<uint32_t>(n_points), scalars_, stream_);
+        BB_LAUNCHED("reweight_beam");
+      }
     } else {
       mark("reweight_lfm");
       launch_reweight_lfm(states_[cur_], weights_, n_, perm, field_, points_, param_points_ ? points_host_ : nullptr, static_cast<uint32_t>(n_points),
@@ -1489,7 +1532,7 @@ int Filter::resample_kld(const bb200_resample_opts& o, uint64_t* accepted) {
 
 int Filter::step_resample(const bb200_motion_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points,
                           const bb200_resample_opts& o, bb200_estimate* est, double* weight_sum, uint64_t* new_size) {
-  int st = step_begin(sampling, step, points_xy, n_points, o);
+  int st = step_begin(sampling, step, points_xy, n_points, o, true);
   for (int phase = kPhaseReweight; st == BB200_OK && phase <= kPhaseFinish; ++phase) st = step_phase(phase);
   if (st != BB200_OK) {
     step_.active = false;

@@ -90,7 +90,8 @@ class Filter {
   /// The fused resampling step (propagate | reweight | normalize | resample | estimate), any number of shards.
   /// step_begin validates and stages the inputs; step_phase(1..4) only enqueues; step_end synchronises once.
   /// A driver holding several shards in one thread enqueues phase k of every shard before phase k+1 of any.
-  int step_begin(const bb200_motion_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points, const bb200_resample_opts& o);
+  int step_begin(const bb200_motion_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points, const bb200_resample_opts& o,
+                 bool resample_planned);
   enum StepPhase : int {
     kPhaseReweight = 1,   // begin_step | propagate | schedule | reweight                      (posts the shard's largest weight)
     kPhaseCdf = 2,        // common exponent | fixed-point CDF                                 (posts the shard's total)
@@ -143,6 +144,8 @@ class Filter {
     uint32_t partial_rows{1};
     bool resampled{false};   // kPhaseResample ran in the batch being closed
     bool normalized{false};  // kPhaseNormalize ran (weights are normalised, the CDF stays valid)
+    bool resample_planned{false};  // kPhaseResample follows kPhaseCdf directly (every_n fired, no ESS decision in between)
+    bool weights_filled{false};
     bool totals_exchanged{false};  // the ranks' totals of this step are in shard_totals_
     unsigned long long total{0};
     int exponent{0};
@@ -230,12 +233,17 @@ class Filter {
   double* table_{nullptr};
   double* tiled_{nullptr};
   double* bordered_{nullptr};
+  uint64_t bordered_bytes_{0};
+  bool prefetch_table_{true};
   FieldView field_{};
   int8_t* occupancy_{nullptr};
   uint8_t* free_distance_{nullptr};
   OccupancyView occupancy_view_{};
   BeamParams beam_{};
   double2* beam_eta_{nullptr};
+  uint32_t* beam_hits_{nullptr};   // two-pass beam model: hit word per (beam, particle) of one pass
+  uint64_t beam_hits_words_{0};
+  bool beam_two_pass_{true};
   bool beam_eta_table_{true};
   uint32_t* free_cells_{nullptr};
   uint64_t n_free_{0};

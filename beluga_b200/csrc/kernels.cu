@@ -179,6 +179,8 @@ struct StepReset {
   uint32_t n_counters;
   unsigned long long* sched_tiles;
   uint32_t n_sched_tiles;
+  const char* prefetch;        // nullable: a table the step is about to gather from (pulled into L2 while propagate runs)
+  uint64_t prefetch_lines;     // its size in 128-byte lines
 };
 
 __global__ void __launch_bounds__(256) begin_fused_step_kernel(StepReset r) {
@@ -205,6 +207,11 @@ __global__ void __launch_bounds__(256) begin_fused_step_kernel(StepReset r) {
     for (uint32_t k = t; k < r.n_counters / 4; k += stride) c4[k] = make_uint4(0u, 0u, 0u, 0u);
     for (uint32_t k = t; k < r.n_sched_tiles; k += stride) r.sched_tiles[k] = 0;
   }
+  // The likelihood table is gathered from at random by the reweight kernel; after an L2 flush (or a map-sized
+  // working set) its first touches would be demand misses to HBM, paid at full latency by warps that have nothing
+  // else to do when a shard is small.  Streaming it into L2 now costs a few microseconds of HBM bandwidth that the
+  // FP64-bound propagate kernel does not use.
+  for (uint64_t k = t; k < r.prefetch_lines; k += stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(r.prefetch + k * 128));
 }
 
 // ---- initialize_normal (a16) ---------------------------------------------------------------------
@@ -983,6 +990,122 @@ __global__ void __launch_bounds__(kBeamThreads, kBeamBlocksPerSm)
     weights[i] = w;
   }
   const unsigned long long m = block_max_u64<kBeamThreads>(active ? weight_order_bits(w) : 0ull, s_red);
+  if (threadIdx.x == 0 && m != 0) atomicMax(&scalars->wmax_bits, m);
+}
+
+// ---- beam model in two passes ----------------------------------------------------------------------
+// The fused kernel above carries the ray walk (integer, one dependent load per iteration) and the mixture (FP64:
+// sqrt, exp, three dozen constants) in one register allocation: 78 registers, 36 % occupancy, 800 issued instructions
+// per beam.  Split: the WALK writes the hit cell of every (particle, beam) as one 32-bit word -- beam-major, so a
+// warp's 32 particles store and later load consecutive words -- and the MIXTURE reads it back.  4 bytes per ray each
+// way (2.9 GB at 1M x 720: under a millisecond of HBM time) buy a 40-register walk kernel at twice the occupancy
+// and a branch-free mixture loop.  Hit words: 0xFFFFFFFF = miss, else cy << 16 | cx (grids up to 65535 cells a side).
+
+constexpr uint32_t kHitMiss = 0xFFFFFFFFu;
+constexpr int kWalkThreads = 256;
+constexpr uint32_t kWalkChunk = 2048;  // far ends staged per shared-memory chunk (32 KB)
+
+__global__ void __launch_bounds__(kWalkThreads, 4)
+    beam_walk_kernel(const Pose2* __restrict__ states, uint64_t n, uint64_t slot_base, uint64_t slot_count, const uint32_t* __restrict__ perm,
+                     OccupancyView grid, double beam_max_range, const double2* __restrict__ points, uint32_t n_points,
+                     uint32_t* __restrict__ hits, uint64_t hit_stride) {
+  __shared__ double2 s_far[kWalkChunk];
+  const uint64_t local = static_cast<uint64_t>(blockIdx.x) * kWalkThreads + threadIdx.x;
+  const uint64_t slot = slot_base + local;
+  const bool active = local < slot_count && slot < n;
+  const uint64_t i = active ? (perm != nullptr ? perm[slot] : slot) : 0;
+  // Ray2d: source pose in the grid frame and its cell (raycasting.hpp:67-70).
+  const Pose2 src = pose_mul(grid.world_to_grid, active ? load_pose(states + i) : Pose2{1.0, 0.0, 0.0, 0.0});
+  const int sx = cell_near(src.x, grid.inv_resolution), sy = cell_near(src.y, grid.inv_resolution);
+  for (uint32_t base = 0; base < n_points; base += kWalkChunk) {
+    const uint32_t count = min(kWalkChunk, n_points - base);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < count; b += kWalkThreads) {
+      const double2 p = points[base + b];
+      const double z = sqrt(p.x * p.x + p.y * p.y);                                    // beam_model.hpp:116
+      s_far[b] = make_double2((p.x / z) * beam_max_range, (p.y / z) * beam_max_range);  // :120-123, raycasting.hpp:83
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (uint32_t b = 0; b < count; ++b) {
+      // far end = r1 * t2 + t1 (raycasting.hpp:81-85)
+      const double2 f = s_far[b];
+      const double ex = (src.c * f.x - src.s * f.y) + src.x;
+      const double ey = (src.s * f.x + src.c * f.y) + src.y;
+      RayWalk walk;
+      ray_begin(walk, sx, sy, cell_near(ex, grid.inv_resolution), cell_near(ey, grid.inv_resolution));
+      while (walk.active) ray_step(walk, grid);
+      const uint32_t word = walk.hit ? ((static_cast<uint32_t>(walk.hit_y) << 16) | static_cast<uint32_t>(walk.hit_x)) : kHitMiss;
+      __stcs(hits + static_cast<uint64_t>(base + b) * hit_stride + local, word);  // written once, read once: streaming
+    }
+  }
+}
+
+constexpr int kMixThreads = 256;
+constexpr uint32_t kMixChunk = 2048;
+
+__global__ void __launch_bounds__(kMixThreads)
+    beam_mixture_kernel(const Pose2* __restrict__ states, double* __restrict__ weights, uint64_t n, uint64_t slot_base, uint64_t slot_count,
+                        const uint32_t* __restrict__ perm, OccupancyView grid, BeamParams params, const double2* __restrict__ points,
+                        uint32_t n_points, const uint32_t* __restrict__ hits, uint64_t hit_stride, Scalars* __restrict__ scalars) {
+  __shared__ double2 s_beam[kMixChunk];  // {z, exp(-lambda_short * z)}
+  __shared__ unsigned long long s_red[kMixThreads / kWarp];
+  const uint64_t local = static_cast<uint64_t>(blockIdx.x) * kMixThreads + threadIdx.x;
+  const uint64_t slot = slot_base + local;
+  const bool active = local < slot_count && slot < n;
+  const uint64_t i = active ? (perm != nullptr ? perm[slot] : slot) : 0;
+  const Pose2 src = pose_mul(grid.world_to_grid, active ? load_pose(states + i) : Pose2{1.0, 0.0, 0.0, 0.0});
+  const int sx = cell_near(src.x, grid.inv_resolution), sy = cell_near(src.y, grid.inv_resolution);
+  const double source_x = (static_cast<double>(sx) + 0.5) * grid.resolution, source_y = (static_cast<double>(sy) + 0.5) * grid.resolution;
+  const double n_norm = 1. / (sqrt(2. * 3.14159265358979323846) * params.sigma_hit);  // beam_model.hpp:107
+
+  auto value = [&](uint32_t word, const double2& beam) {
+    const bool hit_cell = word != kHitMiss;
+    const int cx = static_cast<int>(word & 0xFFFFu), cy = static_cast<int>(word >> 16);
+    // distance between the centroids of the source cell and the hit cell (raycasting.hpp:91-104), clamped to the range
+    const double dxm = (static_cast<double>(cx) + 0.5) * grid.resolution - source_x;
+    const double dym = (static_cast<double>(cy) + 0.5) * grid.resolution - source_y;
+    const double hit = fmin(sqrt(dxm * dxm + dym * dym), params.beam_max_range);
+    const double z_mean = hit_cell ? hit : params.beam_max_range;  // value_or(beam_max_range)
+    double2 eta;
+    if (params.eta != nullptr) {
+      const long long ix = static_cast<long long>(cx) - sx, iy = static_cast<long long>(cy) - sy;
+      const unsigned long long d2 = static_cast<unsigned long long>(ix * ix + iy * iy);
+      const bool in_table = hit_cell && hit < params.beam_max_range && d2 + 1 < params.eta_entries;
+      eta = __ldg(params.eta + (in_table ? static_cast<uint32_t>(d2) : params.eta_entries - 1u));
+    } else {
+      eta = beam_normalisers(params, z_mean);
+    }
+    return beam_pz3(params, beam.x, beam.y, z_mean, n_norm, eta.x, eta.y);
+  };
+
+  double acc = 0.0;
+  for (uint32_t base = 0; base < n_points; base += kMixChunk) {
+    const uint32_t count = min(kMixChunk, n_points - base);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < count; b += kMixThreads) {
+      const double2 p = points[base + b];
+      const double z = sqrt(p.x * p.x + p.y * p.y);  // beam_model.hpp:116
+      s_beam[b] = make_double2(z, exp(-params.lambda_short * z));
+    }
+    __syncthreads();
+    if (!active) continue;
+    const uint32_t* h = hits + static_cast<uint64_t>(base) * hit_stride + local;
+    uint32_t b = 0;
+    for (; b + 4 <= count; b += 4) {  // transform_reduce grouping (numeric:439-462)
+      const uint32_t w0 = __ldcs(h + static_cast<uint64_t>(b) * hit_stride), w1 = __ldcs(h + static_cast<uint64_t>(b + 1) * hit_stride);
+      const uint32_t w2 = __ldcs(h + static_cast<uint64_t>(b + 2) * hit_stride), w3 = __ldcs(h + static_cast<uint64_t>(b + 3) * hit_stride);
+      const double f0 = value(w0, s_beam[b]), f1 = value(w1, s_beam[b + 1]), f2 = value(w2, s_beam[b + 2]), f3 = value(w3, s_beam[b + 3]);
+      acc = acc + ((f0 + f1) + (f2 + f3));
+    }
+    for (; b < count; ++b) acc = acc + value(__ldcs(h + static_cast<uint64_t>(b) * hit_stride), s_beam[b]);
+  }
+  double w = 0.0;
+  if (active) {
+    w = weights[i] * acc;  // actions/reweight.hpp:54-60
+    weights[i] = w;
+  }
+  const unsigned long long m = block_max_u64<kMixThreads>(active ? weight_order_bits(w) : 0ull, s_red);
   if (threadIdx.x == 0 && m != 0) atomicMax(&scalars->wmax_bits, m);
 }
 
@@ -1822,10 +1945,12 @@ void launch_propagate_binned(Pose2* states, uint64_t n, const MotionSampling& sa
 }
 
 void launch_begin_fused_step(Scalars* scalars, unsigned long long* tile_state, uint32_t n_tiles, Schedule* sched, uint32_t* counters,
-                             uint32_t n_counters, unsigned long long* sched_tiles, uint32_t n_sched_tiles, cudaStream_t stream) {
-  const StepReset r{scalars, tile_state, n_tiles, sched, counters, (n_counters + 3u) & ~3u, sched_tiles, n_sched_tiles};
-  const uint32_t work = std::max(n_tiles, counters != nullptr ? r.n_counters / 4 : 0u);
-  const unsigned blocks = std::max(1u, std::min((work + 255u) / 256u, 148u));
+                             uint32_t n_counters, unsigned long long* sched_tiles, uint32_t n_sched_tiles, const void* prefetch,
+                             uint64_t prefetch_bytes, cudaStream_t stream) {
+  const StepReset r{scalars, tile_state, n_tiles, sched, counters, (n_counters + 3u) & ~3u, sched_tiles, n_sched_tiles,
+                    static_cast<const char*>(prefetch), prefetch != nullptr ? prefetch_bytes / 128 : 0};
+  const uint64_t work = std::max<uint64_t>(std::max(n_tiles, counters != nullptr ? r.n_counters / 4 : 0u), r.prefetch_lines / 8);
+  const unsigned blocks = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>((work + 255u) / 256u, 148u * 4u)));
   begin_fused_step_kernel<<<blocks, 256, 0, stream>>>(r);
 }
 
@@ -1907,6 +2032,25 @@ uint32_t beam_eta_entries(double beam_max_range, double resolution) {
 void launch_beam_eta_table(const BeamParams& params, double resolution, double2* table, uint32_t entries, cudaStream_t stream) {
   if (entries == 0) return;
   beam_eta_table_kernel<<<(entries + 255) / 256, 256, 0, stream>>>(params, resolution, table, entries);
+}
+
+uint64_t beam_hit_words(uint64_t particles, uint32_t n_points) {
+  const uint64_t stride = (particles + 31) / 32 * 32;
+  return stride * n_points;
+}
+
+void launch_reweight_beam_two_pass(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const OccupancyView& grid,
+                                   const BeamParams& params, const double* points_xy_device, uint32_t n_points, uint32_t* hits,
+                                   uint64_t pass_particles, Scalars* scalars, cudaStream_t stream) {
+  if (n == 0 || n_points == 0 || pass_particles == 0) return;
+  const double2* points = reinterpret_cast<const double2*>(points_xy_device);
+  const uint64_t stride = (pass_particles + 31) / 32 * 32;
+  for (uint64_t base = 0; base < n; base += pass_particles) {
+    const uint64_t count = std::min<uint64_t>(pass_particles, n - base);
+    const unsigned blocks = static_cast<unsigned>((count + kWalkThreads - 1) / kWalkThreads);
+    beam_walk_kernel<<<blocks, kWalkThreads, 0, stream>>>(states, n, base, count, perm, grid, params.beam_max_range, points, n_points, hits, stride);
+    beam_mixture_kernel<<<blocks, kMixThreads, 0, stream>>>(states, weights, n, base, count, perm, grid, params, points, n_points, hits, stride, scalars);
+  }
 }
 
 void launch_reweight_beam(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const OccupancyView& grid,

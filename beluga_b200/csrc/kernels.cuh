@@ -214,9 +214,11 @@ void launch_propagate_binned(Pose2* states, uint64_t n, const MotionSampling& sa
                              const Schedule& grid, uint2* bin_rank, uint32_t* counters, Schedule* sched, cudaStream_t stream);
 void launch_finish_schedule(const uint2* bin_rank, uint64_t n, uint32_t n_bins, Schedule* sched, uint32_t* counters, uint32_t* perm,
                             unsigned long long* tile_state, cudaStream_t stream);
-/// One launch resetting the per-step scalars, the CDF scan state and (counters != nullptr) the schedule's counters / scan state.
+/// One launch resetting the per-step scalars, the CDF scan state and (counters != nullptr) the schedule's counters / scan state;
+/// `prefetch` (nullable) is streamed into L2 (the table the reweight kernel gathers from).
 void launch_begin_fused_step(Scalars* scalars, unsigned long long* tile_state, uint32_t n_tiles, Schedule* sched, uint32_t* counters,
-                             uint32_t n_counters, unsigned long long* sched_tiles, uint32_t n_sched_tiles, cudaStream_t stream);
+                             uint32_t n_counters, unsigned long long* sched_tiles, uint32_t n_sched_tiles, const void* prefetch,
+                             uint64_t prefetch_bytes, cudaStream_t stream);
 uint32_t schedule_max_bins();
 uint32_t schedule_tile_count();
 /// Counting sort of the particle indices over pose bins -> perm (needs launch_propagate's moments).
@@ -231,6 +233,13 @@ void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const
 /// reweight with the beam model (Bresenham ray casting) in schedule order | block max.
 void launch_reweight_beam(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const OccupancyView& grid,
                           const BeamParams& params, const double* points_xy_device, uint32_t n_points, Scalars* scalars, cudaStream_t stream);
+
+/// The same in two passes over `pass_particles` particles at a time: ray walk -> one 32-bit hit word per (beam, particle)
+/// in `hits` (beam_hit_words(pass_particles, n_points) words), then the mixture.  Grids up to 65535 cells a side.
+uint64_t beam_hit_words(uint64_t particles, uint32_t n_points);
+void launch_reweight_beam_two_pass(const Pose2* states, double* weights, uint64_t n, const uint32_t* perm, const OccupancyView& grid,
+                                   const BeamParams& params, const double* points_xy_device, uint32_t n_points, uint32_t* hits,
+                                   uint64_t pass_particles, Scalars* scalars, cudaStream_t stream);
 
 /// Largest weight only (when propagate/reweight ran separately or particles were set by hand).
 void launch_max_weight(const double* weights, uint64_t n, Scalars* scalars, cudaStream_t stream);

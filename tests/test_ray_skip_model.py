@@ -1,7 +1,7 @@
 """Integer model of the empty-space skipping in cast_ray (csrc/kernels.cu): the beam kernel walks the reference's
 standard Bresenham line (algorithm/raycasting/bresenham.hpp:84-160) but advances d steps at once where the
 Chebyshev free-distance map says the next d - 1 cells cannot stop the ray, updating (x, y, error) in closed form
-(with the reciprocal-multiply-and-correct quotient the kernel uses).  Checked here against a plain cell-by-cell
+(with the 32-bit reciprocal-multiply-and-correct quotient the kernel uses).  Checked here against a plain cell-by-cell
 walk over the oracle's Bresenham cells on random maps and rays.  CPU only."""
 import numpy as np
 import pytest
@@ -31,7 +31,7 @@ def skip_walk(dist, sx, sy, fx, fy):
         xstep, ystep = ystep, xstep
         reversed_ = True
     dxspan, dyspan = 2 * xspan, 2 * yspan
-    inv = 1.0 / dxspan if dxspan else float("inf")
+    recip = 0xFFFFFFFF // dxspan if dxspan else 0  # ray_begin: floor((2^32 - 1) / dxspan)
     error, step = xspan, 0
     while True:
         cx, cy = (y, x) if reversed_ else (x, y)
@@ -46,10 +46,13 @@ def skip_walk(dist, sx, sy, fx, fy):
         step += k
         x += k * xstep
         t = error + k * dyspan
-        m = int(np.floor(float(t - 1) * inv))  # __double2int_rd(double(t - 1) * inv_dxspan)
+        assert 0 <= t - 1 < 2 ** 32
+        m = ((t - 1) * recip) >> 32  # __umulhi(t - 1, recip): the quotient or one below it
         r = (t - 1) - m * dxspan
-        m += 1 if r >= dxspan else (-1 if r < 0 else 0)
-        assert m == (t - 1) // dxspan  # the correction step makes the quotient exact
+        assert 0 <= r < 2 * dxspan
+        if r >= dxspan:
+            m += 1
+        assert m == (t - 1) // dxspan  # one remainder check makes the quotient exact
         y += m * ystep
         error = t - m * dxspan
         assert 0 < error <= dxspan
