@@ -83,6 +83,36 @@ def cluster_select_host(cells, n_particles: int, linear: float = 0.20, angular: 
     return np.array(ids[: len(cells)], dtype=np.uint32), n_clusters.value, bool(found.value), best.value, out
 
 
+def particle_cloud_markers(bins):
+    """Host half of assign_particle_cloud(..., MarkerArray) (beluga_ros/particle_cloud.hpp:212-294) on histogram bins
+    (representative[4], weight): -> (bodies [2n, 7], heads [3n, 7], body_scale_x); columns x, y, z, r, g, b, a."""
+    lib = _capi.load()
+    n = len(bins)
+    arr = (_capi.ClusterCell * max(n, 1))()
+    for k, (rep, weight) in enumerate(bins):
+        arr[k].representative[:] = list(rep)
+        arr[k].weight = float(weight)
+    bodies = (_capi.MarkerVertex * max(2 * n, 1))()
+    heads = (_capi.MarkerVertex * max(3 * n, 1))()
+    scale = C.c_double(0.0)
+    st = lib.bb200_particle_cloud_markers(arr, n, bodies, heads, C.byref(scale))
+    if st != 0:
+        raise RuntimeError(f"bb200_particle_cloud_markers: status {st}")
+    unpack = lambda vs, m: np.array([[v.x, v.y, v.z, v.r, v.g, v.b, v.a] for v in vs[:m]]).reshape(m, 7)  # noqa: E731
+    return unpack(bodies, 2 * n), unpack(heads, 3 * n), scale.value
+
+
+def likelihood_field_to_occupancy(field) -> np.ndarray:
+    """assign_likelihood_field (beluga_ros/likelihood_field.hpp:44-79): float field -> int8 cells in [0, 100]."""
+    lib = _capi.load()
+    f = np.ascontiguousarray(field, dtype=np.float32)
+    out = np.zeros(f.shape, dtype=np.int8)
+    st = lib.bb200_likelihood_field_to_occupancy(f.ctypes.data_as(C.POINTER(C.c_float)), f.size, out.ctypes.data_as(C.POINTER(C.c_int8)))
+    if st != 0:
+        raise RuntimeError(f"bb200_likelihood_field_to_occupancy: status {st}")
+    return out
+
+
 def estimate_from_moments(moments, pivot):
     """beluga::estimate (algorithm/estimation.hpp:436-475) from globally summed raw moments."""
     e = _capi.Estimate()
@@ -465,6 +495,24 @@ class Filter:
             C.byref(cells), C.byref(clusters)))
         est = (np.array(e.mean), np.array(e.cov).reshape(3, 3))
         return (*est, ids, cells.value, clusters.value) if with_ids else est
+
+    def particle_histogram(self, linear: float = 1e-3, angular: float = 1e-3):
+        """Device-side histogram of the cloud over spatial-hash buckets (beluga_ros/particle_cloud.hpp:197-210).
+        -> (representatives [m, 4], weights [m], counts [m], first_index [m], max_bin_weight)."""
+        n_bins, top = C.c_uint64(0), C.c_double(0.0)
+        self._check(self._lib.bb200_filter_particle_histogram(self._h, linear, angular, None, 0, C.byref(n_bins), C.byref(top)))
+        m = n_bins.value
+        arr = (_capi.ClusterCell * max(m, 1))()
+        self._check(self._lib.bb200_filter_particle_histogram(self._h, linear, angular, arr, m, C.byref(n_bins), C.byref(top)))
+        raw = np.frombuffer(arr, dtype=np.dtype([("rep", "<f8", 4), ("hash", "<u8"), ("first", "<u4"), ("count", "<u4"), ("weight", "<f8"), ("m", "<f8", 9)]),
+                            count=m)
+        return raw["rep"].copy(), raw["weight"].copy(), raw["count"].copy(), raw["first"].copy(), top.value
+
+    def sample_states(self, count: int, step: int = 0xFFFFFFFF) -> np.ndarray:
+        """`count` states drawn by weight without touching the set (assign_particle_cloud(..., size, PoseArray))."""
+        out = np.zeros((count, 4))
+        self._check(self._lib.bb200_filter_sample_states(self._h, count, step, _dptr(out) if count else None))
+        return out
 
     def moments(self, pivot=(0.0, 0.0)) -> np.ndarray:
         out = np.zeros(9)

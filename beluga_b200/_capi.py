@@ -99,6 +99,10 @@ class LaserScan(C.Structure):
                 ("min_range", C.c_double), ("max_range", C.c_double), ("max_beams", C.c_uint64), ("laser_origin", C.POINTER(C.c_double))]
 
 
+class MarkerVertex(C.Structure):
+    _fields_ = [("x", C.c_double), ("y", C.c_double), ("z", C.c_double), ("r", C.c_float), ("g", C.c_float), ("b", C.c_float), ("a", C.c_float)]
+
+
 class UpdateResult(C.Structure):
     _fields_ = [("updated", C.c_int), ("resampled", C.c_int), ("n_particles", C.c_uint64), ("estimate", Estimate),
                 ("random_state_probability", C.c_double), ("weight_sum", C.c_double), ("weights_degenerate", C.c_int)]
@@ -155,6 +159,10 @@ SIGNATURES = {
     "bb200_cluster_select_host": (C.c_int, [_P(ClusterCell), C.c_uint64, C.c_uint64, _P(ClusterParam), _P(C.c_uint32), _P(C.c_uint32), _P(C.c_int),
                                             _P(C.c_uint32), _dbl]),
     "bb200_filter_cluster_estimate": (C.c_int, [_vp, _P(ClusterParam), _P(Estimate), _P(C.c_uint32), C.c_uint64, _P(C.c_uint32), _P(C.c_uint32)]),
+    "bb200_filter_particle_histogram": (C.c_int, [_vp, C.c_double, C.c_double, _P(ClusterCell), C.c_uint64, _P(C.c_uint64), _dbl]),
+    "bb200_filter_sample_states": (C.c_int, [_vp, C.c_uint64, C.c_uint32, _dbl]),
+    "bb200_particle_cloud_markers": (C.c_int, [_P(ClusterCell), C.c_uint64, _P(MarkerVertex), _P(MarkerVertex), _dbl]),
+    "bb200_likelihood_field_to_occupancy": (C.c_int, [_P(C.c_float), C.c_uint64, _P(C.c_int8)]),
     "bb200_filter_moments": (C.c_int, [_vp, _dbl, _dbl]),
     "bb200_filter_set_timing": (C.c_int, [_vp, C.c_int]),
     "bb200_filter_clear_timings": (C.c_int, [_vp]),

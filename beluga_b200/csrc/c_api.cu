@@ -1,6 +1,7 @@
 // extern "C" surface of libbeluga_b200.so (declared in include/beluga_b200.h).
 #include <algorithm>
 #include <cmath>
+#include <limits>
 #include <memory>
 #include <new>
 #include <string>
@@ -301,6 +302,83 @@ int bb200_cluster_select_host(const bb200_cluster_cell* cells, uint64_t n_cells,
     return static_cast<int>(BB200_OK);
   });
 }
+int bb200_filter_particle_histogram(bb200_filter* f, double linear_resolution, double angular_resolution, bb200_cluster_cell* bins, uint64_t capacity,
+                                    uint64_t* n_bins, double* max_bin_weight) {
+  BB_REQUIRE(f);
+  return guarded(f->impl, [&] { return f->impl.particle_histogram(linear_resolution, angular_resolution, bins, capacity, n_bins, max_bin_weight); });
+}
+int bb200_filter_sample_states(bb200_filter* f, uint64_t count, uint32_t step, double* states_out) {
+  BB_REQUIRE(f);
+  return guarded(f->impl, [&] { return f->impl.sample_states(count, step, states_out); });
+}
+
+namespace {
+// detail::alphaHueToRGBA (beluga_ros/particle_cloud.hpp:56-70): single-precision HSV -> RGB for V = S = 1.
+void alpha_hue_to_rgba(float hue, float alpha, float rgba[4]) {
+  const float kr = std::fmod(5.0F + hue / 60.0F, 6.0F);
+  const float kg = std::fmod(3.0F + hue / 60.0F, 6.0F);
+  const float kb = std::fmod(1.0F + hue / 60.0F, 6.0F);
+  rgba[0] = 1.0F - 1.0F * std::max(0.0F, std::min({kr, 4.0F - kr, 1.0F}));
+  rgba[1] = 1.0F - 1.0F * std::max(0.0F, std::min({kg, 4.0F - kg, 1.0F}));
+  rgba[2] = 1.0F - 1.0F * std::max(0.0F, std::min({kb, 4.0F - kb, 1.0F}));
+  rgba[3] = alpha;
+}
+}  // namespace
+
+int bb200_particle_cloud_markers(const bb200_cluster_cell* bins, uint64_t n_bins, bb200_marker_vertex* bodies, bb200_marker_vertex* heads,
+                                 double* body_scale_x) {
+  BB_REQUIRE((bins || n_bins == 0) && (bodies || n_bins == 0) && (heads || n_bins == 0) && body_scale_x);
+  // beluga_ros/particle_cloud.hpp:212-294: arrows as a line list (bodies) and a triangle list (heads), sizes and
+  // colours scaled by the bin weight relative to the heaviest bin.
+  const double kArrowBodyLength = 0.5, kArrowHeadLength = 0.1, kArrowHeadWidth = kArrowHeadLength / 5.0;
+  const double kArrowLength = kArrowBodyLength + kArrowHeadLength;
+  double max_bin_weight = 1e-3;
+  for (uint64_t k = 0; k < n_bins; ++k) max_bin_weight = bins[k].weight > max_bin_weight ? bins[k].weight : max_bin_weight;
+  double min_scale_factor = 1.0;
+  for (uint64_t k = 0; k < n_bins; ++k) {
+    const double* st = bins[k].representative;  // {cos, sin, x, y}
+    const double scale_factor = std::max(bins[k].weight / max_bin_weight, 1e-1);
+    if (scale_factor < min_scale_factor) min_scale_factor = scale_factor;
+    float rgba[4];
+    alpha_hue_to_rgba(static_cast<float>((1.0 - scale_factor) * 270.0), static_cast<float>(0.25 + 0.75 * scale_factor), rgba);
+    auto put = [&](bb200_marker_vertex& v, double lx, double ly) {  // state * (scale_factor * local point)
+      const double px = scale_factor * lx, py = scale_factor * ly;
+      v.x = (st[0] * px - st[1] * py) + st[2];
+      v.y = (st[1] * px + st[0] * py) + st[3];
+      v.z = 0.0;
+      v.r = rgba[0], v.g = rgba[1], v.b = rgba[2], v.a = rgba[3];
+    };
+    put(bodies[2 * k], 0.0, 0.0);
+    put(bodies[2 * k + 1], kArrowBodyLength, 0.0);
+    put(heads[3 * k], kArrowBodyLength, kArrowHeadWidth / 2.0);
+    put(heads[3 * k + 1], kArrowBodyLength, -(kArrowHeadWidth / 2.0));
+    put(heads[3 * k + 2], kArrowLength, 0.0);
+  }
+  *body_scale_x = static_cast<double>(min_scale_factor * kArrowHeadWidth) * 0.8;
+  return BB200_OK;
+}
+
+int bb200_likelihood_field_to_occupancy(const float* field, uint64_t n, int8_t* out) {
+  BB_REQUIRE((field && out) || n == 0);
+  if (n == 0) return BB200_OK;
+  // beluga_ros/likelihood_field.hpp:44-79
+  float min_val = field[0], max_val = field[0];
+  for (uint64_t i = 1; i < n; ++i) {
+    if (field[i] < min_val) min_val = field[i];
+    if (max_val < field[i]) max_val = field[i];
+  }
+  const float range = max_val - min_val;
+  if (range <= std::numeric_limits<float>::epsilon()) {
+    for (uint64_t i = 0; i < n; ++i) out[i] = 0;
+    return BB200_OK;
+  }
+  for (uint64_t i = 0; i < n; ++i) {
+    const float normalized = (field[i] - min_val) / range;
+    out[i] = static_cast<int8_t>(normalized * 100.0f);
+  }
+  return BB200_OK;
+}
+
 int bb200_filter_moments(bb200_filter* f, const double pivot_xy[2], double out[9]) {
   BB_REQUIRE(f && pivot_xy && out);
   return guarded(f->impl, [&] { return f->impl.moments(pivot_xy, out); });

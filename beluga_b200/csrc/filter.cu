@@ -210,6 +210,7 @@ Filter::~Filter() {
   cudaFree(bordered_);
   cudaFree(beam_eta_);
   cudaFree(beam_hits_);
+  cudaFree(free_padded_);
   cudaFree(occupancy_);
   cudaFree(free_distance_);
   cudaFree(free_cells_);
@@ -926,6 +927,25 @@ int Filter::set_beam_map(const bb200_beam_param& p, const bb200_occupancy_grid& 
   free_distance_ = nullptr;
   BB_CHECK(dev_alloc(&free_distance_, count));
   BB_CHECK(cudaMemcpy(free_distance_, free_distance.data(), count, cudaMemcpyHostToDevice));
+  // padded copy for the two-pass walk: a border of zeros, power-of-two pitch
+  cudaFree(free_padded_);
+  free_padded_ = nullptr;
+  occupancy_view_.free_padded = nullptr;
+  occupancy_view_.pad_shift = 0;
+  {
+    int shift = 1;
+    while ((1 << shift) < g.width + 2) ++shift;
+    const size_t rows = static_cast<size_t>(g.height) + 2;
+    if (shift <= 16 && g.height <= 65535) {
+      std::vector<uint8_t> padded(rows << shift, 0);
+      for (int y = 0; y < g.height; ++y)
+        std::memcpy(padded.data() + ((static_cast<size_t>(y) + 1) << shift) + 1, free_distance.data() + static_cast<size_t>(y) * g.width, static_cast<size_t>(g.width));
+      BB_CHECK(dev_alloc(&free_padded_, padded.size()));
+      BB_CHECK(cudaMemcpy(free_padded_, padded.data(), padded.size(), cudaMemcpyHostToDevice));
+      occupancy_view_.free_padded = free_padded_;
+      occupancy_view_.pad_shift = shift;
+    }
+  }
   occupancy_view_.cells = occupancy_;
   occupancy_view_.free_distance = free_distance_;
   occupancy_view_.width = g.width;
@@ -1121,13 +1141,16 @@ int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t 
     if (sensor_ == BB200_SENSOR_BEAM) {
       mark("reweight_beam");
       uint64_t pass = 0;
-      if (beam_two_pass_ && n_points > 0 && occupancy_view_.width <= 65535 && occupancy_view_.height <= 65535) {
+      // spans of the walk's 32-bit arithmetic: far ends lie within beam_max_range of the source, sources inside the grid
+      const double reach_cells = beam_.beam_max_range * occupancy_view_.inv_resolution + 4.0;
+      if (beam_two_pass_ && n_points > 0 && occupancy_view_.free_padded != nullptr && reach_cells < static_cast<double>(1 << 21)) {
         // hit words of one pass: at most 3 GiB, whole warps of particles
         pass = std::min<uint64_t>(n_, std::max<uint64_t>(32, ((3ull << 30) / (4ull * n_points)) / 32 * 32));
         const uint64_t words = beam_hit_words(pass, static_cast<uint32_t>(n_points));
         if (words > beam_hits_words_) {
           BB_CHECK(cudaStreamSynchronize(stream_));
           cudaFree(beam_hits_);
+  cudaFree(free_padded_);
           beam_hits_ = nullptr;
           beam_hits_words_ = 0;
           // sized for the filter's capacity so that a growing particle count (KLD) does not reallocate every step
@@ -1347,20 +1370,17 @@ int Filter::ensure_cluster_scratch(uint32_t cells) {
   return BB200_OK;
 }
 
-int Filter::cluster_estimate(const bb200_cluster_param& p, bb200_estimate* out, uint32_t* cluster_ids, uint64_t ids_capacity, uint32_t* n_cells,
-                             uint32_t* n_clusters) {
-  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
-  if (!(p.linear_hash_resolution > 0.0) || !(p.angular_hash_resolution > 0.0) || !(p.weight_cap_percentile >= 0.0) ||
-      !(p.weight_cap_percentile < 1.0))
-    return fail(BB200_ERR_INVALID_ARGUMENT, "cluster parameters: resolutions must be positive and the percentile in [0, 1)");
-  if (cluster_ids != nullptr && ids_capacity < n_) return fail(BB200_ERR_CAPACITY, "cluster id buffer too small");
+int Filter::cell_records(double linear_resolution, double angular_resolution, std::vector<HostCell>* host) {
+  // Per-particle half of the clusterizer, also the device-side histogram of the particle cloud: spatial hash ->
+  // first-occurrence numbering of the occupied cells -> stable sort of the particle indices by cell -> one record per
+  // cell (representative = first particle, count, weight summed in particle order, raw moments).
   BB_CHECK(cudaSetDevice(config_.device));
   {
     const int st = ensure_cluster_scratch(0);
     if (st != BB200_OK) return st;
   }
   mark("cluster_cells");
-  launch_cluster_cells_begin(states_[cur_], n_, p.linear_hash_resolution, p.angular_hash_resolution, cluster_, stream_);
+  launch_cluster_cells_begin(states_[cur_], n_, linear_resolution, angular_resolution, cluster_, stream_);
   BB_LAUNCHED_N("cluster_cells_begin", 3);
   unsigned long long cells64 = 0;
   BB_CHECK(cudaMemcpyAsync(&cells64, cluster_.words + 1, sizeof(cells64), cudaMemcpyDeviceToHost, stream_));
@@ -1377,12 +1397,27 @@ int Filter::cluster_estimate(const bb200_cluster_param& p, bb200_estimate* out, 
   mark("cluster_records");
   launch_cluster_records(states_[cur_], weights_, sorted, cells, pivot_[0], pivot_[1], cluster_, stream_);
   BB_LAUNCHED("cluster_records");
-  std::vector<HostCell> host(cells);
+  host->resize(cells);
   static_assert(sizeof(HostCell) == sizeof(CellRecord), "record layouts must agree");
-  BB_CHECK(cudaMemcpyAsync(host.data(), cluster_.records, static_cast<size_t>(cells) * sizeof(CellRecord), cudaMemcpyDeviceToHost, stream_));
+  BB_CHECK(cudaMemcpyAsync(host->data(), cluster_.records, static_cast<size_t>(cells) * sizeof(CellRecord), cudaMemcpyDeviceToHost, stream_));
   BB_CHECK(cudaStreamSynchronize(stream_));
   finish_marks();
+  return BB200_OK;
+}
 
+int Filter::cluster_estimate(const bb200_cluster_param& p, bb200_estimate* out, uint32_t* cluster_ids, uint64_t ids_capacity, uint32_t* n_cells,
+                             uint32_t* n_clusters) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  if (!(p.linear_hash_resolution > 0.0) || !(p.angular_hash_resolution > 0.0) || !(p.weight_cap_percentile >= 0.0) ||
+      !(p.weight_cap_percentile < 1.0))
+    return fail(BB200_ERR_INVALID_ARGUMENT, "cluster parameters: resolutions must be positive and the percentile in [0, 1)");
+  if (cluster_ids != nullptr && ids_capacity < n_) return fail(BB200_ERR_CAPACITY, "cluster id buffer too small");
+  std::vector<HostCell> host;
+  {
+    const int st = cell_records(p.linear_hash_resolution, p.angular_hash_resolution, &host);
+    if (st != BB200_OK) return st;
+  }
+  const uint32_t cells = static_cast<uint32_t>(host.size());
   const ClusterSelection sel = select_cluster(host.data(), host.size(), n_, p.linear_hash_resolution, p.angular_hash_resolution, p.weight_cap_percentile);
   if (out != nullptr) estimate_from_moments(sel.moments, out);
   if (n_cells != nullptr) *n_cells = cells;
@@ -1392,6 +1427,50 @@ int Filter::cluster_estimate(const bb200_cluster_param& p, bb200_estimate* out, 
     BB_CHECK(cudaMemcpy(cell_of.data(), cluster_.cell_of, n_ * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     for (uint64_t i = 0; i < n_; ++i) cluster_ids[i] = sel.cluster_of_cell[cell_of[i]];
   }
+  return BB200_OK;
+}
+
+int Filter::particle_histogram(double linear_resolution, double angular_resolution, bb200_cluster_cell* bins, uint64_t capacity, uint64_t* n_bins,
+                               double* max_bin_weight) {
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  if (!(linear_resolution > 0.0) || !(angular_resolution > 0.0)) return fail(BB200_ERR_INVALID_ARGUMENT, "histogram resolutions must be positive");
+  std::vector<HostCell> host;
+  const int st = cell_records(linear_resolution, angular_resolution, &host);
+  if (st != BB200_OK) return st;
+  if (n_bins != nullptr) *n_bins = host.size();
+  double top = 1e-3;  // beluga_ros/particle_cloud.hpp:197
+  for (const HostCell& c : host) top = c.weight > top ? c.weight : top;
+  if (max_bin_weight != nullptr) *max_bin_weight = top;
+  if (bins != nullptr) {
+    if (capacity < host.size()) return fail(BB200_ERR_CAPACITY, "histogram bin buffer too small (n_bins has the count)");
+    static_assert(sizeof(bb200_cluster_cell) == sizeof(HostCell), "public and internal cell records must agree");
+    std::memcpy(bins, host.data(), host.size() * sizeof(HostCell));
+  }
+  return BB200_OK;
+}
+
+int Filter::sample_states(uint64_t count, uint32_t step, double* states_out) {
+  // views::sample | take_exactly(count) (beluga_ros/particle_cloud.hpp:141-147): `count` states drawn by weight, the
+  // particle set itself untouched.  Counter RNG: the multinomial draws of `step` (the caller picks a step the filter
+  // does not use, e.g. 0xFFFFFFFF - publish count).
+  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  if (count > capacity_) return fail(BB200_ERR_CAPACITY, "more samples than the filter capacity");
+  if (count > 0 && states_out == nullptr) return fail(BB200_ERR_INVALID_ARGUMENT, "states_out is null");
+  if (count == 0) return BB200_OK;
+  int st = ensure_cdf_ready();
+  if (st != BB200_OK && !cdf_valid_) return st;
+  BB_CHECK(cudaSetDevice(config_.device));
+  bb200_resample_opts o{};
+  o.scheme = BB200_RESAMPLE_MULTINOMIAL;
+  o.step = step;
+  o.min_particles = o.max_particles = count;
+  ResampleArgs a = make_resample_args(o, 0, count, false);
+  a.weights_out = nullptr;  // the weights stay what they are
+  a.ancestors = nullptr;
+  launch_resample(a, scalars_, partials_, stream_);  // into the staging state buffer; no flip
+  BB_LAUNCHED("sample_states");
+  BB_CHECK(cudaMemcpyAsync(states_out, states_[cur_ ^ 1], count * sizeof(Pose2), cudaMemcpyDeviceToHost, stream_));
+  BB_CHECK(cudaStreamSynchronize(stream_));
   return BB200_OK;
 }
 

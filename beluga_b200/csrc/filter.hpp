@@ -12,6 +12,7 @@
 
 #include "../../include/beluga_b200.h"
 #include "cluster.cuh"
+#include "cluster_host.hpp"
 #include "kernels.cuh"
 
 namespace bb200 {
@@ -51,6 +52,12 @@ class Filter {
   /// (optional, one per particle) is the parity hook for ParticleClusterizer::operator() (:304-316).
   int cluster_estimate(const bb200_cluster_param& p, bb200_estimate* out, uint32_t* cluster_ids, uint64_t ids_capacity, uint32_t* n_cells,
                        uint32_t* n_clusters);
+  /// Device-side histogram of the particle cloud over spatial-hash buckets (beluga_ros/particle_cloud.hpp:197-210): one
+  /// record per occupied bucket in first-occurrence order.  bins may be null (count only).
+  int particle_histogram(double linear_resolution, double angular_resolution, bb200_cluster_cell* bins, uint64_t capacity, uint64_t* n_bins,
+                         double* max_bin_weight);
+  /// `count` states drawn by weight without touching the set (views::sample | take_exactly, particle_cloud.hpp:141-147).
+  int sample_states(uint64_t count, uint32_t step, double* states_out);
   static void estimate_from_moments_static(const double m[kMomentCount], const double pivot[2], bb200_estimate* out);
 
   /// Fused single-GPU step: propagate | reweight | normalize | resample | estimate with one
@@ -196,6 +203,7 @@ class Filter {
 
   // clusterizer scratch (allocated on first use)
   int ensure_cluster_scratch(uint32_t cells);
+  int cell_records(double linear_resolution, double angular_resolution, std::vector<HostCell>* host);
   ClusterScratch cluster_{};
 
   // KLD scratch
@@ -238,6 +246,7 @@ class Filter {
   FieldView field_{};
   int8_t* occupancy_{nullptr};
   uint8_t* free_distance_{nullptr};
+  uint8_t* free_padded_{nullptr};
   OccupancyView occupancy_view_{};
   BeamParams beam_{};
   double2* beam_eta_{nullptr};

@@ -1005,6 +1005,12 @@ constexpr uint32_t kHitMiss = 0xFFFFFFFFu;
 constexpr int kWalkThreads = 256;
 constexpr uint32_t kWalkChunk = 2048;  // far ends staged per shared-memory chunk (32 KB)
 
+/// The walk against the PADDED free-distance map (one border cell of zeros all round, 2^pad_shift bytes per row): a
+/// jump of k <= d cells can at most land on the border, so the loop needs no bounds test -- a zero either is the first
+/// non-free cell or the border (= the ray left the grid: a miss, raycasting.hpp:86-87), told apart after the loop.  The
+/// iterator state is the linear cell index, advanced by k * (major stride) + m * (minor stride), so the x/y swap of the
+/// steep case (bresenham.hpp:99-105) costs nothing per iteration.  Spans stay below 2^22 (checked by the launcher), so
+/// the 32-bit reciprocal quotient of ray_step is the only path.  16 instructions per iteration instead of 45.
 __global__ void __launch_bounds__(kWalkThreads, 4)
     beam_walk_kernel(const Pose2* __restrict__ states, uint64_t n, uint64_t slot_base, uint64_t slot_count, const uint32_t* __restrict__ perm,
                      OccupancyView grid, double beam_max_range, const double2* __restrict__ points, uint32_t n_points,
@@ -1017,6 +1023,11 @@ __global__ void __launch_bounds__(kWalkThreads, 4)
   // Ray2d: source pose in the grid frame and its cell (raycasting.hpp:67-70).
   const Pose2 src = pose_mul(grid.world_to_grid, active ? load_pose(states + i) : Pose2{1.0, 0.0, 0.0, 0.0});
   const int sx = cell_near(src.x, grid.inv_resolution), sy = cell_near(src.y, grid.inv_resolution);
+  const bool source_inside = static_cast<unsigned>(sx) < static_cast<unsigned>(grid.width) && static_cast<unsigned>(sy) < static_cast<unsigned>(grid.height);
+  const int shift = grid.pad_shift;
+  const int pitch = 1 << shift;
+  const uint8_t* __restrict__ map = grid.free_padded;
+  const int source_index = ((sy + 1) << shift) + (sx + 1);
   for (uint32_t base = 0; base < n_points; base += kWalkChunk) {
     const uint32_t count = min(kWalkChunk, n_points - base);
     __syncthreads();
@@ -1028,14 +1039,55 @@ __global__ void __launch_bounds__(kWalkThreads, 4)
     __syncthreads();
     if (!active) continue;
     for (uint32_t b = 0; b < count; ++b) {
-      // far end = r1 * t2 + t1 (raycasting.hpp:81-85)
-      const double2 f = s_far[b];
-      const double ex = (src.c * f.x - src.s * f.y) + src.x;
-      const double ey = (src.s * f.x + src.c * f.y) + src.y;
-      RayWalk walk;
-      ray_begin(walk, sx, sy, cell_near(ex, grid.inv_resolution), cell_near(ey, grid.inv_resolution));
-      while (walk.active) ray_step(walk, grid);
-      const uint32_t word = walk.hit ? ((static_cast<uint32_t>(walk.hit_y) << 16) | static_cast<uint32_t>(walk.hit_x)) : kHitMiss;
+      uint32_t word = kHitMiss;
+      if (source_inside) {  // a source outside the grid sees nothing: the first cell already fails cell_is_valid
+        // far end = r1 * t2 + t1 (raycasting.hpp:81-85)
+        const double2 f = s_far[b];
+        const double ex = (src.c * f.x - src.s * f.y) + src.x;
+        const double ey = (src.s * f.x + src.c * f.y) + src.y;
+        int span = cell_near(ex, grid.inv_resolution) - sx, minor = cell_near(ey, grid.inv_resolution) - sy;
+        int stride_major = 1, stride_minor = pitch;
+        if (span < 0) {
+          span = -span;
+          stride_major = -1;
+        }
+        if (minor < 0) {
+          minor = -minor;
+          stride_minor = -pitch;
+        }
+        if (span < minor) {  // iterate along the longer axis (bresenham.hpp:99-105)
+          int t = span; span = minor; minor = t;
+          t = stride_major; stride_major = stride_minor; stride_minor = t;
+        }
+        const uint32_t dxspan = 2u * static_cast<uint32_t>(span), dyspan = 2u * static_cast<uint32_t>(minor);
+        const uint32_t recip = span > 0 ? 0xFFFFFFFFu / dxspan : 0u;
+        int index = source_index;
+        uint32_t err1 = static_cast<uint32_t>(span) - 1u;  // error - 1, error in (0, dxspan] (span == 0: never used)
+        int remaining = span;
+        for (;;) {
+          const int d = __ldg(map + index);
+          if (d == 0) {  // first non-free cell on the line, or the border
+            const int cx = (index & (pitch - 1)) - 1, cy = (index >> shift) - 1;
+            if (static_cast<unsigned>(cx) < static_cast<unsigned>(grid.width) && static_cast<unsigned>(cy) < static_cast<unsigned>(grid.height))
+              word = (static_cast<uint32_t>(cy) << 16) | static_cast<uint32_t>(cx);
+            break;
+          }
+          // Every cell within Chebyshev distance d - 1 is free and the line moves at most one cell per step in each axis:
+          // advance d steps of the iterator (bresenham.hpp:122-160, standard variant) in closed form.
+          const int k = min(d, remaining);
+          if (k == 0) break;  // the far end cell was free too: sentinel reached (bresenham.hpp:179)
+          remaining -= k;
+          const uint32_t tm1 = err1 + static_cast<uint32_t>(k) * dyspan;  // t - 1, t = error + k * dyspan < 2^32
+          uint32_t q = __umulhi(tm1, recip);                              // floor((t - 1) / dxspan) or one below
+          uint32_t r = tm1 - q * dxspan;
+          if (r >= dxspan) {
+            ++q;
+            r -= dxspan;
+          }
+          err1 = r;  // new error - 1
+          index += k * stride_major + static_cast<int>(q) * stride_minor;
+        }
+      }
       __stcs(hits + static_cast<uint64_t>(base + b) * hit_stride + local, word);  // written once, read once: streaming
     }
   }

@@ -48,6 +48,8 @@ constexpr int kFixedMaxSide = 8000;
 struct OccupancyView {
   const int8_t* cells;
   const uint8_t* free_distance;  // Chebyshev distance to the nearest non-free / outside cell (map_host.hpp)
+  const uint8_t* free_padded;    // the same with one border cell of zeros all round, 2^pad_shift bytes per row (two-pass walk)
+  int pad_shift;
   int width, height;
   double resolution, inv_resolution;
   Pose2 world_to_grid;  // grid.origin().inverse()

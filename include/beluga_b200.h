@@ -312,6 +312,33 @@ typedef struct bb200_cluster_cell {
 } bb200_cluster_cell;
 int bb200_cluster_select_host(const bb200_cluster_cell* cells, uint64_t n_cells, uint64_t n_particles, const bb200_cluster_param* p,
                               uint32_t* cluster_of_cell, uint32_t* n_clusters, int* found, uint32_t* best, double moments_out[9]);
+/* ---- output side: what beluga_ros publishes after a step, without moving N x 40 bytes to the host ----
+ * Device-side histogram of the particle cloud over spatial_hash<SE2d>{linear, linear, angular} buckets -- the
+ * unordered_map pass of assign_particle_cloud(particles, linear_resolution, angular_resolution, MarkerArray)
+ * (beluga_ros/include/beluga_ros/particle_cloud.hpp:197-210): one bin per occupied bucket, in the order in which the
+ * particle sequence first touches them; representative = the first particle of the bucket, weight = the bucket's weights
+ * added in particle order.  After a resample the million particles are copies of a few thousand candidates: the
+ * publish costs a few-KB read-back.  (The reference's map additionally splits a bucket when two of its states are
+ * not detail::almost_equal_to; with its 1 mm / 1 mrad defaults a bucket holds exact copies, and that refinement is not
+ * reproduced.)  bins may be NULL to query the count.  max_bin_weight: max(1e-3, heaviest bin) (:197,205-207). */
+int bb200_filter_particle_histogram(bb200_filter* f, double linear_resolution, double angular_resolution, bb200_cluster_cell* bins, uint64_t capacity,
+                                    uint64_t* n_bins, double* max_bin_weight);
+/* assign_particle_cloud(particles, size, PoseArray) (particle_cloud.hpp:129-147): `count` states drawn by weight
+ * (views::sample | take_exactly) -- multinomial counter-RNG draws of `step` -- into states_out (count x {cos, sin, x, y});
+ * the particle set is not modified. */
+int bb200_filter_sample_states(bb200_filter* f, uint64_t count, uint32_t step, double* states_out);
+/* Host only.  The marker geometry of assign_particle_cloud(..., MarkerArray) (particle_cloud.hpp:212-294) from the
+ * histogram bins: 2 vertices per bin for the LINE_LIST "bodies" marker, 3 per bin for the TRIANGLE_LIST "heads"
+ * marker, each with its RGBA colour (detail::alphaHueToRGBA, :56-70), and arrow_bodies.scale.x. */
+typedef struct bb200_marker_vertex {
+  double x, y, z;
+  float r, g, b, a;
+} bb200_marker_vertex;
+int bb200_particle_cloud_markers(const bb200_cluster_cell* bins, uint64_t n_bins, bb200_marker_vertex* bodies, bb200_marker_vertex* heads,
+                                 double* body_scale_x);
+/* Host only.  assign_likelihood_field (beluga_ros/include/beluga_ros/likelihood_field.hpp:44-79): the likelihood field
+ * (bb200_filter_get_likelihood_field) normalised to the [0, 100] int8 cells of a nav_msgs/OccupancyGrid. */
+int bb200_likelihood_field_to_occupancy(const float* field, uint64_t n, int8_t* out);
 /* Raw weighted moments of the local shard for a multi-rank estimate:
  * {sum w, sum w^2, sum w*cos, sum w*sin, sum w*dx, sum w*dy, sum w*dx^2, sum w*dx*dy, sum w*dy^2}
  * with (dx, dy) = (x, y) - pivot. */

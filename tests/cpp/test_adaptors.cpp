@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "beluga_b200/amcl.hpp"
+#include "beluga_b200/particle_cloud.hpp"
 
 namespace {
 
@@ -142,6 +143,22 @@ void ClusterBasedEstimateCanBeUsed() {  // beluga_ros/src/amcl.cpp:125
   ASSERT_TRUE(std::abs(pose.x() - plain->first.x()) < 0.1 && std::abs(pose.y() - plain->first.y()) < 0.1);
   ASSERT_TRUE(covariance[0] > 0.0 && covariance[4] > 0.0);
 }
+void OutputBuildersCanBeUsed() {  // beluga_ros/particle_cloud.hpp:129-147,197-294, likelihood_field.hpp:44-79
+  auto amcl = make_amcl();
+  amcl.initialize(beluga_b200::SE2d{0.3, 1.0, 1.0}, beluga_b200::Matrix3d{0.01, 0, 0, 0, 0.01, 0, 0, 0, 0.01});
+  ASSERT_TRUE(amcl.update(kDummyControl, kDummyMeasurement).has_value());
+  const auto markers = beluga_b200::particle_cloud_markers(amcl);
+  ASSERT_TRUE(!markers.bodies.empty() && markers.bodies.size() % 2 == 0 && markers.heads.size() == markers.bodies.size() / 2 * 3);
+  ASSERT_TRUE(markers.body_scale_x > 0.0 && markers.body_scale_x <= 0.02 * 0.8 + 1e-12);
+  const auto poses = beluga_b200::sample_poses(amcl, 25);
+  ASSERT_TRUE(poses.size() == 25);
+  for (const auto& p : poses) ASSERT_TRUE(std::abs(p.cos_yaw * p.cos_yaw + p.sin_yaw * p.sin_yaw - 1.0) < 1e-12);
+#ifdef BELUGA_B200_WITH_SOPHUS
+  const Sophus::SE2d sophus_pose = beluga_b200::SE2d{0.3, 1.0, 1.0};  // the conversion path, type-checked against the stub headers
+  const beluga_b200::SE2d back{sophus_pose};
+  ASSERT_TRUE(back.x() == 1.0 && back.y() == 1.0);
+#endif
+}
 void InvalidCovarianceThrows() {  // multivariate_normal_distribution.hpp:114-116
   auto amcl = make_amcl();
   bool thrown = false;
@@ -165,6 +182,7 @@ int main() {
   TestRandomParticlesInserting();
   OtherMotionModelsCanBeUsed();
   ClusterBasedEstimateCanBeUsed();
+  OutputBuildersCanBeUsed();
   InvalidCovarianceThrows();
   if (g_failures == 0) std::printf("CPP_ADAPTORS_OK\n");
   return g_failures == 0 ? 0 : 1;

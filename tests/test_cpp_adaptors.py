@@ -9,17 +9,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "cpp", "_build", "test_adaptors")
 
 
-def build_exe():
+def build_exe(with_sophus_stub: bool = False):
     from beluga_b200 import build as bb_build
 
     bb_build.build()
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     src = os.path.join(ROOT, "tests", "cpp", "test_adaptors.cpp")
     lib_dir = os.path.join(ROOT, "beluga_b200")
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
+    exe = EXE + ("_sophus" if with_sophus_stub else "")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
            "-L", lib_dir, "-lbeluga_b200", f"-Wl,-rpath,{lib_dir}"]
+    if with_sophus_stub:  # Sophus/Eigen are absent here: 30-line stand-ins type-check the BELUGA_B200_WITH_SOPHUS conversion path
+        cmd[1:1] = ["-DBELUGA_B200_WITH_SOPHUS", "-I", os.path.join(ROOT, "tests", "cpp", "stubs")]
     out = subprocess.run(cmd, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-4000:]
+
+
+def test_adaptors_compile_with_sophus_conversions():
+    build_exe(with_sophus_stub=True)
 
 
 def test_adaptors_compile():

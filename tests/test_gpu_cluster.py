@@ -125,3 +125,51 @@ def test_cluster_estimate_of_a_running_filter(bb, orc):
         states, weights = g.particles()
         assert np.all(weights == 1.0) == (interval == 1)
         check(bb, orc, states, weights)
+
+
+# ---- output side: device histogram of the cloud, weighted pose samples ---------------------------
+def test_particle_histogram_matches_a_host_grouping(bb, orc):
+    """bb200_filter_particle_histogram against a plain host pass over the particles in order (the unordered_map loop of
+    beluga_ros/particle_cloud.hpp:197-210 with spatial_hash buckets): same bins in first-occurrence order, same
+    representatives, weights added in particle order (bit-identical), max_bin_weight."""
+    rng = np.random.default_rng(12)
+    base = random_cloud(rng, 300, modes=[(0.0, 0.0, 0.2), (3.0, 1.0, -1.0)])
+    states = base[rng.integers(0, len(base), 20_000)]  # a resampled set: many exact copies of few candidates
+    weights = rng.uniform(0.5, 1.5, len(states))
+    f = bb.Filter(capacity=len(states))
+    f.set_particles(states, weights)
+    rep, w, count, first, top = f.particle_histogram(1e-3, 1e-3)
+    seen = {}
+    order = []
+    for i, st in enumerate(states):
+        h = orc.spatial_hash(st, 1e-3, 1e-3, 1e-3)
+        if h not in seen:
+            seen[h] = [i, 0.0, 0]
+            order.append(h)
+        seen[h][1] += weights[i]
+        seen[h][2] += 1
+    assert len(order) == len(rep) <= 300
+    assert np.array_equal(first, [seen[h][0] for h in order])
+    assert np.array_equal(rep, states[first])
+    assert np.array_equal(w, [seen[h][1] for h in order])
+    assert np.array_equal(count, [seen[h][2] for h in order])
+    assert top == max(1e-3, max(seen[h][1] for h in order))
+    # coarser buckets merge neighbours: fewer bins, the total weight is conserved
+    _, w2, c2, _, _ = f.particle_histogram(0.5, 0.5)
+    assert len(w2) < len(w) and c2.sum() == len(states) and w2.sum() == pytest.approx(weights.sum(), rel=1e-12)
+
+
+def test_sample_states_draws_by_weight_and_leaves_the_set_alone(bb, orc):
+    rng = np.random.default_rng(3)
+    states = random_cloud(rng, 64, modes=[(0.0, 0.0, 0.0)])
+    weights = np.zeros(64)
+    weights[[5, 17]] = [1.0, 3.0]
+    f = bb.Filter(capacity=64, seed=9)
+    f.set_particles(states, weights)
+    s = f.sample_states(40, step=123)
+    idx = [int(np.flatnonzero((states == row).all(axis=1))[0]) for row in s]
+    assert set(idx) <= {5, 17} and 20 <= idx.count(17) <= 40
+    exp, _, _ = orc.resample_indices(weights, orc.MULTINOMIAL, seed=9, step=123, m=40)
+    assert idx == list(exp)  # the multinomial counter draws of that step over the same integer CDF
+    st_after, w_after = f.particles()
+    assert np.array_equal(st_after, states) and np.array_equal(w_after, weights)
