@@ -606,14 +606,14 @@ class Amcl:
         return res
 
     def export_shard(self) -> bytes:
-        """192 bytes of CUDA IPC handles (two state buffers + mail block) for the peer ranks of a sharded filter."""
-        buf = C.create_string_buffer(192)
+        """256 bytes of CUDA IPC handles (two state buffers, mail block, KLD hash array) for the peer ranks of a sharded filter."""
+        buf = C.create_string_buffer(256)
         self._check(self._lib.bb200_amcl_export_shard(self._h, buf))
         return buf.raw
 
     def join_shards(self, world: int, rank: int, handles: bytes):
-        """Map every rank's exported buffers (world x 192 bytes, rank order); update() then runs in lock step with the peers."""
-        assert len(handles) == 192 * world
+        """Map every rank's exported buffers (world x 256 bytes, rank order); update() then runs in lock step with the peers."""
+        assert len(handles) == 256 * world
         self._check(self._lib.bb200_amcl_join_shards(self._h, world, rank, C.create_string_buffer(handles, len(handles))))
 
     def leave_shards(self):

@@ -97,6 +97,7 @@ Amcl::Amcl(const bb200_amcl_param& p, const bb200_motion_param& motion) : params
   c.record_ancestors = p.record_ancestors;
   filter_ = std::make_unique<Filter>(c);
   if (params_.resample_interval == 0) params_.resample_interval = 1;
+  if (sharded() && params_.min_particles < params_.max_particles && filter_->ok()) (void)filter_->enable_shard_kld();
 }
 
 int Amcl::initialize(const double mean[3], const double cov[9]) {
@@ -134,7 +135,7 @@ int Amcl::plan_update(const double control[4], bb200_step_plan* plan) {
   *plan = bb200_step_plan{};
   const Pose2 pose{control[0], control[1], control[2], control[3]};
   // Sharded filters gate on the GLOBAL particle count, which never drops to zero once initialised.
-  const uint64_t n = sharded() ? params_.max_particles * (initialized_ ? 1u : 0u) : filter_->size();
+  const uint64_t n = sharded() ? (initialized_ ? filter_->global_size() : 0u) : filter_->size();
   if (n == 0) return BB200_OK;  // amcl_core.hpp:166-168 -> std::nullopt
 
   // update_policy_(control_action) -- on_motion vs the last ACCEPTED pose (on_motion.hpp:121-133)
@@ -215,8 +216,11 @@ int Amcl::update_group(Amcl* const* ranks, int count, const double control[4], c
   *out = bb200_update_result{};
   if (ranks == nullptr || count < 1 || count > kMaxShards) return BB200_ERR_INVALID_ARGUMENT;
   Amcl& lead = *ranks[0];
-  if (lead.params_.min_particles < lead.params_.max_particles)
-    return lead.filter_->fail_with(BB200_ERR_STATE, "KLD-adaptive resampling is not available on a sharded filter");
+  const bool kld = lead.params_.min_particles < lead.params_.max_particles;
+  if (kld)
+    for (int r = 0; r < count; ++r)
+      if (!ranks[r]->filter_->shard_kld())
+        return ranks[r]->filter_->fail_with(BB200_ERR_STATE, "KLD-adaptive resampling on shards: the hash arrays were not exported (create the shards with min_particles < max_particles before joining them)");
   for (int r = 0; r < count; ++r)
     if (ranks[r]->sharded() && ranks[r]->filter_->shard_world() <= 1)
       return ranks[r]->filter_->fail_with(BB200_ERR_STATE, "this shard has not joined its peers (bb200_amcl_join_shards / bb200_sharded_amcl_create)");
@@ -272,8 +276,63 @@ int Amcl::update_group(Amcl* const* ranks, int count, const double control[4], c
     const int st = ranks[r]->filter_->step_begin(plan.sampling, plan.step, points_xy, n_points, plan.opts, resample_now);
     if (st != BB200_OK) return rollback(st);
   }
-  int st = resample_now ? run_phases({Filter::kPhaseReweight, Filter::kPhaseCdf, Filter::kPhaseResample, Filter::kPhaseFinish})
-                        : run_phases({Filter::kPhaseReweight, Filter::kPhaseCdf, Filter::kPhaseNormalize, Filter::kPhaseFinish});
+  // views::take_while_kld over the shards (take_while_kld.hpp:72-137): the candidate stream is ordered by output slot, and
+  // every rank sees the spatial hash of every candidate, so all ranks count distinct buckets over the same stream and
+  // stop at the same slot.  Windows of slots double like the single-GPU chunks; one host decision per window.
+  auto kld_size = [&](uint64_t* accepted) {
+    const uint64_t max = lead.params_.max_particles;
+    for (int r = 0; r < count; ++r) {
+      const int st = ranks[r]->filter_->step_totals(nullptr, nullptr);  // enqueue the totals exchange on every shard
+      if (st != BB200_OK) return st;
+    }
+    uint64_t begin = 0, k_before = 0;
+    uint64_t end = std::min<uint64_t>(max, std::max<uint64_t>(2 * lead.params_.min_particles, 65536));
+    *accepted = max;
+    while (begin < max) {
+      for (int r = 0; r < count; ++r) {
+        const int st = ranks[r]->filter_->kld_sharded_candidates(begin, end);
+        if (st != BB200_OK) return st;
+      }
+      for (int r = 0; r < count; ++r) {
+        const int st = ranks[r]->filter_->kld_sharded_count(begin, end, k_before);
+        if (st != BB200_OK) return st;
+      }
+      uint64_t cutoff = ~0ull, fresh = 0;
+      for (int r = 0; r < count; ++r) {
+        uint64_t c = 0, f = 0;
+        const int st = ranks[r]->filter_->kld_sharded_read(&c, &f);
+        if (st != BB200_OK) return st;
+        if (r == 0) {
+          cutoff = c;
+          fresh = f;
+        } else if (c != cutoff || f != fresh) {
+          return lead.filter_->fail_with(BB200_ERR_STATE, "KLD on shards: the ranks disagree on the count");
+        }
+      }
+      if (cutoff != ~0ull) {
+        *accepted = std::min<uint64_t>(cutoff - 1, max);  // take_while drops the first element whose condition fails (:134-136)
+        break;
+      }
+      k_before += fresh;
+      begin = end;
+      end = std::min<uint64_t>(max, end * 2);
+    }
+    return static_cast<int>(BB200_OK);
+  };
+
+  int st = BB200_OK;
+  if (resample_now && kld) {
+    st = run_phases({Filter::kPhaseReweight, Filter::kPhaseCdf});
+    uint64_t accepted = 0;
+    if (st == BB200_OK) st = kld_size(&accepted);
+    if (st == BB200_OK) {
+      for (int r = 0; r < count; ++r) ranks[r]->filter_->step_set_kld_accepted(accepted);
+      st = run_phases({Filter::kPhaseResample, Filter::kPhaseFinish});
+    }
+  } else {
+    st = resample_now ? run_phases({Filter::kPhaseReweight, Filter::kPhaseCdf, Filter::kPhaseResample, Filter::kPhaseFinish})
+                      : run_phases({Filter::kPhaseReweight, Filter::kPhaseCdf, Filter::kPhaseNormalize, Filter::kPhaseFinish});
+  }
   double sum_sq = 0.0;
   if (st == BB200_OK) st = close_batch(&sum_sq);
   if (st != BB200_OK) return rollback(st);
@@ -281,7 +340,13 @@ int Amcl::update_group(Amcl* const* ranks, int count, const double control[4], c
   if (!resample_now && plan.resample != 0) {
     // on_effective_size_drop (on_effective_size_drop.hpp:45-49): ESS = 1 / sum w~^2 < N / 2
     const double ess = sum_sq > 0.0 ? 1.0 / sum_sq : 0.0;
-    if (ess < static_cast<double>(lead.params_.max_particles) * 0.5) {
+    if (ess < static_cast<double>(lead.filter_->global_size()) * 0.5) {
+      if (kld) {
+        uint64_t accepted = 0;
+        st = kld_size(&accepted);
+        if (st != BB200_OK) return rollback(st);
+        for (int r = 0; r < count; ++r) ranks[r]->filter_->step_set_kld_accepted(accepted);
+      }
       st = run_phases({Filter::kPhaseResample, Filter::kPhaseFinish});
       if (st == BB200_OK) st = close_batch(nullptr);
       if (st != BB200_OK) return rollback(st);

@@ -419,8 +419,8 @@ int bb200_amcl_create_with_motion(const bb200_amcl_param* p, const bb200_motion_
     g_create_error = "unknown motion model";
     return BB200_ERR_INVALID_ARGUMENT;
   }
-  if (p->shard_capacity != 0 && (p->shard_first_index + p->shard_capacity > p->max_particles || p->min_particles != p->max_particles)) {
-    g_create_error = "a shard must lie inside [0, max_particles) and use min_particles == max_particles";
+  if (p->shard_capacity != 0 && p->shard_first_index + p->shard_capacity > p->max_particles) {
+    g_create_error = "a shard must lie inside [0, max_particles)";
     return BB200_ERR_INVALID_ARGUMENT;
   }
   if (p->max_particles == 0 || p->min_particles > p->max_particles) {
@@ -542,9 +542,9 @@ int bb200_amcl_update_scan(bb200_amcl* a, const double control_pose[4], const bb
 
 // ---- sharded filters ---------------------------------------------------------------------------------
 
-int bb200_amcl_export_shard(bb200_amcl* a, void* out192) {
-  BB_REQUIRE(a && out192);
-  return guarded(a->impl, [&] { return a->impl.filter().export_shard(out192); });
+int bb200_amcl_export_shard(bb200_amcl* a, void* out256) {
+  BB_REQUIRE(a && out256);
+  return guarded(a->impl, [&] { return a->impl.filter().export_shard(out256); });
 }
 int bb200_amcl_join_shards(bb200_amcl* a, int world, int rank, const void* handles) {
   BB_REQUIRE(a && handles);
@@ -554,9 +554,9 @@ int bb200_amcl_leave_shards(bb200_amcl* a) {
   BB_REQUIRE(a);
   return guarded(a->impl, [&] { return a->impl.filter().leave_shards(); });
 }
-int bb200_filter_export_shard(bb200_filter* f, void* out192) {
-  BB_REQUIRE(f && out192);
-  return guarded(f->impl, [&] { return f->impl.export_shard(out192); });
+int bb200_filter_export_shard(bb200_filter* f, void* out256) {
+  BB_REQUIRE(f && out256);
+  return guarded(f->impl, [&] { return f->impl.export_shard(out256); });
 }
 int bb200_filter_join_shards(bb200_filter* f, int world, int rank, const void* handles) {
   BB_REQUIRE(f && handles);
@@ -579,7 +579,6 @@ int bb200_sharded_amcl_create(const bb200_amcl_param* p, const bb200_motion_para
     std::vector<bb200::Filter*> filters;
     for (int r = 0; r < n_shards; ++r) {
       bb200_amcl_param q = *p;
-      q.min_particles = q.max_particles;  // the particle count of a sharded filter is fixed
       q.device = devices[r];
       q.shard_capacity = shard;
       q.shard_first_index = static_cast<uint64_t>(r) * shard;
@@ -588,10 +587,6 @@ int bb200_sharded_amcl_create(const bb200_amcl_param* p, const bb200_motion_para
       if (st != BB200_OK) return st;
       group->ranks.push_back(a);
       filters.push_back(&a->impl.filter());
-    }
-    if (p->min_particles != p->max_particles) {
-      g_create_error = "KLD-adaptive resampling is not available on a sharded filter (min_particles must equal max_particles)";
-      return static_cast<int>(BB200_ERR_INVALID_ARGUMENT);
     }
     const int st = bb200::Filter::join_shards_local(filters.data(), n_shards);
     if (st != BB200_OK) {

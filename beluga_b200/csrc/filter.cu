@@ -117,6 +117,7 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   if (const char* v = std::getenv("BB200_PER_BIN")) schedule_per_bin_ = std::atof(v);        // development knob: particles per pose bin
   if (const char* v = std::getenv("BB200_LEVER")) schedule_lever_ = std::atof(v);            // development knob: heading lever arm / mean range
   capacity_ = config.capacity;
+  first_index_ = config.first_index;
 #define BB_TRY(expr)                                \
   do {                                              \
     const int st = check((expr), #expr);            \
@@ -155,6 +156,7 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   BB_TRY(cudaMemsetAsync(scalars_, 0, sizeof(Scalars), stream_));
   BB_TRY(cudaStreamSynchronize(stream_));
 #undef BB_TRY
+  global_size_ = config_.global_count;
   created_ = true;
 }
 
@@ -203,6 +205,8 @@ Filter::~Filter() {
   cudaFree(kld_vals_);
   cudaFree(kld_flags_);
   cudaFree(kld_scan_);
+  cudaFree(kld_tile_state_);
+  cudaFree(kld_hashes_global_);
   cudaFree(points_);
   cudaFreeHost(points_host_);
   cudaFree(table_);
@@ -377,11 +381,13 @@ void Filter::release_peers() {
       for (int b = 0; b < 2; ++b)
         if (peer_states_[b][r] != nullptr) cudaIpcCloseMemHandle(peer_states_[b][r]);
       if (peer_mail_[r] != nullptr) cudaIpcCloseMemHandle(peer_mail_[r]);
+      if (peer_kld_hashes_[r] != nullptr) cudaIpcCloseMemHandle(peer_kld_hashes_[r]);
     }
   }
   for (int r = 0; r < kMaxShards; ++r) {
     peer_states_[0][r] = peer_states_[1][r] = nullptr;
     peer_mail_[r] = nullptr;
+    peer_kld_hashes_[r] = nullptr;
   }
   peer_world_ = 0;
   peers_ipc_ = false;
@@ -394,14 +400,24 @@ int Filter::leave_shards() {
   return BB200_OK;
 }
 
-int Filter::export_shard(void* out192) {
+int Filter::enable_shard_kld() {
+  if (kld_hashes_global_ != nullptr) return BB200_OK;
+  if (peer_world_ != 0) return fail(BB200_ERR_STATE, "KLD on shards must be enabled before the shards are joined");
   BB_CHECK(cudaSetDevice(config_.device));
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "three IPC handles are exported as 192 bytes");
-  cudaIpcMemHandle_t h[3];
+  BB_CHECK(dev_alloc(&kld_hashes_global_, config_.global_count));  // one spatial hash per candidate slot of the WHOLE filter
+  return BB200_OK;
+}
+
+int Filter::export_shard(void* out256) {
+  BB_CHECK(cudaSetDevice(config_.device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "four IPC handles are exported as 256 bytes");
+  cudaIpcMemHandle_t h[4];
+  std::memset(h, 0, sizeof(h));
   BB_CHECK(cudaIpcGetMemHandle(&h[0], states_[0]));
   BB_CHECK(cudaIpcGetMemHandle(&h[1], states_[1]));
   BB_CHECK(cudaIpcGetMemHandle(&h[2], mail_));
-  std::memcpy(out192, h, sizeof(h));
+  if (kld_hashes_global_ != nullptr) BB_CHECK(cudaIpcGetMemHandle(&h[3], kld_hashes_global_));
+  std::memcpy(out256, h, sizeof(h));
   return BB200_OK;
 }
 
@@ -420,14 +436,18 @@ int Filter::join_shards_ipc(int world, int rank, const void* handles) {
       peer_states_[0][r] = states_[0];
       peer_states_[1][r] = states_[1];
       peer_mail_[r] = mail_;
+      peer_kld_hashes_[r] = kld_hashes_global_;
       continue;
     }
-    void* p[3] = {nullptr, nullptr, nullptr};
-    for (int b = 0; b < 3; ++b) {
-      const int st = check(cudaIpcOpenMemHandle(&p[b], all[3 * r + b], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    static const cudaIpcMemHandle_t kNoHandle{};
+    void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int b = 0; b < 4; ++b) {
+      if (b == 3 && (kld_hashes_global_ == nullptr || std::memcmp(&all[4 * r + 3], &kNoHandle, sizeof(kNoHandle)) == 0)) continue;  // no KLD on this filter
+      const int st = check(cudaIpcOpenMemHandle(&p[b], all[4 * r + b], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
       if (st != BB200_OK) {
         peer_states_[0][r] = static_cast<Pose2*>(p[0]);
         peer_states_[1][r] = static_cast<Pose2*>(p[1]);
+        peer_mail_[r] = static_cast<ShardMail*>(p[2]);
         release_peers();
         return st;
       }
@@ -435,7 +455,10 @@ int Filter::join_shards_ipc(int world, int rank, const void* handles) {
     peer_states_[0][r] = static_cast<Pose2*>(p[0]);
     peer_states_[1][r] = static_cast<Pose2*>(p[1]);
     peer_mail_[r] = static_cast<ShardMail*>(p[2]);
+    peer_kld_hashes_[r] = static_cast<unsigned long long*>(p[3]);
   }
+  shard_kld_ = kld_hashes_global_ != nullptr;
+  for (int r = 0; r < world; ++r) shard_kld_ = shard_kld_ && peer_kld_hashes_[r] != nullptr;
   split_posts_ = false;  // every rank has its own host thread: post and wait travel in one launch
   return BB200_OK;
 }
@@ -466,7 +489,10 @@ int Filter::join_shards_local(Filter* const* filters, int world) {
       fa->peer_states_[0][b] = fb->states_[0];
       fa->peer_states_[1][b] = fb->states_[1];
       fa->peer_mail_[b] = fb->mail_;
+      fa->peer_kld_hashes_[b] = fb->kld_hashes_global_;
     }
+    fa->shard_kld_ = true;
+    for (int b = 0; b < world; ++b) fa->shard_kld_ = fa->shard_kld_ && filters[b]->kld_hashes_global_ != nullptr;
     fa->peer_world_ = world;
     fa->peer_rank_ = a;
     fa->peers_ipc_ = false;
@@ -498,14 +524,16 @@ int Filter::enqueue_exchange(int kind, bool post, bool wait) {
 
 int Filter::step_begin(const bb200_motion_sampling& sampling, uint32_t step, const double* points_xy, uint64_t n_points, const bb200_resample_opts& o,
                        bool resample_planned) {
-  if (n_ == 0) return fail(BB200_ERR_STATE, "no particles");
+  const uint64_t world = peer_world_ > 1 ? static_cast<uint64_t>(peer_world_) : 1;
+  const bool kld = o.min_particles < o.max_particles;
+  if (n_ == 0 && !(world > 1 && shard_kld_)) return fail(BB200_ERR_STATE, "no particles");  // a KLD-sized filter may leave a shard empty
   if (sensor_ < 0) return fail(BB200_ERR_STATE, "no sensor model map set");
-  if (o.min_particles < o.max_particles) return fail(BB200_ERR_STATE, "the fused step does not run KLD; use resample()");
+  if (kld && !(world > 1 && shard_kld_)) return fail(BB200_ERR_STATE, "the fused step does not run KLD on one GPU; use resample()");
   if (n_points > 0xffffffffull) return fail(BB200_ERR_INVALID_ARGUMENT, "too many points");
   if (o.random_state_probability > 0.0 && n_free_ == 0) return fail(BB200_ERR_STATE, "recovery injection needs a map with free cells");
-  const uint64_t world = peer_world_ > 1 ? static_cast<uint64_t>(peer_world_) : 1;
   if (world > 1) {
-    if (n_ != capacity_ || o.max_particles != world * capacity_) return fail(BB200_ERR_STATE, "a sharded filter keeps `capacity` particles on every rank");
+    if ((!shard_kld_ && n_ != capacity_) || n_ > capacity_ || o.max_particles != world * capacity_)
+      return fail(BB200_ERR_STATE, "a sharded filter keeps `capacity` particles on every rank (fewer only under KLD)");
   } else if (o.max_particles == 0 || o.max_particles > capacity_) {
     return fail(BB200_ERR_CAPACITY, "max_particles exceeds the filter capacity");
   }
@@ -589,18 +617,25 @@ int Filter::step_phase(int phase) {
           step_.totals_exchanged = true;
         }
         const bool systematic = o.scheme == BB200_RESAMPLE_SYSTEMATIC;
-        a = make_resample_args(o, 0, systematic ? capacity_ : o.max_particles, false);
+        const uint64_t accepted = step_.kld_accepted;  // KLD on shards: the count take_while_kld settled on (0: fixed size)
+        const uint64_t slots = accepted != 0 ? accepted : o.max_particles;
+        a = make_resample_args(o, 0, systematic ? capacity_ : slots, false);
         a.slot_first = 0;
         a.weights_out = nullptr;
         a.ancestors = nullptr;
         a.peer_count = peer_world_;
-        a.peer_shard = capacity_;
+        a.peer_shard = accepted != 0 ? (accepted + static_cast<uint64_t>(peer_world_) - 1) / static_cast<uint64_t>(peer_world_) : capacity_;
         a.rank_totals = shard_totals_;
         a.rank = peer_rank_;
         a.world = peer_world_;
+        if (accepted != 0) {  // the comb still spans max_particles slots; only [0, accepted) are kept
+          a.window_begin = 0;
+          a.window_end = accepted;
+          a.inject_mod = peer_world_;
+        }
         if (!systematic) {  // draws are independent: walk all global slots, keep those landing in this rank's CDF span
           a.span_filter = 1;
-          a.owner_first = config_.first_index;
+          a.owner_first = first_index_;
           a.owner_count = capacity_;
         }
         for (int r = 0; r < peer_world_; ++r) a.peer_out[r] = peer_states_[cur_ ^ 1][r];
@@ -667,6 +702,96 @@ int Filter::step_phase(int phase) {
   }
 }
 
+int Filter::kld_sharded_candidates(uint64_t begin, uint64_t end) {
+  if (!step_.active || !shard_kld_ || peer_world_ < 2) return fail(BB200_ERR_STATE, "KLD on shards: no step in progress on a KLD-enabled shard group");
+  if (!step_.totals_exchanged) return fail(BB200_ERR_STATE, "KLD on shards: the totals exchange must run first");
+  if (end <= begin || end > config_.global_count) return fail(BB200_ERR_INVALID_ARGUMENT, "KLD on shards: bad slot window");
+  BB_CHECK(cudaSetDevice(config_.device));
+  const bb200_resample_opts& o = step_.opts;
+  if (kld_keys_ == nullptr) {  // the counting pass runs over ALL slots on every rank: tables sized for the whole filter
+    const uint64_t n = config_.global_count;
+    BB_CHECK(dev_alloc(&kld_flags_, n));
+    BB_CHECK(dev_alloc(&kld_scan_, n));
+    kld_table_size_ = 2;
+    while (kld_table_size_ < 2 * n) kld_table_size_ <<= 1;
+    BB_CHECK(dev_alloc(&kld_keys_, kld_table_size_));
+    BB_CHECK(dev_alloc(&kld_vals_, kld_table_size_));
+    BB_CHECK(dev_alloc(&kld_tile_state_, static_cast<size_t>(scan_tile_count(n)) + 1));
+  }
+  if (begin == 0) {
+    mark("kld");
+    launch_kld_clear(kld_keys_, kld_vals_, kld_table_size_, stream_);
+  }
+  const bool systematic = o.scheme == BB200_RESAMPLE_SYSTEMATIC;
+  ResampleArgs a = make_resample_args(o, 0, std::min<uint64_t>(end - begin, capacity_), false);
+  a.states_out = nullptr;
+  a.weights_out = nullptr;
+  a.ancestors = nullptr;
+  a.rank_totals = shard_totals_;
+  a.rank = peer_rank_;
+  a.world = peer_world_;
+  a.window_begin = begin;
+  a.window_end = end;
+  a.peer_hash_count = peer_world_;
+  for (int r = 0; r < peer_world_; ++r) a.peer_hashes[r] = peer_kld_hashes_[r];
+  a.inject_mod = peer_world_;
+  a.slot_first = 0;
+  if (!systematic) {
+    a.span_filter = 1;
+    a.slot_first = begin;
+    a.slot_count = end - begin;
+  }
+  mark("kld_candidates");
+  launch_resample(a, scalars_, partials_, stream_);
+  BB_LAUNCHED("kld_candidates");
+  ++epoch_;
+  if (split_posts_) return enqueue_exchange(kExchangeKld, true, false);
+  return BB200_OK;
+}
+
+int Filter::kld_sharded_count(uint64_t begin, uint64_t end, uint64_t k_before) {
+  if (!step_.active || !shard_kld_) return fail(BB200_ERR_STATE, "KLD on shards: no step in progress");
+  BB_CHECK(cudaSetDevice(config_.device));
+  const bb200_resample_opts& o = step_.opts;
+  mark("exchange_kld");
+  const int st = enqueue_exchange(kExchangeKld, !split_posts_, true);  // every rank's hashes of this window have arrived
+  if (st != BB200_OK) return st;
+  mark("kld");
+  KldArgs k{kld_hashes_global_ + begin, end - begin, begin, k_before, o.min_particles, o.kld_epsilon, o.kld_z};
+  launch_kld_chunk(k, kld_keys_, kld_vals_, kld_table_size_, kld_flags_, kld_scan_, scalars_, kld_tile_state_, stream_);
+  BB_LAUNCHED_N("kld", 5);
+  BB_CHECK(cudaMemcpyAsync(scalars_host_, scalars_, sizeof(Scalars), cudaMemcpyDeviceToHost, stream_));
+  return BB200_OK;
+}
+
+int Filter::kld_sharded_read(uint64_t* cutoff, uint64_t* new_buckets) {
+  BB_CHECK(cudaSetDevice(config_.device));
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  if (scalars_host_->exchange_error != 0) return fail(BB200_ERR_STATE, "shard exchange timed out during the KLD count");
+  *cutoff = scalars_host_->kld_cutoff;
+  *new_buckets = scalars_host_->pad[1];
+  return BB200_OK;
+}
+
+int Filter::step_totals(uint64_t* rank_totals, int* exponent) {
+  if (!step_.active || peer_world_ < 2) return fail(BB200_ERR_STATE, "no sharded step in progress");
+  BB_CHECK(cudaSetDevice(config_.device));
+  if (!step_.totals_exchanged) {
+    mark("exchange_total");
+    const int st = enqueue_exchange(kExchangeTotal, !split_posts_, true);
+    if (st != BB200_OK) return st;
+    step_.totals_exchanged = true;
+  }
+  if (rank_totals == nullptr) return BB200_OK;  // enqueue only
+  BB_CHECK(cudaStreamSynchronize(stream_));
+  if (summary_host_->error != 0) return fail(BB200_ERR_STATE, "shard exchange timed out");
+  for (int r = 0; r < peer_world_; ++r) rank_totals[r] = summary_host_->rank_totals[r];
+  if (exponent != nullptr) *exponent = summary_host_->exponent;
+  return BB200_OK;
+}
+
+void Filter::step_set_kld_accepted(uint64_t accepted) { step_.kld_accepted = accepted; }
+
 int Filter::step_end(bb200_estimate* est, double* weight_sum, uint64_t* new_size, double* sum_sq) {
   if (!step_.active) return fail(BB200_ERR_STATE, "step_begin must run first");
   BB_CHECK(cudaSetDevice(config_.device));
@@ -684,6 +809,14 @@ int Filter::step_end(bb200_estimate* est, double* weight_sum, uint64_t* new_size
   if (step_.resampled) {
     cur_ ^= 1;
     n_ = sharded ? capacity_ : step_.opts.max_particles;
+    if (sharded && step_.kld_accepted != 0) {  // the new set of `accepted` particles in equal contiguous shards
+      const uint64_t shard = (step_.kld_accepted + static_cast<uint64_t>(peer_world_) - 1) / static_cast<uint64_t>(peer_world_);
+      const uint64_t begin = std::min<uint64_t>(static_cast<uint64_t>(peer_rank_) * shard, step_.kld_accepted);
+      n_ = std::min<uint64_t>(shard, step_.kld_accepted - begin);
+      first_index_ = static_cast<uint64_t>(peer_rank_) * shard;
+    } else if (sharded) {
+      first_index_ = config_.first_index;
+    }
     ancestors_n_ = n_;
     cdf_valid_ = false;
     step_.active = false;
@@ -691,7 +824,8 @@ int Filter::step_end(bb200_estimate* est, double* weight_sum, uint64_t* new_size
     cdf_valid_ = true;  // kPhaseResample may still follow (selective resampling)
     ++epoch_;           // ... as a new batch of exchanges
   }
-  if (new_size != nullptr) *new_size = sharded ? config_.global_count : n_;
+  if (new_size != nullptr) *new_size = !sharded ? n_ : (step_.resampled && step_.kld_accepted != 0 ? step_.kld_accepted : global_size_);
+  if (sharded && step_.resampled) global_size_ = step_.kld_accepted != 0 ? step_.kld_accepted : config_.global_count;
   if (weight_sum != nullptr) *weight_sum = std::ldexp(static_cast<double>(step_.total), -step_.exponent);
   if (sum_sq != nullptr) *sum_sq = moments[1];
   if (!weights_valid_) error_ = "no positive finite weight (uniform CDF substituted)";
@@ -718,7 +852,7 @@ int Filter::enqueue_resample_push(const bb200_resample_opts& o, uint64_t global_
   a.slot_first = slot_begin;
   if (o.scheme != BB200_RESAMPLE_SYSTEMATIC) {  // draws are independent: every rank filters the global slots by its CDF span
     a.span_filter = 1;
-    a.owner_first = config_.first_index;
+    a.owner_first = first_index_;
     a.owner_count = shard;
   }
   a.global_total = global_total;
@@ -761,7 +895,7 @@ int Filter::enqueue_resample_push_device(const bb200_resample_opts& o, const uin
   a.world = world;
   if (!systematic) {
     a.span_filter = 1;
-    a.owner_first = config_.first_index;
+    a.owner_first = first_index_;
     a.owner_count = shard;
   }
   for (int r = 0; r < peer_world_; ++r) a.peer_out[r] = peer_states_[cur_ ^ 1][r];
@@ -1028,7 +1162,7 @@ int Filter::initialize_normal(const double mean[3], const double cov[9], uint64_
   std::string message;
   if (!normal_transform(cov, transform, &message)) return fail(BB200_ERR_INVALID_ARGUMENT, message);
   BB_CHECK(cudaSetDevice(config_.device));
-  launch_initialize_normal(states_[cur_], weights_, n, mean, transform, config_.seed, config_.first_index, stream_);
+  launch_initialize_normal(states_[cur_], weights_, n, mean, transform, config_.seed, first_index_, stream_);
   BB_LAUNCHED("initialize_normal");
   BB_CHECK(cudaStreamSynchronize(stream_));
   n_ = n;
@@ -1049,7 +1183,7 @@ int Filter::initialize_uniform(uint64_t n) {
   if (n_free_ == 0) return fail(BB200_ERR_STATE, "the map has no free cell to sample from");
   BB_CHECK(cudaSetDevice(config_.device));
   launch_initialize_uniform(states_[cur_], weights_, n, free_cells_, n_free_, grid_width_, grid_resolution_, grid_origin_, config_.seed,
-                            config_.first_index, stream_);
+                            first_index_, stream_);
   BB_LAUNCHED("initialize_uniform");
   BB_CHECK(cudaStreamSynchronize(stream_));
   n_ = n;
@@ -1119,7 +1253,7 @@ int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t 
   if (scheduled && counters_reset && sampling != nullptr && predict_schedule(*sampling, &grid)) {
     // Bin grid predicted on the host: propagate histograms its own output, two more launches turn it into the order.
     mark("propagate");
-    launch_propagate_binned(states_[cur_], n_, *sampling, config_.seed, step, config_.first_index, grid, bin_rank_, counters_, sched_, stream_);
+    launch_propagate_binned(states_[cur_], n_, *sampling, config_.seed, step, first_index_, grid, bin_rank_, counters_, sched_, stream_);
     BB_LAUNCHED("propagate");
     mark("schedule");
     launch_finish_schedule(bin_rank_, n_, grid.n_bins, sched_, counters_, perm_, sched_tiles_, stream_);
@@ -1128,7 +1262,7 @@ int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t 
   } else if (sampling != nullptr || scheduled) {
     mark("propagate");
     launch_propagate(states_[cur_], n_, sampling != nullptr, sampling != nullptr ? *sampling : MotionSampling{}, config_.seed, step,
-                     config_.first_index, scheduled ? sched_ : nullptr, stream_);
+                     first_index_, scheduled ? sched_ : nullptr, stream_);
     BB_LAUNCHED_N("propagate", scheduled ? 2 : 1);
   }
   if (scheduled && perm == nullptr) {
@@ -1150,7 +1284,6 @@ int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t 
         if (words > beam_hits_words_) {
           BB_CHECK(cudaStreamSynchronize(stream_));
           cudaFree(beam_hits_);
-  cudaFree(free_padded_);
           beam_hits_ = nullptr;
           beam_hits_words_ = 0;
           // sized for the filter's capacity so that a growing particle count (KLD) does not reallocate every step
@@ -1483,7 +1616,7 @@ ResampleArgs Filter::make_resample_args(const bb200_resample_opts& o, uint64_t s
   a.weights_out = weights_ + slot_begin;
   a.ancestors = ancestors_ != nullptr ? ancestors_ + slot_begin : nullptr;
   a.hashes = with_hashes ? hashes_ + slot_begin : nullptr;
-  a.slot_first = config_.first_index + slot_begin;
+  a.slot_first = first_index_ + slot_begin;
   a.slot_count = slot_end - slot_begin;
   a.total_slots = o.max_particles;
   a.scheme = o.scheme;
@@ -1572,7 +1705,7 @@ int Filter::adopt(uint64_t n, int from_staging) {
 }
 
 int Filter::resample_kld(const bb200_resample_opts& o, uint64_t* accepted) {
-  if (config_.global_count != capacity_ || config_.first_index != 0) return fail(BB200_ERR_STATE, "KLD-adaptive resampling runs on a single shard");
+  if (config_.global_count != capacity_ || first_index_ != 0) return fail(BB200_ERR_STATE, "KLD-adaptive resampling runs on a single shard");
   if (o.max_particles >= (1ull << 32)) return fail(BB200_ERR_CAPACITY, "KLD-adaptive resampling keeps 32-bit slot indices: max_particles must be below 2^32");
   if (hashes_ == nullptr) {
     BB_CHECK(dev_alloc(&hashes_, capacity_));

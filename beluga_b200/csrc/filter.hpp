@@ -85,8 +85,11 @@ class Filter {
 
   // ---- one filter over several shards, exchanges through peer memory (no NCCL, no host round trip) ----
   /// CUDA IPC handles of the two state buffers and the mail block (3 x 64 bytes) for peers in OTHER processes.
-  int export_shard(void* out192);
-  /// Map the peers' buffers from their exported handles (world x 192 bytes, rank order); one process per GPU.
+  int export_shard(void* out256);
+  /// KLD-adaptive resampling on shards needs one hash array of the WHOLE filter's slot count on every rank, exported
+  /// with the other buffers: call before export_shard / join_shards_local.
+  int enable_shard_kld();
+  /// Map the peers' buffers from their exported handles (world x 256 bytes, rank order); one process per GPU.
   int join_shards_ipc(int world, int rank, const void* handles);
   /// Shards living in THIS process (one per device, or several on one device): direct pointers, peer access enabled
   /// between distinct devices.  filters[r] becomes rank r.
@@ -108,6 +111,19 @@ class Filter {
   };
   int step_phase(int phase);
   void step_abort();
+  // KLD on shards (views/take_while_kld.hpp:72-137 over the globally ordered candidate stream).  After kPhaseCdf:
+  //   step_totals            the ranks' fixed-point totals (also enqueues their exchange)
+  //   kld_sharded_candidates hashes of this rank's candidates among the slots [begin, end) -> every rank's hash array
+  //   kld_sharded_count      (after all ranks' candidates) distinct-bucket count over the window, on every rank alike
+  //   kld_sharded_read       first failing count (~0: none in this window), new buckets of the window
+  //   step_set_kld_accepted  the count the loop settled on; kPhaseResample then produces exactly those slots
+  int step_totals(uint64_t* rank_totals, int* exponent);
+  int kld_sharded_candidates(uint64_t begin, uint64_t end);
+  int kld_sharded_count(uint64_t begin, uint64_t end, uint64_t k_before);
+  int kld_sharded_read(uint64_t* cutoff, uint64_t* new_buckets);
+  void step_set_kld_accepted(uint64_t accepted);
+  bool shard_kld() const { return shard_kld_; }
+  uint64_t global_size() const { return peer_world_ > 1 ? global_size_ : n_; }
   /// Synchronises and closes the batch of phases enqueued so far.  After kPhaseNormalize a caller may still run
   /// kPhaseResample + kPhaseFinish + step_end (selective resampling: the decision needs the effective sample size).
   int step_end(bb200_estimate* est, double* weight_sum, uint64_t* new_size, double* sum_sq);
@@ -153,7 +169,8 @@ class Filter {
     bool normalized{false};  // kPhaseNormalize ran (weights are normalised, the CDF stays valid)
     bool resample_planned{false};  // kPhaseResample follows kPhaseCdf directly (every_n fired, no ESS decision in between)
     bool weights_filled{false};
-    bool totals_exchanged{false};  // the ranks' totals of this step are in shard_totals_
+    bool totals_exchanged{false};
+    uint64_t kld_accepted{0};  // KLD on shards: particle count of the new set (0: fixed size)  // the ranks' totals of this step are in shard_totals_
     unsigned long long total{0};
     int exponent{0};
   };
@@ -181,6 +198,8 @@ class Filter {
 
   // particle set (ping-pong states for the resample gather)
   uint64_t capacity_{0}, n_{0};
+  uint64_t first_index_{0};   // global index of local particle 0 (moves when a KLD-sized filter re-splits its particles)
+  uint64_t global_size_{0};   // particles over all shards
   Pose2* states_[2]{nullptr, nullptr};
   int cur_{0};
   double* weights_{nullptr};
@@ -212,6 +231,10 @@ class Filter {
   uint64_t kld_table_size_{0};
   uint32_t* kld_flags_{nullptr};
   uint32_t* kld_scan_{nullptr};
+  unsigned long long* kld_tile_state_{nullptr};
+  unsigned long long* kld_hashes_global_{nullptr};          // KLD on shards: spatial hash of every candidate slot (all ranks hold all)
+  unsigned long long* peer_kld_hashes_[kMaxShards]{};
+  bool shard_kld_{false};
 
   // measurement
   double* points_{nullptr};

@@ -1640,8 +1640,14 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, Sc
         return j < a.total_slots ? j : a.total_slots;
       };
       slot_first = first_slot_at_or_after(cdf_offset);
-      const uint64_t slot_end = a.rank + 1 == a.world ? a.total_slots : first_slot_at_or_after(span_end);
-      slot_count = slot_end - slot_first;
+      uint64_t slot_end = a.rank + 1 == a.world ? a.total_slots : first_slot_at_or_after(span_end);
+      // KLD on shards: only the slots of the current window [window_begin, window_end) -- the chunk being counted, or
+      // [0, accepted count) for the final pass -- are produced.
+      if (a.window_end > a.window_begin) {
+        slot_first = slot_first < a.window_begin ? a.window_begin : slot_first;
+        slot_end = slot_end > a.window_end ? a.window_end : slot_end;
+      }
+      slot_count = slot_end > slot_first ? slot_end - slot_first : 0;
     }
   }
   double m[kMomentCount];
@@ -1661,7 +1667,11 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, Sc
     unsigned long long t = 0;
     if (!inject) t = a.scheme == 1 ? offset + j * stride : mulhi64(d.b, total);
     if (a.span_filter != 0) {
-      const bool mine = inject ? (j >= a.owner_first && j - a.owner_first < a.owner_count) : (t >= cdf_offset && t - cdf_offset < scalars->total);
+      // an injected state belongs to the slot's owner; with a particle count that is still being decided (KLD on shards)
+      // slots are dealt round robin instead
+      const bool my_slot = a.inject_mod > 0 ? (j % static_cast<uint64_t>(a.inject_mod) == static_cast<uint64_t>(a.rank))
+                                            : (j >= a.owner_first && j - a.owner_first < a.owner_count);
+      const bool mine = inject ? my_slot : (t >= cdf_offset && t - cdf_offset < scalars->total);
       if (!mine) continue;
     }
     if (inject) {
@@ -1671,6 +1681,13 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(ResampleArgs a, Sc
       const uint64_t idx = cdf_upper_bound(a.cdf, a.n_in, t - cdf_offset);  // the caller guarantees t lies in this shard's span
       ancestor = static_cast<long long>(idx);
       st = load_pose(a.states_in + idx);
+    }
+    if (a.peer_hash_count > 0) {
+      // KLD on shards, counting pass: only the candidate's spatial hash is needed, and every rank needs it -- the
+      // ranks then count distinct buckets over the same globally ordered hash stream and reach the same cutoff.
+      const unsigned long long h = spatial_hash(st, a.hash_resolution[0], a.hash_resolution[1], a.hash_resolution[2]);
+      for (int r = 0; r < a.peer_hash_count; ++r) a.peer_hashes[r][j] = h;
+      continue;
     }
     if (a.peer_count > 0) {
       const uint64_t owner = j / a.peer_shard;  // P2P store over NVLink (or a local store when owner == this rank)
@@ -1736,6 +1753,8 @@ __global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleAr
   }
   __syncthreads();
   const unsigned long long stride = s_comb[0], offset = s_comb[1], magic = s_comb[2];
+  // the comb spans total_slots; only the slots below window_end (KLD: the accepted count) are produced
+  const uint64_t slot_limit = a.window_end > 0 ? a.window_end : a.total_slots;
   const int lane = threadIdx.x % kWarp;
   double m[kMomentCount];
 #pragma unroll
@@ -1768,8 +1787,8 @@ __global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleAr
       ja[u] = 0;
       copies[u] = 0;
       if (i < a.n_in) {
-        ja[u] = comb_slots_before_magic(cdf_offset + (i > 0 ? __ldg(a.cdf + i - 1) : 0ull), offset, stride, magic, a.total_slots);
-        copies[u] = comb_slots_before_magic(cdf_offset + __ldg(a.cdf + i), offset, stride, magic, a.total_slots) - ja[u];
+        ja[u] = comb_slots_before_magic(cdf_offset + (i > 0 ? __ldg(a.cdf + i - 1) : 0ull), offset, stride, magic, slot_limit);
+        copies[u] = comb_slots_before_magic(cdf_offset + __ldg(a.cdf + i), offset, stride, magic, slot_limit) - ja[u];
       }
     }
     Pose2 st[kRsUnroll];
@@ -2182,6 +2201,7 @@ uint32_t launch_resample(const ResampleArgs& args, Scalars* scalars, double* mom
   // The whole set on one GPU with the systematic comb and nothing per slot to draw: scatter form.
   // (Sharded with peer memory and device-side totals: the same, every copy stored into its owner's buffer.)
   const bool plain = args.scheme == 1 && args.random_state_probability <= 0.0 && args.hashes == nullptr && args.span_filter == 0 &&
+                     args.peer_hash_count == 0 && args.window_begin == 0 &&
                      args.global_total == 0 && args.cdf_offset == 0 && args.slot_first == 0 && scatter_resample_enabled();
   const bool scatter = plain && ((args.peer_count == 0 && args.rank_totals == nullptr && args.slot_count == args.total_slots) ||
                                  (args.peer_count > 0 && args.rank_totals != nullptr));

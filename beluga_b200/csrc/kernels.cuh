@@ -302,6 +302,13 @@ struct ResampleArgs {
   // for the systematic comb -- its slot range itself, so the host does not have to read the totals back first.
   const unsigned long long* rank_totals;
   int rank, world;
+  // KLD on shards.  window: produce only the slots in [window_begin, window_end) (0, 0: all).  peer_hashes: counting
+  // pass -- write the candidate's spatial hash to entry [slot] of every rank's hash array instead of storing the state.
+  // inject_mod: recovery injection of slot j is handled by rank j % inject_mod (0: by the slot's owner).
+  uint64_t window_begin, window_end;
+  int peer_hash_count;
+  unsigned long long* peer_hashes[8];
+  int inject_mod;
   int scheme;
   uint64_t seed;
   uint32_t step;

@@ -4,7 +4,7 @@ Default path (p2p=True, up to 8 ranks with peer access): the whole sharded step 
 bb200_amcl_update -- the three per-step exchanges (largest weight, fixed-point totals, raw moments) go through
 mail blocks in peer memory written and polled by single-CTA kernels, the resampled states are stored straight
 into the slot owner's buffer over NVLink by the resample kernel itself.  torch.distributed is used ONCE, at
-construction, to hand the 192-byte CUDA IPC handle blobs around (any transport would do).  No NCCL call, no
+construction, to hand the 256-byte CUDA IPC handle blobs around (any transport would do).  No NCCL call, no
 host round trip inside a step; one host synchronisation per step.
 
 Fallback path (p2p=False, or more than 8 ranks / no peer access): NCCL collectives enqueued from here, described below.
@@ -111,7 +111,7 @@ def _state_view(filter_, which: int, count: int):
 class ShardedAmcl:
     """beluga::Amcl (algorithm/amcl_core.hpp:81-233) over `world` GPUs; call from every rank in lock step."""
 
-    def __init__(self, motion, params, shard: int, process_group=None, p2p: bool = True):
+    def __init__(self, motion, params, shard: int, process_group=None, p2p: bool = True, kld_min_particles: int | None = None):
         import torch
         import torch.distributed as dist
 
@@ -125,7 +125,8 @@ class ShardedAmcl:
         self.shard = shard
         self.total = shard * self.world
         params.max_particles = self.total
-        params.min_particles = self.total
+        # KLD-adaptive sizing on shards (peer-memory path only): pass the lower bound explicitly; the shard size is max_particles / world
+        params.min_particles = int(kld_min_particles) if (kld_min_particles and p2p) else self.total
         params.shard_capacity = shard
         params.shard_first_index = self.rank * shard
         self.params = params

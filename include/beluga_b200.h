@@ -463,11 +463,13 @@ int bb200_amcl_update_scan(bb200_amcl* a, const double control_pose[4], const bb
  * (1) One process, several devices (or several shards on one device): bb200_sharded_amcl -- the shape
  *     of beluga_ros::Amcl (one node, one thread calling update; beluga_ros/src/amcl.cpp:83-126).
  * (2) One process per GPU (torchrun, MPI): every rank creates a bb200_amcl with shard_first_index /
- *     shard_capacity set, exports 192 bytes of CUDA IPC handles (bb200_amcl_export_shard), gathers
+ *     shard_capacity set, exports 256 bytes of CUDA IPC handles (bb200_amcl_export_shard), gathers
  *     the handles of all ranks by whatever transport it has, maps them (bb200_amcl_join_shards) and
  *     from then on calls bb200_amcl_update in lock step with its peers.
  * Policies: every_n resampling and selective resampling (on_effective_size_drop), systematic or
- * multinomial, recovery injection; min_particles must equal max_particles.
+ * multinomial, recovery injection, KLD-adaptive particle counts (min_particles < max_particles: every rank
+ * sees the spatial hash of every candidate slot and counts distinct buckets over the same ordered stream, so
+ * all ranks stop at the reference's count; the new set is re-split into equal contiguous shards).
  * ------------------------------------------------------------------------------------------- */
 typedef struct bb200_sharded_amcl bb200_sharded_amcl;
 /* p->max_particles is the GLOBAL particle count (a multiple of n_shards); devices[r] is the CUDA ordinal of
@@ -489,15 +491,16 @@ int bb200_sharded_amcl_update(bb200_sharded_amcl* g, const double control_pose[4
                               bb200_update_result* out);
 /* particles() in global index order (rank 0's shard first). */
 int bb200_sharded_amcl_get_particles(bb200_sharded_amcl* g, double* states, double* weights, uint64_t capacity);
-/* One process per GPU: CUDA IPC handles of this shard's two state buffers and mail block (192 bytes) ... */
-int bb200_amcl_export_shard(bb200_amcl* a, void* out192);
-/* ... and the mapping of all ranks' handles (world x 192 bytes, rank order).  shard_capacity * world must equal
+#define BB200_SHARD_HANDLE_BYTES 256
+/* One process per GPU: CUDA IPC handles of this shard's two state buffers, mail block and (KLD) hash array (256 bytes) ... */
+int bb200_amcl_export_shard(bb200_amcl* a, void* out256);
+/* ... and the mapping of all ranks' handles (world x 256 bytes, rank order).  shard_capacity * world must equal
  * max_particles and shard_first_index must be rank * shard_capacity. */
 int bb200_amcl_join_shards(bb200_amcl* a, int world, int rank, const void* handles);
 /* Unmap the peers' buffers again.  CUDA IPC wants every importer to close before the exporter frees: call this on all
  * ranks, synchronise the ranks (barrier), then destroy. */
 int bb200_amcl_leave_shards(bb200_amcl* a);
-int bb200_filter_export_shard(bb200_filter* f, void* out192);
+int bb200_filter_export_shard(bb200_filter* f, void* out256);
 int bb200_filter_join_shards(bb200_filter* f, int world, int rank, const void* handles);
 
 /* The two host halves of bb200_amcl_update for callers that drive the filter themselves. */

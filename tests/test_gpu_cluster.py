@@ -133,7 +133,7 @@ def test_particle_histogram_matches_a_host_grouping(bb, orc):
     beluga_ros/particle_cloud.hpp:197-210 with spatial_hash buckets): same bins in first-occurrence order, same
     representatives, weights added in particle order (bit-identical), max_bin_weight."""
     rng = np.random.default_rng(12)
-    base = random_cloud(rng, 300, modes=[(0.0, 0.0, 0.2), (3.0, 1.0, -1.0)])
+    base = random_cloud(rng, 300, modes=[(0.0, 0.0, 0.2, 0.3, 0.2, 0.5), (3.0, 1.0, -1.0, 0.2, 0.1, 0.5)])
     states = base[rng.integers(0, len(base), 20_000)]  # a resampled set: many exact copies of few candidates
     weights = rng.uniform(0.5, 1.5, len(states))
     f = bb.Filter(capacity=len(states))
@@ -161,7 +161,7 @@ def test_particle_histogram_matches_a_host_grouping(bb, orc):
 
 def test_sample_states_draws_by_weight_and_leaves_the_set_alone(bb, orc):
     rng = np.random.default_rng(3)
-    states = random_cloud(rng, 64, modes=[(0.0, 0.0, 0.0)])
+    states = random_cloud(rng, 64, modes=[(0.0, 0.0, 0.0, 0.5, 0.3, 1.0)])
     weights = np.zeros(64)
     weights[[5, 17]] = [1.0, 3.0]
     f = bb.Filter(capacity=64, seed=9)

@@ -117,11 +117,53 @@ def test_sharded_matches_the_oracle(bb, orc, scene):
         assert np.abs(sg - so).max() < 1e-10  # same ancestors everywhere, states through libm
 
 
+@pytest.mark.parametrize("shards,scheme", [(2, 1), (4, 1), (3, 0)])
+def test_kld_on_shards_follows_the_single_filter(bb, scene, shards, scheme):
+    """min_particles < max_particles on a sharded filter: every rank counts distinct spatial-hash buckets over the same
+    globally ordered candidate stream, so the particle count take_while_kld settles on, the Thrun probability that reacts
+    to it, and the particle set itself are those of the single-GPU filter, step by step."""
+    n_max = 12_000 * shards if shards != 3 else 36_000
+    ap = dict(min_particles=600, max_particles=n_max, kld_epsilon=0.05, kld_z=3.0, seed=31, resample_scheme=scheme,
+              spatial_resolution=(0.5, 0.5, float(np.deg2rad(10.0))))
+    single = bb.Amcl(bb.DifferentialDriveModelParam(*MOTION), bb.AmclParams(**ap))
+    group = bb.ShardedAmcl(bb.DifferentialDriveModelParam(*MOTION), bb.AmclParams(**ap), devices=[0] * shards)
+    for f in (single, group):
+        f.update_map(0, bb.LikelihoodFieldModelParam(**LFM), bb.OccupancyGrid(scene.cells, scene.resolution))
+        f.initialize(scene.initial_mean, scene.initial_cov)
+    sizes = []
+    for k in range(8):
+        pose = bb.se2(*scene.poses[k])
+        rs, rg = single.update(pose, scene.scans[k]), group.update(pose, scene.scans[k])
+        assert rs.updated == rg.updated == 1 and rs.resampled == rg.resampled == 1
+        assert rs.n_particles == rg.n_particles, f"step {k}: KLD count {rg.n_particles} on {shards} shards, {rs.n_particles} on one"
+        assert rs.random_state_probability == rg.random_state_probability
+        ss, ws = single.particles()
+        n = int(rs.n_particles)
+        gs, gw = group_particles(group, n)
+        assert np.array_equal(ss, gs), f"step {k}: particle states differ"
+        assert np.all(gw == 1.0)
+        assert np.abs(np.array(rs.estimate.mean) - np.array(rg.estimate.mean)).max() < 1e-11
+        assert np.abs(np.array(rs.estimate.cov) - np.array(rg.estimate.cov)).max() < 1e-11
+        sizes.append(n)
+    assert min(sizes) < n_max and len(set(sizes)) > 1  # the count really adapts
+
+
+def group_particles(group, n):
+    """The first n particles of a sharded filter in global order (each shard holds ceil(n / R) of them, the last fewer)."""
+    r = len(group.shards)
+    shard = -(-n // r)
+    states, weights = [], []
+    for f in group.shards:
+        st, w = f.particles()
+        states.append(st)
+        weights.append(w)
+    assert [len(s) for s in states] == [max(0, min(shard, n - k * shard)) for k in range(r)]
+    return np.concatenate(states), np.concatenate(weights)
+
+
 def test_sharded_errors(bb, scene):
     with pytest.raises(bb.BelugaB200Error):  # not a multiple of the shard count
         bb.ShardedAmcl(bb.DifferentialDriveModelParam(*MOTION), bb.AmclParams(min_particles=1001, max_particles=1001), devices=[0, 0])
-    with pytest.raises(bb.BelugaB200Error):  # KLD needs a variable particle count
-        bb.ShardedAmcl(bb.DifferentialDriveModelParam(*MOTION), bb.AmclParams(min_particles=500, max_particles=1000), devices=[0, 0])
     # a shard that never joined its peers refuses to step instead of hanging
     lone = bb.Amcl(bb.DifferentialDriveModelParam(*MOTION), bb.AmclParams(min_particles=1000, max_particles=1000, shard_first_index=0, shard_capacity=500))
     lone.update_map(0, bb.LikelihoodFieldModelParam(**LFM), bb.OccupancyGrid(scene.cells, scene.resolution))
