@@ -539,18 +539,27 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
 constexpr double kFixedMagicX = 1572864.0;  // 1.5 * 2^20: ulp 2^-32; high word = 0x41380000 + floor(g)      for |g| < 2^19
 constexpr double kFixedMagicY = 393216.0;   // 1.5 * 2^18: ulp 2^-34; high word = 0x41180000 + floor(4 g)    for |g| < 2^17
 constexpr uint32_t kFixedBiasX = 0x41380000u, kFixedBiasY = 0x41180000u;
+// The magic constants ride in the FMAs' addend (per-particle offsets ox, oy below), which saves the two additions per beam
+// but lets THREE roundings at the magic's ulp into the word instead of one (the offset sum and both FMAs): the computed
+// fixed-point value is within 3 half-ulps + 2^-36 cells of the reference's.  Two ulps of guard are added to the offset so
+// that the reference's value lies in (computed - 4.07 ulp, computed + 0.07 ulp): the high word is the reference's cell
+// whenever the fraction word is at least 5.  tests/test_fixed_point_lookup_model.py replays this with exact rationals,
+// including end points a hair (2^-36 .. 2^-30 cells) either side of a cell edge at arbitrary headings.
+constexpr double kFixedGuardX = 4.656612873077392578125e-10;   // 2^-31 = 2 ulp of kFixedMagicX
+constexpr double kFixedGuardY = 1.16415321826934814453125e-10; // 2^-33 = 2 ulp of kFixedMagicY
+constexpr uint32_t kFixedAmbiguous = 4u;  // fraction words 0..4: the cell is not decided (5 * 2^-32 per coordinate)
 
 struct FixedParticle {
   double cx, sx;         // cos, sin of the field-frame heading, times 1/resolution
-  double ox, oy;         // field-frame position in cells, plus the border cell
+  double ox, oy;         // field-frame position in cells, plus the border cell, plus magic constant and guard
   uint32_t x_max, y_max; // width + 1, 4 (height + 1) + 3: largest padded x and 4 * padded y (+ 2 fraction bits)
   uint32_t row_pitch;    // 2^kx: tiles per row
 };
 
-/// `margin` collects the smallest fraction word seen (0 = an ambiguous coordinate).
+/// `margin` collects the smallest fraction word seen (<= kFixedAmbiguous: a coordinate too close to a cell edge to call).
 __device__ __forceinline__ double fixed_lookup(const double* __restrict__ bordered, const FixedParticle& q, double px, double py, uint32_t& margin) {
-  const double gx = fma(px, q.cx, fma(-py, q.sx, q.ox)) + kFixedMagicX;  // gx + 1
-  const double gy = fma(px, q.sx, fma(py, q.cx, q.oy)) + kFixedMagicY;   // gy + 1
+  const double gx = fma(px, q.cx, fma(-py, q.sx, q.ox));  // gx + 1 + magic + guard
+  const double gy = fma(px, q.sx, fma(py, q.cx, q.oy));   // gy + 1 + magic + guard
   margin = __vimin3_u32(margin, static_cast<uint32_t>(__double2loint(gx)), static_cast<uint32_t>(__double2loint(gy)));
   // min(word - bias, max): a negative coordinate wraps to a huge unsigned and clamps to the far border,
   // which holds the same unknown-space value as the near one.
@@ -605,7 +614,7 @@ struct ScanParam {
       const double2 p0 = POINT(b);                                                                            \
       acc = acc + LOOKUP(TABLE, q, p0.x, p0.y, margin);                                                       \
     }                                                                                                         \
-    if (margin == 0u) { /* a coordinate within 2^-33 cells of a cell edge, or a particle out of range */     \
+    if (margin <= kFixedAmbiguous) { /* a coordinate within ~2^-30 cells of a cell edge, or a particle out of range */ \
       const Pose2 te = field_frame_pose(field, states, i, active);                                            \
       acc = acc_before;                                                                                       \
       b = 0;                                                                                                  \
@@ -632,7 +641,9 @@ __device__ __forceinline__ void fixed_particle_setup(const FieldView& field, con
   // The error bound above needs every term of g below 2^13 cells.
   const double reach = (points_radius + fmax(fabs(t.x), fabs(t.y))) * inv + 2.0;
   margin_start = reach < 8100.0 ? 0xFFFFFFFFu : 0u;  // 0 also for NaN: straight to the exact sequence
-  q.cx = t.c * inv, q.sx = t.s * inv, q.ox = t.x * inv + 1.0, q.oy = t.y * inv + 1.0;
+  q.cx = t.c * inv, q.sx = t.s * inv;
+  q.ox = (t.x * inv + 1.0) + (kFixedMagicX + kFixedGuardX);
+  q.oy = (t.y * inv + 1.0) + (kFixedMagicY + kFixedGuardY);
   q.x_max = field.border_x_max;
   q.y_max = field.border_y_max;
   q.row_pitch = field.border_pitch;

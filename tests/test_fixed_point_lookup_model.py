@@ -1,6 +1,7 @@
 """Executable version of the argument behind reweight_lfm_fixed_*_kernel (csrc/kernels.cu): the kernel finds the
 likelihood-field CELL of a beam end point with two FMAs per coordinate and a magic-number add instead of the
-reference's rounded operation sequence, and claims the same cell whenever the fraction word it reads is non-zero.
+reference's rounded operation sequence -- the magic number riding in the FMAs' addend -- and claims the same cell
+whenever the fraction word it reads is at least 5.
 
 This test replays both evaluations on the CPU -- IEEE doubles for the reference sequence, exact rationals rounded
 once for the FMAs -- on random and adversarial (cell-edge) inputs and checks the claim, plus how often the
@@ -14,6 +15,12 @@ import pytest
 
 MAGIC_X, MAGIC_Y = 1572864.0, 393216.0  # 1.5 * 2^20, 1.5 * 2^18 (kFixedMagicX / kFixedMagicY)
 BIAS_X, BIAS_Y = 0x41380000, 0x41180000
+# Folding the magic add into the FMA chain costs three roundings at the magic's ulp (2^-32 for x, 2^-34 for y) instead of
+# one: the computed fixed-point value lies within 3 half-ulps + 2^-36 of the reference's.  Two ulps of guard are added to
+# the offset, so that the uncertainty interval sits entirely BELOW the computed value: the cell is the reference's
+# whenever the fraction word is at least 5 (kFixedGuardX / kFixedGuardY / kFixedAmbiguous in the kernel).
+GUARD_X, GUARD_Y = 2.0 ** -31, 2.0 ** -33
+AMBIGUOUS_BELOW = 4
 
 
 def fma(a: float, b: float, c: float) -> float:
@@ -34,15 +41,16 @@ def reference_cells(px, py, c, s, tx, ty, inv):
 def kernel_cells(px, py, c, s, tx, ty, inv):
     """-> (cell x, cell y, ambiguous) as fixed_lookup computes them (before clamping to the border)."""
     cx, sx = c * inv, s * inv
-    ox, oy = tx * inv + 1.0, ty * inv + 1.0
-    gx = fma(px, cx, fma(-py, sx, ox)) + MAGIC_X
-    gy = fma(px, sx, fma(py, cx, oy)) + MAGIC_Y
+    # the magic constants ride in the FMAs' addend: (offset + 1 border cell) + (magic + guard), each sum rounded once
+    ox, oy = (tx * inv + 1.0) + (MAGIC_X + GUARD_X), (ty * inv + 1.0) + (MAGIC_Y + GUARD_Y)
+    gx = fma(px, cx, fma(-py, sx, ox))
+    gy = fma(px, sx, fma(py, cx, oy))
     hx, lx = words(gx)
     hy, ly = words(gy)
     ux = (hx - BIAS_X) & 0xFFFFFFFF  # padded x = cell + 1 (for cells >= -1)
     uy = (hy - BIAS_Y) & 0xFFFFFFFF  # 4 * padded y + 2 fraction bits
     to_signed = lambda u: u - (1 << 32) if u >= (1 << 31) else u  # noqa: E731
-    return to_signed(ux) - 1, (to_signed(uy) >> 2) - 1, (lx == 0 or ly == 0)
+    return to_signed(ux) - 1, (to_signed(uy) >> 2) - 1, (lx <= AMBIGUOUS_BELOW or ly <= AMBIGUOUS_BELOW)
 
 
 def random_case(rng, res):
@@ -65,7 +73,7 @@ def test_random_end_points(res):
         ambiguous += amb
         if not amb:
             assert (xk, yk) == (xr, yr), case
-    assert ambiguous <= 1  # 2^-32 per coordinate
+    assert ambiguous <= 1  # 5 * 2^-32 per coordinate
 
 
 def test_end_points_on_and_around_cell_edges():
@@ -115,3 +123,38 @@ def test_range_limit_of_the_argument():
         xk, yk, amb = kernel_cells(*case)
         if not amb:
             assert (xk, yk) == (xr, yr), case
+
+
+def test_end_points_a_hair_either_side_of_an_edge_at_any_heading():
+    """Arbitrary headings (every product rounds): end points placed within 2^-30 .. 2^-36 cells of a cell edge, on both
+    sides.  Three roundings at the magic's ulp can move the computed word either way; the guard keeps every such case
+    either flagged or decided like the reference."""
+    rng = np.random.default_rng(11)
+    res = 0.05
+    inv = 1.0 / res
+    flagged = decided = 0
+    for _ in range(1500):
+        theta = rng.uniform(-math.pi, math.pi)
+        c, s = math.cos(theta), math.sin(theta)
+        tx, ty = float(rng.uniform(0.0, 100.0)), float(rng.uniform(0.0, 100.0))
+        py = float(rng.uniform(-30.0, 30.0))
+        if abs(c) < 0.2:
+            continue
+        cell = int(rng.integers(10, 1990))
+        for eps in (0.0, 2.0 ** -36, -2.0 ** -36, 2.0 ** -34, -2.0 ** -34, 2.0 ** -33, -2.0 ** -33, 1.5 * 2.0 ** -32, -1.5 * 2.0 ** -32,
+                    2.0 ** -31, -2.0 ** -31, 2.0 ** -30, -2.0 ** -30):
+            target = (Fraction(cell) + Fraction(eps)) / Fraction(inv)
+            # x word: solve (px * c - py * s + tx) * inv = cell + eps for px in exact arithmetic, then round px once
+            px = float((target - Fraction(tx) + Fraction(py) * Fraction(s)) / Fraction(c))
+            # y word (other magic constant): solve (qx * s + qy * c + ty) * inv = cell + eps for qy
+            qx = py
+            qy = float((target - Fraction(ty) - Fraction(qx) * Fraction(s)) / Fraction(c))
+            for case in ((px, py, c, s, tx, ty, inv), (qx, qy, c, s, tx, ty, inv)):
+                xr, yr = reference_cells(*case)
+                xk, yk, amb = kernel_cells(*case)
+                if amb:
+                    flagged += 1
+                else:
+                    decided += 1
+                    assert (xk, yk) == (xr, yr), (case, eps)
+    assert flagged > 200 and decided > 200
