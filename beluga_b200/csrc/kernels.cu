@@ -1013,18 +1013,6 @@ __global__ void __launch_bounds__(kBeamThreads, kBeamBlocksPerSm)
 // and a branch-free mixture loop.  Hit words: 0xFFFFFFFF = miss, else cy << 16 | cx (grids up to 65535 cells a side).
 
 constexpr uint32_t kHitMiss = 0xFFFFFFFFu;
-#ifndef BB200_WALK_RAYS
-#define BB200_WALK_RAYS 2
-#endif
-#ifndef BB200_WALK_BLOCKS
-#define BB200_WALK_BLOCKS 4
-#endif
-constexpr int kWalkRays = BB200_WALK_RAYS;
-struct WalkState {
-  int index, stride_major, stride_minor, remaining;
-  uint32_t dxspan, dyspan, recip, err1, word;
-  bool active;
-};
 constexpr int kWalkThreads = 256;
 constexpr uint32_t kWalkChunk = 2048;  // far ends staged per shared-memory chunk (32 KB)
 
@@ -1034,7 +1022,9 @@ constexpr uint32_t kWalkChunk = 2048;  // far ends staged per shared-memory chun
 /// iterator state is the linear cell index, advanced by k * (major stride) + m * (minor stride), so the x/y swap of the
 /// steep case (bresenham.hpp:99-105) costs nothing per iteration.  Spans stay below 2^22 (checked by the launcher), so
 /// the 32-bit reciprocal quotient of ray_step is the only path.  16 instructions per iteration instead of 45.
-__global__ void __launch_bounds__(kWalkThreads, BB200_WALK_BLOCKS)
+/// (Walking 2 or 4 rays per thread together was measured on this kernel as well: 21.9 / 25.6 ms against 18.5 ms at C3 --
+/// the per-ray state machine and its activity flags cost more than the second load chain hides.)
+__global__ void __launch_bounds__(kWalkThreads, 4)
     beam_walk_kernel(const Pose2* __restrict__ states, uint64_t n, uint64_t slot_base, uint64_t slot_count, const uint32_t* __restrict__ perm,
                      OccupancyView grid, double beam_max_range, const double2* __restrict__ points, uint32_t n_points,
                      uint32_t* __restrict__ hits, uint64_t hit_stride) {
@@ -1061,79 +1051,57 @@ __global__ void __launch_bounds__(kWalkThreads, BB200_WALK_BLOCKS)
     }
     __syncthreads();
     if (!active) continue;
-    // kWalkRays rays per thread are walked together: each iteration is one dependent load, and two independent chains
-    // hide each other's latency (the tightened loop is 16 instructions long, so the registers are there).
-    for (uint32_t b = 0; b < count; b += kWalkRays) {
-      WalkState w[kWalkRays];
-#pragma unroll
-      for (int r = 0; r < kWalkRays; ++r) {
-        w[r].word = kHitMiss;
-        w[r].active = false;
-        if (b + r < count && source_inside) {  // a source outside the grid sees nothing: the first cell already fails cell_is_valid
-          // far end = r1 * t2 + t1 (raycasting.hpp:81-85)
-          const double2 f = s_far[b + r];
-          const double ex = (src.c * f.x - src.s * f.y) + src.x;
-          const double ey = (src.s * f.x + src.c * f.y) + src.y;
-          int span = cell_near(ex, grid.inv_resolution) - sx, minor = cell_near(ey, grid.inv_resolution) - sy;
-          int stride_major = 1, stride_minor = pitch;
-          if (span < 0) {
-            span = -span;
-            stride_major = -1;
-          }
-          if (minor < 0) {
-            minor = -minor;
-            stride_minor = -pitch;
-          }
-          if (span < minor) {  // iterate along the longer axis (bresenham.hpp:99-105)
-            int t = span; span = minor; minor = t;
-            t = stride_major; stride_major = stride_minor; stride_minor = t;
-          }
-          w[r].stride_major = stride_major, w[r].stride_minor = stride_minor;
-          w[r].dxspan = 2u * static_cast<uint32_t>(span), w[r].dyspan = 2u * static_cast<uint32_t>(minor);
-          w[r].recip = span > 0 ? 0xFFFFFFFFu / w[r].dxspan : 0u;
-          w[r].index = source_index;
-          w[r].err1 = static_cast<uint32_t>(span) - 1u;  // error - 1, error in (0, dxspan] (span == 0: never used)
-          w[r].remaining = span;
-          w[r].active = true;
+    for (uint32_t b = 0; b < count; ++b) {
+      uint32_t word = kHitMiss;
+      if (source_inside) {  // a source outside the grid sees nothing: the first cell already fails cell_is_valid
+        // far end = r1 * t2 + t1 (raycasting.hpp:81-85)
+        const double2 f = s_far[b];
+        const double ex = (src.c * f.x - src.s * f.y) + src.x;
+        const double ey = (src.s * f.x + src.c * f.y) + src.y;
+        int span = cell_near(ex, grid.inv_resolution) - sx, minor = cell_near(ey, grid.inv_resolution) - sy;
+        int stride_major = 1, stride_minor = pitch;
+        if (span < 0) {
+          span = -span;
+          stride_major = -1;
         }
-      }
-      bool any = true;
-      while (any) {
-        any = false;
-#pragma unroll
-        for (int r = 0; r < kWalkRays; ++r) {
-          if (!w[r].active) continue;
-          const int d = __ldg(map + w[r].index);
+        if (minor < 0) {
+          minor = -minor;
+          stride_minor = -pitch;
+        }
+        if (span < minor) {  // iterate along the longer axis (bresenham.hpp:99-105)
+          int t = span; span = minor; minor = t;
+          t = stride_major; stride_major = stride_minor; stride_minor = t;
+        }
+        const uint32_t dxspan = 2u * static_cast<uint32_t>(span), dyspan = 2u * static_cast<uint32_t>(minor);
+        const uint32_t recip = span > 0 ? 0xFFFFFFFFu / dxspan : 0u;
+        int index = source_index;
+        uint32_t err1 = static_cast<uint32_t>(span) - 1u;  // error - 1, error in (0, dxspan] (span == 0: never used)
+        int remaining = span;
+        for (;;) {
+          const int d = __ldg(map + index);
           if (d == 0) {  // first non-free cell on the line, or the border
-            const int cx = (w[r].index & (pitch - 1)) - 1, cy = (w[r].index >> shift) - 1;
+            const int cx = (index & (pitch - 1)) - 1, cy = (index >> shift) - 1;
             if (static_cast<unsigned>(cx) < static_cast<unsigned>(grid.width) && static_cast<unsigned>(cy) < static_cast<unsigned>(grid.height))
-              w[r].word = (static_cast<uint32_t>(cy) << 16) | static_cast<uint32_t>(cx);
-            w[r].active = false;
-            continue;
+              word = (static_cast<uint32_t>(cy) << 16) | static_cast<uint32_t>(cx);
+            break;
           }
           // Every cell within Chebyshev distance d - 1 is free and the line moves at most one cell per step in each axis:
           // advance d steps of the iterator (bresenham.hpp:122-160, standard variant) in closed form.
-          const int k = min(d, w[r].remaining);
-          if (k == 0) {  // the far end cell was free too: sentinel reached (bresenham.hpp:179)
-            w[r].active = false;
-            continue;
-          }
-          w[r].remaining -= k;
-          const uint32_t tm1 = w[r].err1 + static_cast<uint32_t>(k) * w[r].dyspan;  // t - 1, t = error + k * dyspan < 2^32
-          uint32_t q = __umulhi(tm1, w[r].recip);                                    // floor((t - 1) / dxspan) or one below
-          uint32_t rem = tm1 - q * w[r].dxspan;
-          if (rem >= w[r].dxspan) {
+          const int k = min(d, remaining);
+          if (k == 0) break;  // the far end cell was free too: sentinel reached (bresenham.hpp:179)
+          remaining -= k;
+          const uint32_t tm1 = err1 + static_cast<uint32_t>(k) * dyspan;  // t - 1, t = error + k * dyspan < 2^32
+          uint32_t q = __umulhi(tm1, recip);                              // floor((t - 1) / dxspan) or one below
+          uint32_t r = tm1 - q * dxspan;
+          if (r >= dxspan) {
             ++q;
-            rem -= w[r].dxspan;
+            r -= dxspan;
           }
-          w[r].err1 = rem;  // new error - 1
-          w[r].index += k * w[r].stride_major + static_cast<int>(q) * w[r].stride_minor;
-          any = true;
+          err1 = r;  // new error - 1
+          index += k * stride_major + static_cast<int>(q) * stride_minor;
         }
       }
-#pragma unroll
-      for (int r = 0; r < kWalkRays; ++r)
-        if (b + r < count) __stcs(hits + static_cast<uint64_t>(base + b + r) * hit_stride + local, w[r].word);  // written once, read once: streaming
+      __stcs(hits + static_cast<uint64_t>(base + b) * hit_stride + local, word);  // written once, read once: streaming
     }
   }
 }
