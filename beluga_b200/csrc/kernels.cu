@@ -356,12 +356,24 @@ __global__ void __launch_bounds__(kPrThreads) propagate_binned_kernel(Pose2* __r
   }
 }
 
+constexpr int kPlaceItems = 4;  // particles per thread: the bin-offset gathers of one thread are independent
 __global__ void __launch_bounds__(256) schedule_place_kernel(const uint2* __restrict__ bin_rank, uint64_t n, const uint32_t* __restrict__ offsets,
                                                              uint32_t* __restrict__ perm) {
-  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= n) return;
-  const uint2 br = __ldcs(bin_rank + i);
-  perm[__ldg(offsets + br.x) + br.y] = static_cast<uint32_t>(i);
+  const uint64_t first = static_cast<uint64_t>(blockIdx.x) * (256 * kPlaceItems) + threadIdx.x;
+  uint2 br[kPlaceItems];
+  uint32_t off[kPlaceItems];
+#pragma unroll
+  for (int k = 0; k < kPlaceItems; ++k) {
+    const uint64_t i = first + static_cast<uint64_t>(k) * 256;
+    br[k] = i < n ? __ldcs(bin_rank + i) : make_uint2(0u, 0u);
+  }
+#pragma unroll
+  for (int k = 0; k < kPlaceItems; ++k) off[k] = __ldg(offsets + br[k].x);
+#pragma unroll
+  for (int k = 0; k < kPlaceItems; ++k) {
+    const uint64_t i = first + static_cast<uint64_t>(k) * 256;
+    if (i < n) perm[off[k] + br[k].y] = static_cast<uint32_t>(i);
+  }
 }
 
 __global__ void __launch_bounds__(256) schedule_histogram_kernel(const Pose2* __restrict__ states, uint64_t n, const Schedule* __restrict__ sched,
@@ -2058,7 +2070,7 @@ void launch_finish_schedule(const uint2* bin_rank, uint64_t n, uint32_t n_bins, 
   if (n == 0) return;
   // (Scanning the counters in the tail of propagate_binned_kernel -- its last block -- was tried: one SM reading 250 KB
   // in dependent 16-byte steps takes 40 us; sixteen look-back tiles take 8.)
-  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  const unsigned blocks = static_cast<unsigned>((n + 256 * kPlaceItems - 1) / (256 * kPlaceItems));
   const uint32_t tiles = (n_bins + kScanTile - 1) / kScanTile;
   scan_u32_kernel<<<tiles, kScanThreads, 0, stream>>>(counters, counters, n_bins, &sched->tile_ticket, tile_state, nullptr);
   schedule_place_kernel<<<blocks, 256, 0, stream>>>(bin_rank, n, counters, perm);

@@ -102,7 +102,8 @@ BB_HD Pose2 motion_apply(int model, const Pose2& st, double d0, double d1, doubl
 // ---- device-only variants for the propagate kernel ------------------------------------------------
 // Same quantities as rot_make / rot_exp / rot_mul / pose_mul / box_muller above with fewer FP64 instructions:
 // sqrt(c^2 + s^2) instead of hypot (the arguments are within an ulp of the unit circle: no overflow guard needed),
-// one reciprocal and two multiplications instead of two divisions, sincos / sincospi instead of separate calls.
+// one reciprocal and two multiplications instead of two divisions, sincos / sincospi instead of separate calls, and
+// no normalisation that the next product repeats.
 // Each substitution moves a result by at most an ulp or two -- the size of the CUDA-vs-glibc libm difference the
 // states carry anyway (tests bound them at 1e-12, the north star at 1e-5); nothing downstream is bit-compared
 // against these values except through the likelihood-field CELL they select.
@@ -111,19 +112,15 @@ __device__ __forceinline__ Rot2 rot_make_fast(double re, double im) {
   return Rot2{re * inv, im * inv};
 }
 __device__ __forceinline__ Rot2 rot_exp_fast(double theta) {
+  // sincos returns a unit vector to within an ulp; the products below renormalise anyway
   double sn, cs;
   sincos(theta, &sn, &cs);
-  return rot_make_fast(cs, sn);
+  return Rot2{cs, sn};
 }
 __device__ __forceinline__ Rot2 rot_mul_fast(const Rot2& a, const Rot2& b) {
-  double re = a.c * b.c - a.s * b.s;
-  double im = a.c * b.s + a.s * b.c;
-  const double sq = re * re + im * im;
-  if (sq != 1.0) {
-    const double scale = 2.0 / (1.0 + sq);
-    re = re * scale;
-    im = im * scale;
-  }
+  // Sophus scales the product by 2 / (1 + |z|^2) before normalising it; a positive scale cancels in the normalisation
+  const double re = a.c * b.c - a.s * b.s;
+  const double im = a.c * b.s + a.s * b.c;
   return rot_make_fast(re, im);
 }
 __device__ __forceinline__ Pose2 pose_mul_fast(const Pose2& a, const Pose2& b) {
