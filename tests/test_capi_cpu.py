@@ -1,6 +1,7 @@
 """CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
 include/beluga_b200.h declares, refuses to run without a GPU, and its host-only logic matches the oracle."""
 import ctypes as C
+import math
 import os
 import re
 import subprocess
@@ -120,3 +121,38 @@ def test_scan_to_points(lib):
     origin = np.array([[0.0, -1.0, 0.0, 0.3], [1.0, 0.0, 0.0, -0.2], [0.0, 0.0, 1.0, 0.5]])  # yaw 90 deg, offset
     moved = bb.scan_to_points(ranges, -0.5, 0.25, 0.1, 10.0, laser_origin=origin)
     assert np.allclose(moved, np.stack([-pts[:, 1] + 0.3, pts[:, 0] - 0.2], axis=1))
+
+
+def test_scan_to_points_follows_the_reference_arithmetic():
+    """bb200_scan_to_points against a numpy restatement of beluga_ros::LaserScan (beluga_ros/include/beluga_ros/laser_scan.hpp:69-80:
+    take_evenly over ranges and angles, angle = float(angle_min + float(i) * angle_increment)), BaseLaserScan
+    (beluga/sensor/data/laser_scan.hpp:64-91: drop NaN and out-of-range readings, x = r cos a, y = r sin a) and the laser origin
+    transform of beluga_ros/src/amcl.cpp:57-62 -- bit for bit (the arithmetic is float32 angles widened to double)."""
+    import beluga_b200 as bb
+
+    rng = np.random.default_rng(6)
+    n = 1081
+    ranges = rng.uniform(0.05, 40.0, n).astype(np.float32)
+    ranges[rng.integers(0, n, 40)] = np.nan
+    ranges[rng.integers(0, n, 20)] = np.inf
+    angle_min, angle_inc = np.float32(-2.35619449), np.float32(0.004363323)
+    origin = np.array([[math.cos(0.3), -math.sin(0.3), 0.0, 0.25], [math.sin(0.3), math.cos(0.3), 0.0, -0.1], [0.0, 0.0, 1.0, 0.4]])
+    for max_beams, use_origin in ((0, False), (60, False), (181, True), (5000, True)):
+        got = bb.scan_to_points(ranges, float(angle_min), float(angle_inc), min_range=0.1, max_range=30.0, max_beams=max_beams,
+                                laser_origin=origin if use_origin else None)
+        count = n if max_beams == 0 else max_beams
+        if count > n:
+            idx = np.arange(n)
+        else:  # take_evenly (views/take_evenly.hpp:118-145): first, last and evenly spaced in between, rounded up
+            idx = np.array([0] + [-(-(p * (n - 1)) // (count - 1)) for p in range(1, count)], dtype=np.int64)
+        exp = []
+        for i in idx:
+            r = float(ranges[i])
+            theta = float(np.float32(angle_min + np.float32(np.float32(int(i)) * angle_inc)))
+            if math.isnan(r) or not (r >= 0.1) or not (r <= 30.0):
+                continue
+            x, y = r * math.cos(theta), r * math.sin(theta)
+            if use_origin:
+                x, y = origin[0, 0] * x + origin[0, 1] * y + origin[0, 3], origin[1, 0] * x + origin[1, 1] * y + origin[1, 3]
+            exp.append((x, y))
+        assert np.array_equal(got, np.array(exp).reshape(-1, 2))
