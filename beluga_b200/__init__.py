@@ -692,6 +692,14 @@ class ShardedAmcl:
         self._check(self._lib.bb200_sharded_amcl_update(self._h, _dptr(_f64(control_pose)), _dptr(pts) if len(pts) else None, len(pts), C.byref(res)))
         return res
 
+    def cluster_estimate(self, linear: float = 0.20, angular: float = 0.524, percentile: float = 0.90):
+        """beluga::cluster_based_estimate over all shards -> (mean[4], cov[3, 3], n_cells, n_clusters)."""
+        p = _capi.ClusterParam(linear, angular, percentile)
+        est = _capi.Estimate()
+        cells, clusters = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.bb200_sharded_amcl_cluster_estimate(self._h, C.byref(p), C.byref(est), C.byref(cells), C.byref(clusters)))
+        return np.array(est.mean), np.array(est.cov).reshape(3, 3), cells.value, clusters.value
+
     def particles(self):
         n = self.params.max_particles
         st = np.zeros((n, 4))

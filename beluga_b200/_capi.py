@@ -194,6 +194,8 @@ SIGNATURES = {
     "bb200_sharded_amcl_force_update": (None, [_vp]),
     "bb200_sharded_amcl_update": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64, _P(UpdateResult)]),
     "bb200_sharded_amcl_get_particles": (C.c_int, [_vp, _dbl, _dbl, C.c_uint64]),
+    "bb200_sharded_amcl_cluster_estimate": (C.c_int, [_vp, _P(ClusterParam), _P(Estimate), _P(C.c_uint32), _P(C.c_uint32)]),
+    "bb200_cluster_merge_host": (C.c_int, [_P(_P(ClusterCell)), _P(C.c_uint64), _P(C.c_uint64), C.c_int, _P(ClusterCell), C.c_uint64, _P(C.c_uint64)]),
     "bb200_amcl_export_shard": (C.c_int, [_vp, _vp]),
     "bb200_amcl_join_shards": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "bb200_amcl_leave_shards": (C.c_int, [_vp]),

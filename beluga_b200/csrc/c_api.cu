@@ -5,6 +5,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/beluga_b200.h"
@@ -649,6 +650,85 @@ int bb200_sharded_amcl_update(bb200_sharded_amcl* g, const double control_pose[4
     return Amcl::update_group(ranks.data(), static_cast<int>(ranks.size()), control_pose, points_xy != nullptr ? points_xy : kNoPoints, n_points, out);
   });
 }
+int bb200_cluster_merge_host(const bb200_cluster_cell* const* shard_cells, const uint64_t* shard_counts, const uint64_t* shard_first_index, int shards,
+                             bb200_cluster_cell* merged, uint64_t capacity, uint64_t* n_merged) {
+  BB_REQUIRE(shard_cells && shard_counts && n_merged && shards >= 1);
+  return guarded_create([&] {
+    // The reference's cluster map is filled by ONE pass over the particles in order (cluster_based_estimation.hpp:141-161).
+    // Shards hold contiguous index ranges, so going through the shards in rank order -- and through each shard's cells in
+    // ITS first-occurrence order -- visits the cells in the global first-occurrence order; a cell met again adds its count,
+    // weight and raw moments to the record opened by the lower rank (whose representative is the globally first particle).
+    std::unordered_map<uint64_t, uint64_t> slot_of;
+    uint64_t n = 0;
+    for (int r = 0; r < shards; ++r) {
+      for (uint64_t k = 0; k < shard_counts[r]; ++k) {
+        const bb200_cluster_cell& c = shard_cells[r][k];
+        const auto it = slot_of.find(c.hash);
+        if (it == slot_of.end()) {
+          if (merged != nullptr) {
+            if (n >= capacity) return static_cast<int>(BB200_ERR_CAPACITY);
+            merged[n] = c;
+            merged[n].first_index = static_cast<uint32_t>(c.first_index + (shard_first_index != nullptr ? shard_first_index[r] : 0));
+          }
+          slot_of.emplace(c.hash, n++);
+        } else if (merged != nullptr) {
+          bb200_cluster_cell& m = merged[it->second];
+          m.count += c.count;
+          m.weight += c.weight;
+          for (int j = 0; j < 9; ++j) m.moments[j] += c.moments[j];
+        }
+      }
+    }
+    *n_merged = n;
+    return static_cast<int>(BB200_OK);
+  });
+}
+
+int bb200_sharded_amcl_cluster_estimate(bb200_sharded_amcl* g, const bb200_cluster_param* p, bb200_estimate* out, uint32_t* n_cells,
+                                        uint32_t* n_clusters) {
+  BB_REQUIRE(g && p && out);
+  g->error.clear();
+  return guarded(*g, [&] {
+    const int shards = static_cast<int>(g->ranks.size());
+    std::vector<std::vector<bb200_cluster_cell>> cells(static_cast<size_t>(shards));
+    std::vector<const bb200_cluster_cell*> ptrs;
+    std::vector<uint64_t> counts, firsts;
+    uint64_t total_cells = 0, n_particles = 0;
+    for (int r = 0; r < shards; ++r) {
+      Filter& f = g->ranks[static_cast<size_t>(r)]->impl.filter();
+      uint64_t n = 0;
+      double top = 0.0;
+      if (f.size() > 0) {
+        int st = f.particle_histogram(p->linear_hash_resolution, p->angular_hash_resolution, nullptr, 0, &n, &top);
+        if (st != BB200_OK) return st;
+        cells[static_cast<size_t>(r)].resize(n);
+        st = f.particle_histogram(p->linear_hash_resolution, p->angular_hash_resolution, cells[static_cast<size_t>(r)].data(), n, &n, &top);
+        if (st != BB200_OK) return st;
+      }
+      ptrs.push_back(cells[static_cast<size_t>(r)].data());
+      counts.push_back(n);
+      firsts.push_back(f.first_index());
+      total_cells += n;
+      n_particles += f.size();
+    }
+    if (n_particles == 0) {
+      g->error = "no particles";
+      return static_cast<int>(BB200_ERR_STATE);
+    }
+    std::vector<bb200_cluster_cell> merged(total_cells);
+    uint64_t n_merged = 0;
+    const int st = bb200_cluster_merge_host(ptrs.data(), counts.data(), firsts.data(), shards, merged.data(), merged.size(), &n_merged);
+    if (st != BB200_OK) return st;
+    static_assert(sizeof(bb200_cluster_cell) == sizeof(bb200::HostCell), "public and internal cell records must agree");
+    const bb200::ClusterSelection sel = bb200::select_cluster(reinterpret_cast<const bb200::HostCell*>(merged.data()), n_merged, n_particles,
+                                                              p->linear_hash_resolution, p->angular_hash_resolution, p->weight_cap_percentile);
+    bb200::Filter::estimate_from_moments_static(sel.moments, g->ranks[0]->impl.filter().pivot(), out);  // every shard accumulates about the same pivot
+    if (n_cells != nullptr) *n_cells = static_cast<uint32_t>(n_merged);
+    if (n_clusters != nullptr) *n_clusters = sel.clusters;
+    return static_cast<int>(BB200_OK);
+  });
+}
+
 int bb200_sharded_amcl_get_particles(bb200_sharded_amcl* g, double* states, double* weights, uint64_t capacity) {
   BB_REQUIRE(g);
   g->error.clear();

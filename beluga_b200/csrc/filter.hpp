@@ -124,6 +124,8 @@ class Filter {
   void step_set_kld_accepted(uint64_t accepted);
   bool shard_kld() const { return shard_kld_; }
   uint64_t global_size() const { return peer_world_ > 1 ? global_size_ : n_; }
+  uint64_t first_index() const { return first_index_; }
+  const double* pivot() const { return pivot_; }
   /// Synchronises and closes the batch of phases enqueued so far.  After kPhaseNormalize a caller may still run
   /// kPhaseResample + kPhaseFinish + step_end (selective resampling: the decision needs the effective sample size).
   int step_end(bb200_estimate* est, double* weight_sum, uint64_t* new_size, double* sum_sq);

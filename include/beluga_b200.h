@@ -489,6 +489,19 @@ void bb200_sharded_amcl_force_update(bb200_sharded_amcl* g);
 /* Amcl::update (amcl_core.hpp:165-201) over all shards. */
 int bb200_sharded_amcl_update(bb200_sharded_amcl* g, const double control_pose[4], const double* points_xy, uint64_t n_points,
                               bb200_update_result* out);
+/* beluga::cluster_based_estimate over all shards: every shard builds its cell records on its device
+ * (bb200_filter_particle_histogram with the clusterizer's resolutions), the records are merged on the host in rank
+ * order (bb200_cluster_merge_host) and flooded like the single-GPU estimate.  Counts, weights and moments of a cell
+ * that spans shards are added shard by shard: exact for unit weights (the state after a resample), otherwise equal to
+ * the reference's single sequential sum up to the grouping of the additions. */
+int bb200_sharded_amcl_cluster_estimate(bb200_sharded_amcl* g, const bb200_cluster_param* p, bb200_estimate* out, uint32_t* n_cells,
+                                        uint32_t* n_clusters);
+/* Host only: merges per-shard cell records (each list in its shard's first-occurrence order, shards in rank order) into
+ * the global first-occurrence order; shard_first_index (may be NULL) turns local particle indices into global ones.
+ * One process per GPU: gather the lists of bb200_filter_particle_histogram with the application's transport, then
+ * bb200_cluster_merge_host + bb200_cluster_select_host + bb200_estimate_from_moments. */
+int bb200_cluster_merge_host(const bb200_cluster_cell* const* shard_cells, const uint64_t* shard_counts, const uint64_t* shard_first_index, int shards,
+                             bb200_cluster_cell* merged, uint64_t capacity, uint64_t* n_merged);
 /* particles() in global index order (rank 0's shard first). */
 int bb200_sharded_amcl_get_particles(bb200_sharded_amcl* g, double* states, double* weights, uint64_t capacity);
 #define BB200_SHARD_HANDLE_BYTES 256

@@ -161,6 +161,28 @@ def group_particles(group, n):
     return np.concatenate(states), np.concatenate(weights)
 
 
+@pytest.mark.parametrize("shards", [2, 4])
+def test_cluster_based_estimate_over_shards(bb, scene, shards):
+    """beluga::cluster_based_estimate on a sharded filter: per-shard cell records merged on the host in rank order give the
+    single filter's cells, clusters and estimate (the particles carry unit weights after the resample, so the sums are exact)."""
+    n = 30_000
+    ap = dict(min_particles=n, max_particles=n, seed=17, resample_scheme=1)
+    single = bb.Amcl(bb.DifferentialDriveModelParam(*MOTION), bb.AmclParams(**ap))
+    group = bb.ShardedAmcl(bb.DifferentialDriveModelParam(*MOTION), bb.AmclParams(**ap), devices=[0] * shards)
+    for f in (single, group):
+        f.update_map(0, bb.LikelihoodFieldModelParam(**LFM), bb.OccupancyGrid(scene.cells, scene.resolution))
+        f.initialize(scene.initial_mean, scene.initial_cov)
+    for k in range(3):
+        pose = bb.se2(*scene.poses[k])
+        single.update(pose, scene.scans[k])
+        group.update(pose, scene.scans[k])
+    for kw in (dict(), dict(linear=0.05, angular=0.1, percentile=0.5)):
+        ms, cs, _, cells_s, clusters_s = single.filter.cluster_estimate(with_ids=True, **kw)
+        mg, cg, cells_g, clusters_g = group.cluster_estimate(**kw)
+        assert (cells_g, clusters_g) == (cells_s, clusters_s)
+        assert np.abs(ms - mg).max() < 1e-12 and np.abs(cs - cg).max() < 1e-12
+
+
 def test_sharded_errors(bb, scene):
     with pytest.raises(bb.BelugaB200Error):  # not a multiple of the shard count
         bb.ShardedAmcl(bb.DifferentialDriveModelParam(*MOTION), bb.AmclParams(min_particles=1001, max_particles=1001), devices=[0, 0])
