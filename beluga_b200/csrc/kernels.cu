@@ -1318,7 +1318,10 @@ __device__ __forceinline__ unsigned long long lookback_exclusive_prefix(unsigned
 // split into two power-of-two factors so that each stays a normal double for any exponent.
 constexpr int kQsThreads = 256;
 constexpr int kQsItemsSmall = 8;   // up to a few million weights: more tiles than SM slots, shortest chain
-constexpr int kQsItemsLarge = 16;  // beyond: half the tiles (look-back words, barriers) per byte
+#ifndef BB200_QS_LARGE_ITEMS
+#define BB200_QS_LARGE_ITEMS 8  // 16 halves the tiles per byte but measured slower at 12.5M (83 us against 67)
+#endif
+constexpr int kQsItemsLarge = BB200_QS_LARGE_ITEMS;
 constexpr uint32_t kQsTile = kQsThreads * kQsItemsSmall;  // the smaller tile sizes the look-back state
 
 __device__ __forceinline__ double pow2_double(int e) {  // |e| <= 1000
@@ -1337,37 +1340,28 @@ __global__ void __launch_bounds__(kQsThreads) quantize_scan_kernel(const double*
                                                                    unsigned long long* tile_state, int derive_exponent, int ceil_log2_count) {
   __shared__ unsigned long long s_warp[kQsThreads / kWarp];
   __shared__ unsigned long long s_prefix;
-  __shared__ uint32_t s_tile;
-  __shared__ double s_factor[2];
-  __shared__ int s_valid;
-  if (threadIdx.x == 0) {
-    const uint32_t tile = static_cast<uint32_t>(atomicAdd(&scalars->tile_ticket, 1ull));
-    s_tile = tile;
-    int exponent, valid;
-    if (derive_exponent) {
-      const double wmax = __longlong_as_double(static_cast<long long>(scalars->wmax_bits));
-      int ex = 0;
-      const bool ok = wmax > 0.0 && wmax <= DBL_MAX;
-      if (ok) (void)frexp(wmax, &ex);
-      exponent = min(52, 62 - ceil_log2_count) - ex;
-      valid = ok ? 1 : 0;
-      if (tile == 0) {
-        scalars->exponent = exponent;
-        scalars->valid = valid;
-      }
-    } else {
-      exponent = scalars->exponent;
-      valid = scalars->valid;
+  // Tiles are taken in blockIdx order (CTAs are dispatched in that order, which is what the look-back's forward progress
+  // needs -- the same assumption CUB's decoupled look-back makes): no ticket atomic and no barrier before the loads.
+  const uint32_t tile = blockIdx.x;
+  int exponent, valid_flag;
+  if (derive_exponent) {  // every thread derives the exponent itself: a broadcast load and a few integer operations
+    const double wmax = __longlong_as_double(static_cast<long long>(scalars->wmax_bits));
+    int ex = 0;
+    const bool ok = wmax > 0.0 && wmax <= DBL_MAX;
+    if (ok) (void)frexp(wmax, &ex);
+    exponent = min(52, 62 - ceil_log2_count) - ex;
+    valid_flag = ok ? 1 : 0;
+    if (tile == 0 && threadIdx.x == 0) {
+      scalars->exponent = exponent;
+      scalars->valid = valid_flag;
     }
-    const int e1 = exponent / 2;
-    s_factor[0] = pow2_double(e1);
-    s_factor[1] = pow2_double(exponent - e1);
-    s_valid = valid;
+  } else {
+    exponent = scalars->exponent;
+    valid_flag = scalars->valid;
   }
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  const double f1 = s_factor[0], f2 = s_factor[1];
-  const bool valid = s_valid != 0;
+  const int e1 = exponent / 2;
+  const double f1 = pow2_double(e1), f2 = pow2_double(exponent - e1);
+  const bool valid = valid_flag != 0;
 
   const uint64_t base = static_cast<uint64_t>(tile) * (kQsThreads * kQsItems) + static_cast<uint64_t>(threadIdx.x) * kQsItems;
   unsigned long long q[kQsItems];
@@ -1422,10 +1416,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_u32_kernel(const uint32_t* 
                                                                 unsigned long long* tile_state, unsigned long long* total_out) {
   __shared__ unsigned long long s_warp[kScanThreads / kWarp];
   __shared__ unsigned long long s_prefix;
-  __shared__ uint32_t s_tile;
-  if (threadIdx.x == 0) s_tile = static_cast<uint32_t>(atomicAdd(ticket, 1ull));
-  __syncthreads();
-  const uint32_t tile = s_tile;
+  (void)ticket;  // tiles in blockIdx order (see quantize_scan_kernel)
+  const uint32_t tile = blockIdx.x;
   const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
   unsigned long long q[kScanItems];
   unsigned long long local = 0;
