@@ -38,11 +38,15 @@ ClusterSelection select_cluster(const HostCell* cells, std::size_t n_cells, std:
   // n/5 buckets (1.6 MB at 1M particles) has to be paid again.
   thread_local std::unordered_map<std::size_t, Node> map;
   thread_local std::size_t reserved_for = static_cast<std::size_t>(-1);
+  thread_local std::size_t fresh_buckets = 0;
   const std::size_t want = static_cast<std::size_t>(n_particles / 5);
-  if (reserved_for != want || !map.empty()) {
+  // ... as long as its bucket count is still the freshly reserved one: more cells than n/5 make the map rehash while it
+  // fills (as the reference's does), and a map that has grown would iterate in a different order next time.
+  if (reserved_for != want || !map.empty() || map.bucket_count() != fresh_buckets) {
     std::unordered_map<std::size_t, Node>().swap(map);
     map.reserve(want);
     reserved_for = want;
+    fresh_buckets = map.bucket_count();
   }
   for (std::size_t k = 0; k < n_cells; ++k) {
     // normalize_and_cap_weights, first loop (:181-184)

@@ -100,3 +100,20 @@ def test_argument_checks():
         bb.cluster_select_host([], 0, linear=-1.0)
     ids, n_clusters, found, _, _ = bb.cluster_select_host([], 0)
     assert len(ids) == 0 and n_clusters == 0 and not found
+
+
+def test_more_cells_than_the_reserve_twice_in_a_row(orc):
+    """make_cluster_map reserves n / 5 buckets (:146); a fine hash gives more cells than that and the map rehashes while it
+    fills.  The host pass keeps its map between calls: a map that has grown must not be reused (its iteration order --
+    which breaks the ties between the unit-weight cells of a resampled set -- would differ from a fresh one's).  Two calls
+    in a row, sandwiching a small one, must all agree with the oracle."""
+    rng = np.random.default_rng(8)
+    n = 4000
+    th = rng.uniform(-PI, PI, n)
+    states = np.stack([np.cos(th), np.sin(th), rng.uniform(0.0, 6.0, n), rng.uniform(0.0, 6.0, n)], axis=1)
+    weights = np.ones(n)  # every cell ties
+    for linear, angular in ((0.05, 0.1), (0.5, 1.0), (0.05, 0.1), (0.05, 0.1)):
+        cells, _ = cell_records(orc, states, weights, linear, angular)
+        if linear == 0.05:
+            assert len(cells) > n // 5
+        check(orc, states, weights, linear, angular, 0.5)
