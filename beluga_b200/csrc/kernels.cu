@@ -33,6 +33,9 @@
 #ifndef BB200_RS_UNROLL
 #define BB200_RS_UNROLL 4  // particles per thread and round in resample_scatter_kernel
 #endif
+#ifndef BB200_RS_BLOCKS
+#define BB200_RS_BLOCKS 2  // resident CTAs per SM the kernel is compiled for (register cap)
+#endif
 
 #include <algorithm>
 #include <cfloat>
@@ -1025,8 +1028,11 @@ __global__ void __launch_bounds__(kBeamThreads, kBeamBlocksPerSm)
 // and a branch-free mixture loop.  Hit words: 0xFFFFFFFF = miss, else cy << 16 | cx (grids up to 65535 cells a side).
 
 constexpr uint32_t kHitMiss = 0xFFFFFFFFu;
+#ifndef BB200_WALK_BLOCKS
+#define BB200_WALK_BLOCKS 4
+#endif
 constexpr int kWalkThreads = 256;
-constexpr uint32_t kWalkChunk = 2048;  // far ends staged per shared-memory chunk (32 KB)
+constexpr uint32_t kWalkChunk = 1024;  // far ends staged per shared-memory chunk (16 KB)
 
 /// The walk against the PADDED free-distance map (one border cell of zeros all round, 2^pad_shift bytes per row): a
 /// jump of k <= d cells can at most land on the border, so the loop needs no bounds test -- a zero either is the first
@@ -1036,7 +1042,7 @@ constexpr uint32_t kWalkChunk = 2048;  // far ends staged per shared-memory chun
 /// the 32-bit reciprocal quotient of ray_step is the only path.  16 instructions per iteration instead of 45.
 /// (Walking 2 or 4 rays per thread together was measured on this kernel as well: 21.9 / 25.6 ms against 18.5 ms at C3 --
 /// the per-ray state machine and its activity flags cost more than the second load chain hides.)
-__global__ void __launch_bounds__(kWalkThreads, 4)
+__global__ void __launch_bounds__(kWalkThreads, BB200_WALK_BLOCKS)
     beam_walk_kernel(const Pose2* __restrict__ states, uint64_t n, uint64_t slot_base, uint64_t slot_count, const uint32_t* __restrict__ perm,
                      OccupancyView grid, double beam_max_range, const double2* __restrict__ points, uint32_t n_points,
                      uint32_t* __restrict__ hits, uint64_t hit_stride) {
@@ -1747,7 +1753,7 @@ __device__ __forceinline__ uint64_t comb_slots_before_magic(unsigned long long p
   return j < total_slots ? j : total_slots;
 }
 
-__global__ void __launch_bounds__(kRsThreads) resample_scatter_kernel(ResampleArgs a, Scalars* __restrict__ scalars,
+__global__ void __launch_bounds__(kRsThreads, BB200_RS_BLOCKS) resample_scatter_kernel(ResampleArgs a, Scalars* __restrict__ scalars,
                                                                      double* __restrict__ moment_partials) {
   __shared__ double s_red[kMomentCount * kRsThreads / kWarp];
   __shared__ unsigned long long s_comb[3];
@@ -2224,7 +2230,7 @@ uint32_t launch_resample(const ResampleArgs& args, Scalars* scalars, double* mom
                                  (args.peer_count > 0 && args.rank_totals != nullptr));
   if (scatter) {
     // one pass over the input particles; a few particles per thread amortise the block reduction of the moments
-    const uint32_t per_sm = BB200_RS_UNROLL >= 4 ? 2 : 3;  // resident CTAs at the kernel's register count
+    const uint32_t per_sm = BB200_RS_BLOCKS;  // resident CTAs at the kernel's register count
     const uint32_t blocks = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>((args.n_in + kRsThreads - 1) / kRsThreads, 148 * per_sm)));
     resample_scatter_kernel<<<blocks, kRsThreads, 0, stream>>>(args, scalars, moment_partials);
     return blocks;
