@@ -31,10 +31,11 @@
 #define BB200_RW_BLOCKS 4
 #endif
 #ifndef BB200_RS_UNROLL
-#define BB200_RS_UNROLL 4  // particles per thread and round in resample_scatter_kernel
+#define BB200_RS_UNROLL 2  // particles per thread and round in resample_scatter_kernel
 #endif
 #ifndef BB200_RS_BLOCKS
-#define BB200_RS_BLOCKS 2  // resident CTAs per SM the kernel is compiled for (register cap)
+#define BB200_RS_BLOCKS 3  // resident CTAs per SM the kernel is compiled for (register cap); measured at 1M (blocks, unroll):
+                          // (2, 4) 34.9 us, (3, 4) 45.7 (spills), (4, 2) 39.0, (3, 2) 31.2
 #endif
 
 #include <algorithm>
@@ -1029,7 +1030,7 @@ __global__ void __launch_bounds__(kBeamThreads, kBeamBlocksPerSm)
 
 constexpr uint32_t kHitMiss = 0xFFFFFFFFu;
 #ifndef BB200_WALK_BLOCKS
-#define BB200_WALK_BLOCKS 4
+#define BB200_WALK_BLOCKS 6  // resident CTAs per SM the walk is compiled for; measured at C3: 4 -> 17.8 ms, 5 -> 16.7, 6 -> 16.1
 #endif
 constexpr int kWalkThreads = 256;
 constexpr uint32_t kWalkChunk = 1024;  // far ends staged per shared-memory chunk (16 KB)
