@@ -701,8 +701,10 @@ class ShardedAmcl:
         return np.array(est.mean), np.array(est.cov).reshape(3, 3), cells.value, clusters.value
 
     def particles(self):
-        n = self.params.max_particles
+        """The particle set in global index order (a KLD-sized filter holds fewer than max_particles)."""
+        n = sum(f.size() for f in self.shards)
         st = np.zeros((n, 4))
         w = np.zeros(n)
-        self._check(self._lib.bb200_sharded_amcl_get_particles(self._h, _dptr(st), _dptr(w), n))
+        if n:
+            self._check(self._lib.bb200_sharded_amcl_get_particles(self._h, _dptr(st), _dptr(w), n))
         return st, w

@@ -1030,7 +1030,8 @@ __global__ void __launch_bounds__(kBeamThreads, kBeamBlocksPerSm)
 
 constexpr uint32_t kHitMiss = 0xFFFFFFFFu;
 #ifndef BB200_WALK_BLOCKS
-#define BB200_WALK_BLOCKS 6  // resident CTAs per SM the walk is compiled for; measured at C3: 4 -> 17.8 ms, 5 -> 16.7, 6 -> 16.1
+#define BB200_WALK_BLOCKS 8  // resident CTAs per SM the walk is compiled for (register cap; the loop is latency-bound, so warps beat
+                            // registers even with a few spills); measured at C3: 4 -> 17.8 ms, 5 -> 16.7, 6 -> 16.1, 7 -> 15.6, 8 -> 15.5
 #endif
 constexpr int kWalkThreads = 256;
 constexpr uint32_t kWalkChunk = 1024;  // far ends staged per shared-memory chunk (16 KB)
