@@ -30,6 +30,9 @@
 #ifndef BB200_RW_BLOCKS
 #define BB200_RW_BLOCKS 4
 #endif
+#ifndef BB200_RW_CHUNK
+#define BB200_RW_CHUNK 0  // > 0: experiment -- chunks of adjacent tasks per CTA instead of one global ticket per warp
+#endif
 #ifndef BB200_RS_UNROLL
 #define BB200_RS_UNROLL 2  // particles per thread and round in resample_scatter_kernel
 #endif
@@ -676,11 +679,46 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
   const int lane = threadIdx.x % kWarp;
   const unsigned long long n_tasks = (n + kWarp - 1) / kWarp;  // a task = the next 32 particles of the schedule
   unsigned long long* ticket_counter = &scalars->work_ticket;
+#if BB200_RW_CHUNK > 0
+  // Experiment (profiles/r02_lfm_chunk_tickets.txt): the CTA draws CHUNKS of BB200_RW_CHUNK adjacent tasks from the global
+  // counter and its warps take tasks from the current chunk through a shared-memory word (chunk id << 8 | next index), so that
+  // the warps of a CTA work on neighbouring particles without waiting for each other; the warp that finds the chunk
+  // exhausted fetches the next one, the others spin on the word for that round trip.
+  __shared__ unsigned long long s_chunk;
+  if (threadIdx.x == 0) s_chunk = atomicAdd(ticket_counter, 1ull) << 8;
+  __syncthreads();
+  auto take = [&]() -> unsigned long long {
+    unsigned long long t = 0;
+    if (lane == 0) {
+      for (;;) {
+        const unsigned long long old = atomicAdd(&s_chunk, 1ull);
+        const unsigned long long idx = old & 0xFFull, chunk = old >> 8;
+        if (idx < BB200_RW_CHUNK) {
+          t = chunk * BB200_RW_CHUNK + idx;
+          break;
+        }
+        if (idx == BB200_RW_CHUNK) {  // this warp refills: the new chunk's task 0 is its own
+          const unsigned long long fresh = atomicAdd(ticket_counter, 1ull);
+          atomicExch(&s_chunk, (fresh << 8) | 1ull);
+          t = fresh * BB200_RW_CHUNK;
+          break;
+        }
+        while ((*reinterpret_cast<volatile unsigned long long*>(&s_chunk) >> 8) == chunk) {
+        }
+      }
+    }
+    return __shfl_sync(0xffffffffu, t, 0);
+  };
+  unsigned long long ticket = take();
+#else
   unsigned long long ticket = __shfl_sync(0xffffffffu, lane == 0 ? atomicAdd(ticket_counter, 1ull) : 0ull, 0);
+#endif
   unsigned long long best = 0ull;
   while (ticket < n_tasks) {
+#if BB200_RW_CHUNK == 0
     // Draw the next ticket now; its round trip to L2 hides behind this task's beams.
     const unsigned long long next = lane == 0 ? atomicAdd(ticket_counter, 1ull) : 0ull;
+#endif
     const uint64_t slot = ticket * kWarp + lane;
     const bool active = slot < n;  // idle lanes of the last task walk the beams with a dummy pose
     const uint64_t i = active ? (perm != nullptr ? perm[slot] : slot) : 0;
@@ -698,7 +736,11 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
       const unsigned long long bits = weight_order_bits(w);
       best = bits > best ? bits : best;
     }
+#if BB200_RW_CHUNK > 0
+    ticket = take();
+#else
     ticket = __shfl_sync(0xffffffffu, next, 0);
+#endif
   }
 #pragma unroll
   for (int off = kWarp / 2; off > 0; off >>= 1) {
