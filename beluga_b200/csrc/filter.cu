@@ -115,6 +115,8 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   if (const char* v = std::getenv("BB200_PREFETCH_TABLE")) prefetch_table_ = std::atoi(v) != 0;  // development knob: L2 prefetch of the likelihood table
   if (const char* v = std::getenv("BB200_BEAM_TWO_PASS")) beam_two_pass_ = std::atoi(v) != 0;  // development knob: walk + mixture kernels
   if (const char* v = std::getenv("BB200_PER_BIN")) schedule_per_bin_ = std::atof(v);        // development knob: particles per pose bin
+  if (const char* v = std::getenv("BB200_X_SPLIT")) schedule_x_split_ = std::atof(v);        // development knob: bins per warp along x
+  if (const char* v = std::getenv("BB200_EQUAL_MASS")) schedule_equal_mass_ = std::atoi(v) != 0;  // development knob: 0 = equal-size bins
   if (const char* v = std::getenv("BB200_LEVER")) schedule_lever_ = std::atof(v);            // development knob: heading lever arm / mean range
   capacity_ = config.capacity;
   first_index_ = config.first_index;
@@ -1242,7 +1244,7 @@ bool Filter::predict_schedule(const MotionSampling& s, Schedule* grid) const {
   if (!std::isfinite(var_theta) || !std::isfinite(vx) || !std::isfinite(vy) || !std::isfinite(mean.x) || !std::isfinite(mean.y)) return false;
   const double r = std::exp(-0.5 * var_theta);
   schedule_from_moments(*grid, r * mean.c, r * mean.s, mean.x, mean.y, vx, vy, static_cast<double>(n_), schedule_lever_ * points_mean_range_,
-                        0.5 * grid_resolution_, schedule_per_bin_);
+                        0.5 * grid_resolution_, schedule_per_bin_, schedule_x_split_, schedule_equal_mass_);
   return true;
 }
 
@@ -1267,7 +1269,7 @@ int Filter::enqueue_propagate_reweight(const MotionSampling* sampling, uint32_t 
   }
   if (scheduled && perm == nullptr) {
     mark("schedule");
-    launch_build_schedule(states_[cur_], n_, sched_, bins_, counters_, perm_, sched_tiles_, schedule_lever_ * points_mean_range_, 0.5 * grid_resolution_, schedule_per_bin_, stream_);
+    launch_build_schedule(states_[cur_], n_, sched_, bins_, counters_, perm_, sched_tiles_, schedule_lever_ * points_mean_range_, 0.5 * grid_resolution_, schedule_per_bin_, schedule_x_split_, schedule_equal_mass_, stream_);
     BB_LAUNCHED_N("schedule", 4);
     perm = perm_;
   }

@@ -253,6 +253,8 @@ class Filter {
   bool param_points_{true};
   double schedule_per_bin_{16.0};
   double schedule_lever_{1.0};
+  double schedule_x_split_{1.0};
+  bool schedule_equal_mass_{false};
   Schedule* sched_{nullptr};
   uint32_t* bins_{nullptr};
   uint2* bin_rank_{nullptr};

@@ -330,21 +330,39 @@ __global__ void schedule_reset_kernel(Schedule* sched) {
   sched->tile_ticket = 0;
 }
 
-__global__ void schedule_params_kernel(Schedule* sched, uint64_t n, double mean_range, double min_bin, double per_bin) {
+__global__ void schedule_params_kernel(Schedule* sched, uint64_t n, double mean_range, double min_bin, double per_bin, double x_split,
+                                       bool equal_mass) {
   const double inv_n = 1.0 / static_cast<double>(n);
   const double mx = sched->sums[2] * inv_n, my = sched->sums[3] * inv_n;
   schedule_from_moments(*sched, sched->sums[0] * inv_n, sched->sums[1] * inv_n, mx, my, sched->sums[4] * inv_n - mx * mx,
-                        sched->sums[5] * inv_n - my * my, static_cast<double>(n), mean_range, min_bin, per_bin);
+                        sched->sums[5] * inv_n - my * my, static_cast<double>(n), mean_range, min_bin, per_bin, x_split, equal_mass);
 }
 
 __device__ __forceinline__ uint32_t schedule_bin(const Schedule& g, const Pose2& st) {
   // heading relative to the mean as u = 2 tan(dtheta / 2): monotone in dtheta, one division instead of an atan2
   const double cr = st.c * g.c0 + st.s * g.s0, sr = st.s * g.c0 - st.c * g.s0;
   const double u = cr > -0.4 ? 2.0 * sr / (1.0 + cr) : (sr >= 0.0 ? 1e6 : -1e6);
-  const int bt = min(max(static_cast<int>(fmin(fmax((u + g.half_u) * g.scale_t, 0.0), 1e6)), 0), static_cast<int>(g.nt) - 1);
-  const int bx = min(max(static_cast<int>(fmin(fmax((st.x - g.x0) * g.scale_x, 0.0), 1e6)), 0), static_cast<int>(g.nx) - 1);
-  const int by = min(max(static_cast<int>(fmin(fmax((st.y - g.y0) * g.scale_y, 0.0), 1e6)), 0), static_cast<int>(g.ny) - 1);
-  return (static_cast<uint32_t>(bt) * g.ny + static_cast<uint32_t>(by)) * g.nx + static_cast<uint32_t>(bx);
+  int bt, bx, by;
+  if (g.equal_mass != 0u) {
+    // CDF value of each coordinate (single precision: the bin only decides which thread handles the particle)
+    const float zt = static_cast<float>(u) * g.kt, zx = static_cast<float>(st.x - g.mx) * g.kx, zy = static_cast<float>(st.y - g.my) * g.ky;
+    const float ft = __fdividef(static_cast<float>(g.nt), 1.0f + __expf(-zt));  // exp overflow -> 0, underflow -> count: the edge bins
+    const float fx = __fdividef(static_cast<float>(g.nx), 1.0f + __expf(-zx));
+    const float fy = __fdividef(static_cast<float>(g.ny), 1.0f + __expf(-zy));
+    bt = min(max(__float2int_rz(ft), 0), static_cast<int>(g.nt) - 1);  // NaN converts to 0
+    bx = min(max(__float2int_rz(fx), 0), static_cast<int>(g.nx) - 1);
+    by = min(max(__float2int_rz(fy), 0), static_cast<int>(g.ny) - 1);
+  } else {
+    bt = min(max(static_cast<int>(fmin(fmax((u + g.half_u) * g.scale_t, 0.0), 1e6)), 0), static_cast<int>(g.nt) - 1);
+    bx = min(max(static_cast<int>(fmin(fmax((st.x - g.x0) * g.scale_x, 0.0), 1e6)), 0), static_cast<int>(g.nx) - 1);
+    by = min(max(static_cast<int>(fmin(fmax((st.y - g.y0) * g.scale_y, 0.0), 1e6)), 0), static_cast<int>(g.ny) - 1);
+  }
+  // Boustrophedon order: every other row runs backwards in x and every other plane backwards in y, so that consecutive
+  // bins are always neighbours (a warp crossing a row end would otherwise span the whole cloud).
+  if (bt & 1) by = static_cast<int>(g.ny) - 1 - by;
+  const uint32_t row = static_cast<uint32_t>(bt) * g.ny + static_cast<uint32_t>(by);
+  if (row & 1u) bx = static_cast<int>(g.nx) - 1 - bx;
+  return row * g.nx + static_cast<uint32_t>(bx);
 }
 
 /// propagate with the histogram of the execution schedule fused in (the bin grid comes from the host's prediction).
@@ -2096,12 +2114,13 @@ uint32_t schedule_max_bins() { return kMaxBins; }
 uint32_t schedule_tile_count() { return (kMaxBins + kScanTile - 1) / kScanTile; }
 
 void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uint32_t* bins, uint32_t* counters, uint32_t* perm,
-                           unsigned long long* tile_state, double mean_range, double min_bin, double per_bin, cudaStream_t stream) {
+                           unsigned long long* tile_state, double mean_range, double min_bin, double per_bin, double x_split, bool equal_mass,
+                           cudaStream_t stream) {
   if (n == 0) return;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   cudaMemsetAsync(counters, 0, kMaxBins * sizeof(uint32_t), stream);
   cudaMemsetAsync(tile_state, 0, schedule_tile_count() * sizeof(unsigned long long), stream);
-  schedule_params_kernel<<<1, 1, 0, stream>>>(sched, n, mean_range, min_bin, per_bin);
+  schedule_params_kernel<<<1, 1, 0, stream>>>(sched, n, mean_range, min_bin, per_bin, x_split, equal_mass);
   schedule_histogram_kernel<<<blocks, 256, 0, stream>>>(states, n, sched, bins, counters);
   scan_u32_kernel<<<schedule_tile_count(), kScanThreads, 0, stream>>>(counters, counters, kMaxBins, &sched->tile_ticket, tile_state, nullptr);
   schedule_scatter_kernel<<<blocks, 256, 0, stream>>>(bins, n, counters, perm);

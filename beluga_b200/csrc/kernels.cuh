@@ -165,17 +165,27 @@ struct Schedule {
   double c0, s0;            // mean heading (unit complex)
   double x0, y0, half_u;    // lower corner of the box; half extent of the heading coordinate u = 2 tan(dtheta / 2)
   double scale_t, scale_x, scale_y;
+  double mx, my;            // cloud mean (equal-mass bins)
+  float kt, kx, ky;         // equal-mass bins: 1.702 / sigma of u, x, y (logistic stand-in for the normal CDF)
+  uint32_t equal_mass;      // bins of equal expected particle count instead of equal size
   uint32_t nt, nx, ny;
   uint32_t n_bins;
 };
-constexpr uint32_t kScheduleMaxBins = 1u << 18;  // 16 particles per bin up to 4M particles per shard
+constexpr uint32_t kScheduleMaxBins = 1u << 19;  // 4 particles per bin up to 2M particles per shard, coarser bins beyond
 
 /// The pose-bin grid for a cloud with mean resultant (cbar, sbar), mean position (mx, my) and position variances
-/// (vx, vy): bins of equal physical edge in (range * heading, x, y) covering +-3 sigma, about `per_bin` particles each.
-/// Runs on the device (moments of the propagated cloud) or on the host (moments predicted from the last estimate and
-/// the motion means).  The schedule only decides WHICH THREAD handles a particle, never a result.
+/// (vx, vy), about `per_bin` particles per bin.  Runs on the device (moments of the propagated cloud) or on the host
+/// (moments predicted from the last estimate and the motion means).  The schedule only decides WHICH THREAD handles a
+/// particle, never a result.
+///
+/// equal_mass = false: bins of equal physical edge in (range * heading, x, y) covering +-3 sigma.
+/// equal_mass = true:  every coordinate goes through a sigmoid CDF (logistic with the normal's spread) first, so that bins
+///   hold the same EXPECTED number of particles: small where the cloud is dense, large in the tails.  A uniform grid over
+///   a normal cloud puts most particles into bins 13x over-full, and 32 schedule neighbours then span a whole bin.
+/// x_split: bins are x_split times thinner in x than in the other two coordinates; x is the fastest index of the bin
+///   order, so a warp (32 neighbours of the schedule) covers x_split bins of a row: a cube, whatever the bin boundaries.
 BB_HD void schedule_from_moments(Schedule& g, double cbar, double sbar, double mx, double my, double vx, double vy, double n,
-                                 double mean_range, double min_bin, double per_bin) {
+                                 double mean_range, double min_bin, double per_bin, double x_split = 1.0, bool equal_mass = false) {
   const double r = sqrt(cbar * cbar + sbar * sbar);
   const double pi = 3.14159265358979323846;
   double c0 = 1.0, s0 = 0.0, sigma_theta = pi;
@@ -187,13 +197,18 @@ BB_HD void schedule_from_moments(Schedule& g, double cbar, double sbar, double m
   const double half_theta = fmin(2.0, fmax(3.0 * sigma_theta, 1e-4));  // beyond +-2 rad: the edge bins
   const double half_u = 2.0 * tan(0.5 * half_theta);
   const double half_x = fmax(3.0 * sqrt(fmax(vx, 0.0)), min_bin), half_y = fmax(3.0 * sqrt(fmax(vy, 0.0)), min_bin);
-  const double ext_t = 2.0 * half_u * fmax(mean_range, 1.0), ext_x = 2.0 * half_x, ext_y = 2.0 * half_y;
-  double q = cbrt(ext_t * ext_x * ext_y / fmax(n / per_bin, 1.0));
+  const double lever = fmax(mean_range, 1.0);
+  x_split = fmin(fmax(x_split, 1.0), 32.0);
+  // Extents in physical units.  Equal-size bins tile the +-3 sigma box; equal-mass bins tile the unit cube of CDF values,
+  // where a bin at the centre of the cloud is sigma / (density of the sigmoid at 0 = 1.702 / 4) / count wide.
+  const double centre = equal_mass ? 1.0 / (3.0 * 0.4255) : 2.0;
+  const double ext_t = centre * half_u * lever, ext_x = centre * half_x, ext_y = centre * half_y;
+  double q = cbrt(x_split * ext_t * ext_x * ext_y / fmax(n / per_bin, 1.0));  // edge of x_split bins side by side
   q = fmax(q, min_bin);
   uint32_t nt, nx, ny;
   for (;;) {
     nt = static_cast<uint32_t>(fmin(fmax(ceil(ext_t / q), 1.0), 65536.0));
-    nx = static_cast<uint32_t>(fmin(fmax(ceil(ext_x / q), 1.0), 65536.0));
+    nx = static_cast<uint32_t>(fmin(fmax(ceil(x_split * ext_x / q), 1.0), 65536.0));
     ny = static_cast<uint32_t>(fmin(fmax(ceil(ext_y / q), 1.0), 65536.0));
     if (static_cast<uint64_t>(nt) * nx * ny <= kScheduleMaxBins) break;
     q = q * 1.3;
@@ -201,8 +216,11 @@ BB_HD void schedule_from_moments(Schedule& g, double cbar, double sbar, double m
   g.c0 = c0, g.s0 = s0;
   g.x0 = mx - half_x, g.y0 = my - half_y, g.half_u = half_u;
   g.scale_t = static_cast<double>(nt) / (2.0 * half_u);
-  g.scale_x = static_cast<double>(nx) / ext_x;
-  g.scale_y = static_cast<double>(ny) / ext_y;
+  g.scale_x = static_cast<double>(nx) / (2.0 * half_x);
+  g.scale_y = static_cast<double>(ny) / (2.0 * half_y);
+  g.mx = mx, g.my = my;
+  g.kt = static_cast<float>(1.702 * 3.0 / half_u), g.kx = static_cast<float>(1.702 * 3.0 / half_x), g.ky = static_cast<float>(1.702 * 3.0 / half_y);
+  g.equal_mass = equal_mass ? 1u : 0u;
   g.nt = nt, g.nx = nx, g.ny = ny;
   g.n_bins = nt * nx * ny;
 }
@@ -225,7 +243,8 @@ uint32_t schedule_max_bins();
 uint32_t schedule_tile_count();
 /// Counting sort of the particle indices over pose bins -> perm (needs launch_propagate's moments).
 void launch_build_schedule(const Pose2* states, uint64_t n, Schedule* sched, uint32_t* bins, uint32_t* counters, uint32_t* perm,
-                           unsigned long long* tile_state, double mean_range, double min_bin, double per_bin, cudaStream_t stream);
+                           unsigned long long* tile_state, double mean_range, double min_bin, double per_bin, double x_split, bool equal_mass,
+                           cudaStream_t stream);
 /// reweight with the likelihood-field table in schedule order (perm may be null) | block max.
 /// points_xy_host (optional): the same points in host memory; scans of up to 1920 points then travel as
 /// kernel parameters (constant bank) instead of being staged through shared memory.
