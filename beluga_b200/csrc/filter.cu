@@ -1016,8 +1016,8 @@ int Filter::set_likelihood_field_map(const bb200_likelihood_field_param& p, cons
     field_.bordered = bordered_;
     field_.border_kx = kx;
     field_.border_pitch = 1u << kx;
-    field_.border_x_max = static_cast<uint32_t>(g.width + 1);
-    field_.border_y_max = static_cast<uint32_t>(4 * (g.height + 1) + 3);
+    field_.border_x_max = static_cast<uint32_t>(4 * (g.width + 1) + 3);
+    field_.border_y_max = static_cast<uint32_t>(g.height + 1);
     field_.use_fixed = 1;
   }
   field_.tiled = tiled_;

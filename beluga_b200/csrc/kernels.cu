@@ -562,48 +562,52 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
 // 2 mul and 2 floor conversions per beam, all on the FP64 pipe).  The CELL is all that matters, so the
 // kernel evaluates   g = fma(px, c*inv, fma(-py, s*inv, tx*inv + 1))   (2 fma per coordinate; the +1 is
 // the border cell), which differs from the reference's value by d <= 11 * 2^13 * 2^-53 < 2^-36 cells
-// while every term stays below 2^13 cells, and adds 1.5*2^20: in the sum's bit pattern the low word is
+// while every term stays below 2^13 cells, and adds 1.5*2^20 (y): in the sum's bit pattern the low word is
 // the fraction of g in units of 2^-32 (round to nearest) and the low 20 bits of the high word are
 // 2^19 + floor(g).  If the fraction word is not zero, g is at least 2^-33 > d away from an integer and
-// floor(reference value) = floor(g) exactly.  y adds 1.5*2^18 instead, so its high word carries
-// floor(4g) -- the bits the 4x4-tile index wants -- and a non-zero fraction word puts g at least
-// 2^-35 > d from an integer.  A thread that ever sees a zero fraction word (2^-32 per coordinate, about
-// once every two steps among a million particles) or a particle out of the 2^13 range redoes its
-// beams with the reference's own operation sequence; nothing else in the loop branches.
+// floor(reference value) = floor(g) exactly.  x adds 1.5*2^18 instead, so its high word carries
+// floor(4g) -- x already shifted into the place the 4x4-tile index wants it -- and a non-zero fraction
+// word puts g at least 2^-35 > d from an integer.  A thread that ever sees a zero fraction word (2^-32 per
+// coordinate, about once every two steps among a million particles) or a particle out of the 2^13 range
+// redoes its beams with the reference's own operation sequence; nothing else in the loop branches.
 // Out-of-grid end points clamp (one DPX add-min per coordinate, which also strips the bias) to the
 // one-cell border holding the unknown-space value, so the load is unconditional.
 
-constexpr double kFixedMagicX = 1572864.0;  // 1.5 * 2^20: ulp 2^-32; high word = 0x41380000 + floor(g)      for |g| < 2^19
-constexpr double kFixedMagicY = 393216.0;   // 1.5 * 2^18: ulp 2^-34; high word = 0x41180000 + floor(4 g)    for |g| < 2^17
-constexpr uint32_t kFixedBiasX = 0x41380000u, kFixedBiasY = 0x41180000u;
+constexpr double kFixedMagicX = 393216.0;   // 1.5 * 2^18: ulp 2^-34; high word = 0x41180000 + floor(4 g)    for |g| < 2^17
+constexpr double kFixedMagicY = 1572864.0;  // 1.5 * 2^20: ulp 2^-32; high word = 0x41380000 + floor(g)      for |g| < 2^19
+constexpr uint32_t kFixedBiasX = 0x41180000u, kFixedBiasY = 0x41380000u;
 // The magic constants ride in the FMAs' addend (per-particle offsets ox, oy below), which saves the two additions per beam
 // but lets THREE roundings at the magic's ulp into the word instead of one (the offset sum and both FMAs): the computed
 // fixed-point value is within 3 half-ulps + 2^-36 cells of the reference's.  Two ulps of guard are added to the offset so
 // that the reference's value lies in (computed - 4.07 ulp, computed + 0.07 ulp): the high word is the reference's cell
 // whenever the fraction word is at least 5.  tests/test_fixed_point_lookup_model.py replays this with exact rationals,
 // including end points a hair (2^-36 .. 2^-30 cells) either side of a cell edge at arbitrary headings.
-constexpr double kFixedGuardX = 4.656612873077392578125e-10;   // 2^-31 = 2 ulp of kFixedMagicX
-constexpr double kFixedGuardY = 1.16415321826934814453125e-10; // 2^-33 = 2 ulp of kFixedMagicY
+constexpr double kFixedGuardX = 1.16415321826934814453125e-10; // 2^-33 = 2 ulp of kFixedMagicX
+constexpr double kFixedGuardY = 4.656612873077392578125e-10;   // 2^-31 = 2 ulp of kFixedMagicY
 constexpr uint32_t kFixedAmbiguous = 4u;  // fraction words 0..4: the cell is not decided (5 * 2^-32 per coordinate)
 
 struct FixedParticle {
   double cx, sx;         // cos, sin of the field-frame heading, times 1/resolution
   double ox, oy;         // field-frame position in cells, plus the border cell, plus magic constant and guard
-  uint32_t x_max, y_max; // width + 1, 4 (height + 1) + 3: largest padded x and 4 * padded y (+ 2 fraction bits)
-  uint32_t row_pitch;    // 2^kx: tiles per row
+  uint32_t x_max, y_max; // 4 (width + 1) + 3, height + 1: largest 4 * padded x (+ 2 fraction bits) and padded y
+  uint32_t row_pitch;    // 4 * 2^kx: elements per row of cells (four rows of tiles' worth per tile row)
 };
 
 /// `margin` collects the smallest fraction word seen (<= kFixedAmbiguous: a coordinate too close to a cell edge to call).
+/// x arrives as 4 * padded x with two fraction bits below it, y as padded y: the element index
+///   (y >> 2) * 16 * tiles_per_row  +  (x >> 2) * 16 + (x & 3) * 4 + (y & 3)
+/// is then one bit-select (y's low two bits replace x's fraction bits), one mask and one multiply-add.
 __device__ __forceinline__ double fixed_lookup(const double* __restrict__ bordered, const FixedParticle& q, double px, double py, uint32_t& margin) {
   const double gx = fma(px, q.cx, fma(-py, q.sx, q.ox));  // gx + 1 + magic + guard
   const double gy = fma(px, q.sx, fma(py, q.cx, q.oy));   // gy + 1 + magic + guard
   margin = __vimin3_u32(margin, static_cast<uint32_t>(__double2loint(gx)), static_cast<uint32_t>(__double2loint(gy)));
   // min(word - bias, max): a negative coordinate wraps to a huge unsigned and clamps to the far border,
   // which holds the same unknown-space value as the near one.
-  const uint32_t ux = __viaddmin_u32(static_cast<uint32_t>(__double2hiint(gx)), 0u - kFixedBiasX, q.x_max);  // padded x
-  const uint32_t uy = __viaddmin_u32(static_cast<uint32_t>(__double2hiint(gy)), 0u - kFixedBiasY, q.y_max);  // 4 * padded y + 2 fraction bits
-  const uint32_t a = ux + 3u * (ux & ~3u);                                                                   // (x & 3) | ((x >> 2) << 4)
-  const uint32_t idx = __umul24(uy & ~0xFu, q.row_pitch) + (a | (uy & 0xCu));
+  const uint32_t ux = __viaddmin_u32(static_cast<uint32_t>(__double2hiint(gx)), 0u - kFixedBiasX, q.x_max);  // 4 * padded x + 2 fraction bits
+  const uint32_t uy = __viaddmin_u32(static_cast<uint32_t>(__double2hiint(gy)), 0u - kFixedBiasY, q.y_max);  // padded y
+  uint32_t low;  // (ux & ~3) | (uy & 3) as ONE bit-select (the compiler splits it into two operations)
+  asm("lop3.b32 %0, %1, 3, %2, 0xB8;" : "=r"(low) : "r"(ux), "r"(uy));
+  const uint32_t idx = (uy & ~3u) * q.row_pitch + low;
   return __ldg(bordered + idx);
 }
 
@@ -683,7 +687,7 @@ __device__ __forceinline__ void fixed_particle_setup(const FieldView& field, con
   q.oy = (t.y * inv + 1.0) + (kFixedMagicY + kFixedGuardY);
   q.x_max = field.border_x_max;
   q.y_max = field.border_y_max;
-  q.row_pitch = field.border_pitch;
+  q.row_pitch = 4u * field.border_pitch;
 }
 
 /// Scan in the constant bank: nothing is shared between the warps of a CTA, so the grid is persistent

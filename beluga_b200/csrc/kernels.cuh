@@ -32,14 +32,14 @@ struct FieldView {
   const double* bordered;
   int border_kx;
   uint32_t border_pitch;  // 2^border_kx
-  uint32_t border_x_max;  // width + 1: largest padded x
-  uint32_t border_y_max;  // 4 (height + 1) + 3: largest 4 * padded y with its two fraction bits
+  uint32_t border_x_max;  // 4 (width + 1) + 3: largest 4 * padded x with its two fraction bits
+  uint32_t border_y_max;  // height + 1: largest padded y
   int use_fixed;          // launch the fixed-point kernel (map small enough for 16.16 cell coordinates)
 };
 
 /// Offset of padded cell (px, py) in the bordered tile layout.
 BB_HD uint32_t bordered_index(uint32_t px, uint32_t py, int kx) {
-  return (((py >> 2) << (kx + 4)) | ((px >> 2) << 4)) | ((py & 3u) << 2) | (px & 3u);
+  return (((py >> 2) << (kx + 4)) | ((px >> 2) << 4)) | ((px & 3u) << 2) | (py & 3u);  // 4 x 4 tiles, y fastest inside a tile
 }
 /// Largest padded grid side the fixed-point kernel accepts (cell coordinates below 2^13).
 constexpr int kFixedMaxSide = 8000;

@@ -13,13 +13,13 @@ from fractions import Fraction
 import numpy as np
 import pytest
 
-MAGIC_X, MAGIC_Y = 1572864.0, 393216.0  # 1.5 * 2^20, 1.5 * 2^18 (kFixedMagicX / kFixedMagicY)
-BIAS_X, BIAS_Y = 0x41380000, 0x41180000
-# Folding the magic add into the FMA chain costs three roundings at the magic's ulp (2^-32 for x, 2^-34 for y) instead of
+MAGIC_X, MAGIC_Y = 393216.0, 1572864.0  # 1.5 * 2^18, 1.5 * 2^20 (kFixedMagicX / kFixedMagicY)
+BIAS_X, BIAS_Y = 0x41180000, 0x41380000
+# Folding the magic add into the FMA chain costs three roundings at the magic's ulp (2^-34 for x, 2^-32 for y) instead of
 # one: the computed fixed-point value lies within 3 half-ulps + 2^-36 of the reference's.  Two ulps of guard are added to
 # the offset, so that the uncertainty interval sits entirely BELOW the computed value: the cell is the reference's
 # whenever the fraction word is at least 5 (kFixedGuardX / kFixedGuardY / kFixedAmbiguous in the kernel).
-GUARD_X, GUARD_Y = 2.0 ** -31, 2.0 ** -33
+GUARD_X, GUARD_Y = 2.0 ** -33, 2.0 ** -31
 AMBIGUOUS_BELOW = 4
 
 
@@ -47,10 +47,10 @@ def kernel_cells(px, py, c, s, tx, ty, inv):
     gy = fma(px, sx, fma(py, cx, oy))
     hx, lx = words(gx)
     hy, ly = words(gy)
-    ux = (hx - BIAS_X) & 0xFFFFFFFF  # padded x = cell + 1 (for cells >= -1)
-    uy = (hy - BIAS_Y) & 0xFFFFFFFF  # 4 * padded y + 2 fraction bits
+    ux = (hx - BIAS_X) & 0xFFFFFFFF  # 4 * padded x + 2 fraction bits (padded x = cell + 1, for cells >= -1)
+    uy = (hy - BIAS_Y) & 0xFFFFFFFF  # padded y
     to_signed = lambda u: u - (1 << 32) if u >= (1 << 31) else u  # noqa: E731
-    return to_signed(ux) - 1, (to_signed(uy) >> 2) - 1, (lx <= AMBIGUOUS_BELOW or ly <= AMBIGUOUS_BELOW)
+    return (to_signed(ux) >> 2) - 1, to_signed(uy) - 1, (lx <= AMBIGUOUS_BELOW or ly <= AMBIGUOUS_BELOW)
 
 
 def random_case(rng, res):
@@ -88,7 +88,7 @@ def test_end_points_on_and_around_cell_edges():
         for _ in range(400):
             tx, ty = float(rng.integers(0, 2000)) * res, float(rng.integers(0, 2000)) * res
             # px on a cell edge (before the +-k ulp nudges), py well inside a cell; the quarter turns swap their roles,
-            # so both the x word (16.. fraction bits after 1.5*2^20) and the y word (after 1.5*2^18) meet edges
+            # so both the x word (fraction bits after 1.5*2^18) and the y word (after 1.5*2^20) meet edges
             px = float(rng.integers(-400, 400)) * res
             py = (float(rng.integers(-400, 400)) + float(rng.uniform(0.2, 0.8))) * res  # y: well inside a cell
             for k in (0, 1, -1, 3, -3, 4096, -4096):
