@@ -643,12 +643,27 @@ struct ScanParam {
     const double acc_before = acc;                                                                            \
     uint32_t margin = margin_start;                                                                           \
     uint32_t b = 0;                                                                                           \
-    BB200_PRAGMA_UNROLL(BB200_RW_UNROLL) for (; b + 4 <= (COUNT); b += 4) {                                   \
-      const double2 p0 = POINT(b), p1 = POINT(b + 1), p2 = POINT(b + 2), p3 = POINT(b + 3);                   \
-      const double f0 = LOOKUP(TABLE, q, p0.x, p0.y, margin);                                                 \
-      const double f1 = LOOKUP(TABLE, q, p1.x, p1.y, margin);                                                 \
-      const double f2 = LOOKUP(TABLE, q, p2.x, p2.y, margin);                                                 \
-      const double f3 = LOOKUP(TABLE, q, p3.x, p3.y, margin);                                                 \
+    if (4 <= (COUNT)) {                                                                                       \
+      /* Software pipeline: the loads of the next four beams are issued before the previous four are summed */\
+      /* (a warp issues in order: summing first would leave it with four loads in flight, then none).       */\
+      double f0, f1, f2, f3;                                                                                  \
+      {                                                                                                       \
+        const double2 p0 = POINT(0), p1 = POINT(1), p2 = POINT(2), p3 = POINT(3);                             \
+        f0 = LOOKUP(TABLE, q, p0.x, p0.y, margin);                                                            \
+        f1 = LOOKUP(TABLE, q, p1.x, p1.y, margin);                                                            \
+        f2 = LOOKUP(TABLE, q, p2.x, p2.y, margin);                                                            \
+        f3 = LOOKUP(TABLE, q, p3.x, p3.y, margin);                                                            \
+      }                                                                                                       \
+      b = 4;                                                                                                  \
+      BB200_PRAGMA_UNROLL(BB200_RW_UNROLL) for (; b + 4 <= (COUNT); b += 4) {                                 \
+        const double2 p0 = POINT(b), p1 = POINT(b + 1), p2 = POINT(b + 2), p3 = POINT(b + 3);                 \
+        const double g0 = LOOKUP(TABLE, q, p0.x, p0.y, margin);                                               \
+        const double g1 = LOOKUP(TABLE, q, p1.x, p1.y, margin);                                               \
+        const double g2 = LOOKUP(TABLE, q, p2.x, p2.y, margin);                                               \
+        const double g3 = LOOKUP(TABLE, q, p3.x, p3.y, margin);                                               \
+        acc = acc + ((f0 + f1) + (f2 + f3));                                                                  \
+        f0 = g0, f1 = g1, f2 = g2, f3 = g3;                                                                   \
+      }                                                                                                       \
       acc = acc + ((f0 + f1) + (f2 + f3));                                                                    \
     }                                                                                                         \
     for (; b < (COUNT); ++b) {                                                                                \
