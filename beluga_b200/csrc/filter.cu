@@ -1,6 +1,7 @@
 #include "filter.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -111,6 +112,7 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   if (const char* v = std::getenv("BB200_PARAM_POINTS")) param_points_ = std::atoi(v) != 0;  // development knob: scan as kernel parameters
   if (const char* v = std::getenv("BB200_BEAM_ETA_TABLE")) beam_eta_table_ = std::atoi(v) != 0;  // development knob: tabulated beam normalisers
   if (const char* v = std::getenv("BB200_FIXED")) fixed_lookup_ = std::atoi(v) != 0;         // development knob: fixed-point lookup kernel
+  if (const char* v = std::getenv("BB200_POLL_COMPLETION")) poll_completion_ = std::atoi(v) != 0;  // development knob: 0 = cudaStreamSynchronize
   if (const char* v = std::getenv("BB200_PREDICT_SCHEDULE")) predict_schedule_ = std::atoi(v) != 0;  // development knob: host-predicted pose bins
   if (const char* v = std::getenv("BB200_PREFETCH_TABLE")) prefetch_table_ = std::atoi(v) != 0;  // development knob: L2 prefetch of the likelihood table
   if (const char* v = std::getenv("BB200_BEAM_TWO_PASS")) beam_two_pass_ = std::atoi(v) != 0;  // development knob: walk + mixture kernels
@@ -652,7 +654,13 @@ int Filter::step_phase(int phase) {
         a = make_resample_args(o, 0, o.max_particles, false);
         mark("resample");
       }
-      a.tail = StepTail{1, results_, sharded ? nullptr : summary_host_};  // the last block sums the moments (one GPU: straight into pinned host memory)
+      // the last block sums the moments (one GPU: straight into pinned host memory, with the step's completion ticket)
+      step_.poll_seq = 0;
+      if (!sharded && poll_completion_ && !timing_) {
+        step_seq_ = step_seq_ == 0x7fffffff ? 1 : step_seq_ + 1;
+        step_.poll_seq = step_seq_;
+      }
+      a.tail = StepTail{1, results_, sharded ? nullptr : summary_host_, step_.poll_seq};
       step_.partial_rows = launch_resample(a, scalars_, partials_, stream_);
       BB_LAUNCHED("resample");
       step_.resampled = true;
@@ -797,7 +805,25 @@ void Filter::step_set_kld_accepted(uint64_t accepted) { step_.kld_accepted = acc
 int Filter::step_end(bb200_estimate* est, double* weight_sum, uint64_t* new_size, double* sum_sq) {
   if (!step_.active) return fail(BB200_ERR_STATE, "step_begin must run first");
   BB_CHECK(cudaSetDevice(config_.device));
-  BB_CHECK(cudaStreamSynchronize(stream_));
+  bool done = false;
+  if (step_.poll_seq != 0 && step_.resampled) {
+    // The resample kernel's last block stored the summary to pinned memory and then the step's ticket: spinning on that
+    // word sees the end of the step a few microseconds before a stream synchronisation returns.  Everything later on this
+    // stream is ordered behind the kernel anyway.  The stream is queried now and then so that a failed launch cannot hang us.
+    const volatile int* seq = &summary_host_->seq;
+    for (uint32_t spins = 1; !done; ++spins) {
+      if (*seq == step_.poll_seq) {
+        done = true;
+      } else if ((spins & 0x3fffu) == 0) {
+        const cudaError_t q = cudaStreamQuery(stream_);
+        if (q == cudaSuccess) break;  // finished: the ticket is there (or the plain path below reports what went wrong)
+        if (q != cudaErrorNotReady) break;
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
+  if (!done) BB_CHECK(cudaStreamSynchronize(stream_));
+  step_.poll_seq = 0;
   finish_marks();
   const bool sharded = peer_world_ > 1;
   if (summary_host_->error != 0) {

@@ -172,6 +172,7 @@ class Filter {
     bool resample_planned{false};  // kPhaseResample follows kPhaseCdf directly (every_n fired, no ESS decision in between)
     bool weights_filled{false};
     bool totals_exchanged{false};
+    int poll_seq{0};  // != 0: the resample kernel stores this ticket to the pinned summary when the step is complete
     uint64_t kld_accepted{0};  // KLD on shards: particle count of the new set (0: fixed size)  // the ranks' totals of this step are in shard_totals_
     unsigned long long total{0};
     int exponent{0};
@@ -291,6 +292,8 @@ class Filter {
   bb200_estimate cloud_{};     // last estimate, when it describes the raw (unit-weight) cloud
   bool cloud_known_{false};
   bool predict_schedule_{true};
+  bool poll_completion_{true};
+  int step_seq_{0};
 
   // timing
   bool timing_{false};

@@ -1712,6 +1712,10 @@ __device__ __forceinline__ void finish_block_moments(double* m, double* scratch,
       tail.summary->valid = scalars->valid;
       tail.summary->error = 0;
       __threadfence_system();
+      if (tail.seq != 0) {  // the host polls this word instead of synchronising with the stream
+        *reinterpret_cast<volatile int*>(&tail.summary->seq) = tail.seq;
+        __threadfence_system();
+      }
     }
   }
 }
@@ -2188,6 +2192,11 @@ void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const
       std::memcpy(scan.p, points_xy_host, static_cast<size_t>(n_points) * sizeof(double2));
       const unsigned ctas_needed = static_cast<unsigned>((n + kRwThreads - 1) / kRwThreads);
       const unsigned persistent = std::min<unsigned>(static_cast<unsigned>(sm_count()) * kRwBlocksPerSm, ctas_needed);
+      static const int carveout = [] {  // development knob: shared-memory carve-out in percent (the kernel uses no shared memory)
+        const char* v = std::getenv("BB200_RW_CARVEOUT");
+        return v != nullptr ? std::atoi(v) : -1;
+      }();
+      if (carveout >= 0) cudaFuncSetAttribute(reweight_lfm_fixed_param_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
       reweight_lfm_fixed_param_kernel<<<persistent, kRwThreads, 0, stream>>>(states, weights, n, perm, field, n_points, points_radius, scalars, scan);
     } else {
       reweight_lfm_fixed_kernel<<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars);

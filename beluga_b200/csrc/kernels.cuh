@@ -117,7 +117,7 @@ struct StepSummary {
   int exponent;
   int valid;                      // 0: no positive finite weight anywhere
   int error;                      // 1: a peer never posted (bounded spin ran out)
-  int pad;
+  int seq;                        // completion ticket of the step that wrote this block (written last; the host may poll it)
 };
 struct ShardExchangeArgs {
   int kind, post, wait;
@@ -290,6 +290,7 @@ struct StepTail {
   int enabled;
   double* results;
   StepSummary* summary;
+  int seq;  // != 0: stored to summary->seq after everything else (system-scope fence in between)
 };
 
 struct ResampleArgs {
