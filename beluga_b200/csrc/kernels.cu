@@ -705,6 +705,35 @@ __device__ __forceinline__ void fixed_particle_setup(const FieldView& field, con
   q.row_pitch = 4u * field.border_pitch;
 }
 
+#if BB200_RW_CHUNK > 0
+/// Next task of the CTA's current chunk (see the experiment note in reweight_lfm_fixed_param_kernel).  Every branch is on a
+/// value broadcast from lane 0, so that the warp provably stays converged: a spin loop inside `if (lane == 0)` makes ptxas
+/// give up the uniform datapath (LDCU) for the scan points in the beam loop that follows (LDC through the ADU pipe instead,
+/// which alone costs 20 %).
+__device__ __forceinline__ unsigned long long take_chunk_ticket(unsigned long long* s_chunk, unsigned long long* ticket_counter, int lane) {
+  for (;;) {
+    unsigned long long old = 0;
+    if (lane == 0) old = atomicAdd(s_chunk, 1ull);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    const unsigned long long idx = old & 0xFFull, chunk = old >> 8;
+    if (idx < BB200_RW_CHUNK) return chunk * BB200_RW_CHUNK + idx;
+    if (idx == BB200_RW_CHUNK) {  // this warp refills: the new chunk's task 0 is its own
+      unsigned long long fresh = 0;
+      if (lane == 0) fresh = atomicAdd(ticket_counter, 1ull);
+      fresh = __shfl_sync(0xffffffffu, fresh, 0);
+      if (lane == 0) atomicExch(s_chunk, (fresh << 8) | 1ull);
+      return fresh * BB200_RW_CHUNK;
+    }
+    for (;;) {  // another warp is fetching the next chunk
+      unsigned long long cur = 0;
+      if (lane == 0) cur = *reinterpret_cast<volatile unsigned long long*>(s_chunk);
+      cur = __shfl_sync(0xffffffffu, cur, 0);
+      if ((cur >> 8) != chunk) break;
+    }
+  }
+}
+#endif
+
 /// Scan in the constant bank: nothing is shared between the warps of a CTA, so the grid is persistent
 /// (CTAs/SM x SM count) and every WARP draws the next 32 particles of the schedule from a global
 /// ticket counter.  A CTA-per-256-particles grid loses 10-13 % to its slowest warp (each CTA holds its
@@ -724,29 +753,7 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
   __shared__ unsigned long long s_chunk;
   if (threadIdx.x == 0) s_chunk = atomicAdd(ticket_counter, 1ull) << 8;
   __syncthreads();
-  auto take = [&]() -> unsigned long long {
-    unsigned long long t = 0;
-    if (lane == 0) {
-      for (;;) {
-        const unsigned long long old = atomicAdd(&s_chunk, 1ull);
-        const unsigned long long idx = old & 0xFFull, chunk = old >> 8;
-        if (idx < BB200_RW_CHUNK) {
-          t = chunk * BB200_RW_CHUNK + idx;
-          break;
-        }
-        if (idx == BB200_RW_CHUNK) {  // this warp refills: the new chunk's task 0 is its own
-          const unsigned long long fresh = atomicAdd(ticket_counter, 1ull);
-          atomicExch(&s_chunk, (fresh << 8) | 1ull);
-          t = fresh * BB200_RW_CHUNK;
-          break;
-        }
-        while ((*reinterpret_cast<volatile unsigned long long*>(&s_chunk) >> 8) == chunk) {
-        }
-      }
-    }
-    return __shfl_sync(0xffffffffu, t, 0);
-  };
-  unsigned long long ticket = take();
+  unsigned long long ticket = take_chunk_ticket(&s_chunk, ticket_counter, lane);
 #else
   unsigned long long ticket = __shfl_sync(0xffffffffu, lane == 0 ? atomicAdd(ticket_counter, 1ull) : 0ull, 0);
 #endif
@@ -774,7 +781,7 @@ __global__ void __launch_bounds__(kRwThreads, kRwBlocksPerSm)
       best = bits > best ? bits : best;
     }
 #if BB200_RW_CHUNK > 0
-    ticket = take();
+    ticket = take_chunk_ticket(&s_chunk, ticket_counter, lane);
 #else
     ticket = __shfl_sync(0xffffffffu, next, 0);
 #endif
@@ -2192,11 +2199,6 @@ void launch_reweight_lfm(const Pose2* states, double* weights, uint64_t n, const
       std::memcpy(scan.p, points_xy_host, static_cast<size_t>(n_points) * sizeof(double2));
       const unsigned ctas_needed = static_cast<unsigned>((n + kRwThreads - 1) / kRwThreads);
       const unsigned persistent = std::min<unsigned>(static_cast<unsigned>(sm_count()) * kRwBlocksPerSm, ctas_needed);
-      static const int carveout = [] {  // development knob: shared-memory carve-out in percent (the kernel uses no shared memory)
-        const char* v = std::getenv("BB200_RW_CARVEOUT");
-        return v != nullptr ? std::atoi(v) : -1;
-      }();
-      if (carveout >= 0) cudaFuncSetAttribute(reweight_lfm_fixed_param_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
       reweight_lfm_fixed_param_kernel<<<persistent, kRwThreads, 0, stream>>>(states, weights, n, perm, field, n_points, points_radius, scalars, scan);
     } else {
       reweight_lfm_fixed_kernel<<<blocks, kRwThreads, smem, stream>>>(states, weights, n, perm, field, points, n_points, points_radius, scalars);
