@@ -252,10 +252,10 @@ class Filter {
   bool tiled_layout_{true};
   bool fixed_lookup_{true};
   bool param_points_{true};
-  double schedule_per_bin_{16.0};
+  double schedule_per_bin_{4.0};
   double schedule_lever_{1.0};
-  double schedule_x_split_{1.0};
-  bool schedule_equal_mass_{false};
+  double schedule_x_split_{8.0};
+  bool schedule_equal_mass_{true};
   Schedule* sched_{nullptr};
   uint32_t* bins_{nullptr};
   uint2* bin_rank_{nullptr};
