@@ -155,6 +155,7 @@ Filter::Filter(const bb200_filter_config& config) : config_(config) {
   BB_TRY(dev_alloc(&shard_totals_, kMaxShards));
   BB_TRY(dev_alloc(&summary_, 1));
   BB_TRY(cudaMallocHost(reinterpret_cast<void**>(&summary_host_), sizeof(StepSummary)));
+  std::memset(summary_host_, 0, sizeof(StepSummary));  // pinned allocations are recycled with their old contents (a stale completion ticket)
   BB_TRY(cudaMemsetAsync(mail_, 0, sizeof(ShardMail), stream_));
   BB_TRY(cudaMemsetAsync(summary_, 0, sizeof(StepSummary), stream_));
   BB_TRY(cudaMemsetAsync(scalars_, 0, sizeof(Scalars), stream_));
@@ -659,6 +660,7 @@ int Filter::step_phase(int phase) {
       if (!sharded && poll_completion_ && !timing_) {
         step_seq_ = step_seq_ == 0x7fffffff ? 1 : step_seq_ + 1;
         step_.poll_seq = step_seq_;
+        summary_host_->seq = 0;  // nothing of this filter is in flight: the previous step was seen to end
       }
       a.tail = StepTail{1, results_, sharded ? nullptr : summary_host_, step_.poll_seq};
       step_.partial_rows = launch_resample(a, scalars_, partials_, stream_);

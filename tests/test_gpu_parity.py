@@ -609,3 +609,19 @@ def test_large_scale_properties(bb):
     assert np.all(w == 1.0)
     assert np.abs(np.hypot(st[:, 0], st[:, 1]) - 1.0).max() < 1e-14
     assert np.hypot(r.estimate.mean[2] - sc.poses[5][0], r.estimate.mean[3] - sc.poses[5][1]) < 0.5  # posterior sigma ~0.3 m (1 + sum pz^3 is a weak likelihood)
+
+
+def test_estimate_of_a_fresh_filter_is_its_own(bb, scene):
+    """The host polls a completion ticket in the filter's pinned summary block.  Pinned allocations are recycled with their
+    old contents: a new filter must not take a destroyed filter's last ticket (and its estimate) for its own first step."""
+    lfm = dict(max_obstacle_distance=2.0, max_laser_distance=100.0, z_hit=0.5, z_random=0.5, sigma_hit=0.2)
+    for shift in (0.0, 3.0, -2.5, 1.0):
+        g = bb.Amcl(bb.DifferentialDriveModelParam(0.1, 0.05, 0.1, 0.05), bb.AmclParams(min_particles=5000, max_particles=5000, resample_scheme=1, seed=3))
+        g.update_map(0, bb.LikelihoodFieldModelParam(**lfm), bb.OccupancyGrid(scene.cells, scene.resolution))
+        mean = np.array(scene.initial_mean, dtype=float)
+        mean[0] += shift
+        g.initialize(mean, scene.initial_cov * 0.01)
+        r = g.update(bb.se2(*scene.poses[0]), scene.scans[0])
+        assert r.updated == 1 and r.resampled == 1
+        assert abs(r.estimate.mean[2] - mean[0]) < 0.3 and abs(r.estimate.mean[3] - mean[1]) < 0.3
+        del g
