@@ -85,16 +85,54 @@ class ClockSampler:
         self.samples = []
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
+        self._nvml = self._open_nvml(device)
+
+    @staticmethod
+    def _open_nvml(device: int):
+        """(module, handle) for in-process NVML sampling, or None -> one nvidia-smi process per sample (slow: a 60 ms timed
+        region then sees a single sample)."""
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(device).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)  # probe
+            return pynvml, handle
+        except Exception:
+            return None
+
+    def _sample_nvml(self):
+        nv, h = self._nvml
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        flag = lambda bit: "Active" if mask & bit else "Not Active"  # noqa: E731
+        # same column layout as the nvidia-smi query: index, sm, max sm, power, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        return [str(self.device), str(sm), str(mx), "", flag(0x8), flag(0x40), flag(0x20), flag(0x4)]
 
     def _run(self):
         while not self._stop.is_set():
             try:
+                if self._nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                    self._stop.wait(0.01)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.device)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
                     self.samples.append([c.strip() for c in out.split(",")])
             except Exception:
-                pass
+                self._nvml = None  # NVML went away: fall back to nvidia-smi
             self._stop.wait(0.05)
 
     def __enter__(self):
@@ -116,7 +154,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def measured_peak_gbs():
