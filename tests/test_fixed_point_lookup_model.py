@@ -158,3 +158,46 @@ def test_end_points_a_hair_either_side_of_an_edge_at_any_heading():
                     decided += 1
                     assert (xk, yk) == (xr, yr), (case, eps)
     assert flagged > 200 and decided > 200
+
+
+def bordered_index(px: int, py: int, kx: int) -> int:
+    """kernels.cuh: bordered_index -- 4 x 4 tiles, 2^kx tiles per row, y fastest inside a tile."""
+    return ((py >> 2) << (kx + 4)) | ((px >> 2) << 4) | ((px & 3) << 2) | (py & 3)
+
+
+def kernel_index(ux4: int, uy: int, kx: int) -> int:
+    """fixed_lookup's integer tail: x arrives as 4 * padded x + two fraction bits, y as padded y; one bit-select (lop3 0xB8 with
+    the immediate 3), one mask, one multiply-add with row_pitch = 4 * 2^kx."""
+    low = (ux4 & ~3) | (uy & 3)
+    return ((uy & ~3) * (4 << kx) + low) & 0xFFFFFFFF
+
+
+def test_tile_index_is_the_bordered_layout():
+    """The three integer operations of the lookup reproduce bordered_index for every padded cell and every value of the two
+    fraction bits, the layout is a bijection onto the table, and clamped coordinates stay inside it."""
+    for width, height in ((5, 7), (64, 33), (200, 200)):
+        kx = max(0, math.ceil(math.log2(-(-(width + 2) // 4))))
+        seen = set()
+        for py in range(height + 2):
+            for px in range(width + 2):
+                want = bordered_index(px, py, kx)
+                for frac in range(4):
+                    assert kernel_index(4 * px + frac, py, kx) == want
+                seen.add(want)
+        assert len(seen) == (width + 2) * (height + 2)  # no two cells share an element
+        rows = -(-(height + 2) // 4)
+        assert max(seen) < rows * (16 << kx)
+        # what __viaddmin_u32 leaves of wild coordinates: x_max = 4 (width + 1) + 3, y_max = height + 1 -> the far border
+        x_max, y_max = 4 * (width + 1) + 3, height + 1
+        for raw_x, raw_y in ((-5, 3), (2**31, 1), (7, -1), (4 * (width + 9), height + 40)):
+            ux4 = min(raw_x & 0xFFFFFFFF, x_max)
+            uy = min(raw_y & 0xFFFFFFFF, y_max)
+            idx = kernel_index(ux4, uy, kx)
+            assert idx in seen
+            assert ((raw_x & 0xFFFFFFFF) <= x_max) or idx == bordered_index(width + 1, uy, kx)
+
+
+def test_lop3_truth_table_is_a_bit_select():
+    """lop3.b32 d, a, b, c, 0xB8 with b = 3: the immLut is f(a, b, c) evaluated on the masks 0xF0, 0xCC, 0xAA."""
+    ta, tb, tc = 0xF0, 0xCC, 0xAA
+    assert ((ta & ~tb) | (tc & tb)) & 0xFF == 0xB8
