@@ -608,3 +608,86 @@ def test_uniform_distribution_some_free_slots(orc, mode):  # GridSomeFreeSlots :
         assert got[key] == pytest.approx(0.25, abs=0.01)
     yaw = np.arctan2(st[:, 1], st[:, 0])  # SO2d::sampleUniform: uniform over [-pi, pi)
     assert yaw.min() < -3.1 and yaw.max() > 3.1 and abs(yaw.mean()) < 0.02
+
+
+# ---- sensor/test_likelihood_field_prob_model.cpp:34-158 ----------------------------------------
+def test_lfm_prob_importance_weight(orc):  # ImportanceWeight :34-74
+    grid = grid5(orc, [(2, 2)])
+    assert lfm_weight(orc, grid, [(1.25, 1.25)], grid.origin, kind=1) == pytest.approx(1.022, abs=0.003)
+    assert lfm_weight(orc, grid, [(2.25, 2.25)], grid.origin, kind=1) == pytest.approx(0.025, abs=0.003)
+    assert lfm_weight(orc, grid, [(-50.0, 50.0)], grid.origin, kind=1) == pytest.approx(0.050, abs=0.003)
+    assert lfm_weight(orc, grid, [(1.20, 1.20), (1.25, 1.25), (1.30, 1.30)], grid.origin, kind=1) == pytest.approx(1.068, abs=0.01)
+    assert lfm_weight(orc, grid, [(0.0, 0.0)], orc.se2(1.25, 1.25, 0.0), kind=1) == pytest.approx(1.022, abs=0.003)
+
+
+def test_lfm_prob_grid_with_offset(orc):  # GridWithOffset :76-101
+    grid = grid5(orc, [(4, 4)], 2.0, orc.se2(-5, -5, 0.0))
+    assert lfm_weight(orc, grid, [(4.5, 4.5)], orc.IDENTITY, kind=1) == pytest.approx(1.022, abs=0.003)
+    assert lfm_weight(orc, grid, [(9.5, 9.5)], grid.origin, kind=1) == pytest.approx(1.022, abs=0.003)
+
+
+def test_lfm_prob_grid_with_rotation(orc):  # GridWithRotation :103-128
+    grid = grid5(orc, [(4, 4)], 2.0, orc.se2(0.0, 0.0, PI / 2))
+    assert lfm_weight(orc, grid, [(-9.5, 9.5)], orc.IDENTITY, kind=1) == pytest.approx(1.022, abs=0.003)
+    assert lfm_weight(orc, grid, [(9.5, 9.5)], grid.origin, kind=1) == pytest.approx(1.022, abs=0.003)
+
+
+def test_lfm_prob_grid_with_rotation_and_offset(orc):  # GridWithRotationAndOffset :130-158
+    rot = orc.se2(0.0, 0.0, PI / 2)
+    t = orc.se2_compose(rot, orc.se2(-5, -5, 0.0))
+    origin = np.array([rot[0], rot[1], t[2], t[3]])
+    grid = grid5(orc, [(4, 4)], 2.0, origin)
+    assert lfm_weight(orc, grid, [(-4.5, 4.5)], orc.IDENTITY, kind=1) == pytest.approx(1.022, abs=0.003)
+    assert lfm_weight(orc, grid, [(9.5, 9.5)], grid.origin, kind=1) == pytest.approx(1.022, abs=0.003)
+
+
+# ---- algorithm/test_amcl_core.cpp:73-186 (the filter's control flow: sizes, nullopt, forced updates) -----------------
+def core_filter(orc, sensor="beam", **kw):
+    """make_amcl(): 5 x 5 map at resolution 1 with the centre cell occupied, default diff-drive and beam models."""
+    o = orc.Amcl(orc.AmclParam(spatial_resolution_x=0.1, spatial_resolution_y=0.1, spatial_resolution_theta=0.1, seed=5, **kw),
+                 orc.MotionParam(0.1, 0.05, 0.1, 0.05))
+    grid = grid5(orc, [(2, 2)], 1.0)
+    if sensor == "beam":
+        o.set_map(orc.BEAM, orc.BeamParam(), grid)
+    else:
+        o.set_map(0, orc.LfmParam(), grid5(orc, [], 0.5))
+    return o
+
+
+DUMMY_POINTS = [(0.0, 0.0)] * 3
+
+
+def test_amcl_core_sizes_and_nullopt(orc):
+    o = core_filter(orc)
+    assert len(o.particles()[0]) == 0  # InitializeWithNoParticles
+    assert o.update(orc.IDENTITY, DUMMY_POINTS).updated == 0  # Update / UpdateWithNoParticles: nullopt
+    o.initialize_normal([0.0, 0.0, 0.0], np.eye(3))
+    assert len(o.particles()[0]) == orc.AmclParam().max_particles  # InitializeFromPose
+    assert o.update(orc.IDENTITY, DUMMY_POINTS).updated == 1  # UpdateWithParticles
+    assert o.update(orc.IDENTITY, DUMMY_POINTS).updated == 0  # UpdateWithParticlesNoMotion
+    o.force_update()
+    assert o.update(orc.IDENTITY, DUMMY_POINTS).updated == 1  # UpdateWithParticlesForced
+
+
+def test_amcl_core_selective_resampling_and_likelihood_field(orc):
+    o = core_filter(orc, selective_resampling=True)  # SelectiveResampleCanBeConstructed
+    o.initialize_normal([0.0, 0.0, 0.0], np.eye(3))
+    assert len(o.particles()[0]) == orc.AmclParam().max_particles
+    assert o.update(orc.IDENTITY, DUMMY_POINTS).updated == 1
+    o = core_filter(orc, sensor="lfm")  # ParticlesDependentRandomStateGenerator: an empty map, the likelihood field model
+    o.initialize_normal([0.0, 0.0, 0.0], np.eye(3))
+    assert o.update(orc.IDENTITY, DUMMY_POINTS).updated == 1
+
+
+def test_amcl_core_random_particles_inserting(orc):  # TestRandomParticlesInserting :174-186
+    o = core_filter(orc, min_particles=2, max_particles=100, alpha_slow=0.0, alpha_fast=100.0)
+    o.initialize_normal([1.0, 1.0, 0.0], np.eye(3))
+    sizes = []
+    for _ in range(30):
+        o.force_update()
+        r = o.update(orc.IDENTITY, DUMMY_POINTS)
+        assert r.updated == 1
+        sizes.append(int(r.n_particles))
+        assert 2 <= sizes[-1] <= 100
+        st, w = o.particles()
+        assert np.all(np.isfinite(st)) and np.all(np.isfinite(w))
