@@ -30,5 +30,24 @@ int main() {
     for (uint32_t py = 0; py < 9; ++py)
       for (uint32_t px = 0; px < (4u << kx); ++px) std::printf("index %d %u %u %u\n", kx, px, py, bordered_index(px, py, kx));
   std::printf("max_bins %u\n", kScheduleMaxBins);
+  // se2_math.cuh: the counter RNG (Philox4x32-10 keyed by seed, counter = index | step | stream) and the spatial hash
+  const uint32_t kat[3][6] = {{0u, 0u, 0u, 0u, 0u, 0u},
+                              {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu},
+                              {0x243f6a88u, 0x85a308d3u, 0x13198a2eu, 0x03707344u, 0xa4093822u, 0x299f31d0u}};
+  for (const auto& k : kat) {
+    const Draw d = counter_draw((static_cast<uint64_t>(k[5]) << 32) | k[4], (static_cast<uint64_t>(k[1]) << 32) | k[0], k[2], k[3]);
+    std::printf("philox %08x %08x %08x %08x\n", static_cast<uint32_t>(d.a), static_cast<uint32_t>(d.a >> 32), static_cast<uint32_t>(d.b),
+                static_cast<uint32_t>(d.b >> 32));
+  }
+  for (uint64_t i = 0; i < 64; ++i) {
+    const Draw d = counter_draw(0x9e3779b97f4a7c15ull, i * 0x100000001ull + 7, 3, kStreamRandomState);
+    double z0, z1;
+    box_muller(d, z0, z1);
+    const Pose2 st = pose_from_xytheta(40.0 * uniform01(d.a) - 20.0, 40.0 * uniform01(d.b) - 20.0, 3.0 * z0);
+    std::printf("hash %.17g %.17g %.17g %.17g %llu %llu %.17g %.17g %llu\n", st.c, st.s, st.x, st.y,
+                static_cast<unsigned long long>(spatial_hash(st, 0.5, 0.5, 0.17453292519943295)),
+                static_cast<unsigned long long>(spatial_hash(st, 0.05, 0.1, 0.01)), z0, z1,
+                static_cast<unsigned long long>(mulhi64(d.a, d.b)));
+  }
   return 0;
 }

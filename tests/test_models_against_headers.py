@@ -60,3 +60,23 @@ def test_bordered_index_matches_the_header(probe_lines):
     for kx, px, py, idx in rows:
         assert bordered_index(px, py, kx) == idx
         assert kernel_index(4 * px + 3, py, kx) == idx  # what the kernel's three integer operations make of the same cell
+
+
+def test_counter_rng_and_spatial_hash_of_the_product_header(probe_lines, orc):
+    """se2_math.cuh compiled for the host: Philox4x32-10 known answers (Random123's kat_vectors), and the spatial hash of 64
+    poses against the oracle's restatement of algorithm/spatial_hash.hpp:45-94,190-193."""
+    import numpy as np
+
+    philox = [line.split()[1:] for line in probe_lines if line.startswith("philox ")]
+    assert philox == [["6627e8d5", "e169c58d", "bc57ac4c", "9b00dbd8"], ["408f276d", "41c83b0e", "a20bc7c6", "6d5451fd"],
+                      ["d16cfe09", "94fdcceb", "5001e420", "24126ea1"]]
+    rows = [line.split()[1:] for line in probe_lines if line.startswith("hash ")]
+    assert len(rows) == 64
+    for r in rows:
+        state = np.array([float(v) for v in r[:4]])
+        assert orc.spatial_hash(state, 0.5, 0.5, 0.17453292519943295) == int(r[4])
+        assert orc.spatial_hash(state, 0.05, 0.1, 0.01) == int(r[5])
+        z0, z1 = float(r[6]), float(r[7])
+        assert np.isfinite(z0) and np.isfinite(z1) and abs(z0) < 9.0 and abs(z1) < 9.0
+    z = np.array([[float(r[6]), float(r[7])] for r in rows]).reshape(-1)
+    assert abs(z.mean()) < 0.35 and 0.7 < z.std() < 1.3  # 128 standard normals
