@@ -81,3 +81,46 @@ def test_sharded_scatter_covers_every_slot_once(world):
             assert j not in seen
             seen[j] = r * shard + i
     assert [seen[j] for j in range(m)] == [int(i) for i in whole]
+
+
+def comb_slots_before_magic(position, offset, stride, magic, total_slots):
+    """kernels.cu: comb_slots_before_magic -- the division replaced by __umul64hi with magic = floor((2^64 - 1) / stride) and one
+    remainder check.  64-bit wrap-around arithmetic is modelled with masks."""
+    mask = (1 << 64) - 1
+    if position <= offset:
+        return 0
+    x = (position - offset + stride - 1) & mask
+    j = (x * magic) >> 64
+    if ((x - j * stride) & mask) >= stride:
+        j += 1
+    return min(j, total_slots)
+
+
+def test_reciprocal_multiply_is_the_division():
+    """The high word of x * magic is floor(x / stride) or one below it for every x < 2^64; the remainder check settles which.
+    Totals stay below 2^62 (tests/test_quantize_model.py), so x = position - offset + stride - 1 cannot wrap."""
+    rng = np.random.default_rng(5)
+    mask = (1 << 64) - 1
+    strides = [1, 2, 3, 7, 1 << 20, (1 << 20) + 1, (1 << 40) - 1, 1 << 61, (1 << 62) - 1] + [int(s) for s in rng.integers(1, 1 << 62, 200)]
+    for stride in strides:
+        magic = mask // stride
+        xs = [0, 1, stride - 1, stride, stride + 1, 2 * stride - 1, 2 * stride, mask, mask - 1, (1 << 63) - 1, (1 << 63)]
+        xs += [int(k) * stride + d for k in rng.integers(0, max(1, mask // stride), 20) for d in (-1, 0, 1)]
+        xs += [int(v) for v in rng.integers(0, 1 << 63, 50)]
+        for x in xs:
+            if not (0 <= x <= mask):
+                continue
+            j = (x * magic) >> 64
+            q = x // stride
+            assert j in (q, q - 1), (x, stride)
+            if ((x - j * stride) & mask) >= stride:
+                j += 1
+            assert j == q
+    # and through the function, against the plain division, at CDF scale
+    for _ in range(2000):
+        total = int(rng.integers(1 << 30, 1 << 62))
+        m = int(rng.integers(1, 1 << 24))
+        stride = max(total // m, 1)
+        offset = int(rng.integers(0, stride))
+        position = int(rng.integers(0, total + 1))
+        assert comb_slots_before_magic(position, offset, stride, mask // stride, m) == comb_slots_before(position, offset, stride, m)
