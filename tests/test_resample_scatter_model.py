@@ -99,14 +99,16 @@ def comb_slots_before_magic(position, offset, stride, magic, total_slots):
 def test_reciprocal_multiply_is_the_division():
     """The high word of x * magic is floor(x / stride) or one below it for every x < 2^64; the remainder check settles which.
     Totals stay below 2^62 (tests/test_quantize_model.py), so x = position - offset + stride - 1 cannot wrap."""
-    rng = np.random.default_rng(5)
+    import random
+
+    rng = random.Random(5)
     mask = (1 << 64) - 1
-    strides = [1, 2, 3, 7, 1 << 20, (1 << 20) + 1, (1 << 40) - 1, 1 << 61, (1 << 62) - 1] + [int(s) for s in rng.integers(1, 1 << 62, 200)]
+    strides = [1, 2, 3, 7, 1 << 20, (1 << 20) + 1, (1 << 40) - 1, 1 << 61, (1 << 62) - 1] + [rng.randrange(1, 1 << 62) for _ in range(200)]
     for stride in strides:
         magic = mask // stride
         xs = [0, 1, stride - 1, stride, stride + 1, 2 * stride - 1, 2 * stride, mask, mask - 1, (1 << 63) - 1, (1 << 63)]
-        xs += [int(k) * stride + d for k in rng.integers(0, max(1, mask // stride), 20) for d in (-1, 0, 1)]
-        xs += [int(v) for v in rng.integers(0, 1 << 63, 50)]
+        xs += [rng.randrange(0, mask // stride + 1) * stride + d for _ in range(20) for d in (-1, 0, 1)]
+        xs += [rng.randrange(0, 1 << 64) for _ in range(50)]
         for x in xs:
             if not (0 <= x <= mask):
                 continue
@@ -118,9 +120,9 @@ def test_reciprocal_multiply_is_the_division():
             assert j == q
     # and through the function, against the plain division, at CDF scale
     for _ in range(2000):
-        total = int(rng.integers(1 << 30, 1 << 62))
-        m = int(rng.integers(1, 1 << 24))
+        total = rng.randrange(1 << 30, 1 << 62)
+        m = rng.randrange(1, 1 << 24)
         stride = max(total // m, 1)
-        offset = int(rng.integers(0, stride))
-        position = int(rng.integers(0, total + 1))
+        offset = rng.randrange(0, stride)
+        position = rng.randrange(0, total + 1)
         assert comb_slots_before_magic(position, offset, stride, mask // stride, m) == comb_slots_before(position, offset, stride, m)
