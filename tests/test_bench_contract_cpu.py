@@ -49,3 +49,23 @@ def test_native_arm_needs_a_gpu():
     assert out.returncode != 0
     assert "no CUDA device" in (out.stderr + out.stdout)
     assert not [line for line in out.stdout.splitlines() if line.startswith("{")]  # and no number is printed
+
+
+def test_smoke_and_the_public_api_fail_loudly_without_a_gpu():
+    """No silent fallback anywhere: smoke() raises, and creating a filter through the C ABI returns an error."""
+    import pytest
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+    import beluga_b200 as bb
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        entry.smoke()
+    assert bb.device_count() == 0
+    with pytest.raises(bb.BelugaB200Error):
+        bb.Filter(capacity=16, seed=1)
+    with pytest.raises(bb.BelugaB200Error):
+        bb.Amcl(bb.DifferentialDriveModelParam(0.1, 0.05, 0.1, 0.05), bb.AmclParams(min_particles=10, max_particles=10))
