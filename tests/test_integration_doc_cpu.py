@@ -49,3 +49,36 @@ def test_documented_symbols_exist_in_the_header():
     missing = sorted(n for n in names if not n.endswith("_") and not re.search(r"\b" + re.escape(n) + r"\b", header))
     wildcards = {n for n in missing if any(h.startswith(n) for h in re.findall(r"\bbb200_[a-z0-9_]+", header))}  # `bb200_filter_enqueue_*`
     assert not (set(missing) - wildcards), sorted(set(missing) - wildcards)
+
+
+def test_documents_point_at_files_that_exist():
+    """Paths quoted in the documents (`profiles/...`, `tests/...`, `tools/...`, `include/...`, `oracle/...`, `beluga_b200/...`)."""
+    docs = ["DESIGN.md", "README.md", "INTEGRATION.md", os.path.join("profiles", "README.md"), os.path.join("profiles", "scaling", "README.md"),
+            os.path.join("tools", "README.md")]
+    missing = []
+    for doc in docs:
+        text = open(os.path.join(ROOT, doc)).read()
+        base_dirs = {"profiles/README.md": "profiles", "profiles/scaling/README.md": os.path.join("profiles", "scaling"), "tools/README.md": "tools"}
+        for quoted in re.findall(r"`([^`\n]+)`", text):
+            for token in re.split(r"[\s,;()]+", quoted):
+                token = token.split("::")[0].rstrip(".:")
+                if not re.match(r"^(profiles|tests|tools|include|oracle|beluga_b200)/[A-Za-z0-9_./{}*<>-]+$", token):
+                    continue
+                if any(ch in token for ch in "*{}<>"):  # patterns such as `profiles/r02_lfm_*`
+                    continue
+                if token.endswith("/"):
+                    token = token[:-1]
+                if token in ("oracle/_ref", "oracle/_build"):  # build outputs (the reference itself cannot be compiled here: DESIGN.md)
+                    continue
+                if not os.path.exists(os.path.join(ROOT, token)):
+                    missing.append((doc, token))
+        # bare file names in the profiles tables (relative to the document's own directory)
+        rel = base_dirs.get(doc.replace(os.sep, "/"))
+        if rel:
+            for name in re.findall(r"`([A-Za-z0-9_./-]+\.(?:txt|json|csv|sh|py))`", text):
+                if "/" in name and not name.startswith("scaling/"):
+                    continue
+                if not (os.path.exists(os.path.join(ROOT, rel, name)) or os.path.exists(os.path.join(ROOT, name))
+                        or os.path.exists(os.path.join(ROOT, "profiles", name)) or os.path.exists(os.path.join(ROOT, "tools", name))):
+                    missing.append((doc, name))
+    assert not missing, missing
