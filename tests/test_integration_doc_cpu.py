@@ -82,3 +82,24 @@ def test_documents_point_at_files_that_exist():
                         or os.path.exists(os.path.join(ROOT, "profiles", name)) or os.path.exists(os.path.join(ROOT, "tools", name))):
                     missing.append((doc, name))
     assert not missing, missing
+
+
+def test_headline_numbers_in_the_documents_are_the_committed_bench_line():
+    """DESIGN.md and README.md quote the N = 1 bench line; the figures must be the ones in profiles/r02_bench_n1_final.json."""
+    import json
+
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_n1_final.json")).read())
+    ms, value, e2e = d["ms_per_step"], d["value"], d["e2e"]["value"]
+    reweight, frac = d["kernels_ms"]["reweight_lfm"], d["roofline"]["frac"]
+    assert d["n_gpus"] == 1 and d["config"]["particles"] == 1_000_000 and d["steps"] >= 20 and d["warmup"] >= 3
+    assert abs(ms * value - 1e3) < 1e-6 and 0.0 < frac < 1.0 and reweight < ms
+    assert abs(d["roofline"]["achieved"] / d["roofline"]["peak"] - frac) < 1e-9
+    assert d["clocks"]["reasons"] == [] and d["gpu_launches"] == 7 * d["steps"]
+    design = open(os.path.join(ROOT, "DESIGN.md")).read()
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    for text in (design, readme):
+        assert f"{ms:.3f} ms" in text
+        assert f"{value:.0f} steps/s" in text
+        assert f"{e2e:.0f}" in text
+        assert f"{reweight:.3f} ms" in text
+    assert f"{frac:.3f}" in design and f"{frac:.2f}" in readme
